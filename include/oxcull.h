@@ -1,0 +1,335 @@
+/*
+ * oxcull.h — C ABI of liboxcull.so: the B200-native meshlet visibility pipeline.
+ *
+ * Drop-in boundary for the ONE hot path of oxylusengine/Oxylus that SURVEY.md §8 scopes:
+ *   RendererInstance::cull_geometry      Oxylus/src/Render/Passes/CullGeometry.cpp:61-404
+ *   RendererInstance::generate_hiz       Oxylus/src/Render/Passes/CullGeometry.cpp:10-59
+ *   RendererInstance::draw_for_visbuffer Oxylus/src/Render/Passes/DrawGeometry.cpp:104-190
+ * The reference has no FFI for this path: the seam is the *buffer set and call sequence* those three
+ * member functions record into the vuk render graph.  Every entry point below names the reference
+ * pass it replaces (file:line).  Plain pointers and sizes only; no torch / vuk / glm types.
+ *
+ * Conventions (identical to the reference):
+ *   - reverse-Z (near = 1, far = 0; depth cleared to 0, depth test GreaterOrEqual)
+ *   - matrices are column-major in memory (glm): m[col*4 + row]; Slang M[i] = row i
+ *   - scalar buffer layout; struct sizes are static_assert'ed below against SceneGPU.hpp
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*); no hidden syncs
+ *   - one context per device; a context is not thread-safe (the reference records on one thread)
+ *   - return 0 on success, negative OXC_E_* otherwise; oxc_last_error() gives text
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails loudly.
+ */
+#ifndef OXCULL_H_
+#define OXCULL_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__cplusplus)
+#define OXC_STATIC_ASSERT(c, m) static_assert(c, m)
+#else
+#define OXC_STATIC_ASSERT(c, m) _Static_assert(c, m)
+#endif
+
+/* ------------------------------------------------------------------------------------------------
+ * GPU data ABI — host mirrors of Oxylus/include/Scene/SceneGPU.hpp (scalar layout)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* SceneGPU.hpp:20-22 TransformWorld — glm::mat4, column-major */
+typedef struct OxcTransformWorld { float world[16]; } OxcTransformWorld;
+
+/* SceneGPU.hpp:84-90 / scene.slang:401-435 MeshletBounds (16 B): half3 center, s8 cone xy,
+ * half3 extent (FULL size, halved by the tests), s8 cone z, s8 cutoff */
+typedef struct OxcMeshletBounds {
+  uint16_t aabb_center[3];
+  int8_t cone_axis_xy[2];
+  uint16_t aabb_extent[3];
+  int8_t cone_axis_z;
+  int8_t cone_cutoff;
+} OxcMeshletBounds;
+
+/* SceneGPU.hpp:92-95 MeshBounds */
+typedef struct OxcMeshBounds { float aabb_center[3]; float aabb_extent[3]; } OxcMeshBounds;
+
+/* SceneGPU.hpp:97-104 MeshletInstanceVisibility */
+typedef struct OxcMeshletInstanceVisibility {
+  uint32_t total_visible_meshlet_instances; /* written by cull_meshes only */
+  uint32_t early_visible_meshlet_instances;
+  uint32_t late_visible_meshlet_instances;
+} OxcMeshletInstanceVisibility;
+
+/* SceneGPU.hpp:106-109 */
+typedef struct OxcMeshletInstance { uint32_t mesh_instance_index; uint32_t meshlet_index; } OxcMeshletInstance;
+
+/* SceneGPU.hpp:111-117 (20 B) */
+typedef struct OxcMeshInstance {
+  uint32_t mesh_index;
+  uint32_t lod_index;
+  uint32_t material_index;
+  uint32_t transform_index;
+  uint32_t meshlet_instance_visibility_offset;
+} OxcMeshInstance;
+
+/* SceneGPU.hpp:119-124 (16 B) */
+typedef struct OxcMeshlet {
+  uint32_t indirect_vertex_index_offset;
+  uint32_t local_triangle_index_offset;
+  uint32_t vertex_count;
+  uint32_t triangle_count;
+} OxcMeshlet;
+
+/* SceneGPU.hpp:126-140 (64 B).  The u64 members are device addresses on the GPU (reference ABI);
+ * in an OxcSceneDesc passed to oxc_set_scene they are BYTE OFFSETS into OxcSceneDesc::blob and are
+ * rebased on upload, exactly like upload_gltf_mesh patches blob offsets into device addresses
+ * (Oxylus/src/Asset/AssetManager_GLTF.cpp:778-800). */
+typedef struct OxcMeshLOD {
+  uint64_t indices;
+  uint64_t meshlets;                /* OxcMeshlet[meshlet_count] */
+  uint64_t meshlet_bounds;          /* OxcMeshletBounds[meshlet_bounds_count] */
+  uint64_t local_triangle_indices;  /* u8 micro indices packed in u32 words */
+  uint64_t indirect_vertex_indices; /* u32 */
+  uint32_t indices_count;
+  uint32_t meshlet_count;
+  uint32_t meshlet_bounds_count;
+  uint32_t local_triangle_indices_count;
+  uint32_t indirect_vertex_indices_count;
+  float error;
+} OxcMeshLOD;
+
+/* SceneGPU.hpp:142-152 (64 B) */
+typedef struct OxcMesh {
+  uint64_t vertex_positions; /* u16x4 per vertex (half3 + pad) */
+  uint64_t vertex_normals;
+  uint64_t texture_coords;
+  uint32_t vertex_count;
+  uint32_t lod_count;
+  uint64_t lods; /* OxcMeshLOD[lod_count] */
+  OxcMeshBounds bounds;
+} OxcMesh;
+
+/* SceneGPU.hpp:222-229 (96 B) */
+typedef struct OxcCullCamera {
+  float projection_view[16];
+  float position[3];
+  float acceptable_lod_error;
+  float resolution[2];
+  float near_clip;
+  uint32_t mesh_instance_count;
+} OxcCullCamera;
+
+/* Shaders/gpu/base.slang:5-17 */
+typedef struct OxcDispatchIndirectCommand { uint32_t x, y, z; } OxcDispatchIndirectCommand;
+typedef struct OxcDrawIndexedIndirectCommand {
+  uint32_t index_count;
+  uint32_t instance_count;
+  uint32_t first_index;
+  int32_t vertex_offset;
+  uint32_t first_instance;
+} OxcDrawIndexedIndirectCommand;
+
+OXC_STATIC_ASSERT(sizeof(OxcTransformWorld) == 64, "TransformWorld");
+OXC_STATIC_ASSERT(sizeof(OxcMeshletBounds) == 16, "MeshletBounds");
+OXC_STATIC_ASSERT(sizeof(OxcMeshBounds) == 24, "MeshBounds");
+OXC_STATIC_ASSERT(sizeof(OxcMeshletInstanceVisibility) == 12, "MeshletInstanceVisibility");
+OXC_STATIC_ASSERT(sizeof(OxcMeshletInstance) == 8, "MeshletInstance");
+OXC_STATIC_ASSERT(sizeof(OxcMeshInstance) == 20, "MeshInstance");
+OXC_STATIC_ASSERT(sizeof(OxcMeshlet) == 16, "Meshlet");
+OXC_STATIC_ASSERT(sizeof(OxcMeshLOD) == 64, "MeshLOD");
+OXC_STATIC_ASSERT(sizeof(OxcMesh) == 64, "Mesh");
+OXC_STATIC_ASSERT(sizeof(OxcCullCamera) == 96, "CullCamera");
+OXC_STATIC_ASSERT(sizeof(OxcDispatchIndirectCommand) == 12, "DispatchIndirectCommand");
+OXC_STATIC_ASSERT(sizeof(OxcDrawIndexedIndirectCommand) == 20, "DrawIndexedIndirectCommand");
+
+/* SceneGPU.hpp:345-353 CullFlag */
+enum {
+  OXC_CULL_NONE = 0,
+  OXC_CULL_TEST_FRUSTUM = 1 << 0,
+  OXC_CULL_SELECT_LOD = 1 << 1,
+  OXC_CULL_TEST_OCCLUSION = 1 << 2,
+  OXC_CULL_LATE_PASS = 1 << 3,
+  OXC_CULL_TEST_ALL = (1 << 0) | (1 << 1) | (1 << 2)
+};
+
+/* defines.slang:1-23 */
+#define OXC_MESH_MAX_LODS 8
+#define OXC_MESHLET_MAX_PRIMITIVES 64
+#define OXC_MESHLET_MAX_VERTICES 64
+/* RendererInstance.cpp:573-588: Hi-Z has min(mips, 13) levels */
+#define OXC_HIZ_MAX_LEVELS 13
+/* visbuffer.slang:9-14 */
+#define OXC_VIS_PRIMITIVE_BITS 8u
+#define OXC_VIS_PRIMITIVE_MASK 0xFFu
+#define OXC_VIS_CLEAR 0xFFFFFFFFu
+/* oxc_cull_meshlets_multiview: upper bound on batched views */
+#define OXC_MAX_VIEWS 16
+
+/* error codes */
+enum {
+  OXC_OK = 0,
+  OXC_E_INVALID = -1,  /* bad argument */
+  OXC_E_CUDA = -2,     /* CUDA runtime error (text in oxc_last_error) */
+  OXC_E_NO_DEVICE = -3,/* no CUDA device: there is no CPU fallback */
+  OXC_E_CAPACITY = -4, /* a create-time capacity would be exceeded */
+  OXC_E_STATE = -5     /* call sequence violated (e.g. cull before set_scene) */
+};
+
+/* ------------------------------------------------------------------------------------------------
+ * Context
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OxcContext OxcContext;
+
+typedef struct OxcCreateInfo {
+  uint32_t max_mesh_instances;    /* capacity of mesh_instances[] */
+  uint32_t max_meshlet_instances; /* == RendererInstanceUpdateInfo::max_meshlet_instance_count (Σ LOD0 meshlets),
+                                     sizes meshlet_instances (8 B), visible indices (4 B), mask bits;
+                                     RendererInstance.cpp:1651-1665,1717-1732 */
+  uint32_t hiz_width;             /* bit_ceil((W+1)>>1), RendererInstance.cpp:573-577; power of two */
+  uint32_t hiz_height;
+  uint32_t alloc_reordered_indices; /* 1: allocate the 768 B x max index buffer for oxc_cull_triangles
+                                       (RendererInstance.cpp:1727-1731); 0: fused raster only */
+  uint32_t max_views;             /* 0/1, or up to OXC_MAX_VIEWS for oxc_cull_meshlets_multiview */
+} OxcCreateInfo;
+
+/* Host-side scene tables (what Scene::runtime_update hands to RendererInstance::update,
+ * Oxylus/src/Scene/Scene.cpp:1226-1290).  Mesh/MeshLOD u64 members are byte offsets into blob. */
+typedef struct OxcSceneDesc {
+  const OxcMesh* meshes;
+  uint32_t mesh_count;
+  const OxcMeshInstance* mesh_instances;
+  uint32_t mesh_instance_count;
+  const OxcTransformWorld* transforms;
+  uint32_t transform_count;
+  const uint8_t* blob;   /* vertex / meshlet / bounds / index data of every mesh; 16-byte aligned offsets */
+  uint64_t blob_size;
+} OxcSceneDesc;
+
+/* Device pointers of everything the reference keeps in prepared_frame / CullGeometryContext.
+ * Valid until oxc_destroy; contents are ordered by the stream the producing call was enqueued on. */
+typedef struct OxcOutputs {
+  OxcMeshletInstanceVisibility* visibility;        /* CullGeometry.cpp:97 */
+  OxcDispatchIndirectCommand* cull_meshlets_cmd;   /* CullGeometry.cpp:98-100 */
+  OxcDispatchIndirectCommand* cull_triangles_cmd;  /* CullGeometry.cpp:125-127 (reset by every oxc_cull_meshlets) */
+  OxcDrawIndexedIndirectCommand* draw_cmd;         /* CullGeometry.cpp:380-382 */
+  OxcMeshletInstance* meshlet_instances;           /* RendererInstance.cpp:1717-1721 */
+  uint32_t* visible_meshlet_instances_indices;     /* RendererInstance.cpp:1722-1726 */
+  uint32_t* meshlet_instance_visibility_mask;      /* RendererInstance.cpp:1651-1665 */
+  uint32_t* reordered_indices;                     /* RendererInstance.cpp:1727-1731 (NULL if not allocated) */
+  OxcMeshInstance* mesh_instances;                 /* lod_index is written back by cull_meshes */
+  float* hiz;                                      /* all mips, level l at hiz + hiz_level_offset[l] floats */
+  uint32_t hiz_level_offset[OXC_HIZ_MAX_LEVELS];
+  uint32_t hiz_levels;
+  uint32_t hiz_width, hiz_height;
+  uint32_t visibility_mask_words;
+  uint32_t* view_visibility_bits;                  /* multiview: one u32 per meshlet instance, bit v = view v (NULL if max_views<=1) */
+  uint32_t* view_visible_counts;                   /* multiview: u32[OXC_MAX_VIEWS] */
+  uint64_t* raster_triangle_count;                 /* triangles that survived cull and were rasterised, cumulative per clear */
+} OxcOutputs;
+
+const char* oxc_last_error(void);
+/* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
+uint64_t oxc_kernel_launch_count(void);
+const char* oxc_version(void);
+
+int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx);
+void oxc_destroy(OxcContext* ctx);
+
+/* RendererInstance::update (RendererInstance.cpp:1333-1788): uploads meshes / mesh_instances /
+ * transforms / geometry blob from HOST memory (async on stream; pinned memory recommended),
+ * rebases blob offsets to device addresses, (re)sizes and zero-fills the visibility mask
+ * (instance table changed => zero_fill_pass, :1651-1665). */
+int oxc_set_scene(OxcContext* ctx, const OxcSceneDesc* scene, void* stream);
+/* dirty-range transform upload (RendererInstance.cpp:16-109,1590-1599), HOST source */
+int oxc_update_transforms(OxcContext* ctx, const OxcTransformWorld* transforms, uint32_t first, uint32_t count, void* stream);
+/* zero_fill_pass on the persistent mask (RendererInstance.cpp:1582-1588,1663) */
+int oxc_reset_visibility_mask(OxcContext* ctx, void* stream);
+/* vuk::clear_image(hiz, DepthZero) once per frame (RendererInstance.cpp:579-588) */
+int oxc_clear_hiz(OxcContext* ctx, void* stream);
+
+/* Multi-GPU sharding (no reference equivalent): restrict this context to mesh instances
+ * [first, first+count) — cull_meshes only expands those, so meshlet_instances / survivors are this
+ * rank's shard.  id_base_dev (device u32, may be NULL = 0) is added to every meshlet-instance index
+ * this context emits (survivor list, vis-buffer IDs) so IDs are global across ranks. */
+int oxc_set_shard(OxcContext* ctx, uint32_t first_mesh_instance, uint32_t mesh_instance_count, const uint32_t* id_base_dev);
+
+/* cull_meshes.slang:17-85 via CullGeometry.cpp:68-117 (init_cull_meshes == true).
+ * Resets visibility{0,0,0} and cull_meshlets_cmd{0,1,1} (scratch_buffer init, :97-100), then per
+ * mesh instance: frustum test, LOD select, expansion into meshlet_instances (deterministic order:
+ * ascending mesh instance, ascending meshlet), lod_index write-back. */
+int oxc_cull_meshes(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, void* stream);
+
+/* cull_meshlets_hiz.slang:19-88 (use_hiz != 0; CullGeometry.cpp:129-198) or
+ * cull_meshlets.slang:21-73 (use_hiz == 0; CullGeometry.cpp:274-335).
+ * Resets cull_triangles_cmd{0,1,1} first (CullGeometry.cpp:125-127).  Late pass = cull_flags has
+ * OXC_CULL_LATE_PASS; survivors are appended after the early ones (:70-76). */
+int oxc_cull_meshlets(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, int use_hiz, void* stream);
+
+/* hiz.slang:171-267 via generate_hiz (CullGeometry.cpp:10-59): depth_dev is a device D32F image,
+ * row-major width x height floats.  Fills every mip of the context's pyramid. */
+int oxc_build_hiz(OxcContext* ctx, const float* depth_dev, uint32_t width, uint32_t height, void* stream);
+
+/* cull_triangles.slang:27-90 via CullGeometry.cpp:337-403: resets draw_cmd{0,1,0,0,0}, then one
+ * block per surviving meshlet of this pass (early: [0,E); late: [E,E+L)).  Requires
+ * alloc_reordered_indices. */
+int oxc_cull_triangles(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, void* stream);
+
+/* visbuffer_clear.slang:20-28 on the packed 64-bit image (visbuffer.slang:49-79):
+ * every pixel = depth 0.0 | data ~0u. */
+int oxc_clear_visbuffer(OxcContext* ctx, uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream);
+
+/* Software replacement of cull_triangles + visbuffer_encode (visbuffer_encode.slang:24-74,
+ * visbuffer_encode_ms.slang:110-171; DrawGeometry.cpp:104-190): per surviving meshlet of this pass,
+ * per-triangle near/backface cull then rasterisation with atomicMax on asuint(depth)<<32 | data
+ * (reverse-Z GreaterOrEqual == max; visbuffer.slang:72-74 packing).  small_primitive_cull != 0
+ * additionally drops triangles whose pixel bbox covers no sample centre (not in the reference). */
+int oxc_raster_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width,
+                         uint32_t height, uint64_t* vis_dev, int small_primitive_cull, void* stream);
+
+/* Splits the packed image into the reference's two attachments: R32UI vis (data, ~0u = empty) and
+ * D32F depth.  Either output may be NULL. */
+int oxc_resolve_visbuffer(OxcContext* ctx, const uint64_t* vis_dev, uint32_t width, uint32_t height,
+                          uint32_t* vis32_dev, float* depth_dev, void* stream);
+
+/* Multi-view batched cull (the reference's analogue is cull_meshlets_hpb.slang:27-99, which loops
+ * <=10 shadow clipmaps per meshlet; CullGeometry.cpp:199-273).  Reads every meshlet's bounds ONCE and
+ * tests it against n_views cameras: per view  cone (directional when view_dirs != NULL,
+ * cull.slang:177-179, else positional :173-175) AND frustum (:57-84).  Output: bit v of
+ * view_visibility_bits[i] and view_visible_counts[v]. */
+int oxc_cull_meshlets_multiview(OxcContext* ctx, const OxcCullCamera* views, uint32_t n_views, int directional,
+                                void* stream);
+
+int oxc_get_outputs(OxcContext* ctx, OxcOutputs* out);
+
+/* ------------------------------------------------------------------------------------------------
+ * oxr_* — host-side mirror of the reference's frame sequencing (C++ class ox::RendererInstance in
+ * oxylus_b200/csrc/host/renderer_instance.hpp) exported for non-C++ callers.  One call runs
+ *   run_geometry_pass(false) -> generate_hiz -> run_geometry_pass(true)
+ * (RendererInstance.cpp:842-884) with HOST inputs and HOST outputs.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OxrRenderer OxrRenderer;
+
+typedef struct OxrFrameResult {
+  OxcMeshletInstanceVisibility visibility; /* total / early / late */
+  uint32_t draw_index_count_early;         /* draw_cmd.index_count of the early pass */
+  uint32_t draw_index_count_late;
+  uint64_t raster_triangles;               /* triangles rasterised this frame */
+} OxrFrameResult;
+
+int oxr_create(int device, const OxcCreateInfo* info, uint32_t width, uint32_t height, OxrRenderer** out);
+void oxr_destroy(OxrRenderer* r);
+OxcContext* oxr_context(OxrRenderer* r);
+/* RendererInstance::update */
+int oxr_update(OxrRenderer* r, const OxcSceneDesc* scene);
+/* RendererInstance::render geometry section.  occluder_depth_host (may be NULL) is a width x height
+ * D32F image merged into the frame depth before the early pass (stands in for depth written by
+ * passes outside this path, e.g. terrain).  Outputs may be NULL.  Synchronous. */
+int oxr_render(OxrRenderer* r, const OxcCullCamera* camera, const float* occluder_depth_host,
+               uint32_t* vis32_host, float* depth_host, uint32_t* visible_indices_host,
+               uint32_t visible_indices_capacity, OxrFrameResult* result);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OXCULL_H_ */

@@ -1,0 +1,902 @@
+/*
+ * oxc_oracle.c — CPU ORACLE (test infrastructure; see oxc_oracle.h for the rules and the
+ * "parity unpinned" statement).  Plain C11, compiled with
+ *   gcc -O2 -std=c11 -ffp-contract=off -fno-fast-math -fPIC -shared
+ * Every function cites the reference lines it restates (paths relative to
+ * /root/reference/Oxylus/src/Render/Shaders unless noted).
+ */
+#define _GNU_SOURCE
+#include "oxc_oracle.h"
+
+#include <math.h>
+#include <pthread.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------------------------------------
+ * scalar helpers
+ * ---------------------------------------------------------------------------------------------- */
+static inline uint32_t f2bits(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+static inline float bits2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+
+/* saturating, truncating conversions (PTX cvt.rzi.{u32,s32}.f32; NaN -> 0) */
+static inline uint32_t to_u32_f32(float x) {
+  if (!(x > 0.0f)) return 0u;
+  if (x >= 4294967296.0f) return 0xFFFFFFFFu;
+  return (uint32_t)x;
+}
+static inline int32_t to_i32_f32(float x) {
+  if (x != x) return 0;
+  if (x <= -2147483648.0f) return INT32_MIN;
+  if (x >= 2147483648.0f) return INT32_MAX;
+  return (int32_t)x;
+}
+static inline uint32_t to_u32_f64(double x) {
+  if (!(x > 0.0)) return 0u;
+  if (x >= 4294967296.0) return 0xFFFFFFFFu;
+  return (uint32_t)x;
+}
+static inline int32_t to_i32_f64(double x) {
+  if (x != x) return 0;
+  if (x <= -2147483648.0) return INT32_MIN;
+  if (x >= 2147483648.0) return INT32_MAX;
+  return (int32_t)x;
+}
+static inline float rsqrt__f32(float x) { return sqrtf(x); } /* "real sqrt" */
+static inline double rsqrt__f64(double x) { return sqrt(x); }
+static inline float rfloor_f32(float x) { return floorf(x); }
+static inline double rfloor_f64(double x) { return floor(x); }
+/* asfloat(asuint(v) ^ (asuint(n) & 0x80000000)) — cull.slang:76-77 */
+static inline float xor_sign_f32(float v, float n) { return bits2f(f2bits(v) ^ (f2bits(n) & 0x80000000u)); }
+static inline double xor_sign_f64(double v, double n) { return signbit(n) ? -v : v; }
+
+uint32_t orc_ceil_log2_u32(uint32_t n) {
+  if (n <= 1u) return 0u; /* log2(0) = -inf -> clamp 0; log2(1) = 0 */
+  return 32u - (uint32_t)__builtin_clz(n - 1u);
+}
+
+#define REAL float
+#define SUF(x) x##_f32
+#include "oxc_oracle_math.inc"
+#undef REAL
+#undef SUF
+
+#define REAL double
+#define SUF(x) x##_f64
+#include "oxc_oracle_math.inc"
+#undef REAL
+#undef SUF
+
+/* ------------------------------------------------------------------------------------------------
+ * common/math.slang:193-201 dequantize_half
+ * ---------------------------------------------------------------------------------------------- */
+float orc_dequantize_half(uint16_t h) {
+  uint32_t s = (uint32_t)(h & 0x8000) << 16;
+  int32_t em = h & 0x7fff;
+  int32_t r = (int32_t)((uint32_t)(em + (112 << 10)) << 13);
+  r = (em < (1 << 10)) ? 0 : r;                /* denormals flush to zero */
+  r += (em >= (31 << 10)) ? (112 << 23) : 0;   /* inf / nan exponent fix-up */
+  return bits2f(s | (uint32_t)r);
+}
+
+/* scene.slang:401-435 */
+void orc_bounds_decode(const OxcMeshletBounds* b, float center[3], float extent[3], float cone_axis[3],
+                       float* cone_cutoff) {
+  for (int i = 0; i < 3; i++) {
+    center[i] = orc_dequantize_half(b->aabb_center[i]);
+    extent[i] = orc_dequantize_half(b->aabb_extent[i]);
+  }
+  cone_axis[0] = (float)(int32_t)b->cone_axis_xy[0] / 127.0f;
+  cone_axis[1] = (float)(int32_t)b->cone_axis_xy[1] / 127.0f;
+  cone_axis[2] = (float)(int32_t)b->cone_axis_z / 127.0f;
+  *cone_cutoff = (float)b->cone_cutoff / 127.0f;
+}
+
+void orc_mat4_mul(const float a[16], const float b[16], float out[16]) { mul_mm_f32(a, b, out); }
+
+int orc_project_aabb(const float mvp[16], float near_clip, const float c[3], const float e[3], OrcScreenAabb* out) {
+  Vec3_f32 cc = {c[0], c[1], c[2]}, ee = {e[0], e[1], e[2]};
+  ScreenAabb_f32 sa;
+  if (!project_aabb_f32(mvp, near_clip, cc, ee, &sa)) return 0;
+  memcpy(out->min, sa.min, sizeof sa.min);
+  memcpy(out->max, sa.max, sizeof sa.max);
+  return 1;
+}
+
+int orc_test_frustum(const float mvp[16], const float c[3], const float e[3]) {
+  Vec3_f32 cc = {c[0], c[1], c[2]}, ee = {e[0], e[1], e[2]};
+  return test_frustum_f32(mvp, cc, ee);
+}
+
+int orc_test_occlusion(const OrcScreenAabb* aabb, const OrcHiz* hiz) {
+  ScreenAabb_f32 sa;
+  memcpy(sa.min, aabb->min, sizeof sa.min);
+  memcpy(sa.max, aabb->max, sizeof sa.max);
+  return test_occlusion_f32(&sa, hiz);
+}
+
+int orc_test_cone(const float center[3], float radius, const float axis[3], float cutoff, const float cam[3]) {
+  Vec3_f32 c = {center[0], center[1], center[2]}, a = {axis[0], axis[1], axis[2]}, p = {cam[0], cam[1], cam[2]};
+  return test_cone_f32(c, radius, a, cutoff, p);
+}
+
+/* cull.slang:177-179 */
+int orc_test_cone_directional(const float axis[3], float cutoff, const float view_dir[3]) {
+  Vec3_f32 a = {axis[0], axis[1], axis[2]}, v = {view_dir[0], view_dir[1], view_dir[2]};
+  return dot3_f32(a, v) >= cutoff;
+}
+
+/* cull.slang:169-171: determinant(f32x3x3(c0.xyw, c1.xyw, c2.xyw)) >= 0.0001 */
+static inline float det3_f32(const float m[3][3]) {
+  return (m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0])) +
+         m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+}
+int orc_test_triangle_backface(const float clip[3][4]) {
+  float m[3][3];
+  for (int i = 0; i < 3; i++) { m[i][0] = clip[i][0]; m[i][1] = clip[i][1]; m[i][2] = clip[i][3]; }
+  return det3_f32(m) >= 0.0001f;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Hi-Z layout — Oxylus/include/Asset/Texture.hpp:144-146 (calculate_mip_count) and
+ * RendererInstance.cpp:583-586 (min(., 13))
+ * ---------------------------------------------------------------------------------------------- */
+uint32_t orc_hiz_level_count(uint32_t w, uint32_t h) {
+  uint32_t m = w > h ? w : h;
+  uint32_t levels = 0;
+  while (m) { levels++; m >>= 1; } /* floor(log2(m)) + 1 */
+  return levels < OXC_HIZ_MAX_LEVELS ? levels : OXC_HIZ_MAX_LEVELS;
+}
+void orc_hiz_layout(uint32_t w, uint32_t h, OrcHiz* hiz) {
+  hiz->width = w;
+  hiz->height = h;
+  hiz->levels = orc_hiz_level_count(w, h);
+  uint32_t off = 0;
+  for (uint32_t l = 0; l < OXC_HIZ_MAX_LEVELS; l++) {
+    hiz->level_offset[l] = off;
+    if (l < hiz->levels) {
+      uint32_t mw = w >> l, mh = h >> l;
+      if (mw < 1) mw = 1;
+      if (mh < 1) mh = 1;
+      off += mw * mh;
+    }
+  }
+}
+uint32_t orc_hiz_total_texels(uint32_t w, uint32_t h) {
+  OrcHiz t;
+  orc_hiz_layout(w, h, &t);
+  uint32_t l = t.levels - 1;
+  uint32_t mw = w >> l, mh = h >> l;
+  if (mw < 1) mw = 1;
+  if (mh < 1) mh = 1;
+  return t.level_offset[l] + mw * mh;
+}
+
+/* passes/hiz.slang:92-95 load(): uv = (texel + 1) / hiz_extent sampled with NearestSamplerClamped from a
+ * depth image of a different size  =>  source texel = min(W-1, floor((x+1) * W / hizW)); exact in
+ * integers because hiz extents are powers of two.  mip k: hiz.slang:77-83,137-166. */
+void orc_build_hiz(const float* depth, uint32_t width, uint32_t height, OrcHiz* hiz) {
+  const uint32_t hw = hiz->width, hh = hiz->height;
+  float* m0 = hiz->data + hiz->level_offset[0];
+  for (uint32_t y = 0; y < hh; y++) {
+    uint64_t sy = ((uint64_t)(y + 1) * height) / hh;
+    if (sy > height - 1) sy = height - 1;
+    for (uint32_t x = 0; x < hw; x++) {
+      uint64_t sx = ((uint64_t)(x + 1) * width) / hw;
+      if (sx > width - 1) sx = width - 1;
+      m0[(size_t)y * hw + x] = depth[(size_t)sy * width + sx]; /* transform_z is identity, CullGeometry.cpp:44 */
+    }
+  }
+  for (uint32_t l = 1; l < hiz->levels; l++) {
+    uint32_t pw = hw >> (l - 1), ph = hh >> (l - 1);
+    if (pw < 1) pw = 1;
+    if (ph < 1) ph = 1;
+    uint32_t mw = hw >> l, mh = hh >> l;
+    if (mw < 1) mw = 1;
+    if (mh < 1) mh = 1;
+    const float* src = hiz->data + hiz->level_offset[l - 1];
+    float* dst = hiz->data + hiz->level_offset[l];
+    for (uint32_t y = 0; y < mh; y++)
+      for (uint32_t x = 0; x < mw; x++) {
+        uint32_t x0 = 2 * x, x1 = 2 * x + 1, y0 = 2 * y, y1 = 2 * y + 1;
+        if (x1 > pw - 1) x1 = pw - 1; /* only reachable for non-square pyramids */
+        if (y1 > ph - 1) y1 = ph - 1;
+        if (x0 > pw - 1) x0 = pw - 1;
+        if (y0 > ph - 1) y0 = ph - 1;
+        float a = src[(size_t)y0 * pw + x0], b = src[(size_t)y0 * pw + x1];
+        float c = src[(size_t)y1 * pw + x0], d = src[(size_t)y1 * pw + x1];
+        float ab = a < b ? a : b, cd = c < d ? c : d; /* reduce(): hiz.slang:77-83 */
+        dst[(size_t)y * mw + x] = ab < cd ? ab : cd;
+      }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * scene access (blob offsets instead of device addresses)
+ * ---------------------------------------------------------------------------------------------- */
+static inline const OxcMeshLOD* mesh_lod(const OrcScene* s, const OxcMesh* m, uint32_t lod) {
+  return (const OxcMeshLOD*)(s->blob + m->lods) + lod;
+}
+static inline const OxcMeshletBounds* lod_bounds(const OrcScene* s, const OxcMeshLOD* l) {
+  return (const OxcMeshletBounds*)(s->blob + l->meshlet_bounds);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * passes/cull_meshes.slang:17-85
+ * ---------------------------------------------------------------------------------------------- */
+void orc_cull_meshes(const OrcScene* scene, const OxcCullCamera* cam, uint32_t flags, uint32_t first, uint32_t count,
+                     OxcMeshletInstance* meshlet_instances, OxcMeshletInstanceVisibility* vis,
+                     OxcDispatchIndirectCommand* cull_meshlets_cmd) {
+  /* scratch_buffer init: CullGeometry.cpp:97-100 */
+  vis->total_visible_meshlet_instances = 0;
+  vis->early_visible_meshlet_instances = 0;
+  vis->late_visible_meshlet_instances = 0;
+  cull_meshlets_cmd->x = 0; cull_meshlets_cmd->y = 1; cull_meshlets_cmd->z = 1;
+
+  OxcMeshInstance* mesh_instances = (OxcMeshInstance*)scene->mesh_instances; /* RWStructuredBuffer :13 */
+  uint32_t n = cam->mesh_instance_count;                                      /* :28 */
+  uint32_t lo = first, hi = n;
+  if (count != 0xFFFFFFFFu && first + count < hi) hi = first + count;
+  for (uint32_t mi = lo; mi < hi; mi++) {
+    uint32_t meshlet_count = 0, lod_index = 0;
+    const OxcMeshInstance inst = mesh_instances[mi];
+    const OxcMesh* mesh = &scene->meshes[inst.mesh_index];
+    const float* world = scene->transforms[inst.transform_index].world;
+    float mvp[16];
+    mul_mm_f32(cam->projection_view, world, mvp); /* :32 */
+    Vec3_f32 bc = {mesh->bounds.aabb_center[0], mesh->bounds.aabb_center[1], mesh->bounds.aabb_center[2]};
+    Vec3_f32 be = {mesh->bounds.aabb_extent[0], mesh->bounds.aabb_extent[1], mesh->bounds.aabb_extent[2]};
+    if ((flags & OXC_CULL_TEST_FRUSTUM) && test_frustum_f32(mvp, bc, be)) { /* :34 */
+      if (flags & OXC_CULL_SELECT_LOD) {                                     /* :35-57 */
+        Vec4_f32 c4 = {bc.x, bc.y, bc.z, 1.0f}, e4 = {be.x, be.y, be.z, 0.0f};
+        Vec4_f32 wc = mul_mv_f32(world, c4), we = mul_mv_f32(world, e4);
+        Vec3_f32 aabb_extent = {fabsf(we.x), fabsf(we.y), fabsf(we.z)};
+        float rough_extent = rmax_f32(aabb_extent.x, rmax_f32(aabb_extent.y, aabb_extent.z));
+        Vec3_f32 d = {wc.x - cam->position[0], wc.y - cam->position[1], wc.z - cam->position[2]};
+        float rough_dist = rmax_f32(length3_f32(d) - 0.5f * rough_extent, 0.0f);
+        const float fov90_distance_to_screen_ratio = 2.0f;
+        float pixel_size_at_1m = fov90_distance_to_screen_ratio / rmax_f32(cam->resolution[0], cam->resolution[1]);
+        float aabb_size_at_1m = rough_extent / rough_dist;
+        float rough_aabb_pixel_size = aabb_size_at_1m / pixel_size_at_1m;
+        for (uint32_t i = 1; i < mesh->lod_count; i++) {
+          float rough_pixel_error = rough_aabb_pixel_size * mesh_lod(scene, mesh, i)->error;
+          if (rough_pixel_error < cam->acceptable_lod_error) lod_index = i;
+          else break;
+        }
+      }
+      meshlet_count = mesh_lod(scene, mesh, lod_index)->meshlet_count; /* :59 */
+    }
+    /* :63-84 — serial order == wave order */
+    uint32_t base = vis->total_visible_meshlet_instances;
+    vis->total_visible_meshlet_instances += meshlet_count;
+    uint32_t needed = (vis->total_visible_meshlet_instances + 64u - 1u) / 64u; /* CULLING_MESHLET_COUNT */
+    if (needed > cull_meshlets_cmd->x) cull_meshlets_cmd->x = needed;
+    if (meshlet_count > 0) {
+      mesh_instances[mi].lod_index = lod_index; /* :76 */
+      for (uint32_t i = 0; i < meshlet_count; i++) {
+        meshlet_instances[base + i].mesh_instance_index = mi;
+        meshlet_instances[base + i].meshlet_index = i;
+      }
+    }
+  }
+}
+
+/* gather everything one meshlet-instance needs (cull_meshlets_hiz.slang:30-40) */
+typedef struct MeshletCtx {
+  const float* world;
+  OxcMeshInstance inst;
+  Vec3_f32 c, e, axis;
+  float cutoff;
+} MeshletCtx;
+
+static inline void fetch_meshlet(const OrcScene* s, OxcMeshletInstance mi, MeshletCtx* o) {
+  o->inst = s->mesh_instances[mi.mesh_instance_index];
+  o->world = s->transforms[o->inst.transform_index].world;
+  const OxcMesh* mesh = &s->meshes[o->inst.mesh_index];
+  const OxcMeshLOD* lod = mesh_lod(s, mesh, o->inst.lod_index);
+  const OxcMeshletBounds* b = lod_bounds(s, lod) + mi.meshlet_index;
+  float c[3], e[3], a[3];
+  orc_bounds_decode(b, c, e, a, &o->cutoff);
+  o->c = (Vec3_f32){c[0], c[1], c[2]};
+  o->e = (Vec3_f32){e[0], e[1], e[2]};
+  o->axis = (Vec3_f32){a[0], a[1], a[2]};
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * passes/cull_meshlets_hiz.slang:19-88
+ * ---------------------------------------------------------------------------------------------- */
+void orc_cull_meshlets_hiz(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, const OxcCullCamera* cam,
+                           uint32_t flags, const OrcHiz* hiz, OxcMeshletInstanceVisibility* vis,
+                           uint32_t* visible_indices, uint32_t* mask, OxcDispatchIndirectCommand* cull_triangles_cmd) {
+  cull_triangles_cmd->x = 0; cull_triangles_cmd->y = 1; cull_triangles_cmd->z = 1; /* CullGeometry.cpp:125-127 */
+  const Vec3_f32 campos = {cam->position[0], cam->position[1], cam->position[2]};
+  const uint32_t total = vis->total_visible_meshlet_instances;
+  for (uint32_t i = 0; i < total; i++) { /* :25-28 */
+    MeshletCtx m;
+    fetch_meshlet(scene, meshlet_instances[i], &m);
+    uint32_t mask_index = 0, bit = 0;
+    int was_visible = 1;
+    if (flags & OXC_CULL_TEST_OCCLUSION) { /* :45-51 */
+      uint32_t vi = m.inst.meshlet_instance_visibility_offset + meshlet_instances[i].meshlet_index;
+      mask_index = vi / 32;
+      bit = 1u << (vi - mask_index * 32);
+      was_visible = (mask[mask_index] & bit) != 0;
+    }
+    int visible = meshlet_visible_hiz_f32(cam->projection_view, m.world, cam->near_clip, campos, m.c, m.e, m.axis,
+                                          m.cutoff, flags, was_visible, hiz);
+    if (visible && (!(flags & OXC_CULL_LATE_PASS) || !was_visible)) { /* :67-79 */
+      uint32_t index;
+      if (!(flags & OXC_CULL_LATE_PASS)) index = vis->early_visible_meshlet_instances++;
+      else index = (vis->late_visible_meshlet_instances++) + vis->early_visible_meshlet_instances;
+      visible_indices[index] = i;
+      cull_triangles_cmd->x++;
+    }
+    if (flags & (OXC_CULL_TEST_OCCLUSION | OXC_CULL_LATE_PASS)) { /* :81-87 */
+      if (visible) mask[mask_index] |= bit;
+      else mask[mask_index] &= ~bit;
+    }
+  }
+}
+
+static void meshlet_flags_generic(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                                  const OxcCullCamera* cam, uint32_t flags, const OrcHiz* hiz,
+                                  const OxcMeshletInstanceVisibility* vis, const uint32_t* mask_in, uint8_t* out,
+                                  int use_f64) {
+  const uint32_t total = vis->total_visible_meshlet_instances;
+  for (uint32_t i = 0; i < total; i++) {
+    MeshletCtx m;
+    fetch_meshlet(scene, meshlet_instances[i], &m);
+    int was_visible = 1;
+    if (flags & OXC_CULL_TEST_OCCLUSION) {
+      uint32_t vi = m.inst.meshlet_instance_visibility_offset + meshlet_instances[i].meshlet_index;
+      was_visible = (mask_in[vi / 32] >> (vi & 31)) & 1;
+    }
+    if (use_f64) {
+      double pv[16], w[16];
+      for (int k = 0; k < 16; k++) { pv[k] = cam->projection_view[k]; w[k] = m.world[k]; }
+      Vec3_f64 campos = {cam->position[0], cam->position[1], cam->position[2]};
+      Vec3_f64 c = {m.c.x, m.c.y, m.c.z}, e = {m.e.x, m.e.y, m.e.z};
+      /* cone axis / cutoff re-derived in f64 from the s8 values would differ from the f32 decode only in the
+       * division rounding; keep the f32-decoded inputs so only the predicate arithmetic is re-evaluated */
+      Vec3_f64 ax = {m.axis.x, m.axis.y, m.axis.z};
+      out[i] = (uint8_t)meshlet_visible_hiz_f64(pv, w, (double)cam->near_clip, campos, c, e, ax, (double)m.cutoff,
+                                                flags, was_visible, hiz);
+    } else {
+      Vec3_f32 campos = {cam->position[0], cam->position[1], cam->position[2]};
+      out[i] = (uint8_t)meshlet_visible_hiz_f32(cam->projection_view, m.world, cam->near_clip, campos, m.c, m.e, m.axis,
+                                                m.cutoff, flags, was_visible, hiz);
+    }
+  }
+}
+
+void orc_cull_meshlets_hiz_f64(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                               const OxcCullCamera* cam, uint32_t flags, const OrcHiz* hiz,
+                               const OxcMeshletInstanceVisibility* vis, const uint32_t* mask_in, uint8_t* out_visible) {
+  meshlet_flags_generic(scene, meshlet_instances, cam, flags, hiz, vis, mask_in, out_visible, 1);
+}
+void orc_cull_meshlets_hiz_f32_flags(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                                     const OxcCullCamera* cam, uint32_t flags, const OrcHiz* hiz,
+                                     const OxcMeshletInstanceVisibility* vis, const uint32_t* mask_in,
+                                     uint8_t* out_visible) {
+  meshlet_flags_generic(scene, meshlet_instances, cam, flags, hiz, vis, mask_in, out_visible, 0);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * passes/cull_meshlets.slang:21-73
+ * ---------------------------------------------------------------------------------------------- */
+void orc_cull_meshlets(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, const OxcCullCamera* cam,
+                       OxcMeshletInstanceVisibility* vis, uint32_t* visible_indices,
+                       OxcDispatchIndirectCommand* cull_triangles_cmd) {
+  cull_triangles_cmd->x = 0; cull_triangles_cmd->y = 1; cull_triangles_cmd->z = 1;
+  const Vec3_f32 campos = {cam->position[0], cam->position[1], cam->position[2]};
+  const uint32_t total = vis->total_visible_meshlet_instances;
+  for (uint32_t i = 0; i < total; i++) {
+    MeshletCtx m;
+    fetch_meshlet(scene, meshlet_instances[i], &m);
+    float mvp[16];
+    mul_mm_f32(cam->projection_view, m.world, mvp);                                     /* :40 */
+    int cone_vis = cone_visible_f32(m.world, m.c, m.e, m.axis, m.cutoff, campos);      /* :49-52 */
+    if (cone_vis && test_frustum_f32(mvp, m.c, m.e))                                    /* :54 */
+      visible_indices[cull_triangles_cmd->x++] = i;                                     /* :55-70 */
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * multi-view batched cull: per view the cone + frustum part of cull_meshlets_hpb.slang:39-60
+ * (directional: test_cone_directional with view_dir = camera.position, :54) or of
+ * cull_meshlets.slang:49-54 (positional)
+ * ---------------------------------------------------------------------------------------------- */
+void orc_cull_meshlets_multiview(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, uint32_t total,
+                                 const OxcCullCamera* views, uint32_t n_views, int directional, uint32_t* view_bits,
+                                 uint32_t* view_counts) {
+  for (uint32_t v = 0; v < OXC_MAX_VIEWS; v++) view_counts[v] = 0;
+  for (uint32_t i = 0; i < total; i++) {
+    MeshletCtx m;
+    fetch_meshlet(scene, meshlet_instances[i], &m);
+    uint32_t bits = 0;
+    for (uint32_t v = 0; v < n_views; v++) {
+      const OxcCullCamera* cam = &views[v];
+      const Vec3_f32 campos = {cam->position[0], cam->position[1], cam->position[2]};
+      int cone_vis;
+      if (directional) {
+        if (m.cutoff >= 1.0f) cone_vis = 1;
+        else {
+          Vec3_f32 axis = world_cone_axis_f32(m.world, m.axis);
+          cone_vis = !(dot3_f32(axis, campos) >= m.cutoff);
+        }
+      } else {
+        cone_vis = cone_visible_f32(m.world, m.c, m.e, m.axis, m.cutoff, campos);
+      }
+      if (!cone_vis) continue;
+      float mvp[16];
+      mul_mm_f32(cam->projection_view, m.world, mvp);
+      if (test_frustum_f32(mvp, m.c, m.e)) { bits |= 1u << v; view_counts[v]++; }
+    }
+    view_bits[i] = bits;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * triangles: scene.slang:336-382 (Meshlet::indices / positions), :478-484 (decode_position),
+ * passes/cull_triangles.slang:27-90
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct TriMeshlet {
+  const OxcMesh* mesh;
+  const OxcMeshLOD* lod;
+  OxcMeshlet meshlet;
+  float mvp[16];
+} TriMeshlet;
+
+static void fetch_tri_meshlet(const OrcScene* s, const OxcMeshletInstance* mis, uint32_t meshlet_instance_index,
+                              const OxcCullCamera* cam, TriMeshlet* t) {
+  OxcMeshletInstance mi = mis[meshlet_instance_index];               /* :45 */
+  OxcMeshInstance inst = s->mesh_instances[mi.mesh_instance_index];  /* :46 */
+  t->mesh = &s->meshes[inst.mesh_index];                             /* :47 */
+  t->lod = mesh_lod(s, t->mesh, inst.lod_index);                     /* :48 */
+  t->meshlet = ((const OxcMeshlet*)(s->blob + t->lod->meshlets))[mi.meshlet_index]; /* :49 */
+  mul_mm_f32(cam->projection_view, s->transforms[inst.transform_index].world, t->mvp); /* :51-52 */
+}
+
+/* scene.slang:336-342 get_micro_index */
+static inline uint32_t micro_index(const uint32_t* buf, uint32_t byte_offset) {
+  uint32_t pack = buf[byte_offset >> 2];
+  return (pack >> ((byte_offset & 3) * 8)) & 0xFF;
+}
+
+/* clip positions of triangle `tri` (cull_triangles.slang:60-66); returns vertex clip coords */
+static void tri_clip(const OrcScene* s, const TriMeshlet* t, uint32_t tri, float clip[3][4]) {
+  const uint32_t* micro = (const uint32_t*)(s->blob + t->lod->local_triangle_indices);
+  const uint32_t* vidx = (const uint32_t*)(s->blob + t->lod->indirect_vertex_indices);
+  const uint16_t* pos = (const uint16_t*)(s->blob + t->mesh->vertex_positions);
+  uint32_t base = t->meshlet.local_triangle_index_offset + tri * 3; /* scene.slang:366 */
+  for (int c = 0; c < 3; c++) {
+    uint32_t local = micro_index(micro, base + (uint32_t)c);
+    uint32_t v = vidx[t->meshlet.indirect_vertex_index_offset + local];
+    Vec4_f32 p = {orc_dequantize_half(pos[v * 4 + 0]), orc_dequantize_half(pos[v * 4 + 1]),
+                  orc_dequantize_half(pos[v * 4 + 2]), 1.0f};
+    Vec4_f32 cp = mul_mv_f32(t->mvp, p);
+    clip[c][0] = cp.x; clip[c][1] = cp.y; clip[c][2] = cp.z; clip[c][3] = cp.w;
+  }
+}
+
+static inline int tri_passes(const float clip[3][4]) {
+  int passed = clip[0][2] >= 0.0f && clip[1][2] >= 0.0f && clip[2][2] >= 0.0f; /* :68 */
+  return passed && !orc_test_triangle_backface(clip);                            /* :69 */
+}
+
+void orc_cull_triangles(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                        const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
+                        const OxcCullCamera* cam, uint32_t id_base, uint32_t* reordered_indices,
+                        OxcDrawIndexedIndirectCommand* draw_cmd) {
+  /* CullGeometry.cpp:380-382 */
+  draw_cmd->index_count = 0; draw_cmd->instance_count = 1; draw_cmd->first_index = 0;
+  draw_cmd->vertex_offset = 0; draw_cmd->first_instance = 0;
+  for (uint32_t g = 0; g < pass_count; g++) { /* one workgroup per surviving meshlet, :34-37 */
+    uint32_t mii = visible_indices[pass_first + g];
+    TriMeshlet t;
+    fetch_tri_meshlet(scene, meshlet_instances, mii, cam, &t);
+    for (uint32_t tri = 0; tri < t.meshlet.triangle_count && tri < 64; tri++) { /* :59 */
+      float clip[3][4];
+      tri_clip(scene, &t, tri, clip);
+      if (!tri_passes(clip)) continue;
+      uint32_t off = draw_cmd->index_count; /* :78,84 */
+      uint32_t masked = (mii + id_base) << OXC_VIS_PRIMITIVE_BITS; /* :85 */
+      uint32_t ti = tri * 3;
+      reordered_indices[off + 0] = masked | ((ti + 0) & OXC_VIS_PRIMITIVE_MASK);
+      reordered_indices[off + 1] = masked | ((ti + 1) & OXC_VIS_PRIMITIVE_MASK);
+      reordered_indices[off + 2] = masked | ((ti + 2) & OXC_VIS_PRIMITIVE_MASK);
+      draw_cmd->index_count += 3;
+    }
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * SW raster — SURVEY §8a row R.  No reference implementation exists (the reference uses the HW
+ * rasteriser, DrawGeometry.cpp:104-190); this is the SPECIFICATION the CUDA raster follows:
+ *   1. clip = mvp * (pos,1) per vertex (visbuffer_encode_ms.slang:135-137); triangle kept iff
+ *      cull_triangles' test passes (near z>=0 on all three, det(xyw) < 1e-4).
+ *   2. triangles with any w <= 0 are dropped (no homogeneous clipping; documented limitation).
+ *   3. rw = 1/w; ndc = xyz*rw; screen = (ndc.xy*0.5+0.5)*(W,H); fixed point fx = (int)floor(s*256+0.5),
+ *      dropped if any |fx| > 2^22.
+ *   4. area2 (int64, orient2d) must be < 0 (front face == negative clip-space determinant, the sign
+ *      cull.slang:169-171 keeps); vertices 1,2 are swapped so the edge functions are >= 0 inside.
+ *   5. sample at pixel centres (px*256+128); edge tie-break: a pixel exactly on edge a->b is inside
+ *      iff (dy > 0) || (dy == 0 && dx < 0)  (watertight, no double hits).
+ *   6. depth z = (z0 + l1*(z1-z0)) + l2*(z2-z0), l_i = (float)E_i / (float)area2; fragments with
+ *      z outside [0,1] are clipped (near/far).  value = asuint(z)<<32 | (id<<8 | tri); max wins
+ *      (reverse-Z GreaterOrEqual; equal depth -> larger id, deterministic).
+ * ---------------------------------------------------------------------------------------------- */
+void orc_clear_visbuffer(uint64_t* vis, uint32_t width, uint32_t height) {
+  for (size_t i = 0; i < (size_t)width * height; i++) vis[i] = (uint64_t)OXC_VIS_CLEAR; /* depth 0 | ~0u */
+}
+
+static inline int64_t orient2d(int64_t ax, int64_t ay, int64_t bx, int64_t by, int64_t cx, int64_t cy) {
+  return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+}
+static inline int edge_bias(int64_t ax, int64_t ay, int64_t bx, int64_t by) {
+  int64_t dx = bx - ax, dy = by - ay;
+  return ((dy > 0) || (dy == 0 && dx < 0)) ? 0 : -1;
+}
+
+static void raster_triangle(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis) {
+  if (!(clip[0][3] > 0.0f && clip[1][3] > 0.0f && clip[2][3] > 0.0f)) return; /* step 2 */
+  int64_t fx[3], fy[3];
+  float z[3];
+  for (int i = 0; i < 3; i++) {
+    float rw = 1.0f / clip[i][3];
+    float nx = clip[i][0] * rw, ny = clip[i][1] * rw;
+    z[i] = clip[i][2] * rw;
+    float sx = (nx * 0.5f + 0.5f) * (float)W, sy = (ny * 0.5f + 0.5f) * (float)H;
+    float qx = floorf(sx * 256.0f + 0.5f), qy = floorf(sy * 256.0f + 0.5f);
+    if (!(fabsf(qx) <= 4194304.0f && fabsf(qy) <= 4194304.0f)) return; /* step 3 (also rejects NaN) */
+    fx[i] = (int64_t)qx;
+    fy[i] = (int64_t)qy;
+  }
+  int64_t area2 = orient2d(fx[0], fy[0], fx[1], fy[1], fx[2], fy[2]);
+  if (area2 >= 0) return; /* step 4 */
+  /* swap 1 <-> 2 so that orientation is positive */
+  int64_t ax = fx[0], ay = fy[0], bx = fx[2], by = fy[2], cx = fx[1], cy = fy[1];
+  float za = z[0], zb = z[2], zc = z[1];
+  area2 = -area2;
+  int64_t minx = ax < bx ? (ax < cx ? ax : cx) : (bx < cx ? bx : cx);
+  int64_t maxx = ax > bx ? (ax > cx ? ax : cx) : (bx > cx ? bx : cx);
+  int64_t miny = ay < by ? (ay < cy ? ay : cy) : (by < cy ? by : cy);
+  int64_t maxy = ay > by ? (ay > cy ? ay : cy) : (by > cy ? by : cy);
+  int64_t px0 = (minx - 128 + 255) >> 8, px1 = (maxx - 128) >> 8;
+  int64_t py0 = (miny - 128 + 255) >> 8, py1 = (maxy - 128) >> 8;
+  if (px0 < 0) px0 = 0;
+  if (py0 < 0) py0 = 0;
+  if (px1 > (int64_t)W - 1) px1 = (int64_t)W - 1;
+  if (py1 > (int64_t)H - 1) py1 = (int64_t)H - 1;
+  const int b0 = edge_bias(bx, by, cx, cy), b1 = edge_bias(cx, cy, ax, ay), b2 = edge_bias(ax, ay, bx, by);
+  const float fa = (float)area2;
+  for (int64_t py = py0; py <= py1; py++)
+    for (int64_t px = px0; px <= px1; px++) {
+      int64_t sxp = px * 256 + 128, syp = py * 256 + 128;
+      int64_t e0 = orient2d(bx, by, cx, cy, sxp, syp); /* weight of a */
+      int64_t e1 = orient2d(cx, cy, ax, ay, sxp, syp); /* weight of b */
+      int64_t e2 = orient2d(ax, ay, bx, by, sxp, syp); /* weight of c */
+      if ((e0 + b0) < 0 || (e1 + b1) < 0 || (e2 + b2) < 0) continue;
+      float l1 = (float)e1 / fa, l2 = (float)e2 / fa;
+      float zz = (za + l1 * (zb - za)) + l2 * (zc - za);
+      if (!(zz >= 0.0f && zz <= 1.0f)) continue;
+      uint64_t v = ((uint64_t)f2bits(zz) << 32) | (uint64_t)data;
+      uint64_t* p = &vis[(size_t)py * W + (size_t)px];
+      if (v > *p) *p = v;
+    }
+}
+
+void orc_raster_visbuffer(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                          const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
+                          const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,
+                          uint64_t* triangles_rasterised) {
+  uint64_t ntri = 0;
+  for (uint32_t g = 0; g < pass_count; g++) {
+    uint32_t mii = visible_indices[pass_first + g];
+    TriMeshlet t;
+    fetch_tri_meshlet(scene, meshlet_instances, mii, cam, &t);
+    for (uint32_t tri = 0; tri < t.meshlet.triangle_count && tri < 64; tri++) {
+      float clip[3][4];
+      tri_clip(scene, &t, tri, clip);
+      if (!tri_passes(clip)) continue;
+      ntri++;
+      uint32_t data = ((mii + id_base) << OXC_VIS_PRIMITIVE_BITS) | (tri & OXC_VIS_PRIMITIVE_MASK);
+      raster_triangle(clip, data, width, height, vis);
+    }
+  }
+  if (triangles_rasterised) *triangles_rasterised += ntri;
+}
+
+void orc_resolve_visbuffer(const uint64_t* vis, uint32_t width, uint32_t height, uint32_t* vis32, float* depth) {
+  for (size_t i = 0; i < (size_t)width * height; i++) {
+    if (vis32) vis32[i] = (uint32_t)(vis[i] & 0xFFFFFFFFu); /* visbuffer.slang:67-70 */
+    if (depth) depth[i] = bits2f((uint32_t)(vis[i] >> 32));
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * CPU baseline
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct BaselineJob {
+  const OrcScene* scene;
+  const OxcMeshletInstance* mis;
+  const OxcCullCamera* cam;
+  uint32_t lo, hi;
+  int mode;
+  uint32_t* out; /* chunk-local draw list, written at out[lo..] */
+  uint64_t n_out;
+  float planes[6][4]; /* mode 0 */
+} BaselineJob;
+
+/* Oxylus/include/Utils/OxMath.hpp:54-80 calc_frustum_planes (glm m[col][row]); plane.w negated */
+static void calc_frustum_planes(const float m[16], float planes[6][4]) {
+#define M(c, r) m[(c) * 4 + (r)]
+  for (int i = 0; i < 4; i++) planes[0][i] = M(i, 3) + M(i, 0);
+  for (int i = 0; i < 4; i++) planes[1][i] = M(i, 3) - M(i, 0);
+  for (int i = 0; i < 4; i++) planes[2][i] = M(i, 3) + M(i, 1);
+  for (int i = 0; i < 4; i++) planes[3][i] = M(i, 3) - M(i, 1);
+  for (int i = 0; i < 4; i++) planes[4][i] = M(i, 3) + M(i, 2);
+  for (int i = 0; i < 4; i++) planes[5][i] = M(i, 3) - M(i, 2);
+#undef M
+  for (int p = 0; p < 6; p++) {
+    float len = sqrtf((planes[p][0] * planes[p][0] + planes[p][1] * planes[p][1]) + planes[p][2] * planes[p][2]);
+    for (int i = 0; i < 4; i++) planes[p][i] /= len;
+    planes[p][3] = -planes[p][3];
+  }
+}
+
+static void* baseline_worker(void* arg) {
+  BaselineJob* j = (BaselineJob*)arg;
+  const Vec3_f32 campos = {j->cam->position[0], j->cam->position[1], j->cam->position[2]};
+  uint64_t n = 0;
+  for (uint32_t i = j->lo; i < j->hi; i++) {
+    MeshletCtx m;
+    fetch_meshlet(j->scene, j->mis[i], &m);
+    int vis;
+    if (j->mode == 0) {
+      /* world-space AABB of the meshlet box (8 corners through `world`), then
+       * AABB::is_on_frustum / is_on_or_forward_plane — Oxylus/src/Render/BoundingVolume.cpp:72-88 */
+      float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+      for (int k = 0; k < 8; k++) {
+        Vec4_f32 p = {m.c.x + ((k & 1) ? 0.5f : -0.5f) * m.e.x, m.c.y + ((k & 2) ? 0.5f : -0.5f) * m.e.y,
+                      m.c.z + ((k & 4) ? 0.5f : -0.5f) * m.e.z, 1.0f};
+        Vec4_f32 w = mul_mv_f32(m.world, p);
+        mn[0] = fminf(mn[0], w.x); mn[1] = fminf(mn[1], w.y); mn[2] = fminf(mn[2], w.z);
+        mx[0] = fmaxf(mx[0], w.x); mx[1] = fmaxf(mx[1], w.y); mx[2] = fmaxf(mx[2], w.z);
+      }
+      float cx = (mx[0] + mn[0]) * 0.5f, cy = (mx[1] + mn[1]) * 0.5f, cz = (mx[2] + mn[2]) * 0.5f;
+      float ex = (mx[0] - mn[0]) * 0.5f, ey = (mx[1] - mn[1]) * 0.5f, ez = (mx[2] - mn[2]) * 0.5f;
+      vis = 1;
+      for (int p = 0; p < 6 && vis; p++) {
+        const float* pl = j->planes[p];
+        float r = ex * fabsf(pl[0]) + ey * fabsf(pl[1]) + ez * fabsf(pl[2]);
+        float dist = (pl[0] * cx + pl[1] * cy + pl[2] * cz) - pl[3]; /* Plane::get_distance */
+        vis = -r <= dist;
+      }
+    } else {
+      float mvp[16];
+      mul_mm_f32(j->cam->projection_view, m.world, mvp);
+      vis = cone_visible_f32(m.world, m.c, m.e, m.axis, m.cutoff, campos) && test_frustum_f32(mvp, m.c, m.e);
+    }
+    if (vis) j->out[j->lo + n++] = i;
+  }
+  j->n_out = n;
+  return NULL;
+}
+
+uint64_t orc_cpu_baseline_cull(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, uint32_t total,
+                               const OxcCullCamera* cam, int mode, int n_threads, uint32_t* out_indices) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  BaselineJob jobs[256];
+  pthread_t th[256];
+  float pv[16];
+  memcpy(pv, cam->projection_view, sizeof pv);
+  for (int t = 0; t < n_threads; t++) {
+    BaselineJob* j = &jobs[t];
+    j->scene = scene; j->mis = meshlet_instances; j->cam = cam; j->mode = mode; j->out = out_indices; j->n_out = 0;
+    j->lo = (uint32_t)(((uint64_t)total * (uint64_t)t) / (uint64_t)n_threads);
+    j->hi = (uint32_t)(((uint64_t)total * (uint64_t)(t + 1)) / (uint64_t)n_threads);
+    calc_frustum_planes(pv, j->planes);
+  }
+  if (n_threads == 1) baseline_worker(&jobs[0]);
+  else {
+    for (int t = 0; t < n_threads; t++) pthread_create(&th[t], NULL, baseline_worker, &jobs[t]);
+    for (int t = 0; t < n_threads; t++) pthread_join(th[t], NULL);
+  }
+  /* compact the per-chunk draw lists (the std::vector append of the reference-shaped loop) */
+  uint64_t n = jobs[0].n_out;
+  for (int t = 1; t < n_threads; t++) {
+    memmove(out_indices + n, out_indices + jobs[t].lo, jobs[t].n_out * sizeof(uint32_t));
+    n += jobs[t].n_out;
+  }
+  return n;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Threaded two-pass frame (bench.py --impl reference): same decisions as the serial passes above;
+ * the meshlet culls and the raster are chunked over n_threads (per-thread vis buffers are avoided by
+ * a CAS max on the shared image).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct FrameJob {
+  const OrcScene* scene;
+  const OxcMeshletInstance* mis;
+  const OxcCullCamera* cam;
+  const OrcHiz* hiz;
+  uint32_t flags, lo, hi;
+  uint32_t* mask;       /* read: mask_in snapshot; written bits go to set/clr lists */
+  uint32_t* out;        /* survivors at out[lo..] */
+  uint8_t* new_visible; /* per meshlet instance */
+  uint64_t n_out;
+  /* raster part */
+  const uint32_t* visible;
+  uint32_t width, height;
+  uint64_t* vis;
+  uint64_t ntri;
+} FrameJob;
+
+static void* frame_cull_worker(void* arg) {
+  FrameJob* j = (FrameJob*)arg;
+  const Vec3_f32 campos = {j->cam->position[0], j->cam->position[1], j->cam->position[2]};
+  uint64_t n = 0;
+  for (uint32_t i = j->lo; i < j->hi; i++) {
+    MeshletCtx m;
+    fetch_meshlet(j->scene, j->mis[i], &m);
+    int was_visible = 1;
+    if (j->flags & OXC_CULL_TEST_OCCLUSION) {
+      uint32_t vi = m.inst.meshlet_instance_visibility_offset + j->mis[i].meshlet_index;
+      was_visible = (j->mask[vi / 32] >> (vi & 31)) & 1;
+    }
+    int visible = meshlet_visible_hiz_f32(j->cam->projection_view, m.world, j->cam->near_clip, campos, m.c, m.e, m.axis,
+                                          m.cutoff, j->flags, was_visible, j->hiz);
+    j->new_visible[i] = (uint8_t)visible;
+    if (visible && (!(j->flags & OXC_CULL_LATE_PASS) || !was_visible)) j->out[j->lo + n++] = i;
+  }
+  j->n_out = n;
+  return NULL;
+}
+
+static void raster_triangle_atomic(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis);
+
+static void* frame_raster_worker(void* arg) {
+  FrameJob* j = (FrameJob*)arg;
+  uint64_t ntri = 0;
+  for (uint32_t g = j->lo; g < j->hi; g++) {
+    uint32_t mii = j->visible[g];
+    TriMeshlet t;
+    fetch_tri_meshlet(j->scene, j->mis, mii, j->cam, &t);
+    for (uint32_t tri = 0; tri < t.meshlet.triangle_count && tri < 64; tri++) {
+      float clip[3][4];
+      tri_clip(j->scene, &t, tri, clip);
+      if (!tri_passes(clip)) continue;
+      ntri++;
+      raster_triangle_atomic(clip, (mii << OXC_VIS_PRIMITIVE_BITS) | (tri & OXC_VIS_PRIMITIVE_MASK), j->width, j->height,
+                             j->vis);
+    }
+  }
+  j->ntri = ntri;
+  return NULL;
+}
+
+/* same as raster_triangle but with an atomic max so threads can share the image */
+static void raster_triangle_atomic(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis) {
+  /* rasterise into a tiny private list is overkill: reuse raster_triangle's maths through a CAS loop */
+  if (!(clip[0][3] > 0.0f && clip[1][3] > 0.0f && clip[2][3] > 0.0f)) return;
+  int64_t fx[3], fy[3];
+  float z[3];
+  for (int i = 0; i < 3; i++) {
+    float rw = 1.0f / clip[i][3];
+    float nx = clip[i][0] * rw, ny = clip[i][1] * rw;
+    z[i] = clip[i][2] * rw;
+    float sx = (nx * 0.5f + 0.5f) * (float)W, sy = (ny * 0.5f + 0.5f) * (float)H;
+    float qx = floorf(sx * 256.0f + 0.5f), qy = floorf(sy * 256.0f + 0.5f);
+    if (!(fabsf(qx) <= 4194304.0f && fabsf(qy) <= 4194304.0f)) return;
+    fx[i] = (int64_t)qx;
+    fy[i] = (int64_t)qy;
+  }
+  int64_t area2 = orient2d(fx[0], fy[0], fx[1], fy[1], fx[2], fy[2]);
+  if (area2 >= 0) return;
+  int64_t ax = fx[0], ay = fy[0], bx = fx[2], by = fy[2], cx = fx[1], cy = fy[1];
+  float za = z[0], zb = z[2], zc = z[1];
+  area2 = -area2;
+  int64_t minx = ax < bx ? (ax < cx ? ax : cx) : (bx < cx ? bx : cx);
+  int64_t maxx = ax > bx ? (ax > cx ? ax : cx) : (bx > cx ? bx : cx);
+  int64_t miny = ay < by ? (ay < cy ? ay : cy) : (by < cy ? by : cy);
+  int64_t maxy = ay > by ? (ay > cy ? ay : cy) : (by > cy ? by : cy);
+  int64_t px0 = (minx - 128 + 255) >> 8, px1 = (maxx - 128) >> 8;
+  int64_t py0 = (miny - 128 + 255) >> 8, py1 = (maxy - 128) >> 8;
+  if (px0 < 0) px0 = 0;
+  if (py0 < 0) py0 = 0;
+  if (px1 > (int64_t)W - 1) px1 = (int64_t)W - 1;
+  if (py1 > (int64_t)H - 1) py1 = (int64_t)H - 1;
+  const int b0 = edge_bias(bx, by, cx, cy), b1 = edge_bias(cx, cy, ax, ay), b2 = edge_bias(ax, ay, bx, by);
+  const float fa = (float)area2;
+  for (int64_t py = py0; py <= py1; py++)
+    for (int64_t px = px0; px <= px1; px++) {
+      int64_t sxp = px * 256 + 128, syp = py * 256 + 128;
+      int64_t e0 = orient2d(bx, by, cx, cy, sxp, syp);
+      int64_t e1 = orient2d(cx, cy, ax, ay, sxp, syp);
+      int64_t e2 = orient2d(ax, ay, bx, by, sxp, syp);
+      if ((e0 + b0) < 0 || (e1 + b1) < 0 || (e2 + b2) < 0) continue;
+      float l1 = (float)e1 / fa, l2 = (float)e2 / fa;
+      float zz = (za + l1 * (zb - za)) + l2 * (zc - za);
+      if (!(zz >= 0.0f && zz <= 1.0f)) continue;
+      uint64_t v = ((uint64_t)f2bits(zz) << 32) | (uint64_t)data;
+      uint64_t* p = &vis[(size_t)py * W + (size_t)px];
+      uint64_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
+      while (v > old && !__atomic_compare_exchange_n(p, &old, v, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    }
+}
+
+static void run_jobs(FrameJob* jobs, int n, void* (*fn)(void*)) {
+  pthread_t th[256];
+  if (n == 1) { fn(&jobs[0]); return; }
+  for (int t = 0; t < n; t++) pthread_create(&th[t], NULL, fn, &jobs[t]);
+  for (int t = 0; t < n; t++) pthread_join(th[t], NULL);
+}
+
+uint64_t orc_cpu_frame(const OrcScene* scene, const OxcCullCamera* cam, uint32_t width, uint32_t height, uint32_t hiz_w,
+                       uint32_t hiz_h, uint32_t* mask, const float* occluder_depth, int n_threads,
+                       OxcMeshletInstance* meshlet_instances, uint32_t* visible_indices, uint64_t* vis,
+                       OxcMeshletInstanceVisibility* vc, uint64_t* triangles) {
+  if (n_threads < 1) n_threads = 1;
+  if (n_threads > 256) n_threads = 256;
+  OxcDispatchIndirectCommand cmd;
+  orc_cull_meshes(scene, cam, OXC_CULL_TEST_ALL, 0, 0xFFFFFFFFu, meshlet_instances, vc, &cmd);
+  const uint32_t total = vc->total_visible_meshlet_instances;
+  OrcHiz hiz;
+  orc_hiz_layout(hiz_w, hiz_h, &hiz);
+  hiz.data = (float*)calloc(orc_hiz_total_texels(hiz_w, hiz_h), sizeof(float)); /* cleared to 0 each frame */
+  uint8_t* newvis = (uint8_t*)malloc(total ? total : 1);
+  float* depth = (float*)malloc((size_t)width * height * sizeof(float));
+  FrameJob jobs[256];
+  uint64_t ntri = 0;
+  /* vis = clear, then occluder depth (depth written by passes outside the path) */
+  for (size_t i = 0; i < (size_t)width * height; i++)
+    vis[i] = ((uint64_t)(occluder_depth ? f2bits(occluder_depth[i]) : 0u) << 32) | OXC_VIS_CLEAR;
+
+  for (int pass = 0; pass < 2; pass++) {
+    uint32_t flags = OXC_CULL_TEST_ALL | (pass ? OXC_CULL_LATE_PASS : 0);
+    for (int t = 0; t < n_threads; t++) {
+      FrameJob* j = &jobs[t];
+      memset(j, 0, sizeof *j);
+      j->scene = scene; j->mis = meshlet_instances; j->cam = cam; j->hiz = &hiz; j->flags = flags; j->mask = mask;
+      j->out = visible_indices + (pass ? vc->early_visible_meshlet_instances : 0) ; j->new_visible = newvis;
+      j->lo = (uint32_t)(((uint64_t)total * (uint64_t)t) / (uint64_t)n_threads);
+      j->hi = (uint32_t)(((uint64_t)total * (uint64_t)(t + 1)) / (uint64_t)n_threads);
+    }
+    /* survivors are staged in a scratch list (chunk-local positions), then compacted */
+    uint32_t* scratch = (uint32_t*)malloc((size_t)(total ? total : 1) * sizeof(uint32_t));
+    for (int t = 0; t < n_threads; t++) jobs[t].out = scratch;
+    run_jobs(jobs, n_threads, frame_cull_worker);
+    uint32_t base = pass ? vc->early_visible_meshlet_instances : 0, n = 0;
+    for (int t = 0; t < n_threads; t++) {
+      memcpy(visible_indices + base + n, scratch + jobs[t].lo, jobs[t].n_out * sizeof(uint32_t));
+      n += (uint32_t)jobs[t].n_out;
+    }
+    free(scratch);
+    if (pass) vc->late_visible_meshlet_instances = n; else vc->early_visible_meshlet_instances = n;
+    /* mask rewrite (cull_meshlets_hiz.slang:81-87) */
+    for (uint32_t i = 0; i < total; i++) {
+      OxcMeshletInstance mi = meshlet_instances[i];
+      uint32_t vi = scene->mesh_instances[mi.mesh_instance_index].meshlet_instance_visibility_offset + mi.meshlet_index;
+      if (newvis[i]) mask[vi / 32] |= 1u << (vi & 31); else mask[vi / 32] &= ~(1u << (vi & 31));
+    }
+    /* raster this pass's survivors */
+    for (int t = 0; t < n_threads; t++) {
+      FrameJob* j = &jobs[t];
+      j->visible = visible_indices + base; j->width = width; j->height = height; j->vis = vis;
+      j->lo = (uint32_t)(((uint64_t)n * (uint64_t)t) / (uint64_t)n_threads);
+      j->hi = (uint32_t)(((uint64_t)n * (uint64_t)(t + 1)) / (uint64_t)n_threads);
+    }
+    run_jobs(jobs, n_threads, frame_raster_worker);
+    for (int t = 0; t < n_threads; t++) ntri += jobs[t].ntri;
+    if (!pass) { /* generate_hiz from the early depth */
+      orc_resolve_visbuffer(vis, width, height, NULL, depth);
+      orc_build_hiz(depth, width, height, &hiz);
+    }
+  }
+  if (triangles) *triangles = ntri;
+  free(hiz.data); free(newvis); free(depth);
+  return (uint64_t)vc->early_visible_meshlet_instances + vc->late_visible_meshlet_instances;
+}

@@ -1,0 +1,219 @@
+"""ctypes wrapper of the CPU oracle (oracle/liboxc_oracle.so).  TEST INFRASTRUCTURE ONLY.
+
+Importers allowed by the project rules: tests/, __graft_entry__.smoke(), bench.py's cpu_baseline and
+--impl reference legs.  The product package (oxylus_b200/) never imports this module.
+"""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(_HERE))
+from oxylus_b200 import abi  # noqa: E402  (ABI struct definitions only)
+
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboxc_oracle.so")
+    srcs = [os.path.join(_HERE, f) for f in ("oxc_oracle.c", "oxc_oracle.h", "oxc_oracle_math.inc")]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "oxcull.h"))
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-B"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboxc_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _LIB = C.CDLL(so)
+        _LIB.orc_dequantize_half.restype = C.c_float
+        _LIB.orc_dequantize_half.argtypes = [C.c_uint16]
+        _LIB.orc_ceil_log2_u32.restype = C.c_uint32
+        _LIB.orc_ceil_log2_u32.argtypes = [C.c_uint32]
+        _LIB.orc_hiz_total_texels.restype = C.c_uint32
+        _LIB.orc_hiz_level_count.restype = C.c_uint32
+        _LIB.orc_cpu_baseline_cull.restype = C.c_uint64
+        _LIB.orc_cpu_frame.restype = C.c_uint64
+    return _LIB
+
+
+def _p(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else C.c_void_p(0)
+
+
+class HostScene:
+    """Host copies of a synth.Scene (mesh_instances is mutable: cull_meshes writes lod_index)."""
+
+    def __init__(self, scene):
+        self.meshes = np.ascontiguousarray(scene.meshes)
+        self.mesh_instances = np.ascontiguousarray(scene.mesh_instances).copy()
+        self.transforms = np.ascontiguousarray(scene.transforms)
+        self.blob = np.ascontiguousarray(scene.blob)
+        self.desc = abi.SceneDesc()
+        self.desc.meshes = self.meshes.ctypes.data
+        self.desc.mesh_count = len(self.meshes)
+        self.desc.mesh_instances = self.mesh_instances.ctypes.data
+        self.desc.mesh_instance_count = len(self.mesh_instances)
+        self.desc.transforms = self.transforms.ctypes.data
+        self.desc.transform_count = len(self.transforms)
+        self.desc.blob = self.blob.ctypes.data
+        self.desc.blob_size = self.blob.size
+        self.max_meshlets = scene.max_meshlet_instance_count
+
+    @property
+    def ref(self):
+        return C.byref(self.desc)
+
+
+class Hiz:
+    def __init__(self, w, h):
+        self.w, self.h = w, h
+        self.levels, self.offsets, self.total = abi.hiz_layout(w, h)
+        self.data = np.zeros(self.total, dtype=np.float32)
+        self.c = abi.OrcHiz()
+        lib().orc_hiz_layout(C.c_uint32(w), C.c_uint32(h), C.byref(self.c))
+        assert self.c.levels == self.levels and list(self.c.level_offset)[: self.levels] == self.offsets
+        self.c.data = self.data.ctypes.data
+
+    def level(self, l):
+        mw, mh = max(1, self.w >> l), max(1, self.h >> l)
+        return self.data[self.offsets[l] : self.offsets[l] + mw * mh].reshape(mh, mw)
+
+    @property
+    def ref(self):
+        return C.byref(self.c)
+
+
+def dequantize_half(h):
+    return float(lib().orc_dequantize_half(C.c_uint16(int(h))))
+
+
+def cull_meshes(hs: HostScene, cam, flags, first=0, count=0xFFFFFFFF):
+    mi = np.zeros(max(1, hs.max_meshlets), dtype=abi.MESHLET_INSTANCE_DT)
+    vis = np.zeros(1, dtype=abi.VISIBILITY_DT)
+    cmd = np.zeros(1, dtype=abi.DISPATCH_CMD_DT)
+    lib().orc_cull_meshes(hs.ref, _p(cam), C.c_uint32(flags), C.c_uint32(first), C.c_uint32(count), _p(mi), _p(vis), _p(cmd))
+    return mi, vis, cmd
+
+
+def cull_meshlets_hiz(hs, mi, vis, cam, flags, hiz: Hiz, mask, visible=None):
+    if visible is None:
+        visible = np.zeros(max(1, hs.max_meshlets), dtype=np.uint32)
+    cmd = np.zeros(1, dtype=abi.DISPATCH_CMD_DT)
+    lib().orc_cull_meshlets_hiz(hs.ref, _p(mi), _p(cam), C.c_uint32(flags), hiz.ref, _p(vis), _p(visible), _p(mask), _p(cmd))
+    return visible, cmd
+
+
+def cull_meshlets_flags(hs, mi, vis, cam, flags, hiz: Hiz, mask, f64=False):
+    out = np.zeros(max(1, int(vis["total"][0])), dtype=np.uint8)
+    fn = lib().orc_cull_meshlets_hiz_f64 if f64 else lib().orc_cull_meshlets_hiz_f32_flags
+    fn(hs.ref, _p(mi), _p(cam), C.c_uint32(flags), hiz.ref, _p(vis), _p(mask), _p(out))
+    return out[: int(vis["total"][0])]
+
+
+def cull_meshlets(hs, mi, vis, cam):
+    visible = np.zeros(max(1, hs.max_meshlets), dtype=np.uint32)
+    cmd = np.zeros(1, dtype=abi.DISPATCH_CMD_DT)
+    lib().orc_cull_meshlets(hs.ref, _p(mi), _p(cam), _p(vis), _p(visible), _p(cmd))
+    return visible, cmd
+
+
+def cull_meshlets_multiview(hs, mi, total, views, directional):
+    bits = np.zeros(max(1, total), dtype=np.uint32)
+    counts = np.zeros(abi.MAX_VIEWS, dtype=np.uint32)
+    lib().orc_cull_meshlets_multiview(hs.ref, _p(mi), C.c_uint32(total), _p(views), C.c_uint32(len(views)),
+                                      C.c_int(int(directional)), _p(bits), _p(counts))
+    return bits[:total], counts
+
+
+def build_hiz(depth, hiz: Hiz):
+    depth = np.ascontiguousarray(depth, dtype=np.float32)
+    h, w = depth.shape
+    lib().orc_build_hiz(_p(depth), C.c_uint32(w), C.c_uint32(h), hiz.ref)
+    return hiz
+
+
+def cull_triangles(hs, mi, visible, first, count, cam, id_base=0):
+    out = np.zeros(max(1, count) * 64 * 3, dtype=np.uint32)
+    cmd = np.zeros(1, dtype=abi.DRAW_CMD_DT)
+    lib().orc_cull_triangles(hs.ref, _p(mi), _p(visible), C.c_uint32(first), C.c_uint32(count), _p(cam),
+                             C.c_uint32(id_base), _p(out), _p(cmd))
+    return out[: int(cmd["index_count"][0])], cmd
+
+
+def clear_visbuffer(w, h):
+    vis = np.zeros((h, w), dtype=np.uint64)
+    lib().orc_clear_visbuffer(_p(vis), C.c_uint32(w), C.c_uint32(h))
+    return vis
+
+
+def raster(hs, mi, visible, first, count, cam, vis, id_base=0):
+    h, w = vis.shape
+    ntri = C.c_uint64(0)
+    lib().orc_raster_visbuffer(hs.ref, _p(mi), _p(visible), C.c_uint32(first), C.c_uint32(count), _p(cam),
+                               C.c_uint32(id_base), C.c_uint32(w), C.c_uint32(h), _p(vis), C.byref(ntri))
+    return int(ntri.value)
+
+
+def resolve(vis):
+    h, w = vis.shape
+    v32 = np.zeros((h, w), dtype=np.uint32)
+    d = np.zeros((h, w), dtype=np.float32)
+    lib().orc_resolve_visbuffer(_p(vis), C.c_uint32(w), C.c_uint32(h), _p(v32), _p(d))
+    return v32, d
+
+
+def merge_occluder_depth(vis, occluder_depth):
+    """depth written by passes outside the path: vis = max(vis, depth<<32 | ~0)"""
+    if occluder_depth is None:
+        return vis
+    packed = (occluder_depth.astype(np.float32).view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.uint64(0xFFFFFFFF)
+    np.maximum(vis, packed, out=vis)
+    return vis
+
+
+def frame(hs, cam, width, height, mask, occluder_depth=None):
+    """Serial two-pass frame exactly as RendererInstance::render sequences it (RendererInstance.cpp:842-884).
+    Returns dict with every intermediate the GPU parity tests compare."""
+    hw, hh = abi.hiz_extent(width, height)
+    hiz = Hiz(hw, hh)  # cleared to 0 every frame (RendererInstance.cpp:579-588)
+    mi, vis, cmd = cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    img = clear_visbuffer(width, height)
+    merge_occluder_depth(img, occluder_depth)
+    visible, tcmd_e = cull_meshlets_hiz(hs, mi, vis, cam, abi.CULL_TEST_ALL, hiz, mask)
+    e = int(vis["early"][0])
+    mask_after_early = mask.copy()
+    ntri_e = raster(hs, mi, visible, 0, e, cam, img)
+    _, depth = resolve(img)
+    build_hiz(depth, hiz)
+    visible, tcmd_l = cull_meshlets_hiz(hs, mi, vis, cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, hiz, mask, visible)
+    l = int(vis["late"][0])
+    ntri_l = raster(hs, mi, visible, e, l, cam, img)
+    return dict(meshlet_instances=mi, visibility=vis, visible=visible, early=e, late=l, hiz=hiz, vis64=img,
+                mask_after_early=mask_after_early, ntri_early=ntri_e, ntri_late=ntri_l, cull_meshlets_cmd=cmd)
+
+
+def cpu_baseline_cull(hs, mi, total, cam, mode, n_threads):
+    out = np.zeros(max(1, total), dtype=np.uint32)
+    n = lib().orc_cpu_baseline_cull(hs.ref, _p(mi), C.c_uint32(total), _p(cam), C.c_int(mode), C.c_int(n_threads), _p(out))
+    return out[: int(n)]
+
+
+def cpu_frame(hs, cam, width, height, mask, occluder_depth, n_threads):
+    hw, hh = abi.hiz_extent(width, height)
+    mi = np.zeros(max(1, hs.max_meshlets), dtype=abi.MESHLET_INSTANCE_DT)
+    visible = np.zeros(max(1, hs.max_meshlets), dtype=np.uint32)
+    img = np.zeros((height, width), dtype=np.uint64)
+    vc = np.zeros(1, dtype=abi.VISIBILITY_DT)
+    tri = C.c_uint64(0)
+    occ = np.ascontiguousarray(occluder_depth, dtype=np.float32) if occluder_depth is not None else None
+    lib().orc_cpu_frame(hs.ref, _p(cam), C.c_uint32(width), C.c_uint32(height), C.c_uint32(hw), C.c_uint32(hh),
+                        _p(mask), _p(occ), C.c_int(n_threads), _p(mi), _p(visible), _p(img), _p(vc), C.byref(tri))
+    return dict(meshlet_instances=mi, visible=visible, vis64=img, visibility=vc, triangles=int(tri.value))

@@ -1,0 +1,208 @@
+"""numpy / ctypes mirrors of include/oxcull.h (which mirrors Oxylus/include/Scene/SceneGPU.hpp).
+
+Sizes are asserted against the reference's scalar-layout sizes: MeshletBounds 16 B
+(SceneGPU.hpp:84-90), MeshInstance 20 B (:111-117), Meshlet 16 B (:119-124), MeshLOD 64 B (:126-140),
+Mesh 64 B (:142-152), CullCamera 96 B (:222-229).
+"""
+import ctypes as C
+
+import numpy as np
+
+TRANSFORM_DT = np.dtype([("world", "<f4", (16,))])
+MESHLET_BOUNDS_DT = np.dtype(
+    [
+        ("aabb_center", "<u2", (3,)),
+        ("cone_axis_xy", "i1", (2,)),
+        ("aabb_extent", "<u2", (3,)),
+        ("cone_axis_z", "i1"),
+        ("cone_cutoff", "i1"),
+    ]
+)
+MESH_BOUNDS_DT = np.dtype([("aabb_center", "<f4", (3,)), ("aabb_extent", "<f4", (3,))])
+VISIBILITY_DT = np.dtype([("total", "<u4"), ("early", "<u4"), ("late", "<u4")])
+MESHLET_INSTANCE_DT = np.dtype([("mesh_instance_index", "<u4"), ("meshlet_index", "<u4")])
+MESH_INSTANCE_DT = np.dtype(
+    [
+        ("mesh_index", "<u4"),
+        ("lod_index", "<u4"),
+        ("material_index", "<u4"),
+        ("transform_index", "<u4"),
+        ("meshlet_instance_visibility_offset", "<u4"),
+    ]
+)
+MESHLET_DT = np.dtype(
+    [
+        ("indirect_vertex_index_offset", "<u4"),
+        ("local_triangle_index_offset", "<u4"),
+        ("vertex_count", "<u4"),
+        ("triangle_count", "<u4"),
+    ]
+)
+MESH_LOD_DT = np.dtype(
+    [
+        ("indices", "<u8"),
+        ("meshlets", "<u8"),
+        ("meshlet_bounds", "<u8"),
+        ("local_triangle_indices", "<u8"),
+        ("indirect_vertex_indices", "<u8"),
+        ("indices_count", "<u4"),
+        ("meshlet_count", "<u4"),
+        ("meshlet_bounds_count", "<u4"),
+        ("local_triangle_indices_count", "<u4"),
+        ("indirect_vertex_indices_count", "<u4"),
+        ("error", "<f4"),
+    ]
+)
+MESH_DT = np.dtype(
+    [
+        ("vertex_positions", "<u8"),
+        ("vertex_normals", "<u8"),
+        ("texture_coords", "<u8"),
+        ("vertex_count", "<u4"),
+        ("lod_count", "<u4"),
+        ("lods", "<u8"),
+        ("bounds", MESH_BOUNDS_DT),
+    ]
+)
+CULL_CAMERA_DT = np.dtype(
+    [
+        ("projection_view", "<f4", (16,)),
+        ("position", "<f4", (3,)),
+        ("acceptable_lod_error", "<f4"),
+        ("resolution", "<f4", (2,)),
+        ("near_clip", "<f4"),
+        ("mesh_instance_count", "<u4"),
+    ]
+)
+DISPATCH_CMD_DT = np.dtype([("x", "<u4"), ("y", "<u4"), ("z", "<u4")])
+DRAW_CMD_DT = np.dtype(
+    [
+        ("index_count", "<u4"),
+        ("instance_count", "<u4"),
+        ("first_index", "<u4"),
+        ("vertex_offset", "<i4"),
+        ("first_instance", "<u4"),
+    ]
+)
+
+assert TRANSFORM_DT.itemsize == 64
+assert MESHLET_BOUNDS_DT.itemsize == 16
+assert VISIBILITY_DT.itemsize == 12
+assert MESHLET_INSTANCE_DT.itemsize == 8
+assert MESH_INSTANCE_DT.itemsize == 20
+assert MESHLET_DT.itemsize == 16
+assert MESH_LOD_DT.itemsize == 64
+assert MESH_DT.itemsize == 64
+assert CULL_CAMERA_DT.itemsize == 96
+assert DISPATCH_CMD_DT.itemsize == 12
+assert DRAW_CMD_DT.itemsize == 20
+
+# CullFlag — SceneGPU.hpp:345-353
+CULL_NONE = 0
+CULL_TEST_FRUSTUM = 1 << 0
+CULL_SELECT_LOD = 1 << 1
+CULL_TEST_OCCLUSION = 1 << 2
+CULL_LATE_PASS = 1 << 3
+CULL_TEST_ALL = CULL_TEST_FRUSTUM | CULL_SELECT_LOD | CULL_TEST_OCCLUSION
+
+HIZ_MAX_LEVELS = 13
+MAX_VIEWS = 16
+VIS_PRIMITIVE_BITS = 8
+VIS_CLEAR = 0xFFFFFFFF
+
+
+class SceneDesc(C.Structure):
+    """OxcSceneDesc"""
+
+    _fields_ = [
+        ("meshes", C.c_void_p),
+        ("mesh_count", C.c_uint32),
+        ("mesh_instances", C.c_void_p),
+        ("mesh_instance_count", C.c_uint32),
+        ("transforms", C.c_void_p),
+        ("transform_count", C.c_uint32),
+        ("blob", C.c_void_p),
+        ("blob_size", C.c_uint64),
+    ]
+
+
+class CreateInfo(C.Structure):
+    """OxcCreateInfo"""
+
+    _fields_ = [
+        ("max_mesh_instances", C.c_uint32),
+        ("max_meshlet_instances", C.c_uint32),
+        ("hiz_width", C.c_uint32),
+        ("hiz_height", C.c_uint32),
+        ("alloc_reordered_indices", C.c_uint32),
+        ("max_views", C.c_uint32),
+    ]
+
+
+class Outputs(C.Structure):
+    """OxcOutputs"""
+
+    _fields_ = [
+        ("visibility", C.c_void_p),
+        ("cull_meshlets_cmd", C.c_void_p),
+        ("cull_triangles_cmd", C.c_void_p),
+        ("draw_cmd", C.c_void_p),
+        ("meshlet_instances", C.c_void_p),
+        ("visible_meshlet_instances_indices", C.c_void_p),
+        ("meshlet_instance_visibility_mask", C.c_void_p),
+        ("reordered_indices", C.c_void_p),
+        ("mesh_instances", C.c_void_p),
+        ("hiz", C.c_void_p),
+        ("hiz_level_offset", C.c_uint32 * HIZ_MAX_LEVELS),
+        ("hiz_levels", C.c_uint32),
+        ("hiz_width", C.c_uint32),
+        ("hiz_height", C.c_uint32),
+        ("visibility_mask_words", C.c_uint32),
+        ("view_visibility_bits", C.c_void_p),
+        ("view_visible_counts", C.c_void_p),
+        ("raster_triangle_count", C.c_void_p),
+    ]
+
+
+class OrcHiz(C.Structure):
+    """OrcHiz (oracle/oxc_oracle.h) — also used as a plain layout helper"""
+
+    _fields_ = [
+        ("data", C.c_void_p),
+        ("width", C.c_uint32),
+        ("height", C.c_uint32),
+        ("levels", C.c_uint32),
+        ("level_offset", C.c_uint32 * HIZ_MAX_LEVELS),
+    ]
+
+
+class FrameResult(C.Structure):
+    """OxrFrameResult"""
+
+    _fields_ = [
+        ("total", C.c_uint32),
+        ("early", C.c_uint32),
+        ("late", C.c_uint32),
+        ("draw_index_count_early", C.c_uint32),
+        ("draw_index_count_late", C.c_uint32),
+        ("raster_triangles", C.c_uint64),
+    ]
+
+
+def hiz_extent(width: int, height: int):
+    """RendererInstance.cpp:573-577: bit_ceil((W+1)>>1) per axis."""
+
+    def bit_ceil(v):
+        return 1 if v <= 1 else 1 << (int(v) - 1).bit_length()
+
+    return bit_ceil((width + 1) >> 1), bit_ceil((height + 1) >> 1)
+
+
+def hiz_layout(w: int, h: int):
+    """(levels, offsets[levels], total_texels) — Texture.hpp:144-146 + min(.,13)."""
+    levels = min(int(max(w, h)).bit_length(), HIZ_MAX_LEVELS)
+    offs, off = [], 0
+    for l in range(levels):
+        offs.append(off)
+        off += max(1, w >> l) * max(1, h >> l)
+    return levels, offs, off
