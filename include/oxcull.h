@@ -270,6 +270,10 @@ int oxc_cull_meshlets(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cul
  * row-major width x height floats.  Fills every mip of the context's pyramid. */
 int oxc_build_hiz(OxcContext* ctx, const float* depth_dev, uint32_t width, uint32_t height, void* stream);
 
+/* Same pyramid, sampled straight from the packed 64-bit vis buffer (depth = high 32 bits): saves the
+ * resolve pass between the early raster and generate_hiz.  No reference equivalent (it has a D32F image). */
+int oxc_build_hiz_packed(OxcContext* ctx, const uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream);
+
 /* cull_triangles.slang:27-90 via CullGeometry.cpp:337-403: resets draw_cmd{0,1,0,0,0}, then one
  * block per surviving meshlet of this pass (early: [0,E); late: [E,E+L)).  Requires
  * alloc_reordered_indices. */
@@ -292,6 +296,10 @@ int oxc_raster_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, uint32_t 
 int oxc_resolve_visbuffer(OxcContext* ctx, const uint64_t* vis_dev, uint32_t width, uint32_t height,
                           uint32_t* vis32_dev, float* depth_dev, void* stream);
 
+/* Depth laid down by passes outside this path (terrain, RendererInstance.cpp:862-873): vis = max(vis,
+ * asuint(depth)<<32 | ~0u) per pixel. */
+int oxc_merge_depth(OxcContext* ctx, uint64_t* vis_dev, const float* depth_dev, uint32_t width, uint32_t height, void* stream);
+
 /* Multi-view batched cull (the reference's analogue is cull_meshlets_hpb.slang:27-99, which loops
  * <=10 shadow clipmaps per meshlet; CullGeometry.cpp:199-273).  Reads every meshlet's bounds ONCE and
  * tests it against n_views cameras: per view  cone (directional when view_dirs != NULL,
@@ -301,6 +309,13 @@ int oxc_cull_meshlets_multiview(OxcContext* ctx, const OxcCullCamera* views, uin
                                 void* stream);
 
 int oxc_get_outputs(OxcContext* ctx, OxcOutputs* out);
+
+/* Plumbing for hosts without their own CUDA bindings (the ctypes tests / bench): async copy on `stream`
+ * (kind 0 = host->device, 1 = device->host, 2 = device->device), stream sync, raw device allocations. */
+int oxc_copy(OxcContext* ctx, void* dst, const void* src, uint64_t bytes, int kind, void* stream);
+int oxc_sync(OxcContext* ctx, void* stream);
+int oxc_device_alloc(OxcContext* ctx, uint64_t bytes, void** out);
+int oxc_device_free(OxcContext* ctx, void* ptr);
 
 /* ------------------------------------------------------------------------------------------------
  * oxr_* — host-side mirror of the reference's frame sequencing (C++ class ox::RendererInstance in

@@ -523,7 +523,7 @@ void orc_cull_triangles(const OrcScene* scene, const OxcMeshletInstance* meshlet
  *   5. sample at pixel centres (px*256+128); edge tie-break: a pixel exactly on edge a->b is inside
  *      iff (dy > 0) || (dy == 0 && dx < 0)  (watertight, no double hits).
  *   6. depth z = (z0 + l1*(z1-z0)) + l2*(z2-z0), l_i = (float)E_i / (float)area2; fragments with
- *      z outside [0,1] are clipped (near/far).  value = asuint(z)<<32 | (id<<8 | tri); max wins
+ *      z outside [0,1] are clipped (near/far); -0.0 is stored as +0.0.  value = asuint(z)<<32 | (id<<8 | tri); max wins
  *      (reverse-Z GreaterOrEqual; equal depth -> larger id, deterministic).
  * ---------------------------------------------------------------------------------------------- */
 void orc_clear_visbuffer(uint64_t* vis, uint32_t width, uint32_t height) {
@@ -580,7 +580,9 @@ static void raster_triangle(const float clip[3][4], uint32_t data, uint32_t W, u
       float l1 = (float)e1 / fa, l2 = (float)e2 / fa;
       float zz = (za + l1 * (zb - za)) + l2 * (zc - za);
       if (!(zz >= 0.0f && zz <= 1.0f)) continue;
-      uint64_t v = ((uint64_t)f2bits(zz) << 32) | (uint64_t)data;
+      uint32_t zbits = f2bits(zz);
+      if (zbits == 0x80000000u) zbits = 0u; /* -0.0 -> +0.0 so unsigned order == depth order */
+      uint64_t v = ((uint64_t)zbits << 32) | (uint64_t)data;
       uint64_t* p = &vis[(size_t)py * W + (size_t)px];
       if (v > *p) *p = v;
     }
@@ -821,7 +823,9 @@ static void raster_triangle_atomic(const float clip[3][4], uint32_t data, uint32
       float l1 = (float)e1 / fa, l2 = (float)e2 / fa;
       float zz = (za + l1 * (zb - za)) + l2 * (zc - za);
       if (!(zz >= 0.0f && zz <= 1.0f)) continue;
-      uint64_t v = ((uint64_t)f2bits(zz) << 32) | (uint64_t)data;
+      uint32_t zbits = f2bits(zz);
+      if (zbits == 0x80000000u) zbits = 0u; /* -0.0 -> +0.0 so unsigned order == depth order */
+      uint64_t v = ((uint64_t)zbits << 32) | (uint64_t)data;
       uint64_t* p = &vis[(size_t)py * W + (size_t)px];
       uint64_t old = __atomic_load_n(p, __ATOMIC_RELAXED);
       while (v > old && !__atomic_compare_exchange_n(p, &old, v, 1, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}

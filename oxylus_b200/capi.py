@@ -1,0 +1,318 @@
+"""ctypes binding of liboxcull.so (include/oxcull.h).  Fails loudly when the CUDA library is missing or no
+GPU is present: there is no CPU fallback in the product path.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import abi, build as _build
+
+_LIB = None
+
+OK = 0
+E_NO_DEVICE = -3
+
+# every symbol include/oxcull.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "oxc_last_error", "oxc_kernel_launch_count", "oxc_version", "oxc_create", "oxc_destroy", "oxc_set_scene",
+    "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_cull_meshes",
+    "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_cull_triangles", "oxc_clear_visbuffer",
+    "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview",
+    "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free",
+    "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_render",
+]
+
+
+class OxcError(RuntimeError):
+    pass
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load liboxcull.so; raises if it cannot be built/loaded (never falls back to a CPU path)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.exists(_build.LIB):
+        if not build_if_missing:
+            raise OxcError("liboxcull.so missing: run `python -m oxylus_b200.build` (needs nvcc); no CPU fallback exists")
+        _build.build()
+    lib = C.CDLL(_build.LIB)
+    lib.oxc_last_error.restype = C.c_char_p
+    lib.oxc_version.restype = C.c_char_p
+    lib.oxc_kernel_launch_count.restype = C.c_uint64
+    lib.oxr_context.restype = C.c_void_p
+    vp, u32, u64, i32 = C.c_void_p, C.c_uint32, C.c_uint64, C.c_int
+    lib.oxc_create.argtypes = [i32, C.POINTER(abi.CreateInfo), C.POINTER(vp)]
+    lib.oxc_destroy.argtypes = [vp]
+    lib.oxc_destroy.restype = None
+    lib.oxc_set_scene.argtypes = [vp, C.POINTER(abi.SceneDesc), vp]
+    lib.oxc_update_transforms.argtypes = [vp, vp, u32, u32, vp]
+    lib.oxc_reset_visibility_mask.argtypes = [vp, vp]
+    lib.oxc_clear_hiz.argtypes = [vp, vp]
+    lib.oxc_set_shard.argtypes = [vp, u32, u32, vp]
+    lib.oxc_cull_meshes.argtypes = [vp, vp, u32, vp]
+    lib.oxc_cull_meshlets.argtypes = [vp, vp, u32, i32, vp]
+    lib.oxc_build_hiz.argtypes = [vp, vp, u32, u32, vp]
+    lib.oxc_build_hiz_packed.argtypes = [vp, vp, u32, u32, vp]
+    lib.oxc_cull_triangles.argtypes = [vp, vp, u32, vp]
+    lib.oxc_clear_visbuffer.argtypes = [vp, vp, u32, u32, vp]
+    lib.oxc_raster_visbuffer.argtypes = [vp, vp, u32, u32, u32, vp, i32, vp]
+    lib.oxc_resolve_visbuffer.argtypes = [vp, vp, u32, u32, vp, vp, vp]
+    lib.oxc_merge_depth.argtypes = [vp, vp, vp, u32, u32, vp]
+    lib.oxc_cull_meshlets_multiview.argtypes = [vp, vp, u32, i32, vp]
+    lib.oxc_get_outputs.argtypes = [vp, C.POINTER(abi.Outputs)]
+    lib.oxc_copy.argtypes = [vp, vp, vp, u64, i32, vp]
+    lib.oxc_sync.argtypes = [vp, vp]
+    lib.oxc_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    lib.oxc_device_free.argtypes = [vp, vp]
+    lib.oxr_create.argtypes = [i32, C.POINTER(abi.CreateInfo), u32, u32, C.POINTER(vp)]
+    lib.oxr_destroy.argtypes = [vp]
+    lib.oxr_destroy.restype = None
+    lib.oxr_context.argtypes = [vp]
+    lib.oxr_update.argtypes = [vp, C.POINTER(abi.SceneDesc)]
+    lib.oxr_render.argtypes = [vp, vp, vp, vp, vp, vp, u32, C.POINTER(abi.FrameResult)]
+    _LIB = lib
+    return lib
+
+
+def _check(rc, what):
+    if rc != OK:
+        raise OxcError(f"{what} failed ({rc}): {load().oxc_last_error().decode()}")
+
+
+def kernel_launch_count():
+    return int(load().oxc_kernel_launch_count())
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    return C.c_void_p(int(a))
+
+
+class Context:
+    """OxcContext wrapper.  `stream` is a raw cudaStream_t handle (int; 0 = default stream)."""
+
+    def __init__(self, device, max_mesh_instances, max_meshlet_instances, hiz_w, hiz_h, alloc_reordered_indices=False,
+                 max_views=0, stream=0):
+        self.lib = load()
+        info = abi.CreateInfo(max_mesh_instances, max_meshlet_instances, hiz_w, hiz_h, int(alloc_reordered_indices), max_views)
+        h = C.c_void_p()
+        _check(self.lib.oxc_create(device, C.byref(info), C.byref(h)), "oxc_create")
+        self.h = h
+        self.stream = stream
+        self.max_meshlet_instances = max_meshlet_instances
+        self.max_mesh_instances = max_mesh_instances
+        self._keep = None
+        self.out = abi.Outputs()
+        _check(self.lib.oxc_get_outputs(self.h, C.byref(self.out)), "oxc_get_outputs")
+        self._owned = True
+
+    @classmethod
+    def from_handle(cls, handle, stream=0):
+        self = cls.__new__(cls)
+        self.lib = load()
+        self.h = C.c_void_p(handle)
+        self.stream = stream
+        self._keep = None
+        self.out = abi.Outputs()
+        _check(self.lib.oxc_get_outputs(self.h, C.byref(self.out)), "oxc_get_outputs")
+        self._owned = False
+        return self
+
+    def close(self):
+        if getattr(self, "h", None) and self._owned:
+            self.lib.oxc_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- scene ----
+    def set_scene(self, scene):
+        from . import synth
+
+        desc, keep = synth.scene_desc(scene)
+        self._keep = keep
+        _check(self.lib.oxc_set_scene(self.h, C.byref(desc), self.stream), "oxc_set_scene")
+        self.sync()
+
+    def update_transforms(self, transforms, first=0):
+        t = np.ascontiguousarray(transforms)
+        _check(self.lib.oxc_update_transforms(self.h, _ptr(t), first, len(t), self.stream), "oxc_update_transforms")
+        self.sync()
+
+    def reset_visibility_mask(self):
+        _check(self.lib.oxc_reset_visibility_mask(self.h, self.stream), "oxc_reset_visibility_mask")
+
+    def clear_hiz(self):
+        _check(self.lib.oxc_clear_hiz(self.h, self.stream), "oxc_clear_hiz")
+
+    def set_shard(self, first, count, id_base_dev=None):
+        _check(self.lib.oxc_set_shard(self.h, first, count, _ptr(id_base_dev)), "oxc_set_shard")
+
+    # ---- passes ----
+    def cull_meshes(self, cam, flags=abi.CULL_TEST_ALL):
+        _check(self.lib.oxc_cull_meshes(self.h, _ptr(cam), flags, self.stream), "oxc_cull_meshes")
+
+    def cull_meshlets(self, cam, flags, use_hiz=True):
+        _check(self.lib.oxc_cull_meshlets(self.h, _ptr(cam), flags, int(use_hiz), self.stream), "oxc_cull_meshlets")
+
+    def build_hiz(self, depth_dev, w, h):
+        _check(self.lib.oxc_build_hiz(self.h, _ptr(depth_dev), w, h, self.stream), "oxc_build_hiz")
+
+    def build_hiz_packed(self, vis_dev, w, h):
+        _check(self.lib.oxc_build_hiz_packed(self.h, _ptr(vis_dev), w, h, self.stream), "oxc_build_hiz_packed")
+
+    def cull_triangles(self, cam, flags):
+        _check(self.lib.oxc_cull_triangles(self.h, _ptr(cam), flags, self.stream), "oxc_cull_triangles")
+
+    def clear_visbuffer(self, vis_dev, w, h):
+        _check(self.lib.oxc_clear_visbuffer(self.h, _ptr(vis_dev), w, h, self.stream), "oxc_clear_visbuffer")
+
+    def raster_visbuffer(self, cam, flags, w, h, vis_dev, small_primitive_cull=False):
+        _check(self.lib.oxc_raster_visbuffer(self.h, _ptr(cam), flags, w, h, _ptr(vis_dev), int(small_primitive_cull), self.stream),
+               "oxc_raster_visbuffer")
+
+    def resolve_visbuffer(self, vis_dev, w, h, vis32_dev, depth_dev):
+        _check(self.lib.oxc_resolve_visbuffer(self.h, _ptr(vis_dev), w, h, _ptr(vis32_dev), _ptr(depth_dev), self.stream),
+               "oxc_resolve_visbuffer")
+
+    def merge_depth(self, vis_dev, depth_dev, w, h):
+        _check(self.lib.oxc_merge_depth(self.h, _ptr(vis_dev), _ptr(depth_dev), w, h, self.stream), "oxc_merge_depth")
+
+    def cull_meshlets_multiview(self, views, directional):
+        v = np.ascontiguousarray(views)
+        _check(self.lib.oxc_cull_meshlets_multiview(self.h, _ptr(v), len(v), int(directional), self.stream),
+               "oxc_cull_meshlets_multiview")
+
+    # ---- plumbing ----
+    def sync(self):
+        _check(self.lib.oxc_sync(self.h, self.stream), "oxc_sync")
+
+    def alloc(self, nbytes):
+        p = C.c_void_p()
+        _check(self.lib.oxc_device_alloc(self.h, nbytes, C.byref(p)), "oxc_device_alloc")
+        return p.value
+
+    def free(self, ptr):
+        _check(self.lib.oxc_device_free(self.h, _ptr(ptr)), "oxc_device_free")
+
+    def upload(self, dev_ptr, host: np.ndarray):
+        host = np.ascontiguousarray(host)
+        _check(self.lib.oxc_copy(self.h, _ptr(dev_ptr), _ptr(host), host.nbytes, 0, self.stream), "oxc_copy h2d")
+        self.sync()
+
+    def download(self, dev_ptr, dtype, count):
+        out = np.empty(count, dtype=dtype)
+        if count:
+            _check(self.lib.oxc_copy(self.h, _ptr(out), _ptr(dev_ptr), out.nbytes, 1, self.stream), "oxc_copy d2h")
+        self.sync()
+        return out
+
+    # ---- typed readbacks of OxcOutputs ----
+    def visibility(self):
+        return self.download(self.out.visibility, abi.VISIBILITY_DT, 1)
+
+    def meshlet_instances(self, n):
+        return self.download(self.out.meshlet_instances, abi.MESHLET_INSTANCE_DT, n)
+
+    def visible_indices(self, n):
+        return self.download(self.out.visible_meshlet_instances_indices, np.uint32, n)
+
+    def mask(self):
+        return self.download(self.out.meshlet_instance_visibility_mask, np.uint32, self.out.visibility_mask_words)
+
+    def set_mask(self, mask):
+        self.upload(self.out.meshlet_instance_visibility_mask, np.ascontiguousarray(mask, dtype=np.uint32))
+
+    def mesh_instances(self, n):
+        return self.download(self.out.mesh_instances, abi.MESH_INSTANCE_DT, n)
+
+    def cull_meshlets_cmd(self):
+        return self.download(self.out.cull_meshlets_cmd, abi.DISPATCH_CMD_DT, 1)
+
+    def cull_triangles_cmd(self):
+        return self.download(self.out.cull_triangles_cmd, abi.DISPATCH_CMD_DT, 1)
+
+    def draw_cmd(self):
+        return self.download(self.out.draw_cmd, abi.DRAW_CMD_DT, 1)
+
+    def reordered_indices(self, n):
+        return self.download(self.out.reordered_indices, np.uint32, n)
+
+    def hiz_levels(self):
+        o = self.out
+        total = 0
+        for l in range(o.hiz_levels):
+            total = o.hiz_level_offset[l] + max(1, o.hiz_width >> l) * max(1, o.hiz_height >> l)
+        flat = self.download(o.hiz, np.float32, total)
+        return [flat[o.hiz_level_offset[l]: o.hiz_level_offset[l] + max(1, o.hiz_width >> l) * max(1, o.hiz_height >> l)]
+                .reshape(max(1, o.hiz_height >> l), max(1, o.hiz_width >> l)) for l in range(o.hiz_levels)]
+
+    def upload_hiz(self, flat):
+        self.upload(self.out.hiz, np.ascontiguousarray(flat, dtype=np.float32))
+
+    def view_bits(self, n):
+        return self.download(self.out.view_visibility_bits, np.uint32, n)
+
+    def view_counts(self):
+        return self.download(self.out.view_visible_counts, np.uint32, abi.MAX_VIEWS)
+
+    def raster_triangle_count(self):
+        return int(self.download(self.out.raster_triangle_count, np.uint64, 1)[0])
+
+
+class Renderer:
+    """OxrRenderer wrapper: the host mirror of RendererInstance (HOST buffers in, HOST buffers out)."""
+
+    def __init__(self, device, scene, alloc_reordered_indices=False):
+        self.lib = load()
+        hw, hh = scene.hiz_extent()
+        info = abi.CreateInfo(max(1, scene.mesh_instance_count), max(1, scene.max_meshlet_instance_count), hw, hh,
+                              int(alloc_reordered_indices), 0)
+        h = C.c_void_p()
+        rc = self.lib.oxr_create(device, C.byref(info), scene.width, scene.height, C.byref(h))
+        _check(rc, "oxr_create")
+        self.h = h
+        self.scene = scene
+        from . import synth
+
+        desc, self._keep = synth.scene_desc(scene)
+        _check(self.lib.oxr_update(self.h, C.byref(desc)), "oxr_update")
+        self.ctx = Context.from_handle(self.lib.oxr_context(self.h))
+
+    def render(self, cam, occluder_depth=None, want_image=True, want_indices=True):
+        sc = self.scene
+        vis32 = np.empty((sc.height, sc.width), dtype=np.uint32) if want_image else None
+        depth = np.empty((sc.height, sc.width), dtype=np.float32) if want_image else None
+        idx = np.empty(max(1, sc.max_meshlet_instance_count), dtype=np.uint32) if want_indices else None
+        occ = np.ascontiguousarray(occluder_depth, dtype=np.float32) if occluder_depth is not None else None
+        res = abi.FrameResult()
+        _check(self.lib.oxr_render(self.h, _ptr(cam), _ptr(occ), _ptr(vis32), _ptr(depth), _ptr(idx),
+                                   len(idx) if idx is not None else 0, C.byref(res)), "oxr_render")
+        n = res.early + res.late
+        return dict(vis32=vis32, depth=depth, visible=idx[:n] if idx is not None else None, total=res.total, early=res.early,
+                    late=res.late, draw_index_count_early=res.draw_index_count_early,
+                    draw_index_count_late=res.draw_index_count_late, raster_triangles=res.raster_triangles)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.oxr_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,213 @@
+// renderer_instance.cpp — see renderer_instance.hpp.  Host code only: every byte of compute goes through
+// the C ABI of include/oxcull.h.
+#include "renderer_instance.hpp"
+
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <new>
+
+namespace ox {
+
+namespace {
+struct Readback {
+  OxcMeshletInstanceVisibility visibility;
+  uint32_t draw_index_count[2];
+  unsigned long long raster_triangles;
+};
+} // namespace
+
+int RendererInstance::fail(int rc) {
+  if (rc != OXC_OK && error_.empty()) error_ = oxc_last_error();
+  return rc;
+}
+
+RendererInstance::RendererInstance(int device, const OxcCreateInfo& info, uint32_t width, uint32_t height)
+    : width_(width), height_(height) {
+  if (oxc_create(device, &info, &ctx_) != OXC_OK) {
+    error_ = oxc_last_error();
+    ctx_ = nullptr;
+    return;
+  }
+  cudaStream_t s = nullptr;
+  const size_t px = (size_t)width * height;
+  if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&d_vis64_), px * 8) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&d_vis32_), px * 4) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&d_depth_), px * 4) != cudaSuccess ||
+      cudaMalloc(reinterpret_cast<void**>(&d_occluder_), px * 4) != cudaSuccess ||
+      cudaMallocHost(&h_pinned_, sizeof(Readback)) != cudaSuccess) {
+    error_ = std::string("RendererInstance allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+  }
+  stream_ = s;
+}
+
+RendererInstance::~RendererInstance() {
+  if (stream_) cudaStreamSynchronize(static_cast<cudaStream_t>(stream_));
+  cudaFree(d_vis64_); cudaFree(d_vis32_); cudaFree(d_depth_); cudaFree(d_occluder_);
+  if (h_pinned_) cudaFreeHost(h_pinned_);
+  if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
+  oxc_destroy(ctx_);
+}
+
+// RendererInstance::update (RendererInstance.cpp:1333-1788): table uploads + mask (re)allocation / zero fill
+auto RendererInstance::update(const RendererInstanceUpdateInfo& info) -> int {
+  if (!ctx_) return OXC_E_STATE;
+  error_.clear();
+  return fail(oxc_set_scene(ctx_, &info.scene, stream_));
+}
+
+// CullGeometry.cpp:61-404
+auto RendererInstance::cull_geometry(CullGeometryContext& context) -> int {
+  int rc;
+  // --- Stage 1: cull_meshes (only on the first cull of a sequence), :68-117
+  if (context.init_cull_meshes)
+    if ((rc = oxc_cull_meshes(ctx_, &context.cull_camera, context.cull_flags, stream_)) != OXC_OK) return fail(rc);
+  // --- Stage 2: cull_meshlets, :124-335.  The plain variant is dispatched with TestFrustum only (:275).
+  if (context.use_hiz) rc = oxc_cull_meshlets(ctx_, &context.cull_camera, context.cull_flags, 1, stream_);
+  else rc = oxc_cull_meshlets(ctx_, &context.cull_camera, OXC_CULL_TEST_FRUSTUM, 0, stream_);
+  if (rc != OXC_OK) return fail(rc);
+  // --- Stage 3: cull_triangles, :337-403 (optional here: the raster fuses it)
+  if (context.materialize_indices)
+    if ((rc = oxc_cull_triangles(ctx_, &context.cull_camera, context.cull_flags, stream_)) != OXC_OK) return fail(rc);
+  return OXC_OK;
+}
+
+// CullGeometry.cpp:10-59 — source is the depth half of the packed vis buffer
+auto RendererInstance::generate_hiz(MainGeometryContext& context) -> int {
+  return fail(oxc_build_hiz_packed(ctx_, context.visbuffer_attachment, context.width, context.height, stream_));
+}
+
+// DrawGeometry.cpp:104-190 — "vis encode": the HW raster of reordered_indices becomes the fused
+// triangle-cull + software raster into the packed image
+auto RendererInstance::draw_for_visbuffer(MainGeometryContext& context) -> int {
+  return fail(oxc_raster_visbuffer(ctx_, &context.cull_camera, context.cull_flags, context.width, context.height,
+                                   context.visbuffer_attachment, 0, stream_));
+}
+
+auto RendererInstance::render(const OxcCullCamera& camera, const float* occluder_depth_host, uint32_t* vis32_host,
+                              float* depth_host, uint32_t* visible_indices_host, uint32_t visible_indices_capacity,
+                              OxrFrameResult* result) -> int {
+  if (!ctx_ || !error_.empty()) return OXC_E_STATE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const size_t px = (size_t)width_ * height_;
+  int rc;
+  OxcOutputs out;
+  if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return fail(rc);
+  Readback* rb = static_cast<Readback*>(h_pinned_);
+
+  // attachments: depth cleared to 0, vis buffer to ~0 (RendererInstance.cpp:562-571,629-680), Hi-Z cleared every frame (:579-588)
+  if ((rc = oxc_clear_visbuffer(ctx_, d_vis64_, width_, height_, s)) != OXC_OK) return fail(rc);
+  if ((rc = oxc_clear_hiz(ctx_, s)) != OXC_OK) return fail(rc);
+  if (occluder_depth_host) {
+    if (cudaMemcpyAsync(d_occluder_, occluder_depth_host, px * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return fail(OXC_E_CUDA);
+    if ((rc = oxc_merge_depth(ctx_, d_vis64_, d_occluder_, width_, height_, s)) != OXC_OK) return fail(rc);
+  }
+
+  MainGeometryContext main_geometry_context;
+  main_geometry_context.visbuffer_attachment = d_vis64_;
+  main_geometry_context.width = width_;
+  main_geometry_context.height = height_;
+  // RendererInstance.cpp:796-800: hoisted so the early pass's visibility / dispatch buffers persist into the late pass
+  CullGeometryContext cull_geometry_context;
+  cull_geometry_context.use_hiz = true;
+  cull_geometry_context.init_cull_meshes = true;
+  cull_geometry_context.cull_camera = camera;
+  cull_geometry_context.materialize_indices = out.reordered_indices != nullptr;
+
+  int pass_index = 0;
+  const auto run_geometry_pass = [&](bool late) -> int { // RendererInstance.cpp:842-881
+    if (late) {
+      cull_geometry_context.cull_flags |= OXC_CULL_LATE_PASS;
+      cull_geometry_context.init_cull_meshes = false;
+      cull_geometry_context.cull_camera = camera;
+    }
+    int r = cull_geometry(cull_geometry_context);
+    if (r != OXC_OK) return r;
+    if (cull_geometry_context.materialize_indices)
+      if (cudaMemcpyAsync(&rb->draw_index_count[pass_index], &out.draw_cmd->index_count, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+        return OXC_E_CUDA;
+    pass_index++;
+    main_geometry_context.cull_flags = cull_geometry_context.cull_flags;
+    main_geometry_context.cull_camera = cull_geometry_context.cull_camera;
+    return draw_for_visbuffer(main_geometry_context);
+  };
+
+  rb->draw_index_count[0] = rb->draw_index_count[1] = 0;
+  if ((rc = run_geometry_pass(false)) != OXC_OK) return fail(rc); // :882
+  if ((rc = generate_hiz(main_geometry_context)) != OXC_OK) return fail(rc); // :883
+  if ((rc = run_geometry_pass(true)) != OXC_OK) return fail(rc);  // :884
+
+  // results back to the host (the engine would hand the attachments to decode_visbuffer, :923-925)
+  if (vis32_host || depth_host) {
+    if ((rc = oxc_resolve_visbuffer(ctx_, d_vis64_, width_, height_, vis32_host ? d_vis32_ : nullptr,
+                                    depth_host ? d_depth_ : nullptr, s)) != OXC_OK) return fail(rc);
+    if (vis32_host && cudaMemcpyAsync(vis32_host, d_vis32_, px * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) return fail(OXC_E_CUDA);
+    if (depth_host && cudaMemcpyAsync(depth_host, d_depth_, px * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess) return fail(OXC_E_CUDA);
+  }
+  if (cudaMemcpyAsync(&rb->visibility, out.visibility, sizeof rb->visibility, cudaMemcpyDeviceToHost, s) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (cudaMemcpyAsync(&rb->raster_triangles, out.raster_triangle_count, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (cudaStreamSynchronize(s) != cudaSuccess) {
+    error_ = cudaGetErrorString(cudaGetLastError());
+    return OXC_E_CUDA;
+  }
+  if (visible_indices_host) {
+    uint32_t n = rb->visibility.early_visible_meshlet_instances + rb->visibility.late_visible_meshlet_instances;
+    if (n > visible_indices_capacity) n = visible_indices_capacity;
+    if (n && cudaMemcpy(visible_indices_host, out.visible_meshlet_instances_indices, (size_t)n * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+      return fail(OXC_E_CUDA);
+  }
+  if (result) {
+    result->visibility = rb->visibility;
+    result->draw_index_count_early = rb->draw_index_count[0];
+    result->draw_index_count_late = rb->draw_index_count[1];
+    result->raster_triangles = rb->raster_triangles;
+  }
+  return OXC_OK;
+}
+
+} // namespace ox
+
+// ---- C exports ----
+struct OxrRenderer {
+  ox::RendererInstance impl;
+  OxrRenderer(int device, const OxcCreateInfo& info, uint32_t w, uint32_t h) : impl(device, info, w, h) {}
+};
+
+extern "C" {
+
+int oxr_create(int device, const OxcCreateInfo* info, uint32_t width, uint32_t height, OxrRenderer** out) {
+  if (!info || !out || !width || !height) return OXC_E_INVALID;
+  *out = nullptr;
+  OxrRenderer* r = new (std::nothrow) OxrRenderer(device, *info, width, height);
+  if (!r) return OXC_E_INVALID;
+  if (!r->impl.ok()) {
+    const int rc = r->impl.context() ? OXC_E_CUDA : OXC_E_NO_DEVICE;
+    delete r;
+    return rc;
+  }
+  *out = r;
+  return OXC_OK;
+}
+
+void oxr_destroy(OxrRenderer* r) { delete r; }
+
+OxcContext* oxr_context(OxrRenderer* r) { return r ? r->impl.context() : nullptr; }
+
+int oxr_update(OxrRenderer* r, const OxcSceneDesc* scene) {
+  if (!r || !scene) return OXC_E_INVALID;
+  ox::RendererInstanceUpdateInfo info;
+  info.mesh_instance_count = scene->mesh_instance_count;
+  info.scene = *scene;
+  int rc = r->impl.update(info);
+  if (rc == OXC_OK && cudaStreamSynchronize(static_cast<cudaStream_t>(r->impl.stream())) != cudaSuccess) rc = OXC_E_CUDA;
+  return rc;
+}
+
+int oxr_render(OxrRenderer* r, const OxcCullCamera* camera, const float* occluder_depth_host, uint32_t* vis32_host,
+               float* depth_host, uint32_t* visible_indices_host, uint32_t visible_indices_capacity, OxrFrameResult* result) {
+  if (!r || !camera) return OXC_E_INVALID;
+  return r->impl.render(*camera, occluder_depth_host, vis32_host, depth_host, visible_indices_host, visible_indices_capacity, result);
+}
+
+} // extern "C"

@@ -1,0 +1,79 @@
+// renderer_instance.hpp — host-side mirror of the reference's frame builder for the visibility path.
+//
+// Mirrors (same names, argument meaning and sequencing):
+//   ox::RendererInstance::update              Oxylus/src/Render/RendererInstance.cpp:1333-1788
+//   ox::RendererInstance::cull_geometry       Oxylus/src/Render/Passes/CullGeometry.cpp:61-404
+//   ox::RendererInstance::generate_hiz        Oxylus/src/Render/Passes/CullGeometry.cpp:10-59
+//   ox::RendererInstance::draw_for_visbuffer  Oxylus/src/Render/Passes/DrawGeometry.cpp:104-190
+//   the geometry section of ::render          Oxylus/src/Render/RendererInstance.cpp:768-926
+// The vuk::Value<Buffer|ImageAttachment> futures of the reference's context structs become plain device
+// pointers owned by this object; "recording a pass" becomes enqueuing liboxcull kernels on one stream.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../../include/oxcull.h"
+
+namespace ox {
+
+// RendererInstance.hpp:171-196
+struct CullGeometryContext {
+  bool use_hiz = false;
+  bool use_hpb = false;          // VSM page-bitmap path: out of scope; multi-view cull instead
+  bool init_cull_meshes = false; // run cull_meshes (allocates / zeroes visibility + dispatch buffers)
+  uint32_t cull_flags = OXC_CULL_TEST_ALL;
+  OxcCullCamera cull_camera = {};
+  bool materialize_indices = false; // also run cull_triangles -> reordered_indices + draw cmd (reference stage 3)
+};
+
+// RendererInstance.hpp:198-216 (attachments this path touches)
+struct MainGeometryContext {
+  uint32_t cull_flags = OXC_CULL_TEST_ALL;
+  OxcCullCamera cull_camera = {};
+  uint64_t* visbuffer_attachment = nullptr; // packed depth|data image (device), width x height
+  uint32_t width = 0, height = 0;
+};
+
+// Scene.cpp:1280-1290 RendererInstanceUpdateInfo (the fields this path consumes)
+struct RendererInstanceUpdateInfo {
+  uint32_t mesh_instance_count = 0;
+  uint32_t max_meshlet_instance_count = 0;
+  OxcSceneDesc scene = {};
+};
+
+class RendererInstance {
+public:
+  RendererInstance(int device, const OxcCreateInfo& info, uint32_t width, uint32_t height);
+  ~RendererInstance();
+  RendererInstance(const RendererInstance&) = delete;
+  RendererInstance& operator=(const RendererInstance&) = delete;
+
+  bool ok() const { return ctx_ != nullptr && error_.empty(); }
+  const std::string& error() const { return error_; }
+  OxcContext* context() const { return ctx_; }
+  void* stream() const { return stream_; }
+
+  auto update(const RendererInstanceUpdateInfo& info) -> int;
+  auto cull_geometry(CullGeometryContext& context) -> int;
+  auto generate_hiz(MainGeometryContext& context) -> int;
+  auto draw_for_visbuffer(MainGeometryContext& context) -> int;
+
+  // RendererInstance::render geometry section: run_geometry_pass(false) -> generate_hiz -> run_geometry_pass(true)
+  auto render(const OxcCullCamera& camera, const float* occluder_depth_host, uint32_t* vis32_host, float* depth_host,
+              uint32_t* visible_indices_host, uint32_t visible_indices_capacity, OxrFrameResult* result) -> int;
+
+private:
+  int fail(int rc);
+  OxcContext* ctx_ = nullptr;
+  void* stream_ = nullptr;
+  uint32_t width_ = 0, height_ = 0;
+  uint64_t* d_vis64_ = nullptr;
+  uint32_t* d_vis32_ = nullptr;
+  float* d_depth_ = nullptr;
+  float* d_occluder_ = nullptr;
+  void* h_pinned_ = nullptr; // staging for small readbacks
+  std::string error_;
+};
+
+} // namespace ox

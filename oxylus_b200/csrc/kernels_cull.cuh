@@ -1,0 +1,428 @@
+// kernels_cull.cuh — mesh-level cull + expansion, the two-pass meshlet cull, the multi-view cull.
+// Reference: Oxylus/src/Render/Shaders/passes/{cull_meshes,cull_meshlets_hiz,cull_meshlets,cull_meshlets_hpb}.slang
+#pragma once
+#include "oxc_exact.cuh"
+
+namespace oxc {
+
+constexpr int CULL_MESHES_THREADS = 256;
+constexpr int CULL_THREADS = 256;
+constexpr int CULL_ITEMS = 4;                          // meshlet instances per thread per tile
+constexpr int CULL_TILE = CULL_THREADS * CULL_ITEMS;   // 1024 per CTA iteration -> one atomic per 1024
+
+struct MeshesParams {
+  const OxcMesh* meshes;
+  OxcMeshInstance* mesh_instances;
+  const OxcTransformWorld* transforms;
+  InstCull* inst;
+  InstGeom* geom;
+  uint32_t* counts;      // per mesh instance of the shard (index - first)
+  uint32_t* block_sums;
+  uint32_t first, count; // shard
+  uint32_t flags;
+  int select;            // 1: full cull_meshes (frustum + LOD select + counts); 0: refresh InstCull for a new camera only
+  OxcCullCamera cam;
+};
+
+// cull_meshes.slang:17-61 — one thread per mesh instance of the shard.  Besides the reference's outputs
+// (lod_index write-back, meshlet count) it materialises InstCull / InstGeom for the later passes.
+__global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __grid_constant__ MeshesParams p) {
+  const uint32_t local = blockIdx.x * CULL_MESHES_THREADS + threadIdx.x;
+  uint32_t meshlet_count = 0;
+  if (local < p.count) {
+    const uint32_t mi = p.first + local;
+    OxcMeshInstance inst = p.mesh_instances[mi];
+    const OxcMesh* mesh = &p.meshes[inst.mesh_index];
+    const float* world = p.transforms[inst.transform_index].world;
+    float w[16];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(world) + k);
+      w[k * 4 + 0] = c.x; w[k * 4 + 1] = c.y; w[k * 4 + 2] = c.z; w[k * 4 + 3] = c.w;
+    }
+    float4 rows[4], planes[6];
+    mul_mm_rows(p.cam.projection_view, w, rows); // :32
+    frustum_planes(rows, planes);
+    const OxcMeshLOD* lods = reinterpret_cast<const OxcMeshLOD*>(mesh->lods);
+    uint32_t lod_index = inst.lod_index;
+    if (p.select) {
+      lod_index = 0;
+      const float bcx = mesh->bounds.aabb_center[0], bcy = mesh->bounds.aabb_center[1], bcz = mesh->bounds.aabb_center[2];
+      const float bex = mesh->bounds.aabb_extent[0], bey = mesh->bounds.aabb_extent[1], bez = mesh->bounds.aabb_extent[2];
+      if ((p.flags & OXC_CULL_TEST_FRUSTUM) && test_frustum_rows(planes, bcx, bcy, bcz, bex, bey, bez)) { // :34
+        if (p.flags & OXC_CULL_SELECT_LOD) { // :35-57
+          const float4 w0 = make_float4(w[0], w[4], w[8], w[12]), w1 = make_float4(w[1], w[5], w[9], w[13]),
+                       w2 = make_float4(w[2], w[6], w[10], w[14]);
+          const float cx = row_dot4(w0, bcx, bcy, bcz, 1.0f), cy = row_dot4(w1, bcx, bcy, bcz, 1.0f),
+                      cz = row_dot4(w2, bcx, bcy, bcz, 1.0f);
+          const float ex = fabsf(row_dot4(w0, bex, bey, bez, 0.0f)), ey = fabsf(row_dot4(w1, bex, bey, bez, 0.0f)),
+                      ez = fabsf(row_dot4(w2, bex, bey, bez, 0.0f));
+          const float rough_extent = omax(ex, omax(ey, ez));
+          const float dist = omax(fs(length3(fs(cx, p.cam.position[0]), fs(cy, p.cam.position[1]), fs(cz, p.cam.position[2])),
+                                     fm(0.5f, rough_extent)), 0.0f);
+          const float pixel_size_at_1m = fd(2.0f, omax(p.cam.resolution[0], p.cam.resolution[1]));
+          const float aabb_size_at_1m = fd(rough_extent, dist);
+          const float rough_pixel_size = fd(aabb_size_at_1m, pixel_size_at_1m);
+          for (uint32_t i = 1; i < mesh->lod_count; i++) {
+            const float err = fm(rough_pixel_size, lods[i].error);
+            if (err < p.cam.acceptable_lod_error) lod_index = i;
+            else break;
+          }
+        }
+        meshlet_count = lods[lod_index].meshlet_count; // :59
+      }
+      if (meshlet_count > 0) p.mesh_instances[mi].lod_index = lod_index; // :76
+      else lod_index = inst.lod_index;                                   // untouched when culled
+    } else {
+      meshlet_count = p.inst[mi].meshlet_count; // keep what the last cull_meshes decided
+    }
+    const OxcMeshLOD* lod = &lods[lod_index];
+    InstCull ic;
+#pragma unroll
+    for (int k = 0; k < 6; k++) ic.plane[k] = planes[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) ic.mvp_row[k] = rows[k];
+    ic.world_row[0] = make_float4(w[0], w[4], w[8], w[12]);
+    ic.world_row[1] = make_float4(w[1], w[5], w[9], w[13]);
+    ic.world_row[2] = make_float4(w[2], w[6], w[10], w[14]);
+    // scene.slang:291-298: basis[i] = column i of world3; r0 = cross(b1,b2), r1 = cross(b2,b0), r2 = cross(b0,b1)
+    const float b0x = w[0], b0y = w[1], b0z = w[2], b1x = w[4], b1y = w[5], b1z = w[6], b2x = w[8], b2y = w[9], b2z = w[10];
+#define OXC_CROSS(ax, ay, az, bx, by, bz) \
+  make_float4(fs(fm(ay, bz), fm(az, by)), fs(fm(az, bx), fm(ax, bz)), fs(fm(ax, by), fm(ay, bx)), 0.0f)
+    ic.nrm[0] = OXC_CROSS(b1x, b1y, b1z, b2x, b2y, b2z);
+    ic.nrm[1] = OXC_CROSS(b2x, b2y, b2z, b0x, b0y, b0z);
+    ic.nrm[2] = OXC_CROSS(b0x, b0y, b0z, b1x, b1y, b1z);
+#undef OXC_CROSS
+    // scene.slang:304-309 (Slang world[i] = row i)
+    ic.nrm[0].w = omax(length3(w[0], w[4], w[8]), omax(length3(w[1], w[5], w[9]), length3(w[2], w[6], w[10])));
+    const uint64_t baddr = lod->meshlet_bounds;
+    ic.bounds_lo = (uint32_t)baddr;
+    ic.bounds_hi = (uint32_t)(baddr >> 32);
+    ic.vis_offset = inst.meshlet_instance_visibility_offset;
+    ic.meshlet_count = meshlet_count;
+    p.inst[mi] = ic;
+    if (p.select) {
+      InstGeom g;
+      g.meshlets = reinterpret_cast<const OxcMeshlet*>(lod->meshlets);
+      g.local_triangle_indices = reinterpret_cast<const uint32_t*>(lod->local_triangle_indices);
+      g.indirect_vertex_indices = reinterpret_cast<const uint32_t*>(lod->indirect_vertex_indices);
+      g.vertex_positions = reinterpret_cast<const uint2*>(mesh->vertex_positions);
+      g.transform_index = inst.transform_index;
+      g.pad[0] = g.pad[1] = g.pad[2] = 0;
+      p.geom[mi] = g;
+      p.counts[local] = meshlet_count;
+    }
+  }
+  if (!p.select) return;
+  // block sum of meshlet counts (WaveActiveSum :64, one level up)
+  __shared__ uint32_t warp_sums[CULL_MESHES_THREADS / 32];
+  uint32_t v = meshlet_count;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+#pragma unroll
+    for (int k = 0; k < CULL_MESHES_THREADS / 32; k++) s += warp_sums[k];
+    p.block_sums[blockIdx.x] = s;
+  }
+}
+
+// exclusive scan of the per-block sums in one CTA; publishes the totals the reference accumulates with
+// atomics (cull_meshes.slang:66-72): visibility.total and cull_meshlets_cmd.x = ceil(total / 64).
+__global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t* block_sums, uint32_t n_blocks,
+                                                          OxcMeshletInstanceVisibility* vis,
+                                                          OxcDispatchIndirectCommand* cmd) {
+  __shared__ uint32_t warp_tot[32];
+  __shared__ uint32_t carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_blocks; base += 1024) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t v = i < n_blocks ? block_sums[i] : 0u;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+      if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+      uint32_t w = warp_tot[threadIdx.x], winc = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+        if (threadIdx.x >= o) winc += t;
+      }
+      warp_tot[threadIdx.x] = winc - w; // exclusive
+    }
+    __syncthreads();
+    const uint32_t carry = carry_s;
+    const uint32_t excl = carry + warp_tot[threadIdx.x >> 5] + inc - v;
+    if (i < n_blocks) block_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const uint32_t total = carry_s;
+    vis->total_visible_meshlet_instances = total;
+    vis->early_visible_meshlet_instances = 0;
+    vis->late_visible_meshlet_instances = 0;
+    cmd->x = (total + 63u) / 64u; // CULLING_MESHLET_COUNT, cull_meshes.slang:70-71
+    cmd->y = 1;
+    cmd->z = 1;
+  }
+}
+
+// cull_meshes.slang:74-84 — expansion.  Deterministic: ascending mesh instance, ascending meshlet.
+// One warp per mesh instance writes its run with coalesced 64-bit stores.
+__global__ void __launch_bounds__(CULL_MESHES_THREADS) k_expand_meshlet_instances(const uint32_t* __restrict__ counts,
+                                                                                 const uint32_t* __restrict__ block_offsets,
+                                                                                 uint32_t first, uint32_t count,
+                                                                                 OxcMeshletInstance* out) {
+  __shared__ uint32_t offs[CULL_MESHES_THREADS];
+  __shared__ uint32_t cnts[CULL_MESHES_THREADS];
+  __shared__ uint32_t warp_tot[CULL_MESHES_THREADS / 32];
+  const uint32_t local = blockIdx.x * CULL_MESHES_THREADS + threadIdx.x;
+  const uint32_t v = local < count ? counts[local] : 0u;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if ((threadIdx.x & 31) >= o) inc += t;
+  }
+  if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = inc;
+  __syncthreads();
+  uint32_t wbase = 0;
+  for (int k = 0; k < (int)(threadIdx.x >> 5); k++) wbase += warp_tot[k];
+  offs[threadIdx.x] = block_offsets[blockIdx.x] + wbase + inc - v;
+  cnts[threadIdx.x] = v;
+  __syncthreads();
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint2* o2 = reinterpret_cast<uint2*>(out);
+  for (uint32_t k = warp; k < CULL_MESHES_THREADS; k += CULL_MESHES_THREADS / 32) {
+    const uint32_t n = cnts[k];
+    if (n == 0) continue;
+    const uint32_t base = offs[k];
+    const uint32_t mi = first + blockIdx.x * CULL_MESHES_THREADS + k;
+    for (uint32_t j = lane; j < n; j += 32) o2[base + j] = make_uint2(mi, j);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The meshlet cull.  cull_meshlets_hiz.slang:19-88 (HIZ path) / cull_meshlets.slang:21-73 (plain).
+//   OCC  = HAS_FLAG(CULL_FLAGS, TestOcclusion)   (mask read/modify, :45-51,81-87)
+//   LATE = HAS_FLAG(CULL_FLAGS, LatePass)
+//   HIZ  = use_hiz: project_aabb + test_occlusion run when OCC || LATE (:61, any-bit HAS_FLAG)
+// Persistent CTAs walk tiles of 1024 meshlet instances; survivors are compacted with warp ballots and ONE
+// global atomic per tile (the reference issues three per surviving lane, :70-78).  Mask bits are updated
+// with a single XOR of the changed bits per touched word per warp (own bits only => race-free), instead
+// of one atomic or/and per lane (:81-87).
+// ------------------------------------------------------------------------------------------------
+template <bool HIZ, bool OCC, bool LATE>
+__global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_constant__ CullParams p) {
+  __shared__ uint32_t hiz_off[OXC_HIZ_MAX_LEVELS];
+  __shared__ uint32_t warp_cnt[CULL_THREADS / 32];
+  __shared__ uint32_t tile_base_s;
+  if (threadIdx.x < OXC_HIZ_MAX_LEVELS) hiz_off[threadIdx.x] = p.hiz.level_offset[threadIdx.x];
+  __syncthreads();
+  const uint32_t total = p.vis->total_visible_meshlet_instances; // :26
+  const uint32_t early_count = LATE ? p.vis->early_visible_meshlet_instances : 0u; // :73 (final: early kernel completed)
+  const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t n_tiles = (total + CULL_TILE - 1) / CULL_TILE;
+  const uint2* mi2 = reinterpret_cast<const uint2*>(p.meshlet_instances);
+
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t tile_first = tile * CULL_TILE;
+    uint2 mi[CULL_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CULL_ITEMS; k++) {
+      const uint32_t i = tile_first + k * CULL_THREADS + threadIdx.x;
+      mi[k] = i < total ? __ldg(&mi2[i]) : make_uint2(0xFFFFFFFFu, 0u);
+    }
+    uint32_t emit_bits = 0;
+#pragma unroll
+    for (int k = 0; k < CULL_ITEMS; k++) {
+      const bool valid = mi[k].x != 0xFFFFFFFFu;
+      bool visible = false, was_visible = true;
+      uint32_t word = 0xFFFFFFFFu, bit = 0;
+      if (valid) {
+        const InstCull* ic = p.inst + mi[k].x;
+        const uint4 tail = __ldg(reinterpret_cast<const uint4*>(&ic->bounds_lo));
+        if (OCC) { // :45-51
+          const uint32_t vi = tail.z + mi[k].y;
+          word = vi >> 5;
+          bit = 1u << (vi & 31);
+          was_visible = (p.mask[word] & bit) != 0; // plain load: only this thread ever changes this bit
+        }
+        visible = LATE ? true : was_visible; // :57
+        if (visible) {
+          const uint4* bptr = reinterpret_cast<const uint4*>(((uint64_t)tail.y << 32) | tail.x) + mi[k].y;
+          const uint4 b = __ldg(bptr); // MeshletBounds, one 128-bit load
+          // scene.slang:401-435 unpack: u16x3 center | i8x2 cone xy | u16x3 extent | i8 cone z | i8 cutoff
+          const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
+          const int axq = (int)(int8_t)((b.y >> 16) & 0xFF), ayq = (int)(int8_t)(b.y >> 24);
+          const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
+          const int azq = (int)(int8_t)((b.w >> 16) & 0xFF), cutq = (int)(int8_t)(b.w >> 24);
+          const float cutoff = s8_over_127(cutq);
+          // :58 cone
+          if (cutoff < 1.0f)
+            visible = cone_visible_positional(ic, cx, cy, cz, ex, ey, ez, s8_over_127(axq), s8_over_127(ayq),
+                                              s8_over_127(azq), cutoff, p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]);
+          // :59 frustum
+          visible = visible && test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
+          // :61-65 occlusion
+          if (HIZ && (OCC || LATE) && visible) {
+            ScreenAabb sa;
+            const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]),
+                         r3 = __ldg(&ic->mvp_row[3]);
+            if (project_aabb(r0, r1, r2, r3, p.near_clip, cx, cy, cz, ex, ey, ez, sa))
+              visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, hiz_off);
+          }
+        }
+      }
+      // :81-87 mask rewrite: XOR of the changed own bits, aggregated per word within the warp
+      if (OCC) {
+        const bool changed = valid && (visible != was_visible);
+        const uint32_t key = changed ? word : 0xFFFFFFFFu;
+        if (__any_sync(0xffffffffu, changed)) {
+          const uint32_t peers = __match_any_sync(0xffffffffu, key);
+          const uint32_t delta = __reduce_or_sync(peers, changed ? bit : 0u);
+          if (changed && lane == (uint32_t)(__ffs(peers) - 1)) atomicXor(&p.mask[word], delta);
+        }
+      }
+      if (visible && (!LATE || !was_visible)) emit_bits |= 1u << k; // :67
+    }
+    // ---- compaction: warp ballots -> CTA scan -> one atomic per tile ----
+    uint32_t my_off = 0, warp_total = 0;
+    uint32_t offs[CULL_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CULL_ITEMS; k++) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, (emit_bits >> k) & 1u);
+      offs[k] = warp_total + __popc(bal & ((1u << lane) - 1u));
+      warp_total += __popc(bal);
+    }
+    (void)my_off;
+    if (lane == 0) warp_cnt[warp] = warp_total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t s = 0;
+#pragma unroll
+      for (int w = 0; w < CULL_THREADS / 32; w++) { const uint32_t c = warp_cnt[w]; warp_cnt[w] = s; s += c; }
+      uint32_t base = 0;
+      if (s) {
+        if (!HIZ) base = atomicAdd(&p.tri_cmd->x, s);                                           // cull_meshlets.slang:64
+        else {
+          if (!LATE) base = atomicAdd(&p.vis->early_visible_meshlet_instances, s);             // :70
+          else base = atomicAdd(&p.vis->late_visible_meshlet_instances, s) + early_count;       // :72-73
+          atomicAdd(&p.tri_cmd->x, s);                                                          // :78
+        }
+      }
+      tile_base_s = base;
+    }
+    __syncthreads();
+    const uint32_t wbase = tile_base_s + warp_cnt[warp];
+#pragma unroll
+    for (int k = 0; k < CULL_ITEMS; k++)
+      if ((emit_bits >> k) & 1u)
+        p.visible_indices[wbase + offs[k]] = tile_first + k * CULL_THREADS + threadIdx.x + id_base; // :76
+    __syncthreads(); // warp_cnt / tile_base_s reuse
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Multi-view batched cull (reference analogue: cull_meshlets_hpb.slang:27-99 loops <=10 clipmaps per
+// meshlet).  Bounds are read ONCE per meshlet instance; per view: cone (directional, :53-54, or
+// positional) AND frustum against that view's planes.  Output bit v of view_bits[i], per-view counts.
+// ------------------------------------------------------------------------------------------------
+struct MultiViewParams {
+  const OxcMeshletInstance* meshlet_instances;
+  const InstCull* inst;             // view-independent terms (normal matrix, world rows, bounds ptr)
+  const InstPlanes* view_planes;    // [n_views][I]
+  const OxcMeshletInstanceVisibility* vis;
+  uint32_t* view_bits;
+  uint32_t* view_counts;
+  uint32_t n_views, inst_stride;
+  int directional;
+  float view_pos[OXC_MAX_VIEWS][4]; // camera.position per view (light direction when directional)
+};
+
+__global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets_multiview(const __grid_constant__ MultiViewParams p) {
+  __shared__ uint32_t cnt_s[OXC_MAX_VIEWS];
+  if (threadIdx.x < OXC_MAX_VIEWS) cnt_s[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t total = p.vis->total_visible_meshlet_instances;
+  const uint2* mi2 = reinterpret_cast<const uint2*>(p.meshlet_instances);
+  uint32_t local_cnt[OXC_MAX_VIEWS];
+#pragma unroll
+  for (int v = 0; v < OXC_MAX_VIEWS; v++) local_cnt[v] = 0;
+  for (uint32_t i = blockIdx.x * CULL_THREADS + threadIdx.x; i < total; i += gridDim.x * CULL_THREADS) {
+    const uint2 mi = __ldg(&mi2[i]);
+    const InstCull* ic = p.inst + mi.x;
+    const uint4 tail = __ldg(reinterpret_cast<const uint4*>(&ic->bounds_lo));
+    const uint4 b = __ldg(reinterpret_cast<const uint4*>(((uint64_t)tail.y << 32) | tail.x) + mi.y);
+    const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
+    const int axq = (int)(int8_t)((b.y >> 16) & 0xFF), ayq = (int)(int8_t)(b.y >> 24);
+    const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
+    const int azq = (int)(int8_t)((b.w >> 16) & 0xFF), cutq = (int)(int8_t)(b.w >> 24);
+    const float cutoff = s8_over_127(cutq);
+    const float ax = s8_over_127(axq), ay = s8_over_127(ayq), az = s8_over_127(azq);
+    float wax = 0.f, way = 0.f, waz = 0.f;
+    if (p.directional && cutoff < 1.0f) world_cone_axis(ic, ax, ay, az, wax, way, waz);
+    uint32_t bits = 0;
+    for (uint32_t v = 0; v < p.n_views; v++) {
+      bool vis = true;
+      if (cutoff < 1.0f) {
+        if (p.directional) vis = !(dot3(wax, way, waz, p.view_pos[v][0], p.view_pos[v][1], p.view_pos[v][2]) >= cutoff);
+        else vis = cone_visible_positional(ic, cx, cy, cz, ex, ey, ez, ax, ay, az, cutoff, p.view_pos[v][0],
+                                           p.view_pos[v][1], p.view_pos[v][2]);
+      }
+      if (vis) vis = test_frustum_planes(p.view_planes[(size_t)v * p.inst_stride + mi.x].plane, cx, cy, cz, ex, ey, ez);
+      if (vis) bits |= 1u << v;
+    }
+    p.view_bits[i] = bits;
+#pragma unroll
+    for (int v = 0; v < OXC_MAX_VIEWS; v++) local_cnt[v] += (bits >> v) & 1u;
+  }
+#pragma unroll
+  for (int v = 0; v < OXC_MAX_VIEWS; v++) {
+    uint32_t c = local_cnt[v];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&cnt_s[v], c);
+  }
+  __syncthreads();
+  if (threadIdx.x < OXC_MAX_VIEWS && cnt_s[threadIdx.x]) atomicAdd(&p.view_counts[threadIdx.x], cnt_s[threadIdx.x]);
+}
+
+// per view planes for the multi-view cull: planes of mul(view.projection_view, world)
+__global__ void k_prepare_view_planes(const OxcMeshInstance* __restrict__ mesh_instances,
+                                      const OxcTransformWorld* __restrict__ transforms, const OxcCullCamera* __restrict__ views,
+                                      uint32_t n_views, uint32_t first, uint32_t count, uint32_t inst_stride,
+                                      InstPlanes* out) {
+  const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+  if (local >= count) return;
+  const uint32_t mi = first + local;
+  const float* world = transforms[mesh_instances[mi].transform_index].world;
+  float w[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) w[k] = world[k];
+  for (uint32_t v = 0; v < n_views; v++) {
+    float pv[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) pv[k] = views[v].projection_view[k];
+    float4 rows[4], planes[6];
+    mul_mm_rows(pv, w, rows);
+    frustum_planes(rows, planes);
+    InstPlanes ip;
+#pragma unroll
+    for (int k = 0; k < 6; k++) ip.plane[k] = planes[k];
+    out[(size_t)v * inst_stride + mi] = ip;
+  }
+}
+
+} // namespace oxc

@@ -1,0 +1,277 @@
+// kernels_tri.cuh — per-triangle cull (+ index-buffer output) and the software visibility-buffer raster.
+// Reference: passes/cull_triangles.slang:27-90, passes/visbuffer_encode_ms.slang:110-171 (per-vertex
+// transform into shared memory, per-primitive cull), visbuffer.slang:49-79 (64-bit depth|data packing).
+// The raster itself has no reference implementation (HW rasteriser, DrawGeometry.cpp:104-190); its
+// specification is the comment block above raster_triangle() in oracle/oxc_oracle.c.
+#pragma once
+#include "oxc_exact.cuh"
+
+namespace oxc {
+
+constexpr int TRI_THREADS = 256;
+constexpr int TRI_WARPS = TRI_THREADS / 32;
+
+struct TriParams {
+  const OxcMeshletInstance* meshlet_instances;
+  const InstCull* inst;
+  const InstGeom* geom;
+  const OxcMeshletInstanceVisibility* vis;
+  const OxcDispatchIndirectCommand* tri_cmd;
+  const uint32_t* visible_indices;
+  const uint32_t* id_base;   // may be null; visible_indices already carry it, meshlet_instances is local
+  uint32_t late;             // 0: survivors [0,E); 1: [E,E+L)   (cull_triangles.slang:34-37)
+  // cull_triangles output
+  uint32_t* reordered_indices;
+  OxcDrawIndexedIndirectCommand* draw_cmd;
+  // raster output
+  unsigned long long* visbuf;
+  uint32_t width, height;
+  unsigned long long* tri_counter;
+};
+
+struct MeshletWork {
+  uint32_t data_id;    // global meshlet instance id (<< 8 | tri later)
+  uint32_t tri_count;
+  uint32_t tri_offset; // byte offset of the micro indices
+  const uint32_t* micro;
+};
+
+// Loads one surviving meshlet for a warp: resolves the pointer chase, transforms its <=64 vertices ONCE
+// (clip = mvp * (pos,1), visbuffer_encode_ms.slang:135-137 — same values cull_triangles.slang:62-66
+// recomputes per corner) into the warp's shared-memory slab.
+OXC_DI MeshletWork load_meshlet(const TriParams& p, uint32_t slot, uint32_t id_base, float4* clip_s, uint32_t lane) {
+  MeshletWork w;
+  const uint32_t gid = __ldg(&p.visible_indices[slot]);      // :44 (global id)
+  const uint32_t local = gid - id_base;
+  const uint2 mi = __ldg(reinterpret_cast<const uint2*>(p.meshlet_instances) + local); // :45
+  const InstGeom* g = p.geom + mi.x;
+  const InstCull* ic = p.inst + mi.x;
+  const uint4 m = __ldg(reinterpret_cast<const uint4*>(g->meshlets + mi.y)); // Meshlet, :49
+  const uint32_t vertex_offset = m.x, vertex_count = min(m.z, (uint32_t)OXC_MESHLET_MAX_VERTICES);
+  w.tri_offset = m.y;
+  w.tri_count = min(m.w, (uint32_t)OXC_MESHLET_MAX_PRIMITIVES);
+  w.micro = g->local_triangle_indices;
+  w.data_id = gid;
+  const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
+  const uint32_t* vidx = g->indirect_vertex_indices + vertex_offset;
+  const uint2* pos = g->vertex_positions;
+  for (uint32_t v = lane; v < vertex_count; v += 32) {
+    const uint32_t vi = __ldg(&vidx[v]);
+    const uint2 q = __ldg(&pos[vi]); // u16x4
+    const float x = dequantize_half(q.x & 0xFFFFu), y = dequantize_half(q.x >> 16), z = dequantize_half(q.y & 0xFFFFu);
+    clip_s[v] = make_float4(row_dot_p1(r0, x, y, z), row_dot_p1(r1, x, y, z), row_dot_p1(r2, x, y, z), row_dot_p1(r3, x, y, z));
+  }
+  __syncwarp();
+  return w;
+}
+
+// scene.slang:336-342 get_micro_index
+OXC_DI uint32_t micro_index(const uint32_t* __restrict__ buf, uint32_t byte_offset) {
+  return (__ldg(&buf[byte_offset >> 2]) >> ((byte_offset & 3u) * 8u)) & 0xFFu;
+}
+
+// cull_triangles.slang:59-69
+OXC_DI bool triangle_passes(const MeshletWork& w, uint32_t t, const float4* clip_s, float4& c0, float4& c1, float4& c2) {
+  const uint32_t base = w.tri_offset + t * 3u;
+  c0 = clip_s[micro_index(w.micro, base + 0u)];
+  c1 = clip_s[micro_index(w.micro, base + 1u)];
+  c2 = clip_s[micro_index(w.micro, base + 2u)];
+  const bool in_front = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f;
+  return in_front && !triangle_backface(c0, c1, c2);
+}
+
+// ---- cull_triangles: materialise the reference's reordered index buffer ----
+__global__ void __launch_bounds__(TRI_THREADS) k_cull_triangles(const __grid_constant__ TriParams p) {
+  __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
+  __shared__ uint32_t warp_cnt[TRI_WARPS];
+  __shared__ uint32_t base_s;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t first = p.late ? p.vis->early_visible_meshlet_instances : 0u; // cull_triangles.slang:34-37
+  const uint32_t count = p.tri_cmd->x;                                         // dispatch_indirect(cull_triangles_cmd), CullGeometry.cpp:365
+  const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
+  const uint32_t n_tiles = (count + TRI_WARPS - 1) / TRI_WARPS;
+  float4* clip_s = clip_all[warp];
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t g = tile * TRI_WARPS + warp;
+    bool pass[2] = {false, false};
+    uint32_t rank[2] = {0, 0}, wtotal = 0, data_id = 0;
+    if (g < count) {
+      const MeshletWork w = load_meshlet(p, first + g, id_base, clip_s, lane);
+      data_id = w.data_id;
+#pragma unroll
+      for (int k = 0; k < 2; k++) {
+        const uint32_t t = lane + 32u * k;
+        float4 c0, c1, c2;
+        pass[k] = t < w.tri_count && triangle_passes(w, t, clip_s, c0, c1, c2);
+        const uint32_t bal = __ballot_sync(0xffffffffu, pass[k]);
+        rank[k] = wtotal + __popc(bal & ((1u << lane) - 1u));
+        wtotal += __popc(bal);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) warp_cnt[warp] = wtotal;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t s = 0;
+#pragma unroll
+      for (int k = 0; k < TRI_WARPS; k++) { const uint32_t c = warp_cnt[k]; warp_cnt[k] = s; s += c; }
+      base_s = s ? atomicAdd(&p.draw_cmd->index_count, s * 3u) : 0u; // :78
+    }
+    __syncthreads();
+    const uint32_t wbase = base_s + warp_cnt[warp] * 3u;
+#pragma unroll
+    for (int k = 0; k < 2; k++)
+      if (pass[k]) {
+        const uint32_t t = lane + 32u * k, off = wbase + rank[k] * 3u, masked = data_id << OXC_VIS_PRIMITIVE_BITS; // :84-88
+        p.reordered_indices[off + 0] = masked | ((t * 3u + 0u) & OXC_VIS_PRIMITIVE_MASK);
+        p.reordered_indices[off + 1] = masked | ((t * 3u + 1u) & OXC_VIS_PRIMITIVE_MASK);
+        p.reordered_indices[off + 2] = masked | ((t * 3u + 2u) & OXC_VIS_PRIMITIVE_MASK);
+      }
+    __syncthreads();
+  }
+}
+
+// ---- software raster ----
+struct TriSetup {
+  int ax, ay, bx, by, cx, cy;   // 24.8 fixed point, a/b/c positively oriented (b,c swapped)
+  float za, zb, zc;
+  float fa_;                    // (float)area2
+  int px0, px1, py0, py1;
+  int bias;                     // bit0..2: edge biases (1 = -1)
+};
+
+OXC_DI long long orient2d(int ax, int ay, int bx, int by, int cx, int cy) {
+  return (long long)(bx - ax) * (long long)(cy - ay) - (long long)(by - ay) * (long long)(cx - ax);
+}
+OXC_DI int edge_bias_bit(int ax, int ay, int bx, int by) {
+  const int dx = bx - ax, dy = by - ay;
+  return ((dy > 0) || (dy == 0 && dx < 0)) ? 0 : 1;
+}
+
+// steps 2-4 of the raster spec; false = nothing to draw
+OXC_DI bool tri_setup(float4 c0, float4 c1, float4 c2, uint32_t W, uint32_t H, TriSetup& s) {
+  if (!(c0.w > 0.0f && c1.w > 0.0f && c2.w > 0.0f)) return false;
+  int fx[3], fy[3];
+  float z[3];
+  const float4 c[3] = {c0, c1, c2};
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const float rw = fd(1.0f, c[i].w);
+    const float nx = fm(c[i].x, rw), ny = fm(c[i].y, rw);
+    z[i] = fm(c[i].z, rw);
+    const float sx = fm(fa(fm(nx, 0.5f), 0.5f), (float)W), sy = fm(fa(fm(ny, 0.5f), 0.5f), (float)H);
+    const float qx = floorf(fa(fm(sx, 256.0f), 0.5f)), qy = floorf(fa(fm(sy, 256.0f), 0.5f));
+    if (!(fabsf(qx) <= 4194304.0f && fabsf(qy) <= 4194304.0f)) return false;
+    fx[i] = (int)qx;
+    fy[i] = (int)qy;
+  }
+  long long area2 = orient2d(fx[0], fy[0], fx[1], fy[1], fx[2], fy[2]);
+  if (area2 >= 0) return false;
+  s.ax = fx[0]; s.ay = fy[0]; s.bx = fx[2]; s.by = fy[2]; s.cx = fx[1]; s.cy = fy[1];
+  s.za = z[0]; s.zb = z[2]; s.zc = z[1];
+  s.fa_ = (float)(-area2);
+  const int minx = min(s.ax, min(s.bx, s.cx)), maxx = max(s.ax, max(s.bx, s.cx));
+  const int miny = min(s.ay, min(s.by, s.cy)), maxy = max(s.ay, max(s.by, s.cy));
+  s.px0 = max(0, (minx - 128 + 255) >> 8);
+  s.px1 = min((int)W - 1, (maxx - 128) >> 8);
+  s.py0 = max(0, (miny - 128 + 255) >> 8);
+  s.py1 = min((int)H - 1, (maxy - 128) >> 8);
+  if (s.px1 < s.px0 || s.py1 < s.py0) return false; // covers no sample centre (== small-primitive cull)
+  s.bias = edge_bias_bit(s.bx, s.by, s.cx, s.cy) | (edge_bias_bit(s.cx, s.cy, s.ax, s.ay) << 1) |
+           (edge_bias_bit(s.ax, s.ay, s.bx, s.by) << 2);
+  return true;
+}
+
+// steps 5-6 for one pixel
+OXC_DI void raster_pixel(const TriSetup& s, int px, int py, uint32_t data, unsigned long long* vis, uint32_t W) {
+  const int sx = px * 256 + 128, sy = py * 256 + 128;
+  const long long e0 = orient2d(s.bx, s.by, s.cx, s.cy, sx, sy);
+  const long long e1 = orient2d(s.cx, s.cy, s.ax, s.ay, sx, sy);
+  const long long e2 = orient2d(s.ax, s.ay, s.bx, s.by, sx, sy);
+  if ((e0 - (s.bias & 1)) < 0 || (e1 - ((s.bias >> 1) & 1)) < 0 || (e2 - ((s.bias >> 2) & 1)) < 0) return;
+  const float l1 = fd((float)e1, s.fa_), l2 = fd((float)e2, s.fa_);
+  const float zz = fa(fa(s.za, fm(l1, fs(s.zb, s.za))), fm(l2, fs(s.zc, s.za)));
+  if (!(zz >= 0.0f && zz <= 1.0f)) return;
+  uint32_t zb = __float_as_uint(zz);
+  zb = zb == 0x80000000u ? 0u : zb; // -0.0 -> +0.0 so unsigned order == depth order
+  const unsigned long long v = ((unsigned long long)zb << 32) | data;
+  unsigned long long* ptr = vis + (size_t)py * W + px;
+  if (v > *ptr) atomicMax(ptr, v); // reverse-Z GreaterOrEqual == max (visbuffer.slang:72-74 packing)
+}
+
+constexpr int RASTER_BIG_PIXELS = 64; // bbox area above which the whole warp rasterises the triangle together
+
+__global__ void __launch_bounds__(TRI_THREADS) k_raster_visbuffer(const __grid_constant__ TriParams p) {
+  __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t first = p.late ? p.vis->early_visible_meshlet_instances : 0u; // cull_triangles.slang:34-37
+  const uint32_t count = p.tri_cmd->x;                                         // dispatch_indirect(cull_triangles_cmd), CullGeometry.cpp:365
+  const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
+  float4* clip_s = clip_all[warp];
+  uint32_t kept = 0;
+  for (uint32_t g = blockIdx.x * TRI_WARPS + warp; g < count; g += gridDim.x * TRI_WARPS) {
+    const MeshletWork w = load_meshlet(p, first + g, id_base, clip_s, lane);
+    const uint32_t rounds = (w.tri_count + 31u) >> 5;
+    for (uint32_t k = 0; k < rounds; k++) {
+      const uint32_t t = lane + 32u * k;
+      float4 c0, c1, c2;
+      const bool pass = t < w.tri_count && triangle_passes(w, t, clip_s, c0, c1, c2);
+      kept += pass ? 1u : 0u;
+      TriSetup s;
+      const bool draw = pass && tri_setup(c0, c1, c2, p.width, p.height, s);
+      const uint32_t data = (w.data_id << OXC_VIS_PRIMITIVE_BITS) | (t & OXC_VIS_PRIMITIVE_MASK);
+      const int bw = draw ? s.px1 - s.px0 + 1 : 0, bh = draw ? s.py1 - s.py0 + 1 : 0;
+      const bool big = draw && (bw * bh > RASTER_BIG_PIXELS);
+      if (draw && !big)
+        for (int py = s.py0; py <= s.py1; py++)
+          for (int px = s.px0; px <= s.px1; px++) raster_pixel(s, px, py, data, p.visbuf, p.width);
+      // large triangles: broadcast the setup, all 32 lanes stride over the bounding box
+      uint32_t big_mask = __ballot_sync(0xffffffffu, big);
+      while (big_mask) {
+        const int src = __ffs(big_mask) - 1;
+        big_mask &= big_mask - 1;
+        TriSetup b;
+        b.ax = __shfl_sync(0xffffffffu, s.ax, src); b.ay = __shfl_sync(0xffffffffu, s.ay, src);
+        b.bx = __shfl_sync(0xffffffffu, s.bx, src); b.by = __shfl_sync(0xffffffffu, s.by, src);
+        b.cx = __shfl_sync(0xffffffffu, s.cx, src); b.cy = __shfl_sync(0xffffffffu, s.cy, src);
+        b.za = __shfl_sync(0xffffffffu, s.za, src); b.zb = __shfl_sync(0xffffffffu, s.zb, src);
+        b.zc = __shfl_sync(0xffffffffu, s.zc, src); b.fa_ = __shfl_sync(0xffffffffu, s.fa_, src);
+        b.px0 = __shfl_sync(0xffffffffu, s.px0, src); b.px1 = __shfl_sync(0xffffffffu, s.px1, src);
+        b.py0 = __shfl_sync(0xffffffffu, s.py0, src); b.py1 = __shfl_sync(0xffffffffu, s.py1, src);
+        b.bias = __shfl_sync(0xffffffffu, s.bias, src);
+        const uint32_t bdata = __shfl_sync(0xffffffffu, data, src);
+        const int ww = b.px1 - b.px0 + 1, n = ww * (b.py1 - b.py0 + 1);
+        for (int i = lane; i < n; i += 32) raster_pixel(b, b.px0 + i % ww, b.py0 + i / ww, bdata, p.visbuf, p.width);
+      }
+    }
+    __syncwarp(); // clip_s reuse
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
+  if (lane == 0 && kept) atomicAdd(p.tri_counter, (unsigned long long)kept);
+}
+
+// visbuffer_clear.slang:20-28 on the packed image: depth 0 | data ~0u
+__global__ void k_clear_visbuffer(unsigned long long* vis, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    vis[i] = (unsigned long long)OXC_VIS_CLEAR;
+}
+
+// occluder / external depth merge: vis = max(vis, asuint(depth)<<32 | ~0u)
+__global__ void k_merge_depth(unsigned long long* vis, const float* depth, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long v = ((unsigned long long)__float_as_uint(depth[i]) << 32) | OXC_VIS_CLEAR;
+    if (v > vis[i]) vis[i] = v;
+  }
+}
+
+// visbuffer.slang:67-70
+__global__ void k_resolve_visbuffer(const unsigned long long* vis, uint32_t* vis32, float* depth, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const unsigned long long v = vis[i];
+    if (vis32) vis32[i] = (uint32_t)(v & 0xFFFFFFFFull);
+    if (depth) depth[i] = __uint_as_float((uint32_t)(v >> 32));
+  }
+}
+
+} // namespace oxc

@@ -1,0 +1,602 @@
+// oxcull.cu — liboxcull.so: context management and the C ABI of include/oxcull.h.
+// Every entry point enqueues hand-written sm_100a kernels (kernels_*.cuh) on the caller's stream.
+// There is no CPU fallback: without a CUDA device oxc_create fails with OXC_E_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "kernels_cull.cuh"
+#include "kernels_hiz.cuh"
+#include "kernels_tri.cuh"
+
+using namespace oxc;
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CK(expr)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess) return fail(OXC_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCHED()                                                                                    \
+  do {                                                                                                \
+    g_launches.fetch_add(1, std::memory_order_relaxed);                                               \
+    cudaError_t e_ = cudaGetLastError();                                                              \
+    if (e_ != cudaSuccess) return fail(OXC_E_CUDA, "kernel launch: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+__global__ void k_rebase_meshes(OxcMesh* meshes, uint32_t n, uint64_t base) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  OxcMesh m = meshes[i];
+  m.vertex_positions += base;
+  m.lods += base;
+  OxcMeshLOD* lods = reinterpret_cast<OxcMeshLOD*>(m.lods);
+  for (uint32_t l = 0; l < m.lod_count && l < OXC_MESH_MAX_LODS; l++) {
+    OxcMeshLOD d = lods[l];
+    d.indices += base;
+    d.meshlets += base;
+    d.meshlet_bounds += base;
+    d.local_triangle_indices += base;
+    d.indirect_vertex_indices += base;
+    lods[l] = d;
+  }
+  meshes[i] = m;
+}
+
+__global__ void k_set_cmd3(OxcDispatchIndirectCommand* c, uint32_t x, uint32_t y, uint32_t z) { c->x = x; c->y = y; c->z = z; }
+__global__ void k_reset_draw_cmd(OxcDrawIndexedIndirectCommand* c) {
+  c->index_count = 0; c->instance_count = 1; c->first_index = 0; c->vertex_offset = 0; c->first_instance = 0;
+}
+__global__ void k_reset_visibility(OxcMeshletInstanceVisibility* v, OxcDispatchIndirectCommand* c) {
+  v->total_visible_meshlet_instances = 0; v->early_visible_meshlet_instances = 0; v->late_visible_meshlet_instances = 0;
+  c->x = 0; c->y = 1; c->z = 1;
+}
+
+uint32_t ilog2(uint32_t v) { uint32_t r = 0; while ((1u << r) < v) r++; return r; }
+bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
+
+} // namespace
+
+struct OxcContext {
+  int device = 0;
+  int sm_count = 0;
+  OxcCreateInfo info{};
+  // scene tables (device)
+  OxcMesh* d_meshes = nullptr;
+  OxcMeshInstance* d_mesh_instances = nullptr;
+  OxcTransformWorld* d_transforms = nullptr;
+  uint8_t* d_blob = nullptr;
+  uint32_t mesh_count = 0, mesh_instance_count = 0, transform_count = 0;
+  uint32_t mesh_cap = 0, transform_cap = 0;
+  uint64_t blob_cap = 0;
+  bool scene_set = false;
+  // per-instance caches
+  InstCull* d_inst = nullptr;
+  InstGeom* d_geom = nullptr;
+  uint32_t* d_counts = nullptr;
+  uint32_t* d_block_sums = nullptr;
+  // frame buffers
+  OxcMeshletInstance* d_meshlet_instances = nullptr;
+  uint32_t* d_visible = nullptr;
+  uint32_t* d_mask = nullptr;
+  uint32_t mask_words = 0;
+  OxcMeshletInstanceVisibility* d_vis = nullptr;
+  OxcDispatchIndirectCommand* d_cull_meshlets_cmd = nullptr;
+  OxcDispatchIndirectCommand* d_cull_triangles_cmd = nullptr;
+  OxcDrawIndexedIndirectCommand* d_draw_cmd = nullptr;
+  uint32_t* d_reordered = nullptr;
+  unsigned long long* d_tri_counter = nullptr;
+  // hiz
+  float* d_hiz = nullptr;
+  HizDesc hiz{};
+  uint32_t hiz_total = 0;
+  // camera the InstCull cache was built for
+  OxcCullCamera cached_cam{};
+  bool cache_valid = false;
+  // shard
+  uint32_t shard_first = 0, shard_count = 0xFFFFFFFFu;
+  const uint32_t* id_base = nullptr;
+  // multiview
+  InstPlanes* d_view_planes = nullptr;
+  OxcCullCamera* d_views = nullptr;
+  uint32_t* d_view_bits = nullptr;
+  uint32_t* d_view_counts = nullptr;
+  // launch shapes
+  int occ_cull[2][2][2] = {};
+  int occ_tri = 1, occ_raster = 1, occ_mv = 1;
+};
+
+namespace {
+
+template <typename T>
+int dalloc(T** p, size_t n) {
+  *p = nullptr;
+  if (n == 0) n = 1;
+  CK(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(T)));
+  return OXC_OK;
+}
+
+void shard_range(const OxcContext* c, uint32_t cam_count, uint32_t* first, uint32_t* count) {
+  uint32_t n = cam_count < c->mesh_instance_count ? cam_count : c->mesh_instance_count; // cull_meshes.slang:28
+  uint32_t lo = c->shard_first < n ? c->shard_first : n;
+  uint32_t hi = n;
+  if (c->shard_count != 0xFFFFFFFFu && (uint64_t)c->shard_first + c->shard_count < hi) hi = c->shard_first + c->shard_count;
+  if (hi < lo) hi = lo;
+  *first = lo;
+  *count = hi - lo;
+}
+
+bool same_camera(const OxcCullCamera& a, const OxcCullCamera& b) {
+  return memcmp(a.projection_view, b.projection_view, sizeof a.projection_view) == 0 &&
+         memcmp(a.position, b.position, sizeof a.position) == 0;
+}
+
+// (re)build InstCull for `cam` without touching LOD selection / counts
+int refresh_inst_cache(OxcContext* c, const OxcCullCamera* cam, cudaStream_t s) {
+  if (c->cache_valid && same_camera(c->cached_cam, *cam)) return OXC_OK;
+  if (!c->cache_valid) return fail(OXC_E_STATE, "oxc_cull_meshes must run before the meshlet/triangle passes");
+  MeshesParams p{};
+  p.meshes = c->d_meshes; p.mesh_instances = c->d_mesh_instances; p.transforms = c->d_transforms;
+  p.inst = c->d_inst; p.geom = c->d_geom; p.counts = c->d_counts; p.block_sums = c->d_block_sums;
+  shard_range(c, c->cached_cam.mesh_instance_count, &p.first, &p.count);
+  p.flags = 0; p.select = 0; p.cam = *cam;
+  if (p.count) {
+    k_cull_meshes<<<(p.count + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS, CULL_MESHES_THREADS, 0, s>>>(p);
+    LAUNCHED();
+  }
+  const uint32_t keep = c->cached_cam.mesh_instance_count;
+  c->cached_cam = *cam;
+  c->cached_cam.mesh_instance_count = keep;
+  return OXC_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* oxc_last_error(void) { return g_err; }
+uint64_t oxc_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* oxc_version(void) { return "oxcull 0.1 (sm_100a)"; }
+
+int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
+  if (!info || !out_ctx) return fail(OXC_E_INVALID, "null argument");
+  *out_ctx = nullptr;
+  int n_dev = 0;
+  if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0) {
+    cudaGetLastError();
+    return fail(OXC_E_NO_DEVICE, "no CUDA device: liboxcull has no CPU fallback");
+  }
+  if (device < 0 || device >= n_dev) return fail(OXC_E_INVALID, "device %d out of range (%d devices)", device, n_dev);
+  if (!is_pow2(info->hiz_width) || !is_pow2(info->hiz_height))
+    return fail(OXC_E_INVALID, "hiz extent must be a power of two per axis (RendererInstance.cpp:573-577)");
+  if (info->max_views > OXC_MAX_VIEWS) return fail(OXC_E_INVALID, "max_views > %d", OXC_MAX_VIEWS);
+  CK(cudaSetDevice(device));
+  OxcContext* c = new (std::nothrow) OxcContext();
+  if (!c) return fail(OXC_E_INVALID, "out of host memory");
+  c->device = device;
+  c->info = *info;
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  const uint32_t I = info->max_mesh_instances ? info->max_mesh_instances : 1;
+  const uint32_t N = info->max_meshlet_instances ? info->max_meshlet_instances : 1;
+  int rc;
+#define TRY(x) if ((rc = (x)) != OXC_OK) { oxc_destroy(c); return rc; }
+  TRY(dalloc(&c->d_mesh_instances, (size_t)I));
+  TRY(dalloc(&c->d_inst, (size_t)I));
+  TRY(dalloc(&c->d_geom, (size_t)I));
+  TRY(dalloc(&c->d_counts, (size_t)I));
+  TRY(dalloc(&c->d_block_sums, (size_t)(I + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS + 1));
+  TRY(dalloc(&c->d_meshlet_instances, (size_t)N));
+  TRY(dalloc(&c->d_visible, (size_t)N));
+  c->mask_words = (N + 31) / 32; // RendererInstance.cpp:1651
+  TRY(dalloc(&c->d_mask, (size_t)c->mask_words));
+  TRY(dalloc(&c->d_vis, 1));
+  TRY(dalloc(&c->d_cull_meshlets_cmd, 1));
+  TRY(dalloc(&c->d_cull_triangles_cmd, 1));
+  TRY(dalloc(&c->d_draw_cmd, 1));
+  TRY(dalloc(&c->d_tri_counter, 1));
+  if (info->alloc_reordered_indices) TRY(dalloc(&c->d_reordered, (size_t)N * OXC_MESHLET_MAX_PRIMITIVES * 3));
+  if (info->max_views > 1) {
+    TRY(dalloc(&c->d_view_planes, (size_t)I * info->max_views));
+    TRY(dalloc(&c->d_views, (size_t)OXC_MAX_VIEWS));
+    TRY(dalloc(&c->d_view_bits, (size_t)N));
+    TRY(dalloc(&c->d_view_counts, (size_t)OXC_MAX_VIEWS));
+  }
+  // Hi-Z pyramid: levels = min(floor(log2(max(w,h))) + 1, 13)  (Texture.hpp:144-146, RendererInstance.cpp:583-586)
+  {
+    uint32_t m = info->hiz_width > info->hiz_height ? info->hiz_width : info->hiz_height, levels = 0;
+    while (m) { levels++; m >>= 1; }
+    levels = levels < OXC_HIZ_MAX_LEVELS ? levels : OXC_HIZ_MAX_LEVELS;
+    uint32_t off = 0;
+    for (uint32_t l = 0; l < OXC_HIZ_MAX_LEVELS; l++) {
+      c->hiz.level_offset[l] = off;
+      if (l < levels) {
+        uint32_t mw = info->hiz_width >> l, mh = info->hiz_height >> l;
+        off += (mw < 1 ? 1 : mw) * (mh < 1 ? 1 : mh);
+      }
+    }
+    c->hiz.width = info->hiz_width; c->hiz.height = info->hiz_height; c->hiz.levels = levels;
+    c->hiz_total = off;
+    TRY(dalloc(&c->d_hiz, (size_t)off));
+    c->hiz.data = c->d_hiz;
+  }
+#undef TRY
+  CK(cudaMemset(c->d_mask, 0, (size_t)c->mask_words * 4));
+  CK(cudaMemset(c->d_hiz, 0, (size_t)c->hiz_total * 4));
+  CK(cudaMemset(c->d_vis, 0, sizeof(OxcMeshletInstanceVisibility)));
+  CK(cudaMemset(c->d_tri_counter, 0, 8));
+  OxcDispatchIndirectCommand one{0, 1, 1};
+  CK(cudaMemcpy(c->d_cull_meshlets_cmd, &one, sizeof one, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_cull_triangles_cmd, &one, sizeof one, cudaMemcpyHostToDevice));
+  OxcDrawIndexedIndirectCommand dc{0, 1, 0, 0, 0};
+  CK(cudaMemcpy(c->d_draw_cmd, &dc, sizeof dc, cudaMemcpyHostToDevice));
+#define OCC(dst, kern, threads) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(dst), kern, threads, 0))
+  OCC(c->occ_cull[0][0][0], (k_cull_meshlets<false, false, false>), CULL_THREADS);
+  OCC(c->occ_cull[0][0][1], (k_cull_meshlets<false, false, true>), CULL_THREADS);
+  OCC(c->occ_cull[0][1][0], (k_cull_meshlets<false, true, false>), CULL_THREADS);
+  OCC(c->occ_cull[0][1][1], (k_cull_meshlets<false, true, true>), CULL_THREADS);
+  OCC(c->occ_cull[1][0][0], (k_cull_meshlets<true, false, false>), CULL_THREADS);
+  OCC(c->occ_cull[1][0][1], (k_cull_meshlets<true, false, true>), CULL_THREADS);
+  OCC(c->occ_cull[1][1][0], (k_cull_meshlets<true, true, false>), CULL_THREADS);
+  OCC(c->occ_cull[1][1][1], (k_cull_meshlets<true, true, true>), CULL_THREADS);
+  OCC(c->occ_tri, k_cull_triangles, TRI_THREADS);
+  OCC(c->occ_raster, k_raster_visbuffer, TRI_THREADS);
+  OCC(c->occ_mv, k_cull_meshlets_multiview, CULL_THREADS);
+#undef OCC
+  *out_ctx = c;
+  return OXC_OK;
+}
+
+void oxc_destroy(OxcContext* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_meshes); cudaFree(c->d_mesh_instances); cudaFree(c->d_transforms); cudaFree(c->d_blob);
+  cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
+  cudaFree(c->d_meshlet_instances); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
+  cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
+  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_hiz);
+  cudaFree(c->d_view_planes); cudaFree(c->d_views); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts);
+  delete c;
+}
+
+int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
+  if (!c || !sc) return fail(OXC_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  if (sc->mesh_instance_count > c->info.max_mesh_instances)
+    return fail(OXC_E_CAPACITY, "mesh_instance_count %u > max_mesh_instances %u", sc->mesh_instance_count, c->info.max_mesh_instances);
+  if (sc->mesh_count == 0 || !sc->meshes || !sc->blob || !sc->transforms || (sc->mesh_instance_count && !sc->mesh_instances))
+    return fail(OXC_E_INVALID, "scene tables missing");
+  if (sc->mesh_count > c->mesh_cap) {
+    CK(cudaFree(c->d_meshes)); c->d_meshes = nullptr;
+    CK(cudaMalloc(&c->d_meshes, (size_t)sc->mesh_count * sizeof(OxcMesh)));
+    c->mesh_cap = sc->mesh_count;
+  }
+  if (sc->transform_count > c->transform_cap) {
+    CK(cudaFree(c->d_transforms)); c->d_transforms = nullptr;
+    CK(cudaMalloc(&c->d_transforms, (size_t)sc->transform_count * sizeof(OxcTransformWorld)));
+    c->transform_cap = sc->transform_count;
+  }
+  if (sc->blob_size > c->blob_cap) {
+    CK(cudaFree(c->d_blob)); c->d_blob = nullptr;
+    CK(cudaMalloc(&c->d_blob, (size_t)sc->blob_size));
+    c->blob_cap = sc->blob_size;
+  }
+  CK(cudaMemcpyAsync(c->d_meshes, sc->meshes, (size_t)sc->mesh_count * sizeof(OxcMesh), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->d_mesh_instances, sc->mesh_instances, (size_t)sc->mesh_instance_count * sizeof(OxcMeshInstance), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->d_transforms, sc->transforms, (size_t)sc->transform_count * sizeof(OxcTransformWorld), cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->d_blob, sc->blob, (size_t)sc->blob_size, cudaMemcpyHostToDevice, s));
+  // upload_gltf_mesh (AssetManager_GLTF.cpp:778-800): blob offsets -> device addresses
+  k_rebase_meshes<<<(sc->mesh_count + 127) / 128, 128, 0, s>>>(c->d_meshes, sc->mesh_count, reinterpret_cast<uint64_t>(c->d_blob));
+  LAUNCHED();
+  c->mesh_count = sc->mesh_count; c->mesh_instance_count = sc->mesh_instance_count; c->transform_count = sc->transform_count;
+  c->scene_set = true;
+  c->cache_valid = false;
+  // instance table changed => zero_fill_pass on the mask (RendererInstance.cpp:1651-1665)
+  CK(cudaMemsetAsync(c->d_mask, 0, (size_t)c->mask_words * 4, s));
+  return OXC_OK;
+}
+
+int oxc_update_transforms(OxcContext* c, const OxcTransformWorld* t, uint32_t first, uint32_t count, void* stream) {
+  if (!c || !t) return fail(OXC_E_INVALID, "null argument");
+  if (!c->scene_set) return fail(OXC_E_STATE, "oxc_set_scene first");
+  if ((uint64_t)first + count > c->transform_count) return fail(OXC_E_CAPACITY, "transform range out of bounds");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(c->d_transforms + first, t, (size_t)count * sizeof(OxcTransformWorld), cudaMemcpyHostToDevice,
+                     static_cast<cudaStream_t>(stream)));
+  c->cache_valid = false;
+  return OXC_OK;
+}
+
+int oxc_reset_visibility_mask(OxcContext* c, void* stream) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(c->d_mask, 0, (size_t)c->mask_words * 4, static_cast<cudaStream_t>(stream)));
+  return OXC_OK;
+}
+
+int oxc_clear_hiz(OxcContext* c, void* stream) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(c->d_hiz, 0, (size_t)c->hiz_total * 4, static_cast<cudaStream_t>(stream)));
+  return OXC_OK;
+}
+
+int oxc_set_shard(OxcContext* c, uint32_t first, uint32_t count, const uint32_t* id_base_dev) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  c->shard_first = first; c->shard_count = count; c->id_base = id_base_dev;
+  c->cache_valid = false;
+  return OXC_OK;
+}
+
+int oxc_cull_meshes(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, void* stream) {
+  if (!c || !cam) return fail(OXC_E_INVALID, "null argument");
+  if (!c->scene_set) return fail(OXC_E_STATE, "oxc_set_scene first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  MeshesParams p{};
+  p.meshes = c->d_meshes; p.mesh_instances = c->d_mesh_instances; p.transforms = c->d_transforms;
+  p.inst = c->d_inst; p.geom = c->d_geom; p.counts = c->d_counts; p.block_sums = c->d_block_sums;
+  shard_range(c, cam->mesh_instance_count, &p.first, &p.count);
+  p.flags = flags; p.select = 1; p.cam = *cam;
+  const uint32_t n_blocks = (p.count + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS;
+  if (n_blocks == 0) {
+    k_reset_visibility<<<1, 1, 0, s>>>(c->d_vis, c->d_cull_meshlets_cmd);
+    LAUNCHED();
+  } else {
+    k_cull_meshes<<<n_blocks, CULL_MESHES_THREADS, 0, s>>>(p);
+    LAUNCHED();
+    k_scan_block_sums<<<1, 1024, 0, s>>>(c->d_block_sums, n_blocks, c->d_vis, c->d_cull_meshlets_cmd);
+    LAUNCHED();
+    k_expand_meshlet_instances<<<n_blocks, CULL_MESHES_THREADS, 0, s>>>(c->d_counts, c->d_block_sums, p.first, p.count,
+                                                                      c->d_meshlet_instances);
+    LAUNCHED();
+  }
+  c->cached_cam = *cam;
+  c->cache_valid = true;
+  return OXC_OK;
+}
+
+int oxc_cull_meshlets(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, int use_hiz, void* stream) {
+  if (!c || !cam) return fail(OXC_E_INVALID, "null argument");
+  if (!c->scene_set) return fail(OXC_E_STATE, "oxc_set_scene first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  int rc = refresh_inst_cache(c, cam, s);
+  if (rc != OXC_OK) return rc;
+  k_set_cmd3<<<1, 1, 0, s>>>(c->d_cull_triangles_cmd, 0, 1, 1); // CullGeometry.cpp:125-127
+  LAUNCHED();
+  CullParams p{};
+  p.meshlet_instances = c->d_meshlet_instances; p.inst = c->d_inst; p.vis = c->d_vis; p.visible_indices = c->d_visible;
+  p.mask = c->d_mask; p.tri_cmd = c->d_cull_triangles_cmd; p.id_base = c->id_base; p.hiz = c->hiz;
+  p.cam_pos[0] = cam->position[0]; p.cam_pos[1] = cam->position[1]; p.cam_pos[2] = cam->position[2];
+  p.near_clip = cam->near_clip;
+  // the plain variant is dispatched with TestFrustum only (CullGeometry.cpp:275,298) and has no mask / late logic
+  const bool hizp = use_hiz != 0;
+  const bool occ = hizp && (flags & OXC_CULL_TEST_OCCLUSION) != 0;
+  const bool late = hizp && (flags & OXC_CULL_LATE_PASS) != 0;
+  const uint32_t tiles = (c->info.max_meshlet_instances + CULL_TILE - 1) / CULL_TILE;
+  int occn = c->occ_cull[hizp][occ][late];
+  uint32_t grid = (uint32_t)(c->sm_count * (occn > 0 ? occn : 1));
+  if (grid > tiles) grid = tiles;
+  if (grid == 0) grid = 1;
+#define GO(H, O, L) k_cull_meshlets<H, O, L><<<grid, CULL_THREADS, 0, s>>>(p)
+  if (hizp) {
+    if (occ) { if (late) GO(true, true, true); else GO(true, true, false); }
+    else { if (late) GO(true, false, true); else GO(true, false, false); }
+  } else {
+    GO(false, false, false);
+  }
+#undef GO
+  LAUNCHED();
+  return OXC_OK;
+}
+
+static int build_hiz_impl(OxcContext* c, const float* depth_dev, uint32_t stride, uint32_t offset, uint32_t width,
+                          uint32_t height, void* stream) {
+  if (!c || !depth_dev || !width || !height) return fail(OXC_E_INVALID, "bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  HizBuildParams p{};
+  p.depth = depth_dev; p.elem_stride = stride; p.elem_offset = offset; p.width = width; p.height = height; p.hiz = c->d_hiz;
+  p.hw = c->hiz.width; p.hh = c->hiz.height; p.levels = c->hiz.levels;
+  p.hw_shift = ilog2(p.hw); p.hh_shift = ilog2(p.hh);
+  memcpy(p.level_offset, c->hiz.level_offset, sizeof p.level_offset);
+  if (p.hw % 64 == 0 && p.hh % 64 == 0) {
+    k_hiz_tiles<<<dim3(p.hw / 64, p.hh / 64), 256, 0, s>>>(p);
+    LAUNCHED();
+    if (p.levels > 7) { k_hiz_tail<<<1, 1024, 0, s>>>(p, 7); LAUNCHED(); }
+  } else {
+    const uint32_t n = p.hw * p.hh;
+    k_hiz_mip0_generic<<<(n + 255) / 256, 256, 0, s>>>(p);
+    LAUNCHED();
+    if (p.levels > 1) { k_hiz_tail<<<1, 1024, 0, s>>>(p, 1); LAUNCHED(); }
+  }
+  return OXC_OK;
+}
+
+int oxc_build_hiz(OxcContext* c, const float* depth_dev, uint32_t width, uint32_t height, void* stream) {
+  return build_hiz_impl(c, depth_dev, 1, 0, width, height, stream);
+}
+
+// same pyramid straight from the packed 64-bit vis buffer (depth = high 32 bits, little endian): saves the
+// resolve pass between the early raster and generate_hiz
+int oxc_build_hiz_packed(OxcContext* c, const uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream) {
+  return build_hiz_impl(c, reinterpret_cast<const float*>(vis_dev), 2, 1, width, height, stream);
+}
+
+static int tri_common(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, cudaStream_t s, TriParams* p) {
+  if (!c->scene_set) return fail(OXC_E_STATE, "oxc_set_scene first");
+  int rc = refresh_inst_cache(c, cam, s);
+  if (rc != OXC_OK) return rc;
+  p->meshlet_instances = c->d_meshlet_instances; p->inst = c->d_inst; p->geom = c->d_geom; p->vis = c->d_vis;
+  p->visible_indices = c->d_visible; p->tri_cmd = c->d_cull_triangles_cmd; p->id_base = c->id_base; p->late = (flags & OXC_CULL_LATE_PASS) ? 1u : 0u;
+  p->reordered_indices = c->d_reordered; p->draw_cmd = c->d_draw_cmd; p->tri_counter = c->d_tri_counter;
+  return OXC_OK;
+}
+
+int oxc_cull_triangles(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, void* stream) {
+  if (!c || !cam) return fail(OXC_E_INVALID, "null argument");
+  if (!c->d_reordered) return fail(OXC_E_STATE, "context created without alloc_reordered_indices");
+  if (c->info.max_meshlet_instances > (1u << 24))
+    return fail(OXC_E_CAPACITY, "24-bit meshlet instance ids (visbuffer.slang:9-10) overflow above 2^24 instances");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  TriParams p{};
+  int rc = tri_common(c, cam, flags, s, &p);
+  if (rc != OXC_OK) return rc;
+  k_reset_draw_cmd<<<1, 1, 0, s>>>(c->d_draw_cmd); // CullGeometry.cpp:380-382
+  LAUNCHED();
+  uint32_t tiles = (c->info.max_meshlet_instances + TRI_WARPS - 1) / TRI_WARPS;
+  uint32_t grid = (uint32_t)(c->sm_count * (c->occ_tri > 0 ? c->occ_tri : 1));
+  if (grid > tiles) grid = tiles;
+  if (grid == 0) grid = 1;
+  k_cull_triangles<<<grid, TRI_THREADS, 0, s>>>(p);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+int oxc_clear_visbuffer(OxcContext* c, uint64_t* vis, uint32_t w, uint32_t h, void* stream) {
+  if (!c || !vis) return fail(OXC_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  const size_t n = (size_t)w * h;
+  k_clear_visbuffer<<<c->sm_count * 8, 256, 0, s>>>(reinterpret_cast<unsigned long long*>(vis), n);
+  LAUNCHED();
+  CK(cudaMemsetAsync(c->d_tri_counter, 0, 8, s));
+  return OXC_OK;
+}
+
+int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t w, uint32_t h, uint64_t* vis,
+                         int small_primitive_cull, void* stream) {
+  (void)small_primitive_cull; // triangles that cover no sample centre never reach the pixel loop either way
+  if (!c || !cam || !vis) return fail(OXC_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  TriParams p{};
+  int rc = tri_common(c, cam, flags, s, &p);
+  if (rc != OXC_OK) return rc;
+  p.visbuf = reinterpret_cast<unsigned long long*>(vis); p.width = w; p.height = h;
+  uint32_t tiles = (c->info.max_meshlet_instances + TRI_WARPS - 1) / TRI_WARPS;
+  uint32_t grid = (uint32_t)(c->sm_count * (c->occ_raster > 0 ? c->occ_raster : 1));
+  if (grid > tiles) grid = tiles;
+  if (grid == 0) grid = 1;
+  k_raster_visbuffer<<<grid, TRI_THREADS, 0, s>>>(p);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+int oxc_resolve_visbuffer(OxcContext* c, const uint64_t* vis, uint32_t w, uint32_t h, uint32_t* vis32, float* depth, void* stream) {
+  if (!c || !vis) return fail(OXC_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  k_resolve_visbuffer<<<c->sm_count * 8, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(vis), vis32, depth, (size_t)w * h);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+// internal helper exported for the host mirror: vis = max(vis, depth<<32 | ~0u)
+int oxc_merge_depth(OxcContext* c, uint64_t* vis, const float* depth_dev, uint32_t w, uint32_t h, void* stream) {
+  if (!c || !vis || !depth_dev) return fail(OXC_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  k_merge_depth<<<c->sm_count * 8, 256, 0, s>>>(reinterpret_cast<unsigned long long*>(vis), depth_dev, (size_t)w * h);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+int oxc_cull_meshlets_multiview(OxcContext* c, const OxcCullCamera* views, uint32_t n_views, int directional, void* stream) {
+  if (!c || !views || n_views == 0) return fail(OXC_E_INVALID, "bad argument");
+  if (n_views > c->info.max_views || !c->d_view_planes) return fail(OXC_E_CAPACITY, "n_views %u > max_views %u", n_views, c->info.max_views);
+  if (!c->scene_set || !c->cache_valid) return fail(OXC_E_STATE, "oxc_cull_meshes must run first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(c->d_views, views, (size_t)n_views * sizeof(OxcCullCamera), cudaMemcpyHostToDevice, s));
+  CK(cudaMemsetAsync(c->d_view_counts, 0, OXC_MAX_VIEWS * 4, s));
+  uint32_t first, count;
+  shard_range(c, c->cached_cam.mesh_instance_count, &first, &count);
+  const uint32_t stride = c->info.max_mesh_instances;
+  if (count) {
+    k_prepare_view_planes<<<(count + 127) / 128, 128, 0, s>>>(c->d_mesh_instances, c->d_transforms, c->d_views, n_views, first,
+                                                             count, stride, c->d_view_planes);
+    LAUNCHED();
+  }
+  MultiViewParams p{};
+  p.meshlet_instances = c->d_meshlet_instances; p.inst = c->d_inst; p.view_planes = c->d_view_planes; p.vis = c->d_vis;
+  p.view_bits = c->d_view_bits; p.view_counts = c->d_view_counts; p.n_views = n_views; p.inst_stride = stride;
+  p.directional = directional;
+  for (uint32_t v = 0; v < n_views; v++) {
+    p.view_pos[v][0] = views[v].position[0]; p.view_pos[v][1] = views[v].position[1]; p.view_pos[v][2] = views[v].position[2];
+    p.view_pos[v][3] = 0.f;
+  }
+  uint32_t blocks = (c->info.max_meshlet_instances + CULL_THREADS - 1) / CULL_THREADS;
+  uint32_t grid = (uint32_t)(c->sm_count * (c->occ_mv > 0 ? c->occ_mv : 1));
+  if (grid > blocks) grid = blocks;
+  if (grid == 0) grid = 1;
+  k_cull_meshlets_multiview<<<grid, CULL_THREADS, 0, s>>>(p);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+// plumbing helpers for hosts without their own CUDA bindings (ctypes tests, bench)
+int oxc_copy(OxcContext* c, void* dst, const void* src, uint64_t bytes, int kind, void* stream) {
+  if (!c || (!dst && bytes) || (!src && bytes)) return fail(OXC_E_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  const cudaMemcpyKind k = kind == 0 ? cudaMemcpyHostToDevice : kind == 1 ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+  if (bytes) CK(cudaMemcpyAsync(dst, src, (size_t)bytes, k, static_cast<cudaStream_t>(stream)));
+  return OXC_OK;
+}
+int oxc_sync(OxcContext* c, void* stream) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  return OXC_OK;
+}
+int oxc_device_alloc(OxcContext* c, uint64_t bytes, void** out) {
+  if (!c || !out) return fail(OXC_E_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMalloc(out, (size_t)(bytes ? bytes : 1)));
+  return OXC_OK;
+}
+int oxc_device_free(OxcContext* c, void* p) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaFree(p));
+  return OXC_OK;
+}
+
+int oxc_get_outputs(OxcContext* c, OxcOutputs* o) {
+  if (!c || !o) return fail(OXC_E_INVALID, "null argument");
+  memset(o, 0, sizeof *o);
+  o->visibility = c->d_vis; o->cull_meshlets_cmd = c->d_cull_meshlets_cmd; o->cull_triangles_cmd = c->d_cull_triangles_cmd;
+  o->draw_cmd = c->d_draw_cmd; o->meshlet_instances = c->d_meshlet_instances; o->visible_meshlet_instances_indices = c->d_visible;
+  o->meshlet_instance_visibility_mask = c->d_mask; o->reordered_indices = c->d_reordered; o->mesh_instances = c->d_mesh_instances;
+  o->hiz = c->d_hiz;
+  memcpy(o->hiz_level_offset, c->hiz.level_offset, sizeof o->hiz_level_offset);
+  o->hiz_levels = c->hiz.levels; o->hiz_width = c->hiz.width; o->hiz_height = c->hiz.height;
+  o->visibility_mask_words = c->mask_words;
+  o->view_visibility_bits = c->d_view_bits; o->view_visible_counts = c->d_view_counts;
+  o->raster_triangle_count = reinterpret_cast<uint64_t*>(c->d_tri_counter);
+  return OXC_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,271 @@
+"""CUDA path vs CPU oracle on the same seeded inputs, through the C ABI (include/oxcull.h).
+
+Bar (BASELINE.json north_star): bit-exact for integer outputs (meshlet_instances, survivor ID sets, visibility
+bitmask, triangle index sets, packed vis buffer) and for Hi-Z depths (min-only pyramid => exact, tolerance 0 ULP).
+Survivor / index ORDER is atomics-ordered in the reference => compared as sorted sets.
+"""
+import numpy as np
+import pytest
+
+from oxylus_b200 import abi, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from oxylus_b200 import capi
+
+    capi.load()
+    return capi
+
+
+def make_ctx(capi, sc, reordered=False, views=0):
+    hw, hh = sc.hiz_extent()
+    ctx = capi.Context(0, sc.mesh_instance_count, sc.max_meshlet_instance_count, hw, hh, alloc_reordered_indices=reordered,
+                       max_views=views)
+    ctx.set_scene(sc)
+    return ctx
+
+
+SCENES = {
+    "small": dict(n_meshlets=6000, width=640, height=360, n_unique_meshes=16),
+    "ragged_lods": dict(n_meshlets=9000, width=800, height=450, n_unique_meshes=24, max_lods=3, ragged=True),
+    "box": dict(n_meshlets=20000, width=1280, height=720, n_unique_meshes=32, placement="box"),
+    "medium": dict(n_meshlets=150000, width=1920, height=1080, n_unique_meshes=64),
+}
+
+
+@pytest.fixture(scope="module", params=list(SCENES))
+def scene(request):
+    return synth.make_scene(config_index=2, **SCENES[request.param])
+
+
+def test_cull_meshes_parity(capi, orc, scene):
+    hs = orc.HostScene(scene)
+    ctx = make_ctx(capi, scene)
+    for yaw in (0.0, 25.0):
+        cam = scene.camera(yaw)
+        mi_ref, vis_ref, cmd_ref = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+        ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+        vis = ctx.visibility()
+        total = int(vis_ref["total"][0])
+        assert int(vis["total"][0]) == total
+        assert int(ctx.cull_meshlets_cmd()["x"][0]) == int(cmd_ref["x"][0])
+        # deterministic expansion order == oracle's serial order: compare the arrays themselves
+        np.testing.assert_array_equal(ctx.meshlet_instances(total), mi_ref[:total])
+        np.testing.assert_array_equal(ctx.mesh_instances(scene.mesh_instance_count)["lod_index"], hs.mesh_instances["lod_index"])
+    ctx.close()
+
+
+def test_cull_meshes_flag_quirk(capi, orc, scene):
+    """without TestFrustum nothing is emitted (cull_meshes.slang:34 `HAS_FLAG(TestFrustum) && test_frustum`)"""
+    ctx = make_ctx(capi, scene)
+    ctx.cull_meshes(scene.camera(), abi.CULL_SELECT_LOD)
+    assert int(ctx.visibility()["total"][0]) == 0
+    ctx.close()
+
+
+def _frame_gpu(capi, ctx, sc, cam, occluder_dev, vis_dev, hiz_from_packed=True):
+    """early -> raster -> hiz -> late -> raster, low-level ABI calls.  Returns intermediates."""
+    w, h = sc.width, sc.height
+    ctx.clear_visbuffer(vis_dev, w, h)
+    ctx.clear_hiz()
+    if occluder_dev is not None:
+        ctx.merge_depth(vis_dev, occluder_dev, w, h)
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    ctx.cull_meshlets(cam, abi.CULL_TEST_ALL, True)
+    vis_e = ctx.visibility()
+    e = int(vis_e["early"][0])
+    mask_e = ctx.mask()
+    tcmd_e = int(ctx.cull_triangles_cmd()["x"][0])
+    ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+    if hiz_from_packed:
+        ctx.build_hiz_packed(vis_dev, w, h)
+    else:
+        depth_dev = ctx.alloc(w * h * 4)
+        ctx.resolve_visbuffer(vis_dev, w, h, None, depth_dev)
+        ctx.build_hiz(depth_dev, w, h)
+        ctx.sync()
+        ctx.free(depth_dev)
+    hiz = ctx.hiz_levels()
+    ctx.cull_meshlets(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, True)
+    vis_l = ctx.visibility()
+    l = int(vis_l["late"][0])
+    tcmd_l = int(ctx.cull_triangles_cmd()["x"][0])
+    ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, vis_dev)
+    img = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
+    return dict(early=e, late=l, mask_after_early=mask_e, mask=ctx.mask(), visible=ctx.visible_indices(e + l), hiz=hiz,
+                vis64=img, tcmd_early=tcmd_e, tcmd_late=tcmd_l, total=int(vis_l["total"][0]), ntri=ctx.raster_triangle_count())
+
+
+def test_two_pass_frames_parity(capi, orc, scene):
+    """three consecutive frames (camera yawing 2 deg / frame) — every intermediate of the two-pass pipeline."""
+    hs = orc.HostScene(scene)
+    ctx = make_ctx(capi, scene)
+    w, h = scene.width, scene.height
+    vis_dev = ctx.alloc(w * h * 8)
+    occ_dev = ctx.alloc(w * h * 4)
+    ctx.upload(occ_dev, scene.occluder_depth)
+    mask_ref = np.zeros(ctx.out.visibility_mask_words, dtype=np.uint32)
+    for f in range(3):
+        cam = scene.camera(2.0 * f)
+        ref = orc.frame(hs, cam, w, h, mask_ref, scene.occluder_depth)
+        got = _frame_gpu(capi, ctx, scene, cam, occ_dev, vis_dev, hiz_from_packed=(f != 1))
+        assert got["total"] == int(ref["visibility"]["total"][0])
+        assert got["early"] == ref["early"], f"frame {f}"
+        assert got["late"] == ref["late"], f"frame {f}"
+        assert got["tcmd_early"] == ref["early"] and got["tcmd_late"] == ref["late"]
+        np.testing.assert_array_equal(got["mask_after_early"], ref["mask_after_early"])
+        np.testing.assert_array_equal(got["mask"], mask_ref)
+        e, l = ref["early"], ref["late"]
+        np.testing.assert_array_equal(np.sort(got["visible"][:e]), np.sort(ref["visible"][:e]))
+        np.testing.assert_array_equal(np.sort(got["visible"][e:e + l]), np.sort(ref["visible"][e:e + l]))
+        for lvl in range(ref["hiz"].levels):  # Hi-Z depths: bit-exact (0 ULP)
+            np.testing.assert_array_equal(got["hiz"][lvl].view(np.uint32), ref["hiz"].level(lvl).view(np.uint32))
+        np.testing.assert_array_equal(got["vis64"], ref["vis64"])
+        assert got["ntri"] == ref["ntri_early"] + ref["ntri_late"]
+    ctx.free(vis_dev)
+    ctx.free(occ_dev)
+    ctx.close()
+
+
+def test_cull_meshlets_plain_parity(capi, orc, scene):
+    hs = orc.HostScene(scene)
+    ctx = make_ctx(capi, scene)
+    cam = scene.camera(10.0)
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    ref, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+    n = int(cmd["x"][0])
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, use_hiz=False)
+    assert int(ctx.cull_triangles_cmd()["x"][0]) == n
+    assert int(ctx.visibility()["early"][0]) == 0  # the plain variant never touches visibility (cull_meshlets.slang:55-70)
+    np.testing.assert_array_equal(np.sort(ctx.visible_indices(n)), np.sort(ref[:n]))
+    ctx.close()
+
+
+def test_cull_triangles_parity(capi, orc):
+    sc = synth.make_scene(config_index=3, **SCENES["ragged_lods"])
+    hs = orc.HostScene(sc)
+    ctx = make_ctx(capi, sc, reordered=True)
+    cam = sc.camera(5.0)
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    ref_vis, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+    n = int(cmd["x"][0])
+    ref_idx, ref_draw = orc.cull_triangles(hs, mi, ref_vis, 0, n, cam)
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, use_hiz=False)
+    ctx.cull_triangles(cam, abi.CULL_TEST_FRUSTUM)
+    dc = ctx.draw_cmd()
+    assert int(dc["index_count"][0]) == int(ref_draw["index_count"][0])
+    assert int(dc["instance_count"][0]) == 1
+    got = ctx.reordered_indices(int(dc["index_count"][0])).reshape(-1, 3)
+    # each triangle is three consecutive indices (instance<<8 | corner); order of triangles is atomics-ordered
+    order_g = np.argsort(got[:, 0], kind="stable")
+    order_r = np.argsort(ref_idx.reshape(-1, 3)[:, 0], kind="stable")
+    np.testing.assert_array_equal(got[order_g], ref_idx.reshape(-1, 3)[order_r])
+    ctx.close()
+
+
+def test_hiz_build_shapes(capi, orc):
+    """depth sizes whose Hi-Z extent differs from size/2 (point-sample mapping), incl. a sub-tile pyramid."""
+    rng = np.random.default_rng(7)
+    for (w, h) in [(1920, 1080), (3840, 2160), (640, 360), (100, 60), (64, 64), (1000, 520)]:
+        hw, hh = abi.hiz_extent(w, h)
+        depth = rng.random((h, w), dtype=np.float32)
+        ref = orc.build_hiz(depth, orc.Hiz(hw, hh))
+        ctx = capi.Context(0, 1, 1, hw, hh)
+        d_dev = ctx.alloc(w * h * 4)
+        ctx.upload(d_dev, depth)
+        ctx.build_hiz(d_dev, w, h)
+        got = ctx.hiz_levels()
+        assert len(got) == ref.levels
+        for lvl in range(ref.levels):
+            np.testing.assert_array_equal(got[lvl].view(np.uint32), ref.level(lvl).view(np.uint32), err_msg=f"{w}x{h} mip {lvl}")
+        ctx.free(d_dev)
+        ctx.close()
+
+
+def test_multiview_parity(capi, orc):
+    sc = synth.make_scene(40000, config_index=4, width=1280, height=720, n_unique_meshes=32, placement="box")
+    hs = orc.HostScene(sc)
+    ctx = make_ctx(capi, sc, views=16)
+    cam = sc.camera()
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    total = int(vis["total"][0])
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    dirs = synth.uniform(sc.seed, 90, 48, -1.0, 1.0).reshape(16, 3)
+    dirs[:, 1] = -np.abs(dirs[:, 1]) - 0.2
+    views = np.concatenate([synth.make_ortho_view(dirs[v], (0.0, 0.0, -200.0), 60.0 * (1 + v % 4), 800.0, sc.mesh_instance_count)
+                            for v in range(16)])
+    for directional in (1, 0):
+        ref_bits, ref_counts = orc.cull_meshlets_multiview(hs, mi, total, views, directional)
+        ctx.cull_meshlets_multiview(views, directional)
+        np.testing.assert_array_equal(ctx.view_bits(total), ref_bits)
+        np.testing.assert_array_equal(ctx.view_counts(), ref_counts)
+    # perspective cameras as views, positional cone: view 0 must equal the plain single-view cull
+    pviews = np.concatenate([sc.camera(3.0 * v) for v in range(8)])
+    ref_bits, ref_counts = orc.cull_meshlets_multiview(hs, mi, total, pviews, 0)
+    ctx.cull_meshlets_multiview(pviews, 0)
+    np.testing.assert_array_equal(ctx.view_bits(total), ref_bits)
+    ref_plain, cmd = orc.cull_meshlets(hs, mi, vis, sc.camera(0.0))
+    np.testing.assert_array_equal(np.nonzero(ref_bits & 1)[0], np.sort(ref_plain[: int(cmd["x"][0])]))
+    ctx.close()
+
+
+def test_renderer_host_mirror(capi, orc):
+    """oxr_render (C++ RendererInstance mirror, HOST in / HOST out) vs the oracle frame sequence."""
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    hs = orc.HostScene(sc)
+    r = capi.Renderer(0, sc, alloc_reordered_indices=True)
+    mask_ref = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    for f in range(3):
+        cam = sc.camera(-3.0 * f)
+        ref = orc.frame(hs, cam, sc.width, sc.height, mask_ref, sc.occluder_depth)
+        got = r.render(cam, sc.occluder_depth)
+        assert (got["total"], got["early"], got["late"]) == (int(ref["visibility"]["total"][0]), ref["early"], ref["late"])
+        v32, d = orc.resolve(ref["vis64"])
+        np.testing.assert_array_equal(got["vis32"], v32)
+        np.testing.assert_array_equal(got["depth"].view(np.uint32), d.view(np.uint32))
+        np.testing.assert_array_equal(np.sort(got["visible"]), np.sort(ref["visible"][: ref["early"] + ref["late"]]))
+        assert got["raster_triangles"] == ref["ntri_early"] + ref["ntri_late"]
+        assert got["draw_index_count_early"] == 3 * ref["ntri_early"] and got["draw_index_count_late"] == 3 * ref["ntri_late"]
+        np.testing.assert_array_equal(r.ctx.mask(), mask_ref)
+    r.close()
+
+
+def test_empty_and_edge_inputs(capi, orc):
+    """no survivors / camera looking away / single meshlet / zero mesh instances in the camera."""
+    sc = synth.make_scene(1, config_index=2, width=128, height=64, n_unique_meshes=1, meshlets_per_mesh=(1, 1))
+    ctx = make_ctx(capi, sc, reordered=True)
+    w, h = sc.width, sc.height
+    vis_dev = ctx.alloc(w * h * 8)
+    for yaw in (0.0, 180.0):
+        hs = orc.HostScene(sc)
+        cam = sc.camera(yaw)
+        mask_ref = np.zeros(ctx.out.visibility_mask_words, dtype=np.uint32)
+        ctx.reset_visibility_mask()
+        ref = orc.frame(hs, cam, w, h, mask_ref, None)
+        got = _frame_gpu(capi, ctx, sc, cam, None, vis_dev)
+        assert (got["total"], got["early"], got["late"]) == (int(ref["visibility"]["total"][0]), ref["early"], ref["late"])
+        np.testing.assert_array_equal(got["vis64"], ref["vis64"])
+        np.testing.assert_array_equal(got["mask"], mask_ref)
+    cam = sc.camera()
+    cam["mesh_instance_count"] = 0  # cull_meshes.slang:28
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    ctx.cull_meshlets(cam, abi.CULL_TEST_ALL, True)
+    ctx.cull_triangles(cam, abi.CULL_TEST_ALL)
+    assert int(ctx.visibility()["total"][0]) == 0 and int(ctx.draw_cmd()["index_count"][0]) == 0
+    ctx.free(vis_dev)
+    ctx.close()
+
+
+def test_call_sequence_errors(capi):
+    ctx = capi.Context(0, 4, 64, 64, 64)
+    cam = np.zeros(1, dtype=abi.CULL_CAMERA_DT)
+    with pytest.raises(capi.OxcError):
+        ctx.cull_meshes(cam)  # no scene
+    with pytest.raises(capi.OxcError):
+        capi.Context(0, 4, 64, 48, 64)  # non power-of-two hiz
+    ctx.close()
