@@ -1,0 +1,412 @@
+#!/usr/bin/env python
+"""bench.py — meshlet visibility pipeline on B200 (BASELINE.json metric: meshlets culled/s + tris rasterised/s,
+% of HBM roofline) with the CPU reference arm beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one frame of the hot path over the synthetic scene of BASELINE.json configs[1]
+("1M meshlet instances, 1 camera, two-pass Hi-Z occlusion cull"): clear attachments -> cull_meshes ->
+cull_meshlets(early) -> vis-buffer raster -> generate_hiz -> cull_meshlets(late) -> vis-buffer raster
+(RendererInstance.cpp:842-884).  N > 1: weak scaling, 1M meshlet instances PER GPU, mesh-instance sharded,
+with the real exchange steps (id-base allgather, vis-buffer max-reduce x2, survivor allgather) inside the step.
+
+value   : whole-job meshlet instances culled / s with inputs resident in HBM (CUDA-graph replay of one frame,
+          CUDA events per step on the launching stream, L2 flushed between steps, max over ranks)
+e2e     : same metric through the reference-facing host API oxr_render (C++ RendererInstance mirror) with HOST
+          buffers: camera + occluder depth H2D from pinned memory, vis32 + depth + survivor ids + counters D2H
+roofline: the late meshlet-cull kernel (cull_meshlets_hiz equivalent), algorithmic bytes of SURVEY.md §8d /
+          its CUDA-event duration inside the timed loop, against MEASURED_PEAKS.json hbm_gbs
+cpu_baseline / --impl reference: the oracle port of the same frame (oracle/, pthreads on all host cores) on a
+          bounded sample — the reference's own Vulkan path cannot be built or run here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "meshlet_instances_culled_per_s"
+UNIT = "meshlet instances/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--meshlets", type=int, default=1_000_000, help="meshlet instances per GPU")
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-frames", type=int, default=2)
+    return ap.parse_args()
+
+
+def measured_peak_hbm():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu = gpu_index
+        self.samples, self.proc, self.thread = [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+
+    pyoracle.lib()
+    return pyoracle
+
+
+def cpu_frames(scene, n_frames, n_threads):
+    """The oracle port of the frame on the host cores (cpu_baseline / reference arm).  Returns (seconds per frame, info)."""
+    orc = load_oracle()
+    hs = orc.HostScene(scene)
+    mask = np.zeros((scene.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    # one untimed frame to bring the mask to steady state (frame 0 has no early survivors)
+    orc.cpu_frame(hs, scene.camera(0.0), scene.width, scene.height, mask, scene.occluder_depth, n_threads)
+    times, last = [], None
+    for f in range(n_frames):
+        cam = scene.camera(2.0 * ((f + 1) % 2))
+        t0 = time.perf_counter()
+        last = orc.cpu_frame(hs, cam, scene.width, scene.height, mask, scene.occluder_depth, n_threads)
+        times.append(time.perf_counter() - t0)
+    return float(np.mean(times)), last
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path = the oracle port (kind "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oxylus_b200 import synth
+
+    cores = os.cpu_count() or 1
+    scene = synth.make_scene(args.meshlets * max(1, args.gpus), config_index=2, width=args.width, height=args.height)
+    # bounded sample: every step is one full frame of the same scene on all host threads
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_frames(scene, 1, cores)
+    n = max(1, min(args.steps, 4))
+    sec, last = cpu_frames(scene, n, cores)
+    value = scene.max_meshlet_instance_count / sec
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 1),
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, scene),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{n} full frames of the {scene.max_meshlet_instance_count}-meshlet scene, oracle port, pthreads"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "triangles_per_s": (last["triangles"] / sec) if last else None,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, scene):
+    return {"workload": "BASELINE.json configs[1]: 1M meshlet instances per GPU, 1 camera, two-pass Hi-Z occlusion cull + vis-buffer raster",
+            "meshlet_instances_per_gpu": args.meshlets, "resolution": [args.width, args.height],
+            "hiz": list(scene.hiz_extent()), "mesh_instances": scene.mesh_instance_count, "unique_meshes": len(scene.meshes),
+            "l2": "flushed between timed steps (256 MiB write, untimed)", "cameras": "yaw 0 / 2 deg alternating, steady-state mask",
+            "parallelism": f"mesh-instance shards x{args.gpus}" if args.gpus > 1 else "single GPU"}
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    from oxylus_b200 import abi, capi, dist as oxdist, pipeline, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    multi = world > 1
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if multi:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    n_gpus = world
+    capi.load(build_if_missing=False)
+
+    # ---------------- scene ----------------
+    total_meshlets = args.meshlets * n_gpus
+    scene = synth.make_scene(total_meshlets, config_index=2, width=args.width, height=args.height)
+    shard = None
+    if multi:
+        parts = oxdist.partition_mesh_instances(oxdist.lod0_counts_of(scene), world)
+        shard = parts[rank]
+    pipe = pipeline.VisibilityPipeline(scene, device=local_rank, shard=shard)
+    cams = [scene.camera(0.0), scene.camera(2.0)]
+    dev = pipe.device
+    w, h = scene.width, scene.height
+
+    # multi-GPU exchange state
+    hooks = {}
+    if multi:
+        lod0 = oxdist.lod0_counts_of(scene)
+        cap = max(int(lod0[f:f + c].sum()) for f, c in parts)
+        total_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        count_t = torch.zeros(1, dtype=torch.int32, device=dev)
+        ids_t = torch.zeros(cap, dtype=torch.int32, device=dev)
+        out = pipe.ctx.out
+
+        def after_cull_meshes():
+            pipe.ctx.lib.oxc_copy(pipe.ctx.h, total_t.data_ptr(), out.visibility, 4, 2, pipe.ctx.stream)
+            oxdist.exchange_id_base(total_t, pipe.id_base)
+
+        def between_passes():
+            oxdist.reduce_visbuffer(pipe.vis64)
+
+        def after_frame():
+            oxdist.reduce_visbuffer(pipe.vis64)
+            # survivors: early + late counts -> one count, ids from the context buffer
+            vis_t = torch.empty(3, dtype=torch.int32, device=dev)
+            pipe.ctx.lib.oxc_copy(pipe.ctx.h, vis_t.data_ptr(), out.visibility, 12, 2, pipe.ctx.stream)
+            count_t.copy_(vis_t[1:2] + vis_t[2:3])
+            pipe.ctx.lib.oxc_copy(pipe.ctx.h, ids_t.data_ptr(), out.visible_meshlet_instances_indices, cap * 4, 2, pipe.ctx.stream)
+            hooks["gathered"] = oxdist.gather_survivors(ids_t, count_t)
+
+        hooks = dict(after_cull_meshes=after_cull_meshes, between_passes=between_passes, after_frame=after_frame)
+
+    def barrier():
+        if multi:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- warm-up (also brings the visibility mask to steady state) ----------------
+    W = max(3, args.warmup)
+    K = max(1, args.steps)
+    for i in range(W):
+        pipe.frame(cams[i % 2], **hooks)
+    torch.cuda.synchronize()
+
+    # ---------------- CUDA graphs of one frame per camera ----------------
+    graphs = None
+    if not args.no_graph and not multi:
+        graphs = []
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            pipe.use_torch_stream()
+            for cam in cams:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, stream=side):
+                    pipe.use_torch_stream()
+                    pipe.frame(cam)
+                graphs.append(g)
+        torch.cuda.current_stream().wait_stream(side)
+        pipe.use_torch_stream()
+        for i in range(2):
+            graphs[i % 2].replay()
+        torch.cuda.synchronize()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step(i, mark=None):
+        if graphs is not None and mark is None:
+            graphs[i % 2].replay()
+        else:
+            pipe.frame(cams[i % 2], mark=mark, **hooks)
+
+    # ---------------- timed region: exactly K steps ----------------
+    sampler = ClockSampler(local_rank)
+    launches0 = capi.kernel_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.fill_(i & 0xFF)  # L2 flush, outside the per-step event pair
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    ms_per_step = float(np.mean(step_ms))
+    if graphs is not None:
+        launches_per_step = None  # replayed nodes are counted below from an eager frame
+    launches_timed = capi.kernel_launch_count() - launches0
+    cnt = pipe.counters()
+
+    # ---------------- per-kernel durations (same steps, eager launches, one CUDA event after every stage) ----------------
+    stage_names = ["begin"] + pipeline.STAGES
+    stage_acc = {n: [] for n in pipeline.STAGES}
+    stage_acc["clear"] = []
+    l0 = capi.kernel_launch_count()
+    for i in range(K):
+        flush.fill_(i & 0xFF)
+        marks = {}
+
+        def mark(name):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks[name] = e
+
+        s0 = torch.cuda.Event(enable_timing=True)
+        s0.record()
+        step(i, mark=mark)
+        torch.cuda.synchronize()
+        stage_acc["clear"].append(s0.elapsed_time(marks["begin"]))
+        for a, b in zip(stage_names[:-1], stage_names[1:]):
+            stage_acc[b].append(marks[a].elapsed_time(marks[b]))
+    launches_per_frame = (capi.kernel_launch_count() - l0) // K
+    stages_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
+    cnt_late = pipe.counters()
+
+    # max over ranks
+    if multi:
+        t = torch.tensor([ms_per_step], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_per_step = float(t.item())
+        tot = torch.tensor([cnt["total"], cnt["triangles"]], dtype=torch.float64, device=dev)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        job_meshlets, job_tris = float(tot[0].item()), float(tot[1].item())
+    else:
+        job_meshlets, job_tris = float(cnt["total"]), float(cnt["triangles"])
+    value = job_meshlets / (ms_per_step * 1e-3)
+
+    # ---------------- roofline of the dominant cull kernel (late pass: every meshlet instance fully tested) ----------------
+    peak, peak_src = measured_peak_hbm()
+    N_local = cnt_late["total"]
+    I_local = shard[1] if shard else scene.mesh_instance_count
+    M_bits = scene.max_meshlet_instance_count
+    S_late = cnt_late["late"]
+    algo_bytes = N_local * 24 + 2 * 4 * ((M_bits + 31) // 32) + 4 * S_late + I_local * 84 + len(scene.meshes) * 128
+    t_late = stages_ms["cull_late"] * 1e-3
+    achieved = algo_bytes / t_late / 1e9 if t_late > 0 else 0.0
+    traffic = None
+    prof = os.path.join(ROOT, "profiles", "ncu_cull_late_summary.json")
+    if os.path.exists(prof):
+        try:
+            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k_cull_meshlets<HIZ,OCC,LATE> (late pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": stages_ms["cull_late"],
+                "meshlets_per_s_kernel": N_local / t_late if t_late > 0 else None,
+                "note": "algorithmic bytes = N*24 + 8*ceil(M/32) + 4*S + I*84 + U*128 (SURVEY 8d, Hi-Z bytes excluded); "
+                        "256 unique meshes => bounds are L2-resident and the kernel is issue-bound (DESIGN.md)"}
+
+    # ---------------- e2e through the reference-facing host API with HOST buffers ----------------
+    e2e = None
+    if not args.no_e2e and not multi:
+        r = capi.Renderer(local_rank, scene)
+        pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
+        occ_pinned = pin((h, w), torch.float32)
+        occ_pinned[...] = scene.occluder_depth
+        outbuf = dict(vis32=pin((h, w), torch.int32).view(np.uint32), depth=pin((h, w), torch.float32),
+                      idx=pin((max(1, scene.max_meshlet_instance_count),), torch.int32).view(np.uint32))
+        for i in range(W):
+            res = r.render(cams[i % 2], occ_pinned, out=outbuf)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            res = r.render(cams[i % 2], occ_pinned, out=outbuf)  # synchronous: returns with results in host memory
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / K
+        h2d = 96 + occ_pinned.nbytes
+        d2h = outbuf["vis32"].nbytes + outbuf["depth"].nbytes + 4 * (res["early"] + res["late"]) + 12 + 8 + 8
+        e2e = {"value": res["total"] / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": e2e_s * 1e3, "api": "oxr_render (C++ ox::RendererInstance mirror over the C ABI), pinned host buffers"}
+        r.close()
+    elif multi:
+        e2e = None
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
+    cpu_baseline = None
+    if not args.no_cpu and not multi and rank == 0:
+        cores = os.cpu_count() or 1
+        sec, last = cpu_frames(scene, args.cpu_frames, cores)
+        cpu_baseline = {"value": scene.max_meshlet_instance_count / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{args.cpu_frames} full frames of the same {scene.max_meshlet_instance_count}-meshlet scene "
+                                  f"(oracle port of the reference shaders, pthreads x{cores}); {sec * 1e3:.0f} ms/frame",
+                        "triangles_per_s": last["triangles"] / sec}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(args, scene),
+            "triangles_rasterised_per_s": job_tris / (ms_per_step * 1e-3),
+            "per_frame": {"meshlet_instances": job_meshlets, "early_survivors": cnt["early"], "late_survivors": cnt["late"],
+                          "triangles_rasterised": job_tris},
+            "stages_ms": stages_ms, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
+            "gpu_launches": int(launches_per_frame * K), "gpu_launches_per_step": int(launches_per_frame),
+            "cuda_graph": graphs is not None, "wall_s_timed_region": t_wall,
+        }
+        print(json.dumps(line))
+    pipe.close()
+    if multi:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

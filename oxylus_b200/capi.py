@@ -292,12 +292,16 @@ class Renderer:
         _check(self.lib.oxr_update(self.h, C.byref(desc)), "oxr_update")
         self.ctx = Context.from_handle(self.lib.oxr_context(self.h))
 
-    def render(self, cam, occluder_depth=None, want_image=True, want_indices=True):
+    def render(self, cam, occluder_depth=None, want_image=True, want_indices=True, out=None):
+        """out: optional dict(vis32=, depth=, idx=) of preallocated (e.g. pinned) host arrays to fill."""
         sc = self.scene
-        vis32 = np.empty((sc.height, sc.width), dtype=np.uint32) if want_image else None
-        depth = np.empty((sc.height, sc.width), dtype=np.float32) if want_image else None
-        idx = np.empty(max(1, sc.max_meshlet_instance_count), dtype=np.uint32) if want_indices else None
-        occ = np.ascontiguousarray(occluder_depth, dtype=np.float32) if occluder_depth is not None else None
+        out = out or {}
+        vis32 = out.get("vis32", np.empty((sc.height, sc.width), dtype=np.uint32) if want_image else None)
+        depth = out.get("depth", np.empty((sc.height, sc.width), dtype=np.float32) if want_image else None)
+        idx = out.get("idx", np.empty(max(1, sc.max_meshlet_instance_count), dtype=np.uint32) if want_indices else None)
+        occ = occluder_depth
+        if occ is not None and not (isinstance(occ, np.ndarray) and occ.dtype == np.float32 and occ.flags.c_contiguous):
+            occ = np.ascontiguousarray(occ, dtype=np.float32)
         res = abi.FrameResult()
         _check(self.lib.oxr_render(self.h, _ptr(cam), _ptr(occ), _ptr(vis32), _ptr(depth), _ptr(idx),
                                    len(idx) if idx is not None else 0, C.byref(res)), "oxr_render")

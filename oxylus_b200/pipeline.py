@@ -1,0 +1,79 @@
+"""Python host for the device-resident frame loop (bench.py `value`, multi-GPU sharding).
+
+Sequencing mirrors RendererInstance::render's geometry section (RendererInstance.cpp:842-884):
+    cull_meshes -> cull_meshlets(early) -> vis encode -> generate_hiz -> cull_meshlets(late) -> vis encode
+All compute goes through the C ABI (capi.Context) on torch's current CUDA stream; torch only provides device
+memory, streams, events and (N > 1) torch.distributed.
+"""
+import numpy as np
+import torch
+
+from . import abi, capi
+
+STAGES = ["cull_meshes", "cull_early", "raster_early", "hiz", "cull_late", "raster_late"]
+
+
+class VisibilityPipeline:
+    def __init__(self, scene, device=0, shard=None, alloc_reordered_indices=False):
+        self.scene = scene
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        hw, hh = scene.hiz_extent()
+        self.ctx = capi.Context(device, max(1, scene.mesh_instance_count), max(1, scene.max_meshlet_instance_count), hw, hh,
+                                alloc_reordered_indices=alloc_reordered_indices, stream=0)
+        self.ctx.set_scene(scene)
+        self.w, self.h = scene.width, scene.height
+        self.vis64 = torch.empty((self.h, self.w), dtype=torch.int64, device=self.device)
+        self.occluder = None
+        if scene.occluder_depth is not None:
+            self.occluder = torch.from_numpy(np.ascontiguousarray(scene.occluder_depth)).to(self.device)
+        self.id_base = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if shard is not None:
+            self.ctx.set_shard(shard[0], shard[1], self.id_base.data_ptr())
+        self.use_torch_stream()
+
+    def use_torch_stream(self):
+        self.ctx.stream = torch.cuda.current_stream(self.device).cuda_stream
+
+    def close(self):
+        self.ctx.close()
+
+    # --- one frame; `mark(name)` is called after each stage (records a CUDA event in bench.py) ---
+    def frame(self, cam, mark=None, after_cull_meshes=None, between_passes=None, after_frame=None):
+        c, w, h = self.ctx, self.w, self.h
+        v = self.vis64.data_ptr()
+        c.clear_visbuffer(v, w, h)
+        c.clear_hiz()
+        if self.occluder is not None:
+            c.merge_depth(v, self.occluder.data_ptr(), w, h)
+        if mark:
+            mark("begin")
+        c.cull_meshes(cam, abi.CULL_TEST_ALL)
+        if after_cull_meshes:
+            after_cull_meshes()  # multi-GPU: exchange emitted counts -> this rank's global id base
+        if mark:
+            mark("cull_meshes")
+        c.cull_meshlets(cam, abi.CULL_TEST_ALL, True)
+        if mark:
+            mark("cull_early")
+        c.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, v)
+        if mark:
+            mark("raster_early")
+        if between_passes:
+            between_passes()  # multi-GPU: vis-buffer max-reduce so every rank builds the same Hi-Z
+        c.build_hiz_packed(v, w, h)
+        if mark:
+            mark("hiz")
+        c.cull_meshlets(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, True)
+        if mark:
+            mark("cull_late")
+        c.raster_visbuffer(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, v)
+        if mark:
+            mark("raster_late")
+        if after_frame:
+            after_frame()
+
+    def counters(self):
+        vis = self.ctx.visibility()
+        return dict(total=int(vis["total"][0]), early=int(vis["early"][0]), late=int(vis["late"][0]),
+                    triangles=self.ctx.raster_triangle_count())
