@@ -179,25 +179,35 @@ def merge_occluder_depth(vis, occluder_depth):
     return vis
 
 
-def frame(hs, cam, width, height, mask, occluder_depth=None):
+def frame(hs, cam, width, height, mask, occluder_depth=None, first=0, count=0xFFFFFFFF, id_base_fn=None,
+          between_passes=None, after_frame=None):
     """Serial two-pass frame exactly as RendererInstance::render sequences it (RendererInstance.cpp:842-884).
-    Returns dict with every intermediate the GPU parity tests compare."""
+    Returns dict with every intermediate the GPU parity tests compare.
+
+    Multi-rank simulation (tests/test_dist_cpu.py): first/count = this rank's mesh-instance shard,
+    id_base_fn(total) -> global id base (exchange of emitted counts), between_passes(img) / after_frame(img)
+    = the vis-buffer max-reduce hooks.  `visible` holds LOCAL meshlet-instance indices; add id_base for global ids."""
     hw, hh = abi.hiz_extent(width, height)
     hiz = Hiz(hw, hh)  # cleared to 0 every frame (RendererInstance.cpp:579-588)
-    mi, vis, cmd = cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    mi, vis, cmd = cull_meshes(hs, cam, abi.CULL_TEST_ALL, first, count)
+    id_base = int(id_base_fn(int(vis["total"][0]))) if id_base_fn else 0
     img = clear_visbuffer(width, height)
     merge_occluder_depth(img, occluder_depth)
     visible, tcmd_e = cull_meshlets_hiz(hs, mi, vis, cam, abi.CULL_TEST_ALL, hiz, mask)
     e = int(vis["early"][0])
     mask_after_early = mask.copy()
-    ntri_e = raster(hs, mi, visible, 0, e, cam, img)
+    ntri_e = raster(hs, mi, visible, 0, e, cam, img, id_base)
+    if between_passes:
+        between_passes(img)
     _, depth = resolve(img)
     build_hiz(depth, hiz)
     visible, tcmd_l = cull_meshlets_hiz(hs, mi, vis, cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, hiz, mask, visible)
     l = int(vis["late"][0])
-    ntri_l = raster(hs, mi, visible, e, l, cam, img)
+    ntri_l = raster(hs, mi, visible, e, l, cam, img, id_base)
+    if after_frame:
+        after_frame(img)
     return dict(meshlet_instances=mi, visibility=vis, visible=visible, early=e, late=l, hiz=hiz, vis64=img,
-                mask_after_early=mask_after_early, ntri_early=ntri_e, ntri_late=ntri_l, cull_meshlets_cmd=cmd)
+                mask_after_early=mask_after_early, ntri_early=ntri_e, ntri_late=ntri_l, cull_meshlets_cmd=cmd, id_base=id_base)
 
 
 def cpu_baseline_cull(hs, mi, total, cam, mode, n_threads):

@@ -62,9 +62,9 @@ def gather_survivors(local_ids: torch.Tensor, local_count: torch.Tensor, group=N
     world = dist.get_world_size(group)
     counts = torch.empty(world, dtype=local_count.dtype, device=local_count.device)
     dist.all_gather_into_tensor(counts, local_count, group=group)
-    ids = torch.empty((world, local_ids.numel()), dtype=local_ids.dtype, device=local_ids.device)
-    dist.all_gather_into_tensor(ids, local_ids, group=group)
-    return ids, counts
+    ids = torch.empty(world * local_ids.numel(), dtype=local_ids.dtype, device=local_ids.device)
+    dist.all_gather_into_tensor(ids, local_ids.reshape(-1), group=group)
+    return ids.view(world, local_ids.numel()), counts
 
 
 def merge_survivors(ids: torch.Tensor, counts: torch.Tensor):

@@ -191,7 +191,7 @@ def _build_unique_meshes(seed, counts, lod_counts, ragged):
 
     # --- geometry of every meshlet (patch) ---
     org = np.stack([uniform(seed, 10 + a, total, -4.0, 4.0) for a in range(3)], axis=1)
-    size = np.exp(uniform(seed, 13, total, np.log(0.05), np.log(1.0)))
+    size = np.exp(uniform(seed, 13, total, np.log(0.02), np.log(0.3)))
     # random orthonormal frame from a quaternion
     q = np.stack([uniform(seed, 14 + a, total, -1.0, 1.0) for a in range(4)], axis=1)
     q /= np.maximum(np.linalg.norm(q, axis=1, keepdims=True), 1e-9)
@@ -383,8 +383,10 @@ def make_scene(
     rot[:, 1, 0] = 2 * (x * y + z * w); rot[:, 1, 1] = 1 - 2 * (x * x + z * z); rot[:, 1, 2] = 2 * (y * z - x * w)
     rot[:, 2, 0] = 2 * (x * z - y * w); rot[:, 2, 1] = 2 * (y * z + x * w); rot[:, 2, 2] = 1 - 2 * (x * x + y * y)
     if placement == "frustum":
-        # depth log-uniform in [8, 320]; x/y inside the frustum cross-section (fov 60, 16:9) with 8 % margin
-        d = np.exp(uniform(seed, 35, n_inst, np.log(8.0), np.log(320.0)))
+        # depth log-uniform in [15, 600]; x/y inside the frustum cross-section (fov 60, 16:9) with 8 % margin.
+        # With patch sizes log-uniform in [0.02, 0.3] this gives ~30 % steady-state visible meshlets at 1M / 1080p
+        # (cone ~35 %, frustum, Hi-Z occlusion do the rest) and mostly pixel-sized triangles.
+        d = np.exp(uniform(seed, 35, n_inst, np.log(15.0), np.log(600.0)))
         th = np.tan(np.radians(60.0) / 2.0)
         px = uniform(seed, 36, n_inst, -0.92, 0.92) * d * th * (width / height)
         py = uniform(seed, 37, n_inst, -0.92, 0.92) * d * th
