@@ -522,7 +522,9 @@ void orc_cull_triangles(const OrcScene* scene, const OxcMeshletInstance* meshlet
  *      cull.slang:169-171 keeps); vertices 1,2 are swapped so the edge functions are >= 0 inside.
  *   5. sample at pixel centres (px*256+128); edge tie-break: a pixel exactly on edge a->b is inside
  *      iff (dy > 0) || (dy == 0 && dx < 0)  (watertight, no double hits).
- *   6. depth z = (z0 + l1*(z1-z0)) + l2*(z2-z0), l_i = (float)E_i / (float)area2; fragments with
+ *   6. depth z = (za + (float)E_b * dzb) + (float)E_c * dzc with the per-triangle gradients
+ *      dzb = (zb - za) / (float)area2, dzc = (zc - za) / (float)area2 (a,b,c = the re-oriented vertices,
+ *      E_b / E_c = edge functions opposite b / c, int64 -> float round-to-nearest); fragments with
  *      z outside [0,1] are clipped (near/far); -0.0 is stored as +0.0.  value = asuint(z)<<32 | (id<<8 | tri); max wins
  *      (reverse-Z GreaterOrEqual; equal depth -> larger id, deterministic).
  * ---------------------------------------------------------------------------------------------- */
@@ -570,6 +572,7 @@ static void raster_triangle(const float clip[3][4], uint32_t data, uint32_t W, u
   if (py1 > (int64_t)H - 1) py1 = (int64_t)H - 1;
   const int b0 = edge_bias(bx, by, cx, cy), b1 = edge_bias(cx, cy, ax, ay), b2 = edge_bias(ax, ay, bx, by);
   const float fa = (float)area2;
+  const float dzb = (zb - za) / fa, dzc = (zc - za) / fa; /* per-triangle depth gradients w.r.t. the edge functions */
   for (int64_t py = py0; py <= py1; py++)
     for (int64_t px = px0; px <= px1; px++) {
       int64_t sxp = px * 256 + 128, syp = py * 256 + 128;
@@ -577,8 +580,7 @@ static void raster_triangle(const float clip[3][4], uint32_t data, uint32_t W, u
       int64_t e1 = orient2d(cx, cy, ax, ay, sxp, syp); /* weight of b */
       int64_t e2 = orient2d(ax, ay, bx, by, sxp, syp); /* weight of c */
       if ((e0 + b0) < 0 || (e1 + b1) < 0 || (e2 + b2) < 0) continue;
-      float l1 = (float)e1 / fa, l2 = (float)e2 / fa;
-      float zz = (za + l1 * (zb - za)) + l2 * (zc - za);
+      float zz = (za + (float)e1 * dzb) + (float)e2 * dzc;
       if (!(zz >= 0.0f && zz <= 1.0f)) continue;
       uint32_t zbits = f2bits(zz);
       if (zbits == 0x80000000u) zbits = 0u; /* -0.0 -> +0.0 so unsigned order == depth order */
@@ -813,6 +815,7 @@ static void raster_triangle_atomic(const float clip[3][4], uint32_t data, uint32
   if (py1 > (int64_t)H - 1) py1 = (int64_t)H - 1;
   const int b0 = edge_bias(bx, by, cx, cy), b1 = edge_bias(cx, cy, ax, ay), b2 = edge_bias(ax, ay, bx, by);
   const float fa = (float)area2;
+  const float dzb = (zb - za) / fa, dzc = (zc - za) / fa; /* per-triangle depth gradients w.r.t. the edge functions */
   for (int64_t py = py0; py <= py1; py++)
     for (int64_t px = px0; px <= px1; px++) {
       int64_t sxp = px * 256 + 128, syp = py * 256 + 128;
@@ -820,8 +823,7 @@ static void raster_triangle_atomic(const float clip[3][4], uint32_t data, uint32
       int64_t e1 = orient2d(cx, cy, ax, ay, sxp, syp);
       int64_t e2 = orient2d(ax, ay, bx, by, sxp, syp);
       if ((e0 + b0) < 0 || (e1 + b1) < 0 || (e2 + b2) < 0) continue;
-      float l1 = (float)e1 / fa, l2 = (float)e2 / fa;
-      float zz = (za + l1 * (zb - za)) + l2 * (zc - za);
+      float zz = (za + (float)e1 * dzb) + (float)e2 * dzc;
       if (!(zz >= 0.0f && zz <= 1.0f)) continue;
       uint32_t zbits = f2bits(zz);
       if (zbits == 0x80000000u) zbits = 0u; /* -0.0 -> +0.0 so unsigned order == depth order */

@@ -227,7 +227,9 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
   __shared__ uint32_t hiz_off[OXC_HIZ_MAX_LEVELS];
   __shared__ uint32_t warp_cnt[CULL_THREADS / 32];
   __shared__ uint32_t tile_base_s;
+  __shared__ float s8_lut[256]; // scene.slang:408-418: i8 / 127.0 for every i8 (IEEE divide, done once per CTA)
   if (threadIdx.x < OXC_HIZ_MAX_LEVELS) hiz_off[threadIdx.x] = p.hiz.level_offset[threadIdx.x];
+  s8_lut[threadIdx.x] = s8_over_127((int)threadIdx.x - 128);
   __syncthreads();
   const uint32_t total = p.vis->total_visible_meshlet_instances; // :26
   const uint32_t early_count = LATE ? p.vis->early_visible_meshlet_instances : 0u; // :73 (final: early kernel completed)
@@ -238,61 +240,78 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
 
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t tile_first = tile * CULL_TILE;
+    // ---- staged loads: every level of the (shortened) pointer chase is issued for all items before it is used ----
     uint2 mi[CULL_ITEMS];
 #pragma unroll
     for (int k = 0; k < CULL_ITEMS; k++) {
       const uint32_t i = tile_first + k * CULL_THREADS + threadIdx.x;
       mi[k] = i < total ? __ldg(&mi2[i]) : make_uint2(0xFFFFFFFFu, 0u);
     }
+    const uint4* bptr[CULL_ITEMS];
+    uint32_t word[CULL_ITEMS], bit[CULL_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CULL_ITEMS; k++) {
+      bptr[k] = nullptr; word[k] = 0xFFFFFFFFu; bit[k] = 0;
+      if (mi[k].x != 0xFFFFFFFFu) {
+        const uint4 tail = __ldg(reinterpret_cast<const uint4*>(&p.inst[mi[k].x].bounds_lo));
+        bptr[k] = reinterpret_cast<const uint4*>(((uint64_t)tail.y << 32) | tail.x) + mi[k].y;
+        if (OCC) { // :45-49
+          const uint32_t vi = tail.z + mi[k].y;
+          word[k] = vi >> 5;
+          bit[k] = 1u << (vi & 31);
+        }
+      }
+    }
+    uint32_t was_bits = 0; // bit k: was_visible of item k (:50; true when !OCC, :44)
+#pragma unroll
+    for (int k = 0; k < CULL_ITEMS; k++) {
+      bool wv = true;
+      if (OCC && mi[k].x != 0xFFFFFFFFu) wv = (p.mask[word[k]] & bit[k]) != 0; // plain load: only this thread ever changes this bit
+      was_bits |= (wv ? 1u : 0u) << k;
+    }
+    uint4 bnd[CULL_ITEMS];
+#pragma unroll
+    for (int k = 0; k < CULL_ITEMS; k++) {
+      const bool need = mi[k].x != 0xFFFFFFFFu && (LATE || ((was_bits >> k) & 1u)); // :57
+      bnd[k] = need ? __ldg(bptr[k]) : make_uint4(0, 0, 0, 0); // MeshletBounds, one 128-bit load
+    }
     uint32_t emit_bits = 0;
 #pragma unroll
     for (int k = 0; k < CULL_ITEMS; k++) {
       const bool valid = mi[k].x != 0xFFFFFFFFu;
-      bool visible = false, was_visible = true;
-      uint32_t word = 0xFFFFFFFFu, bit = 0;
-      if (valid) {
+      const bool was_visible = (was_bits >> k) & 1u;
+      bool visible = valid && (LATE ? true : was_visible); // :57
+      if (visible) {
         const InstCull* ic = p.inst + mi[k].x;
-        const uint4 tail = __ldg(reinterpret_cast<const uint4*>(&ic->bounds_lo));
-        if (OCC) { // :45-51
-          const uint32_t vi = tail.z + mi[k].y;
-          word = vi >> 5;
-          bit = 1u << (vi & 31);
-          was_visible = (p.mask[word] & bit) != 0; // plain load: only this thread ever changes this bit
-        }
-        visible = LATE ? true : was_visible; // :57
-        if (visible) {
-          const uint4* bptr = reinterpret_cast<const uint4*>(((uint64_t)tail.y << 32) | tail.x) + mi[k].y;
-          const uint4 b = __ldg(bptr); // MeshletBounds, one 128-bit load
-          // scene.slang:401-435 unpack: u16x3 center | i8x2 cone xy | u16x3 extent | i8 cone z | i8 cutoff
-          const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
-          const int axq = (int)(int8_t)((b.y >> 16) & 0xFF), ayq = (int)(int8_t)(b.y >> 24);
-          const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
-          const int azq = (int)(int8_t)((b.w >> 16) & 0xFF), cutq = (int)(int8_t)(b.w >> 24);
-          const float cutoff = s8_over_127(cutq);
-          // :58 cone
-          if (cutoff < 1.0f)
-            visible = cone_visible_positional(ic, cx, cy, cz, ex, ey, ez, s8_over_127(axq), s8_over_127(ayq),
-                                              s8_over_127(azq), cutoff, p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]);
-          // :59 frustum
-          visible = visible && test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
-          // :61-65 occlusion
-          if (HIZ && (OCC || LATE) && visible) {
-            ScreenAabb sa;
-            const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]),
-                         r3 = __ldg(&ic->mvp_row[3]);
-            if (project_aabb(r0, r1, r2, r3, p.near_clip, cx, cy, cz, ex, ey, ez, sa))
-              visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, hiz_off);
-          }
+        const uint4 b = bnd[k];
+        // scene.slang:401-435 unpack: u16x3 center | i8x2 cone xy | u16x3 extent | i8 cone z | i8 cutoff
+        const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
+        const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
+        const float cutoff = s8_lut[((b.w >> 24) + 128u) & 0xFFu];
+        // :58 cone
+        if (cutoff < 1.0f)
+          visible = cone_visible_positional(ic, cx, cy, cz, ex, ey, ez, s8_lut[(((b.y >> 16) & 0xFFu) + 128u) & 0xFFu],
+                                            s8_lut[((b.y >> 24) + 128u) & 0xFFu], s8_lut[(((b.w >> 16) & 0xFFu) + 128u) & 0xFFu],
+                                            cutoff, p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]);
+        // :59 frustum
+        visible = visible && test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
+        // :61-65 occlusion
+        if (HIZ && (OCC || LATE) && visible) {
+          ScreenAabb sa;
+          const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]),
+                       r3 = __ldg(&ic->mvp_row[3]);
+          if (project_aabb(r0, r1, r2, r3, p.near_clip, cx, cy, cz, ex, ey, ez, sa))
+            visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, hiz_off);
         }
       }
       // :81-87 mask rewrite: XOR of the changed own bits, aggregated per word within the warp
       if (OCC) {
         const bool changed = valid && (visible != was_visible);
-        const uint32_t key = changed ? word : 0xFFFFFFFFu;
+        const uint32_t key = changed ? word[k] : 0xFFFFFFFFu;
         if (__any_sync(0xffffffffu, changed)) {
           const uint32_t peers = __match_any_sync(0xffffffffu, key);
-          const uint32_t delta = __reduce_or_sync(peers, changed ? bit : 0u);
-          if (changed && lane == (uint32_t)(__ffs(peers) - 1)) atomicXor(&p.mask[word], delta);
+          const uint32_t delta = __reduce_or_sync(peers, changed ? bit[k] : 0u);
+          if (changed && lane == (uint32_t)(__ffs(peers) - 1)) atomicXor(&p.mask[word[k]], delta);
         }
       }
       if (visible && (!LATE || !was_visible)) emit_bits |= 1u << k; // :67

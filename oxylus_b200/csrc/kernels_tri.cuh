@@ -4,6 +4,8 @@
 // The raster itself has no reference implementation (HW rasteriser, DrawGeometry.cpp:104-190); its
 // specification is the comment block above raster_triangle() in oracle/oxc_oracle.c.
 #pragma once
+#include <climits>
+
 #include "oxc_exact.cuh"
 
 namespace oxc {
@@ -132,10 +134,30 @@ __global__ void __launch_bounds__(TRI_THREADS) k_cull_triangles(const __grid_con
 }
 
 // ---- software raster ----
+// Per-vertex screen record (computed once per vertex, not per corner): 24.8 fixed-point position + NDC depth.
+// valid = w > 0 and |fx|,|fy| <= 2^22 (raster spec steps 2-3); invalid is flagged with fx == INT_MIN.
+struct __align__(16) ScreenVert {
+  int fx, fy;
+  float z;
+  int pad;
+};
+
+OXC_DI ScreenVert to_screen(float4 c, float fW, float fH) {
+  ScreenVert v;
+  v.fx = INT_MIN; v.fy = 0; v.z = 0.f; v.pad = 0;
+  if (!(c.w > 0.0f)) return v;
+  const float rw = fd(1.0f, c.w);
+  const float nx = fm(c.x, rw), ny = fm(c.y, rw);
+  const float sx = fm(fa(fm(nx, 0.5f), 0.5f), fW), sy = fm(fa(fm(ny, 0.5f), 0.5f), fH);
+  const float qx = floorf(fa(fm(sx, 256.0f), 0.5f)), qy = floorf(fa(fm(sy, 256.0f), 0.5f));
+  if (!(fabsf(qx) <= 4194304.0f && fabsf(qy) <= 4194304.0f)) return v;
+  v.fx = (int)qx; v.fy = (int)qy; v.z = fm(c.z, rw);
+  return v;
+}
+
 struct TriSetup {
   int ax, ay, bx, by, cx, cy;   // 24.8 fixed point, a/b/c positively oriented (b,c swapped)
-  float za, zb, zc;
-  float fa_;                    // (float)area2
+  float za, dzb, dzc;           // depth at a, per-triangle gradients w.r.t. the edge functions of b and c
   int px0, px1, py0, py1;
   int bias;                     // bit0..2: edge biases (1 = -1)
 };
@@ -149,27 +171,11 @@ OXC_DI int edge_bias_bit(int ax, int ay, int bx, int by) {
 }
 
 // steps 2-4 of the raster spec; false = nothing to draw
-OXC_DI bool tri_setup(float4 c0, float4 c1, float4 c2, uint32_t W, uint32_t H, TriSetup& s) {
-  if (!(c0.w > 0.0f && c1.w > 0.0f && c2.w > 0.0f)) return false;
-  int fx[3], fy[3];
-  float z[3];
-  const float4 c[3] = {c0, c1, c2};
-#pragma unroll
-  for (int i = 0; i < 3; i++) {
-    const float rw = fd(1.0f, c[i].w);
-    const float nx = fm(c[i].x, rw), ny = fm(c[i].y, rw);
-    z[i] = fm(c[i].z, rw);
-    const float sx = fm(fa(fm(nx, 0.5f), 0.5f), (float)W), sy = fm(fa(fm(ny, 0.5f), 0.5f), (float)H);
-    const float qx = floorf(fa(fm(sx, 256.0f), 0.5f)), qy = floorf(fa(fm(sy, 256.0f), 0.5f));
-    if (!(fabsf(qx) <= 4194304.0f && fabsf(qy) <= 4194304.0f)) return false;
-    fx[i] = (int)qx;
-    fy[i] = (int)qy;
-  }
-  long long area2 = orient2d(fx[0], fy[0], fx[1], fy[1], fx[2], fy[2]);
+OXC_DI bool tri_setup(const ScreenVert v0, const ScreenVert v1, const ScreenVert v2, uint32_t W, uint32_t H, TriSetup& s) {
+  if (v0.fx == INT_MIN || v1.fx == INT_MIN || v2.fx == INT_MIN) return false;
+  const long long area2 = orient2d(v0.fx, v0.fy, v1.fx, v1.fy, v2.fx, v2.fy);
   if (area2 >= 0) return false;
-  s.ax = fx[0]; s.ay = fy[0]; s.bx = fx[2]; s.by = fy[2]; s.cx = fx[1]; s.cy = fy[1];
-  s.za = z[0]; s.zb = z[2]; s.zc = z[1];
-  s.fa_ = (float)(-area2);
+  s.ax = v0.fx; s.ay = v0.fy; s.bx = v2.fx; s.by = v2.fy; s.cx = v1.fx; s.cy = v1.fy;
   const int minx = min(s.ax, min(s.bx, s.cx)), maxx = max(s.ax, max(s.bx, s.cx));
   const int miny = min(s.ay, min(s.by, s.cy)), maxy = max(s.ay, max(s.by, s.cy));
   s.px0 = max(0, (minx - 128 + 255) >> 8);
@@ -177,20 +183,20 @@ OXC_DI bool tri_setup(float4 c0, float4 c1, float4 c2, uint32_t W, uint32_t H, T
   s.py0 = max(0, (miny - 128 + 255) >> 8);
   s.py1 = min((int)H - 1, (maxy - 128) >> 8);
   if (s.px1 < s.px0 || s.py1 < s.py0) return false; // covers no sample centre (== small-primitive cull)
+  const float fa_ = (float)(-area2);
+  s.za = v0.z;
+  s.dzb = fd(fs(v2.z, v0.z), fa_);
+  s.dzc = fd(fs(v1.z, v0.z), fa_);
   s.bias = edge_bias_bit(s.bx, s.by, s.cx, s.cy) | (edge_bias_bit(s.cx, s.cy, s.ax, s.ay) << 1) |
            (edge_bias_bit(s.ax, s.ay, s.bx, s.by) << 2);
   return true;
 }
 
-// steps 5-6 for one pixel
-OXC_DI void raster_pixel(const TriSetup& s, int px, int py, uint32_t data, unsigned long long* vis, uint32_t W) {
-  const int sx = px * 256 + 128, sy = py * 256 + 128;
-  const long long e0 = orient2d(s.bx, s.by, s.cx, s.cy, sx, sy);
-  const long long e1 = orient2d(s.cx, s.cy, s.ax, s.ay, sx, sy);
-  const long long e2 = orient2d(s.ax, s.ay, s.bx, s.by, sx, sy);
+// steps 5-6 given the three edge-function values at the pixel centre
+OXC_DI void shade_pixel(const TriSetup& s, long long e0, long long e1, long long e2, int px, int py, uint32_t data,
+                        unsigned long long* vis, uint32_t W) {
   if ((e0 - (s.bias & 1)) < 0 || (e1 - ((s.bias >> 1) & 1)) < 0 || (e2 - ((s.bias >> 2) & 1)) < 0) return;
-  const float l1 = fd((float)e1, s.fa_), l2 = fd((float)e2, s.fa_);
-  const float zz = fa(fa(s.za, fm(l1, fs(s.zb, s.za))), fm(l2, fs(s.zc, s.za)));
+  const float zz = fa(fa(s.za, fm((float)e1, s.dzb)), fm((float)e2, s.dzc));
   if (!(zz >= 0.0f && zz <= 1.0f)) return;
   uint32_t zb = __float_as_uint(zz);
   zb = zb == 0x80000000u ? 0u : zb; // -0.0 -> +0.0 so unsigned order == depth order
@@ -199,33 +205,68 @@ OXC_DI void raster_pixel(const TriSetup& s, int px, int py, uint32_t data, unsig
   if (v > *ptr) atomicMax(ptr, v); // reverse-Z GreaterOrEqual == max (visbuffer.slang:72-74 packing)
 }
 
-constexpr int RASTER_BIG_PIXELS = 64; // bbox area above which the whole warp rasterises the triangle together
+OXC_DI void raster_pixel(const TriSetup& s, int px, int py, uint32_t data, unsigned long long* vis, uint32_t W) {
+  const int sx = px * 256 + 128, sy = py * 256 + 128;
+  shade_pixel(s, orient2d(s.bx, s.by, s.cx, s.cy, sx, sy), orient2d(s.cx, s.cy, s.ax, s.ay, sx, sy),
+              orient2d(s.ax, s.ay, s.bx, s.by, sx, sy), px, py, data, vis, W);
+}
+
+// one lane walks the (small) bounding box with incrementally stepped edge functions (64-bit adds only)
+OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* vis, uint32_t W) {
+  const int sx0 = s.px0 * 256 + 128, sy0 = s.py0 * 256 + 128;
+  long long r0 = orient2d(s.bx, s.by, s.cx, s.cy, sx0, sy0);
+  long long r1 = orient2d(s.cx, s.cy, s.ax, s.ay, sx0, sy0);
+  long long r2 = orient2d(s.ax, s.ay, s.bx, s.by, sx0, sy0);
+  // orient2d(a,b,p) = (bx-ax)*(py-ay) - (by-ay)*(px-ax):  d/dpx = -(by-ay), d/dpy = (bx-ax)   (x256 per pixel)
+  const long long dx0 = -(long long)(s.cy - s.by) * 256, dy0 = (long long)(s.cx - s.bx) * 256;
+  const long long dx1 = -(long long)(s.ay - s.cy) * 256, dy1 = (long long)(s.ax - s.cx) * 256;
+  const long long dx2 = -(long long)(s.by - s.ay) * 256, dy2 = (long long)(s.bx - s.ax) * 256;
+  for (int py = s.py0; py <= s.py1; py++) {
+    long long e0 = r0, e1 = r1, e2 = r2;
+    for (int px = s.px0; px <= s.px1; px++) {
+      shade_pixel(s, e0, e1, e2, px, py, data, vis, W);
+      e0 += dx0; e1 += dx1; e2 += dx2;
+    }
+    r0 += dy0; r1 += dy1; r2 += dy2;
+  }
+}
+
+constexpr int RASTER_BIG_PIXELS = 32; // bbox area above which the whole warp rasterises the triangle together
 
 __global__ void __launch_bounds__(TRI_THREADS) k_raster_visbuffer(const __grid_constant__ TriParams p) {
   __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
+  __shared__ ScreenVert scr_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t first = p.late ? p.vis->early_visible_meshlet_instances : 0u; // cull_triangles.slang:34-37
   const uint32_t count = p.tri_cmd->x;                                         // dispatch_indirect(cull_triangles_cmd), CullGeometry.cpp:365
   const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
+  const float fW = (float)p.width, fH = (float)p.height;
   float4* clip_s = clip_all[warp];
+  ScreenVert* scr_s = scr_all[warp];
   uint32_t kept = 0;
   for (uint32_t g = blockIdx.x * TRI_WARPS + warp; g < count; g += gridDim.x * TRI_WARPS) {
     const MeshletWork w = load_meshlet(p, first + g, id_base, clip_s, lane);
+    for (uint32_t v = lane; v < OXC_MESHLET_MAX_VERTICES; v += 32) scr_s[v] = to_screen(clip_s[v], fW, fH);
+    __syncwarp();
     const uint32_t rounds = (w.tri_count + 31u) >> 5;
     for (uint32_t k = 0; k < rounds; k++) {
       const uint32_t t = lane + 32u * k;
-      float4 c0, c1, c2;
-      const bool pass = t < w.tri_count && triangle_passes(w, t, clip_s, c0, c1, c2);
-      kept += pass ? 1u : 0u;
+      bool pass = false;
       TriSetup s;
-      const bool draw = pass && tri_setup(c0, c1, c2, p.width, p.height, s);
+      bool draw = false;
+      if (t < w.tri_count) {
+        const uint32_t base = w.tri_offset + t * 3u;
+        const uint32_t i0 = micro_index(w.micro, base + 0u), i1 = micro_index(w.micro, base + 1u), i2 = micro_index(w.micro, base + 2u);
+        const float4 c0 = clip_s[i0], c1 = clip_s[i1], c2 = clip_s[i2];
+        pass = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f && !triangle_backface(c0, c1, c2); // cull_triangles.slang:68-69
+        if (pass) draw = tri_setup(scr_s[i0], scr_s[i1], scr_s[i2], p.width, p.height, s);
+      }
+      kept += pass ? 1u : 0u;
       const uint32_t data = (w.data_id << OXC_VIS_PRIMITIVE_BITS) | (t & OXC_VIS_PRIMITIVE_MASK);
       const int bw = draw ? s.px1 - s.px0 + 1 : 0, bh = draw ? s.py1 - s.py0 + 1 : 0;
       const bool big = draw && (bw * bh > RASTER_BIG_PIXELS);
-      if (draw && !big)
-        for (int py = s.py0; py <= s.py1; py++)
-          for (int px = s.px0; px <= s.px1; px++) raster_pixel(s, px, py, data, p.visbuf, p.width);
-      // large triangles: broadcast the setup, all 32 lanes stride over the bounding box
+      if (draw && !big) raster_small(s, data, p.visbuf, p.width);
+      // large triangles: broadcast the setup; the warp covers the bounding box in 8x4-pixel tiles
       uint32_t big_mask = __ballot_sync(0xffffffffu, big);
       while (big_mask) {
         const int src = __ffs(big_mask) - 1;
@@ -234,17 +275,21 @@ __global__ void __launch_bounds__(TRI_THREADS) k_raster_visbuffer(const __grid_c
         b.ax = __shfl_sync(0xffffffffu, s.ax, src); b.ay = __shfl_sync(0xffffffffu, s.ay, src);
         b.bx = __shfl_sync(0xffffffffu, s.bx, src); b.by = __shfl_sync(0xffffffffu, s.by, src);
         b.cx = __shfl_sync(0xffffffffu, s.cx, src); b.cy = __shfl_sync(0xffffffffu, s.cy, src);
-        b.za = __shfl_sync(0xffffffffu, s.za, src); b.zb = __shfl_sync(0xffffffffu, s.zb, src);
-        b.zc = __shfl_sync(0xffffffffu, s.zc, src); b.fa_ = __shfl_sync(0xffffffffu, s.fa_, src);
+        b.za = __shfl_sync(0xffffffffu, s.za, src); b.dzb = __shfl_sync(0xffffffffu, s.dzb, src);
+        b.dzc = __shfl_sync(0xffffffffu, s.dzc, src);
         b.px0 = __shfl_sync(0xffffffffu, s.px0, src); b.px1 = __shfl_sync(0xffffffffu, s.px1, src);
         b.py0 = __shfl_sync(0xffffffffu, s.py0, src); b.py1 = __shfl_sync(0xffffffffu, s.py1, src);
         b.bias = __shfl_sync(0xffffffffu, s.bias, src);
         const uint32_t bdata = __shfl_sync(0xffffffffu, data, src);
-        const int ww = b.px1 - b.px0 + 1, n = ww * (b.py1 - b.py0 + 1);
-        for (int i = lane; i < n; i += 32) raster_pixel(b, b.px0 + i % ww, b.py0 + i / ww, bdata, p.visbuf, p.width);
+        const int lx = lane & 7, ly = lane >> 3;
+        for (int ty = b.py0; ty <= b.py1; ty += 4)
+          for (int tx = b.px0; tx <= b.px1; tx += 8) {
+            const int px = tx + lx, py = ty + ly;
+            if (px <= b.px1 && py <= b.py1) raster_pixel(b, px, py, bdata, p.visbuf, p.width);
+          }
       }
     }
-    __syncwarp(); // clip_s reuse
+    __syncwarp(); // clip_s / scr_s reuse
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);

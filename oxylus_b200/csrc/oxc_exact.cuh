@@ -89,15 +89,19 @@ OXC_DI bool project_aabb(const float4 r0, const float4 r1, const float4 r2, cons
 OXC_DI bool test_frustum_planes(const float4* __restrict__ planes, float cx, float cy, float cz, float ex, float ey,
                                 float ez) {
   const float hx = fm(ex, 0.5f), hy = fm(ey, 0.5f), hz = fm(ez, 0.5f);
+  float4 pl[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) pl[i] = __ldg(&planes[i]); // all six loads in flight before the first test
+  bool inside = true;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    const float4 p = __ldg(&planes[i]);
+    const float4 p = pl[i];
     const float sx = __uint_as_float(__float_as_uint(hx) ^ (__float_as_uint(p.x) & 0x80000000u));
     const float sy = __uint_as_float(__float_as_uint(hy) ^ (__float_as_uint(p.y) & 0x80000000u));
     const float sz = __uint_as_float(__float_as_uint(hz) ^ (__float_as_uint(p.z) & 0x80000000u));
-    if (dot3(fa(cx, sx), fa(cy, sy), fa(cz, sz), p.x, p.y, p.z) <= -p.w) return false;
+    inside = inside && !(dot3(fa(cx, sx), fa(cy, sy), fa(cz, sz), p.x, p.y, p.z) <= -p.w);
   }
-  return true;
+  return inside;
 }
 
 // ceil(log2(float(n))) in integers (oracle: orc_ceil_log2_u32)
