@@ -39,7 +39,7 @@ UNIT = "meshlet instances/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--meshlets", type=int, default=1_000_000, help="meshlet instances per GPU")
@@ -74,7 +74,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
@@ -242,6 +242,8 @@ def main():
     # ---------------- warm-up (also brings the visibility mask to steady state) ----------------
     W = max(4, args.warmup)  # >= 4 so the persistent visibility mask reaches its steady state
     K = max(1, args.steps)
+    sampler = ClockSampler(local_rank)  # samples span warm-up + timed region + per-kernel loop (all GPU-busy)
+    sampler.start()
     for i in range(W):
         pipe.frame(cams[i % 2], **hooks)
     torch.cuda.synchronize()
@@ -275,11 +277,9 @@ def main():
             pipe.frame(cams[i % 2], mark=mark, **hooks)
 
     # ---------------- timed region: exactly K steps ----------------
-    sampler = ClockSampler(local_rank)
     launches0 = capi.kernel_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     barrier()
-    sampler.start()
     t_wall0 = time.perf_counter()
     for i in range(K):
         flush.fill_(i & 0xFF)  # L2 flush, outside the per-step event pair
@@ -288,7 +288,6 @@ def main():
         ev[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_per_step = float(np.mean(step_ms))
     if graphs is not None:
@@ -318,6 +317,12 @@ def main():
         for a, b in zip(stage_names[:-1], stage_names[1:]):
             stage_acc[b].append(marks[a].elapsed_time(marks[b]))
     launches_per_frame = (capi.kernel_launch_count() - l0) // K
+    # keep the GPU busy with the same steps until the sampler has a few readings, then stop it
+    t_busy = time.perf_counter()
+    while len(sampler.samples) < 5 and time.perf_counter() - t_busy < 2.0:
+        step(0)
+        torch.cuda.synchronize()
+    clocks = sampler.stop()
     stages_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
     cnt_late = pipe.counters()
 

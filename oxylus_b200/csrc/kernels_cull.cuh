@@ -1,7 +1,7 @@
 // kernels_cull.cuh — mesh-level cull + expansion, the two-pass meshlet cull, the multi-view cull.
 // Reference: Oxylus/src/Render/Shaders/passes/{cull_meshes,cull_meshlets_hiz,cull_meshlets,cull_meshlets_hpb}.slang
 #pragma once
-#include "oxc_exact.cuh"
+#include "oxc_filtered.cuh"
 
 namespace oxc {
 
@@ -217,19 +217,39 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_expand_meshlet_instance
 //   OCC  = HAS_FLAG(CULL_FLAGS, TestOcclusion)   (mask read/modify, :45-51,81-87)
 //   LATE = HAS_FLAG(CULL_FLAGS, LatePass)
 //   HIZ  = use_hiz: project_aabb + test_occlusion run when OCC || LATE (:61, any-bit HAS_FLAG)
-// Persistent CTAs walk tiles of 1024 meshlet instances; survivors are compacted with warp ballots and ONE
-// global atomic per tile (the reference issues three per surviving lane, :70-78).  Mask bits are updated
-// with a single XOR of the changed bits per touched word per warp (own bits only => race-free), instead
-// of one atomic or/and per lane (:81-87).
+//   ZERO = the pyramid is known to be the per-frame cleared image (early pass)
+//
+// Persistent CTAs walk tiles of 1024 meshlet instances (256 threads x 4 items):
+//   phase A  staged loads (instance -> InstCull tail -> mask word -> bounds, each level issued for all four
+//            items before use); canonical frustum test; filtered cone test; items that still need the
+//            Hi-Z test are appended to a shared-memory queue
+//   phase B  the queue is consumed DENSELY (no lanes idling on culled items): filtered projection + occlusion;
+//            margin-ambiguous items go to a second queue
+//   phase C  canonical evaluation of the ambiguous items (a fraction of a percent)
+//   phase D  owners collect the verdicts: mask update = one XOR of the changed own bits per touched word per
+//            warp (reference: one atomic or/and per lane, :81-87); survivors compacted with warp ballots and
+//            ONE global atomic per tile (reference: three per surviving lane, :70-78)
+// Outputs are bit-identical to the canonical path for every input (oxc_filtered.cuh).
 // ------------------------------------------------------------------------------------------------
-template <bool HIZ, bool OCC, bool LATE>
+struct __align__(16) OccWork {
+  uint4 bounds;
+};
+
+template <bool HIZ, bool OCC, bool LATE, bool ZERO>
 __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_constant__ CullParams p) {
   __shared__ uint32_t hiz_off[OXC_HIZ_MAX_LEVELS];
   __shared__ uint32_t warp_cnt[CULL_THREADS / 32];
   __shared__ uint32_t tile_base_s;
-  __shared__ float s8_lut[256]; // scene.slang:408-418: i8 / 127.0 for every i8 (IEEE divide, done once per CTA)
+  __shared__ float s8_lut[256]; // scene.slang:408-418: i8 / 127.0 for every i8 (IEEE divide, once per CTA)
+  __shared__ uint4 q_bounds[HIZ ? CULL_TILE : 1];    // per slot: MeshletBounds of items queued for the Hi-Z test
+  __shared__ uint32_t q_inst[HIZ ? CULL_TILE : 1];   // per slot: mesh instance index
+  __shared__ uint16_t q_occ[HIZ ? CULL_TILE : 1];    // queue of slots for phase B
+  __shared__ uint16_t q_amb[HIZ ? CULL_TILE : 1];    // queue of slots for phase C
+  __shared__ uint8_t q_res[HIZ ? CULL_TILE : 1];     // verdict per slot (1 = visible)
+  __shared__ uint32_t n_occ_s, n_amb_s;
   if (threadIdx.x < OXC_HIZ_MAX_LEVELS) hiz_off[threadIdx.x] = p.hiz.level_offset[threadIdx.x];
   s8_lut[threadIdx.x] = s8_over_127((int)threadIdx.x - 128);
+  if (threadIdx.x == 0) { n_occ_s = 0; n_amb_s = 0; }
   __syncthreads();
   const uint32_t total = p.vis->total_visible_meshlet_instances; // :26
   const uint32_t early_count = LATE ? p.vis->early_visible_meshlet_instances : 0u; // :73 (final: early kernel completed)
@@ -240,7 +260,7 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
 
   for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     const uint32_t tile_first = tile * CULL_TILE;
-    // ---- staged loads: every level of the (shortened) pointer chase is issued for all items before it is used ----
+    // ---- phase A: staged loads ----
     uint2 mi[CULL_ITEMS];
 #pragma unroll
     for (int k = 0; k < CULL_ITEMS; k++) {
@@ -275,35 +295,87 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
       const bool need = mi[k].x != 0xFFFFFFFFu && (LATE || ((was_bits >> k) & 1u)); // :57
       bnd[k] = need ? __ldg(bptr[k]) : make_uint4(0, 0, 0, 0); // MeshletBounds, one 128-bit load
     }
-    uint32_t emit_bits = 0;
+    uint32_t vis_bits = 0;     // bit k: verdict so far
+    uint32_t pending_bits = 0; // bit k: verdict comes from the queue (q_res)
 #pragma unroll
     for (int k = 0; k < CULL_ITEMS; k++) {
       const bool valid = mi[k].x != 0xFFFFFFFFu;
-      const bool was_visible = (was_bits >> k) & 1u;
-      bool visible = valid && (LATE ? true : was_visible); // :57
+      bool visible = valid && (LATE ? true : ((was_bits >> k) & 1u)); // :57
       if (visible) {
         const InstCull* ic = p.inst + mi[k].x;
         const uint4 b = bnd[k];
         // scene.slang:401-435 unpack: u16x3 center | i8x2 cone xy | u16x3 extent | i8 cone z | i8 cutoff
         const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
         const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
-        const float cutoff = s8_lut[((b.w >> 24) + 128u) & 0xFFu];
+        // :59 frustum (canonical; evaluated first: the three tests commute)
+        visible = test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
         // :58 cone
-        if (cutoff < 1.0f)
-          visible = cone_visible_positional(ic, cx, cy, cz, ex, ey, ez, s8_lut[(((b.y >> 16) & 0xFFu) + 128u) & 0xFFu],
+        const float cutoff = s8_lut[((b.w >> 24) + 128u) & 0xFFu];
+        if (visible && cutoff < 1.0f) {
+          const ConeInputs ci = cone_inputs(ic, cx, cy, cz, ex, ey, ez, s8_lut[(((b.y >> 16) & 0xFFu) + 128u) & 0xFFu],
                                             s8_lut[((b.y >> 24) + 128u) & 0xFFu], s8_lut[(((b.w >> 16) & 0xFFu) + 128u) & 0xFFu],
-                                            cutoff, p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]);
-        // :59 frustum
-        visible = visible && test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
+                                            p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]);
+          const Tri t = cone_visible_fast(ci, cutoff);
+          visible = t == TRI_AMBIGUOUS ? cone_visible_exact(ci, cutoff) : (t == TRI_TRUE);
+        }
         // :61-65 occlusion
         if (HIZ && (OCC || LATE) && visible) {
-          ScreenAabb sa;
-          const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]),
-                       r3 = __ldg(&ic->mvp_row[3]);
-          if (project_aabb(r0, r1, r2, r3, p.near_clip, cx, cy, cz, ex, ey, ez, sa))
-            visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, hiz_off);
+          bool queue = true;
+          if (ZERO) queue = !cleared_hiz_surely_visible(__ldg(&ic->mvp_row[2]), __ldg(&ic->mvp_row[3]), cx, cy, cz, ex, ey, ez);
+          if (queue) {
+            const uint32_t slot = k * CULL_THREADS + threadIdx.x;
+            q_bounds[slot] = b;
+            q_inst[slot] = mi[k].x;
+            q_occ[atomicAdd(&n_occ_s, 1u)] = (uint16_t)slot;
+            pending_bits |= 1u << k;
+          }
         }
       }
+      vis_bits |= (visible ? 1u : 0u) << k;
+    }
+    if (HIZ) {
+      // ---- phase B: dense Hi-Z tests ----
+      __syncthreads();
+      const uint32_t n_occ = n_occ_s;
+      for (uint32_t j = threadIdx.x; j < n_occ; j += CULL_THREADS) {
+        const uint32_t slot = q_occ[j];
+        const uint4 b = q_bounds[slot];
+        const InstCull* ic = p.inst + q_inst[slot];
+        const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
+        const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
+        const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
+        const Tri t = occlusion_visible_fast(r0, r1, r2, r3, p.near_clip, cx, cy, cz, ex, ey, ez, p.hiz.data, p.hiz.width,
+                                             p.hiz.height, p.hiz.levels, hiz_off);
+        if (t == TRI_AMBIGUOUS) q_amb[atomicAdd(&n_amb_s, 1u)] = (uint16_t)slot;
+        else q_res[slot] = (uint8_t)t;
+      }
+      // ---- phase C: canonical evaluation of the margin-ambiguous items ----
+      __syncthreads();
+      const uint32_t n_amb = n_amb_s;
+      for (uint32_t j = threadIdx.x; j < n_amb; j += CULL_THREADS) {
+        const uint32_t slot = q_amb[j];
+        const uint4 b = q_bounds[slot];
+        const InstCull* ic = p.inst + q_inst[slot];
+        const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
+        const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
+        const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
+        ScreenAabb sa;
+        bool visible = true;
+        if (project_aabb(r0, r1, r2, r3, p.near_clip, cx, cy, cz, ex, ey, ez, sa))
+          visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, hiz_off);
+        q_res[slot] = visible ? 1 : 0;
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) { n_occ_s = 0; n_amb_s = 0; }
+    }
+    // ---- phase D: verdicts -> mask + survivor list ----
+    uint32_t emit_bits = 0;
+#pragma unroll
+    for (int k = 0; k < CULL_ITEMS; k++) {
+      const bool valid = mi[k].x != 0xFFFFFFFFu;
+      const bool was_visible = (was_bits >> k) & 1u;
+      bool visible = (vis_bits >> k) & 1u;
+      if (HIZ && ((pending_bits >> k) & 1u)) visible = q_res[k * CULL_THREADS + threadIdx.x] != 0;
       // :81-87 mask rewrite: XOR of the changed own bits, aggregated per word within the warp
       if (OCC) {
         const bool changed = valid && (visible != was_visible);
@@ -317,7 +389,7 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
       if (visible && (!LATE || !was_visible)) emit_bits |= 1u << k; // :67
     }
     // ---- compaction: warp ballots -> CTA scan -> one atomic per tile ----
-    uint32_t my_off = 0, warp_total = 0;
+    uint32_t warp_total = 0;
     uint32_t offs[CULL_ITEMS];
 #pragma unroll
     for (int k = 0; k < CULL_ITEMS; k++) {
@@ -325,7 +397,6 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
       offs[k] = warp_total + __popc(bal & ((1u << lane) - 1u));
       warp_total += __popc(bal);
     }
-    (void)my_off;
     if (lane == 0) warp_cnt[warp] = warp_total;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -349,7 +420,7 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
     for (int k = 0; k < CULL_ITEMS; k++)
       if ((emit_bits >> k) & 1u)
         p.visible_indices[wbase + offs[k]] = tile_first + k * CULL_THREADS + threadIdx.x + id_base; // :76
-    __syncthreads(); // warp_cnt / tile_base_s reuse
+    __syncthreads(); // warp_cnt / tile_base_s / queues reuse
   }
 }
 

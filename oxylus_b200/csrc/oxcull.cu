@@ -121,6 +121,7 @@ struct OxcContext {
   uint32_t* d_view_counts = nullptr;
   // launch shapes
   int occ_cull[2][2][2] = {};
+  bool hiz_zero = true; // the pyramid holds the cleared (all-zero) image: lets the early pass skip the Hi-Z fetches
   int occ_tri = 1, occ_raster = 1, occ_mv = 1;
 };
 
@@ -250,14 +251,12 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   OxcDrawIndexedIndirectCommand dc{0, 1, 0, 0, 0};
   CK(cudaMemcpy(c->d_draw_cmd, &dc, sizeof dc, cudaMemcpyHostToDevice));
 #define OCC(dst, kern, threads) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(dst), kern, threads, 0))
-  OCC(c->occ_cull[0][0][0], (k_cull_meshlets<false, false, false>), CULL_THREADS);
-  OCC(c->occ_cull[0][0][1], (k_cull_meshlets<false, false, true>), CULL_THREADS);
-  OCC(c->occ_cull[0][1][0], (k_cull_meshlets<false, true, false>), CULL_THREADS);
-  OCC(c->occ_cull[0][1][1], (k_cull_meshlets<false, true, true>), CULL_THREADS);
-  OCC(c->occ_cull[1][0][0], (k_cull_meshlets<true, false, false>), CULL_THREADS);
-  OCC(c->occ_cull[1][0][1], (k_cull_meshlets<true, false, true>), CULL_THREADS);
-  OCC(c->occ_cull[1][1][0], (k_cull_meshlets<true, true, false>), CULL_THREADS);
-  OCC(c->occ_cull[1][1][1], (k_cull_meshlets<true, true, true>), CULL_THREADS);
+  OCC(c->occ_cull[0][0][0], (k_cull_meshlets<false, false, false, false>), CULL_THREADS);
+  OCC(c->occ_cull[1][0][0], (k_cull_meshlets<true, false, false, false>), CULL_THREADS);
+  OCC(c->occ_cull[1][0][1], (k_cull_meshlets<true, false, true, false>), CULL_THREADS);
+  OCC(c->occ_cull[1][1][0], (k_cull_meshlets<true, true, false, false>), CULL_THREADS);
+  OCC(c->occ_cull[1][1][1], (k_cull_meshlets<true, true, true, false>), CULL_THREADS);
+  c->occ_cull[0][0][1] = c->occ_cull[0][1][0] = c->occ_cull[0][1][1] = c->occ_cull[0][0][0];
   OCC(c->occ_tri, k_cull_triangles, TRI_THREADS);
   OCC(c->occ_raster, k_raster_visbuffer, TRI_THREADS);
   OCC(c->occ_mv, k_cull_meshlets_multiview, CULL_THREADS);
@@ -338,6 +337,7 @@ int oxc_clear_hiz(OxcContext* c, void* stream) {
   if (!c) return fail(OXC_E_INVALID, "null context");
   CK(cudaSetDevice(c->device));
   CK(cudaMemsetAsync(c->d_hiz, 0, (size_t)c->hiz_total * 4, static_cast<cudaStream_t>(stream)));
+  c->hiz_zero = true;
   return OXC_OK;
 }
 
@@ -399,12 +399,18 @@ int oxc_cull_meshlets(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, i
   uint32_t grid = (uint32_t)(c->sm_count * (occn > 0 ? occn : 1));
   if (grid > tiles) grid = tiles;
   if (grid == 0) grid = 1;
-#define GO(H, O, L) k_cull_meshlets<H, O, L><<<grid, CULL_THREADS, 0, s>>>(p)
+#define GO(H, O, L, Z) k_cull_meshlets<H, O, L, Z><<<grid, CULL_THREADS, 0, s>>>(p)
+  const bool zero = hizp && c->hiz_zero;
   if (hizp) {
-    if (occ) { if (late) GO(true, true, true); else GO(true, true, false); }
-    else { if (late) GO(true, false, true); else GO(true, false, false); }
+    if (occ) {
+      if (late) { if (zero) GO(true, true, true, true); else GO(true, true, true, false); }
+      else { if (zero) GO(true, true, false, true); else GO(true, true, false, false); }
+    } else {
+      if (late) { if (zero) GO(true, false, true, true); else GO(true, false, true, false); }
+      else { if (zero) GO(true, false, false, true); else GO(true, false, false, false); }
+    }
   } else {
-    GO(false, false, false);
+    GO(false, false, false, false);
   }
 #undef GO
   LAUNCHED();
@@ -431,6 +437,7 @@ static int build_hiz_impl(OxcContext* c, const float* depth_dev, uint32_t stride
     LAUNCHED();
     if (p.levels > 1) { k_hiz_tail<<<1, 1024, 0, s>>>(p, 1); LAUNCHED(); }
   }
+  c->hiz_zero = false;
   return OXC_OK;
 }
 
