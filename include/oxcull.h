@@ -316,6 +316,9 @@ int oxc_copy(OxcContext* ctx, void* dst, const void* src, uint64_t bytes, int ki
 int oxc_sync(OxcContext* ctx, void* stream);
 int oxc_device_alloc(OxcContext* ctx, uint64_t bytes, void** out);
 int oxc_device_free(OxcContext* ctx, void* ptr);
+/* Test hook: evaluates both device implementations of com::dequantize_half (common/math.slang:193-201) on all
+ * 65536 inputs into two float[65536] device arrays. */
+int oxc_debug_dequantize_half(OxcContext* ctx, float* canonical_dev, float* hw_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * oxr_* — host-side mirror of the reference's frame sequencing (C++ class ox::RendererInstance in

@@ -19,7 +19,7 @@ SYMBOLS = [
     "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_cull_meshes",
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_cull_triangles", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview",
-    "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free",
+    "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_render",
 ]
 
@@ -70,6 +70,7 @@ def load(build_if_missing=True):
     lib.oxc_sync.argtypes = [vp, vp]
     lib.oxc_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     lib.oxc_device_free.argtypes = [vp, vp]
+    lib.oxc_debug_dequantize_half.argtypes = [vp, vp, vp, vp]
     lib.oxr_create.argtypes = [i32, C.POINTER(abi.CreateInfo), u32, u32, C.POINTER(vp)]
     lib.oxr_destroy.argtypes = [vp]
     lib.oxr_destroy.restype = None

@@ -95,6 +95,14 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __gri
 #undef OXC_CROSS
     // scene.slang:304-309 (Slang world[i] = row i)
     ic.nrm[0].w = omax(length3(w[0], w[4], w[8]), omax(length3(w[1], w[5], w[9]), length3(w[2], w[6], w[10])));
+    {  // nrm[1].w: 1.0 when every mvp entry is finite and |x| <= 2^60 (precondition of the filtered projection)
+      bool ok = true;
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        ok = ok && fabsf(rows[k].x) <= 1.152921504606847e18f && fabsf(rows[k].y) <= 1.152921504606847e18f &&
+             fabsf(rows[k].z) <= 1.152921504606847e18f && fabsf(rows[k].w) <= 1.152921504606847e18f;
+      ic.nrm[1].w = ok ? 1.0f : 0.0f;
+    }
     const uint64_t baddr = lod->meshlet_bounds;
     ic.bounds_lo = (uint32_t)baddr;
     ic.bounds_hi = (uint32_t)(baddr >> 32);
@@ -231,30 +239,33 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_expand_meshlet_instance
 //            ONE global atomic per tile (reference: three per surviving lane, :70-78)
 // Outputs are bit-identical to the canonical path for every input (oxc_filtered.cuh).
 // ------------------------------------------------------------------------------------------------
-struct __align__(16) OccWork {
-  uint4 bounds;
+constexpr int CULL_WARP_ITEMS = 32 * CULL_ITEMS; // items owned by one warp per tile
+
+// one queued Hi-Z test: decoded bounds + instance + the owner's slot (item k of lane l: k*32 + l)
+struct __align__(16) OccEntry {
+  float cx, cy, cz, ex;
+  float ey, ez;
+  uint32_t inst, slot;
 };
 
 template <bool HIZ, bool OCC, bool LATE, bool ZERO>
-__global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_constant__ CullParams p) {
+__global__ void __launch_bounds__(CULL_THREADS, 4) k_cull_meshlets(const __grid_constant__ CullParams p) {
   __shared__ uint32_t hiz_off[OXC_HIZ_MAX_LEVELS];
   __shared__ uint32_t warp_cnt[CULL_THREADS / 32];
   __shared__ uint32_t tile_base_s;
   __shared__ float s8_lut[256]; // scene.slang:408-418: i8 / 127.0 for every i8 (IEEE divide, once per CTA)
-  __shared__ uint4 q_bounds[HIZ ? CULL_TILE : 1];    // per slot: MeshletBounds of items queued for the Hi-Z test
-  __shared__ uint32_t q_inst[HIZ ? CULL_TILE : 1];   // per slot: mesh instance index
-  __shared__ uint16_t q_occ[HIZ ? CULL_TILE : 1];    // queue of slots for phase B
-  __shared__ uint16_t q_amb[HIZ ? CULL_TILE : 1];    // queue of slots for phase C
-  __shared__ uint8_t q_res[HIZ ? CULL_TILE : 1];     // verdict per slot (1 = visible)
-  __shared__ uint32_t n_occ_s, n_amb_s;
+  // warp-private queues: no CTA barrier between the phases
+  __shared__ OccEntry q_ent[HIZ ? CULL_THREADS / 32 : 1][HIZ ? CULL_WARP_ITEMS : 1];
+  __shared__ uint8_t q_amb[HIZ ? CULL_THREADS / 32 : 1][HIZ ? CULL_WARP_ITEMS : 1]; // entry indices needing the canonical path
+  __shared__ uint8_t q_res[HIZ ? CULL_THREADS / 32 : 1][HIZ ? CULL_WARP_ITEMS : 1]; // verdict per owner slot
   if (threadIdx.x < OXC_HIZ_MAX_LEVELS) hiz_off[threadIdx.x] = p.hiz.level_offset[threadIdx.x];
   s8_lut[threadIdx.x] = s8_over_127((int)threadIdx.x - 128);
-  if (threadIdx.x == 0) { n_occ_s = 0; n_amb_s = 0; }
   __syncthreads();
   const uint32_t total = p.vis->total_visible_meshlet_instances; // :26
   const uint32_t early_count = LATE ? p.vis->early_visible_meshlet_instances : 0u; // :73 (final: early kernel completed)
   const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t lane_lt = (1u << lane) - 1u;
   const uint32_t n_tiles = (total + CULL_TILE - 1) / CULL_TILE;
   const uint2* mi2 = reinterpret_cast<const uint2*>(p.meshlet_instances);
 
@@ -297,16 +308,19 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
     }
     uint32_t vis_bits = 0;     // bit k: verdict so far
     uint32_t pending_bits = 0; // bit k: verdict comes from the queue (q_res)
+    uint32_t n_occ = 0;        // warp-uniform queue length
 #pragma unroll
     for (int k = 0; k < CULL_ITEMS; k++) {
       const bool valid = mi[k].x != 0xFFFFFFFFu;
       bool visible = valid && (LATE ? true : ((was_bits >> k) & 1u)); // :57
+      bool queue = false;
+      float cx = 0.f, cy = 0.f, cz = 0.f, ex = 0.f, ey = 0.f, ez = 0.f;
       if (visible) {
         const InstCull* ic = p.inst + mi[k].x;
         const uint4 b = bnd[k];
         // scene.slang:401-435 unpack: u16x3 center | i8x2 cone xy | u16x3 extent | i8 cone z | i8 cutoff
-        const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
-        const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
+        cx = dequantize_half_hw(b.x & 0xFFFFu); cy = dequantize_half_hw(b.x >> 16); cz = dequantize_half_hw(b.y & 0xFFFFu);
+        ex = dequantize_half_hw(b.z & 0xFFFFu); ey = dequantize_half_hw(b.z >> 16); ez = dequantize_half_hw(b.w & 0xFFFFu);
         // :59 frustum (canonical; evaluated first: the three tests commute)
         visible = test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
         // :58 cone
@@ -320,53 +334,57 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
         }
         // :61-65 occlusion
         if (HIZ && (OCC || LATE) && visible) {
-          bool queue = true;
+          queue = true;
           if (ZERO) queue = !cleared_hiz_surely_visible(__ldg(&ic->mvp_row[2]), __ldg(&ic->mvp_row[3]), cx, cy, cz, ex, ey, ez);
-          if (queue) {
-            const uint32_t slot = k * CULL_THREADS + threadIdx.x;
-            q_bounds[slot] = b;
-            q_inst[slot] = mi[k].x;
-            q_occ[atomicAdd(&n_occ_s, 1u)] = (uint16_t)slot;
-            pending_bits |= 1u << k;
-          }
         }
+      }
+      if (HIZ) { // append to the warp's dense queue (ballot prefix: no atomics)
+        const uint32_t bal = __ballot_sync(0xffffffffu, queue);
+        if (queue) {
+          OccEntry e;
+          e.cx = cx; e.cy = cy; e.cz = cz; e.ex = ex; e.ey = ey; e.ez = ez; e.inst = mi[k].x; e.slot = k * 32 + lane;
+          q_ent[warp][n_occ + __popc(bal & lane_lt)] = e;
+          pending_bits |= 1u << k;
+        }
+        n_occ += __popc(bal);
       }
       vis_bits |= (visible ? 1u : 0u) << k;
     }
     if (HIZ) {
-      // ---- phase B: dense Hi-Z tests ----
-      __syncthreads();
-      const uint32_t n_occ = n_occ_s;
-      for (uint32_t j = threadIdx.x; j < n_occ; j += CULL_THREADS) {
-        const uint32_t slot = q_occ[j];
-        const uint4 b = q_bounds[slot];
-        const InstCull* ic = p.inst + q_inst[slot];
-        const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
-        const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
-        const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
-        const Tri t = occlusion_visible_fast(r0, r1, r2, r3, p.near_clip, cx, cy, cz, ex, ey, ez, p.hiz.data, p.hiz.width,
-                                             p.hiz.height, p.hiz.levels, hiz_off);
-        if (t == TRI_AMBIGUOUS) q_amb[atomicAdd(&n_amb_s, 1u)] = (uint16_t)slot;
-        else q_res[slot] = (uint8_t)t;
+      // ---- phase B: the warp consumes its queue densely ----
+      __syncwarp();
+      uint32_t n_amb = 0;
+      for (uint32_t j0 = 0; j0 < n_occ; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        Tri t = TRI_TRUE;
+        if (j < n_occ) {
+          const OccEntry e = q_ent[warp][j];
+          const InstCull* ic = p.inst + e.inst;
+          const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
+          t = occlusion_visible_fast(r0, r1, r2, r3, p.near_clip, e.cx, e.cy, e.cz, e.ex, e.ey, e.ez, p.hiz.data, p.hiz.width,
+                                     p.hiz.height, p.hiz.levels, hiz_off, __ldg(&ic->nrm[1].w) != 0.0f);
+          if (t != TRI_AMBIGUOUS) q_res[warp][e.slot] = (uint8_t)t;
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, t == TRI_AMBIGUOUS);
+        if (t == TRI_AMBIGUOUS) q_amb[warp][n_amb + __popc(bal & lane_lt)] = (uint8_t)j;
+        n_amb += __popc(bal);
       }
-      // ---- phase C: canonical evaluation of the margin-ambiguous items ----
-      __syncthreads();
-      const uint32_t n_amb = n_amb_s;
-      for (uint32_t j = threadIdx.x; j < n_amb; j += CULL_THREADS) {
-        const uint32_t slot = q_amb[j];
-        const uint4 b = q_bounds[slot];
-        const InstCull* ic = p.inst + q_inst[slot];
-        const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
-        const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
-        const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
-        ScreenAabb sa;
-        bool visible = true;
-        if (project_aabb(r0, r1, r2, r3, p.near_clip, cx, cy, cz, ex, ey, ez, sa))
-          visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, hiz_off);
-        q_res[slot] = visible ? 1 : 0;
+      // ---- phase C: canonical evaluation of the margin-ambiguous entries (a fraction of a percent) ----
+      __syncwarp();
+      for (uint32_t a0 = 0; a0 < n_amb; a0 += 32) {
+        const uint32_t a = a0 + lane;
+        if (a < n_amb) {
+          const OccEntry e = q_ent[warp][q_amb[warp][a]];
+          const InstCull* ic = p.inst + e.inst;
+          const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
+          ScreenAabb sa;
+          bool visible = true;
+          if (project_aabb(r0, r1, r2, r3, p.near_clip, e.cx, e.cy, e.cz, e.ex, e.ey, e.ez, sa))
+            visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, hiz_off);
+          q_res[warp][e.slot] = visible ? 1 : 0;
+        }
       }
-      __syncthreads();
-      if (threadIdx.x == 0) { n_occ_s = 0; n_amb_s = 0; }
+      __syncwarp();
     }
     // ---- phase D: verdicts -> mask + survivor list ----
     uint32_t emit_bits = 0;
@@ -375,7 +393,7 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets(const __grid_con
       const bool valid = mi[k].x != 0xFFFFFFFFu;
       const bool was_visible = (was_bits >> k) & 1u;
       bool visible = (vis_bits >> k) & 1u;
-      if (HIZ && ((pending_bits >> k) & 1u)) visible = q_res[k * CULL_THREADS + threadIdx.x] != 0;
+      if (HIZ && ((pending_bits >> k) & 1u)) visible = q_res[warp][k * 32 + lane] != 0;
       // :81-87 mask rewrite: XOR of the changed own bits, aggregated per word within the warp
       if (OCC) {
         const bool changed = valid && (visible != was_visible);

@@ -5,6 +5,8 @@
 // The __f*_rn intrinsics are never contracted by nvcc, whatever -fmad says.
 // Reference lines: Oxylus/src/Render/Shaders/cull.slang, scene.slang, common/math.slang.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "oxc_types.cuh"
 
 namespace oxc {
@@ -34,6 +36,13 @@ OXC_DI float dequantize_half(uint32_t h) {
   r = (em < (1u << 10)) ? 0u : r;
   r += (em >= (31u << 10)) ? (112u << 23) : 0u;
   return __uint_as_float(s | r);
+}
+
+// Same function through the hardware half->float conversion: identical for all 65536 inputs up to NaN
+// payloads (hardware quiets signalling NaNs; every consumer only compares).  ~4 instructions instead of ~10.
+OXC_DI float dequantize_half_hw(uint32_t h) {
+  const float f = __half2float(__ushort_as_half((unsigned short)h));
+  return (h & 0x7C00u) == 0u ? __uint_as_float((h & 0x8000u) << 16) : f; // denormals flush to signed zero
 }
 
 // scene.slang:408-418: i8 / 127.0

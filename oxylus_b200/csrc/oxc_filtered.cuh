@@ -106,7 +106,13 @@ OXC_DI bool texel_safe_hi(float t_raw, float size_m1, float delta) { // u32(min(
 
 OXC_DI Tri occlusion_visible_fast(const float4 r0, const float4 r1, const float4 r2, const float4 r3, float near_clip,
                                   float cx, float cy, float cz, float ex, float ey, float ez, const float* __restrict__ hiz,
-                                  uint32_t hw_u, uint32_t hh_u, uint32_t levels, const uint32_t* hiz_off) {
+                                  uint32_t hw_u, uint32_t hh_u, uint32_t levels, const uint32_t* hiz_off, bool mvp_ok) {
+  // Preconditions that rule out NaN / Inf in the corner arithmetic (then fminf/fmaxf == the canonical
+  // `a < b ? a : b` up to the sign of zero, which no consumer observes): |mvp| <= 2^60 (InstCull flag), bounds
+  // finite (|half| <= 65504 => |products| < 2^77), W >= 1e-18 so the reciprocal stays finite.
+  if (!mvp_ok || !(fabsf(cx) <= 65504.0f && fabsf(cy) <= 65504.0f && fabsf(cz) <= 65504.0f && fabsf(ex) <= 65504.0f &&
+                   fabsf(ey) <= 65504.0f && fabsf(ez) <= 65504.0f))
+    return TRI_AMBIGUOUS;
   // --- canonical corner construction (same ops as project_aabb) ---
   const float SXx = fm(r0.x, ex), SXy = fm(r1.x, ex), SXz = fm(r2.x, ex), SXw = fm(r3.x, ex);
   const float SYx = fm(r0.y, ey), SYy = fm(r1.y, ey), SYz = fm(r2.y, ey), SYw = fm(r3.y, ey);
@@ -119,10 +125,9 @@ OXC_DI Tri occlusion_visible_fast(const float4 r0, const float4 r1, const float4
   OXC_ADDV(1, 0, SZ) OXC_ADDV(2, 0, SY) OXC_ADDV(3, 2, SZ) OXC_ADDV(4, 0, SX)
   OXC_ADDV(5, 4, SZ) OXC_ADDV(6, 4, SY) OXC_ADDV(7, 6, SZ)
 #undef OXC_ADDV
-  float depth = W[7];
-#pragma unroll
-  for (int i = 6; i >= 0; i--) depth = omin(W[i], depth);
+  const float depth = fminf(fminf(fminf(W[0], W[1]), fminf(W[2], W[3])), fminf(fminf(W[4], W[5]), fminf(W[6], W[7])));
   if (depth < near_clip) return TRI_TRUE; // project_aabb == none => visible (cull_meshlets_hiz.slang:62-64)
+  if (!(depth >= 1e-18f)) return TRI_AMBIGUOUS;
   // --- fast perspective divide ---
   float mnx, mny, mxx, mxy, mxz;
 #pragma unroll
@@ -131,8 +136,8 @@ OXC_DI Tri occlusion_visible_fast(const float4 r0, const float4 r1, const float4
     const float dx = X[i] * r, dy = Y[i] * r, dz = Z[i] * r;
     if (i == 7) { mnx = mxx = dx; mny = mxy = dy; mxz = dz; }
     else {
-      mnx = omin(dx, mnx); mny = omin(dy, mny);
-      mxx = omax(dx, mxx); mxy = omax(dy, mxy); mxz = omax(dz, mxz);
+      mnx = fminf(dx, mnx); mny = fminf(dy, mny);
+      mxx = fmaxf(dx, mxx); mxy = fmaxf(dy, mxy); mxz = fmaxf(dz, mxz);
     }
   }
   const float hw = (float)hw_u, hh = (float)hh_u;

@@ -70,6 +70,12 @@ __global__ void k_reset_visibility(OxcMeshletInstanceVisibility* v, OxcDispatchI
   c->x = 0; c->y = 1; c->z = 1;
 }
 
+// debug: both half decoders over all 65536 inputs (tests/test_gpu_parity.py::test_dequantize_half_all_inputs)
+__global__ void k_debug_dequantize(float* canonical, float* hw) {
+  const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < 65536u) { canonical[h] = dequantize_half(h); hw[h] = dequantize_half_hw(h); }
+}
+
 uint32_t ilog2(uint32_t v) { uint32_t r = 0; while ((1u << r) < v) r++; return r; }
 bool is_pow2(uint32_t v) { return v && !(v & (v - 1)); }
 
@@ -560,6 +566,14 @@ int oxc_cull_meshlets_multiview(OxcContext* c, const OxcCullCamera* views, uint3
   if (grid > blocks) grid = blocks;
   if (grid == 0) grid = 1;
   k_cull_meshlets_multiview<<<grid, CULL_THREADS, 0, s>>>(p);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+int oxc_debug_dequantize_half(OxcContext* c, float* canonical_dev, float* hw_dev, void* stream) {
+  if (!c || !canonical_dev || !hw_dev) return fail(OXC_E_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  k_debug_dequantize<<<256, 256, 0, static_cast<cudaStream_t>(stream)>>>(canonical_dev, hw_dev);
   LAUNCHED();
   return OXC_OK;
 }

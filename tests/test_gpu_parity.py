@@ -269,3 +269,21 @@ def test_call_sequence_errors(capi):
     with pytest.raises(capi.OxcError):
         capi.Context(0, 4, 64, 48, 64)  # non power-of-two hiz
     ctx.close()
+
+
+def test_dequantize_half_all_inputs(capi, orc):
+    """both device decoders vs the oracle for all 65536 half patterns (NaN payloads may differ: hardware quiets sNaNs)."""
+    ctx = capi.Context(0, 1, 1, 64, 64)
+    a, b = ctx.alloc(65536 * 4), ctx.alloc(65536 * 4)
+    rc = ctx.lib.oxc_debug_dequantize_half(ctx.h, a, b, ctx.stream)
+    assert rc == 0
+    canon = ctx.download(a, np.float32, 65536)
+    hw = ctx.download(b, np.float32, 65536)
+    want = np.array([orc.dequantize_half(h) for h in range(65536)], dtype=np.float32)
+    nan = np.isnan(want)
+    np.testing.assert_array_equal(canon.view(np.uint32), want.view(np.uint32))
+    np.testing.assert_array_equal(hw[~nan].view(np.uint32), want[~nan].view(np.uint32))
+    assert np.all(np.isnan(hw[nan]))
+    ctx.free(a)
+    ctx.free(b)
+    ctx.close()
