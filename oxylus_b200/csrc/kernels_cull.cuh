@@ -7,8 +7,8 @@ namespace oxc {
 
 constexpr int CULL_MESHES_THREADS = 256;
 constexpr int CULL_THREADS = 256;
-constexpr int CULL_ITEMS = 4;                          // meshlet instances per thread per tile
-constexpr int CULL_TILE = CULL_THREADS * CULL_ITEMS;   // 1024 per CTA iteration -> one atomic per 1024
+constexpr int CULL_ITEMS = 2;                          // meshlet instances per thread per tile
+constexpr int CULL_TILE = CULL_THREADS * CULL_ITEMS;   // 512 per CTA iteration -> one atomic per 512
 
 struct MeshesParams {
   const OxcMesh* meshes;
@@ -16,6 +16,7 @@ struct MeshesParams {
   const OxcTransformWorld* transforms;
   InstCull* inst;
   InstGeom* geom;
+  const float* lod_aabb; // [mesh][OXC_MESH_MAX_LODS][6]: union AABB (min xyz, max xyz) of the decoded meshlet boxes
   uint32_t* counts;      // per mesh instance of the shard (index - first)
   uint32_t* block_sums;
   uint32_t first, count; // shard
@@ -103,6 +104,33 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __gri
              fabsf(rows[k].z) <= 1.152921504606847e18f && fabsf(rows[k].w) <= 1.152921504606847e18f;
       ic.nrm[1].w = ok ? 1.0f : 0.0f;
     }
+    {  // nrm[2].w: 1.0 when every meshlet box of the selected LOD is provably inside all six planes for the
+       // canonical test, so the per-meshlet frustum test can be skipped.  U = union AABB of the decoded meshlet
+       // boxes (inflated for the rounding of c +- h).  The canonical test rejects only if fl(dot(p,n)) <= -w; its
+       // rounding error is <= 3.1u * sum|p_i| <= 3.1u * B with B = sum_i max(|Umin_i|, |Umax_i|), and the real
+       // p-vertex value is >= the n-vertex value of U.  Require n-vertex(U) + w > 2^-18 (B + |w|)  (64u: > 8x slack
+       // incl. the rounding of this very evaluation).
+      const float* ua = p.lod_aabb + ((size_t)inst.mesh_index * OXC_MESH_MAX_LODS + lod_index) * 6;
+      bool inside = p.lod_aabb != nullptr;
+      float B = 0.0f;
+      float lo[3], hi[3];
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const float mn = ua[a], mx = ua[3 + a];
+        const float pad = fmaxf(fabsf(mn), fabsf(mx)) * 4.76837158203125e-07f; // 2^-21 relative inflation
+        lo[a] = mn - pad; hi[a] = mx + pad;
+        B += fmaxf(fabsf(lo[a]), fabsf(hi[a]));
+        inside = inside && (mn <= mx); // NaN / empty => false
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) {
+        const float4 pl = planes[k];
+        const float vx = pl.x >= 0.0f ? lo[0] : hi[0], vy = pl.y >= 0.0f ? lo[1] : hi[1], vz = pl.z >= 0.0f ? lo[2] : hi[2];
+        const float sv = fmaf(vx, pl.x, fmaf(vy, pl.y, fmaf(vz, pl.z, pl.w)));
+        inside = inside && (sv > (B + fabsf(pl.w)) * 3.814697265625e-06f);
+      }
+      ic.nrm[2].w = inside ? 1.0f : 0.0f;
+    }
     const uint64_t baddr = lod->meshlet_bounds;
     ic.bounds_lo = (uint32_t)baddr;
     ic.bounds_hi = (uint32_t)(baddr >> 32);
@@ -134,6 +162,45 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __gri
 #pragma unroll
     for (int k = 0; k < CULL_MESHES_THREADS / 32; k++) s += warp_sums[k];
     p.block_sums[blockIdx.x] = s;
+  }
+}
+
+// One-time per scene: union AABB of the DECODED meshlet boxes (c +- e/2) of every (mesh, LOD).  One warp per
+// (mesh, lod).  Feeds the instance-level "provably inside the frustum" shortcut.
+__global__ void k_lod_union_aabb(const OxcMesh* __restrict__ meshes, uint32_t n_meshes, float* __restrict__ out) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (w >= n_meshes * OXC_MESH_MAX_LODS) return;
+  const uint32_t m = w / OXC_MESH_MAX_LODS, l = w % OXC_MESH_MAX_LODS;
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  bool bad = false;
+  if (l < meshes[m].lod_count) {
+    const OxcMeshLOD* lod = reinterpret_cast<const OxcMeshLOD*>(meshes[m].lods) + l;
+    const uint4* b = reinterpret_cast<const uint4*>(lod->meshlet_bounds);
+    for (uint32_t i = lane; i < lod->meshlet_bounds_count; i += 32) {
+      const uint4 v = b[i];
+      const float c[3] = {dequantize_half(v.x & 0xFFFFu), dequantize_half(v.x >> 16), dequantize_half(v.y & 0xFFFFu)};
+      const float e[3] = {dequantize_half(v.z & 0xFFFFu), dequantize_half(v.z >> 16), dequantize_half(v.w & 0xFFFFu)};
+#pragma unroll
+      for (int a = 0; a < 3; a++) {
+        const float h = fabsf(e[a]) * 0.5f;
+        const float a0 = c[a] - h, a1 = c[a] + h;
+        bad = bad || !(fabsf(a0) <= 3.0e38f) || !(fabsf(a1) <= 3.0e38f);
+        mn[a] = fminf(mn[a], a0); mx[a] = fmaxf(mx[a], a1);
+      }
+    }
+  } else bad = true;
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    float* o = out + (size_t)w * 6;
+    if (bad) { o[0] = o[1] = o[2] = 1.0f; o[3] = o[4] = o[5] = -1.0f; } // empty => shortcut disabled
+    else { o[0] = mn[0]; o[1] = mn[1]; o[2] = mn[2]; o[3] = mx[0]; o[4] = mx[1]; o[5] = mx[2]; }
   }
 }
 
@@ -321,8 +388,9 @@ __global__ void __launch_bounds__(CULL_THREADS, 4) k_cull_meshlets(const __grid_
         // scene.slang:401-435 unpack: u16x3 center | i8x2 cone xy | u16x3 extent | i8 cone z | i8 cutoff
         cx = dequantize_half_hw(b.x & 0xFFFFu); cy = dequantize_half_hw(b.x >> 16); cz = dequantize_half_hw(b.y & 0xFFFFu);
         ex = dequantize_half_hw(b.z & 0xFFFFu); ey = dequantize_half_hw(b.z >> 16); ez = dequantize_half_hw(b.w & 0xFFFFu);
-        // :59 frustum (canonical; evaluated first: the three tests commute)
-        visible = test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
+        // :59 frustum (canonical; evaluated first: the three tests commute).  Skipped when the whole instance is
+        // provably inside every plane for the canonical test (InstCull::nrm[2].w, see k_cull_meshes).
+        if (__ldg(&ic->nrm[2].w) == 0.0f) visible = test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
         // :58 cone
         const float cutoff = s8_lut[((b.w >> 24) + 128u) & 0xFFu];
         if (visible && cutoff < 1.0f) {

@@ -233,7 +233,48 @@ OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* v
 
 constexpr int RASTER_BIG_PIXELS = 32; // bbox area above which the whole warp rasterises the triangle together
 
-__global__ void __launch_bounds__(TRI_THREADS) k_raster_visbuffer(const __grid_constant__ TriParams p) {
+// Header of one surviving meshlet, fetched by ONE lane (32 headers in flight per warp): the 4-level pointer
+// chase visible_indices -> meshlet_instances -> InstGeom -> Meshlet is paid once per 32 meshlets per warp.
+struct MeshletHeader {
+  uint32_t gid, inst, vertex_offset, vertex_count, tri_offset, tri_count;
+  const uint32_t* micro;
+  const uint32_t* vidx;
+  const uint2* pos;
+};
+
+OXC_DI MeshletHeader fetch_header(const TriParams& p, uint32_t slot, uint32_t id_base) {
+  MeshletHeader h;
+  h.gid = __ldg(&p.visible_indices[slot]);                                                    // cull_triangles.slang:44
+  const uint2 mi = __ldg(reinterpret_cast<const uint2*>(p.meshlet_instances) + (h.gid - id_base)); // :45
+  const InstGeom* g = p.geom + mi.x;
+  const uint4 g0 = __ldg(reinterpret_cast<const uint4*>(g));      // meshlets, local_triangle_indices
+  const uint4 g1 = __ldg(reinterpret_cast<const uint4*>(g) + 1);  // indirect_vertex_indices, vertex_positions
+  const OxcMeshlet* meshlets = reinterpret_cast<const OxcMeshlet*>(((uint64_t)g0.y << 32) | g0.x);
+  const uint4 m = __ldg(reinterpret_cast<const uint4*>(meshlets + mi.y));                    // :49
+  h.inst = mi.x;
+  h.vertex_offset = m.x;
+  h.tri_offset = m.y;
+  h.vertex_count = min(m.z, (uint32_t)OXC_MESHLET_MAX_VERTICES);
+  h.tri_count = min(m.w, (uint32_t)OXC_MESHLET_MAX_PRIMITIVES);
+  h.micro = reinterpret_cast<const uint32_t*>(((uint64_t)g0.w << 32) | g0.z);
+  h.vidx = reinterpret_cast<const uint32_t*>(((uint64_t)g1.y << 32) | g1.x) + m.x;
+  h.pos = reinterpret_cast<const uint2*>(((uint64_t)g1.w << 32) | g1.z);
+  return h;
+}
+
+OXC_DI MeshletHeader bcast_header(const MeshletHeader& h, int src) {
+  MeshletHeader o;
+  o.gid = __shfl_sync(0xffffffffu, h.gid, src); o.inst = __shfl_sync(0xffffffffu, h.inst, src);
+  o.vertex_offset = 0;
+  o.vertex_count = __shfl_sync(0xffffffffu, h.vertex_count, src);
+  o.tri_offset = __shfl_sync(0xffffffffu, h.tri_offset, src); o.tri_count = __shfl_sync(0xffffffffu, h.tri_count, src);
+  o.micro = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(h.micro), src));
+  o.vidx = reinterpret_cast<const uint32_t*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(h.vidx), src));
+  o.pos = reinterpret_cast<const uint2*>(__shfl_sync(0xffffffffu, reinterpret_cast<unsigned long long>(h.pos), src));
+  return o;
+}
+
+__global__ void __launch_bounds__(TRI_THREADS, 3) k_raster_visbuffer(const __grid_constant__ TriParams p) {
   __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   __shared__ ScreenVert scr_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -244,52 +285,87 @@ __global__ void __launch_bounds__(TRI_THREADS) k_raster_visbuffer(const __grid_c
   float4* clip_s = clip_all[warp];
   ScreenVert* scr_s = scr_all[warp];
   uint32_t kept = 0;
-  for (uint32_t g = blockIdx.x * TRI_WARPS + warp; g < count; g += gridDim.x * TRI_WARPS) {
-    const MeshletWork w = load_meshlet(p, first + g, id_base, clip_s, lane);
-    for (uint32_t v = lane; v < OXC_MESHLET_MAX_VERTICES; v += 32) scr_s[v] = to_screen(clip_s[v], fW, fH);
-    __syncwarp();
-    const uint32_t rounds = (w.tri_count + 31u) >> 5;
-    for (uint32_t k = 0; k < rounds; k++) {
-      const uint32_t t = lane + 32u * k;
-      bool pass = false;
-      TriSetup s;
-      bool draw = false;
-      if (t < w.tri_count) {
-        const uint32_t base = w.tri_offset + t * 3u;
-        const uint32_t i0 = micro_index(w.micro, base + 0u), i1 = micro_index(w.micro, base + 1u), i2 = micro_index(w.micro, base + 2u);
-        const float4 c0 = clip_s[i0], c1 = clip_s[i1], c2 = clip_s[i2];
-        pass = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f && !triangle_backface(c0, c1, c2); // cull_triangles.slang:68-69
-        if (pass) draw = tri_setup(scr_s[i0], scr_s[i1], scr_s[i2], p.width, p.height, s);
+  // a warp owns batches of 32 consecutive survivors
+  for (uint32_t g0 = (blockIdx.x * TRI_WARPS + warp) * 32u; g0 < count; g0 += gridDim.x * TRI_WARPS * 32u) {
+    const uint32_t nb = min(32u, count - g0);
+    MeshletHeader mine;
+    mine.gid = 0; mine.inst = 0; mine.vertex_offset = 0; mine.vertex_count = 0; mine.tri_offset = 0; mine.tri_count = 0;
+    mine.micro = nullptr; mine.vidx = nullptr; mine.pos = nullptr;
+    if (lane < nb) mine = fetch_header(p, first + g0 + lane, id_base);
+    // vertex indices of the first meshlet, prefetched one meshlet ahead from here on
+    MeshletHeader cur = bcast_header(mine, 0);
+    uint32_t vi0 = lane < cur.vertex_count ? __ldg(&cur.vidx[lane]) : 0u;
+    uint32_t vi1 = lane + 32u < cur.vertex_count ? __ldg(&cur.vidx[lane + 32u]) : 0u;
+    for (uint32_t j = 0; j < nb; j++) {
+      const MeshletHeader w = cur;
+      // positions of this meshlet (indices already here) ...
+      const uint2 q0 = lane < w.vertex_count ? __ldg(&w.pos[vi0]) : make_uint2(0, 0);
+      const uint2 q1 = lane + 32u < w.vertex_count ? __ldg(&w.pos[vi1]) : make_uint2(0, 0);
+      // ... and the next meshlet's vertex indices, in flight while this one is rasterised
+      if (j + 1 < nb) {
+        cur = bcast_header(mine, (int)(j + 1));
+        vi0 = lane < cur.vertex_count ? __ldg(&cur.vidx[lane]) : 0u;
+        vi1 = lane + 32u < cur.vertex_count ? __ldg(&cur.vidx[lane + 32u]) : 0u;
       }
-      kept += pass ? 1u : 0u;
-      const uint32_t data = (w.data_id << OXC_VIS_PRIMITIVE_BITS) | (t & OXC_VIS_PRIMITIVE_MASK);
-      const int bw = draw ? s.px1 - s.px0 + 1 : 0, bh = draw ? s.py1 - s.py0 + 1 : 0;
-      const bool big = draw && (bw * bh > RASTER_BIG_PIXELS);
-      if (draw && !big) raster_small(s, data, p.visbuf, p.width);
-      // large triangles: broadcast the setup; the warp covers the bounding box in 8x4-pixel tiles
-      uint32_t big_mask = __ballot_sync(0xffffffffu, big);
-      while (big_mask) {
-        const int src = __ffs(big_mask) - 1;
-        big_mask &= big_mask - 1;
-        TriSetup b;
-        b.ax = __shfl_sync(0xffffffffu, s.ax, src); b.ay = __shfl_sync(0xffffffffu, s.ay, src);
-        b.bx = __shfl_sync(0xffffffffu, s.bx, src); b.by = __shfl_sync(0xffffffffu, s.by, src);
-        b.cx = __shfl_sync(0xffffffffu, s.cx, src); b.cy = __shfl_sync(0xffffffffu, s.cy, src);
-        b.za = __shfl_sync(0xffffffffu, s.za, src); b.dzb = __shfl_sync(0xffffffffu, s.dzb, src);
-        b.dzc = __shfl_sync(0xffffffffu, s.dzc, src);
-        b.px0 = __shfl_sync(0xffffffffu, s.px0, src); b.px1 = __shfl_sync(0xffffffffu, s.px1, src);
-        b.py0 = __shfl_sync(0xffffffffu, s.py0, src); b.py1 = __shfl_sync(0xffffffffu, s.py1, src);
-        b.bias = __shfl_sync(0xffffffffu, s.bias, src);
-        const uint32_t bdata = __shfl_sync(0xffffffffu, data, src);
-        const int lx = lane & 7, ly = lane >> 3;
-        for (int ty = b.py0; ty <= b.py1; ty += 4)
-          for (int tx = b.px0; tx <= b.px1; tx += 8) {
-            const int px = tx + lx, py = ty + ly;
-            if (px <= b.px1 && py <= b.py1) raster_pixel(b, px, py, bdata, p.visbuf, p.width);
-          }
+      const InstCull* ic = p.inst + w.inst;
+      const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
+      // clip = mvp * (pos,1) once per vertex (visbuffer_encode_ms.slang:135-137), then the screen record
+      {
+        const float x = dequantize_half_hw(q0.x & 0xFFFFu), y = dequantize_half_hw(q0.x >> 16), z = dequantize_half_hw(q0.y & 0xFFFFu);
+        const float4 c = make_float4(row_dot_p1(r0, x, y, z), row_dot_p1(r1, x, y, z), row_dot_p1(r2, x, y, z), row_dot_p1(r3, x, y, z));
+        clip_s[lane] = c;
+        scr_s[lane] = to_screen(c, fW, fH);
       }
+      if (w.vertex_count > 32u) {
+        const float x = dequantize_half_hw(q1.x & 0xFFFFu), y = dequantize_half_hw(q1.x >> 16), z = dequantize_half_hw(q1.y & 0xFFFFu);
+        const float4 c = make_float4(row_dot_p1(r0, x, y, z), row_dot_p1(r1, x, y, z), row_dot_p1(r2, x, y, z), row_dot_p1(r3, x, y, z));
+        clip_s[lane + 32] = c;
+        scr_s[lane + 32] = to_screen(c, fW, fH);
+      }
+      __syncwarp();
+      const uint32_t rounds = (w.tri_count + 31u) >> 5;
+      for (uint32_t k = 0; k < rounds; k++) {
+        const uint32_t t = lane + 32u * k;
+        bool pass = false;
+        TriSetup s;
+        bool draw = false;
+        if (t < w.tri_count) {
+          const uint32_t base = w.tri_offset + t * 3u;
+          const uint32_t i0 = micro_index(w.micro, base + 0u), i1 = micro_index(w.micro, base + 1u), i2 = micro_index(w.micro, base + 2u);
+          const float4 c0 = clip_s[i0], c1 = clip_s[i1], c2 = clip_s[i2];
+          pass = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f && !triangle_backface(c0, c1, c2); // cull_triangles.slang:68-69
+          if (pass) draw = tri_setup(scr_s[i0], scr_s[i1], scr_s[i2], p.width, p.height, s);
+        }
+        kept += pass ? 1u : 0u;
+        const uint32_t data = (w.gid << OXC_VIS_PRIMITIVE_BITS) | (t & OXC_VIS_PRIMITIVE_MASK);
+        const int bw = draw ? s.px1 - s.px0 + 1 : 0, bh = draw ? s.py1 - s.py0 + 1 : 0;
+        const bool big = draw && (bw * bh > RASTER_BIG_PIXELS);
+        if (draw && !big) raster_small(s, data, p.visbuf, p.width);
+        // large triangles: broadcast the setup; the warp covers the bounding box in 8x4-pixel tiles
+        uint32_t big_mask = __ballot_sync(0xffffffffu, big);
+        while (big_mask) {
+          const int src = __ffs(big_mask) - 1;
+          big_mask &= big_mask - 1;
+          TriSetup b;
+          b.ax = __shfl_sync(0xffffffffu, s.ax, src); b.ay = __shfl_sync(0xffffffffu, s.ay, src);
+          b.bx = __shfl_sync(0xffffffffu, s.bx, src); b.by = __shfl_sync(0xffffffffu, s.by, src);
+          b.cx = __shfl_sync(0xffffffffu, s.cx, src); b.cy = __shfl_sync(0xffffffffu, s.cy, src);
+          b.za = __shfl_sync(0xffffffffu, s.za, src); b.dzb = __shfl_sync(0xffffffffu, s.dzb, src);
+          b.dzc = __shfl_sync(0xffffffffu, s.dzc, src);
+          b.px0 = __shfl_sync(0xffffffffu, s.px0, src); b.px1 = __shfl_sync(0xffffffffu, s.px1, src);
+          b.py0 = __shfl_sync(0xffffffffu, s.py0, src); b.py1 = __shfl_sync(0xffffffffu, s.py1, src);
+          b.bias = __shfl_sync(0xffffffffu, s.bias, src);
+          const uint32_t bdata = __shfl_sync(0xffffffffu, data, src);
+          const int lx = lane & 7, ly = lane >> 3;
+          for (int ty = b.py0; ty <= b.py1; ty += 4)
+            for (int tx = b.px0; tx <= b.px1; tx += 8) {
+              const int px = tx + lx, py = ty + ly;
+              if (px <= b.px1 && py <= b.py1) raster_pixel(b, px, py, bdata, p.visbuf, p.width);
+            }
+        }
+      }
+      __syncwarp(); // clip_s / scr_s reuse
     }
-    __syncwarp(); // clip_s / scr_s reuse
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);

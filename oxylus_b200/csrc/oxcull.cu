@@ -99,6 +99,7 @@ struct OxcContext {
   InstGeom* d_geom = nullptr;
   uint32_t* d_counts = nullptr;
   uint32_t* d_block_sums = nullptr;
+  float* d_lod_aabb = nullptr; // [mesh_cap][OXC_MESH_MAX_LODS][6]
   // frame buffers
   OxcMeshletInstance* d_meshlet_instances = nullptr;
   uint32_t* d_visible = nullptr;
@@ -162,7 +163,7 @@ int refresh_inst_cache(OxcContext* c, const OxcCullCamera* cam, cudaStream_t s) 
   if (!c->cache_valid) return fail(OXC_E_STATE, "oxc_cull_meshes must run before the meshlet/triangle passes");
   MeshesParams p{};
   p.meshes = c->d_meshes; p.mesh_instances = c->d_mesh_instances; p.transforms = c->d_transforms;
-  p.inst = c->d_inst; p.geom = c->d_geom; p.counts = c->d_counts; p.block_sums = c->d_block_sums;
+  p.inst = c->d_inst; p.geom = c->d_geom; p.counts = c->d_counts; p.block_sums = c->d_block_sums; p.lod_aabb = c->d_lod_aabb;
   shard_range(c, c->cached_cam.mesh_instance_count, &p.first, &p.count);
   p.flags = 0; p.select = 0; p.cam = *cam;
   if (p.count) {
@@ -275,7 +276,7 @@ void oxc_destroy(OxcContext* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   cudaFree(c->d_meshes); cudaFree(c->d_mesh_instances); cudaFree(c->d_transforms); cudaFree(c->d_blob);
-  cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
+  cudaFree(c->d_lod_aabb); cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
   cudaFree(c->d_meshlet_instances); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
   cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_hiz);
@@ -294,6 +295,8 @@ int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
   if (sc->mesh_count > c->mesh_cap) {
     CK(cudaFree(c->d_meshes)); c->d_meshes = nullptr;
     CK(cudaMalloc(&c->d_meshes, (size_t)sc->mesh_count * sizeof(OxcMesh)));
+    CK(cudaFree(c->d_lod_aabb)); c->d_lod_aabb = nullptr;
+    CK(cudaMalloc(&c->d_lod_aabb, (size_t)sc->mesh_count * OXC_MESH_MAX_LODS * 6 * sizeof(float)));
     c->mesh_cap = sc->mesh_count;
   }
   if (sc->transform_count > c->transform_cap) {
@@ -313,6 +316,11 @@ int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
   // upload_gltf_mesh (AssetManager_GLTF.cpp:778-800): blob offsets -> device addresses
   k_rebase_meshes<<<(sc->mesh_count + 127) / 128, 128, 0, s>>>(c->d_meshes, sc->mesh_count, reinterpret_cast<uint64_t>(c->d_blob));
   LAUNCHED();
+  {
+    const uint32_t warps = sc->mesh_count * OXC_MESH_MAX_LODS;
+    k_lod_union_aabb<<<(warps * 32 + 255) / 256, 256, 0, s>>>(c->d_meshes, sc->mesh_count, c->d_lod_aabb);
+    LAUNCHED();
+  }
   c->mesh_count = sc->mesh_count; c->mesh_instance_count = sc->mesh_instance_count; c->transform_count = sc->transform_count;
   c->scene_set = true;
   c->cache_valid = false;
@@ -361,7 +369,7 @@ int oxc_cull_meshes(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, voi
   CK(cudaSetDevice(c->device));
   MeshesParams p{};
   p.meshes = c->d_meshes; p.mesh_instances = c->d_mesh_instances; p.transforms = c->d_transforms;
-  p.inst = c->d_inst; p.geom = c->d_geom; p.counts = c->d_counts; p.block_sums = c->d_block_sums;
+  p.inst = c->d_inst; p.geom = c->d_geom; p.counts = c->d_counts; p.block_sums = c->d_block_sums; p.lod_aabb = c->d_lod_aabb;
   shard_range(c, cam->mesh_instance_count, &p.first, &p.count);
   p.flags = flags; p.select = 1; p.cam = *cam;
   const uint32_t n_blocks = (p.count + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS;

@@ -281,7 +281,9 @@ def test_dequantize_half_all_inputs(capi, orc):
     hw = ctx.download(b, np.float32, 65536)
     want = np.array([orc.dequantize_half(h) for h in range(65536)], dtype=np.float32)
     nan = np.isnan(want)
-    np.testing.assert_array_equal(canon.view(np.uint32), want.view(np.uint32))
+    # (signalling-NaN payloads are quietened when the oracle's float crosses ctypes: compare NaN-ness there)
+    np.testing.assert_array_equal(canon[~nan].view(np.uint32), want[~nan].view(np.uint32))
+    assert np.all(np.isnan(canon[nan]))
     np.testing.assert_array_equal(hw[~nan].view(np.uint32), want[~nan].view(np.uint32))
     assert np.all(np.isnan(hw[nan]))
     ctx.free(a)
