@@ -29,6 +29,7 @@ struct TriParams {
   unsigned long long* visbuf;
   uint32_t width, height;
   unsigned long long* tri_counter;
+  uint32_t* work_counter;    // zeroed before every raster launch
 };
 
 struct MeshletWork {
@@ -231,6 +232,7 @@ OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* v
   }
 }
 
+constexpr int RASTER_BATCH = 8;       // meshlets per work grab
 constexpr int RASTER_BIG_PIXELS = 32; // bbox area above which the whole warp rasterises the triangle together
 
 // Header of one surviving meshlet, fetched by ONE lane (32 headers in flight per warp): the 4-level pointer
@@ -285,9 +287,14 @@ __global__ void __launch_bounds__(TRI_THREADS, 3) k_raster_visbuffer(const __gri
   float4* clip_s = clip_all[warp];
   ScreenVert* scr_s = scr_all[warp];
   uint32_t kept = 0;
-  // a warp owns batches of 32 consecutive survivors
-  for (uint32_t g0 = (blockIdx.x * TRI_WARPS + warp) * 32u; g0 < count; g0 += gridDim.x * TRI_WARPS * 32u) {
-    const uint32_t nb = min(32u, count - g0);
+  // warps pull batches of RASTER_BATCH consecutive survivors from a global work counter (dynamic balance);
+  // lanes 0..RASTER_BATCH-1 each chase one meshlet header, so RASTER_BATCH pointer chases are in flight together
+  for (;;) {
+    uint32_t g0 = 0;
+    if (lane == 0) g0 = atomicAdd(p.work_counter, (uint32_t)RASTER_BATCH);
+    g0 = __shfl_sync(0xffffffffu, g0, 0);
+    if (g0 >= count) break;
+    const uint32_t nb = min((uint32_t)RASTER_BATCH, count - g0);
     MeshletHeader mine;
     mine.gid = 0; mine.inst = 0; mine.vertex_offset = 0; mine.vertex_count = 0; mine.tri_offset = 0; mine.tri_count = 0;
     mine.micro = nullptr; mine.vidx = nullptr; mine.pos = nullptr;

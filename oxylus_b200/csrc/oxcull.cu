@@ -111,6 +111,7 @@ struct OxcContext {
   OxcDrawIndexedIndirectCommand* d_draw_cmd = nullptr;
   uint32_t* d_reordered = nullptr;
   unsigned long long* d_tri_counter = nullptr;
+  uint32_t* d_raster_work = nullptr;
   // hiz
   float* d_hiz = nullptr;
   HizDesc hiz{};
@@ -222,6 +223,7 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   TRY(dalloc(&c->d_cull_triangles_cmd, 1));
   TRY(dalloc(&c->d_draw_cmd, 1));
   TRY(dalloc(&c->d_tri_counter, 1));
+  TRY(dalloc(&c->d_raster_work, 1));
   if (info->alloc_reordered_indices) TRY(dalloc(&c->d_reordered, (size_t)N * OXC_MESHLET_MAX_PRIMITIVES * 3));
   if (info->max_views > 1) {
     TRY(dalloc(&c->d_view_planes, (size_t)I * info->max_views));
@@ -279,7 +281,7 @@ void oxc_destroy(OxcContext* c) {
   cudaFree(c->d_lod_aabb); cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
   cudaFree(c->d_meshlet_instances); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
-  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_hiz);
+  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_hiz);
   cudaFree(c->d_view_planes); cudaFree(c->d_views); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts);
   delete c;
 }
@@ -517,6 +519,8 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
   int rc = tri_common(c, cam, flags, s, &p);
   if (rc != OXC_OK) return rc;
   p.visbuf = reinterpret_cast<unsigned long long*>(vis); p.width = w; p.height = h;
+  p.work_counter = c->d_raster_work;
+  CK(cudaMemsetAsync(c->d_raster_work, 0, 4, s));
   uint32_t tiles = (c->info.max_meshlet_instances + TRI_WARPS - 1) / TRI_WARPS;
   uint32_t grid = (uint32_t)(c->sm_count * (c->occ_raster > 0 ? c->occ_raster : 1));
   if (grid > tiles) grid = tiles;
