@@ -161,6 +161,7 @@ struct TriSetup {
   float za, dzb, dzc;           // depth at a, per-triangle gradients w.r.t. the edge functions of b and c
   int px0, px1, py0, py1;
   int bias;                     // bit0..2: edge biases (1 = -1)
+  bool narrow;                  // all edge functions fit 32 bits (extent < 2^14 sub-pixels)
 };
 
 OXC_DI long long orient2d(int ax, int ay, int bx, int by, int cx, int cy) {
@@ -171,19 +172,24 @@ OXC_DI int edge_bias_bit(int ax, int ay, int bx, int by) {
   return ((dy > 0) || (dy == 0 && dx < 0)) ? 0 : 1;
 }
 
-// steps 2-4 of the raster spec; false = nothing to draw
+// steps 2-4 of the raster spec; false = nothing to draw.  Rejections commute, so the cheapest go first:
+// the bounding box (most sub-pixel triangles cover no sample centre) before the signed area.
 OXC_DI bool tri_setup(const ScreenVert v0, const ScreenVert v1, const ScreenVert v2, uint32_t W, uint32_t H, TriSetup& s) {
   if (v0.fx == INT_MIN || v1.fx == INT_MIN || v2.fx == INT_MIN) return false;
-  const long long area2 = orient2d(v0.fx, v0.fy, v1.fx, v1.fy, v2.fx, v2.fy);
-  if (area2 >= 0) return false;
-  s.ax = v0.fx; s.ay = v0.fy; s.bx = v2.fx; s.by = v2.fy; s.cx = v1.fx; s.cy = v1.fy;
-  const int minx = min(s.ax, min(s.bx, s.cx)), maxx = max(s.ax, max(s.bx, s.cx));
-  const int miny = min(s.ay, min(s.by, s.cy)), maxy = max(s.ay, max(s.by, s.cy));
+  const int minx = min(v0.fx, min(v1.fx, v2.fx)), maxx = max(v0.fx, max(v1.fx, v2.fx));
+  const int miny = min(v0.fy, min(v1.fy, v2.fy)), maxy = max(v0.fy, max(v1.fy, v2.fy));
   s.px0 = max(0, (minx - 128 + 255) >> 8);
   s.px1 = min((int)W - 1, (maxx - 128) >> 8);
   s.py0 = max(0, (miny - 128 + 255) >> 8);
   s.py1 = min((int)H - 1, (maxy - 128) >> 8);
   if (s.px1 < s.px0 || s.py1 < s.py0) return false; // covers no sample centre (== small-primitive cull)
+  // extent < 2^14 sub-pixels per axis: every edge-function value inside the bbox fits 32 bits
+  s.narrow = (maxx - minx) < 16384 && (maxy - miny) < 16384;
+  long long area2;
+  if (s.narrow) area2 = (long long)((v1.fx - v0.fx) * (v2.fy - v0.fy) - (v1.fy - v0.fy) * (v2.fx - v0.fx));
+  else area2 = orient2d(v0.fx, v0.fy, v1.fx, v1.fy, v2.fx, v2.fy);
+  if (area2 >= 0) return false;
+  s.ax = v0.fx; s.ay = v0.fy; s.bx = v2.fx; s.by = v2.fy; s.cx = v1.fx; s.cy = v1.fy;
   const float fa_ = (float)(-area2);
   s.za = v0.z;
   s.dzb = fd(fs(v2.z, v0.z), fa_);
@@ -212,9 +218,38 @@ OXC_DI void raster_pixel(const TriSetup& s, int px, int py, uint32_t data, unsig
               orient2d(s.ax, s.ay, s.bx, s.by, sx, sy), px, py, data, vis, W);
 }
 
-// one lane walks the (small) bounding box with incrementally stepped edge functions (64-bit adds only)
+OXC_DI int orient2d_32(int ax, int ay, int bx, int by, int cx, int cy) { return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax); }
+
+OXC_DI void shade_pixel_32(const TriSetup& s, int e0, int e1, int e2, int px, int py, uint32_t data, unsigned long long* vis,
+                           uint32_t W) {
+  if ((e0 - (s.bias & 1)) < 0 || (e1 - ((s.bias >> 1) & 1)) < 0 || (e2 - ((s.bias >> 2) & 1)) < 0) return;
+  const float zz = fa(fa(s.za, fm((float)e1, s.dzb)), fm((float)e2, s.dzc)); // (float)int32 == (float)int64 of the same value
+  if (!(zz >= 0.0f && zz <= 1.0f)) return;
+  uint32_t zb = __float_as_uint(zz);
+  zb = zb == 0x80000000u ? 0u : zb;
+  const unsigned long long v = ((unsigned long long)zb << 32) | data;
+  unsigned long long* ptr = vis + (size_t)py * W + px;
+  if (v > *ptr) atomicMax(ptr, v);
+}
+
+// one lane walks the (small) bounding box with incrementally stepped edge functions (adds only)
 OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* vis, uint32_t W) {
   const int sx0 = s.px0 * 256 + 128, sy0 = s.py0 * 256 + 128;
+  if (s.narrow) {
+    int r0 = orient2d_32(s.bx, s.by, s.cx, s.cy, sx0, sy0), r1 = orient2d_32(s.cx, s.cy, s.ax, s.ay, sx0, sy0),
+        r2 = orient2d_32(s.ax, s.ay, s.bx, s.by, sx0, sy0);
+    const int dx0 = -(s.cy - s.by) * 256, dy0 = (s.cx - s.bx) * 256, dx1 = -(s.ay - s.cy) * 256, dy1 = (s.ax - s.cx) * 256,
+              dx2 = -(s.by - s.ay) * 256, dy2 = (s.bx - s.ax) * 256;
+    for (int py = s.py0; py <= s.py1; py++) {
+      int e0 = r0, e1 = r1, e2 = r2;
+      for (int px = s.px0; px <= s.px1; px++) {
+        shade_pixel_32(s, e0, e1, e2, px, py, data, vis, W);
+        e0 += dx0; e1 += dx1; e2 += dx2;
+      }
+      r0 += dy0; r1 += dy1; r2 += dy2;
+    }
+    return;
+  }
   long long r0 = orient2d(s.bx, s.by, s.cx, s.cy, sx0, sy0);
   long long r1 = orient2d(s.cx, s.cy, s.ax, s.ay, sx0, sy0);
   long long r2 = orient2d(s.ax, s.ay, s.bx, s.by, sx0, sy0);
