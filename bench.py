@@ -207,7 +207,7 @@ def main():
     w, h = scene.width, scene.height
 
     # multi-GPU exchange state
-    hooks = {}
+    hooks, gathered = {}, {}
     if multi:
         lod0 = oxdist.lod0_counts_of(scene)
         cap = max(int(lod0[f:f + c].sum()) for f, c in parts)
@@ -230,7 +230,7 @@ def main():
             pipe.ctx.lib.oxc_copy(pipe.ctx.h, vis_t.data_ptr(), out.visibility, 12, 2, pipe.ctx.stream)
             count_t.copy_(vis_t[1:2] + vis_t[2:3])
             pipe.ctx.lib.oxc_copy(pipe.ctx.h, ids_t.data_ptr(), out.visible_meshlet_instances_indices, cap * 4, 2, pipe.ctx.stream)
-            hooks["gathered"] = oxdist.gather_survivors(ids_t, count_t)
+            gathered["last"] = oxdist.gather_survivors(ids_t, count_t)
 
         hooks = dict(after_cull_meshes=after_cull_meshes, between_passes=between_passes, after_frame=after_frame)
 
