@@ -161,7 +161,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "triangles_per_s": (last["triangles"] / sec) if last else None,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def workload_config(args, scene):
@@ -408,7 +408,7 @@ def main():
             "gpu_launches": int(launches_per_frame * K), "gpu_launches_per_step": int(launches_per_frame),
             "cuda_graph": graphs is not None, "wall_s_timed_region": t_wall,
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     pipe.close()
     if multi:
         dist.destroy_process_group()
