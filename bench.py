@@ -190,6 +190,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if multi:
+        os.environ["NCCL_DEBUG"] = os.environ.get("OXC_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
     capi.load(build_if_missing=False)
@@ -250,23 +251,29 @@ def main():
 
     # ---------------- CUDA graphs of one frame per camera ----------------
     graphs = None
-    if not args.no_graph and not multi:
-        graphs = []
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
+    if not args.no_graph:
+        try:
+            graphs = []
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                pipe.use_torch_stream()
+                for cam in cams:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=side):
+                        pipe.use_torch_stream()
+                        pipe.frame(cam, **hooks)  # N > 1: the NCCL exchange steps are captured with the kernels
+                    graphs.append(g)
+            torch.cuda.current_stream().wait_stream(side)
             pipe.use_torch_stream()
-            for cam in cams:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g, stream=side):
-                    pipe.use_torch_stream()
-                    pipe.frame(cam)
-                graphs.append(g)
-        torch.cuda.current_stream().wait_stream(side)
-        pipe.use_torch_stream()
-        for i in range(2):
-            graphs[i % 2].replay()
-        torch.cuda.synchronize()
+            for i in range(2):
+                graphs[i % 2].replay()
+            torch.cuda.synchronize()
+        except Exception as e:  # capture of the collectives unsupported: launch eagerly (still correct, more launch gaps)
+            sys.stderr.write(f"[bench] CUDA graph capture failed ({e!r}); timing eager launches\n")
+            graphs = None
+            pipe.use_torch_stream()
+            torch.cuda.synchronize()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
