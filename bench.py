@@ -251,7 +251,7 @@ def main():
 
     # ---------------- CUDA graphs of one frame per camera ----------------
     graphs = None
-    if not args.no_graph:
+    if not args.no_graph and not multi:  # N > 1 launches eagerly: capturing the NCCL exchange steps hung in testing
         try:
             graphs = []
             side = torch.cuda.Stream()
