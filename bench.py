@@ -212,26 +212,26 @@ def main():
     if multi:
         lod0 = oxdist.lod0_counts_of(scene)
         cap = max(int(lod0[f:f + c].sum()) for f, c in parts)
-        total_t = torch.zeros(1, dtype=torch.int32, device=dev)
-        count_t = torch.zeros(1, dtype=torch.int32, device=dev)
-        ids_t = torch.zeros(cap, dtype=torch.int32, device=dev)
         out = pipe.ctx.out
+        # zero-copy torch views of the context's device buffers (no staging copies in the exchange)
+        vis_view = pipeline.wrap_device(out.visibility, 3, torch.int32, dev)            # total / early / late
+        ids_view = pipeline.wrap_device(out.visible_meshlet_instances_indices, cap, torch.int32, dev)
+        vis_all = torch.zeros(world * 3, dtype=torch.int32, device=dev)
+        ids_all = torch.zeros(world * cap, dtype=torch.int32, device=dev)
 
         def after_cull_meshes():
-            pipe.ctx.lib.oxc_copy(pipe.ctx.h, total_t.data_ptr(), out.visibility, 4, 2, pipe.ctx.stream)
-            oxdist.exchange_id_base(total_t, pipe.id_base)
+            # emitted counts of every rank -> exclusive prefix = this rank's global meshlet-instance id base
+            dist.all_gather_into_tensor(vis_all, vis_view)
+            pipe.id_base.copy_(vis_all.view(world, 3)[:rank, 0].sum())
 
         def between_passes():
             oxdist.reduce_visbuffer(pipe.vis64)
 
         def after_frame():
             oxdist.reduce_visbuffer(pipe.vis64)
-            # survivors: early + late counts -> one count, ids from the context buffer
-            vis_t = torch.empty(3, dtype=torch.int32, device=dev)
-            pipe.ctx.lib.oxc_copy(pipe.ctx.h, vis_t.data_ptr(), out.visibility, 12, 2, pipe.ctx.stream)
-            count_t.copy_(vis_t[1:2] + vis_t[2:3])
-            pipe.ctx.lib.oxc_copy(pipe.ctx.h, ids_t.data_ptr(), out.visible_meshlet_instances_indices, cap * 4, 2, pipe.ctx.stream)
-            gathered["last"] = oxdist.gather_survivors(ids_t, count_t)
+            dist.all_gather_into_tensor(vis_all, vis_view)   # early / late counts of every rank
+            dist.all_gather_into_tensor(ids_all, ids_view)   # survivor ids (global), fixed-capacity segments
+            gathered["last"] = (ids_all, vis_all)
 
         hooks = dict(after_cull_meshes=after_cull_meshes, between_passes=between_passes, after_frame=after_frame)
 

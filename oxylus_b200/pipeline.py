@@ -13,6 +13,18 @@ from . import abi, capi
 STAGES = ["cull_meshes", "cull_early", "raster_early", "hiz", "cull_late", "raster_late"]
 
 
+class _DevView:
+    """Zero-copy torch view of a raw device pointer owned by the C-ABI context (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, n, typestr):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def wrap_device(ptr, n, dtype, device):
+    typestr = {torch.int32: "<i4", torch.float32: "<f4", torch.int64: "<i8"}[dtype]
+    return torch.as_tensor(_DevView(ptr, n, typestr), device=device)
+
+
 class VisibilityPipeline:
     def __init__(self, scene, device=0, shard=None, alloc_reordered_indices=False):
         self.scene = scene
