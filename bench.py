@@ -190,7 +190,10 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if multi:
-        os.environ["NCCL_DEBUG"] = os.environ.get("OXC_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        if "OXC_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["OXC_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)  # the version banner goes to stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
     capi.load(build_if_missing=False)
@@ -224,8 +227,11 @@ def main():
             dist.all_gather_into_tensor(vis_all, vis_view)
             pipe.id_base.copy_(vis_all.view(world, 3)[:rank, 0].sum())
 
+        hw_, hh_ = scene.hiz_extent()
+        mip0_view = pipeline.wrap_device(out.hiz, hw_ * hh_, torch.int32, dev)  # level 0 starts at offset 0
+
         def between_passes():
-            oxdist.reduce_visbuffer(pipe.vis64)
+            dist.all_reduce(mip0_view, op=dist.ReduceOp.MAX)  # depths are >= +0: int32 order == float order
 
         def after_frame():
             oxdist.reduce_visbuffer(pipe.vis64)

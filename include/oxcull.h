@@ -274,6 +274,13 @@ int oxc_build_hiz(OxcContext* ctx, const float* depth_dev, uint32_t width, uint3
  * resolve pass between the early raster and generate_hiz.  No reference equivalent (it has a D32F image). */
 int oxc_build_hiz_packed(OxcContext* ctx, const uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream);
 
+/* Multi-GPU split of generate_hiz (no reference equivalent): mip 0 is a point sample and max-over-ranks
+ * commutes with sampling, so ranks exchange mip 0 only.  oxc_build_hiz_mip0_packed writes just mip 0 (texels
+ * at OxcOutputs::hiz + hiz_level_offset[0]); after an all_reduce(MAX) on those texels (non-negative floats
+ * order like their int32 bits) oxc_build_hiz_from_mip0 builds mips 1.. . */
+int oxc_build_hiz_mip0_packed(OxcContext* ctx, const uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream);
+int oxc_build_hiz_from_mip0(OxcContext* ctx, void* stream);
+
 /* cull_triangles.slang:27-90 via CullGeometry.cpp:337-403: resets draw_cmd{0,1,0,0,0}, then one
  * block per surviving meshlet of this pass (early: [0,E); late: [E,E+L)).  Requires
  * alloc_reordered_indices. */

@@ -17,7 +17,7 @@ E_NO_DEVICE = -3
 SYMBOLS = [
     "oxc_last_error", "oxc_kernel_launch_count", "oxc_version", "oxc_create", "oxc_destroy", "oxc_set_scene",
     "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_cull_meshes",
-    "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_cull_triangles", "oxc_clear_visbuffer",
+    "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview",
     "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_render",
@@ -59,6 +59,8 @@ def load(build_if_missing=True):
     lib.oxc_cull_meshlets.argtypes = [vp, vp, u32, i32, vp]
     lib.oxc_build_hiz.argtypes = [vp, vp, u32, u32, vp]
     lib.oxc_build_hiz_packed.argtypes = [vp, vp, u32, u32, vp]
+    lib.oxc_build_hiz_mip0_packed.argtypes = [vp, vp, u32, u32, vp]
+    lib.oxc_build_hiz_from_mip0.argtypes = [vp, vp]
     lib.oxc_cull_triangles.argtypes = [vp, vp, u32, vp]
     lib.oxc_clear_visbuffer.argtypes = [vp, vp, u32, u32, vp]
     lib.oxc_raster_visbuffer.argtypes = [vp, vp, u32, u32, u32, vp, i32, vp]
@@ -174,6 +176,12 @@ class Context:
 
     def build_hiz_packed(self, vis_dev, w, h):
         _check(self.lib.oxc_build_hiz_packed(self.h, _ptr(vis_dev), w, h, self.stream), "oxc_build_hiz_packed")
+
+    def build_hiz_mip0_packed(self, vis_dev, w, h):
+        _check(self.lib.oxc_build_hiz_mip0_packed(self.h, _ptr(vis_dev), w, h, self.stream), "oxc_build_hiz_mip0_packed")
+
+    def build_hiz_from_mip0(self):
+        _check(self.lib.oxc_build_hiz_from_mip0(self.h, self.stream), "oxc_build_hiz_from_mip0")
 
     def cull_triangles(self, cam, flags):
         _check(self.lib.oxc_cull_triangles(self.h, _ptr(cam), flags, self.stream), "oxc_cull_triangles")

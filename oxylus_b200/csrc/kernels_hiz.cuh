@@ -18,6 +18,7 @@ struct HizBuildParams {
   float* hiz;
   uint32_t hw, hh, levels;  // pyramid
   uint32_t hw_shift, hh_shift;
+  uint32_t mode;            // 0: sample depth -> all mips; 1: sample depth -> mip 0 only; 2: mips 1.. from the mip 0 already in the pyramid
   uint32_t level_offset[OXC_HIZ_MAX_LEVELS];
 };
 
@@ -43,11 +44,20 @@ __global__ void __launch_bounds__(256) k_hiz_tiles(const __grid_constant__ HizBu
 #pragma unroll
   for (int j = 0; j < 4; j++)
 #pragma unroll
-    for (int i = 0; i < 4; i++) v[j][i] = hiz_sample(p, x0 + i, y0 + j);
+    for (int i = 0; i < 4; i++) v[j][i] = p.mode == 2 ? 0.0f : hiz_sample(p, x0 + i, y0 + j);
   float* m0 = p.hiz + p.level_offset[0];
+  if (p.mode == 2) { // mip 0 was produced earlier (and max-reduced across GPUs): read it back instead of sampling
 #pragma unroll
-  for (int j = 0; j < 4; j++)
-    *reinterpret_cast<float4*>(m0 + (size_t)(y0 + j) * p.hw + x0) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+    for (int j = 0; j < 4; j++) {
+      const float4 r = *reinterpret_cast<const float4*>(m0 + (size_t)(y0 + j) * p.hw + x0);
+      v[j][0] = r.x; v[j][1] = r.y; v[j][2] = r.z; v[j][3] = r.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      *reinterpret_cast<float4*>(m0 + (size_t)(y0 + j) * p.hw + x0) = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+    if (p.mode == 1) return;
+  }
   // mip 1
   float q[2][2];
 #pragma unroll

@@ -434,24 +434,24 @@ int oxc_cull_meshlets(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, i
 }
 
 static int build_hiz_impl(OxcContext* c, const float* depth_dev, uint32_t stride, uint32_t offset, uint32_t width,
-                          uint32_t height, void* stream) {
-  if (!c || !depth_dev || !width || !height) return fail(OXC_E_INVALID, "bad argument");
+                          uint32_t height, void* stream, uint32_t mode = 0) {
+  if (!c || (!depth_dev && mode != 2) || ((!width || !height) && mode != 2)) return fail(OXC_E_INVALID, "bad argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(c->device));
   HizBuildParams p{};
   p.depth = depth_dev; p.elem_stride = stride; p.elem_offset = offset; p.width = width; p.height = height; p.hiz = c->d_hiz;
   p.hw = c->hiz.width; p.hh = c->hiz.height; p.levels = c->hiz.levels;
   p.hw_shift = ilog2(p.hw); p.hh_shift = ilog2(p.hh);
+  p.mode = mode;
   memcpy(p.level_offset, c->hiz.level_offset, sizeof p.level_offset);
   if (p.hw % 64 == 0 && p.hh % 64 == 0) {
     k_hiz_tiles<<<dim3(p.hw / 64, p.hh / 64), 256, 0, s>>>(p);
     LAUNCHED();
-    if (p.levels > 7) { k_hiz_tail<<<1, 1024, 0, s>>>(p, 7); LAUNCHED(); }
+    if (p.levels > 7 && mode != 1) { k_hiz_tail<<<1, 1024, 0, s>>>(p, 7); LAUNCHED(); }
   } else {
     const uint32_t n = p.hw * p.hh;
-    k_hiz_mip0_generic<<<(n + 255) / 256, 256, 0, s>>>(p);
-    LAUNCHED();
-    if (p.levels > 1) { k_hiz_tail<<<1, 1024, 0, s>>>(p, 1); LAUNCHED(); }
+    if (mode != 2) { k_hiz_mip0_generic<<<(n + 255) / 256, 256, 0, s>>>(p); LAUNCHED(); }
+    if (p.levels > 1 && mode != 1) { k_hiz_tail<<<1, 1024, 0, s>>>(p, 1); LAUNCHED(); }
   }
   c->hiz_zero = false;
   return OXC_OK;
@@ -466,6 +466,14 @@ int oxc_build_hiz(OxcContext* c, const float* depth_dev, uint32_t width, uint32_
 int oxc_build_hiz_packed(OxcContext* c, const uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream) {
   return build_hiz_impl(c, reinterpret_cast<const float*>(vis_dev), 2, 1, width, height, stream);
 }
+
+// Multi-GPU split of generate_hiz: mip 0 is a point sample, and max over ranks commutes with sampling, so ranks
+// exchange only mip 0 (hw*hh floats, e.g. 4 MB at 1080p instead of the 16.6 MB packed image):
+//   oxc_build_hiz_mip0_packed -> all_reduce(MAX) on the mip-0 texels -> oxc_build_hiz_from_mip0
+int oxc_build_hiz_mip0_packed(OxcContext* c, const uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream) {
+  return build_hiz_impl(c, reinterpret_cast<const float*>(vis_dev), 2, 1, width, height, stream, 1);
+}
+int oxc_build_hiz_from_mip0(OxcContext* c, void* stream) { return build_hiz_impl(c, nullptr, 1, 0, 0, 0, stream, 2); }
 
 static int tri_common(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, cudaStream_t s, TriParams* p) {
   if (!c->scene_set) return fail(OXC_E_STATE, "oxc_set_scene first");

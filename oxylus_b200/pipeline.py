@@ -72,8 +72,12 @@ class VisibilityPipeline:
         if mark:
             mark("raster_early")
         if between_passes:
-            between_passes()  # multi-GPU: vis-buffer max-reduce so every rank builds the same Hi-Z
-        c.build_hiz_packed(v, w, h)
+            # multi-GPU: only the point-sampled mip 0 is exchanged (max over ranks commutes with sampling)
+            c.build_hiz_mip0_packed(v, w, h)
+            between_passes()
+            c.build_hiz_from_mip0()
+        else:
+            c.build_hiz_packed(v, w, h)
         if mark:
             mark("hiz")
         c.cull_meshlets(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, True)

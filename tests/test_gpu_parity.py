@@ -289,3 +289,23 @@ def test_dequantize_half_all_inputs(capi, orc):
     ctx.free(a)
     ctx.free(b)
     ctx.close()
+
+
+def test_hiz_split_build_equals_single_pass(capi, orc):
+    """multi-GPU split (mip 0 only -> [all_reduce] -> mips 1..) == the one-shot pyramid, packed source."""
+    rng = np.random.default_rng(11)
+    for (w, h) in [(1920, 1080), (100, 60)]:
+        hw, hh = abi.hiz_extent(w, h)
+        depth = rng.random((h, w), dtype=np.float32)
+        packed = (depth.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.uint64(0xFFFFFFFF)
+        ref = orc.build_hiz(depth, orc.Hiz(hw, hh))
+        ctx = capi.Context(0, 1, 1, hw, hh)
+        v_dev = ctx.alloc(w * h * 8)
+        ctx.upload(v_dev, packed)
+        ctx.build_hiz_mip0_packed(v_dev, w, h)
+        ctx.build_hiz_from_mip0()
+        got = ctx.hiz_levels()
+        for lvl in range(ref.levels):
+            np.testing.assert_array_equal(got[lvl].view(np.uint32), ref.level(lvl).view(np.uint32), err_msg=f"{w}x{h} mip {lvl}")
+        ctx.free(v_dev)
+        ctx.close()
