@@ -307,6 +307,36 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_expand_meshlet_instance
 // Outputs are bit-identical to the canonical path for every input (oxc_filtered.cuh).
 // ------------------------------------------------------------------------------------------------
 constexpr int CULL_WARP_ITEMS = 32 * CULL_ITEMS; // items owned by one warp per tile
+constexpr uint32_t CULL_TILE_BYTES = CULL_TILE * sizeof(OxcMeshletInstance);
+
+// ---- TMA (bulk async copy engine) staging of the meshlet-instance stream: 1-D cp.async.bulk global -> shared,
+//      completion on an mbarrier; the next tile's 4 KB are in flight while the current tile is culled ----
+OXC_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+OXC_DI void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+OXC_DI void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+OXC_DI void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+OXC_DI void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+OXC_DI void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
 
 // one queued Hi-Z test: decoded bounds + instance + the owner's slot (item k of lane l: k*32 + l)
 struct __align__(16) OccEntry {
@@ -321,12 +351,15 @@ __global__ void __launch_bounds__(CULL_THREADS, 4) k_cull_meshlets(const __grid_
   __shared__ uint32_t warp_cnt[CULL_THREADS / 32];
   __shared__ uint32_t tile_base_s;
   __shared__ float s8_lut[256]; // scene.slang:408-418: i8 / 127.0 for every i8 (IEEE divide, once per CTA)
+  __shared__ __align__(128) uint2 mi_s[2][CULL_TILE]; // double-buffered tiles of the instance stream (TMA destination)
+  __shared__ __align__(8) uint64_t mi_bar[2];
   // warp-private queues: no CTA barrier between the phases
   __shared__ OccEntry q_ent[HIZ ? CULL_THREADS / 32 : 1][HIZ ? CULL_WARP_ITEMS : 1];
   __shared__ uint8_t q_amb[HIZ ? CULL_THREADS / 32 : 1][HIZ ? CULL_WARP_ITEMS : 1]; // entry indices needing the canonical path
   __shared__ uint8_t q_res[HIZ ? CULL_THREADS / 32 : 1][HIZ ? CULL_WARP_ITEMS : 1]; // verdict per owner slot
   if (threadIdx.x < OXC_HIZ_MAX_LEVELS) hiz_off[threadIdx.x] = p.hiz.level_offset[threadIdx.x];
   s8_lut[threadIdx.x] = s8_over_127((int)threadIdx.x - 128);
+  if (threadIdx.x == 0) { mbar_init(&mi_bar[0], 1); mbar_init(&mi_bar[1], 1); mbar_fence_init(); }
   __syncthreads();
   const uint32_t total = p.vis->total_visible_meshlet_instances; // :26
   const uint32_t early_count = LATE ? p.vis->early_visible_meshlet_instances : 0u; // :73 (final: early kernel completed)
@@ -336,14 +369,27 @@ __global__ void __launch_bounds__(CULL_THREADS, 4) k_cull_meshlets(const __grid_
   const uint32_t n_tiles = (total + CULL_TILE - 1) / CULL_TILE;
   const uint2* mi2 = reinterpret_cast<const uint2*>(p.meshlet_instances);
 
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  // prologue: this CTA's first tile (the buffer is padded by one tile, so a full-size copy never leaves the allocation)
+  if (threadIdx.x == 0 && blockIdx.x < n_tiles) {
+    mbar_expect_tx(&mi_bar[0], CULL_TILE_BYTES);
+    tma_load_1d(mi_s[0], mi2 + (size_t)blockIdx.x * CULL_TILE, CULL_TILE_BYTES, &mi_bar[0]);
+  }
+  uint32_t it = 0;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
     const uint32_t tile_first = tile * CULL_TILE;
+    const uint32_t buf = it & 1u;
+    // next tile -> other buffer (its previous readers finished before the trailing barrier of the last iteration)
+    if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) {
+      mbar_expect_tx(&mi_bar[buf ^ 1u], CULL_TILE_BYTES);
+      tma_load_1d(mi_s[buf ^ 1u], mi2 + (size_t)(tile + gridDim.x) * CULL_TILE, CULL_TILE_BYTES, &mi_bar[buf ^ 1u]);
+    }
+    mbar_wait(&mi_bar[buf], (it >> 1) & 1u);
     // ---- phase A: staged loads ----
     uint2 mi[CULL_ITEMS];
 #pragma unroll
     for (int k = 0; k < CULL_ITEMS; k++) {
       const uint32_t i = tile_first + k * CULL_THREADS + threadIdx.x;
-      mi[k] = i < total ? __ldg(&mi2[i]) : make_uint2(0xFFFFFFFFu, 0u);
+      mi[k] = i < total ? mi_s[buf][k * CULL_THREADS + threadIdx.x] : make_uint2(0xFFFFFFFFu, 0u);
     }
     const uint4* bptr[CULL_ITEMS];
     uint32_t word[CULL_ITEMS], bit[CULL_ITEMS];

@@ -214,7 +214,7 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   TRY(dalloc(&c->d_geom, (size_t)I));
   TRY(dalloc(&c->d_counts, (size_t)I));
   TRY(dalloc(&c->d_block_sums, (size_t)(I + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS + 1));
-  TRY(dalloc(&c->d_meshlet_instances, (size_t)N));
+  TRY(dalloc(&c->d_meshlet_instances, (size_t)N + CULL_TILE)); // + one tile: full-size bulk copies of the last tile stay in bounds
   TRY(dalloc(&c->d_visible, (size_t)N));
   c->mask_words = (N + 31) / 32; // RendererInstance.cpp:1651
   TRY(dalloc(&c->d_mask, (size_t)c->mask_words));
