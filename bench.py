@@ -379,22 +379,27 @@ def main():
     if not args.no_e2e and not multi:
         r = capi.Renderer(local_rank, scene)
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()  # noqa: E731
-        occ_pinned = pin((h, w), torch.float32)
-        occ_pinned[...] = scene.occluder_depth
+        # per-frame HOST inputs = what RendererInstance::update / render receive every frame: the camera and the (dirty)
+        # transforms; the external depth (terrain stand-in) is GPU-resident in the engine, so it is uploaded once
+        r.set_external_depth(scene.occluder_depth)
+        xf_pinned = pin((len(scene.transforms), 16), torch.float32)
+        xf_pinned[...] = scene.transforms["world"]
         outbuf = dict(vis32=pin((h, w), torch.int32).view(np.uint32), depth=pin((h, w), torch.float32),
                       idx=pin((max(1, scene.max_meshlet_instance_count),), torch.int32).view(np.uint32))
         for i in range(W):
-            res = r.render(cams[i % 2], occ_pinned, out=outbuf)
+            r.update_transforms(xf_pinned)
+            res = r.render(cams[i % 2], None, out=outbuf)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(K):
-            res = r.render(cams[i % 2], occ_pinned, out=outbuf)  # synchronous: returns with results in host memory
+            r.update_transforms(xf_pinned)                      # H2D: all transforms (pinned)
+            res = r.render(cams[i % 2], None, out=outbuf)       # H2D camera; D2H vis32 + depth + survivors + counters; synchronous
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / K
-        h2d = 96 + occ_pinned.nbytes
+        h2d = 96 + xf_pinned.nbytes
         d2h = outbuf["vis32"].nbytes + outbuf["depth"].nbytes + 4 * (res["early"] + res["late"]) + 12 + 8 + 8
         e2e = {"value": res["total"] / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e2e_s * 1e3, "api": "oxr_render (C++ ox::RendererInstance mirror over the C ABI), pinned host buffers"}
+               "ms_per_step": e2e_s * 1e3, "api": "oxr_update_transforms + oxr_render (C++ ox::RendererInstance mirror over the C ABI), pinned host buffers"}
         r.close()
     elif multi:
         e2e = None

@@ -347,9 +347,15 @@ void oxr_destroy(OxrRenderer* r);
 OxcContext* oxr_context(OxrRenderer* r);
 /* RendererInstance::update */
 int oxr_update(OxrRenderer* r, const OxcSceneDesc* scene);
+/* dirty-range transform upload (RendererInstance.cpp:16-109,1590-1599) from HOST memory, async on the renderer's
+ * stream (ordered before the next oxr_render) */
+int oxr_update_transforms(OxrRenderer* r, const OxcTransformWorld* transforms, uint32_t first, uint32_t count);
+/* Depth laid down by passes outside this path (terrain, RendererInstance.cpp:862-873): a width x height D32F HOST
+ * image copied to the device once and merged into every following frame; NULL removes it. */
+int oxr_set_external_depth(OxrRenderer* r, const float* depth_host);
 /* RendererInstance::render geometry section.  occluder_depth_host (may be NULL) is a width x height
- * D32F image merged into the frame depth before the early pass (stands in for depth written by
- * passes outside this path, e.g. terrain).  Outputs may be NULL.  Synchronous. */
+ * D32F image uploaded THIS frame and merged into the frame depth before the early pass (replaces the image of
+ * oxr_set_external_depth).  Outputs may be NULL.  Synchronous. */
 int oxr_render(OxrRenderer* r, const OxcCullCamera* camera, const float* occluder_depth_host,
                uint32_t* vis32_host, float* depth_host, uint32_t* visible_indices_host,
                uint32_t visible_indices_capacity, OxrFrameResult* result);

@@ -20,7 +20,7 @@ SYMBOLS = [
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview",
     "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
-    "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_render",
+    "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render",
 ]
 
 
@@ -78,6 +78,8 @@ def load(build_if_missing=True):
     lib.oxr_destroy.restype = None
     lib.oxr_context.argtypes = [vp]
     lib.oxr_update.argtypes = [vp, C.POINTER(abi.SceneDesc)]
+    lib.oxr_update_transforms.argtypes = [vp, vp, u32, u32]
+    lib.oxr_set_external_depth.argtypes = [vp, vp]
     lib.oxr_render.argtypes = [vp, vp, vp, vp, vp, vp, u32, C.POINTER(abi.FrameResult)]
     _LIB = lib
     return lib
@@ -300,6 +302,14 @@ class Renderer:
         desc, self._keep = synth.scene_desc(scene)
         _check(self.lib.oxr_update(self.h, C.byref(desc)), "oxr_update")
         self.ctx = Context.from_handle(self.lib.oxr_context(self.h))
+
+    def update_transforms(self, transforms, first=0):
+        t = transforms if isinstance(transforms, np.ndarray) and transforms.flags.c_contiguous else np.ascontiguousarray(transforms)
+        _check(self.lib.oxr_update_transforms(self.h, _ptr(t), first, len(t)), "oxr_update_transforms")
+
+    def set_external_depth(self, depth):
+        d = None if depth is None else np.ascontiguousarray(depth, dtype=np.float32)
+        _check(self.lib.oxr_set_external_depth(self.h, _ptr(d)), "oxr_set_external_depth")
 
     def render(self, cam, occluder_depth=None, want_image=True, want_indices=True, out=None):
         """out: optional dict(vis32=, depth=, idx=) of preallocated (e.g. pinned) host arrays to fill."""

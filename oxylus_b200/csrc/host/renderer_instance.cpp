@@ -57,6 +57,22 @@ auto RendererInstance::update(const RendererInstanceUpdateInfo& info) -> int {
   return fail(oxc_set_scene(ctx_, &info.scene, stream_));
 }
 
+auto RendererInstance::update_transforms(const OxcTransformWorld* transforms, uint32_t first, uint32_t count) -> int {
+  if (!ctx_) return OXC_E_STATE;
+  return fail(oxc_update_transforms(ctx_, transforms, first, count, stream_));
+}
+
+auto RendererInstance::set_external_depth(const float* depth_host) -> int {
+  if (!ctx_) return OXC_E_STATE;
+  has_external_depth_ = depth_host != nullptr;
+  if (!depth_host) return OXC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (cudaMemcpyAsync(d_occluder_, depth_host, (size_t)width_ * height_ * 4, cudaMemcpyHostToDevice, s) != cudaSuccess ||
+      cudaStreamSynchronize(s) != cudaSuccess)
+    return fail(OXC_E_CUDA);
+  return OXC_OK;
+}
+
 // CullGeometry.cpp:61-404
 auto RendererInstance::cull_geometry(CullGeometryContext& context) -> int {
   int rc;
@@ -101,8 +117,10 @@ auto RendererInstance::render(const OxcCullCamera& camera, const float* occluder
   if ((rc = oxc_clear_hiz(ctx_, s)) != OXC_OK) return fail(rc);
   if (occluder_depth_host) {
     if (cudaMemcpyAsync(d_occluder_, occluder_depth_host, px * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return fail(OXC_E_CUDA);
-    if ((rc = oxc_merge_depth(ctx_, d_vis64_, d_occluder_, width_, height_, s)) != OXC_OK) return fail(rc);
+    has_external_depth_ = true;
   }
+  if (has_external_depth_)
+    if ((rc = oxc_merge_depth(ctx_, d_vis64_, d_occluder_, width_, height_, s)) != OXC_OK) return fail(rc);
 
   MainGeometryContext main_geometry_context;
   main_geometry_context.visbuffer_attachment = d_vis64_;
@@ -202,6 +220,16 @@ int oxr_update(OxrRenderer* r, const OxcSceneDesc* scene) {
   int rc = r->impl.update(info);
   if (rc == OXC_OK && cudaStreamSynchronize(static_cast<cudaStream_t>(r->impl.stream())) != cudaSuccess) rc = OXC_E_CUDA;
   return rc;
+}
+
+int oxr_update_transforms(OxrRenderer* r, const OxcTransformWorld* transforms, uint32_t first, uint32_t count) {
+  if (!r || !transforms) return OXC_E_INVALID;
+  return r->impl.update_transforms(transforms, first, count);
+}
+
+int oxr_set_external_depth(OxrRenderer* r, const float* depth_host) {
+  if (!r) return OXC_E_INVALID;
+  return r->impl.set_external_depth(depth_host);
 }
 
 int oxr_render(OxrRenderer* r, const OxcCullCamera* camera, const float* occluder_depth_host, uint32_t* vis32_host,

@@ -55,6 +55,10 @@ public:
   void* stream() const { return stream_; }
 
   auto update(const RendererInstanceUpdateInfo& info) -> int;
+  // dirty-range transform upload (RendererInstance.cpp:16-109,1590-1599); async on the renderer's stream
+  auto update_transforms(const OxcTransformWorld* transforms, uint32_t first, uint32_t count) -> int;
+  // depth laid down by passes outside this path (terrain): kept on the device until replaced; nullptr clears it
+  auto set_external_depth(const float* depth_host) -> int;
   auto cull_geometry(CullGeometryContext& context) -> int;
   auto generate_hiz(MainGeometryContext& context) -> int;
   auto draw_for_visbuffer(MainGeometryContext& context) -> int;
@@ -72,6 +76,7 @@ private:
   uint32_t* d_vis32_ = nullptr;
   float* d_depth_ = nullptr;
   float* d_occluder_ = nullptr;
+  bool has_external_depth_ = false;
   void* h_pinned_ = nullptr; // staging for small readbacks
   std::string error_;
 };

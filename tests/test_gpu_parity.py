@@ -309,3 +309,29 @@ def test_hiz_split_build_equals_single_pass(capi, orc):
             np.testing.assert_array_equal(got[lvl].view(np.uint32), ref.level(lvl).view(np.uint32), err_msg=f"{w}x{h} mip {lvl}")
         ctx.free(v_dev)
         ctx.close()
+
+
+def test_renderer_persistent_depth_and_transform_updates(capi, orc):
+    """oxr_set_external_depth + oxr_update_transforms (per-frame HOST inputs of the e2e bench) vs the oracle."""
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    r = capi.Renderer(0, sc)
+    r.set_external_depth(sc.occluder_depth)
+    mask_ref = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    rng = np.random.default_rng(5)
+    xf = sc.transforms.copy()
+    for f in range(3):
+        # move a third of the instances a little every frame
+        sel = rng.random(len(xf)) < 0.33
+        xf["world"][sel, 12:15] += rng.normal(0, 0.5, size=(int(sel.sum()), 3)).astype(np.float32)
+        sc_f = synth.Scene(sc.meshes, sc.mesh_instances, xf.copy(), sc.blob, sc.max_meshlet_instance_count, sc.width, sc.height, sc.seed)
+        hs = orc.HostScene(sc_f)
+        cam = sc.camera(1.5 * f)
+        ref = orc.frame(hs, cam, sc.width, sc.height, mask_ref, sc.occluder_depth)
+        r.update_transforms(xf)
+        got = r.render(cam, None)
+        v32, d = orc.resolve(ref["vis64"])
+        assert (got["total"], got["early"], got["late"]) == (int(ref["visibility"]["total"][0]), ref["early"], ref["late"])
+        np.testing.assert_array_equal(got["vis32"], v32)
+        np.testing.assert_array_equal(np.sort(got["visible"]), np.sort(ref["visible"][: ref["early"] + ref["late"]]))
+        np.testing.assert_array_equal(r.ctx.mask(), mask_ref)
+    r.close()
