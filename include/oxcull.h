@@ -360,6 +360,15 @@ int oxr_render(OxrRenderer* r, const OxcCullCamera* camera, const float* occlude
                uint32_t* vis32_host, float* depth_host, uint32_t* visible_indices_host,
                uint32_t visible_indices_capacity, OxrFrameResult* result);
 
+/* Pipelined frames: oxr_submit enqueues the frame and the device->host copies of its results (separate copy
+ * stream, double-buffered staging) and returns a ticket (0/1) without waiting; oxr_wait blocks until that frame's
+ * outputs are in the caller's (pinned) host buffers and fills `result`.  At most two frames in flight; a slot's
+ * ticket must be waited before the slot is reused.  Survivor ids: min(capacity, max_meshlet_instances) entries are
+ * copied; the valid prefix is result->visibility.early + late. */
+int oxr_submit(OxrRenderer* r, const OxcCullCamera* camera, uint32_t* vis32_host, float* depth_host,
+               uint32_t* visible_indices_host, uint32_t visible_indices_capacity, int* ticket);
+int oxr_wait(OxrRenderer* r, int ticket, OxrFrameResult* result);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,7 +20,7 @@ SYMBOLS = [
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview",
     "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
-    "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render",
+    "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
 ]
 
 
@@ -80,6 +80,8 @@ def load(build_if_missing=True):
     lib.oxr_update.argtypes = [vp, C.POINTER(abi.SceneDesc)]
     lib.oxr_update_transforms.argtypes = [vp, vp, u32, u32]
     lib.oxr_set_external_depth.argtypes = [vp, vp]
+    lib.oxr_submit.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(C.c_int)]
+    lib.oxr_wait.argtypes = [vp, i32, C.POINTER(abi.FrameResult)]
     lib.oxr_render.argtypes = [vp, vp, vp, vp, vp, vp, u32, C.POINTER(abi.FrameResult)]
     _LIB = lib
     return lib
@@ -328,6 +330,20 @@ class Renderer:
         return dict(vis32=vis32, depth=depth, visible=idx[:n] if idx is not None else None, total=res.total, early=res.early,
                     late=res.late, draw_index_count_early=res.draw_index_count_early,
                     draw_index_count_late=res.draw_index_count_late, raster_triangles=res.raster_triangles)
+
+    def submit(self, cam, out):
+        """Pipelined frame: out = dict(vis32=, depth=, idx=) of PINNED host arrays for this frame.  Returns a ticket."""
+        t = C.c_int(-1)
+        idx = out.get("idx")
+        _check(self.lib.oxr_submit(self.h, _ptr(cam), _ptr(out.get("vis32")), _ptr(out.get("depth")), _ptr(idx),
+                                   len(idx) if idx is not None else 0, C.byref(t)), "oxr_submit")
+        return t.value
+
+    def wait(self, ticket):
+        res = abi.FrameResult()
+        _check(self.lib.oxr_wait(self.h, ticket, C.byref(res)), "oxr_wait")
+        return dict(total=res.total, early=res.early, late=res.late, raster_triangles=res.raster_triangles,
+                    draw_index_count_early=res.draw_index_count_early, draw_index_count_late=res.draw_index_count_late)
 
     def close(self):
         if getattr(self, "h", None):

@@ -40,12 +40,36 @@ RendererInstance::RendererInstance(int device, const OxcCreateInfo& info, uint32
     error_ = std::string("RendererInstance allocation failed: ") + cudaGetErrorString(cudaGetLastError());
   }
   stream_ = s;
+  ids_capacity_ = info.max_meshlet_instances ? info.max_meshlet_instances : 1;
+  cudaStream_t cs = nullptr;
+  bool ok = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess;
+  copy_stream_ = cs;
+  for (auto& sl : slots_) {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    ok = ok && cudaMalloc(reinterpret_cast<void**>(&sl.d_vis32), px * 4) == cudaSuccess &&
+         cudaMalloc(reinterpret_cast<void**>(&sl.d_depth), px * 4) == cudaSuccess &&
+         cudaMalloc(reinterpret_cast<void**>(&sl.d_ids), (size_t)ids_capacity_ * 4) == cudaSuccess &&
+         cudaMallocHost(&sl.h_readback, sizeof(Readback)) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e0, cudaEventDisableTiming) == cudaSuccess &&
+         cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) == cudaSuccess;
+    sl.ev_compute = e0;
+    sl.ev_copy = e1;
+  }
+  if (!ok && error_.empty()) error_ = std::string("RendererInstance pipeline allocation failed: ") + cudaGetErrorString(cudaGetLastError());
 }
 
 RendererInstance::~RendererInstance() {
   if (stream_) cudaStreamSynchronize(static_cast<cudaStream_t>(stream_));
   cudaFree(d_vis64_); cudaFree(d_vis32_); cudaFree(d_depth_); cudaFree(d_occluder_);
   if (h_pinned_) cudaFreeHost(h_pinned_);
+  if (copy_stream_) cudaStreamSynchronize(static_cast<cudaStream_t>(copy_stream_));
+  for (auto& sl : slots_) {
+    cudaFree(sl.d_vis32); cudaFree(sl.d_depth); cudaFree(sl.d_ids);
+    if (sl.h_readback) cudaFreeHost(sl.h_readback);
+    if (sl.ev_compute) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_compute));
+    if (sl.ev_copy) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_copy));
+  }
+  if (copy_stream_) cudaStreamDestroy(static_cast<cudaStream_t>(copy_stream_));
   if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
   oxc_destroy(ctx_);
 }
@@ -101,26 +125,24 @@ auto RendererInstance::draw_for_visbuffer(MainGeometryContext& context) -> int {
                                    context.visbuffer_attachment, 0, stream_));
 }
 
-auto RendererInstance::render(const OxcCullCamera& camera, const float* occluder_depth_host, uint32_t* vis32_host,
-                              float* depth_host, uint32_t* visible_indices_host, uint32_t visible_indices_capacity,
-                              OxrFrameResult* result) -> int {
-  if (!ctx_ || !error_.empty()) return OXC_E_STATE;
+// The geometry section of RendererInstance::render (RendererInstance.cpp:768-884), enqueued on stream_.
+int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const size_t px = (size_t)width_ * height_;
   int rc;
   OxcOutputs out;
-  if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return fail(rc);
-  Readback* rb = static_cast<Readback*>(h_pinned_);
+  if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return rc;
+  Readback* rb = static_cast<Readback*>(readback);
 
   // attachments: depth cleared to 0, vis buffer to ~0 (RendererInstance.cpp:562-571,629-680), Hi-Z cleared every frame (:579-588)
-  if ((rc = oxc_clear_visbuffer(ctx_, d_vis64_, width_, height_, s)) != OXC_OK) return fail(rc);
-  if ((rc = oxc_clear_hiz(ctx_, s)) != OXC_OK) return fail(rc);
+  if ((rc = oxc_clear_visbuffer(ctx_, d_vis64_, width_, height_, s)) != OXC_OK) return rc;
+  if ((rc = oxc_clear_hiz(ctx_, s)) != OXC_OK) return rc;
   if (occluder_depth_host) {
-    if (cudaMemcpyAsync(d_occluder_, occluder_depth_host, px * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return fail(OXC_E_CUDA);
+    if (cudaMemcpyAsync(d_occluder_, occluder_depth_host, px * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return OXC_E_CUDA;
     has_external_depth_ = true;
   }
   if (has_external_depth_)
-    if ((rc = oxc_merge_depth(ctx_, d_vis64_, d_occluder_, width_, height_, s)) != OXC_OK) return fail(rc);
+    if ((rc = oxc_merge_depth(ctx_, d_vis64_, d_occluder_, width_, height_, s)) != OXC_OK) return rc;
 
   MainGeometryContext main_geometry_context;
   main_geometry_context.visbuffer_attachment = d_vis64_;
@@ -152,9 +174,23 @@ auto RendererInstance::render(const OxcCullCamera& camera, const float* occluder
   };
 
   rb->draw_index_count[0] = rb->draw_index_count[1] = 0;
-  if ((rc = run_geometry_pass(false)) != OXC_OK) return fail(rc); // :882
-  if ((rc = generate_hiz(main_geometry_context)) != OXC_OK) return fail(rc); // :883
-  if ((rc = run_geometry_pass(true)) != OXC_OK) return fail(rc);  // :884
+  if ((rc = run_geometry_pass(false)) != OXC_OK) return rc; // :882
+  if ((rc = generate_hiz(main_geometry_context)) != OXC_OK) return rc; // :883
+  if ((rc = run_geometry_pass(true)) != OXC_OK) return rc;  // :884
+  return OXC_OK;
+}
+
+auto RendererInstance::render(const OxcCullCamera& camera, const float* occluder_depth_host, uint32_t* vis32_host,
+                              float* depth_host, uint32_t* visible_indices_host, uint32_t visible_indices_capacity,
+                              OxrFrameResult* result) -> int {
+  if (!ctx_ || !error_.empty()) return OXC_E_STATE;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const size_t px = (size_t)width_ * height_;
+  int rc;
+  OxcOutputs out;
+  if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return fail(rc);
+  Readback* rb = static_cast<Readback*>(h_pinned_);
+  if ((rc = run_frame(camera, occluder_depth_host, rb)) != OXC_OK) return fail(rc);
 
   // results back to the host (the engine would hand the attachments to decode_visbuffer, :923-925)
   if (vis32_host || depth_host) {
@@ -176,6 +212,62 @@ auto RendererInstance::render(const OxcCullCamera& camera, const float* occluder
       return fail(OXC_E_CUDA);
   }
   if (result) {
+    result->visibility = rb->visibility;
+    result->draw_index_count_early = rb->draw_index_count[0];
+    result->draw_index_count_late = rb->draw_index_count[1];
+    result->raster_triangles = rb->raster_triangles;
+  }
+  return OXC_OK;
+}
+
+auto RendererInstance::submit(const OxcCullCamera& camera, uint32_t* vis32_host, float* depth_host,
+                              uint32_t* visible_indices_host, uint32_t visible_indices_capacity, int* ticket) -> int {
+  if (!ctx_ || !error_.empty() || !ticket) return OXC_E_STATE;
+  const int slot = (int)(frame_ & 1);
+  Slot& sl = slots_[slot];
+  if (sl.in_flight) {
+    error_ = "oxr_submit: the previous frame of this slot has not been waited";
+    return OXC_E_STATE;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream_), cs = static_cast<cudaStream_t>(copy_stream_);
+  const size_t px = (size_t)width_ * height_;
+  int rc;
+  OxcOutputs out;
+  if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return fail(rc);
+  Readback* rb = static_cast<Readback*>(sl.h_readback);
+  if ((rc = run_frame(camera, nullptr, rb)) != OXC_OK) return fail(rc);
+  // stage the results of this frame (the staging of this slot was drained by wait() of its previous ticket)
+  if ((rc = oxc_resolve_visbuffer(ctx_, d_vis64_, width_, height_, vis32_host ? sl.d_vis32 : nullptr, depth_host ? sl.d_depth : nullptr, s)) != OXC_OK)
+    return fail(rc);
+  uint32_t n_ids = visible_indices_host ? (visible_indices_capacity < ids_capacity_ ? visible_indices_capacity : ids_capacity_) : 0;
+  if (n_ids && cudaMemcpyAsync(sl.d_ids, out.visible_meshlet_instances_indices, (size_t)n_ids * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    return fail(OXC_E_CUDA);
+  if (cudaMemcpyAsync(&rb->visibility, out.visibility, sizeof rb->visibility, cudaMemcpyDeviceToHost, s) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (cudaMemcpyAsync(&rb->raster_triangles, out.raster_triangle_count, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_compute), s) != cudaSuccess) return fail(OXC_E_CUDA);
+  // device -> host on the copy stream, overlapping the next frame's kernels
+  if (cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(sl.ev_compute), 0) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (vis32_host && cudaMemcpyAsync(vis32_host, sl.d_vis32, px * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (depth_host && cudaMemcpyAsync(depth_host, sl.d_depth, px * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (n_ids && cudaMemcpyAsync(visible_indices_host, sl.d_ids, (size_t)n_ids * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_copy), cs) != cudaSuccess) return fail(OXC_E_CUDA);
+  sl.in_flight = true;
+  *ticket = slot;
+  frame_++;
+  return OXC_OK;
+}
+
+auto RendererInstance::wait(int ticket, OxrFrameResult* result) -> int {
+  if (ticket < 0 || ticket > 1) return OXC_E_INVALID;
+  Slot& sl = slots_[ticket];
+  if (!sl.in_flight) return OXC_E_STATE;
+  if (cudaEventSynchronize(static_cast<cudaEvent_t>(sl.ev_copy)) != cudaSuccess) {
+    error_ = cudaGetErrorString(cudaGetLastError());
+    return OXC_E_CUDA;
+  }
+  sl.in_flight = false;
+  if (result) {
+    const Readback* rb = static_cast<const Readback*>(sl.h_readback);
     result->visibility = rb->visibility;
     result->draw_index_count_early = rb->draw_index_count[0];
     result->draw_index_count_late = rb->draw_index_count[1];
@@ -230,6 +322,17 @@ int oxr_update_transforms(OxrRenderer* r, const OxcTransformWorld* transforms, u
 int oxr_set_external_depth(OxrRenderer* r, const float* depth_host) {
   if (!r) return OXC_E_INVALID;
   return r->impl.set_external_depth(depth_host);
+}
+
+int oxr_submit(OxrRenderer* r, const OxcCullCamera* camera, uint32_t* vis32_host, float* depth_host,
+               uint32_t* visible_indices_host, uint32_t visible_indices_capacity, int* ticket) {
+  if (!r || !camera || !ticket) return OXC_E_INVALID;
+  return r->impl.submit(*camera, vis32_host, depth_host, visible_indices_host, visible_indices_capacity, ticket);
+}
+
+int oxr_wait(OxrRenderer* r, int ticket, OxrFrameResult* result) {
+  if (!r) return OXC_E_INVALID;
+  return r->impl.wait(ticket, result);
 }
 
 int oxr_render(OxrRenderer* r, const OxcCullCamera* camera, const float* occluder_depth_host, uint32_t* vis32_host,

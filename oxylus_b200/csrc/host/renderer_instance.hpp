@@ -67,8 +67,30 @@ public:
   auto render(const OxcCullCamera& camera, const float* occluder_depth_host, uint32_t* vis32_host, float* depth_host,
               uint32_t* visible_indices_host, uint32_t visible_indices_capacity, OxrFrameResult* result) -> int;
 
+  // Pipelined variant: submit() enqueues the frame and the device->host copies of its results (on a copy stream,
+  // from double-buffered staging) and returns a ticket without waiting; wait(ticket) blocks until that frame's
+  // outputs are in the caller's host buffers.  At most two frames in flight; a ticket must be waited before
+  // its slot is reused (submit returns OXC_E_STATE otherwise).  Survivor ids: the full capacity is copied
+  // (the count is only known on the device when the copy is enqueued).
+  auto submit(const OxcCullCamera& camera, uint32_t* vis32_host, float* depth_host, uint32_t* visible_indices_host,
+              uint32_t visible_indices_capacity, int* ticket) -> int;
+  auto wait(int ticket, OxrFrameResult* result) -> int;
+
 private:
   int fail(int rc);
+  int run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback_draw_counts);
+  struct Slot {
+    uint32_t* d_vis32 = nullptr;
+    float* d_depth = nullptr;
+    uint32_t* d_ids = nullptr;
+    void* h_readback = nullptr; // pinned
+    void* ev_compute = nullptr;
+    void* ev_copy = nullptr;
+    bool in_flight = false;
+  } slots_[2];
+  void* copy_stream_ = nullptr;
+  uint64_t frame_ = 0;
+  uint32_t ids_capacity_ = 0;
   OxcContext* ctx_ = nullptr;
   void* stream_ = nullptr;
   uint32_t width_ = 0, height_ = 0;

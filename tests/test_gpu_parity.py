@@ -335,3 +335,39 @@ def test_renderer_persistent_depth_and_transform_updates(capi, orc):
         np.testing.assert_array_equal(np.sort(got["visible"]), np.sort(ref["visible"][: ref["early"] + ref["late"]]))
         np.testing.assert_array_equal(r.ctx.mask(), mask_ref)
     r.close()
+
+
+def test_renderer_pipelined_submit_wait(capi, orc):
+    """oxr_submit / oxr_wait (two frames in flight, copy stream) deliver the same results as the oracle, frame by frame."""
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    hs = orc.HostScene(sc)
+    r = capi.Renderer(0, sc)
+    r.set_external_depth(sc.occluder_depth)
+    mask_ref = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    bufs = [dict(vis32=np.zeros((sc.height, sc.width), np.uint32), depth=np.zeros((sc.height, sc.width), np.float32),
+                 idx=np.zeros(sc.max_meshlet_instance_count, np.uint32)) for _ in range(2)]
+    refs, prev = [], None
+
+    def check(frame_index, res):
+        ref = refs[frame_index]
+        b = bufs[frame_index % 2]
+        assert (res["total"], res["early"], res["late"]) == ref[0]
+        np.testing.assert_array_equal(b["vis32"], ref[1])
+        np.testing.assert_array_equal(b["depth"].view(np.uint32), ref[2].view(np.uint32))
+        np.testing.assert_array_equal(np.sort(b["idx"][: res["early"] + res["late"]]), ref[3])
+
+    for f in range(5):
+        cam = sc.camera(2.0 * f)
+        ref = orc.frame(hs, cam, sc.width, sc.height, mask_ref, sc.occluder_depth)
+        v32, d = orc.resolve(ref["vis64"])
+        n = ref["early"] + ref["late"]
+        refs.append(((int(ref["visibility"]["total"][0]), ref["early"], ref["late"]), v32, d, np.sort(ref["visible"][:n])))
+        t = r.submit(cam, bufs[f % 2])
+        if prev is not None:
+            check(f - 1, r.wait(prev))
+        prev = t
+    check(4, r.wait(prev))
+    np.testing.assert_array_equal(r.ctx.mask(), mask_ref)
+    with pytest.raises(capi.OxcError):
+        r.wait(0)  # nothing in flight
+    r.close()
