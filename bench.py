@@ -218,9 +218,12 @@ def main():
         out = pipe.ctx.out
         # zero-copy torch views of the context's device buffers (no staging copies in the exchange)
         vis_view = pipeline.wrap_device(out.visibility, 3, torch.int32, dev)            # total / early / late
-        ids_view = pipeline.wrap_device(out.visible_meshlet_instances_indices, cap, torch.int32, dev)
+        # survivor allgather: fixed-capacity segments (NCCL has no allgatherv).  Half a shard is ample for this scene
+        # (~30 % visible); an overflow is detected from the gathered counts after the run and reported.
+        gcap = max(1024, cap // 2)
+        ids_view = pipeline.wrap_device(out.visible_meshlet_instances_indices, gcap, torch.int32, dev)
         vis_all = torch.zeros(world * 3, dtype=torch.int32, device=dev)
-        ids_all = torch.zeros(world * cap, dtype=torch.int32, device=dev)
+        ids_all = torch.zeros(world * gcap, dtype=torch.int32, device=dev)
 
         def after_cull_meshes():
             # emitted counts of every rank -> exclusive prefix = this rank's global meshlet-instance id base
@@ -423,6 +426,12 @@ def main():
                                   f"(oracle port of the reference shaders, pthreads x{cores}); {sec * 1e3:.0f} ms/frame",
                         "triangles_per_s": last["triangles"] / sec}
 
+    exchange = None
+    if multi:
+        cnts = vis_all.view(world, 3).cpu().numpy()
+        exchange = {"survivor_gather_capacity": int(gcap), "max_survivors_per_rank": int((cnts[:, 1] + cnts[:, 2]).max()),
+                    "overflow": bool((cnts[:, 1] + cnts[:, 2]).max() > gcap),
+                    "steps": "allgather(counts) -> id base; all_reduce(MAX) Hi-Z mip 0; all_reduce(MAX) vis buffer; allgather(counts); allgather(survivor ids)"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
@@ -433,7 +442,7 @@ def main():
                           "triangles_rasterised": job_tris},
             "stages_ms": stages_ms, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches_per_frame * K), "gpu_launches_per_step": int(launches_per_frame),
-            "cuda_graph": graphs is not None, "wall_s_timed_region": t_wall,
+            "cuda_graph": graphs is not None, "wall_s_timed_region": t_wall, "exchange": exchange,
         }
         print(json.dumps(line), flush=True)
     pipe.close()
