@@ -205,7 +205,7 @@ def main():
     if multi:
         parts = oxdist.partition_mesh_instances(oxdist.lod0_counts_of(scene), world)
         shard = parts[rank]
-    pipe = pipeline.VisibilityPipeline(scene, device=local_rank, shard=shard)
+    pipe = pipeline.VisibilityPipeline(scene, device=local_rank, shard=shard, auto_id_base=True)
     cams = [scene.camera(0.0), scene.camera(2.0)]
     dev = pipe.device
     w, h = scene.width, scene.height
@@ -225,10 +225,7 @@ def main():
         vis_all = torch.zeros(world * 3, dtype=torch.int32, device=dev)
         ids_all = torch.zeros(world * gcap, dtype=torch.int32, device=dev)
 
-        def after_cull_meshes():
-            # emitted counts of every rank -> exclusive prefix = this rank's global meshlet-instance id base
-            dist.all_gather_into_tensor(vis_all, vis_view)
-            pipe.id_base.copy_(vis_all.view(world, 3)[:rank, 0].sum())
+        after_cull_meshes = None  # global id base: computed locally by oxc_cull_meshes (oxc_set_shard_auto), no exchange
 
         hw_, hh_ = scene.hiz_extent()
         mip0_view = pipeline.wrap_device(out.hiz, hw_ * hh_, torch.int32, dev)  # level 0 starts at offset 0
@@ -237,7 +234,7 @@ def main():
             dist.all_reduce(mip0_view, op=dist.ReduceOp.MAX)  # depths are >= +0: int32 order == float order
 
         def after_frame():
-            oxdist.reduce_visbuffer(pipe.vis64)
+            dist.reduce(pipe.vis64, dst=0, op=dist.ReduceOp.MAX)  # per-pixel max of the packed depth|id image -> rank 0
             dist.all_gather_into_tensor(vis_all, vis_view)   # early / late counts of every rank
             dist.all_gather_into_tensor(ids_all, ids_view)   # survivor ids (global), fixed-capacity segments
             gathered["last"] = (ids_all, vis_all)
@@ -431,7 +428,7 @@ def main():
         cnts = vis_all.view(world, 3).cpu().numpy()
         exchange = {"survivor_gather_capacity": int(gcap), "max_survivors_per_rank": int((cnts[:, 1] + cnts[:, 2]).max()),
                     "overflow": bool((cnts[:, 1] + cnts[:, 2]).max() > gcap),
-                    "steps": "allgather(counts) -> id base; all_reduce(MAX) Hi-Z mip 0; all_reduce(MAX) vis buffer; allgather(counts); allgather(survivor ids)"}
+                    "steps": "id base from a local count-only replay (no exchange); all_reduce(MAX) Hi-Z mip 0; reduce(MAX) vis buffer -> rank 0; allgather(counts); allgather(survivor ids)"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": ms_per_step,

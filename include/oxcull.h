@@ -253,6 +253,10 @@ int oxc_clear_hiz(OxcContext* ctx, void* stream);
  * rank's shard.  id_base_dev (device u32, may be NULL = 0) is added to every meshlet-instance index
  * this context emits (survivor list, vis-buffer IDs) so IDs are global across ranks. */
 int oxc_set_shard(OxcContext* ctx, uint32_t first_mesh_instance, uint32_t mesh_instance_count, const uint32_t* id_base_dev);
+/* Same shard, but the id base is computed by oxc_cull_meshes itself: the number of meshlet instances the mesh
+ * instances below the shard emit under the same camera / flags (count-only replay of the mesh-level cull; the
+ * small tables are replicated on every rank) — no inter-GPU exchange needed for global ids. */
+int oxc_set_shard_auto(OxcContext* ctx, uint32_t first_mesh_instance, uint32_t mesh_instance_count);
 
 /* cull_meshes.slang:17-85 via CullGeometry.cpp:68-117 (init_cull_meshes == true).
  * Resets visibility{0,0,0} and cull_meshlets_cmd{0,1,1} (scratch_buffer init, :97-100), then per

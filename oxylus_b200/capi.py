@@ -16,7 +16,7 @@ E_NO_DEVICE = -3
 # every symbol include/oxcull.h declares (tests check the .so exports all of them)
 SYMBOLS = [
     "oxc_last_error", "oxc_kernel_launch_count", "oxc_version", "oxc_create", "oxc_destroy", "oxc_set_scene",
-    "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_cull_meshes",
+    "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_set_shard_auto", "oxc_cull_meshes",
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview",
     "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
@@ -55,6 +55,7 @@ def load(build_if_missing=True):
     lib.oxc_reset_visibility_mask.argtypes = [vp, vp]
     lib.oxc_clear_hiz.argtypes = [vp, vp]
     lib.oxc_set_shard.argtypes = [vp, u32, u32, vp]
+    lib.oxc_set_shard_auto.argtypes = [vp, u32, u32]
     lib.oxc_cull_meshes.argtypes = [vp, vp, u32, vp]
     lib.oxc_cull_meshlets.argtypes = [vp, vp, u32, i32, vp]
     lib.oxc_build_hiz.argtypes = [vp, vp, u32, u32, vp]
@@ -167,6 +168,9 @@ class Context:
 
     def set_shard(self, first, count, id_base_dev=None):
         _check(self.lib.oxc_set_shard(self.h, first, count, _ptr(id_base_dev)), "oxc_set_shard")
+
+    def set_shard_auto(self, first, count):
+        _check(self.lib.oxc_set_shard_auto(self.h, first, count), "oxc_set_shard_auto")
 
     # ---- passes ----
     def cull_meshes(self, cam, flags=abi.CULL_TEST_ALL):

@@ -165,6 +165,52 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __gri
   }
 }
 
+// Multi-GPU id base without communication: the number of meshlet instances the mesh instances [0, first) emit
+// under this camera (same frustum test + LOD selection as k_cull_meshes, count only).  Every rank can evaluate it
+// locally because the small tables are replicated; integer sum => order independent.
+__global__ void __launch_bounds__(CULL_MESHES_THREADS) k_count_prefix_meshlets(const __grid_constant__ MeshesParams p, uint32_t* id_base) {
+  const uint32_t mi = blockIdx.x * CULL_MESHES_THREADS + threadIdx.x;
+  uint32_t meshlet_count = 0;
+  if (mi < p.first) {
+    const OxcMeshInstance inst = p.mesh_instances[mi];
+    const OxcMesh* mesh = &p.meshes[inst.mesh_index];
+    const float* world = p.transforms[inst.transform_index].world;
+    float w[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) w[k] = world[k];
+    float4 rows[4], planes[6];
+    mul_mm_rows(p.cam.projection_view, w, rows);
+    frustum_planes(rows, planes);
+    const OxcMeshLOD* lods = reinterpret_cast<const OxcMeshLOD*>(mesh->lods);
+    const float bcx = mesh->bounds.aabb_center[0], bcy = mesh->bounds.aabb_center[1], bcz = mesh->bounds.aabb_center[2];
+    const float bex = mesh->bounds.aabb_extent[0], bey = mesh->bounds.aabb_extent[1], bez = mesh->bounds.aabb_extent[2];
+    if ((p.flags & OXC_CULL_TEST_FRUSTUM) && test_frustum_rows(planes, bcx, bcy, bcz, bex, bey, bez)) {
+      uint32_t lod_index = 0;
+      if (p.flags & OXC_CULL_SELECT_LOD) {
+        const float4 w0 = make_float4(w[0], w[4], w[8], w[12]), w1 = make_float4(w[1], w[5], w[9], w[13]),
+                     w2 = make_float4(w[2], w[6], w[10], w[14]);
+        const float cx = row_dot4(w0, bcx, bcy, bcz, 1.0f), cy = row_dot4(w1, bcx, bcy, bcz, 1.0f), cz = row_dot4(w2, bcx, bcy, bcz, 1.0f);
+        const float ex = fabsf(row_dot4(w0, bex, bey, bez, 0.0f)), ey = fabsf(row_dot4(w1, bex, bey, bez, 0.0f)),
+                    ez = fabsf(row_dot4(w2, bex, bey, bez, 0.0f));
+        const float rough_extent = omax(ex, omax(ey, ez));
+        const float dist = omax(fs(length3(fs(cx, p.cam.position[0]), fs(cy, p.cam.position[1]), fs(cz, p.cam.position[2])),
+                                   fm(0.5f, rough_extent)), 0.0f);
+        const float pixel_size_at_1m = fd(2.0f, omax(p.cam.resolution[0], p.cam.resolution[1]));
+        const float rough_pixel_size = fd(fd(rough_extent, dist), pixel_size_at_1m);
+        for (uint32_t i = 1; i < mesh->lod_count; i++) {
+          if (fm(rough_pixel_size, lods[i].error) < p.cam.acceptable_lod_error) lod_index = i;
+          else break;
+        }
+      }
+      meshlet_count = lods[lod_index].meshlet_count;
+    }
+  }
+  uint32_t v = meshlet_count;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0 && v) atomicAdd(id_base, v);
+}
+
 // One-time per scene: union AABB of the DECODED meshlet boxes (c +- e/2) of every (mesh, LOD).  One warp per
 // (mesh, lod).  Feeds the instance-level "provably inside the frustum" shortcut.
 __global__ void k_lod_union_aabb(const OxcMesh* __restrict__ meshes, uint32_t n_meshes, float* __restrict__ out) {

@@ -122,6 +122,8 @@ struct OxcContext {
   // shard
   uint32_t shard_first = 0, shard_count = 0xFFFFFFFFu;
   const uint32_t* id_base = nullptr;
+  uint32_t* d_id_base_auto = nullptr; // id base computed locally by oxc_cull_meshes (oxc_set_shard_auto)
+  bool id_base_auto = false;
   // multiview
   InstPlanes* d_view_planes = nullptr;
   OxcCullCamera* d_views = nullptr;
@@ -224,6 +226,7 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   TRY(dalloc(&c->d_draw_cmd, 1));
   TRY(dalloc(&c->d_tri_counter, 1));
   TRY(dalloc(&c->d_raster_work, 1));
+  TRY(dalloc(&c->d_id_base_auto, 1));
   if (info->alloc_reordered_indices) TRY(dalloc(&c->d_reordered, (size_t)N * OXC_MESHLET_MAX_PRIMITIVES * 3));
   if (info->max_views > 1) {
     TRY(dalloc(&c->d_view_planes, (size_t)I * info->max_views));
@@ -281,7 +284,7 @@ void oxc_destroy(OxcContext* c) {
   cudaFree(c->d_lod_aabb); cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
   cudaFree(c->d_meshlet_instances); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
-  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_hiz);
+  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_id_base_auto); cudaFree(c->d_hiz);
   cudaFree(c->d_view_planes); cudaFree(c->d_views); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts);
   delete c;
 }
@@ -359,7 +362,14 @@ int oxc_clear_hiz(OxcContext* c, void* stream) {
 
 int oxc_set_shard(OxcContext* c, uint32_t first, uint32_t count, const uint32_t* id_base_dev) {
   if (!c) return fail(OXC_E_INVALID, "null context");
-  c->shard_first = first; c->shard_count = count; c->id_base = id_base_dev;
+  c->shard_first = first; c->shard_count = count; c->id_base = id_base_dev; c->id_base_auto = false;
+  c->cache_valid = false;
+  return OXC_OK;
+}
+
+int oxc_set_shard_auto(OxcContext* c, uint32_t first, uint32_t count) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  c->shard_first = first; c->shard_count = count; c->id_base = c->d_id_base_auto; c->id_base_auto = true;
   c->cache_valid = false;
   return OXC_OK;
 }
@@ -374,6 +384,13 @@ int oxc_cull_meshes(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, voi
   p.inst = c->d_inst; p.geom = c->d_geom; p.counts = c->d_counts; p.block_sums = c->d_block_sums; p.lod_aabb = c->d_lod_aabb;
   shard_range(c, cam->mesh_instance_count, &p.first, &p.count);
   p.flags = flags; p.select = 1; p.cam = *cam;
+  if (c->id_base_auto) { // global id base of this shard = meshlets emitted by the mesh instances below it (no communication)
+    CK(cudaMemsetAsync(c->d_id_base_auto, 0, 4, s));
+    if (p.first) {
+      k_count_prefix_meshlets<<<(p.first + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS, CULL_MESHES_THREADS, 0, s>>>(p, c->d_id_base_auto);
+      LAUNCHED();
+    }
+  }
   const uint32_t n_blocks = (p.count + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS;
   if (n_blocks == 0) {
     k_reset_visibility<<<1, 1, 0, s>>>(c->d_vis, c->d_cull_meshlets_cmd);

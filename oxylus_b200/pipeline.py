@@ -26,7 +26,7 @@ def wrap_device(ptr, n, dtype, device):
 
 
 class VisibilityPipeline:
-    def __init__(self, scene, device=0, shard=None, alloc_reordered_indices=False):
+    def __init__(self, scene, device=0, shard=None, alloc_reordered_indices=False, auto_id_base=False):
         self.scene = scene
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
@@ -41,7 +41,10 @@ class VisibilityPipeline:
             self.occluder = torch.from_numpy(np.ascontiguousarray(scene.occluder_depth)).to(self.device)
         self.id_base = torch.zeros(1, dtype=torch.int32, device=self.device)
         if shard is not None:
-            self.ctx.set_shard(shard[0], shard[1], self.id_base.data_ptr())
+            if auto_id_base:
+                self.ctx.set_shard_auto(shard[0], shard[1])  # id base from a local count-only replay: no exchange
+            else:
+                self.ctx.set_shard(shard[0], shard[1], self.id_base.data_ptr())
         self.use_torch_stream()
 
     def use_torch_stream(self):

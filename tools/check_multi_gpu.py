@@ -30,7 +30,8 @@ def main():
     lod0 = oxdist.lod0_counts_of(sc)
     parts = oxdist.partition_mesh_instances(lod0, world)
     cap = max(int(lod0[f:f + c].sum()) for f, c in parts)
-    pipe = pipeline.VisibilityPipeline(sc, device=local, shard=parts[rank])
+    auto = os.environ.get("OXC_AUTO_ID_BASE", "1") == "1"
+    pipe = pipeline.VisibilityPipeline(sc, device=local, shard=parts[rank], auto_id_base=auto)
     out = pipe.ctx.out
     vis_view = pipeline.wrap_device(out.visibility, 3, torch.int32, dev)
     ids_view = pipeline.wrap_device(out.visible_meshlet_instances_indices, cap, torch.int32, dev)
@@ -55,7 +56,7 @@ def main():
     ok = True
     for f in range(4):
         cam = sc.camera(2.0 * f)
-        pipe.frame(cam, after_cull_meshes=after_cull_meshes, between_passes=between_passes, after_frame=after_frame)
+        pipe.frame(cam, after_cull_meshes=None if auto else after_cull_meshes, between_passes=between_passes, after_frame=after_frame)
         torch.cuda.synchronize()
         counts = vis_all.view(world, 3).cpu().numpy()
         ids = ids_all.view(world, cap).cpu().numpy()
