@@ -234,7 +234,7 @@ def main():
             dist.all_reduce(mip0_view, op=dist.ReduceOp.MAX)  # depths are >= +0: int32 order == float order
 
         def after_frame():
-            dist.reduce(pipe.vis64, dst=0, op=dist.ReduceOp.MAX)  # per-pixel max of the packed depth|id image -> rank 0
+            oxdist.reduce_visbuffer(pipe.vis64)               # per-pixel max of the packed depth|id image (NVLS all-reduce)
             dist.all_gather_into_tensor(vis_all, vis_view)   # early / late counts of every rank
             dist.all_gather_into_tensor(ids_all, ids_view)   # survivor ids (global), fixed-capacity segments
             gathered["last"] = (ids_all, vis_all)
@@ -428,7 +428,7 @@ def main():
         cnts = vis_all.view(world, 3).cpu().numpy()
         exchange = {"survivor_gather_capacity": int(gcap), "max_survivors_per_rank": int((cnts[:, 1] + cnts[:, 2]).max()),
                     "overflow": bool((cnts[:, 1] + cnts[:, 2]).max() > gcap),
-                    "steps": "id base from a local count-only replay (no exchange); all_reduce(MAX) Hi-Z mip 0; reduce(MAX) vis buffer -> rank 0; allgather(counts); allgather(survivor ids)"}
+                    "steps": "id base from a local count-only replay (no exchange); all_reduce(MAX) Hi-Z mip 0; all_reduce(MAX) vis buffer; allgather(counts); allgather(survivor ids)"}
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
