@@ -339,6 +339,16 @@ def main():
     stages_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
     cnt_late = pipe.counters()
 
+    stages_all = None
+    if multi:
+        keys = sorted(stages_ms)
+        t_st = torch.tensor([stages_ms[k] for k in keys] + [cnt_late["early"] + cnt_late["late"], cnt_late["triangles"]], dtype=torch.float64, device=dev)
+        g_st = torch.empty(world * len(t_st), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(g_st, t_st)
+        g_st = g_st.view(world, -1).cpu().numpy()
+        stages_all = {k: [round(float(g_st[r, i]), 4) for r in range(world)] for i, k in enumerate(keys)}
+        stages_all["survivors"] = [int(g_st[r, len(keys)]) for r in range(world)]
+        stages_all["triangles"] = [int(g_st[r, len(keys) + 1]) for r in range(world)]
     # max over ranks
     if multi:
         t = torch.tensor([ms_per_step], dtype=torch.float64, device=dev)
@@ -439,7 +449,7 @@ def main():
                           "triangles_rasterised": job_tris},
             "stages_ms": stages_ms, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches_per_frame * K), "gpu_launches_per_step": int(launches_per_frame),
-            "cuda_graph": graphs is not None, "wall_s_timed_region": t_wall, "exchange": exchange,
+            "cuda_graph": graphs is not None, "wall_s_timed_region": t_wall, "exchange": exchange, "stages_ms_per_rank": stages_all,
         }
         print(json.dumps(line), flush=True)
     pipe.close()
