@@ -435,9 +435,26 @@ def main():
 
     exchange = None
     if multi:
+        def time_op(fn, n=10):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n * 1e3  # us
+
+        op_us = {"all_reduce_max_visbuffer_%dMB" % (pipe.vis64.numel() * 8 >> 20): time_op(lambda: oxdist.reduce_visbuffer(pipe.vis64)),
+                 "all_reduce_max_hiz_mip0_%dMB" % (mip0_view.numel() * 4 >> 20): time_op(lambda: dist.all_reduce(mip0_view, op=dist.ReduceOp.MAX)),
+                 "all_gather_survivor_ids_%dMB_per_rank" % (gcap * 4 >> 20): time_op(lambda: dist.all_gather_into_tensor(ids_all, ids_view)),
+                 "all_gather_counts": time_op(lambda: dist.all_gather_into_tensor(vis_all, vis_view))}
         cnts = vis_all.view(world, 3).cpu().numpy()
         exchange = {"survivor_gather_capacity": int(gcap), "max_survivors_per_rank": int((cnts[:, 1] + cnts[:, 2]).max()),
-                    "overflow": bool((cnts[:, 1] + cnts[:, 2]).max() > gcap),
+                    "overflow": bool((cnts[:, 1] + cnts[:, 2]).max() > gcap), "op_us_back_to_back": op_us,
                     "steps": "id base from a local count-only replay (no exchange); all_reduce(MAX) Hi-Z mip 0; all_reduce(MAX) vis buffer; allgather(counts); allgather(survivor ids)"}
     if rank == 0:
         line = {
