@@ -281,11 +281,43 @@ def main():
             pipe.use_torch_stream()
             torch.cuda.synchronize()
 
+    # N > 1: the two halves of the frame around the Hi-Z exchange are captured as CUDA graphs; the NCCL collectives are
+    # launched between / after them (capturing the collectives themselves hung in testing)
+    half_graphs = None
+    if multi and not args.no_graph:
+        try:
+            half_graphs = []
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for cam in cams:
+                    pair = []
+                    for part in (pipe.frame_before_exchange, pipe.frame_after_exchange):
+                        g = torch.cuda.CUDAGraph()
+                        with torch.cuda.graph(g, stream=side):
+                            pipe.use_torch_stream()
+                            part(cam)
+                        pair.append(g)
+                    half_graphs.append(pair)
+            torch.cuda.current_stream().wait_stream(side)
+            pipe.use_torch_stream()
+            torch.cuda.synchronize()
+        except Exception as e:
+            sys.stderr.write(f"[bench] half-frame graph capture failed ({e!r}); timing eager launches\n")
+            half_graphs = None
+            pipe.use_torch_stream()
+            torch.cuda.synchronize()
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def step(i, mark=None):
         if graphs is not None and mark is None:
             graphs[i % 2].replay()
+        elif half_graphs is not None and mark is None:
+            half_graphs[i % 2][0].replay()
+            hooks["between_passes"]()
+            half_graphs[i % 2][1].replay()
+            hooks["after_frame"]()
         else:
             pipe.frame(cams[i % 2], mark=mark, **hooks)
 
@@ -466,7 +498,7 @@ def main():
                           "triangles_rasterised": job_tris},
             "stages_ms": stages_ms, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches_per_frame * K), "gpu_launches_per_step": int(launches_per_frame),
-            "cuda_graph": graphs is not None, "wall_s_timed_region": t_wall, "exchange": exchange, "stages_ms_per_rank": stages_all,
+            "cuda_graph": (graphs is not None) or (half_graphs is not None), "wall_s_timed_region": t_wall, "exchange": exchange, "stages_ms_per_rank": stages_all,
         }
         print(json.dumps(line), flush=True)
     pipe.close()

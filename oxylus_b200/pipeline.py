@@ -92,6 +92,27 @@ class VisibilityPipeline:
         if after_frame:
             after_frame()
 
+    # --- the same frame in two halves around the multi-GPU Hi-Z exchange (each half can be a CUDA graph; the NCCL
+    #     collectives stay outside the graphs) ---
+    def frame_before_exchange(self, cam):
+        c, w, h = self.ctx, self.w, self.h
+        v = self.vis64.data_ptr()
+        c.clear_visbuffer(v, w, h)
+        c.clear_hiz()
+        if self.occluder is not None:
+            c.merge_depth(v, self.occluder.data_ptr(), w, h)
+        c.cull_meshes(cam, abi.CULL_TEST_ALL)
+        c.cull_meshlets(cam, abi.CULL_TEST_ALL, True)
+        c.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, v)
+        c.build_hiz_mip0_packed(v, w, h)
+
+    def frame_after_exchange(self, cam):
+        c, w, h = self.ctx, self.w, self.h
+        v = self.vis64.data_ptr()
+        c.build_hiz_from_mip0()
+        c.cull_meshlets(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, True)
+        c.raster_visbuffer(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, v)
+
     def counters(self):
         vis = self.ctx.visibility()
         return dict(total=int(vis["total"][0]), early=int(vis["early"][0]), late=int(vis["late"][0]),
