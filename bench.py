@@ -137,6 +137,34 @@ def cpu_frames(scene, n_frames, n_threads):
     return float(np.mean(times)), last
 
 
+def cpu_frustum_loops(scene, cam, cores):
+    """the reference's CPU primitives looped over the meshlet bounds + draw-list build
+    (engine AABB::is_on_frustum test, and the shader-equivalent cone+frustum), 1 thread and all host threads;
+    plus BASELINE.json configs[0] (10 k bounds, 1 camera, scalar)."""
+    orc = load_oracle()
+    hs = orc.HostScene(scene)
+    mi, vis, _ = orc.cull_meshes(hs, cam, 7)
+    total = int(vis["total"][0])
+    out = {}
+    for name, mode in (("engine_aabb_is_on_frustum", 0), ("shader_equivalent_cone_frustum", 1)):
+        for threads in (1, cores):
+            n = total if threads > 1 else min(total, 200_000)
+            best = 1e9
+            for _ in range(3):
+                t0 = time.perf_counter()
+                surv = orc.cpu_baseline_cull(hs, mi, n, cam, mode, threads)
+                best = min(best, time.perf_counter() - t0)
+            out[f"{name}_{threads}t"] = {"meshlets_per_s": n / best, "meshlets": n, "survivors": int(len(surv))}
+    n = min(total, 10_000)
+    best = 1e9
+    for _ in range(20):
+        t0 = time.perf_counter()
+        orc.cpu_baseline_cull(hs, mi, n, cam, 1, 1)
+        best = min(best, time.perf_counter() - t0)
+    out["configs0_10k_bounds_scalar_1t"] = {"meshlets_per_s": n / best, "meshlets": n}
+    return out
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path = the oracle port (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
@@ -463,7 +491,8 @@ def main():
         cpu_baseline = {"value": scene.max_meshlet_instance_count / sec, "unit": UNIT, "cores": cores, "kind": "port",
                         "sample": f"{args.cpu_frames} full frames of the same {scene.max_meshlet_instance_count}-meshlet scene "
                                   f"(oracle port of the reference shaders, pthreads x{cores}); {sec * 1e3:.0f} ms/frame",
-                        "triangles_per_s": last["triangles"] / sec}
+                        "triangles_per_s": last["triangles"] / sec,
+                        "frustum_cull_draw_list_loops": cpu_frustum_loops(scene, cams[0], cores)}
 
     exchange = None
     if multi:
