@@ -319,6 +319,23 @@ int oxc_merge_depth(OxcContext* ctx, uint64_t* vis_dev, const float* depth_dev, 
 int oxc_cull_meshlets_multiview(OxcContext* ctx, const OxcCullCamera* views, uint32_t n_views, int directional,
                                 void* stream);
 
+/* Terrain patch cull: passes/terrain_cull.slang:19-83 via RendererInstance::cull_terrain
+ * (Passes/Terrain.cpp:159-216).  One thread per patch: AABB from the patch grid + patch_minmax, frustum test against
+ * projection_view itself, Hi-Z occlusion against the context's pyramid, own persistent visibility mask, early/late
+ * semantics identical to the meshlet cull.  draw_cmd is reset to {4, 0, 0, 0} first (Terrain.cpp:168-170);
+ * instance_count counts the emitted patches, visible_patches holds their indices (order unspecified). */
+typedef struct OxcTerrainData { /* scene.slang:634-647, the fields the cull reads */
+  float world_min[2];
+  float world_size[2];
+  uint32_t patch_count[2];
+  float base_height;
+  float height_scale;
+} OxcTerrainData;
+typedef struct OxcDrawIndirectCommand { uint32_t vertex_count, instance_count, first_vertex, first_instance; } OxcDrawIndirectCommand;
+int oxc_cull_terrain(OxcContext* ctx, const OxcTerrainData* terrain, const float* patch_minmax_dev /* float2 per patch, row-major */,
+                     const OxcCullCamera* camera, uint32_t cull_flags, uint32_t* visible_patches_dev,
+                     uint32_t* patch_visibility_mask_dev, OxcDrawIndirectCommand* draw_cmd_dev, void* stream);
+
 int oxc_get_outputs(OxcContext* ctx, OxcOutputs* out);
 
 /* Plumbing for hosts without their own CUDA bindings (the ctypes tests / bench): async copy on `stream`

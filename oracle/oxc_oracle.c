@@ -619,6 +619,44 @@ void orc_resolve_visbuffer(const uint64_t* vis, uint32_t width, uint32_t height,
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * passes/terrain_cull.slang:19-83; TerrainData::patch_corner / decode_height scene.slang:648-660
+ * ---------------------------------------------------------------------------------------------- */
+void orc_cull_terrain(const OxcTerrainData* t, const float* patch_minmax, const OxcCullCamera* cam, uint32_t flags,
+                      const OrcHiz* hiz, uint32_t* visible_patches, uint32_t* mask, OxcDrawIndirectCommand* draw_cmd) {
+  draw_cmd->vertex_count = 4; draw_cmd->instance_count = 0; draw_cmd->first_vertex = 0; draw_cmd->first_instance = 0; /* Terrain.cpp:168-170 */
+  const uint32_t patch_total = t->patch_count[0] * t->patch_count[1]; /* :21 */
+  for (uint32_t patch_index = 0; patch_index < patch_total; patch_index++) {
+    const uint32_t px = patch_index % t->patch_count[0], py = patch_index / t->patch_count[0]; /* :26 */
+    /* patch_corner: world_min + (f32x2(patch + corner) / f32x2(patch_count)) * world_size */
+    const float g0x = (float)(px + 0) / (float)t->patch_count[0], g0y = (float)(py + 0) / (float)t->patch_count[1];
+    const float g1x = (float)(px + 1) / (float)t->patch_count[0], g1y = (float)(py + 1) / (float)t->patch_count[1];
+    const float cminx = t->world_min[0] + g0x * t->world_size[0], cminy = t->world_min[1] + g0y * t->world_size[1];
+    const float cmaxx = t->world_min[0] + g1x * t->world_size[0], cmaxy = t->world_min[1] + g1y * t->world_size[1];
+    const float bx = patch_minmax[2 * patch_index + 0], by = patch_minmax[2 * patch_index + 1]; /* :30 */
+    Vec3_f32 c, e;
+    c.x = (cminx + cmaxx) * 0.5f;
+    c.y = t->base_height + ((bx + by) * 0.5f) * t->height_scale; /* decode_height */
+    c.z = (cminy + cmaxy) * 0.5f;
+    e.x = cmaxx - cminx;
+    e.y = rmax_f32(t->height_scale * (by - bx), 1e-3f);
+    e.z = cmaxy - cminy;
+    const uint32_t mask_word = patch_index / 32u, mask_bit = 1u << (patch_index % 32u);
+    const int was_visible = (mask[mask_word] & mask_bit) != 0u; /* :45 */
+    int visible = (flags & OXC_CULL_LATE_PASS) ? 1 : was_visible; /* :47 */
+    if (flags & OXC_CULL_TEST_FRUSTUM) visible = visible && test_frustum_f32(cam->projection_view, c, e); /* :49-51 */
+    if ((flags & (OXC_CULL_TEST_OCCLUSION | OXC_CULL_LATE_PASS)) != 0 && visible) { /* :53-57 */
+      ScreenAabb_f32 sa;
+      if (project_aabb_f32(cam->projection_view, cam->near_clip, c, e, &sa)) visible = !test_occlusion_f32(&sa, hiz);
+    }
+    const int emit = visible && (!(flags & OXC_CULL_LATE_PASS) || !was_visible); /* :59 */
+    if (flags & (OXC_CULL_TEST_OCCLUSION | OXC_CULL_LATE_PASS)) { /* :61-67 */
+      if (visible) mask[mask_word] |= mask_bit; else mask[mask_word] &= ~mask_bit;
+    }
+    if (emit) visible_patches[draw_cmd->instance_count++] = patch_index; /* :70-82 */
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * CPU baseline
  * ---------------------------------------------------------------------------------------------- */
 typedef struct BaselineJob {

@@ -115,6 +115,10 @@ void orc_raster_visbuffer(const OrcScene* scene, const OxcMeshletInstance* meshl
                           uint64_t* vis, uint64_t* triangles_rasterised);
 void orc_resolve_visbuffer(const uint64_t* vis, uint32_t width, uint32_t height, uint32_t* vis32, float* depth);
 
+/* passes/terrain_cull.slang:19-83 */
+void orc_cull_terrain(const OxcTerrainData* terrain, const float* patch_minmax, const OxcCullCamera* cam, uint32_t flags,
+                      const OrcHiz* hiz, uint32_t* visible_patches, uint32_t* mask, OxcDrawIndirectCommand* draw_cmd);
+
 /* ---- CPU baseline: the reference's CPU primitives over meshlet bounds ----
  * mode 0: AABB::is_on_frustum (BoundingVolume.cpp:72-88) with planes from math::calc_frustum_planes
  *         (OxMath.hpp:54-80) on world-space AABBs of dequantised bounds

@@ -210,6 +210,15 @@ def frame(hs, cam, width, height, mask, occluder_depth=None, first=0, count=0xFF
                 mask_after_early=mask_after_early, ntri_early=ntri_e, ntri_late=ntri_l, cull_meshlets_cmd=cmd, id_base=id_base)
 
 
+def cull_terrain(terrain, patch_minmax, cam, flags, hiz: Hiz, mask):
+    n = int(terrain["patch_count"][0][0]) * int(terrain["patch_count"][0][1])
+    visible = np.zeros(max(1, n), dtype=np.uint32)
+    cmd = np.zeros(1, dtype=abi.DRAW_INDIRECT_DT)
+    pm = np.ascontiguousarray(patch_minmax, dtype=np.float32)
+    lib().orc_cull_terrain(_p(terrain), _p(pm), _p(cam), C.c_uint32(flags), hiz.ref, _p(visible), _p(mask), _p(cmd))
+    return visible[: int(cmd["instance_count"][0])], cmd
+
+
 def cpu_baseline_cull(hs, mi, total, cam, mode, n_threads):
     out = np.zeros(max(1, total), dtype=np.uint32)
     n = lib().orc_cpu_baseline_cull(hs.ref, _p(mi), C.c_uint32(total), _p(cam), C.c_int(mode), C.c_int(n_threads), _p(out))

@@ -85,6 +85,10 @@ DRAW_CMD_DT = np.dtype(
     ]
 )
 
+TERRAIN_DT = np.dtype([("world_min", "<f4", (2,)), ("world_size", "<f4", (2,)), ("patch_count", "<u4", (2,)),
+                       ("base_height", "<f4"), ("height_scale", "<f4")])
+DRAW_INDIRECT_DT = np.dtype([("vertex_count", "<u4"), ("instance_count", "<u4"), ("first_vertex", "<u4"), ("first_instance", "<u4")])
+assert TERRAIN_DT.itemsize == 32 and DRAW_INDIRECT_DT.itemsize == 16
 assert TRANSFORM_DT.itemsize == 64
 assert MESHLET_BOUNDS_DT.itemsize == 16
 assert VISIBILITY_DT.itemsize == 12

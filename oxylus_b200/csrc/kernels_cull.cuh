@@ -667,6 +667,84 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets_multiview(const 
   if (threadIdx.x < OXC_MAX_VIEWS && cnt_s[threadIdx.x]) atomicAdd(&p.view_counts[threadIdx.x], cnt_s[threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Terrain patch cull — passes/terrain_cull.slang:19-83 (canonical arithmetic throughout: patch counts are small)
+// ------------------------------------------------------------------------------------------------
+struct TerrainParams {
+  OxcTerrainData terrain;
+  const float2* patch_minmax;
+  uint32_t* visible_patches;
+  uint32_t* mask;
+  OxcDrawIndirectCommand* draw_cmd;
+  HizDesc hiz;
+  OxcCullCamera cam;
+  uint32_t flags;
+};
+
+__global__ void __launch_bounds__(256) k_cull_terrain(const __grid_constant__ TerrainParams p) {
+  __shared__ uint32_t hiz_off[OXC_HIZ_MAX_LEVELS];
+  __shared__ float4 planes_s[6];
+  __shared__ float4 rows_s[4];
+  __shared__ uint32_t warp_cnt[8];
+  __shared__ uint32_t base_s;
+  if (threadIdx.x < OXC_HIZ_MAX_LEVELS) hiz_off[threadIdx.x] = p.hiz.level_offset[threadIdx.x];
+  if (threadIdx.x == 0) { // planes of projection_view itself (terrain_cull.slang:50 passes camera.projection_view as mvp)
+    float4 rows[4], planes[6];
+    const float* m = p.cam.projection_view;
+    for (int i = 0; i < 4; i++) rows[i] = make_float4(m[0 * 4 + i], m[1 * 4 + i], m[2 * 4 + i], m[3 * 4 + i]);
+    frustum_planes(rows, planes);
+    for (int i = 0; i < 6; i++) planes_s[i] = planes[i];
+    for (int i = 0; i < 4; i++) rows_s[i] = rows[i];
+  }
+  __syncthreads();
+  const OxcTerrainData& t = p.terrain;
+  const uint32_t patch_total = t.patch_count[0] * t.patch_count[1];
+  const uint32_t patch_index = blockIdx.x * 256 + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  bool emit = false;
+  if (patch_index < patch_total) {
+    const uint32_t px = patch_index % t.patch_count[0], py = patch_index / t.patch_count[0];
+    const float pcx = (float)t.patch_count[0], pcy = (float)t.patch_count[1];
+    const float cminx = fa(t.world_min[0], fm(fd((float)px, pcx), t.world_size[0]));
+    const float cminy = fa(t.world_min[1], fm(fd((float)py, pcy), t.world_size[1]));
+    const float cmaxx = fa(t.world_min[0], fm(fd((float)(px + 1), pcx), t.world_size[0]));
+    const float cmaxy = fa(t.world_min[1], fm(fd((float)(py + 1), pcy), t.world_size[1]));
+    const float2 b = __ldg(&p.patch_minmax[patch_index]);
+    const float cx = fm(fa(cminx, cmaxx), 0.5f);
+    const float cy = fa(t.base_height, fm(fm(fa(b.x, b.y), 0.5f), t.height_scale));
+    const float cz = fm(fa(cminy, cmaxy), 0.5f);
+    const float ex = fs(cmaxx, cminx), ey = omax(fm(t.height_scale, fs(b.y, b.x)), 1e-3f), ez = fs(cmaxy, cminy);
+    const uint32_t word = patch_index >> 5, bit = 1u << (patch_index & 31);
+    const bool was_visible = (p.mask[word] & bit) != 0u;
+    bool visible = (p.flags & OXC_CULL_LATE_PASS) ? true : was_visible;
+    if (p.flags & OXC_CULL_TEST_FRUSTUM) {
+      float4 pl[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) pl[i] = planes_s[i];
+      visible = visible && test_frustum_rows(pl, cx, cy, cz, ex, ey, ez);
+    }
+    if ((p.flags & (OXC_CULL_TEST_OCCLUSION | OXC_CULL_LATE_PASS)) != 0 && visible) {
+      ScreenAabb sa;
+      if (project_aabb(rows_s[0], rows_s[1], rows_s[2], rows_s[3], p.cam.near_clip, cx, cy, cz, ex, ey, ez, sa))
+        visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, hiz_off);
+    }
+    emit = visible && (!(p.flags & OXC_CULL_LATE_PASS) || !was_visible);
+    if ((p.flags & (OXC_CULL_TEST_OCCLUSION | OXC_CULL_LATE_PASS)) && visible != was_visible) atomicXor(&p.mask[word], bit);
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, emit);
+  if (lane == 0) warp_cnt[warp] = __popc(bal);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t s = 0;
+    for (int w = 0; w < 8; w++) { const uint32_t c = warp_cnt[w]; warp_cnt[w] = s; s += c; }
+    base_s = s ? atomicAdd(&p.draw_cmd->instance_count, s) : 0u; // :76
+  }
+  __syncthreads();
+  if (emit) p.visible_patches[base_s + warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = patch_index; // :81
+}
+
+__global__ void k_reset_terrain_cmd(OxcDrawIndirectCommand* c) { c->vertex_count = 4; c->instance_count = 0; c->first_vertex = 0; c->first_instance = 0; }
+
 // per view planes for the multi-view cull: planes of mul(view.projection_view, world)
 __global__ void k_prepare_view_planes(const OxcMeshInstance* __restrict__ mesh_instances,
                                       const OxcTransformWorld* __restrict__ transforms, const OxcCullCamera* __restrict__ views,

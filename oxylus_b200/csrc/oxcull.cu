@@ -642,6 +642,21 @@ int oxc_device_free(OxcContext* c, void* p) {
   return OXC_OK;
 }
 
+int oxc_cull_terrain(OxcContext* c, const OxcTerrainData* terrain, const float* patch_minmax_dev, const OxcCullCamera* cam,
+                     uint32_t flags, uint32_t* visible_patches_dev, uint32_t* mask_dev, OxcDrawIndirectCommand* draw_cmd_dev, void* stream) {
+  if (!c || !terrain || !patch_minmax_dev || !cam || !visible_patches_dev || !mask_dev || !draw_cmd_dev) return fail(OXC_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  TerrainParams p{};
+  p.terrain = *terrain; p.patch_minmax = reinterpret_cast<const float2*>(patch_minmax_dev); p.visible_patches = visible_patches_dev;
+  p.mask = mask_dev; p.draw_cmd = draw_cmd_dev; p.hiz = c->hiz; p.cam = *cam; p.flags = flags;
+  k_reset_terrain_cmd<<<1, 1, 0, s>>>(draw_cmd_dev); // Terrain.cpp:168-170
+  LAUNCHED();
+  const uint32_t n = terrain->patch_count[0] * terrain->patch_count[1];
+  if (n) { k_cull_terrain<<<(n + 255) / 256, 256, 0, s>>>(p); LAUNCHED(); }
+  return OXC_OK;
+}
+
 int oxc_get_outputs(OxcContext* c, OxcOutputs* o) {
   if (!c || !o) return fail(OXC_E_INVALID, "null argument");
   memset(o, 0, sizeof *o);

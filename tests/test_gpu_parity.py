@@ -371,3 +371,42 @@ def test_renderer_pipelined_submit_wait(capi, orc):
     with pytest.raises(capi.OxcError):
         r.wait(0)  # nothing in flight
     r.close()
+
+
+def test_terrain_cull_parity(capi, orc):
+    """terrain_cull.slang equivalent: early / late passes against a real Hi-Z, own mask, bit-exact."""
+    rng = np.random.default_rng(21)
+    w, h = 1280, 720
+    hw, hh = abi.hiz_extent(w, h)
+    terrain = np.zeros(1, dtype=abi.TERRAIN_DT)
+    terrain["world_min"][0] = (-300.0, -500.0)
+    terrain["world_size"][0] = (600.0, 600.0)
+    terrain["patch_count"][0] = (96, 80)
+    terrain["base_height"] = -30.0
+    terrain["height_scale"] = 40.0
+    n = 96 * 80
+    lo = rng.random(n, dtype=np.float32) * 0.6
+    minmax = np.stack([lo, lo + rng.random(n, dtype=np.float32) * 0.4], axis=1).astype(np.float32)
+    minmax[::97, 1] = minmax[::97, 0]  # flat patches -> the 1e-3 floor of the extent
+    depth = (rng.random((h, w), dtype=np.float32) * 0.02).astype(np.float32)
+    depth[200:500, 300:900] = 0.01  # a large near occluder region
+    ref_hiz = orc.build_hiz(depth, orc.Hiz(hw, hh))
+    ctx = capi.Context(0, 1, 1, hw, hh)
+    d_dev = ctx.alloc(w * h * 4); ctx.upload(d_dev, depth); ctx.build_hiz(d_dev, w, h)
+    mm_dev = ctx.alloc(minmax.nbytes); ctx.upload(mm_dev, minmax)
+    vis_dev, mask_dev, cmd_dev = ctx.alloc(n * 4), ctx.alloc(((n + 31) // 32) * 4), ctx.alloc(16)
+    mask_ref = rng.integers(0, 2**32, size=(n + 31) // 32, dtype=np.uint64).astype(np.uint32)
+    ctx.upload(mask_dev, mask_ref)
+    cam = synth.make_camera(w, h, 0, yaw_deg=8.0, eye=(0.0, 5.0, 60.0))
+    for flags in (abi.CULL_TEST_FRUSTUM | abi.CULL_TEST_OCCLUSION, abi.CULL_TEST_FRUSTUM | abi.CULL_TEST_OCCLUSION | abi.CULL_LATE_PASS,
+                  abi.CULL_TEST_FRUSTUM):
+        ref_vis, ref_cmd = orc.cull_terrain(terrain, minmax, cam, flags, ref_hiz, mask_ref)
+        ctx.cull_terrain(terrain, mm_dev, cam, flags, vis_dev, mask_dev, cmd_dev)
+        cmd = ctx.download(cmd_dev, abi.DRAW_INDIRECT_DT, 1)
+        assert (int(cmd["vertex_count"][0]), int(cmd["instance_count"][0])) == (4, int(ref_cmd["instance_count"][0]))
+        np.testing.assert_array_equal(np.sort(ctx.download(vis_dev, np.uint32, len(ref_vis))), np.sort(ref_vis))
+        np.testing.assert_array_equal(ctx.download(mask_dev, np.uint32, len(mask_ref)), mask_ref)
+        assert 0 < len(ref_vis) < n
+    for p in (d_dev, mm_dev, vis_dev, mask_dev, cmd_dev):
+        ctx.free(p)
+    ctx.close()

@@ -217,3 +217,30 @@ def test_raster_watertight_and_depth(orc):
     assert set(np.unique(v32[covered] & 0xFF)) == {0, 1} and np.all((v32[covered] >> 8) == 0)
     np.testing.assert_allclose(d[covered], 0.5, rtol=0, atol=1e-6)
     assert np.all(d[~covered] == 0.0)
+
+
+def test_terrain_cull_hand_case(orc):
+    """terrain_cull.slang:19-83 with projection_view = I: 2x1 patches over x in [-2,2], z in [0,1]; the left patch is
+    outside the x in [-1,1] frustum slab only if it does not touch it (it spans [-2,0] -> straddles -> visible)."""
+    t = np.zeros(1, dtype=abi.TERRAIN_DT)
+    t["world_min"][0] = (-2.0, 0.25)
+    t["world_size"][0] = (4.0, 0.5)
+    t["patch_count"][0] = (2, 1)
+    t["base_height"] = 0.0
+    t["height_scale"] = 1.0
+    minmax = np.array([[0.0, 0.5], [3.0, 3.5]], dtype=np.float32)  # second patch: y in [3, 3.5] -> above the y<=1 slab
+    cam = np.zeros(1, dtype=abi.CULL_CAMERA_DT)
+    cam["projection_view"][0] = np.eye(4, dtype=np.float32).reshape(16)
+    cam["near_clip"] = 0.01
+    hz = orc.Hiz(8, 8)  # all-zero pyramid: nothing occludes
+    mask = np.zeros(1, dtype=np.uint32)
+    flags = abi.CULL_TEST_FRUSTUM | abi.CULL_TEST_OCCLUSION | abi.CULL_LATE_PASS
+    vis, cmd = orc.cull_terrain(t, minmax, cam, flags, hz, mask)
+    assert list(vis) == [0] and int(cmd["instance_count"][0]) == 1 and int(cmd["vertex_count"][0]) == 4
+    assert int(mask[0]) == 0b01
+    # early pass: emits only what was visible; the mask bit of patch 0 stays, nothing new
+    vis, cmd = orc.cull_terrain(t, minmax, cam, abi.CULL_TEST_FRUSTUM | abi.CULL_TEST_OCCLUSION, hz, mask)
+    assert list(vis) == [0] and int(mask[0]) == 0b01
+    # late pass again: patch 0 was visible -> not re-emitted
+    vis, cmd = orc.cull_terrain(t, minmax, cam, flags, hz, mask)
+    assert len(vis) == 0 and int(mask[0]) == 0b01
