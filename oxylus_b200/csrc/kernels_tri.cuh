@@ -324,12 +324,14 @@ __global__ void __launch_bounds__(TRI_THREADS, 3) k_raster_visbuffer(const __gri
   uint32_t kept = 0;
   // warps pull batches of RASTER_BATCH consecutive survivors from a global work counter (dynamic balance);
   // lanes 0..RASTER_BATCH-1 each chase one meshlet header, so RASTER_BATCH pointer chases are in flight together
+  // batch size adapts to the survivor count so short lists (late pass) still spread over every warp
+  const uint32_t batch = min((uint32_t)RASTER_BATCH, max(1u, count / (gridDim.x * TRI_WARPS * 3u)));
   for (;;) {
     uint32_t g0 = 0;
-    if (lane == 0) g0 = atomicAdd(p.work_counter, (uint32_t)RASTER_BATCH);
+    if (lane == 0) g0 = atomicAdd(p.work_counter, batch);
     g0 = __shfl_sync(0xffffffffu, g0, 0);
     if (g0 >= count) break;
-    const uint32_t nb = min((uint32_t)RASTER_BATCH, count - g0);
+    const uint32_t nb = min(batch, count - g0);
     MeshletHeader mine;
     mine.gid = 0; mine.inst = 0; mine.vertex_offset = 0; mine.vertex_count = 0; mine.tri_offset = 0; mine.tri_count = 0;
     mine.micro = nullptr; mine.vidx = nullptr; mine.pos = nullptr;
