@@ -7,7 +7,13 @@ namespace oxc {
 
 constexpr int CULL_MESHES_THREADS = 256;
 constexpr int CULL_THREADS = 256;
-constexpr int CULL_ITEMS = 2;                          // meshlet instances per thread per tile
+#ifndef OXC_CULL_ITEMS
+#define OXC_CULL_ITEMS 2
+#endif
+#ifndef OXC_CULL_MIN_BLOCKS
+#define OXC_CULL_MIN_BLOCKS 4
+#endif
+constexpr int CULL_ITEMS = OXC_CULL_ITEMS;               // meshlet instances per thread per tile
 constexpr int CULL_TILE = CULL_THREADS * CULL_ITEMS;   // 512 per CTA iteration -> one atomic per 512
 
 struct MeshesParams {
@@ -392,7 +398,7 @@ struct __align__(16) OccEntry {
 };
 
 template <bool HIZ, bool OCC, bool LATE, bool ZERO>
-__global__ void __launch_bounds__(CULL_THREADS, 4) k_cull_meshlets(const __grid_constant__ CullParams p) {
+__global__ void __launch_bounds__(CULL_THREADS, OXC_CULL_MIN_BLOCKS) k_cull_meshlets(const __grid_constant__ CullParams p) {
   __shared__ uint32_t hiz_off[OXC_HIZ_MAX_LEVELS];
   __shared__ uint32_t warp_cnt[CULL_THREADS / 32];
   __shared__ uint32_t tile_base_s;

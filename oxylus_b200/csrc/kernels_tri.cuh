@@ -267,8 +267,17 @@ OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* v
   }
 }
 
-constexpr int RASTER_BATCH = 8;       // meshlets per work grab
-constexpr int RASTER_BIG_PIXELS = 32; // bbox area above which the whole warp rasterises the triangle together
+#ifndef OXC_RASTER_MIN_BLOCKS
+#define OXC_RASTER_MIN_BLOCKS 3
+#endif
+#ifndef OXC_RASTER_BIG_PIXELS
+#define OXC_RASTER_BIG_PIXELS 32
+#endif
+#ifndef OXC_RASTER_BATCH
+#define OXC_RASTER_BATCH 8
+#endif
+constexpr int RASTER_BATCH = OXC_RASTER_BATCH;       // meshlets per work grab
+constexpr int RASTER_BIG_PIXELS = OXC_RASTER_BIG_PIXELS; // bbox area above which the whole warp rasterises the triangle together
 
 // Header of one surviving meshlet, fetched by ONE lane (32 headers in flight per warp): the 4-level pointer
 // chase visible_indices -> meshlet_instances -> InstGeom -> Meshlet is paid once per 32 meshlets per warp.
@@ -311,7 +320,7 @@ OXC_DI MeshletHeader bcast_header(const MeshletHeader& h, int src) {
   return o;
 }
 
-__global__ void __launch_bounds__(TRI_THREADS, 3) k_raster_visbuffer(const __grid_constant__ TriParams p) {
+__global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_visbuffer(const __grid_constant__ TriParams p) {
   __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   __shared__ ScreenVert scr_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
