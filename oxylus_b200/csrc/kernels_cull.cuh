@@ -11,7 +11,7 @@ constexpr int CULL_THREADS = 256;
 #define OXC_CULL_ITEMS 2
 #endif
 #ifndef OXC_CULL_MIN_BLOCKS
-#define OXC_CULL_MIN_BLOCKS 4
+#define OXC_CULL_MIN_BLOCKS 5
 #endif
 constexpr int CULL_ITEMS = OXC_CULL_ITEMS;               // meshlet instances per thread per tile
 constexpr int CULL_TILE = CULL_THREADS * CULL_ITEMS;   // 512 per CTA iteration -> one atomic per 512

@@ -268,7 +268,7 @@ OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* v
 }
 
 #ifndef OXC_RASTER_MIN_BLOCKS
-#define OXC_RASTER_MIN_BLOCKS 3
+#define OXC_RASTER_MIN_BLOCKS 4
 #endif
 #ifndef OXC_RASTER_BIG_PIXELS
 #define OXC_RASTER_BIG_PIXELS 32
