@@ -410,3 +410,108 @@ def test_terrain_cull_parity(capi, orc):
     for p in (d_dev, mm_dev, vis_dev, mask_dev, cmd_dev):
         ctx.free(p)
     ctx.close()
+
+
+def test_filtered_predicates_adversarial_boundaries(capi, orc):
+    """Boxes steered (bisection on the f32 instance translation, evaluated with the oracle's own mvp + projection) so
+    that a projected texel coordinate lands within ~1e-5 of an INTEGER Hi-Z texel boundary, and Hi-Z depths set within
+    an ulp of the box's max.z: the filtered fast path must classify these as ambiguous and fall back to the canonical
+    path -> decisions identical to the oracle."""
+    import ctypes as C
+
+    from tests.helpers_scene import boxes_scene
+
+    w, h = 1920, 1080
+    hw, hh = abi.hiz_extent(w, h)
+    cam0 = synth.make_camera(w, h, 0)
+    pv = np.ascontiguousarray(cam0["projection_view"][0], dtype=np.float32)
+    rng = np.random.default_rng(99)
+    n = 4000
+    half = lambda a: np.asarray(a, np.float32).astype(np.float16).astype(np.float32)  # noqa: E731
+    centers = half(np.stack([rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(-2, 2, n)], axis=1))
+    extents = half(rng.uniform(0.2, 3.0, size=(n, 3)))
+    trans = np.stack([rng.uniform(-40, 40, n), rng.uniform(-20, 20, n), -rng.uniform(20, 200, n)], axis=1).astype(np.float32)
+    lib = orc.lib()
+
+    def proj(i, t):
+        wm = np.eye(4, dtype=np.float32)
+        wm[3, :3] = t
+        wflat = np.ascontiguousarray(wm.reshape(16))
+        mvp = np.zeros(16, dtype=np.float32)
+        lib.orc_mat4_mul(C.c_void_p(pv.ctypes.data), C.c_void_p(wflat.ctypes.data), C.c_void_p(mvp.ctypes.data))
+        out = np.zeros(6, dtype=np.float32)
+        cc, ee = np.ascontiguousarray(centers[i]), np.ascontiguousarray(extents[i])
+        ok = lib.orc_project_aabb(C.c_void_p(mvp.ctypes.data), C.c_float(0.1), C.c_void_p(cc.ctypes.data),
+                                  C.c_void_p(ee.ctypes.data), C.c_void_p(out.ctypes.data))
+        return ok, out
+
+    steered = 0
+    for i in range(n):
+        which = i % 4  # 0: min x, 1: max x, 2: min y, 3: max y
+        col, size, axis = ((0, hw, 0), (3, hw, 0), (1, hh, 1), (4, hh, 1))[which]
+        ok, o = proj(i, trans[i])
+        if not ok:
+            continue
+        target = float(np.round(o[col] * size))
+        if target < 2 or target > size - 3:
+            continue
+        t = trans[i].copy()
+        lo, hi = np.float32(t[axis] - 1.0), np.float32(t[axis] + 1.0)
+        t[axis] = lo; okl, ol = proj(i, t)
+        t[axis] = hi; okh, oh = proj(i, t)
+        if not (okl and okh):
+            continue
+        inc = oh[col] > ol[col]
+        if not (min(ol[col], oh[col]) * size < target < max(ol[col], oh[col]) * size):
+            continue
+        for _ in range(60):
+            mid = np.float32((np.float64(lo) + np.float64(hi)) / 2)
+            if mid == lo or mid == hi:
+                break
+            t[axis] = mid
+            _, om = proj(i, t)
+            if (om[col] * size < target) == inc:
+                lo = mid
+            else:
+                hi = mid
+        trans[i, axis] = lo if i % 8 < 4 else hi
+        steered += 1
+    assert steered > n // 2
+    sc, cdec, edec = boxes_scene(centers, extents, w, h, translations=trans)
+    cam = synth.make_camera(w, h, sc.mesh_instance_count)
+    hs = orc.HostScene(sc)
+    # how close did we get?  (diagnostic: most steered coordinates are within 1e-4 texel of an integer)
+    close = 0
+    for i in range(0, n, 7):
+        ok, o = proj(i, trans[i])
+        col, size, _ = ((0, hw, 0), (3, hw, 0), (1, hh, 1), (4, hh, 1))[i % 4]
+        if ok and abs(o[col] * size - np.round(o[col] * size)) < 1e-3:
+            close += 1
+    assert close > 50
+    # Hi-Z: depth around every third box set within an ulp of (its max.z + 1e-7) so the final compare is tight too
+    depth = np.zeros((h, w), dtype=np.float32)
+    for i in range(0, n, 3):
+        ok, o = proj(i, trans[i])
+        if ok:
+            x0, x1 = int(max(0, o[0] * w - 8)), int(min(w, o[3] * w + 8))
+            y0, y1 = int(max(0, o[1] * h - 8)), int(min(h, o[4] * h + 8))
+            z = np.float32(o[5]) + np.float32(1e-7)
+            z = np.nextafter(z, np.float32(2.0 if i % 2 else -1.0))
+            depth[y0:y1, x0:x1] = np.maximum(depth[y0:y1, x0:x1], z)
+    ref_hiz = orc.build_hiz(depth, orc.Hiz(hw, hh))
+    ctx = make_ctx(capi, sc)
+    d_dev = ctx.alloc(w * h * 4)
+    ctx.upload(d_dev, depth)
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    mask_ref = np.zeros(ctx.out.visibility_mask_words, dtype=np.uint32)
+    flags = abi.CULL_TEST_ALL | abi.CULL_LATE_PASS
+    ref_vis, _ = orc.cull_meshlets_hiz(hs, mi, vis, cam, flags, ref_hiz, mask_ref)
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    ctx.build_hiz(d_dev, w, h)
+    ctx.cull_meshlets(cam, flags, True)
+    nl = int(vis["late"][0])
+    assert int(ctx.visibility()["late"][0]) == nl and 0 < nl < int(vis["total"][0])
+    np.testing.assert_array_equal(np.sort(ctx.visible_indices(nl)), np.sort(ref_vis[:nl]))
+    np.testing.assert_array_equal(ctx.mask(), mask_ref)
+    ctx.free(d_dev)
+    ctx.close()
