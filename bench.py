@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels directly instead of replaying a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: run the trailing exchange on the main stream (no overlap with the next frame)")
     ap.add_argument("--cpu-frames", type=int, default=2)
     return ap.parse_args()
 
@@ -318,7 +319,8 @@ def main():
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                for cam in cams:
+                for b, cam in enumerate(cams):
+                    pipe.select_buffer(b)  # camera index == buffer index: both alternate every step
                     pair = []
                     for part in (pipe.frame_before_exchange, pipe.frame_after_exchange):
                         g = torch.cuda.CUDAGraph()
@@ -329,25 +331,74 @@ def main():
                     half_graphs.append(pair)
             torch.cuda.current_stream().wait_stream(side)
             pipe.use_torch_stream()
+            pipe.select_buffer(0)
             torch.cuda.synchronize()
         except Exception as e:
             sys.stderr.write(f"[bench] half-frame graph capture failed ({e!r}); timing eager launches\n")
             half_graphs = None
             pipe.use_torch_stream()
+            pipe.select_buffer(0)
             torch.cuda.synchronize()
 
+    # N > 1: trailing exchange (vis-buffer max-reduce, survivor allgather) on a side stream with its own communicator and
+    # double-buffered vis / survivor staging, so it overlaps the next frame; buffer b is reused two frames later, after
+    # its exchange has completed (event wait on the main stream)
+    overlap = None
+    if multi and not args.no_overlap:
+        overlap = dict(pg=dist.new_group(), cs=torch.cuda.Stream(),
+                       ids_stage=[torch.zeros(gcap, dtype=torch.int32, device=dev) for _ in range(2)],
+                       cnt_stage=[torch.zeros(3, dtype=torch.int32, device=dev) for _ in range(2)],
+                       ids_all=[torch.zeros(world * gcap, dtype=torch.int32, device=dev) for _ in range(2)],
+                       cnt_all=[torch.zeros(world * 3, dtype=torch.int32, device=dev) for _ in range(2)],
+                       frame_done=[torch.cuda.Event() for _ in range(2)], tail_done=[torch.cuda.Event() for _ in range(2)],
+                       pending=[False, False])
+
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_overlapped(i):
+        b = i & 1
+        o = overlap
+        main = torch.cuda.current_stream()
+        if o["pending"][b]:
+            main.wait_event(o["tail_done"][b])  # the exchange that last used buffer b (two frames ago) has finished
+        pipe.select_buffer(b)
+        if half_graphs is not None:
+            half_graphs[b][0].replay()
+            hooks["between_passes"]()
+            half_graphs[b][1].replay()
+        else:
+            pipe.frame(cams[b], between_passes=hooks["between_passes"])
+        o["ids_stage"][b].copy_(ids_view)   # the context's survivor list / counters are overwritten by the next frame
+        o["cnt_stage"][b].copy_(vis_view)
+        o["frame_done"][b].record(main)
+        o["cs"].wait_event(o["frame_done"][b])
+        with torch.cuda.stream(o["cs"]):
+            dist.all_reduce(pipe.vis64_bufs[b], op=dist.ReduceOp.MAX, group=o["pg"])
+            dist.all_gather_into_tensor(o["cnt_all"][b], o["cnt_stage"][b], group=o["pg"])
+            dist.all_gather_into_tensor(o["ids_all"][b], o["ids_stage"][b], group=o["pg"])
+            o["tail_done"][b].record(o["cs"])
+        o["pending"][b] = True
 
     def step(i, mark=None):
         if graphs is not None and mark is None:
             graphs[i % 2].replay()
+        elif overlap is not None and mark is None:
+            step_overlapped(i)
         elif half_graphs is not None and mark is None:
+            pipe.select_buffer(i & 1)
             half_graphs[i % 2][0].replay()
             hooks["between_passes"]()
             half_graphs[i % 2][1].replay()
             hooks["after_frame"]()
         else:
+            pipe.select_buffer(0)
             pipe.frame(cams[i % 2], mark=mark, **hooks)
+
+    if overlap is not None:  # warm the second communicator / side stream outside the timed region
+        for i in range(4):
+            step_overlapped(i)
+        torch.cuda.current_stream().wait_stream(overlap["cs"])
+        torch.cuda.synchronize()
 
     # ---------------- timed region: exactly K steps ----------------
     launches0 = capi.kernel_launch_count()
@@ -358,6 +409,8 @@ def main():
         flush.fill_(i & 0xFF)  # L2 flush, outside the per-step event pair
         ev[i][0].record()
         step(i)
+        if overlap is not None and i == K - 1:
+            torch.cuda.current_stream().wait_stream(overlap["cs"])  # the last steps' exchanges are inside the timed region
         ev[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
@@ -527,7 +580,7 @@ def main():
                           "triangles_rasterised": job_tris},
             "stages_ms": stages_ms, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches_per_frame * K), "gpu_launches_per_step": int(launches_per_frame),
-            "cuda_graph": (graphs is not None) or (half_graphs is not None), "wall_s_timed_region": t_wall, "exchange": exchange, "stages_ms_per_rank": stages_all,
+            "cuda_graph": (graphs is not None) or (half_graphs is not None), "exchange_overlapped": overlap is not None, "wall_s_timed_region": t_wall, "exchange": exchange, "stages_ms_per_rank": stages_all,
         }
         print(json.dumps(line), flush=True)
     pipe.close()

@@ -35,7 +35,10 @@ class VisibilityPipeline:
                                 alloc_reordered_indices=alloc_reordered_indices, stream=0)
         self.ctx.set_scene(scene)
         self.w, self.h = scene.width, scene.height
-        self.vis64 = torch.empty((self.h, self.w), dtype=torch.int64, device=self.device)
+        # two packed vis buffers: multi-GPU runs alternate them so the trailing exchange of frame i (side stream) can
+        # overlap frame i+1; single-GPU code only ever uses buffer 0
+        self.vis64_bufs = [torch.empty((self.h, self.w), dtype=torch.int64, device=self.device) for _ in range(2)]
+        self.vis64 = self.vis64_bufs[0]
         self.occluder = None
         if scene.occluder_depth is not None:
             self.occluder = torch.from_numpy(np.ascontiguousarray(scene.occluder_depth)).to(self.device)
@@ -46,6 +49,9 @@ class VisibilityPipeline:
             else:
                 self.ctx.set_shard(shard[0], shard[1], self.id_base.data_ptr())
         self.use_torch_stream()
+
+    def select_buffer(self, b):
+        self.vis64 = self.vis64_bufs[b & 1]
 
     def use_torch_stream(self):
         self.ctx.stream = torch.cuda.current_stream(self.device).cuda_stream
