@@ -547,6 +547,25 @@ def main():
                         "triangles_per_s": last["triangles"] / sec,
                         "frustum_cull_draw_list_loops": cpu_frustum_loops(scene, cams[0], cores)}
 
+    overlap_check = None
+    if overlap is not None:
+        # the overlapped steps must deliver what the serial exchange delivers: same per-rank counts and, for the same
+        # camera in steady state, the same reduced image and survivor set
+        torch.cuda.current_stream().wait_stream(overlap["cs"])
+        torch.cuda.synchronize()
+        b = (K - 1) & 1
+        img_o = pipe.vis64_bufs[b].clone()
+        cnt_o = overlap["cnt_all"][b].view(world, 3).cpu().numpy()
+        ids_o = overlap["ids_all"][b].view(world, gcap).cpu().numpy()
+        pipe.select_buffer(0)
+        for _ in range(2):  # serial path, same camera, steady state
+            pipe.frame(cams[b], **hooks)
+        torch.cuda.synchronize()
+        cnt_s = vis_all.view(world, 3).cpu().numpy()
+        ids_s = ids_all.view(world, gcap).cpu().numpy()
+        same_ids = all(np.array_equal(np.sort(ids_o[r, : cnt_o[r, 1] + cnt_o[r, 2]]), np.sort(ids_s[r, : cnt_s[r, 1] + cnt_s[r, 2]])) for r in range(world))
+        overlap_check = bool(np.array_equal(cnt_o, cnt_s) and same_ids and torch.equal(img_o, pipe.vis64))
+
     exchange = None
     if multi:
         def time_op(fn, n=10):
@@ -580,7 +599,7 @@ def main():
                           "triangles_rasterised": job_tris},
             "stages_ms": stages_ms, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches_per_frame * K), "gpu_launches_per_step": int(launches_per_frame),
-            "cuda_graph": (graphs is not None) or (half_graphs is not None), "exchange_overlapped": overlap is not None, "wall_s_timed_region": t_wall, "exchange": exchange, "stages_ms_per_rank": stages_all,
+            "cuda_graph": (graphs is not None) or (half_graphs is not None), "exchange_overlapped": overlap is not None, "overlap_check": overlap_check, "wall_s_timed_region": t_wall, "exchange": exchange, "stages_ms_per_rank": stages_all,
         }
         print(json.dumps(line), flush=True)
     pipe.close()
