@@ -549,17 +549,22 @@ def main():
 
     overlap_check = None
     if overlap is not None:
-        # the overlapped steps must deliver what the serial exchange delivers: same per-rank counts and, for the same
-        # camera in steady state, the same reduced image and survivor set
+        # the overlapped steps must deliver what the serial exchange delivers: replay the same 4-frame sequence from a
+        # zeroed visibility mask through both paths and compare counts, survivor sets and the reduced image
         torch.cuda.current_stream().wait_stream(overlap["cs"])
         torch.cuda.synchronize()
-        b = (K - 1) & 1
-        img_o = pipe.vis64_bufs[b].clone()
-        cnt_o = overlap["cnt_all"][b].view(world, 3).cpu().numpy()
-        ids_o = overlap["ids_all"][b].view(world, gcap).cpu().numpy()
+        pipe.ctx.reset_visibility_mask()
+        for i in range(4):
+            step_overlapped(i)
+        torch.cuda.current_stream().wait_stream(overlap["cs"])
+        torch.cuda.synchronize()
+        img_o = pipe.vis64_bufs[1].clone()
+        cnt_o = overlap["cnt_all"][1].view(world, 3).cpu().numpy()
+        ids_o = overlap["ids_all"][1].view(world, gcap).cpu().numpy()
+        pipe.ctx.reset_visibility_mask()
         pipe.select_buffer(0)
-        for _ in range(2):  # serial path, same camera, steady state
-            pipe.frame(cams[b], **hooks)
+        for i in range(4):
+            pipe.frame(cams[i % 2], **hooks)
         torch.cuda.synchronize()
         cnt_s = vis_all.view(world, 3).cpu().numpy()
         ids_s = ids_all.view(world, gcap).cpu().numpy()
