@@ -158,8 +158,7 @@ OXC_DI ScreenVert to_screen(float4 c, float fW, float fH) {
 
 struct TriSetup {
   int ax, ay, bx, by, cx, cy;   // 24.8 fixed point, a/b/c positively oriented (b,c swapped)
-  float za, zb, zc, fa_;        // depths of the re-oriented vertices and (float)area2; the gradients
-                                // dzb = (zb-za)/fa_, dzc = (zc-za)/fa_ are formed lazily (first covered pixel)
+  float za, dzb, dzc;           // depth at a, per-triangle gradients w.r.t. the edge functions of b and c
   int px0, px1, py0, py1;
   int bias;                     // bit0..2: edge biases (1 = -1)
   bool narrow;                  // all edge functions fit 32 bits (extent < 2^14 sub-pixels)
@@ -191,27 +190,20 @@ OXC_DI bool tri_setup(const ScreenVert v0, const ScreenVert v1, const ScreenVert
   else area2 = orient2d(v0.fx, v0.fy, v1.fx, v1.fy, v2.fx, v2.fy);
   if (area2 >= 0) return false;
   s.ax = v0.fx; s.ay = v0.fy; s.bx = v2.fx; s.by = v2.fy; s.cx = v1.fx; s.cy = v1.fy;
-  s.fa_ = (float)(-area2);
-  s.za = v0.z; s.zb = v2.z; s.zc = v1.z;
+  const float fa_ = (float)(-area2);
+  s.za = v0.z;
+  s.dzb = fd(fs(v2.z, v0.z), fa_);
+  s.dzc = fd(fs(v1.z, v0.z), fa_);
   s.bias = edge_bias_bit(s.bx, s.by, s.cx, s.cy) | (edge_bias_bit(s.cx, s.cy, s.ax, s.ay) << 1) |
            (edge_bias_bit(s.ax, s.ay, s.bx, s.by) << 2);
   return true;
 }
 
 // steps 5-6 given the three edge-function values at the pixel centre
-struct DepthGrad {
-  float dzb, dzc;
-  bool ready;
-};
-OXC_DI void depth_grad(const TriSetup& s, DepthGrad& g) { // raster spec step 6; identical bits whenever it is evaluated
-  if (!g.ready) { g.dzb = fd(fs(s.zb, s.za), s.fa_); g.dzc = fd(fs(s.zc, s.za), s.fa_); g.ready = true; }
-}
-
-OXC_DI void shade_pixel(const TriSetup& s, DepthGrad& g, long long e0, long long e1, long long e2, int px, int py, uint32_t data,
+OXC_DI void shade_pixel(const TriSetup& s, long long e0, long long e1, long long e2, int px, int py, uint32_t data,
                         unsigned long long* vis, uint32_t W) {
   if ((e0 - (s.bias & 1)) < 0 || (e1 - ((s.bias >> 1) & 1)) < 0 || (e2 - ((s.bias >> 2) & 1)) < 0) return;
-  depth_grad(s, g);
-  const float zz = fa(fa(s.za, fm((float)e1, g.dzb)), fm((float)e2, g.dzc));
+  const float zz = fa(fa(s.za, fm((float)e1, s.dzb)), fm((float)e2, s.dzc));
   if (!(zz >= 0.0f && zz <= 1.0f)) return;
   uint32_t zb = __float_as_uint(zz);
   zb = zb == 0x80000000u ? 0u : zb; // -0.0 -> +0.0 so unsigned order == depth order
@@ -220,19 +212,18 @@ OXC_DI void shade_pixel(const TriSetup& s, DepthGrad& g, long long e0, long long
   if (v > *ptr) atomicMax(ptr, v); // reverse-Z GreaterOrEqual == max (visbuffer.slang:72-74 packing)
 }
 
-OXC_DI void raster_pixel(const TriSetup& s, DepthGrad& g, int px, int py, uint32_t data, unsigned long long* vis, uint32_t W) {
+OXC_DI void raster_pixel(const TriSetup& s, int px, int py, uint32_t data, unsigned long long* vis, uint32_t W) {
   const int sx = px * 256 + 128, sy = py * 256 + 128;
-  shade_pixel(s, g, orient2d(s.bx, s.by, s.cx, s.cy, sx, sy), orient2d(s.cx, s.cy, s.ax, s.ay, sx, sy),
+  shade_pixel(s, orient2d(s.bx, s.by, s.cx, s.cy, sx, sy), orient2d(s.cx, s.cy, s.ax, s.ay, sx, sy),
               orient2d(s.ax, s.ay, s.bx, s.by, sx, sy), px, py, data, vis, W);
 }
 
 OXC_DI int orient2d_32(int ax, int ay, int bx, int by, int cx, int cy) { return (bx - ax) * (cy - ay) - (by - ay) * (cx - ax); }
 
-OXC_DI void shade_pixel_32(const TriSetup& s, DepthGrad& g, int e0, int e1, int e2, int px, int py, uint32_t data,
-                           unsigned long long* vis, uint32_t W) {
+OXC_DI void shade_pixel_32(const TriSetup& s, int e0, int e1, int e2, int px, int py, uint32_t data, unsigned long long* vis,
+                           uint32_t W) {
   if ((e0 - (s.bias & 1)) < 0 || (e1 - ((s.bias >> 1) & 1)) < 0 || (e2 - ((s.bias >> 2) & 1)) < 0) return;
-  depth_grad(s, g);
-  const float zz = fa(fa(s.za, fm((float)e1, g.dzb)), fm((float)e2, g.dzc)); // (float)int32 == (float)int64 of the same value
+  const float zz = fa(fa(s.za, fm((float)e1, s.dzb)), fm((float)e2, s.dzc)); // (float)int32 == (float)int64 of the same value
   if (!(zz >= 0.0f && zz <= 1.0f)) return;
   uint32_t zb = __float_as_uint(zz);
   zb = zb == 0x80000000u ? 0u : zb;
@@ -244,21 +235,15 @@ OXC_DI void shade_pixel_32(const TriSetup& s, DepthGrad& g, int e0, int e1, int 
 // one lane walks the (small) bounding box with incrementally stepped edge functions (adds only)
 OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* vis, uint32_t W) {
   const int sx0 = s.px0 * 256 + 128, sy0 = s.py0 * 256 + 128;
-  DepthGrad g;
-  g.ready = false;
   if (s.narrow) {
     int r0 = orient2d_32(s.bx, s.by, s.cx, s.cy, sx0, sy0), r1 = orient2d_32(s.cx, s.cy, s.ax, s.ay, sx0, sy0),
         r2 = orient2d_32(s.ax, s.ay, s.bx, s.by, sx0, sy0);
-    if (s.px0 == s.px1 && s.py0 == s.py1) { // the common case for pixel-sized triangles: one candidate sample
-      shade_pixel_32(s, g, r0, r1, r2, s.px0, s.py0, data, vis, W);
-      return;
-    }
     const int dx0 = -(s.cy - s.by) * 256, dy0 = (s.cx - s.bx) * 256, dx1 = -(s.ay - s.cy) * 256, dy1 = (s.ax - s.cx) * 256,
               dx2 = -(s.by - s.ay) * 256, dy2 = (s.bx - s.ax) * 256;
     for (int py = s.py0; py <= s.py1; py++) {
       int e0 = r0, e1 = r1, e2 = r2;
       for (int px = s.px0; px <= s.px1; px++) {
-        shade_pixel_32(s, g, e0, e1, e2, px, py, data, vis, W);
+        shade_pixel_32(s, e0, e1, e2, px, py, data, vis, W);
         e0 += dx0; e1 += dx1; e2 += dx2;
       }
       r0 += dy0; r1 += dy1; r2 += dy2;
@@ -275,7 +260,7 @@ OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* v
   for (int py = s.py0; py <= s.py1; py++) {
     long long e0 = r0, e1 = r1, e2 = r2;
     for (int px = s.px0; px <= s.px1; px++) {
-      shade_pixel(s, g, e0, e1, e2, px, py, data, vis, W);
+      shade_pixel(s, e0, e1, e2, px, py, data, vis, W);
       e0 += dx0; e1 += dx1; e2 += dx2;
     }
     r0 += dy0; r1 += dy1; r2 += dy2;
@@ -338,7 +323,6 @@ OXC_DI MeshletHeader bcast_header(const MeshletHeader& h, int src) {
 __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_visbuffer(const __grid_constant__ TriParams p) {
   __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   __shared__ ScreenVert scr_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
-  __shared__ uint32_t micro_all[TRI_WARPS][64]; // the meshlet's micro-index bytes (<= 192 B + misalignment), word aligned
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t first = p.late ? p.vis->early_visible_meshlet_instances : 0u; // cull_triangles.slang:34-37
   const uint32_t count = p.tri_cmd->x;                                         // dispatch_indirect(cull_triangles_cmd), CullGeometry.cpp:365
@@ -346,7 +330,6 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
   const float fW = (float)p.width, fH = (float)p.height;
   float4* clip_s = clip_all[warp];
   ScreenVert* scr_s = scr_all[warp];
-  uint32_t* micro_s = micro_all[warp];
   uint32_t kept = 0;
   // warps pull batches of RASTER_BATCH consecutive survivors from a global work counter (dynamic balance);
   // lanes 0..RASTER_BATCH-1 each chase one meshlet header, so RASTER_BATCH pointer chases are in flight together
@@ -366,24 +349,16 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
     MeshletHeader cur = bcast_header(mine, 0);
     uint32_t vi0 = lane < cur.vertex_count ? __ldg(&cur.vidx[lane]) : 0u;
     uint32_t vi1 = lane + 32u < cur.vertex_count ? __ldg(&cur.vidx[lane + 32u]) : 0u;
-    // micro-index words of the meshlet (scene.slang:336-342 reads them byte-wise from packed u32 words)
-#define OXC_MICRO_WORDS(h) ((((h).tri_offset & 3u) + 3u * (h).tri_count + 3u) >> 2)
-    uint32_t mw0 = lane < OXC_MICRO_WORDS(cur) ? __ldg(&cur.micro[(cur.tri_offset >> 2) + lane]) : 0u;
-    uint32_t mw1 = lane + 32u < OXC_MICRO_WORDS(cur) ? __ldg(&cur.micro[(cur.tri_offset >> 2) + lane + 32u]) : 0u;
     for (uint32_t j = 0; j < nb; j++) {
       const MeshletHeader w = cur;
       // positions of this meshlet (indices already here) ...
       const uint2 q0 = lane < w.vertex_count ? __ldg(&w.pos[vi0]) : make_uint2(0, 0);
       const uint2 q1 = lane + 32u < w.vertex_count ? __ldg(&w.pos[vi1]) : make_uint2(0, 0);
-      micro_s[lane] = mw0;
-      micro_s[lane + 32] = mw1;
-      // ... and the next meshlet's vertex / micro indices, in flight while this one is rasterised
+      // ... and the next meshlet's vertex indices, in flight while this one is rasterised
       if (j + 1 < nb) {
         cur = bcast_header(mine, (int)(j + 1));
         vi0 = lane < cur.vertex_count ? __ldg(&cur.vidx[lane]) : 0u;
         vi1 = lane + 32u < cur.vertex_count ? __ldg(&cur.vidx[lane + 32u]) : 0u;
-        mw0 = lane < OXC_MICRO_WORDS(cur) ? __ldg(&cur.micro[(cur.tri_offset >> 2) + lane]) : 0u;
-        mw1 = lane + 32u < OXC_MICRO_WORDS(cur) ? __ldg(&cur.micro[(cur.tri_offset >> 2) + lane + 32u]) : 0u;
       }
       const InstCull* ic = p.inst + w.inst;
       const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
@@ -408,8 +383,8 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
         TriSetup s;
         bool draw = false;
         if (t < w.tri_count) {
-          const uint8_t* mb = reinterpret_cast<const uint8_t*>(micro_s) + (w.tri_offset & 3u) + t * 3u;
-          const uint32_t i0 = mb[0] & 63u, i1 = mb[1] & 63u, i2 = mb[2] & 63u; // (valid data: < vertex_count <= 64)
+          const uint32_t base = w.tri_offset + t * 3u;
+          const uint32_t i0 = micro_index(w.micro, base + 0u), i1 = micro_index(w.micro, base + 1u), i2 = micro_index(w.micro, base + 2u);
           const float4 c0 = clip_s[i0], c1 = clip_s[i1], c2 = clip_s[i2];
           pass = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f && !triangle_backface(c0, c1, c2); // cull_triangles.slang:68-69
           if (pass) draw = tri_setup(scr_s[i0], scr_s[i1], scr_s[i2], p.width, p.height, s);
@@ -428,19 +403,17 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
           b.ax = __shfl_sync(0xffffffffu, s.ax, src); b.ay = __shfl_sync(0xffffffffu, s.ay, src);
           b.bx = __shfl_sync(0xffffffffu, s.bx, src); b.by = __shfl_sync(0xffffffffu, s.by, src);
           b.cx = __shfl_sync(0xffffffffu, s.cx, src); b.cy = __shfl_sync(0xffffffffu, s.cy, src);
-          b.za = __shfl_sync(0xffffffffu, s.za, src); b.zb = __shfl_sync(0xffffffffu, s.zb, src);
-          b.zc = __shfl_sync(0xffffffffu, s.zc, src); b.fa_ = __shfl_sync(0xffffffffu, s.fa_, src);
+          b.za = __shfl_sync(0xffffffffu, s.za, src); b.dzb = __shfl_sync(0xffffffffu, s.dzb, src);
+          b.dzc = __shfl_sync(0xffffffffu, s.dzc, src);
           b.px0 = __shfl_sync(0xffffffffu, s.px0, src); b.px1 = __shfl_sync(0xffffffffu, s.px1, src);
           b.py0 = __shfl_sync(0xffffffffu, s.py0, src); b.py1 = __shfl_sync(0xffffffffu, s.py1, src);
           b.bias = __shfl_sync(0xffffffffu, s.bias, src);
           const uint32_t bdata = __shfl_sync(0xffffffffu, data, src);
           const int lx = lane & 7, ly = lane >> 3;
-          DepthGrad bg;
-          bg.ready = false;
           for (int ty = b.py0; ty <= b.py1; ty += 4)
             for (int tx = b.px0; tx <= b.px1; tx += 8) {
               const int px = tx + lx, py = ty + ly;
-              if (px <= b.px1 && py <= b.py1) raster_pixel(b, bg, px, py, bdata, p.visbuf, p.width);
+              if (px <= b.px1 && py <= b.py1) raster_pixel(b, px, py, bdata, p.visbuf, p.width);
             }
         }
       }
