@@ -319,6 +319,24 @@ int oxc_merge_depth(OxcContext* ctx, uint64_t* vis_dev, const float* depth_dev, 
 int oxc_cull_meshlets_multiview(OxcContext* ctx, const OxcCullCamera* views, uint32_t n_views, int directional,
                                 void* stream);
 
+/* Shadow-clipmap cull: passes/cull_meshlets_hpb.slang:27-99 via CullGeometry.cpp:199-273 (use_hpb).  Per meshlet:
+ * directional cone test against camera->position (= -light_dir, Shadowmaps.cpp:433-463) and frustum test against the
+ * coarse view `camera`; then for each clipmap whose dirty flag is set: frustum test, project_aabb with the clipmap's
+ * z_near, and the hierarchical page-bitmap test test_vsm_page (cull.slang:137-166; nearest, clamped sampling of an R8UI
+ * pyramid: 4 corner taps at mip = clamp(ceil(log2(box extent in pages)), 0, levels-1), visible iff any tap != 0); a
+ * projection failure counts as visible; first visible clipmap wins.  Survivors are appended like the plain variant
+ * (base index from cull_triangles_cmd.x, which is reset first).  Requires OxcCreateInfo::max_views >= clipmap_count.
+ * hpb_dev layout: for level l = 0..levels-1 (side s_l = max(1, hpb_size >> l)): layers x s_l x s_l bytes, layer-major. */
+typedef struct OxcVirtualClipmap { /* SceneGPU.hpp:339-343, scalar layout, 76 B */
+  float projection_view_mat[16];
+  int32_t page_offset[2];
+  float z_near;
+} OxcVirtualClipmap;
+OXC_STATIC_ASSERT(sizeof(OxcVirtualClipmap) == 76, "VirtualClipmap");
+int oxc_cull_meshlets_hpb(OxcContext* ctx, const OxcCullCamera* camera, const OxcVirtualClipmap* clipmaps /* host */,
+                          const uint32_t* clipmap_dirty_flags /* host */, uint32_t clipmap_count, const uint8_t* hpb_dev,
+                          uint32_t hpb_size, uint32_t hpb_levels, void* stream);
+
 /* Terrain patch cull: passes/terrain_cull.slang:19-83 via RendererInstance::cull_terrain
  * (Passes/Terrain.cpp:159-216).  One thread per patch: AABB from the patch grid + patch_minmax, frustum test against
  * projection_view itself, Hi-Z occlusion against the context's pyramid, own persistent visibility mask, early/late

@@ -619,6 +619,82 @@ void orc_resolve_visbuffer(const uint64_t* vis, uint32_t width, uint32_t height,
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * cull.slang:137-166 test_vsm_page + passes/cull_meshlets_hpb.slang:27-99
+ * ---------------------------------------------------------------------------------------------- */
+/* max(0, ceil(log2(x))) on the float's bits: exact, no libm (x <= 0 or NaN -> 0; log2(+inf) -> 255) */
+uint32_t orc_ceil_log2_f32(float x) {
+  if (!(x > 1.0f)) return 0u;
+  uint32_t b = f2bits(x);
+  if ((b >> 23) == 255u) return 255u; /* inf */
+  int32_t e = (int32_t)(b >> 23) - 127;
+  return (uint32_t)(e + ((b & 0x7FFFFFu) ? 1 : 0));
+}
+
+static inline float fract_f32(float x) { return x - floorf(x); } /* Slang fract */
+
+/* SampleLevel(NearestSamplerClamped, uv, level) != 0 on the R8UI pyramid: texel = clamp(floor(uv * size), 0, size-1) */
+static int hpb_tap(const uint8_t* hpb, uint32_t hpb_size, uint32_t layers, uint32_t layer, uint32_t level, float u, float v) {
+  size_t off = 0;
+  for (uint32_t l = 0; l < level; l++) { uint32_t sl = hpb_size >> l; if (sl < 1) sl = 1; off += (size_t)layers * sl * sl; }
+  uint32_t sz = hpb_size >> level; if (sz < 1) sz = 1;
+  int32_t x = to_i32_f32(floorf(u * (float)sz)), y = to_i32_f32(floorf(v * (float)sz));
+  if (x < 0) x = 0;
+  if (x > (int32_t)sz - 1) x = (int32_t)sz - 1;
+  if (y < 0) y = 0;
+  if (y > (int32_t)sz - 1) y = (int32_t)sz - 1;
+  return hpb[off + ((size_t)layer * sz + (size_t)y) * sz + (size_t)x] != 0;
+}
+
+static int test_vsm_page(const ScreenAabb_f32* a, const uint8_t* hpb, uint32_t hpb_size, uint32_t levels, uint32_t layers,
+                         uint32_t layer, const int32_t page_offset[2]) {
+  const float hs = (float)hpb_size;                                     /* :148-149 (square pyramid) */
+  const float pox = (float)page_offset[0] / hs, poy = (float)page_offset[1] / hs; /* :151 */
+  const float minu = a->min[0], minv = a->min[1], maxu = a->max[0], maxv = a->max[1];
+  const float box_w = (maxu - minu) * hs, box_h = (maxv - minv) * hs;   /* :156-157 */
+  uint32_t mip = orc_ceil_log2_f32(rmax_f32(box_w, box_h));             /* :158 */
+  if (mip > levels - 1) mip = levels - 1;
+  const int tl = hpb_tap(hpb, hpb_size, layers, layer, mip, fract_f32(minu + pox), fract_f32(minv + poy)); /* :160 */
+  const int tr = hpb_tap(hpb, hpb_size, layers, layer, mip, fract_f32(maxu + pox), fract_f32(minv + poy)); /* :161 */
+  const int bl = hpb_tap(hpb, hpb_size, layers, layer, mip, fract_f32(minu + pox), fract_f32(maxv + poy)); /* :162 */
+  const int br = hpb_tap(hpb, hpb_size, layers, layer, mip, fract_f32(maxu + pox), fract_f32(maxv + poy)); /* :163 */
+  return tl | tr | bl | br;
+}
+
+void orc_cull_meshlets_hpb(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, const OxcCullCamera* cam,
+                           const OxcVirtualClipmap* clipmaps, const uint32_t* dirty_flags, uint32_t clipmap_count,
+                           const uint8_t* hpb, uint32_t hpb_size, uint32_t hpb_levels, const OxcMeshletInstanceVisibility* vis,
+                           uint32_t* visible_indices, OxcDispatchIndirectCommand* cmd) {
+  cmd->x = 0; cmd->y = 1; cmd->z = 1;
+  const Vec3_f32 view_dir = {cam->position[0], cam->position[1], cam->position[2]};
+  const uint32_t total = vis->total_visible_meshlet_instances;
+  for (uint32_t i = 0; i < total; i++) { /* :39-40 */
+    MeshletCtx m;
+    fetch_meshlet(scene, meshlet_instances[i], &m);
+    float mvp[16];
+    mul_mm_f32(cam->projection_view, m.world, mvp); /* :44 */
+    int cone_vis = 1;                               /* :53-54 */
+    if (!(m.cutoff >= 1.0f)) {
+      Vec3_f32 axis = world_cone_axis_f32(m.world, m.axis);
+      cone_vis = !(dot3_f32(axis, view_dir) >= m.cutoff);
+    }
+    if (!(cone_vis && test_frustum_f32(mvp, m.c, m.e))) continue; /* :56 */
+    int visible = 0;
+    for (uint32_t ci = 0; ci < clipmap_count; ci++) { /* :59-79 */
+      if (dirty_flags[ci] == 0u) continue;
+      float cmvp[16];
+      mul_mm_f32(clipmaps[ci].projection_view_mat, m.world, cmvp);
+      if (!test_frustum_f32(cmvp, m.c, m.e)) continue;
+      ScreenAabb_f32 sa;
+      if (project_aabb_f32(cmvp, clipmaps[ci].z_near, m.c, m.e, &sa))
+        visible = test_vsm_page(&sa, hpb, hpb_size, hpb_levels, clipmap_count, ci, clipmaps[ci].page_offset);
+      else visible = 1;
+      if (visible) break;
+    }
+    if (visible) visible_indices[cmd->x++] = i; /* :81-98 */
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * passes/terrain_cull.slang:19-83; TerrainData::patch_corner / decode_height scene.slang:648-660
  * ---------------------------------------------------------------------------------------------- */
 void orc_cull_terrain(const OxcTerrainData* t, const float* patch_minmax, const OxcCullCamera* cam, uint32_t flags,

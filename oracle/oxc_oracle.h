@@ -115,6 +115,13 @@ void orc_raster_visbuffer(const OrcScene* scene, const OxcMeshletInstance* meshl
                           uint64_t* vis, uint64_t* triangles_rasterised);
 void orc_resolve_visbuffer(const uint64_t* vis, uint32_t width, uint32_t height, uint32_t* vis32, float* depth);
 
+/* passes/cull_meshlets_hpb.slang:27-99 + cull.slang:137-166 test_vsm_page.  hpb: levels of (layers x s x s) bytes. */
+void orc_cull_meshlets_hpb(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, const OxcCullCamera* cam,
+                           const OxcVirtualClipmap* clipmaps, const uint32_t* dirty_flags, uint32_t clipmap_count,
+                           const uint8_t* hpb, uint32_t hpb_size, uint32_t hpb_levels, const OxcMeshletInstanceVisibility* vis,
+                           uint32_t* visible_indices, OxcDispatchIndirectCommand* cull_triangles_cmd);
+uint32_t orc_ceil_log2_f32(float x); /* ceil(log2(x)) clamped at 0 from below, evaluated on the float's bits */
+
 /* passes/terrain_cull.slang:19-83 */
 void orc_cull_terrain(const OxcTerrainData* terrain, const float* patch_minmax, const OxcCullCamera* cam, uint32_t flags,
                       const OrcHiz* hiz, uint32_t* visible_patches, uint32_t* mask, OxcDrawIndirectCommand* draw_cmd);

@@ -210,6 +210,17 @@ def frame(hs, cam, width, height, mask, occluder_depth=None, first=0, count=0xFF
                 mask_after_early=mask_after_early, ntri_early=ntri_e, ntri_late=ntri_l, cull_meshlets_cmd=cmd, id_base=id_base)
 
 
+def cull_meshlets_hpb(hs, mi, vis, cam, clipmaps, dirty_flags, hpb, hpb_size, hpb_levels):
+    visible = np.zeros(max(1, hs.max_meshlets), dtype=np.uint32)
+    cmd = np.zeros(1, dtype=abi.DISPATCH_CMD_DT)
+    cm = np.ascontiguousarray(clipmaps)
+    df = np.ascontiguousarray(dirty_flags, dtype=np.uint32)
+    hp = np.ascontiguousarray(hpb, dtype=np.uint8)
+    lib().orc_cull_meshlets_hpb(hs.ref, _p(mi), _p(cam), _p(cm), _p(df), C.c_uint32(len(cm)), _p(hp), C.c_uint32(hpb_size),
+                                C.c_uint32(hpb_levels), _p(vis), _p(visible), _p(cmd))
+    return visible[: int(cmd["x"][0])], cmd
+
+
 def cull_terrain(terrain, patch_minmax, cam, flags, hiz: Hiz, mask):
     n = int(terrain["patch_count"][0][0]) * int(terrain["patch_count"][0][1])
     visible = np.zeros(max(1, n), dtype=np.uint32)

@@ -88,6 +88,8 @@ DRAW_CMD_DT = np.dtype(
 TERRAIN_DT = np.dtype([("world_min", "<f4", (2,)), ("world_size", "<f4", (2,)), ("patch_count", "<u4", (2,)),
                        ("base_height", "<f4"), ("height_scale", "<f4")])
 DRAW_INDIRECT_DT = np.dtype([("vertex_count", "<u4"), ("instance_count", "<u4"), ("first_vertex", "<u4"), ("first_instance", "<u4")])
+CLIPMAP_DT = np.dtype([("projection_view_mat", "<f4", (16,)), ("page_offset", "<i4", (2,)), ("z_near", "<f4")])
+assert CLIPMAP_DT.itemsize == 76
 assert TERRAIN_DT.itemsize == 32 and DRAW_INDIRECT_DT.itemsize == 16
 assert TRANSFORM_DT.itemsize == 64
 assert MESHLET_BOUNDS_DT.itemsize == 16

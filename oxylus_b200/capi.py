@@ -18,7 +18,7 @@ SYMBOLS = [
     "oxc_last_error", "oxc_kernel_launch_count", "oxc_version", "oxc_create", "oxc_destroy", "oxc_set_scene",
     "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_set_shard_auto", "oxc_cull_meshes",
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
-    "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview", "oxc_cull_terrain",
+    "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
     "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
 ]
@@ -68,6 +68,7 @@ def load(build_if_missing=True):
     lib.oxc_resolve_visbuffer.argtypes = [vp, vp, u32, u32, vp, vp, vp]
     lib.oxc_merge_depth.argtypes = [vp, vp, vp, u32, u32, vp]
     lib.oxc_cull_meshlets_multiview.argtypes = [vp, vp, u32, i32, vp]
+    lib.oxc_cull_meshlets_hpb.argtypes = [vp, vp, vp, vp, u32, vp, u32, u32, vp]
     lib.oxc_cull_terrain.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp]
     lib.oxc_get_outputs.argtypes = [vp, C.POINTER(abi.Outputs)]
     lib.oxc_copy.argtypes = [vp, vp, vp, u64, i32, vp]
@@ -213,6 +214,12 @@ class Context:
         v = np.ascontiguousarray(views)
         _check(self.lib.oxc_cull_meshlets_multiview(self.h, _ptr(v), len(v), int(directional), self.stream),
                "oxc_cull_meshlets_multiview")
+
+    def cull_meshlets_hpb(self, cam, clipmaps, dirty_flags, hpb_dev, hpb_size, hpb_levels):
+        cm = np.ascontiguousarray(clipmaps)
+        df = np.ascontiguousarray(dirty_flags, dtype=np.uint32)
+        _check(self.lib.oxc_cull_meshlets_hpb(self.h, _ptr(cam), _ptr(cm), _ptr(df), len(cm), _ptr(hpb_dev), hpb_size, hpb_levels,
+                                              self.stream), "oxc_cull_meshlets_hpb")
 
     def cull_terrain(self, terrain, patch_minmax_dev, cam, flags, visible_patches_dev, mask_dev, draw_cmd_dev):
         t = np.ascontiguousarray(terrain)

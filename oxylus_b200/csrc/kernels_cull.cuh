@@ -674,6 +674,140 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets_multiview(const 
 }
 
 // ------------------------------------------------------------------------------------------------
+// Shadow-clipmap cull — passes/cull_meshlets_hpb.slang:27-99 + cull.slang:137-166 (canonical arithmetic)
+// ------------------------------------------------------------------------------------------------
+struct HpbParams {
+  const OxcMeshletInstance* meshlet_instances;
+  const InstCull* inst;          // built for the coarse view `camera`
+  const InstView* views;         // [clipmap][inst_stride]
+  const OxcMeshletInstanceVisibility* vis;
+  uint32_t* visible_indices;
+  OxcDispatchIndirectCommand* tri_cmd;
+  const uint32_t* id_base;
+  const uint8_t* hpb;
+  uint32_t hpb_size, hpb_levels, clipmap_count, inst_stride;
+  uint32_t dirty_mask;           // bit c: clipmap_dirty_flags[c] != 0
+  float view_dir[3];             // camera.position (= -light_dir)
+  float z_near[OXC_MAX_VIEWS];
+  int page_offset[OXC_MAX_VIEWS][2];
+};
+
+// max(0, ceil(log2(x))) evaluated on the bits of the float: exact, no libm
+OXC_DI uint32_t ceil_log2_f32(float x) {
+  if (!(x > 1.0f)) return 0u;
+  const uint32_t b = __float_as_uint(x);
+  if ((b >> 23) == 255u) return 255u;
+  return (uint32_t)((int)(b >> 23) - 127 + ((b & 0x7FFFFFu) ? 1 : 0));
+}
+
+OXC_DI bool hpb_tap(const HpbParams& p, uint32_t layer, uint32_t level, float u, float v) {
+  size_t off = 0;
+  for (uint32_t l = 0; l < level; l++) { uint32_t sl = p.hpb_size >> l; sl = sl < 1 ? 1 : sl; off += (size_t)p.clipmap_count * sl * sl; }
+  uint32_t sz = p.hpb_size >> level;
+  sz = sz < 1 ? 1 : sz;
+  int x = __float2int_rz(floorf(fm(u, (float)sz))), y = __float2int_rz(floorf(fm(v, (float)sz)));
+  x = min(max(x, 0), (int)sz - 1);
+  y = min(max(y, 0), (int)sz - 1);
+  return __ldg(p.hpb + off + ((size_t)layer * sz + (size_t)y) * sz + (size_t)x) != 0;
+}
+
+OXC_DI bool test_vsm_page(const HpbParams& p, const ScreenAabb& a, uint32_t layer) {
+  const float hs = (float)p.hpb_size;
+  const float pox = fd((float)p.page_offset[layer][0], hs), poy = fd((float)p.page_offset[layer][1], hs);
+  const float box_w = fm(fs(a.maxx, a.minx), hs), box_h = fm(fs(a.maxy, a.miny), hs);
+  uint32_t mip = ceil_log2_f32(omax(box_w, box_h));
+  mip = mip > p.hpb_levels - 1 ? p.hpb_levels - 1 : mip;
+#define OXC_FRACT(x) fs((x), floorf(x))
+  const float u0 = fa(a.minx, pox), u1 = fa(a.maxx, pox), v0 = fa(a.miny, poy), v1 = fa(a.maxy, poy);
+  const bool tl = hpb_tap(p, layer, mip, OXC_FRACT(u0), OXC_FRACT(v0));
+  const bool tr = hpb_tap(p, layer, mip, OXC_FRACT(u1), OXC_FRACT(v0));
+  const bool bl = hpb_tap(p, layer, mip, OXC_FRACT(u0), OXC_FRACT(v1));
+  const bool br = hpb_tap(p, layer, mip, OXC_FRACT(u1), OXC_FRACT(v1));
+#undef OXC_FRACT
+  return tl | tr | bl | br;
+}
+
+__global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets_hpb(const __grid_constant__ HpbParams p) {
+  __shared__ uint32_t warp_cnt[CULL_THREADS / 32];
+  __shared__ uint32_t base_s;
+  const uint32_t total = p.vis->total_visible_meshlet_instances;
+  const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint2* mi2 = reinterpret_cast<const uint2*>(p.meshlet_instances);
+  const uint32_t n_tiles = (total + CULL_THREADS - 1) / CULL_THREADS;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t i = tile * CULL_THREADS + threadIdx.x;
+    bool visible = false;
+    if (i < total) {
+      const uint2 mi = __ldg(&mi2[i]);
+      const InstCull* ic = p.inst + mi.x;
+      const uint4 tail = __ldg(reinterpret_cast<const uint4*>(&ic->bounds_lo));
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(((uint64_t)tail.y << 32) | tail.x) + mi.y);
+      const float cx = dequantize_half(b.x & 0xFFFFu), cy = dequantize_half(b.x >> 16), cz = dequantize_half(b.y & 0xFFFFu);
+      const float ex = dequantize_half(b.z & 0xFFFFu), ey = dequantize_half(b.z >> 16), ez = dequantize_half(b.w & 0xFFFFu);
+      const float cutoff = s8_over_127((int)(int8_t)(b.w >> 24));
+      bool cone_vis = true; // :53-54
+      if (cutoff < 1.0f) {
+        float wax, way, waz;
+        world_cone_axis(ic, s8_over_127((int)(int8_t)((b.y >> 16) & 0xFF)), s8_over_127((int)(int8_t)(b.y >> 24)),
+                        s8_over_127((int)(int8_t)((b.w >> 16) & 0xFF)), wax, way, waz);
+        cone_vis = !(dot3(wax, way, waz, p.view_dir[0], p.view_dir[1], p.view_dir[2]) >= cutoff);
+      }
+      if (cone_vis && test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez)) { // :56
+        for (uint32_t ci = 0; ci < p.clipmap_count; ci++) { // :59-79
+          if (!((p.dirty_mask >> ci) & 1u)) continue;
+          const InstView* v = p.views + (size_t)ci * p.inst_stride + mi.x;
+          if (!test_frustum_planes(v->plane, cx, cy, cz, ex, ey, ez)) continue;
+          ScreenAabb sa;
+          if (project_aabb(__ldg(&v->row[0]), __ldg(&v->row[1]), __ldg(&v->row[2]), __ldg(&v->row[3]), p.z_near[ci], cx, cy, cz, ex, ey, ez, sa))
+            visible = test_vsm_page(p, sa, ci);
+          else visible = true;
+          if (visible) break;
+        }
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, visible);
+    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t s = 0;
+#pragma unroll
+      for (int w = 0; w < CULL_THREADS / 32; w++) { const uint32_t c = warp_cnt[w]; warp_cnt[w] = s; s += c; }
+      base_s = s ? atomicAdd(&p.tri_cmd->x, s) : 0u; // :91
+    }
+    __syncthreads();
+    if (visible) p.visible_indices[base_s + warp_cnt[warp] + __popc(bal & ((1u << lane) - 1u))] = i + id_base; // :96
+    __syncthreads();
+  }
+}
+
+__global__ void k_prepare_inst_views(const OxcMeshInstance* __restrict__ mesh_instances, const OxcTransformWorld* __restrict__ transforms,
+                                     const float* __restrict__ view_pv /* [n_views][16] */, uint32_t n_views, uint32_t first,
+                                     uint32_t count, uint32_t inst_stride, InstView* out) {
+  const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+  if (local >= count) return;
+  const uint32_t mi = first + local;
+  const float* world = transforms[mesh_instances[mi].transform_index].world;
+  float w[16];
+#pragma unroll
+  for (int k = 0; k < 16; k++) w[k] = world[k];
+  for (uint32_t v = 0; v < n_views; v++) {
+    float pv[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) pv[k] = view_pv[v * 16 + k];
+    float4 rows[4], planes[6];
+    mul_mm_rows(pv, w, rows);
+    frustum_planes(rows, planes);
+    InstView iv;
+#pragma unroll
+    for (int k = 0; k < 6; k++) iv.plane[k] = planes[k];
+#pragma unroll
+    for (int k = 0; k < 4; k++) iv.row[k] = rows[k];
+    out[(size_t)v * inst_stride + mi] = iv;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Terrain patch cull — passes/terrain_cull.slang:19-83 (canonical arithmetic throughout: patch counts are small)
 // ------------------------------------------------------------------------------------------------
 struct TerrainParams {

@@ -47,6 +47,12 @@ struct __align__(16) InstPlanes {
   float4 plane[6];
 };
 
+// Per clipmap, per mesh instance (shadow-clipmap cull): planes + rows of mul(clipmap.pv, world).
+struct __align__(16) InstView {
+  float4 plane[6];
+  float4 row[4];
+};
+
 struct HizDesc {
   const float* data;
   uint32_t width, height, levels;

@@ -129,6 +129,8 @@ struct OxcContext {
   OxcCullCamera* d_views = nullptr;
   uint32_t* d_view_bits = nullptr;
   uint32_t* d_view_counts = nullptr;
+  InstView* d_inst_views = nullptr; // shadow-clipmap cull: [max_views][max_mesh_instances]
+  float* d_view_pv = nullptr;       // [OXC_MAX_VIEWS][16]
   // launch shapes
   int occ_cull[2][2][2] = {};
   bool hiz_zero = true; // the pyramid holds the cleared (all-zero) image: lets the early pass skip the Hi-Z fetches
@@ -233,6 +235,8 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
     TRY(dalloc(&c->d_views, (size_t)OXC_MAX_VIEWS));
     TRY(dalloc(&c->d_view_bits, (size_t)N));
     TRY(dalloc(&c->d_view_counts, (size_t)OXC_MAX_VIEWS));
+    TRY(dalloc(&c->d_inst_views, (size_t)I * info->max_views));
+    TRY(dalloc(&c->d_view_pv, (size_t)OXC_MAX_VIEWS * 16));
   }
   // Hi-Z pyramid: levels = min(floor(log2(max(w,h))) + 1, 13)  (Texture.hpp:144-146, RendererInstance.cpp:583-586)
   {
@@ -285,7 +289,7 @@ void oxc_destroy(OxcContext* c) {
   cudaFree(c->d_meshlet_instances); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
   cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_id_base_auto); cudaFree(c->d_hiz);
-  cudaFree(c->d_view_planes); cudaFree(c->d_views); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts);
+  cudaFree(c->d_view_planes); cudaFree(c->d_views); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts); cudaFree(c->d_inst_views); cudaFree(c->d_view_pv);
   delete c;
 }
 
@@ -639,6 +643,46 @@ int oxc_device_free(OxcContext* c, void* p) {
   if (!c) return fail(OXC_E_INVALID, "null context");
   CK(cudaSetDevice(c->device));
   CK(cudaFree(p));
+  return OXC_OK;
+}
+
+int oxc_cull_meshlets_hpb(OxcContext* c, const OxcCullCamera* cam, const OxcVirtualClipmap* clipmaps, const uint32_t* dirty,
+                          uint32_t n, const uint8_t* hpb_dev, uint32_t hpb_size, uint32_t hpb_levels, void* stream) {
+  if (!c || !cam || !clipmaps || !dirty || !hpb_dev || n == 0 || hpb_size == 0 || hpb_levels == 0) return fail(OXC_E_INVALID, "bad argument");
+  if (n > c->info.max_views || !c->d_inst_views) return fail(OXC_E_CAPACITY, "clipmap_count %u > max_views %u", n, c->info.max_views);
+  if (!c->scene_set) return fail(OXC_E_STATE, "oxc_set_scene first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  int rc = refresh_inst_cache(c, cam, s); // InstCull for the coarse view
+  if (rc != OXC_OK) return rc;
+  float pv[OXC_MAX_VIEWS][16];
+  HpbParams p{};
+  for (uint32_t v = 0; v < n; v++) {
+    memcpy(pv[v], clipmaps[v].projection_view_mat, sizeof pv[v]);
+    p.z_near[v] = clipmaps[v].z_near;
+    p.page_offset[v][0] = clipmaps[v].page_offset[0]; p.page_offset[v][1] = clipmaps[v].page_offset[1];
+    if (dirty[v]) p.dirty_mask |= 1u << v;
+  }
+  CK(cudaMemcpyAsync(c->d_view_pv, pv, (size_t)n * 16 * sizeof(float), cudaMemcpyHostToDevice, s));
+  uint32_t first, count;
+  shard_range(c, c->cached_cam.mesh_instance_count, &first, &count);
+  const uint32_t stride = c->info.max_mesh_instances;
+  if (count) {
+    k_prepare_inst_views<<<(count + 127) / 128, 128, 0, s>>>(c->d_mesh_instances, c->d_transforms, c->d_view_pv, n, first, count, stride, c->d_inst_views);
+    LAUNCHED();
+  }
+  k_set_cmd3<<<1, 1, 0, s>>>(c->d_cull_triangles_cmd, 0, 1, 1); // CullGeometry.cpp:125-127
+  LAUNCHED();
+  p.meshlet_instances = c->d_meshlet_instances; p.inst = c->d_inst; p.views = c->d_inst_views; p.vis = c->d_vis;
+  p.visible_indices = c->d_visible; p.tri_cmd = c->d_cull_triangles_cmd; p.id_base = c->id_base; p.hpb = hpb_dev;
+  p.hpb_size = hpb_size; p.hpb_levels = hpb_levels; p.clipmap_count = n; p.inst_stride = stride;
+  p.view_dir[0] = cam->position[0]; p.view_dir[1] = cam->position[1]; p.view_dir[2] = cam->position[2];
+  uint32_t blocks = (c->info.max_meshlet_instances + CULL_THREADS - 1) / CULL_THREADS;
+  uint32_t grid = (uint32_t)c->sm_count * 4u;
+  if (grid > blocks) grid = blocks;
+  if (grid == 0) grid = 1;
+  k_cull_meshlets_hpb<<<grid, CULL_THREADS, 0, s>>>(p);
+  LAUNCHED();
   return OXC_OK;
 }
 

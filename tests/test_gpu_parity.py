@@ -573,3 +573,43 @@ def test_full_size_config2_properties(capi):
             assert got["late"] == prev["late"]
         prev = got
     r.close()
+
+
+def test_cull_meshlets_hpb_parity(capi, orc):
+    """cull_meshlets_hpb.slang equivalent: coarse view + 10 ortho clipmaps with page offsets, dirty flags, random R8UI page
+    pyramid (64x64 pages, 7 mips); survivor set bit-exact."""
+    sc = synth.make_scene(60000, config_index=4, width=1280, height=720, n_unique_meshes=32, placement="box")
+    hs = orc.HostScene(sc)
+    ctx = make_ctx(capi, sc, views=10)
+    cam0 = sc.camera()
+    mi, vis, _ = orc.cull_meshes(hs, cam0, abi.CULL_TEST_ALL)
+    ctx.cull_meshes(cam0, abi.CULL_TEST_ALL)
+    rng = np.random.default_rng(17)
+    light = np.float64([0.3, -0.8, -0.5])
+    n_clip = 10
+    clip = np.zeros(n_clip, dtype=abi.CLIPMAP_DT)
+    for c in range(n_clip):
+        v = synth.make_ortho_view(light, (0.0, 0.0, -200.0), 12.0 * (1.6 ** c), 1200.0, sc.mesh_instance_count)
+        clip["projection_view_mat"][c] = v["projection_view"][0]
+        clip["page_offset"][c] = rng.integers(-40, 40, size=2)
+        clip["z_near"][c] = 0.0
+    coarse = synth.make_ortho_view(light, (0.0, 0.0, -200.0), 12.0 * (1.6 ** (n_clip - 1)), 1200.0, sc.mesh_instance_count)
+    coarse["position"][0] = -light / np.linalg.norm(light)
+    size, levels = 64, 7
+    lv = [(rng.random((n_clip, size, size)) < 0.12).astype(np.uint8)]
+    for l in range(1, levels):
+        p = lv[l - 1]
+        lv.append(np.maximum(np.maximum(p[:, 0::2, 0::2], p[:, 0::2, 1::2]), np.maximum(p[:, 1::2, 0::2], p[:, 1::2, 1::2])))
+    hpb = np.concatenate([a.reshape(-1) for a in lv])
+    hpb_dev = ctx.alloc(hpb.nbytes)
+    ctx.upload(hpb_dev, hpb)
+    for dirty in ([1] * n_clip, [1, 0, 1, 0, 0, 1, 0, 0, 0, 1], [0] * n_clip):
+        ref, cmd = orc.cull_meshlets_hpb(hs, mi, vis, coarse, clip, dirty, hpb, size, levels)
+        ctx.cull_meshlets_hpb(coarse, clip, dirty, hpb_dev, size, levels)
+        n = int(cmd["x"][0])
+        assert int(ctx.cull_triangles_cmd()["x"][0]) == n
+        np.testing.assert_array_equal(np.sort(ctx.visible_indices(n)), np.sort(ref))
+        assert (n == 0) == (sum(dirty) == 0)
+    assert 0 < n_clip
+    ctx.free(hpb_dev)
+    ctx.close()

@@ -244,3 +244,66 @@ def test_terrain_cull_hand_case(orc):
     # late pass again: patch 0 was visible -> not re-emitted
     vis, cmd = orc.cull_terrain(t, minmax, cam, flags, hz, mask)
     assert len(vis) == 0 and int(mask[0]) == 0b01
+
+
+def test_ceil_log2_f32_matches_libm(orc):
+    """cull.slang:158 ceil(log2(float)) on the float's bits == libm for every finite x > 1 tested, 0 below."""
+    fn = orc.lib().orc_ceil_log2_f32
+    fn.restype = C.c_uint32
+    fn.argtypes = [C.c_float]
+    rng = np.random.default_rng(4)
+    xs = np.concatenate([np.float32(2.0) ** np.arange(0, 30), np.nextafter(np.float32(2.0) ** np.arange(1, 30), np.float32(0)),
+                         np.nextafter(np.float32(2.0) ** np.arange(0, 30), np.float32(1e30)), rng.uniform(0.0, 5000.0, 4000).astype(np.float32),
+                         np.float32([0.0, -3.0, 0.5, 1.0, 1.0000001])])
+    for x in xs.astype(np.float32):
+        want = 0 if not (x > 1.0) else max(0, math.ceil(math.log2(float(x))))
+        assert fn(C.c_float(float(x))) == want, float(x)
+
+
+def test_vsm_page_and_hpb_cull_hand_case(orc):
+    """cull_meshlets_hpb.slang:27-99 with identity matrices: one meshlet box projected to uv [0.25,0.5]^2 of an 8x8 page
+    table, two clipmaps (layer 0 clean -> skipped, layer 1 dirty)."""
+    from tests.helpers_scene import boxes_scene
+
+    # box centre (-0.25,-0.25,0.5), extent 0.5 -> NDC [-0.5,0]^2 -> uv [0.25,0.5]^2
+    sc, _, _ = boxes_scene(np.float32([[-0.25, -0.25, 0.5]]), np.float32([[0.5, 0.5, 0.2]]), 64, 64)
+    hs = orc.HostScene(sc)
+    cam = np.zeros(1, dtype=abi.CULL_CAMERA_DT)
+    cam["projection_view"][0] = np.eye(4, dtype=np.float32).reshape(16)
+    cam["position"][0] = (0.0, 0.0, 1.0)
+    cam["mesh_instance_count"] = 1
+    cam["resolution"][0] = (64, 64)
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    assert int(vis["total"][0]) == 1
+    clip = np.zeros(2, dtype=abi.CLIPMAP_DT)
+    clip["projection_view_mat"] = np.eye(4, dtype=np.float32).reshape(16)
+    clip["z_near"] = 0.01
+    size, levels, layers = 8, 4, 2
+
+    def pyramid(bits1):
+        lv = []
+        for l in range(levels):
+            s_ = size >> l
+            a = np.zeros((layers, s_, s_), dtype=np.uint8)
+            if l == 0:
+                a[1] = bits1
+            lv.append(a)
+        for l in range(1, levels):  # OR-downsample (any page present below)
+            p = lv[l - 1]
+            lv[l] = np.maximum(np.maximum(p[:, 0::2, 0::2], p[:, 0::2, 1::2]), np.maximum(p[:, 1::2, 0::2], p[:, 1::2, 1::2]))
+        return np.concatenate([a.reshape(-1) for a in lv])
+
+    # box extent = 0.25 * 8 = 2 pages -> mip = ceil(log2(2)) = 1 (4x4): corner taps at uv 0.25 / 0.5 -> texels 1 and 2
+    empty = np.zeros((size, size), dtype=np.uint8)
+    only_far = empty.copy(); only_far[7, 7] = 1          # page far from the box: mip-1 texel (3,3) -> not tapped
+    near = empty.copy(); near[2, 3] = 1                   # mip-1 texel (x=1,y=1) -> tapped by the tl corner
+    for bits, dirty, want in ((only_far, [1, 1], 0), (near, [1, 1], 1), (near, [1, 0], 0), (near, [0, 1], 1)):
+        got, cmd = orc.cull_meshlets_hpb(hs, mi, vis, cam, clip, dirty, pyramid(bits), size, levels)
+        assert int(cmd["x"][0]) == want and len(got) == want
+    # page_offset shifts the lookup (fract wraps): offset (+2 pages, 0) moves the taps to mip-1 texels x = 2 and 3
+    clip["page_offset"][1] = (2, 0)
+    got, cmd = orc.cull_meshlets_hpb(hs, mi, vis, cam, clip, [0, 1], pyramid(near), size, levels)
+    assert int(cmd["x"][0]) == 0
+    shifted = empty.copy(); shifted[2, 5] = 1             # mip-1 texel (x=2,y=1)
+    got, cmd = orc.cull_meshlets_hpb(hs, mi, vis, cam, clip, [0, 1], pyramid(shifted), size, levels)
+    assert int(cmd["x"][0]) == 1
