@@ -102,8 +102,8 @@ typedef struct OxcMeshLOD {
 /* SceneGPU.hpp:142-152 (64 B) */
 typedef struct OxcMesh {
   uint64_t vertex_positions; /* u16x4 per vertex (half3 + pad) */
-  uint64_t vertex_normals;
-  uint64_t texture_coords;
+  uint64_t vertex_normals;   /* u32 per vertex, 10:10:10 (scene.slang:486-489); 0 = none (read by oxc_decode_visbuffer only) */
+  uint64_t texture_coords;   /* u16x2 halves per vertex (scene.slang:491-497); 0 = none (Mesh::texture_coords == nullptr) */
   uint32_t vertex_count;
   uint32_t lod_count;
   uint64_t lods; /* OxcMeshLOD[lod_count] */
@@ -353,6 +353,38 @@ typedef struct OxcDrawIndirectCommand { uint32_t vertex_count, instance_count, f
 int oxc_cull_terrain(OxcContext* ctx, const OxcTerrainData* terrain, const float* patch_minmax_dev /* float2 per patch, row-major */,
                      const OxcCullCamera* camera, uint32_t cull_flags, uint32_t* visible_patches_dev,
                      uint32_t* patch_visibility_mask_dev, OxcDrawIndirectCommand* draw_cmd_dev, void* stream);
+
+/* Vis-buffer decode, geometry part: passes/visbuffer_decode.slang:42-183 via RendererInstance's
+ * "vis decode" pass.  Per pixel: texel -> (meshlet instance, triangle) (visbuffer.slang:31-36), triangle re-fetch
+ * (scene.slang:363-399), world positions, compute_partial_derivatives (:42-92: analytic perspective-correct
+ * barycentrics lambda and their per-pixel derivatives), gradient_of the vertex texture coordinates (:33-40) and the
+ * geometric world normal normalize(mul(lambda, to_world_normals)) (:146-147) oct-encoded (common/encoding.slang:17-21).
+ * The material evaluation (texture sampling, tangent frame from the sampled normal map, :118-183) needs the engine's
+ * material and image tables and is not part of this library.  The frame's oxc_cull_meshes must have run (it resolves
+ * LODs and pointers).  Exactly one of vis64_dev (our packed image) / vis32_dev (the reference's R32UI attachment).
+ * Targets are float4-per-pixel planes, any may be NULL:
+ *   lambda    = (lambda.xyz, status)  status 0: discarded (clear / terrain texel, :97-99), 1: decoded,
+ *                                     2: a vertex index >= Mesh::vertex_count (:115-117, zero output)
+ *   ddx / ddy = (d lambda / d pixel x|y .xyz, 0)
+ *   uv_normal = (uv.xy, oct(world_normal).xy)       uv_grad = (uv ddx.xy, uv ddy.xy)
+ * Meshes without normals / texture coordinates (OxcMesh::vertex_normals / texture_coords == 0) decode them as 0. */
+typedef struct OxcDecodeTargets {
+  float* lambda;
+  float* ddx;
+  float* ddy;
+  float* uv_normal;
+  float* uv_grad;
+} OxcDecodeTargets;
+int oxc_decode_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, const uint64_t* vis64_dev, const uint32_t* vis32_dev,
+                         uint32_t width, uint32_t height, const OxcDecodeTargets* targets /* host struct of device ptrs */,
+                         void* stream);
+
+/* Hierarchical page bitmap build: passes/rmvsm_downsample_hpb.slang:15-33 dispatched per level by
+ * Shadowmaps.cpp:331-366.  Level 0: byte = page is visible && backed && dirty (VSMPageState bits 1 | 4 | 2,
+ * rmvsm.slang:16-28) for every entry of the layers x size x size R32UI virtual page table; level k: 2x2 OR of
+ * level k-1.  Output layout == the hpb_dev input of oxc_cull_meshlets_hpb. */
+int oxc_build_hpb(OxcContext* ctx, const uint32_t* page_table_dev, uint32_t page_table_size, uint32_t layers,
+                  uint8_t* hpb_dev, uint32_t hpb_levels, void* stream);
 
 int oxc_get_outputs(OxcContext* ctx, OxcOutputs* out);
 

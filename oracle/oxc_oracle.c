@@ -695,6 +695,183 @@ void orc_cull_meshlets_hpb(const OrcScene* scene, const OxcMeshletInstance* mesh
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * passes/rmvsm_downsample_hpb.slang:15-33 via Shadowmaps.cpp:331-366: level 0 from the page table
+ * (cached = visible && backed && dirty, rmvsm.slang:16-28 [Flags] Visible=1 Dirty=2 Backed=4), level k
+ * from level k-1 with the shader's `(tl | tr | bl | br) == 1` (values are 0/1 bytes).
+ * hpb layout == oxc_cull_meshlets_hpb's: level l is layers x s_l x s_l bytes, s_l = max(1, size >> l).
+ * ---------------------------------------------------------------------------------------------- */
+void orc_build_hpb(const uint32_t* page_table, uint32_t size, uint32_t layers, uint8_t* hpb, uint32_t levels) {
+  size_t src_off = 0, dst_off = 0;
+  for (uint32_t l = 0; l < levels; l++) {
+    uint32_t s = size >> l; if (s < 1) s = 1;                /* Shadowmaps.cpp:342-346 */
+    uint32_t ps = l ? (size >> (l - 1)) : size; if (ps < 1) ps = 1;
+    for (uint32_t z = 0; z < layers; z++)
+      for (uint32_t y = 0; y < s; y++)
+        for (uint32_t x = 0; x < s; x++) {
+          uint8_t cached;
+          if (l == 0) {                                     /* :24-26 */
+            uint32_t page = page_table[((size_t)z * size + y) * size + x];
+            cached = (page & 1u) != 0 && (page & 4u) != 0 && (page & 2u) != 0;
+          } else {                                          /* :27-32; out-of-range loads return 0 (robust image access) */
+            const uint8_t* src = hpb + src_off + (size_t)z * ps * ps;
+            uint32_t x0 = x * 2, y0 = y * 2;
+            uint8_t tl = (x0 < ps && y0 < ps) ? src[(size_t)y0 * ps + x0] : 0;
+            uint8_t tr = (x0 < ps && y0 + 1 < ps) ? src[(size_t)(y0 + 1) * ps + x0] : 0;
+            uint8_t bl = (x0 + 1 < ps && y0 < ps) ? src[(size_t)y0 * ps + x0 + 1] : 0;
+            uint8_t br = (x0 + 1 < ps && y0 + 1 < ps) ? src[(size_t)(y0 + 1) * ps + x0 + 1] : 0;
+            cached = (uint8_t)((tl | tr | bl | br) == 1);
+          }
+          hpb[dst_off + ((size_t)z * s + y) * s + x] = cached;
+        }
+    src_off = dst_off;
+    dst_off += (size_t)layers * s * s;
+  }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * passes/visbuffer_decode.slang:42-183, geometry part: vis texel -> triangle re-fetch ->
+ * analytic barycentrics + screen-space derivatives (compute_partial_derivatives :42-92), interpolated
+ * texture coordinate with its gradients (:33-40,118-125 without the material's uv transform), geometric
+ * world normal (:146-147) oct-encoded (common/encoding.slang:17-21).  Material / texture sampling and the
+ * tangent frame built from it (:127-183) need the engine's material + image tables and stay out of scope.
+ * Canonical arithmetic as in oxc_oracle.h; `1.0 / x` and `a / b` are IEEE divisions.
+ * ---------------------------------------------------------------------------------------------- */
+static inline Vec3_f32 decode_normal_f32(uint32_t packed) { /* scene.slang:486-489 */
+  int32_t p = (int32_t)packed;
+  Vec3_f32 n = {(float)((p >> 20) & 1023) / 511.0f - 1.0f, (float)((p >> 10) & 1023) / 511.0f - 1.0f,
+                (float)(p & 1023) / 511.0f - 1.0f};
+  return n;
+}
+
+static inline void vec3_to_oct_f32(Vec3_f32 v, float out[2]) { /* common/encoding.slang:17-21 */
+  const float inv = 1.0f / ((fabsf(v.x) + fabsf(v.y)) + fabsf(v.z));
+  const float px = v.x * inv, py = v.y * inv;
+  if (v.z <= 0.0f) {
+    out[0] = (1.0f - fabsf(py)) * (px >= 0.0f ? 1.0f : -1.0f);
+    out[1] = (1.0f - fabsf(px)) * (py >= 0.0f ? 1.0f : -1.0f);
+  } else {
+    out[0] = px; out[1] = py;
+  }
+}
+
+void orc_decode_visbuffer(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, uint32_t total,
+                          const OxcCullCamera* cam, const uint32_t* vis32, uint32_t width, uint32_t height,
+                          float* lambda_out, float* ddx_out, float* ddy_out, float* uv_normal_out, float* uv_grad_out) {
+  const float* pv = cam->projection_view;
+  for (uint32_t y = 0; y < height; y++)
+    for (uint32_t x = 0; x < width; x++) {
+      const size_t pix = (size_t)y * width + x;
+      float L[4] = {0, 0, 0, 0}, DX[4] = {0, 0, 0, 0}, DY[4] = {0, 0, 0, 0}, UN[4] = {0, 0, 0, 0}, UG[4] = {0, 0, 0, 0};
+      const uint32_t texel = vis32[pix];                                                  /* :96 */
+      const uint32_t mii = (texel >> OXC_VIS_PRIMITIVE_BITS) & 0xFFFFFFu;                 /* visbuffer.slang:34 */
+      const uint32_t tri = texel & OXC_VIS_PRIMITIVE_MASK;
+      if (texel == 0xFFFFFFFFu || mii == 0xFFFFFEu || mii >= total) goto store;           /* :97-99 discard (+ range guard) */
+      {
+        const OxcMeshletInstance mi = meshlet_instances[mii];                             /* :103 */
+        const OxcMeshInstance inst = scene->mesh_instances[mi.mesh_instance_index];       /* :104 */
+        const OxcMesh* mesh = &scene->meshes[inst.mesh_index];                            /* :105 */
+        const float* world = scene->transforms[inst.transform_index].world;               /* :107 */
+        const OxcMeshLOD* lod = mesh_lod(scene, mesh, inst.lod_index);                    /* :108 */
+        const OxcMeshlet meshlet = ((const OxcMeshlet*)(scene->blob + lod->meshlets))[mi.meshlet_index]; /* :109 */
+        const uint32_t* micro = (const uint32_t*)(scene->blob + lod->local_triangle_indices);
+        const uint32_t* vidx = (const uint32_t*)(scene->blob + lod->indirect_vertex_indices);
+        const uint16_t* pos = (const uint16_t*)(scene->blob + mesh->vertex_positions);
+        uint32_t idx[3];
+        const uint32_t base = meshlet.local_triangle_index_offset + tri * 3;              /* scene.slang:366 */
+        for (int c = 0; c < 3; c++) idx[c] = vidx[meshlet.indirect_vertex_index_offset + micro_index(micro, base + (uint32_t)c)];
+        L[3] = 2.0f;
+        if (idx[0] > mesh->vertex_count - 1 || idx[1] > mesh->vertex_count - 1 || idx[2] > mesh->vertex_count - 1) goto store; /* :115-117 */
+        L[3] = 1.0f;
+        Vec4_f32 wp[3];
+        Vec3_f32 nrm[3];
+        float tc[3][2];
+        for (int c = 0; c < 3; c++) {
+          Vec4_f32 p = {orc_dequantize_half(pos[idx[c] * 4 + 0]), orc_dequantize_half(pos[idx[c] * 4 + 1]),
+                        orc_dequantize_half(pos[idx[c] * 4 + 2]), 1.0f};
+          wp[c] = mul_mv_f32(world, p);                                                   /* :121 to_world_positions */
+          if (mesh->vertex_normals) nrm[c] = decode_normal_f32(((const uint32_t*)(scene->blob + mesh->vertex_normals))[idx[c]]);
+          else { nrm[c].x = 0; nrm[c].y = 0; nrm[c].z = 0; }
+          if (mesh->texture_coords) {                                                     /* scene.slang:390-399 */
+            const uint16_t* t = (const uint16_t*)(scene->blob + mesh->texture_coords) + (size_t)idx[c] * 2;
+            tc[c][0] = orc_dequantize_half(t[0]); tc[c][1] = orc_dequantize_half(t[1]);
+          } else { tc[c][0] = 0; tc[c][1] = 0; }
+        }
+        /* fullscreen.slang:11-17: tex_coord at the pixel centre; NDC = tex_coord * 2 - 1 (:122) */
+        const float u = ((float)x + 0.5f) / (float)width, v = ((float)y + 0.5f) / (float)height;
+        const float ndcx = u * 2.0f - 1.0f, ndcy = v * 2.0f - 1.0f;
+        /* compute_partial_derivatives :42-92 */
+        float inv_w[3], nx[3], ny[3];
+        for (int c = 0; c < 3; c++) {
+          Vec4_f32 w1 = {wp[c].x, wp[c].y, wp[c].z, 1.0f};
+          Vec4_f32 cp = mul_mv_f32(pv, w1);                                               /* :45-47 */
+          inv_w[c] = 1.0f / cp.w;                                                         /* :50 */
+          nx[c] = cp.x * inv_w[c]; ny[c] = cp.y * inv_w[c];                               /* :51-53 */
+        }
+        /* :58 determinant(f32x2x2(ndc_2 - ndc_1, ndc_0 - ndc_1)) = a.x*b.y - a.y*b.x */
+        const float ax = nx[2] - nx[1], ay = ny[2] - ny[1], bx = nx[0] - nx[1], by = ny[0] - ny[1];
+        const float inv_det = 1.0f / (ax * by - ay * bx);
+        float ddx[3], ddy[3];
+        ddx[0] = ((ny[1] - ny[2]) * inv_det) * inv_w[0];                                  /* :60 */
+        ddx[1] = ((ny[2] - ny[0]) * inv_det) * inv_w[1];
+        ddx[2] = ((ny[0] - ny[1]) * inv_det) * inv_w[2];
+        ddy[0] = ((nx[2] - nx[1]) * inv_det) * inv_w[0];                                  /* :62 */
+        ddy[1] = ((nx[0] - nx[2]) * inv_det) * inv_w[1];
+        ddy[2] = ((nx[1] - nx[0]) * inv_det) * inv_w[2];
+        float ddx_sum = (ddx[0] * 1.0f + ddx[1] * 1.0f) + ddx[2] * 1.0f;                  /* :63 dot(v, 1.0) */
+        float ddy_sum = (ddy[0] * 1.0f + ddy[1] * 1.0f) + ddy[2] * 1.0f;                  /* :64 */
+        const float dvx = ndcx - nx[0], dvy = ndcy - ny[0];                               /* :66 */
+        const float interp_inv_w = (inv_w[0] + dvx * ddx_sum) + dvy * ddy_sum;            /* :67 */
+        const float interp_w = 1.0f / interp_inv_w;                                       /* :68 */
+        float lam[3];
+        lam[0] = interp_w * ((inv_w[0] + dvx * ddx[0]) + dvy * ddy[0]);                   /* :69-73 */
+        lam[1] = interp_w * (dvx * ddx[1] + dvy * ddy[1]);
+        lam[2] = interp_w * (dvx * ddx[2] + dvy * ddy[2]);
+        const float torx = 2.0f / cam->resolution[0], tory = 2.0f / cam->resolution[1];   /* :74 */
+        for (int c = 0; c < 3; c++) { ddx[c] = ddx[c] * torx; ddy[c] = ddy[c] * -tory; }  /* :75-76 */
+        ddx_sum = ddx_sum * torx; ddy_sum = ddy_sum * -tory;                              /* :77-78 */
+        const float interp_ddx_w = 1.0f / (interp_inv_w + ddx_sum);                       /* :80 */
+        const float interp_ddy_w = 1.0f / (interp_inv_w + ddy_sum);                       /* :81 */
+        for (int c = 0; c < 3; c++) {                                                     /* :82-83 */
+          ddx[c] = interp_ddx_w * (lam[c] * interp_inv_w + ddx[c]) - lam[c];
+          ddy[c] = interp_ddy_w * (lam[c] * interp_inv_w + ddy[c]) - lam[c];
+        }
+        for (int c = 0; c < 3; c++) { L[c] = lam[c]; DX[c] = ddx[c]; DY[c] = ddy[c]; }
+        /* gradient_of :33-40: mul(row vector, 3x2 matrix) */
+        for (int j = 0; j < 2; j++) {
+          UN[j] = (lam[0] * tc[0][j] + lam[1] * tc[1][j]) + lam[2] * tc[2][j];
+          UG[j] = (ddx[0] * tc[0][j] + ddx[1] * tc[1][j]) + ddx[2] * tc[2][j];
+          UG[2 + j] = (ddy[0] * tc[0][j] + ddy[1] * tc[1][j]) + ddy[2] * tc[2][j];
+        }
+        /* :146-147 world_normal = normalize(mul(lambda, to_world_normals(normals))); scene.slang:291-302,319-322 */
+        {
+          Vec3_f32 b0 = {world[0], world[1], world[2]}, b1 = {world[4], world[5], world[6]}, b2 = {world[8], world[9], world[10]};
+          Vec3_f32 r0 = cross3_f32(b1, b2), r1 = cross3_f32(b2, b0), r2 = cross3_f32(b0, b1);
+          Vec3_f32 wn[3];
+          for (int c = 0; c < 3; c++) {
+            wn[c].x = (r0.x * nrm[c].x + r1.x * nrm[c].y) + r2.x * nrm[c].z;
+            wn[c].y = (r0.y * nrm[c].x + r1.y * nrm[c].y) + r2.y * nrm[c].z;
+            wn[c].z = (r0.z * nrm[c].x + r1.z * nrm[c].y) + r2.z * nrm[c].z;
+          }
+          Vec3_f32 n = {(lam[0] * wn[0].x + lam[1] * wn[1].x) + lam[2] * wn[2].x,
+                        (lam[0] * wn[0].y + lam[1] * wn[1].y) + lam[2] * wn[2].y,
+                        (lam[0] * wn[0].z + lam[1] * wn[1].z) + lam[2] * wn[2].z};
+          const float len = length3_f32(n);
+          Vec3_f32 nn = {n.x / len, n.y / len, n.z / len};
+          vec3_to_oct_f32(nn, &UN[2]);                                                    /* :170 */
+        }
+      }
+    store:
+      for (int c = 0; c < 4; c++) {
+        if (lambda_out) lambda_out[pix * 4 + c] = L[c];
+        if (ddx_out) ddx_out[pix * 4 + c] = DX[c];
+        if (ddy_out) ddy_out[pix * 4 + c] = DY[c];
+        if (uv_normal_out) uv_normal_out[pix * 4 + c] = UN[c];
+        if (uv_grad_out) uv_grad_out[pix * 4 + c] = UG[c];
+      }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * passes/terrain_cull.slang:19-83; TerrainData::patch_corner / decode_height scene.slang:648-660
  * ---------------------------------------------------------------------------------------------- */
 void orc_cull_terrain(const OxcTerrainData* t, const float* patch_minmax, const OxcCullCamera* cam, uint32_t flags,

@@ -122,6 +122,17 @@ void orc_cull_meshlets_hpb(const OrcScene* scene, const OxcMeshletInstance* mesh
                            uint32_t* visible_indices, OxcDispatchIndirectCommand* cull_triangles_cmd);
 uint32_t orc_ceil_log2_f32(float x); /* ceil(log2(x)) clamped at 0 from below, evaluated on the float's bits */
 
+/* passes/rmvsm_downsample_hpb.slang:15-33 via Shadowmaps.cpp:331-366: page table (layers x size x size
+ * u32, rmvsm.slang VSMPageState bits) -> the R8UI pyramid oxc_cull_meshlets_hpb consumes. */
+void orc_build_hpb(const uint32_t* page_table, uint32_t size, uint32_t layers, uint8_t* hpb, uint32_t levels);
+
+/* passes/visbuffer_decode.slang:42-183, geometry part.  Five float4 planes (any may be NULL):
+ * lambda.xyz + status (0 discarded, 1 decoded, 2 vertex index out of range), ddx.xyz, ddy.xyz,
+ * (uv.xy, oct(world_normal).xy), (uv_ddx.xy, uv_ddy.xy). */
+void orc_decode_visbuffer(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, uint32_t total,
+                          const OxcCullCamera* cam, const uint32_t* vis32, uint32_t width, uint32_t height,
+                          float* lambda_out, float* ddx_out, float* ddy_out, float* uv_normal_out, float* uv_grad_out);
+
 /* passes/terrain_cull.slang:19-83 */
 void orc_cull_terrain(const OxcTerrainData* terrain, const float* patch_minmax, const OxcCullCamera* cam, uint32_t flags,
                       const OrcHiz* hiz, uint32_t* visible_patches, uint32_t* mask, OxcDrawIndirectCommand* draw_cmd);

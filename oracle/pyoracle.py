@@ -230,6 +230,36 @@ def cull_terrain(terrain, patch_minmax, cam, flags, hiz: Hiz, mask):
     return visible[: int(cmd["instance_count"][0])], cmd
 
 
+def hpb_layout(size, layers, levels):
+    """(offsets[levels], total bytes) of the pyramid: level l is layers x s_l x s_l bytes, s_l = max(1, size >> l)."""
+    offs, off = [], 0
+    for l in range(levels):
+        offs.append(off)
+        s = max(1, size >> l)
+        off += layers * s * s
+    return offs, off
+
+
+def build_hpb(page_table, levels):
+    """page_table: (layers, size, size) u32 -> flat pyramid bytes."""
+    pt = np.ascontiguousarray(page_table, dtype=np.uint32)
+    layers, size, _ = pt.shape
+    _, total = hpb_layout(size, layers, levels)
+    out = np.zeros(total, dtype=np.uint8)
+    lib().orc_build_hpb(_p(pt), C.c_uint32(size), C.c_uint32(layers), _p(out), C.c_uint32(levels))
+    return out
+
+
+def decode_visbuffer(hs, mi, total, cam, vis32):
+    """Five (H, W, 4) f32 planes: lambda(+status), ddx, ddy, uv_normal, uv_grad."""
+    v = np.ascontiguousarray(vis32, dtype=np.uint32)
+    h, w = v.shape
+    planes = [np.zeros((h, w, 4), dtype=np.float32) for _ in range(5)]
+    lib().orc_decode_visbuffer(hs.ref, _p(mi), C.c_uint32(total), _p(cam), _p(v), C.c_uint32(w), C.c_uint32(h),
+                               *[_p(x) for x in planes])
+    return dict(zip(("lambda_", "ddx", "ddy", "uv_normal", "uv_grad"), planes))
+
+
 def cpu_baseline_cull(hs, mi, total, cam, mode, n_threads):
     out = np.zeros(max(1, total), dtype=np.uint32)
     n = lib().orc_cpu_baseline_cull(hs.ref, _p(mi), C.c_uint32(total), _p(cam), C.c_int(mode), C.c_int(n_threads), _p(out))

@@ -116,6 +116,11 @@ MAX_VIEWS = 16
 VIS_PRIMITIVE_BITS = 8
 VIS_CLEAR = 0xFFFFFFFF
 
+# VSMPageState — Shaders/rmvsm.slang:16-28 ([Flags] enum)
+VSM_PAGE_VISIBLE = 1
+VSM_PAGE_DIRTY = 2
+VSM_PAGE_BACKED = 4
+
 
 class SceneDesc(C.Structure):
     """OxcSceneDesc"""
@@ -168,6 +173,12 @@ class Outputs(C.Structure):
         ("view_visible_counts", C.c_void_p),
         ("raster_triangle_count", C.c_void_p),
     ]
+
+
+class DecodeTargets(C.Structure):
+    """OxcDecodeTargets: device pointers of the five float4 planes (any may be NULL)"""
+
+    _fields_ = [("lambda_", C.c_void_p), ("ddx", C.c_void_p), ("ddy", C.c_void_p), ("uv_normal", C.c_void_p), ("uv_grad", C.c_void_p)]
 
 
 class OrcHiz(C.Structure):

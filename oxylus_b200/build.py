@@ -14,7 +14,7 @@ LIB = os.path.join(HERE, "liboxcull.so")
 SOURCES = [os.path.join(CSRC, "oxcull.cu"), os.path.join(CSRC, "host", "renderer_instance.cpp")]
 DEPS = SOURCES + [
     os.path.join(CSRC, f)
-    for f in ("oxc_types.cuh", "oxc_exact.cuh", "kernels_cull.cuh", "kernels_hiz.cuh", "kernels_tri.cuh")
+    for f in ("oxc_types.cuh", "oxc_exact.cuh", "oxc_filtered.cuh", "kernels_cull.cuh", "kernels_decode.cuh", "kernels_hiz.cuh", "kernels_tri.cuh")
 ] + [os.path.join(CSRC, "host", "renderer_instance.hpp"), os.path.join(os.path.dirname(HERE), "include", "oxcull.h")]
 
 NVCC_FLAGS = [

@@ -19,6 +19,7 @@ SYMBOLS = [
     "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_set_shard_auto", "oxc_cull_meshes",
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
+    "oxc_decode_visbuffer", "oxc_build_hpb",
     "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
 ]
@@ -70,6 +71,8 @@ def load(build_if_missing=True):
     lib.oxc_cull_meshlets_multiview.argtypes = [vp, vp, u32, i32, vp]
     lib.oxc_cull_meshlets_hpb.argtypes = [vp, vp, vp, vp, u32, vp, u32, u32, vp]
     lib.oxc_cull_terrain.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp]
+    lib.oxc_decode_visbuffer.argtypes = [vp, vp, vp, vp, u32, u32, C.POINTER(abi.DecodeTargets), vp]
+    lib.oxc_build_hpb.argtypes = [vp, vp, u32, u32, vp, u32, vp]
     lib.oxc_get_outputs.argtypes = [vp, C.POINTER(abi.Outputs)]
     lib.oxc_copy.argtypes = [vp, vp, vp, u64, i32, vp]
     lib.oxc_sync.argtypes = [vp, vp]
@@ -225,6 +228,15 @@ class Context:
         t = np.ascontiguousarray(terrain)
         _check(self.lib.oxc_cull_terrain(self.h, _ptr(t), _ptr(patch_minmax_dev), _ptr(cam), flags, _ptr(visible_patches_dev),
                                          _ptr(mask_dev), _ptr(draw_cmd_dev), self.stream), "oxc_cull_terrain")
+
+    def decode_visbuffer(self, cam, w, h, targets, vis64_dev=None, vis32_dev=None):
+        """targets: dict with any of lambda_, ddx, ddy, uv_normal, uv_grad -> device pointers (float4 planes)."""
+        t = abi.DecodeTargets(*[targets.get(k) for k in ("lambda_", "ddx", "ddy", "uv_normal", "uv_grad")])
+        _check(self.lib.oxc_decode_visbuffer(self.h, _ptr(cam), _ptr(vis64_dev), _ptr(vis32_dev), w, h, C.byref(t), self.stream),
+               "oxc_decode_visbuffer")
+
+    def build_hpb(self, page_table_dev, size, layers, hpb_dev, levels):
+        _check(self.lib.oxc_build_hpb(self.h, _ptr(page_table_dev), size, layers, _ptr(hpb_dev), levels, self.stream), "oxc_build_hpb")
 
     # ---- plumbing ----
     def sync(self):

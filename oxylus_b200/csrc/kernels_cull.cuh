@@ -149,8 +149,11 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __gri
       g.local_triangle_indices = reinterpret_cast<const uint32_t*>(lod->local_triangle_indices);
       g.indirect_vertex_indices = reinterpret_cast<const uint32_t*>(lod->indirect_vertex_indices);
       g.vertex_positions = reinterpret_cast<const uint2*>(mesh->vertex_positions);
+      g.vertex_normals = reinterpret_cast<const uint32_t*>(mesh->vertex_normals);
+      g.texture_coords = reinterpret_cast<const uint32_t*>(mesh->texture_coords);
       g.transform_index = inst.transform_index;
-      g.pad[0] = g.pad[1] = g.pad[2] = 0;
+      g.vertex_count = mesh->vertex_count;
+      g.pad[0] = g.pad[1] = 0;
       p.geom[mi] = g;
       p.counts[local] = meshlet_count;
     }

@@ -7,7 +7,7 @@
 //                                                            recomputes per meshlet (mvp, 6 planes,
 //                                                            normal matrix, scale) hoisted here; read
 //                                                            through L1 as warp-broadcast 128-bit loads
-//   InstGeom           I x 48 B                               resolved pointer chase for the triangle passes
+//   InstGeom           I x 64 B                               resolved pointer chase for the triangle passes
 //   visibility mask    ceil(M/32) x 4 B                       persistent across frames
 #pragma once
 #include <cuda_runtime.h>
@@ -37,10 +37,13 @@ struct __align__(16) InstGeom {
   const uint32_t* local_triangle_indices;
   const uint32_t* indirect_vertex_indices;
   const uint2* vertex_positions; // u16x4
+  const uint32_t* vertex_normals; // 10:10:10 packed (scene.slang:486-489); null when the mesh has none
+  const uint32_t* texture_coords; // half2 per vertex (scene.slang:491-497); null when the mesh has none
   uint32_t transform_index;
-  uint32_t pad[3];
+  uint32_t vertex_count;          // Mesh::vertex_count (visbuffer_decode.slang:115)
+  uint32_t pad[2];
 };
-static_assert(sizeof(InstGeom) == 48, "InstGeom");
+static_assert(sizeof(InstGeom) == 64, "InstGeom");
 
 // Per view, per mesh instance (multi-view cull): just the six planes.
 struct __align__(16) InstPlanes {

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "kernels_cull.cuh"
+#include "kernels_decode.cuh"
 #include "kernels_hiz.cuh"
 #include "kernels_tri.cuh"
 
@@ -47,6 +48,8 @@ __global__ void k_rebase_meshes(OxcMesh* meshes, uint32_t n, uint64_t base) {
   if (i >= n) return;
   OxcMesh m = meshes[i];
   m.vertex_positions += base;
+  if (m.vertex_normals) m.vertex_normals += base;  // 0 = the mesh has none (Mesh::vertex_normals == nullptr)
+  if (m.texture_coords) m.texture_coords += base;  // 0 = none (scene.slang:354-356,390-392)
   m.lods += base;
   OxcMeshLOD* lods = reinterpret_cast<OxcMeshLOD*>(m.lods);
   for (uint32_t l = 0; l < m.lod_count && l < OXC_MESH_MAX_LODS; l++) {
@@ -698,6 +701,62 @@ int oxc_cull_terrain(OxcContext* c, const OxcTerrainData* terrain, const float* 
   LAUNCHED();
   const uint32_t n = terrain->patch_count[0] * terrain->patch_count[1];
   if (n) { k_cull_terrain<<<(n + 255) / 256, 256, 0, s>>>(p); LAUNCHED(); }
+  return OXC_OK;
+}
+
+int oxc_decode_visbuffer(OxcContext* c, const OxcCullCamera* cam, const uint64_t* vis64_dev, const uint32_t* vis32_dev,
+                         uint32_t w, uint32_t h, const OxcDecodeTargets* t, void* stream) {
+  if (!c || !cam || !t) return fail(OXC_E_INVALID, "null argument");
+  if ((vis64_dev == nullptr) == (vis32_dev == nullptr)) return fail(OXC_E_INVALID, "exactly one of vis64_dev / vis32_dev");
+  if (!c->scene_set) return fail(OXC_E_STATE, "oxc_set_scene first");
+  if (w == 0 || h == 0) return OXC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  int rc = refresh_inst_cache(c, cam, s); // world rows / normal-matrix rows of the frame's mesh instances
+  if (rc != OXC_OK) return rc;
+  DecodeParams p{};
+  p.vis64 = reinterpret_cast<const unsigned long long*>(vis64_dev); p.vis32 = vis32_dev;
+  p.meshlet_instances = c->d_meshlet_instances; p.vis = c->d_vis; p.inst = c->d_inst; p.geom = c->d_geom; p.id_base = c->id_base;
+  p.lambda = reinterpret_cast<float4*>(t->lambda); p.ddx = reinterpret_cast<float4*>(t->ddx); p.ddy = reinterpret_cast<float4*>(t->ddy);
+  p.uv_normal = reinterpret_cast<float4*>(t->uv_normal); p.uv_grad = reinterpret_cast<float4*>(t->uv_grad);
+  const float* m = cam->projection_view; // column-major: row i = (m[i], m[4+i], m[8+i], m[12+i])
+  for (int i = 0; i < 4; i++) p.pv_row[i] = make_float4(m[i], m[4 + i], m[8 + i], m[12 + i]);
+  p.res_x = cam->resolution[0]; p.res_y = cam->resolution[1];
+  p.width = w; p.height = h;
+  const dim3 grid((w + DECODE_TX - 1) / DECODE_TX, (h + DECODE_TY - 1) / DECODE_TY);
+  k_decode_visbuffer<<<grid, dim3(DECODE_TX, DECODE_TY), 0, s>>>(p);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+int oxc_build_hpb(OxcContext* c, const uint32_t* page_table_dev, uint32_t size, uint32_t layers, uint8_t* hpb_dev, uint32_t levels,
+                  void* stream) {
+  if (!c || !page_table_dev || !hpb_dev) return fail(OXC_E_INVALID, "null argument");
+  if (size == 0 || layers == 0 || levels == 0 || levels > 16) return fail(OXC_E_INVALID, "bad hpb shape");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  const size_t smem = (size_t)size * size + (size_t)(size / 2 + 1) * (size / 2 + 1);
+  if (size <= 256) {
+    static bool attr_set = false;
+    if (!attr_set && smem > 48 * 1024) {
+      CK(cudaFuncSetAttribute(k_hpb_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+      attr_set = true;
+    }
+    HpbBuildParams p{page_table_dev, hpb_dev, size, layers, levels};
+    k_hpb_fused<<<layers, 256, smem, s>>>(p);
+    LAUNCHED();
+    return OXC_OK;
+  }
+  size_t src_off = 0, dst_off = 0;
+  for (uint32_t l = 0; l < levels; l++) { // Shadowmaps.cpp:338-360
+    const uint32_t sl = (size >> l) ? (size >> l) : 1u, ps = l ? ((size >> (l - 1)) ? (size >> (l - 1)) : 1u) : size;
+    const size_t n = (size_t)layers * sl * sl;
+    const uint32_t grid = (uint32_t)((n + 255) / 256 < (size_t)c->sm_count * 8 ? (n + 255) / 256 : (size_t)c->sm_count * 8);
+    k_hpb_level<<<grid ? grid : 1, 256, 0, s>>>(page_table_dev, hpb_dev + src_off, hpb_dev + dst_off, ps, sl, layers, l == 0);
+    LAUNCHED();
+    src_off = dst_off;
+    dst_off += n;
+  }
   return OXC_OK;
 }
 

@@ -254,6 +254,13 @@ def _build_unique_meshes(seed, counts, lod_counts, ragged):
 
     pos_q = np.zeros((total, _VERTS, 4), dtype=np.uint16)
     pos_q[:, :, :3] = quantize_half(pos)
+    # vertex attributes the vis-buffer decode reads (AssetManager_GLTF.cpp:579-581 packing): analytic normal of the
+    # height field, 10:10:10 unorm (scene.slang:486-489 decodes c / 511 - 1); uv = grid parameter as half2
+    nv = nrm[:, None, :] - (2.0 * curv[:, None] * u)[:, :, None] * t[:, None, :] - (2.0 * curv[:, None] * v)[:, :, None] * b[:, None, :]
+    nv /= np.maximum(np.linalg.norm(nv, axis=2, keepdims=True), 1e-30)
+    nq = np.clip(np.rint((nv + 1.0) * 511.0), 0, 1022).astype(np.uint32)
+    normals_q = (nq[:, :, 0] << 20) | (nq[:, :, 1] << 10) | nq[:, :, 2]
+    uv_q = quantize_half(np.stack([u + 0.5, v + 0.5], axis=2).astype(np.float32))  # total x 49 x 2 u16
 
     # --- pack the blob ---
     meshes = np.zeros(n_mesh, dtype=abi.MESH_DT)
@@ -276,6 +283,8 @@ def _build_unique_meshes(seed, counts, lod_counts, ragged):
         n_all = sum(lod_meshlets[m])
         sl = slice(cursor, cursor + n_all)
         meshes[m]["vertex_positions"] = put(pos_q[sl].reshape(-1, 4))
+        meshes[m]["vertex_normals"] = put(normals_q[sl].reshape(-1))
+        meshes[m]["texture_coords"] = put(uv_q[sl].reshape(-1, 2))
         meshes[m]["vertex_count"] = n_all * _VERTS
         meshes[m]["lod_count"] = lod_counts[m]
         lods = np.zeros(int(lod_counts[m]), dtype=abi.MESH_LOD_DT)

@@ -44,6 +44,11 @@ def generate():
             ntri_early=r["ntri_early"], ntri_late=r["ntri_late"],
             first_late=[int(x) for x in np.sort(r["visible"][e:e + l])[:8]],
         ))
+    # vis-buffer decode of the last frame (NaN-free by construction of the scene; hashed as raw bits)
+    v32, _ = orc.resolve(r["vis64"])
+    dec = orc.decode_visbuffer(hs, r["meshlet_instances"], int(r["visibility"]["total"][0]), cam, v32)
+    frames[-1]["decode_sha"] = {k: sha(v) for k, v in dec.items()}
+    frames[-1]["decoded_pixels"] = int((dec["lambda_"][:, :, 3] == 1.0).sum())
     return dict(scene=SCENE, scene_blob_sha=sha(sc.blob), transforms_sha=sha(sc.transforms["world"]), frames=frames)
 
 

@@ -4,7 +4,7 @@ import numpy as np
 from oxylus_b200 import abi, synth
 
 
-def quad_scene(width, height, depth_a=0.5, depth_b=0.5):
+def quad_scene(width, height, depth_a=0.5, depth_b=0.5, attributes=False):
     """One mesh, one meshlet: a quad (2 triangles, 4 vertices) spanning x,y in [-0.5,0.5] in a clip space where
     projection_view = diag(1,1,1,1) (so clip == local, w = 1).  Winding is front-facing (negative xyw determinant)."""
     pos = np.array([[-0.5, -0.5, depth_a], [0.5, -0.5, depth_a], [0.5, 0.5, depth_b], [-0.5, 0.5, depth_b]], dtype=np.float32)
@@ -30,6 +30,9 @@ def quad_scene(width, height, depth_a=0.5, depth_b=0.5):
     mesh["vertex_positions"] = put(pq)
     mesh["vertex_count"] = 4
     mesh["lod_count"] = 1
+    if attributes:  # normals (0,0,1) packed 10:10:10 (scene.slang:486-489), uv = xy + 0.5 as half2
+        mesh["vertex_normals"] = put(np.full(4, (511 << 20) | (511 << 10) | 1022, dtype=np.uint32))
+        mesh["texture_coords"] = put(synth.quantize_half(pos[:, :2] + np.float32(0.5)))
     meshlet = np.zeros(1, dtype=abi.MESHLET_DT)
     meshlet["vertex_count"] = 4
     meshlet["triangle_count"] = 2

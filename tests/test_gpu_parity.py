@@ -613,3 +613,135 @@ def test_cull_meshlets_hpb_parity(capi, orc):
     assert 0 < n_clip
     ctx.free(hpb_dev)
     ctx.close()
+
+
+def _assert_planes_equal(got, ref, name):
+    """bit-exact, except that NaNs only have to be NaNs (x86 and PTX disagree on the default NaN's sign / payload)"""
+    g, r = got.view(np.uint32), ref.view(np.uint32)
+    nan_g, nan_r = np.isnan(got), np.isnan(ref)
+    np.testing.assert_array_equal(nan_g, nan_r, err_msg=name)
+    np.testing.assert_array_equal(np.where(nan_g, 0, g), np.where(nan_r, 0, r), err_msg=name)
+
+
+def _decode_gpu(ctx, cam, w, h, vis64_dev=None, vis32_dev=None, planes=("lambda_", "ddx", "ddy", "uv_normal", "uv_grad")):
+    dev = {k: ctx.alloc(w * h * 16) for k in planes}
+    ctx.decode_visbuffer(cam, w, h, dev, vis64_dev=vis64_dev, vis32_dev=vis32_dev)
+    out = {k: ctx.download(p, np.float32, w * h * 4).reshape(h, w, 4) for k, p in dev.items()}
+    for p in dev.values():
+        ctx.free(p)
+    return out
+
+
+def test_decode_visbuffer_parity(capi, orc, scene):
+    """visbuffer_decode.slang (geometry part): barycentrics, derivatives, uv (+ gradients), oct normal — every float
+    bit-exact against the oracle, from the packed 64-bit image and from the resolved R32UI attachment; discarded
+    texels (clear, terrain sentinel, out-of-range instance) produce zeros."""
+    hs = orc.HostScene(scene)
+    ctx = make_ctx(capi, scene)
+    w, h = scene.width, scene.height
+    vis_dev = ctx.alloc(w * h * 8)
+    occ_dev = ctx.alloc(w * h * 4)
+    ctx.upload(occ_dev, scene.occluder_depth)
+    mask_ref = np.zeros(ctx.out.visibility_mask_words, dtype=np.uint32)
+    for f in range(2):
+        cam = scene.camera(2.0 * f)
+        ref = orc.frame(hs, cam, w, h, mask_ref, scene.occluder_depth)
+        got = _frame_gpu(capi, ctx, scene, cam, occ_dev, vis_dev)
+        np.testing.assert_array_equal(got["vis64"], ref["vis64"])
+    total = int(ref["visibility"]["total"][0])
+    v32, _ = orc.resolve(ref["vis64"])
+    want = orc.decode_visbuffer(hs, ref["meshlet_instances"], total, cam, v32)
+    assert (want["lambda_"][:, :, 3] == 1.0).sum() > 100
+    dec = _decode_gpu(ctx, cam, w, h, vis64_dev=vis_dev)
+    for k in want:
+        _assert_planes_equal(dec[k], want[k], k)
+    # R32UI input + hostile texels + a subset of planes
+    v32b = v32.copy()
+    v32b[0, :7] = [(0xFFFFFE << 8) | 5, ((total + 3) << 8) | 1, (total << 8), 0xFFFFFF00, ((total - 1) << 8), 0, 0xFFFFFFFF]
+    want = orc.decode_visbuffer(hs, ref["meshlet_instances"], total, cam, v32b)
+    v32_dev = ctx.alloc(w * h * 4)
+    ctx.upload(v32_dev, v32b)
+    dec = _decode_gpu(ctx, cam, w, h, vis32_dev=v32_dev, planes=("lambda_", "uv_normal"))
+    for k in dec:
+        _assert_planes_equal(dec[k], want[k], k)
+    with pytest.raises(capi.OxcError):
+        ctx.decode_visbuffer(cam, w, h, {}, vis64_dev=vis_dev, vis32_dev=v32_dev)
+    for p in (vis_dev, occ_dev, v32_dev):
+        ctx.free(p)
+    ctx.close()
+
+
+def test_decode_visbuffer_full_size(capi, orc):
+    """configs[1] at full size: decode of the steady-state 1920x1080 frame, bit-exact; also meshes without vertex
+    attributes (null pointers) and the vertex-index range check."""
+    import os
+
+    sc = synth.make_scene(1_000_000, config_index=2, width=1920, height=1080)
+    hs = orc.HostScene(sc)
+    r = capi.Renderer(0, sc)
+    r.set_external_depth(sc.occluder_depth)
+    mask_ref = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    threads = min(64, os.cpu_count() or 1)
+    cam = sc.camera(0.0)
+    for f in range(2):
+        ref = orc.cpu_frame(hs, cam, sc.width, sc.height, mask_ref, sc.occluder_depth, threads)
+        got = r.render(cam, None)
+    v32, _ = orc.resolve(ref["vis64"])
+    np.testing.assert_array_equal(got["vis32"], v32)
+    total = int(ref["visibility"]["total"][0])
+    want = orc.decode_visbuffer(hs, ref["meshlet_instances"], total, cam, v32)
+    ctx = r.ctx
+    v32_dev = ctx.alloc(v32.nbytes)
+    ctx.upload(v32_dev, v32)
+    dec = _decode_gpu(ctx, cam, sc.width, sc.height, vis32_dev=v32_dev)
+    assert (dec["lambda_"][:, :, 3] == 1.0).sum() > 200_000
+    for k in want:
+        _assert_planes_equal(dec[k], want[k], k)
+    ctx.free(v32_dev)
+    r.close()
+
+
+def test_decode_null_attributes_and_index_guard(capi, orc):
+    from tests.helpers_scene import quad_scene
+
+    W = H = 16
+    for attributes, vertex_count in ((False, 4), (True, 4), (True, 2)):
+        sc, cam = quad_scene(W, H, attributes=attributes)
+        sc.meshes["vertex_count"] = vertex_count
+        hs = orc.HostScene(sc)
+        ctx = make_ctx(capi, sc)
+        mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+        ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+        v32 = np.full((H, W), 0xFFFFFFFF, dtype=np.uint32)
+        v32[4:12, 4:12] = np.arange(64).reshape(8, 8) % 2
+        want = orc.decode_visbuffer(hs, mi, 1, cam, v32)
+        v32_dev = ctx.alloc(v32.nbytes)
+        ctx.upload(v32_dev, v32)
+        dec = _decode_gpu(ctx, cam, W, H, vis32_dev=v32_dev)
+        for k in want:
+            _assert_planes_equal(dec[k], want[k], f"{k} attributes={attributes} vertex_count={vertex_count}")
+        assert (dec["lambda_"][4:12, 4:12, 3] == (1.0 if vertex_count == 4 else 2.0)).all()
+        ctx.free(v32_dev)
+        ctx.close()
+
+
+def test_build_hpb_parity(capi, orc):
+    """rmvsm_downsample_hpb.slang: page table -> hierarchical page bitmap, fused single-launch path (size <= 256) and
+    the per-level path, exact; the result drives oxc_cull_meshlets_hpb identically to the oracle's pyramid."""
+    sc = synth.make_scene(2000, config_index=2, width=640, height=360, n_unique_meshes=8)
+    ctx = make_ctx(capi, sc)
+    rng = np.random.default_rng(23)
+    for size, layers, levels in ((128, 10, 8), (64, 3, 7), (256, 2, 9), (512, 2, 10), (1, 1, 1), (4, 2, 5), (96, 1, 4)):
+        pt = (rng.integers(0, 32, size=(layers, size, size)).astype(np.uint32)
+              | (rng.integers(0, 65536, size=(layers, size, size)).astype(np.uint32) << 16))
+        pt[rng.random(pt.shape) < 0.7] &= ~np.uint32(1)  # most pages invisible: sparse pyramid like a real frame
+        want = orc.build_hpb(pt, levels)
+        pt_dev, hpb_dev = ctx.alloc(pt.nbytes), ctx.alloc(want.nbytes)
+        ctx.upload(pt_dev, pt)
+        ctx.upload(hpb_dev, np.full(want.nbytes, 0xAB, dtype=np.uint8))
+        ctx.build_hpb(pt_dev, size, layers, hpb_dev, levels)
+        got = ctx.download(hpb_dev, np.uint8, want.nbytes)
+        np.testing.assert_array_equal(got, want, err_msg=f"size {size} layers {layers} levels {levels}")
+        ctx.free(pt_dev)
+        ctx.free(hpb_dev)
+    ctx.close()
