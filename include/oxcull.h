@@ -440,6 +440,34 @@ int oxr_submit(OxrRenderer* r, const OxcCullCamera* camera, uint32_t* vis32_host
                uint32_t* visible_indices_host, uint32_t visible_indices_capacity, int* ticket);
 int oxr_wait(OxrRenderer* r, int ticket, OxrFrameResult* result);
 
+/* ------------------------------------------------------------------------------------------------
+ * oxb_* — mesh builder: host-side producer of the blob layout above, mirroring build_gltf_mesh
+ * (Oxylus/src/Asset/AssetManager_GLTF.cpp:481-771) after the glTF accessors are read.  Pure host code (no CUDA).
+ * The four meshoptimizer v1.2 calls of the reference (not vendored in /root/reference) are restated from their
+ * published definitions — fetch remap, quantizeHalf, quantizeSnorm, computeMeshletBounds' normal cone —; the spatial
+ * clusteriser (meshopt_buildMeshlets) and the simplifier are NOT: meshlets come from a linear scan of the index buffer
+ * (<= 64 vertices, <= 64 triangles, Model.hpp:27-28) and coarser LODs are caller-supplied index buffers.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OxbMeshInput {
+  const float* positions;  /* vertex_count x 3 */
+  const float* normals;    /* vertex_count x 3, or NULL */
+  const float* texcoords;  /* vertex_count x 2, or NULL */
+  uint32_t vertex_count;
+  uint32_t lod_count;      /* 1..OXC_MESH_MAX_LODS */
+  const uint32_t* lod_indices[OXC_MESH_MAX_LODS]; /* triangle lists in input vertex numbering; [0] = full detail */
+  uint32_t lod_index_counts[OXC_MESH_MAX_LODS];
+  float lod_errors[OXC_MESH_MAX_LODS];            /* MeshLOD::error (cull_meshes.slang:35-57 LOD selection) */
+} OxbMeshInput;
+typedef struct OxbMesh OxbMesh;
+const char* oxb_last_error(void);
+int oxb_build_mesh(const OxbMeshInput* in, OxbMesh** out);
+uint64_t oxb_mesh_blob_size(const OxbMesh* m);            /* multiple of 16 */
+uint32_t oxb_mesh_lod0_meshlet_count(const OxbMesh* m);   /* for MeshInstance::meshlet_instance_visibility_offset sums, Scene.cpp:1255-1260 */
+/* Copies the mesh's blob to dst (= scene blob + base_offset, 16-byte aligned) and writes the OxcMesh record with every
+ * offset (also inside the copied MeshLOD table) rebased by base_offset: the tables OxcSceneDesc expects. */
+int oxb_mesh_emit(const OxbMesh* m, uint64_t base_offset, uint8_t* dst, OxcMesh* mesh_out);
+void oxb_mesh_free(OxbMesh* m);
+
 #ifdef __cplusplus
 }
 #endif

@@ -181,6 +181,24 @@ class DecodeTargets(C.Structure):
     _fields_ = [("lambda_", C.c_void_p), ("ddx", C.c_void_p), ("ddy", C.c_void_p), ("uv_normal", C.c_void_p), ("uv_grad", C.c_void_p)]
 
 
+MESH_MAX_LODS = 8
+
+
+class MeshInput(C.Structure):
+    """OxbMeshInput"""
+
+    _fields_ = [
+        ("positions", C.c_void_p),
+        ("normals", C.c_void_p),
+        ("texcoords", C.c_void_p),
+        ("vertex_count", C.c_uint32),
+        ("lod_count", C.c_uint32),
+        ("lod_indices", C.c_void_p * MESH_MAX_LODS),
+        ("lod_index_counts", C.c_uint32 * MESH_MAX_LODS),
+        ("lod_errors", C.c_float * MESH_MAX_LODS),
+    ]
+
+
 class OrcHiz(C.Structure):
     """OrcHiz (oracle/oxc_oracle.h) — also used as a plain layout helper"""
 

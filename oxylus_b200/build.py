@@ -11,7 +11,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "liboxcull.so")
 
-SOURCES = [os.path.join(CSRC, "oxcull.cu"), os.path.join(CSRC, "host", "renderer_instance.cpp")]
+SOURCES = [os.path.join(CSRC, "oxcull.cu"), os.path.join(CSRC, "host", "renderer_instance.cpp"),
+           os.path.join(CSRC, "host", "mesh_builder.cpp")]
 DEPS = SOURCES + [
     os.path.join(CSRC, f)
     for f in ("oxc_types.cuh", "oxc_exact.cuh", "oxc_filtered.cuh", "kernels_cull.cuh", "kernels_decode.cuh", "kernels_hiz.cuh", "kernels_tri.cuh")
@@ -22,7 +23,7 @@ NVCC_FLAGS = [
     "-O3", "-lineinfo", "-std=c++17",
     "--fmad=false",          # canonical arithmetic: no fma contraction (oracle/oxc_oracle.h)
     "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-shared",
     "-Xptxas", "-v",
 ]
 

@@ -21,6 +21,7 @@ SYMBOLS = [
     "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
     "oxc_decode_visbuffer", "oxc_build_hpb",
     "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
+    "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
 ]
 
@@ -79,6 +80,15 @@ def load(build_if_missing=True):
     lib.oxc_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
     lib.oxc_device_free.argtypes = [vp, vp]
     lib.oxc_debug_dequantize_half.argtypes = [vp, vp, vp, vp]
+    lib.oxb_last_error.restype = C.c_char_p
+    lib.oxb_build_mesh.argtypes = [C.POINTER(abi.MeshInput), C.POINTER(vp)]
+    lib.oxb_mesh_blob_size.argtypes = [vp]
+    lib.oxb_mesh_blob_size.restype = u64
+    lib.oxb_mesh_lod0_meshlet_count.argtypes = [vp]
+    lib.oxb_mesh_lod0_meshlet_count.restype = u32
+    lib.oxb_mesh_emit.argtypes = [vp, u64, vp, vp]
+    lib.oxb_mesh_free.argtypes = [vp]
+    lib.oxb_mesh_free.restype = None
     lib.oxr_create.argtypes = [i32, C.POINTER(abi.CreateInfo), u32, u32, C.POINTER(vp)]
     lib.oxr_destroy.argtypes = [vp]
     lib.oxr_destroy.restype = None
@@ -108,6 +118,76 @@ def _ptr(a):
     if isinstance(a, np.ndarray):
         return C.c_void_p(a.ctypes.data)
     return C.c_void_p(int(a))
+
+
+class BuiltMesh:
+    """OxbMesh wrapper: one mesh run through the host-side builder (oxb_build_mesh).  lods = [(indices, error), ...],
+    LOD 0 first.  Host-only: works without a GPU."""
+
+    def __init__(self, positions, lods, normals=None, texcoords=None):
+        self.lib = load()
+        pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+        nrm = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        tc = None if texcoords is None else np.ascontiguousarray(texcoords, dtype=np.float32).reshape(-1, 2)
+        idx = [np.ascontiguousarray(i, dtype=np.uint32).reshape(-1) for i, _ in lods]
+        mi = abi.MeshInput()
+        mi.positions, mi.normals, mi.texcoords = _ptr(pos), _ptr(nrm), _ptr(tc)
+        mi.vertex_count, mi.lod_count = len(pos), len(lods)
+        for l, (a, (_, err)) in enumerate(zip(idx, lods)):
+            mi.lod_indices[l] = a.ctypes.data
+            mi.lod_index_counts[l] = a.size
+            mi.lod_errors[l] = float(err)
+        h = C.c_void_p()
+        rc = self.lib.oxb_build_mesh(C.byref(mi), C.byref(h))
+        if rc != OK:
+            raise OxcError(f"oxb_build_mesh failed ({rc}): {self.lib.oxb_last_error().decode()}")
+        self.h = h
+        self.blob_size = int(self.lib.oxb_mesh_blob_size(h))
+        self.lod0_meshlet_count = int(self.lib.oxb_mesh_lod0_meshlet_count(h))
+
+    def emit(self, base_offset, dst: np.ndarray):
+        """copies the blob into dst (uint8 view at scene_blob[base_offset:]) and returns the rebased MESH_DT record"""
+        assert dst.dtype == np.uint8 and dst.size >= self.blob_size
+        rec = np.zeros(1, dtype=abi.MESH_DT)
+        rc = self.lib.oxb_mesh_emit(self.h, base_offset, _ptr(dst), _ptr(rec))
+        if rc != OK:
+            raise OxcError(f"oxb_mesh_emit failed ({rc}): {self.lib.oxb_last_error().decode()}")
+        return rec
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.oxb_mesh_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def assemble_scene(built, mesh_of_instance, transforms, width, height, transform_index=None, seed=0):
+    """Scene tables from builder output (the shape Scene::runtime_update hands over, Scene.cpp:1226-1290): one blob of
+    all meshes, mesh instances with LOD-0 prefix sums as visibility offsets (Scene.cpp:1255-1260)."""
+    from . import synth
+
+    bases, off = [], 0
+    for b in built:
+        bases.append(off)
+        off += b.blob_size
+    blob = np.zeros(max(16, off), dtype=np.uint8)
+    meshes = np.zeros(len(built), dtype=abi.MESH_DT)
+    for i, b in enumerate(built):
+        meshes[i] = b.emit(bases[i], blob[bases[i]:])[0]
+    mesh_of_instance = np.asarray(mesh_of_instance, dtype=np.uint32)
+    inst = np.zeros(len(mesh_of_instance), dtype=abi.MESH_INSTANCE_DT)
+    inst["mesh_index"] = mesh_of_instance
+    inst["transform_index"] = np.arange(len(inst)) if transform_index is None else transform_index
+    lod0 = np.array([b.lod0_meshlet_count for b in built], dtype=np.int64)[mesh_of_instance]
+    inst["meshlet_instance_visibility_offset"] = np.concatenate([[0], np.cumsum(lod0)[:-1]]) if len(inst) else []
+    xf = np.zeros(len(transforms), dtype=abi.TRANSFORM_DT)
+    xf["world"] = np.asarray(transforms, dtype=np.float32).reshape(len(transforms), 16)
+    return synth.Scene(meshes, inst, xf, blob, int(lod0.sum()), width, height, seed)
 
 
 class Context:

@@ -304,6 +304,28 @@ int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
     return fail(OXC_E_CAPACITY, "mesh_instance_count %u > max_mesh_instances %u", sc->mesh_instance_count, c->info.max_mesh_instances);
   if (sc->mesh_count == 0 || !sc->meshes || !sc->blob || !sc->transforms || (sc->mesh_instance_count && !sc->mesh_instances))
     return fail(OXC_E_INVALID, "scene tables missing");
+  // Layout checks on the host tables (the kernels use 128-bit loads of Meshlet / MeshletBounds records and 64-bit
+  // loads of vertex positions; a misaligned or out-of-range offset must be an error here, not a device fault later).
+  for (uint32_t m = 0; m < sc->mesh_count; m++) {
+    const OxcMesh& me = sc->meshes[m];
+    if (me.lod_count == 0 || me.lod_count > OXC_MESH_MAX_LODS) return fail(OXC_E_INVALID, "mesh %u: lod_count %u not in 1..%d", m, me.lod_count, OXC_MESH_MAX_LODS);
+    if ((me.vertex_positions & 7u) || (me.vertex_normals & 3u) || (me.texture_coords & 3u) || (me.lods & 7u))
+      return fail(OXC_E_INVALID, "mesh %u: vertex_positions / lods need 8-byte, normals / texcoords 4-byte aligned blob offsets", m);
+    if (me.lods + (uint64_t)me.lod_count * sizeof(OxcMeshLOD) > sc->blob_size || me.vertex_positions + (uint64_t)me.vertex_count * 8u > sc->blob_size)
+      return fail(OXC_E_INVALID, "mesh %u: offsets outside the blob", m);
+    const OxcMeshLOD* lods = reinterpret_cast<const OxcMeshLOD*>(sc->blob + me.lods);
+    for (uint32_t l = 0; l < me.lod_count; l++) {
+      OxcMeshLOD d;
+      memcpy(&d, &lods[l], sizeof d);
+      if ((d.meshlets & 15u) || (d.meshlet_bounds & 15u) || (d.local_triangle_indices & 3u) || (d.indirect_vertex_indices & 3u))
+        return fail(OXC_E_INVALID, "mesh %u lod %u: meshlets / meshlet_bounds need 16-byte, index arrays 4-byte aligned blob offsets", m, l);
+      if (d.meshlets + (uint64_t)d.meshlet_count * sizeof(OxcMeshlet) > sc->blob_size ||
+          d.meshlet_bounds + (uint64_t)d.meshlet_count * sizeof(OxcMeshletBounds) > sc->blob_size ||
+          d.local_triangle_indices + (uint64_t)d.local_triangle_indices_count > sc->blob_size ||
+          d.indirect_vertex_indices + (uint64_t)d.indirect_vertex_indices_count * 4u > sc->blob_size)
+        return fail(OXC_E_INVALID, "mesh %u lod %u: arrays outside the blob", m, l);
+    }
+  }
   if (sc->mesh_count > c->mesh_cap) {
     CK(cudaFree(c->d_meshes)); c->d_meshes = nullptr;
     CK(cudaMalloc(&c->d_meshes, (size_t)sc->mesh_count * sizeof(OxcMesh)));

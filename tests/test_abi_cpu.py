@@ -26,7 +26,7 @@ def _has_gpu():
 def declared_symbols():
     src = open(HEADER).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(ox[cr]_[a-z0-9_]+)\s*\(", src)))
+    return sorted(set(re.findall(r"\b(ox[bcr]_[a-z0-9_]+)\s*\(", src)))
 
 
 def test_header_is_valid_c_and_cxx():

@@ -745,3 +745,66 @@ def test_build_hpb_parity(capi, orc):
         ctx.free(pt_dev)
         ctx.free(hpb_dev)
     ctx.close()
+
+
+def test_builder_scene_parity(capi, orc):
+    """content produced by the mesh builder (oxb_build_mesh: scan meshlets, meshopt-style bounds / cones, 2 LODs) through
+    the whole GPU path: cull_meshes (LOD selection), two-pass frames, raster, decode — bit-exact against the oracle; and
+    oxc_set_scene rejects a blob whose meshlet table is not 16-byte aligned instead of faulting later."""
+    from tests.test_builder_cpu import torus
+
+    pos, nrm, uv, i0, i1 = torus(128, 64)
+    pos2, nrm2, uv2, j0, j1 = torus(40, 20, R=1.0, r=0.45, seed=9)
+    built = [capi.BuiltMesh(pos, [(i0, 0.0), (i1, 0.03)], normals=nrm, texcoords=uv),
+             capi.BuiltMesh(pos2, [(j0, 0.0), (j1, 0.08)], normals=nrm2)]
+    rng = np.random.default_rng(11)
+    n = 160
+    xf = np.zeros((n, 4, 4), dtype=np.float32)  # [col][row]
+    for i in range(n):
+        q = rng.standard_normal(4)
+        q /= np.linalg.norm(q)
+        w, x, y, z = q
+        rot = np.array([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                        [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                        [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]])
+        s = rng.uniform(0.4, 2.5, size=3)  # non-uniform scale
+        m = np.eye(4)
+        m[:3, :3] = rot * s[None, :]
+        m[:3, 3] = (rng.uniform(-60, 60), rng.uniform(-25, 25), -rng.uniform(6, 220))
+        xf[i] = m.T
+    sc = capi.assemble_scene(built, rng.integers(0, 2, size=n), xf.reshape(n, 16), 1280, 720)
+    hs = orc.HostScene(sc)
+    ctx = make_ctx(capi, sc, reordered=True)
+    w, h = sc.width, sc.height
+    vis_dev = ctx.alloc(w * h * 8)
+    mask_ref = np.zeros(ctx.out.visibility_mask_words, dtype=np.uint32)
+    for f in range(3):
+        cam = sc.camera(3.0 * f)
+        ref = orc.frame(hs, cam, w, h, mask_ref, None)
+        got = _frame_gpu(capi, ctx, sc, cam, None, vis_dev)
+        total = int(ref["visibility"]["total"][0])
+        assert (got["total"], got["early"], got["late"]) == (total, ref["early"], ref["late"])
+        np.testing.assert_array_equal(ctx.meshlet_instances(total), ref["meshlet_instances"][:total])
+        np.testing.assert_array_equal(ctx.mesh_instances(n)["lod_index"], hs.mesh_instances["lod_index"])
+        np.testing.assert_array_equal(np.sort(got["visible"]), np.sort(ref["visible"][: ref["early"] + ref["late"]]))
+        np.testing.assert_array_equal(got["mask"], mask_ref)
+        np.testing.assert_array_equal(got["vis64"], ref["vis64"])
+        for a, b in zip(got["hiz"], [ref["hiz"].level(l) for l in range(ref["hiz"].levels)]):
+            np.testing.assert_array_equal(a.view(np.uint32), b.view(np.uint32))
+    assert len(set(hs.mesh_instances["lod_index"])) == 2 and ref["early"] > 100
+    v32, _ = orc.resolve(ref["vis64"])
+    want = orc.decode_visbuffer(hs, ref["meshlet_instances"], total, cam, v32)
+    dec = _decode_gpu(ctx, cam, w, h, vis64_dev=vis_dev)
+    assert (dec["lambda_"][:, :, 3] == 1.0).sum() > 20000
+    for k in want:
+        _assert_planes_equal(dec[k], want[k], k)
+    # misaligned meshlet table -> OXC_E_INVALID from oxc_set_scene
+    bad = capi.assemble_scene(built, [0], xf.reshape(n, 16)[:1], 64, 64)
+    lods = np.frombuffer(bad.blob, dtype=abi.MESH_LOD_DT, count=1, offset=int(bad.meshes["lods"][0]))
+    lods = lods.copy()
+    lods["meshlets"] += 8
+    bad.blob[int(bad.meshes["lods"][0]): int(bad.meshes["lods"][0]) + 64] = lods.view(np.uint8)
+    with pytest.raises(capi.OxcError):
+        ctx.set_scene(bad)
+    ctx.free(vis_dev)
+    ctx.close()
