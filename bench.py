@@ -12,8 +12,8 @@ with the real exchange steps (id-base allgather, vis-buffer max-reduce x2, survi
 
 value   : whole-job meshlet instances culled / s with inputs resident in HBM (CUDA-graph replay of one frame,
           CUDA events per step on the launching stream, L2 flushed between steps, max over ranks)
-e2e     : same metric through the reference-facing host API oxr_render (C++ RendererInstance mirror) with HOST
-          buffers: camera + occluder depth H2D from pinned memory, vis32 + depth + survivor ids + counters D2H
+e2e     : same metric through the reference-facing host API oxr_submit / oxr_wait (C++ RendererInstance mirror) with
+          HOST buffers: camera + all transforms H2D from pinned memory, vis32 + survivor ids + counters D2H every frame
 roofline: the late meshlet-cull kernel (cull_meshlets_hiz equivalent), algorithmic bytes of SURVEY.md §8d /
           its CUDA-event duration inside the timed loop, against MEASURED_PEAKS.json hbm_gbs
 cpu_baseline / --impl reference: the oracle port of the same frame (oracle/, pthreads on all host cores) on a
@@ -507,12 +507,14 @@ def main():
         r.set_external_depth(scene.occluder_depth)
         xf_pinned = pin((len(scene.transforms), 16), torch.float32)
         xf_pinned[...] = scene.transforms["world"]
-        outbufs = [dict(vis32=pin((h, w), torch.int32).view(np.uint32), depth=pin((h, w), torch.float32),
+        # per-frame HOST outputs = the integer results of the path: the R32UI vis image, the survivor ids and the counters.
+        # The D32F depth attachment only feeds GPU passes (Hi-Z, shading) and stays device-resident, as in the engine.
+        outbufs = [dict(vis32=pin((h, w), torch.int32).view(np.uint32),
                         idx=pin((max(1, scene.max_meshlet_instance_count),), torch.int32).view(np.uint32)) for _ in range(2)]
 
         def e2e_steps(n):
             """n pipelined frames: frame i's device->host copies overlap frame i+1's kernels (oxr_submit / oxr_wait);
-            every frame still pays its own H2D (camera, transforms) and D2H (vis32, depth, survivor ids, counters)."""
+            every frame still pays its own H2D (camera, transforms) and D2H (vis32, survivor ids, counters)."""
             prev, res_ = None, None
             for i in range(n):
                 r.update_transforms(xf_pinned)                   # H2D: all transforms (pinned)
@@ -529,9 +531,10 @@ def main():
         torch.cuda.synchronize()
         e2e_s = (time.perf_counter() - t0) / K
         h2d = 96 + xf_pinned.nbytes
-        d2h = outbufs[0]["vis32"].nbytes + outbufs[0]["depth"].nbytes + outbufs[0]["idx"].nbytes + 12 + 8 + 8
+        d2h = outbufs[0]["vis32"].nbytes + outbufs[0]["idx"].nbytes + 12 + 8 + 8
         e2e = {"value": res["total"] / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": e2e_s * 1e3, "api": "oxr_update_transforms + oxr_submit / oxr_wait (C++ ox::RendererInstance mirror over the C ABI), pinned host buffers, 2 frames in flight"}
+               "ms_per_step": e2e_s * 1e3, "api": "oxr_update_transforms + oxr_submit / oxr_wait (C++ ox::RendererInstance mirror over the C ABI), pinned host buffers, "
+                      "2 frames in flight; H2D camera + all transforms, D2H vis32 image + survivor ids + counters (depth stays on the device)"}
         r.close()
     elif multi:
         e2e = None

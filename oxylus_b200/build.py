@@ -9,7 +9,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "liboxcull.so")
+# OXC_LIB_PATH: tuning sweeps load a variant built with OXC_NVCC_EXTRA overrides instead of the default library
+LIB = os.environ.get("OXC_LIB_PATH") or os.path.join(HERE, "liboxcull.so")
 
 SOURCES = [os.path.join(CSRC, "oxcull.cu"), os.path.join(CSRC, "host", "renderer_instance.cpp"),
            os.path.join(CSRC, "host", "mesh_builder.cpp")]
