@@ -4,12 +4,26 @@
 
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
 namespace ox {
 
 namespace {
+// OXR_TRACE=1: per-frame device timeline of the pipelined path (frame start / compute end / copy start / copy end),
+// printed by oxr_wait relative to the first traced frame.  Debug aid for tools/e2e_probe.py.
+struct Trace {
+  bool on = false, have_base = false;
+  cudaEvent_t base = nullptr;
+  cudaEvent_t ev[2][4] = {};
+  Trace() {
+    const char* e = std::getenv("OXR_TRACE");
+    on = e && e[0] == '1';
+  }
+} g_trace;
+
 struct Readback {
   OxcMeshletInstanceVisibility visibility;
   uint32_t draw_index_count[2];
@@ -49,6 +63,8 @@ RendererInstance::RendererInstance(int device, const OxcCreateInfo& info, uint32
     ok = ok && cudaMalloc(reinterpret_cast<void**>(&sl.d_vis32), px * 4) == cudaSuccess &&
          cudaMalloc(reinterpret_cast<void**>(&sl.d_depth), px * 4) == cudaSuccess &&
          cudaMalloc(reinterpret_cast<void**>(&sl.d_ids), (size_t)ids_capacity_ * 4) == cudaSuccess &&
+         cudaMalloc(&sl.d_counters, sizeof(Readback)) == cudaSuccess &&
+         cudaMemset(sl.d_counters, 0, sizeof(Readback)) == cudaSuccess &&
          cudaMallocHost(&sl.h_readback, sizeof(Readback)) == cudaSuccess &&
          cudaEventCreateWithFlags(&e0, cudaEventDisableTiming) == cudaSuccess &&
          cudaEventCreateWithFlags(&e1, cudaEventDisableTiming) == cudaSuccess;
@@ -64,7 +80,7 @@ RendererInstance::~RendererInstance() {
   if (h_pinned_) cudaFreeHost(h_pinned_);
   if (copy_stream_) cudaStreamSynchronize(static_cast<cudaStream_t>(copy_stream_));
   for (auto& sl : slots_) {
-    cudaFree(sl.d_vis32); cudaFree(sl.d_depth); cudaFree(sl.d_ids);
+    cudaFree(sl.d_vis32); cudaFree(sl.d_depth); cudaFree(sl.d_ids); cudaFree(sl.d_counters);
     if (sl.h_readback) cudaFreeHost(sl.h_readback);
     if (sl.ev_compute) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_compute));
     if (sl.ev_copy) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_copy));
@@ -126,7 +142,7 @@ auto RendererInstance::draw_for_visbuffer(MainGeometryContext& context) -> int {
 }
 
 // The geometry section of RendererInstance::render (RendererInstance.cpp:768-884), enqueued on stream_.
-int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback) {
+int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback, bool readback_on_device) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const size_t px = (size_t)width_ * height_;
   int rc;
@@ -165,7 +181,7 @@ int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occlud
     int r = cull_geometry(cull_geometry_context);
     if (r != OXC_OK) return r;
     if (cull_geometry_context.materialize_indices)
-      if (cudaMemcpyAsync(&rb->draw_index_count[pass_index], &out.draw_cmd->index_count, 4, cudaMemcpyDeviceToHost, s) != cudaSuccess)
+      if (cudaMemcpyAsync(&rb->draw_index_count[pass_index], &out.draw_cmd->index_count, 4, cudaMemcpyDefault, s) != cudaSuccess)
         return OXC_E_CUDA;
     pass_index++;
     main_geometry_context.cull_flags = cull_geometry_context.cull_flags;
@@ -173,7 +189,11 @@ int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occlud
     return draw_for_visbuffer(main_geometry_context);
   };
 
-  rb->draw_index_count[0] = rb->draw_index_count[1] = 0;
+  if (readback_on_device) {
+    if (cudaMemsetAsync(rb->draw_index_count, 0, sizeof rb->draw_index_count, s) != cudaSuccess) return OXC_E_CUDA;
+  } else {
+    rb->draw_index_count[0] = rb->draw_index_count[1] = 0;
+  }
   if ((rc = run_geometry_pass(false)) != OXC_OK) return rc; // :882
   if ((rc = generate_hiz(main_geometry_context)) != OXC_OK) return rc; // :883
   if ((rc = run_geometry_pass(true)) != OXC_OK) return rc;  // :884
@@ -190,7 +210,7 @@ auto RendererInstance::render(const OxcCullCamera& camera, const float* occluder
   OxcOutputs out;
   if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return fail(rc);
   Readback* rb = static_cast<Readback*>(h_pinned_);
-  if ((rc = run_frame(camera, occluder_depth_host, rb)) != OXC_OK) return fail(rc);
+  if ((rc = run_frame(camera, occluder_depth_host, rb, false)) != OXC_OK) return fail(rc);
 
   // results back to the host (the engine would hand the attachments to decode_visbuffer, :923-925)
   if (vis32_host || depth_host) {
@@ -235,21 +255,35 @@ auto RendererInstance::submit(const OxcCullCamera& camera, uint32_t* vis32_host,
   OxcOutputs out;
   if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return fail(rc);
   Readback* rb = static_cast<Readback*>(sl.h_readback);
-  if ((rc = run_frame(camera, nullptr, rb)) != OXC_OK) return fail(rc);
+  // The compute stream carries no device->host copy at all: a D2H on it would queue behind the previous frame's image
+  // copies in the copy engine and stall the next frame's kernels.  Counters are staged device-side like the images.
+  Readback* dc = static_cast<Readback*>(sl.d_counters);
+  if (g_trace.on) {
+    if (!g_trace.ev[slot][0])
+      for (int k = 0; k < 4; k++) cudaEventCreate(&g_trace.ev[slot][k]);
+    if (!g_trace.have_base) { cudaEventCreate(&g_trace.base); cudaEventRecord(g_trace.base, s); g_trace.have_base = true; }
+    cudaEventRecord(g_trace.ev[slot][0], s);
+  }
+  if ((rc = run_frame(camera, nullptr, dc, true)) != OXC_OK) return fail(rc);
   // stage the results of this frame (the staging of this slot was drained by wait() of its previous ticket)
-  if ((rc = oxc_resolve_visbuffer(ctx_, d_vis64_, width_, height_, vis32_host ? sl.d_vis32 : nullptr, depth_host ? sl.d_depth : nullptr, s)) != OXC_OK)
-    return fail(rc);
+  if (vis32_host || depth_host)
+    if ((rc = oxc_resolve_visbuffer(ctx_, d_vis64_, width_, height_, vis32_host ? sl.d_vis32 : nullptr, depth_host ? sl.d_depth : nullptr, s)) != OXC_OK)
+      return fail(rc);
   uint32_t n_ids = visible_indices_host ? (visible_indices_capacity < ids_capacity_ ? visible_indices_capacity : ids_capacity_) : 0;
   if (n_ids && cudaMemcpyAsync(sl.d_ids, out.visible_meshlet_instances_indices, (size_t)n_ids * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
     return fail(OXC_E_CUDA);
-  if (cudaMemcpyAsync(&rb->visibility, out.visibility, sizeof rb->visibility, cudaMemcpyDeviceToHost, s) != cudaSuccess) return fail(OXC_E_CUDA);
-  if (cudaMemcpyAsync(&rb->raster_triangles, out.raster_triangle_count, 8, cudaMemcpyDeviceToHost, s) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (cudaMemcpyAsync(&dc->visibility, out.visibility, sizeof dc->visibility, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (cudaMemcpyAsync(&dc->raster_triangles, out.raster_triangle_count, 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(OXC_E_CUDA);
   if (cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_compute), s) != cudaSuccess) return fail(OXC_E_CUDA);
   // device -> host on the copy stream, overlapping the next frame's kernels
+  if (g_trace.on) cudaEventRecord(g_trace.ev[slot][1], s);
   if (cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(sl.ev_compute), 0) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (g_trace.on) cudaEventRecord(g_trace.ev[slot][2], cs);
+  if (cudaMemcpyAsync(rb, dc, sizeof(Readback), cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
   if (vis32_host && cudaMemcpyAsync(vis32_host, sl.d_vis32, px * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
   if (depth_host && cudaMemcpyAsync(depth_host, sl.d_depth, px * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
   if (n_ids && cudaMemcpyAsync(visible_indices_host, sl.d_ids, (size_t)n_ids * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
+  if (g_trace.on) cudaEventRecord(g_trace.ev[slot][3], cs);
   if (cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_copy), cs) != cudaSuccess) return fail(OXC_E_CUDA);
   sl.in_flight = true;
   *ticket = slot;
@@ -266,6 +300,11 @@ auto RendererInstance::wait(int ticket, OxrFrameResult* result) -> int {
     return OXC_E_CUDA;
   }
   sl.in_flight = false;
+  if (g_trace.on && g_trace.ev[ticket][0]) {
+    float t[4];
+    for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], g_trace.base, g_trace.ev[ticket][k]);
+    std::fprintf(stderr, "[oxr trace] slot %d: start %.3f  compute_end %.3f  copy_start %.3f  copy_end %.3f ms\n", ticket, t[0], t[1], t[2], t[3]);
+  }
   if (result) {
     const Readback* rb = static_cast<const Readback*>(sl.h_readback);
     result->visibility = rb->visibility;

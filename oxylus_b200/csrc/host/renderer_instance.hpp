@@ -78,11 +78,12 @@ public:
 
 private:
   int fail(int rc);
-  int run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback_draw_counts);
+  int run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback_draw_counts, bool readback_on_device);
   struct Slot {
     uint32_t* d_vis32 = nullptr;
     float* d_depth = nullptr;
     uint32_t* d_ids = nullptr;
+    void* d_counters = nullptr;  // device staging of the frame's counters (Readback layout)
     void* h_readback = nullptr; // pinned
     void* ev_compute = nullptr;
     void* ev_copy = nullptr;
