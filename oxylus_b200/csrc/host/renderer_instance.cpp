@@ -18,6 +18,13 @@ struct Trace {
   bool on = false, have_base = false;
   cudaEvent_t base = nullptr;
   cudaEvent_t ev[2][4] = {};
+  cudaEvent_t stage[2][8] = {}; // OXR_TRACE=1: after clear+merge, cull_meshes+early cull, early raster, hiz, late cull, late raster
+  int cur_slot = 0, n_stage = 0;
+  void mark(cudaStream_t s) {
+    if (!on || n_stage >= 8) return;
+    if (!stage[cur_slot][n_stage]) cudaEventCreate(&stage[cur_slot][n_stage]);
+    cudaEventRecord(stage[cur_slot][n_stage++], s);
+  }
   Trace() {
     const char* e = std::getenv("OXR_TRACE");
     on = e && e[0] == '1';
@@ -58,6 +65,11 @@ RendererInstance::RendererInstance(int device, const OxcCreateInfo& info, uint32
   cudaStream_t cs = nullptr;
   bool ok = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) == cudaSuccess;
   copy_stream_ = cs;
+  {
+    cudaEvent_t ew = nullptr;
+    ok = ok && cudaEventCreateWithFlags(&ew, cudaEventDisableTiming) == cudaSuccess;
+    ev_window_ = ew;
+  }
   for (auto& sl : slots_) {
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     ok = ok && cudaMalloc(reinterpret_cast<void**>(&sl.d_vis32), px * 4) == cudaSuccess &&
@@ -85,6 +97,7 @@ RendererInstance::~RendererInstance() {
     if (sl.ev_compute) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_compute));
     if (sl.ev_copy) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_copy));
   }
+  if (ev_window_) cudaEventDestroy(static_cast<cudaEvent_t>(ev_window_));
   if (copy_stream_) cudaStreamDestroy(static_cast<cudaStream_t>(copy_stream_));
   if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
   oxc_destroy(ctx_);
@@ -160,6 +173,7 @@ int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occlud
   if (has_external_depth_)
     if ((rc = oxc_merge_depth(ctx_, d_vis64_, d_occluder_, width_, height_, s)) != OXC_OK) return rc;
 
+  g_trace.mark(s);
   MainGeometryContext main_geometry_context;
   main_geometry_context.visbuffer_attachment = d_vis64_;
   main_geometry_context.width = width_;
@@ -180,13 +194,17 @@ int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occlud
     }
     int r = cull_geometry(cull_geometry_context);
     if (r != OXC_OK) return r;
+    g_trace.mark(s);
+    if (!late && pending_.active && (r = flush_pending_copy(true)) != OXC_OK) return r; // previous frame's results go out now
     if (cull_geometry_context.materialize_indices)
       if (cudaMemcpyAsync(&rb->draw_index_count[pass_index], &out.draw_cmd->index_count, 4, cudaMemcpyDefault, s) != cudaSuccess)
         return OXC_E_CUDA;
     pass_index++;
     main_geometry_context.cull_flags = cull_geometry_context.cull_flags;
     main_geometry_context.cull_camera = cull_geometry_context.cull_camera;
-    return draw_for_visbuffer(main_geometry_context);
+    r = draw_for_visbuffer(main_geometry_context);
+    g_trace.mark(s);
+    return r;
   };
 
   if (readback_on_device) {
@@ -196,6 +214,7 @@ int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occlud
   }
   if ((rc = run_geometry_pass(false)) != OXC_OK) return rc; // :882
   if ((rc = generate_hiz(main_geometry_context)) != OXC_OK) return rc; // :883
+  g_trace.mark(s);
   if ((rc = run_geometry_pass(true)) != OXC_OK) return rc;  // :884
   return OXC_OK;
 }
@@ -249,20 +268,20 @@ auto RendererInstance::submit(const OxcCullCamera& camera, uint32_t* vis32_host,
     error_ = "oxr_submit: the previous frame of this slot has not been waited";
     return OXC_E_STATE;
   }
-  cudaStream_t s = static_cast<cudaStream_t>(stream_), cs = static_cast<cudaStream_t>(copy_stream_);
-  const size_t px = (size_t)width_ * height_;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
   int rc;
   OxcOutputs out;
   if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return fail(rc);
-  Readback* rb = static_cast<Readback*>(sl.h_readback);
-  // The compute stream carries no device->host copy at all: a D2H on it would queue behind the previous frame's image
-  // copies in the copy engine and stall the next frame's kernels.  Counters are staged device-side like the images.
+  // The compute stream carries no device->host copy: counters are staged device-side like the images and every D2H
+  // goes out on the copy stream (flush_pending_copy).
   Readback* dc = static_cast<Readback*>(sl.d_counters);
   if (g_trace.on) {
     if (!g_trace.ev[slot][0])
       for (int k = 0; k < 4; k++) cudaEventCreate(&g_trace.ev[slot][k]);
     if (!g_trace.have_base) { cudaEventCreate(&g_trace.base); cudaEventRecord(g_trace.base, s); g_trace.have_base = true; }
     cudaEventRecord(g_trace.ev[slot][0], s);
+    g_trace.cur_slot = slot;
+    g_trace.n_stage = 0;
   }
   if ((rc = run_frame(camera, nullptr, dc, true)) != OXC_OK) return fail(rc);
   // stage the results of this frame (the staging of this slot was drained by wait() of its previous ticket)
@@ -275,19 +294,42 @@ auto RendererInstance::submit(const OxcCullCamera& camera, uint32_t* vis32_host,
   if (cudaMemcpyAsync(&dc->visibility, out.visibility, sizeof dc->visibility, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(OXC_E_CUDA);
   if (cudaMemcpyAsync(&dc->raster_triangles, out.raster_triangle_count, 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(OXC_E_CUDA);
   if (cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_compute), s) != cudaSuccess) return fail(OXC_E_CUDA);
-  // device -> host on the copy stream, overlapping the next frame's kernels
+  // the device -> host copies are issued later, from inside the next frame (or by wait()): see PendingCopy
   if (g_trace.on) cudaEventRecord(g_trace.ev[slot][1], s);
-  if (cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(sl.ev_compute), 0) != cudaSuccess) return fail(OXC_E_CUDA);
-  if (g_trace.on) cudaEventRecord(g_trace.ev[slot][2], cs);
-  if (cudaMemcpyAsync(rb, dc, sizeof(Readback), cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
-  if (vis32_host && cudaMemcpyAsync(vis32_host, sl.d_vis32, px * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
-  if (depth_host && cudaMemcpyAsync(depth_host, sl.d_depth, px * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
-  if (n_ids && cudaMemcpyAsync(visible_indices_host, sl.d_ids, (size_t)n_ids * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return fail(OXC_E_CUDA);
-  if (g_trace.on) cudaEventRecord(g_trace.ev[slot][3], cs);
-  if (cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_copy), cs) != cudaSuccess) return fail(OXC_E_CUDA);
+  pending_.active = true;
+  pending_.slot = slot;
+  pending_.vis32_host = vis32_host;
+  pending_.depth_host = depth_host;
+  pending_.ids_host = visible_indices_host;
+  pending_.n_ids = n_ids;
   sl.in_flight = true;
   *ticket = slot;
   frame_++;
+  return OXC_OK;
+}
+
+// Enqueues the device->host copies of the pending frame on the copy stream.  behind_window: called from inside the next
+// frame after its early cull was launched — the copies then also wait for that point of the compute stream.
+int RendererInstance::flush_pending_copy(bool behind_window) {
+  if (!pending_.active) return OXC_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_), cs = static_cast<cudaStream_t>(copy_stream_);
+  Slot& sl = slots_[pending_.slot];
+  const size_t px = (size_t)width_ * height_;
+  const int slot = pending_.slot;
+  pending_.active = false;
+  if (behind_window) {
+    if (cudaEventRecord(static_cast<cudaEvent_t>(ev_window_), s) != cudaSuccess) return OXC_E_CUDA;
+    if (cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(ev_window_), 0) != cudaSuccess) return OXC_E_CUDA;
+  }
+  if (cudaStreamWaitEvent(cs, static_cast<cudaEvent_t>(sl.ev_compute), 0) != cudaSuccess) return OXC_E_CUDA;
+  if (g_trace.on) cudaEventRecord(g_trace.ev[slot][2], cs);
+  if (cudaMemcpyAsync(sl.h_readback, sl.d_counters, sizeof(Readback), cudaMemcpyDeviceToHost, cs) != cudaSuccess) return OXC_E_CUDA;
+  if (pending_.vis32_host && cudaMemcpyAsync(pending_.vis32_host, sl.d_vis32, px * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return OXC_E_CUDA;
+  if (pending_.depth_host && cudaMemcpyAsync(pending_.depth_host, sl.d_depth, px * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess) return OXC_E_CUDA;
+  if (pending_.n_ids && cudaMemcpyAsync(pending_.ids_host, sl.d_ids, (size_t)pending_.n_ids * 4, cudaMemcpyDeviceToHost, cs) != cudaSuccess)
+    return OXC_E_CUDA;
+  if (g_trace.on) cudaEventRecord(g_trace.ev[slot][3], cs);
+  if (cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_copy), cs) != cudaSuccess) return OXC_E_CUDA;
   return OXC_OK;
 }
 
@@ -295,6 +337,10 @@ auto RendererInstance::wait(int ticket, OxrFrameResult* result) -> int {
   if (ticket < 0 || ticket > 1) return OXC_E_INVALID;
   Slot& sl = slots_[ticket];
   if (!sl.in_flight) return OXC_E_STATE;
+  if (pending_.active && pending_.slot == ticket) { // nobody submitted a frame after this one: send its results now
+    const int rc = flush_pending_copy(false);
+    if (rc != OXC_OK) return fail(rc);
+  }
   if (cudaEventSynchronize(static_cast<cudaEvent_t>(sl.ev_copy)) != cudaSuccess) {
     error_ = cudaGetErrorString(cudaGetLastError());
     return OXC_E_CUDA;
@@ -303,7 +349,15 @@ auto RendererInstance::wait(int ticket, OxrFrameResult* result) -> int {
   if (g_trace.on && g_trace.ev[ticket][0]) {
     float t[4];
     for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], g_trace.base, g_trace.ev[ticket][k]);
-    std::fprintf(stderr, "[oxr trace] slot %d: start %.3f  compute_end %.3f  copy_start %.3f  copy_end %.3f ms\n", ticket, t[0], t[1], t[2], t[3]);
+    std::fprintf(stderr, "[oxr trace] slot %d: start %.3f  compute_end %.3f  copy_start %.3f  copy_end %.3f ms | stages us:", ticket, t[0], t[1], t[2], t[3]);
+    float prev_t = t[0];
+    for (int k = 0; k < 8 && g_trace.stage[ticket][k]; k++) {
+      float st;
+      if (cudaEventElapsedTime(&st, g_trace.base, g_trace.stage[ticket][k]) != cudaSuccess) break;
+      std::fprintf(stderr, " %.0f", (st - prev_t) * 1e3f);
+      prev_t = st;
+    }
+    std::fprintf(stderr, " | tail %.0f\n", (t[1] - prev_t) * 1e3f);
   }
   if (result) {
     const Readback* rb = static_cast<const Readback*>(sl.h_readback);

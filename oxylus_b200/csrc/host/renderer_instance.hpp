@@ -79,6 +79,7 @@ public:
 private:
   int fail(int rc);
   int run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback_draw_counts, bool readback_on_device);
+  int flush_pending_copy(bool behind_window);
   struct Slot {
     uint32_t* d_vis32 = nullptr;
     float* d_depth = nullptr;
@@ -89,6 +90,19 @@ private:
     void* ev_copy = nullptr;
     bool in_flight = false;
   } slots_[2];
+  // Device->host copies of the last submitted frame, not yet enqueued.  They are issued from inside the NEXT frame,
+  // right after its early cull has been launched (or by wait(), whichever comes first): measured on B200, a copy-engine
+  // transfer running while the many short kernels at the head of a frame are being launched doubles their latency
+  // (+85 us / frame), whereas it is free next to the one long early-raster kernel (OXR_TRACE=1 shows the timeline).
+  struct PendingCopy {
+    bool active = false;
+    int slot = 0;
+    uint32_t* vis32_host = nullptr;
+    float* depth_host = nullptr;
+    uint32_t* ids_host = nullptr;
+    uint32_t n_ids = 0;
+  } pending_;
+  void* ev_window_ = nullptr;
   void* copy_stream_ = nullptr;
   uint64_t frame_ = 0;
   uint32_t ids_capacity_ = 0;
