@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(DECODE_TX* DECODE_TY) k_decode_visbuffer(const
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         const uint2 q = __ldg(&pos[idx[c]]);
-        const float px = dequantize_half(q.x & 0xFFFFu), py = dequantize_half(q.x >> 16), pz = dequantize_half(q.y & 0xFFFFu);
+        // hardware half decode: identical to the canonical one for all 65536 inputs up to NaN payloads (oxc_exact.cuh)
+        const float px = dequantize_half_hw(q.x & 0xFFFFu), py = dequantize_half_hw(q.x >> 16), pz = dequantize_half_hw(q.y & 0xFFFFu);
         const float wx = row_dot_p1(w0, px, py, pz), wy = row_dot_p1(w1, px, py, pz), wz = row_dot_p1(w2, px, py, pz); // :121
         const float cx = row_dot_p1(p.pv_row[0], wx, wy, wz), cy = row_dot_p1(p.pv_row[1], wx, wy, wz),
                     cw = row_dot_p1(p.pv_row[3], wx, wy, wz); // :45-47
@@ -91,7 +92,7 @@ __global__ void __launch_bounds__(DECODE_TX* DECODE_TY) k_decode_visbuffer(const
         else { nrx[c] = 0.f; nry[c] = 0.f; nrz[c] = 0.f; }
         if (tcs) { // scene.slang:390-399
           const uint32_t t = __ldg(&tcs[idx[c]]);
-          tu[c] = dequantize_half(t & 0xFFFFu); tv[c] = dequantize_half(t >> 16);
+          tu[c] = dequantize_half_hw(t & 0xFFFFu); tv[c] = dequantize_half_hw(t >> 16);
         } else { tu[c] = 0.f; tv[c] = 0.f; }
       }
       // fullscreen.slang:11-17 + :122
@@ -179,7 +180,7 @@ struct HpbBuildParams {
 OXC_DI uint8_t hpb_cached(uint32_t page) { return (uint8_t)((page & 7u) == 7u); } // visible && backed && dirty (:24-26)
 
 // One CTA per layer: level 0 from the page table, every further level out of shared memory (size <= 256).
-__global__ void __launch_bounds__(256) k_hpb_fused(const __grid_constant__ HpbBuildParams p) {
+__global__ void __launch_bounds__(1024) k_hpb_fused(const __grid_constant__ HpbBuildParams p) {
   extern __shared__ uint8_t lv[]; // ping: size^2, pong: (size/2)^2
   const uint32_t z = blockIdx.x, s0 = p.size;
   uint8_t* cur = lv;

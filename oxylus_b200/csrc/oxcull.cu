@@ -765,7 +765,7 @@ int oxc_build_hpb(OxcContext* c, const uint32_t* page_table_dev, uint32_t size, 
       attr_set = true;
     }
     HpbBuildParams p{page_table_dev, hpb_dev, size, layers, levels};
-    k_hpb_fused<<<layers, 256, smem, s>>>(p);
+    k_hpb_fused<<<layers, 1024, smem, s>>>(p);
     LAUNCHED();
     return OXC_OK;
   }
