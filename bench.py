@@ -497,6 +497,20 @@ def main():
                 "note": "algorithmic bytes = N*24 + 8*ceil(M/32) + 4*S + I*84 + U*128 (SURVEY 8d, Hi-Z bytes excluded); "
                         "256 unique meshes => bounds are L2-resident and the kernel is issue-bound (DESIGN.md)"}
 
+    # the other kernels of the step against the same HBM roofline (SURVEY 8d byte formulas; 64 triangles / 49 vertices
+    # per meshlet in the synthetic meshes): the step is dominated by the raster, which is instruction-bound like the cull
+    def _k(name, algo, ms):
+        return {"kernel": name, "algorithmic_bytes": int(algo), "ms": ms, "achieved_gbs": algo / (ms * 1e-3) / 1e9 if ms > 0 else None,
+                "frac": algo / (ms * 1e-3) / 1e9 / peak if ms > 0 else None}
+    per_meshlet = 16 + 3 * 64 + 4 * 49 + 8 * 49          # Meshlet + micro indices + vertex indices + positions
+    hw_, hh_ = scene.hiz_extent()
+    roofline["other_kernels"] = [] if any(k not in stages_ms for k in ("cull_early", "raster_early", "hiz", "raster_late")) else [
+        _k("k_cull_meshlets<HIZ,OCC,EARLY,ZERO>", N_local * 24 + 2 * 4 * ((M_bits + 31) // 32) + 4 * cnt_late["early"] + I_local * 84, stages_ms["cull_early"]),
+        _k("k_raster_visbuffer (early)", cnt_late["early"] * per_meshlet + 8 * w * h, stages_ms["raster_early"]),
+        _k("k_hiz_tiles + k_hiz_tail", 4 * hw_ * hh_ + 4 * (4 * hw_ * hh_) // 3, stages_ms["hiz"]),
+        _k("k_raster_visbuffer (late)", cnt_late["late"] * per_meshlet, stages_ms["raster_late"]),
+    ]
+
     # ---------------- e2e through the reference-facing host API with HOST buffers ----------------
     e2e = None
     if not args.no_e2e and not multi:
