@@ -138,6 +138,7 @@ struct OxcContext {
   int occ_cull[2][2][2] = {};
   bool hiz_zero = true; // the pyramid holds the cleared (all-zero) image: lets the early pass skip the Hi-Z fetches
   int occ_tri = 1, occ_raster = 1, occ_mv = 1;
+  bool hpb_smem_opt_in = false;
 };
 
 namespace {
@@ -306,6 +307,12 @@ int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
     return fail(OXC_E_INVALID, "scene tables missing");
   // Layout checks on the host tables (the kernels use 128-bit loads of Meshlet / MeshletBounds records and 64-bit
   // loads of vertex positions; a misaligned or out-of-range offset must be an error here, not a device fault later).
+  // The reference's own builder aligns the meshlet / bounds tables to 8 bytes only (blob_append(..., 8),
+  // AssetManager_GLTF.cpp:749-750): such tables are accepted and moved to a 16-byte aligned tail of the DEVICE copy of
+  // the blob (relocated below); the caller's blob is not modified.
+  struct Reloc { uint64_t lod_record, src, size; int field; };
+  std::vector<Reloc> relocs;
+  uint64_t reloc_bytes = 0;
   for (uint32_t m = 0; m < sc->mesh_count; m++) {
     const OxcMesh& me = sc->meshes[m];
     if (me.lod_count == 0 || me.lod_count > OXC_MESH_MAX_LODS) return fail(OXC_E_INVALID, "mesh %u: lod_count %u not in 1..%d", m, me.lod_count, OXC_MESH_MAX_LODS);
@@ -317,14 +324,37 @@ int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
     for (uint32_t l = 0; l < me.lod_count; l++) {
       OxcMeshLOD d;
       memcpy(&d, &lods[l], sizeof d);
-      if ((d.meshlets & 15u) || (d.meshlet_bounds & 15u) || (d.local_triangle_indices & 3u) || (d.indirect_vertex_indices & 3u))
-        return fail(OXC_E_INVALID, "mesh %u lod %u: meshlets / meshlet_bounds need 16-byte, index arrays 4-byte aligned blob offsets", m, l);
+      if ((d.meshlets & 7u) || (d.meshlet_bounds & 7u) || (d.local_triangle_indices & 3u) || (d.indirect_vertex_indices & 3u))
+        return fail(OXC_E_INVALID, "mesh %u lod %u: meshlets / meshlet_bounds need 8-byte, index arrays 4-byte aligned blob offsets", m, l);
       if (d.meshlets + (uint64_t)d.meshlet_count * sizeof(OxcMeshlet) > sc->blob_size ||
           d.meshlet_bounds + (uint64_t)d.meshlet_count * sizeof(OxcMeshletBounds) > sc->blob_size ||
           d.local_triangle_indices + (uint64_t)d.local_triangle_indices_count > sc->blob_size ||
           d.indirect_vertex_indices + (uint64_t)d.indirect_vertex_indices_count * 4u > sc->blob_size)
         return fail(OXC_E_INVALID, "mesh %u lod %u: arrays outside the blob", m, l);
+      const uint64_t rec = me.lods + (uint64_t)l * sizeof(OxcMeshLOD);
+      if (d.meshlets & 15u) { relocs.push_back({rec, d.meshlets, (uint64_t)d.meshlet_count * sizeof(OxcMeshlet), 0}); reloc_bytes += (relocs.back().size + 15u) & ~15ull; }
+      if (d.meshlet_bounds & 15u) { relocs.push_back({rec, d.meshlet_bounds, (uint64_t)d.meshlet_count * sizeof(OxcMeshletBounds), 1}); reloc_bytes += (relocs.back().size + 15u) & ~15ull; }
     }
+  }
+  // device copy of the blob: the caller's bytes, or (8-byte aligned tables present) a patched copy with those tables
+  // appended at 16-byte aligned offsets and the MeshLOD records pointing at the copies
+  const uint8_t* upload = sc->blob;
+  uint64_t upload_size = sc->blob_size;
+  std::vector<uint8_t> patched;
+  if (!relocs.empty()) {
+    uint64_t cursor = (sc->blob_size + 15u) & ~15ull;
+    patched.resize((size_t)(cursor + reloc_bytes));
+    memcpy(patched.data(), sc->blob, (size_t)sc->blob_size);
+    for (const Reloc& r : relocs) {
+      memcpy(patched.data() + cursor, sc->blob + r.src, (size_t)r.size);
+      OxcMeshLOD d;
+      memcpy(&d, patched.data() + r.lod_record, sizeof d);
+      (r.field == 0 ? d.meshlets : d.meshlet_bounds) = cursor;
+      memcpy(patched.data() + r.lod_record, &d, sizeof d);
+      cursor += (r.size + 15u) & ~15ull;
+    }
+    upload = patched.data();
+    upload_size = patched.size();
   }
   if (sc->mesh_count > c->mesh_cap) {
     CK(cudaFree(c->d_meshes)); c->d_meshes = nullptr;
@@ -338,15 +368,16 @@ int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
     CK(cudaMalloc(&c->d_transforms, (size_t)sc->transform_count * sizeof(OxcTransformWorld)));
     c->transform_cap = sc->transform_count;
   }
-  if (sc->blob_size > c->blob_cap) {
+  if (upload_size > c->blob_cap) {
     CK(cudaFree(c->d_blob)); c->d_blob = nullptr;
-    CK(cudaMalloc(&c->d_blob, (size_t)sc->blob_size));
-    c->blob_cap = sc->blob_size;
+    CK(cudaMalloc(&c->d_blob, (size_t)upload_size));
+    c->blob_cap = upload_size;
   }
   CK(cudaMemcpyAsync(c->d_meshes, sc->meshes, (size_t)sc->mesh_count * sizeof(OxcMesh), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(c->d_mesh_instances, sc->mesh_instances, (size_t)sc->mesh_instance_count * sizeof(OxcMeshInstance), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(c->d_transforms, sc->transforms, (size_t)sc->transform_count * sizeof(OxcTransformWorld), cudaMemcpyHostToDevice, s));
-  CK(cudaMemcpyAsync(c->d_blob, sc->blob, (size_t)sc->blob_size, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(c->d_blob, upload, (size_t)upload_size, cudaMemcpyHostToDevice, s));
+  if (!patched.empty()) CK(cudaStreamSynchronize(s)); // the patched copy dies with this call
   // upload_gltf_mesh (AssetManager_GLTF.cpp:778-800): blob offsets -> device addresses
   k_rebase_meshes<<<(sc->mesh_count + 127) / 128, 128, 0, s>>>(c->d_meshes, sc->mesh_count, reinterpret_cast<uint64_t>(c->d_blob));
   LAUNCHED();
@@ -759,10 +790,9 @@ int oxc_build_hpb(OxcContext* c, const uint32_t* page_table_dev, uint32_t size, 
   CK(cudaSetDevice(c->device));
   const size_t smem = (size_t)size * size + (size_t)(size / 2 + 1) * (size / 2 + 1);
   if (size <= 256) {
-    static bool attr_set = false;
-    if (!attr_set && smem > 48 * 1024) {
+    if (!c->hpb_smem_opt_in && smem > 48 * 1024) { // per context == per device
       CK(cudaFuncSetAttribute(k_hpb_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-      attr_set = true;
+      c->hpb_smem_opt_in = true;
     }
     HpbBuildParams p{page_table_dev, hpb_dev, size, layers, levels};
     k_hpb_fused<<<layers, 1024, smem, s>>>(p);

@@ -798,13 +798,56 @@ def test_builder_scene_parity(capi, orc):
     assert (dec["lambda_"][:, :, 3] == 1.0).sum() > 20000
     for k in want:
         _assert_planes_equal(dec[k], want[k], k)
-    # misaligned meshlet table -> OXC_E_INVALID from oxc_set_scene
+    # meshlet table at a 4-byte offset -> OXC_E_INVALID from oxc_set_scene (8-byte alignment is the reference's layout
+    # and is accepted: test_reference_blob_alignment_is_accepted)
     bad = capi.assemble_scene(built, [0], xf.reshape(n, 16)[:1], 64, 64)
     lods = np.frombuffer(bad.blob, dtype=abi.MESH_LOD_DT, count=1, offset=int(bad.meshes["lods"][0]))
     lods = lods.copy()
-    lods["meshlets"] += 8
+    lods["meshlets"] += 4
     bad.blob[int(bad.meshes["lods"][0]): int(bad.meshes["lods"][0]) + 64] = lods.view(np.uint8)
     with pytest.raises(capi.OxcError):
         ctx.set_scene(bad)
     ctx.free(vis_dev)
     ctx.close()
+
+
+def test_reference_blob_alignment_is_accepted(capi, orc):
+    """The reference's builder aligns the Meshlet / MeshletBounds tables to 8 bytes (blob_append(..., 8),
+    AssetManager_GLTF.cpp:749-750) while the kernels load those records as 128-bit words: oxc_set_scene relocates such
+    tables inside its device copy.  The same scene with every blob offset shifted by 8 bytes gives identical frames."""
+    sc = synth.make_scene(20000, config_index=2, width=960, height=540, n_unique_meshes=24, max_lods=3, ragged=True)
+    shifted = synth.Scene(sc.meshes.copy(), sc.mesh_instances.copy(), sc.transforms.copy(),
+                          np.concatenate([np.zeros(8, dtype=np.uint8), sc.blob, np.zeros(8, dtype=np.uint8)]),
+                          sc.max_meshlet_instance_count, sc.width, sc.height, sc.seed, occluder_depth=sc.occluder_depth)
+    for f in ("vertex_positions", "vertex_normals", "texture_coords", "lods"):
+        shifted.meshes[f] = np.where(sc.meshes[f] != 0, sc.meshes[f] + 8, 0) if f in ("vertex_normals", "texture_coords") else sc.meshes[f] + 8
+    for m in shifted.meshes:
+        lods = np.frombuffer(shifted.blob, dtype=abi.MESH_LOD_DT, count=int(m["lod_count"]), offset=int(m["lods"])).copy()
+        for f in ("indices", "meshlets", "meshlet_bounds", "local_triangle_indices", "indirect_vertex_indices"):
+            lods[f] += 8
+        shifted.blob[int(m["lods"]): int(m["lods"]) + lods.nbytes] = lods.view(np.uint8)
+    lod0 = np.frombuffer(shifted.blob, dtype=abi.MESH_LOD_DT, count=1, offset=int(shifted.meshes["lods"][0]))[0]
+    assert lod0["meshlets"] % 16 == 8 and lod0["meshlet_bounds"] % 16 == 8
+    w, h = sc.width, sc.height
+    results = []
+    for scene_ in (sc, shifted):
+        ctx = make_ctx(capi, scene_)
+        vis_dev = ctx.alloc(w * h * 8)
+        occ_dev = ctx.alloc(w * h * 4)
+        ctx.upload(occ_dev, sc.occluder_depth)
+        frames = [_frame_gpu(capi, ctx, scene_, sc.camera(2.0 * f), occ_dev, vis_dev) for f in range(2)]
+        results.append(frames)
+        ctx.free(vis_dev)
+        ctx.free(occ_dev)
+        ctx.close()
+    hs = orc.HostScene(shifted)   # the oracle reads the shifted blob directly (no alignment requirement)
+    mask_ref = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    for f in range(2):
+        a, b = results[0][f], results[1][f]
+        ref = orc.frame(hs, sc.camera(2.0 * f), w, h, mask_ref, sc.occluder_depth)
+        assert (a["total"], a["early"], a["late"], a["ntri"]) == (b["total"], b["early"], b["late"], b["ntri"])
+        assert (b["early"], b["late"]) == (ref["early"], ref["late"])
+        np.testing.assert_array_equal(a["vis64"], b["vis64"])
+        np.testing.assert_array_equal(b["vis64"], ref["vis64"])
+        np.testing.assert_array_equal(a["mask"], b["mask"])
+        np.testing.assert_array_equal(np.sort(a["visible"]), np.sort(b["visible"]))
