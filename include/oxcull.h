@@ -310,6 +310,9 @@ int oxc_resolve_visbuffer(OxcContext* ctx, const uint64_t* vis_dev, uint32_t wid
 /* Depth laid down by passes outside this path (terrain, RendererInstance.cpp:862-873): vis = max(vis,
  * asuint(depth)<<32 | ~0u) per pixel. */
 int oxc_merge_depth(OxcContext* ctx, uint64_t* vis_dev, const float* depth_dev, uint32_t width, uint32_t height, void* stream);
+/* oxc_clear_visbuffer followed by oxc_merge_depth in one pass over the image (same result, bit for bit). */
+int oxc_clear_visbuffer_with_depth(OxcContext* ctx, uint64_t* vis_dev, const float* depth_dev, uint32_t width, uint32_t height,
+                                   void* stream);
 
 /* Multi-view batched cull (the reference's analogue is cull_meshlets_hpb.slang:27-99, which loops
  * <=10 shadow clipmaps per meshlet; CullGeometry.cpp:199-273).  Reads every meshlet's bounds ONCE and

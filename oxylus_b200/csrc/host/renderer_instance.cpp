@@ -164,15 +164,14 @@ int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occlud
   Readback* rb = static_cast<Readback*>(readback);
 
   // attachments: depth cleared to 0, vis buffer to ~0 (RendererInstance.cpp:562-571,629-680), Hi-Z cleared every frame (:579-588)
-  if ((rc = oxc_clear_visbuffer(ctx_, d_vis64_, width_, height_, s)) != OXC_OK) return rc;
-  if ((rc = oxc_clear_hiz(ctx_, s)) != OXC_OK) return rc;
   if (occluder_depth_host) {
     if (cudaMemcpyAsync(d_occluder_, occluder_depth_host, px * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return OXC_E_CUDA;
     has_external_depth_ = true;
   }
-  if (has_external_depth_)
-    if ((rc = oxc_merge_depth(ctx_, d_vis64_, d_occluder_, width_, height_, s)) != OXC_OK) return rc;
-
+  if (has_external_depth_) rc = oxc_clear_visbuffer_with_depth(ctx_, d_vis64_, d_occluder_, width_, height_, s); // clear + merge, one pass
+  else rc = oxc_clear_visbuffer(ctx_, d_vis64_, width_, height_, s);
+  if (rc != OXC_OK) return rc;
+  if ((rc = oxc_clear_hiz(ctx_, s)) != OXC_OK) return rc;
   g_trace.mark(s);
   MainGeometryContext main_geometry_context;
   main_geometry_context.visbuffer_attachment = d_vis64_;

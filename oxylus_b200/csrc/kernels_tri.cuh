@@ -443,6 +443,13 @@ __global__ void k_clear_visbuffer(unsigned long long* vis, size_t n) {
     vis[i] = (unsigned long long)OXC_VIS_CLEAR;
 }
 
+// clear + external depth in one pass: max(clear, asuint(depth)<<32 | ~0u) == asuint(depth)<<32 | ~0u for every depth bit
+// pattern (the clear value is the smallest word of that form), so the merge after a clear is an unconditional store
+__global__ void k_clear_visbuffer_depth(unsigned long long* vis, const float* depth, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    vis[i] = ((unsigned long long)__float_as_uint(__ldg(&depth[i])) << 32) | OXC_VIS_CLEAR;
+}
+
 // occluder / external depth merge: vis = max(vis, asuint(depth)<<32 | ~0u)
 __global__ void k_merge_depth(unsigned long long* vis, const float* depth, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {

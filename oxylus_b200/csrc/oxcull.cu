@@ -624,6 +624,16 @@ int oxc_resolve_visbuffer(OxcContext* c, const uint64_t* vis, uint32_t w, uint32
   return OXC_OK;
 }
 
+int oxc_clear_visbuffer_with_depth(OxcContext* c, uint64_t* vis, const float* depth_dev, uint32_t w, uint32_t h, void* stream) {
+  if (!c || !vis || !depth_dev) return fail(OXC_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  k_clear_visbuffer_depth<<<c->sm_count * 8, 256, 0, s>>>(reinterpret_cast<unsigned long long*>(vis), depth_dev, (size_t)w * h);
+  LAUNCHED();
+  CK(cudaMemsetAsync(c->d_tri_counter, 0, 8, s));
+  return OXC_OK;
+}
+
 // internal helper exported for the host mirror: vis = max(vis, depth<<32 | ~0u)
 int oxc_merge_depth(OxcContext* c, uint64_t* vis, const float* depth_dev, uint32_t w, uint32_t h, void* stream) {
   if (!c || !vis || !depth_dev) return fail(OXC_E_INVALID, "null argument");

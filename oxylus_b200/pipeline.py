@@ -63,10 +63,11 @@ class VisibilityPipeline:
     def frame(self, cam, mark=None, after_cull_meshes=None, between_passes=None, after_frame=None):
         c, w, h = self.ctx, self.w, self.h
         v = self.vis64.data_ptr()
-        c.clear_visbuffer(v, w, h)
-        c.clear_hiz()
         if self.occluder is not None:
-            c.merge_depth(v, self.occluder.data_ptr(), w, h)
+            c.clear_visbuffer_with_depth(v, self.occluder.data_ptr(), w, h)  # clear + external depth, one pass
+        else:
+            c.clear_visbuffer(v, w, h)
+        c.clear_hiz()
         if mark:
             mark("begin")
         c.cull_meshes(cam, abi.CULL_TEST_ALL)
@@ -103,10 +104,11 @@ class VisibilityPipeline:
     def frame_before_exchange(self, cam):
         c, w, h = self.ctx, self.w, self.h
         v = self.vis64.data_ptr()
-        c.clear_visbuffer(v, w, h)
-        c.clear_hiz()
         if self.occluder is not None:
-            c.merge_depth(v, self.occluder.data_ptr(), w, h)
+            c.clear_visbuffer_with_depth(v, self.occluder.data_ptr(), w, h)  # clear + external depth, one pass
+        else:
+            c.clear_visbuffer(v, w, h)
+        c.clear_hiz()
         c.cull_meshes(cam, abi.CULL_TEST_ALL)
         c.cull_meshlets(cam, abi.CULL_TEST_ALL, True)
         c.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, v)

@@ -851,3 +851,28 @@ def test_reference_blob_alignment_is_accepted(capi, orc):
         np.testing.assert_array_equal(b["vis64"], ref["vis64"])
         np.testing.assert_array_equal(a["mask"], b["mask"])
         np.testing.assert_array_equal(np.sort(a["visible"]), np.sort(b["visible"]))
+
+
+def test_clear_with_depth_equals_clear_then_merge(capi):
+    """oxc_clear_visbuffer_with_depth == oxc_clear_visbuffer + oxc_merge_depth for every depth bit pattern class
+    (zeros, ones, denormals, negative, inf, NaN payloads)"""
+    sc = synth.make_scene(2000, config_index=2, width=256, height=128, n_unique_meshes=4)
+    ctx = make_ctx(capi, sc)
+    w, h = 256, 128
+    rng = np.random.default_rng(5)
+    bits = rng.integers(0, 2**32, size=w * h, dtype=np.uint64).astype(np.uint32)
+    bits[:8] = [0, 0x80000000, 0x3F800000, 0x7F800000, 0xFF800000, 0x7FC00001, 0x00000001, 0xFFFFFFFF]
+    depth = bits.view(np.float32)
+    d_dev, a_dev, b_dev = ctx.alloc(w * h * 4), ctx.alloc(w * h * 8), ctx.alloc(w * h * 8)
+    ctx.upload(d_dev, depth)
+    ctx.clear_visbuffer(a_dev, w, h)
+    ctx.merge_depth(a_dev, d_dev, w, h)
+    ctx.upload(b_dev, np.full(w * h, 0x1234567812345678, dtype=np.uint64))
+    ctx.clear_visbuffer_with_depth(b_dev, d_dev, w, h)
+    a, b = ctx.download(a_dev, np.uint64, w * h), ctx.download(b_dev, np.uint64, w * h)
+    np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(b >> np.uint64(32), bits.astype(np.uint64))
+    assert ctx.raster_triangle_count() == 0
+    for p in (d_dev, a_dev, b_dev):
+        ctx.free(p)
+    ctx.close()
