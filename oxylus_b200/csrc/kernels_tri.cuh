@@ -33,6 +33,10 @@ struct TriParams {
   uint32_t width, height;
   unsigned long long* tri_counter;
   uint32_t* work_counter;    // zeroed before every raster launch
+  // deferred large triangles (k_raster_big): [0] = entries pushed, [1] = entries taken; zeroed before every raster launch
+  uint4* big_queue;          // BIG_WORDS/4 uint4 per entry
+  uint32_t* big_counters;
+  uint32_t big_capacity;
 };
 
 struct MeshletWork {
@@ -323,6 +327,73 @@ OXC_DI MeshletHeader bcast_header(const MeshletHeader& h, int src) {
   return o;
 }
 
+// ---- deferred large triangles ----
+// A triangle whose pixel bounding box exceeds RASTER_BIG_PIXELS is not rasterised by the warp that found it: a meshlet
+// close to the camera has dozens of them (hundreds of thousands of instructions for ONE warp, the tail of the launch).
+// They are pushed to a global queue, split into chunks of at most BIG_CHUNK_W x BIG_CHUNK_H pixels, and k_raster_big
+// spreads the chunks over every warp of the GPU.  Entry = the TriSetup with the chunk's bounding box + the vis data word.
+constexpr int BIG_CHUNK_W = 64, BIG_CHUNK_H = 32;
+
+OXC_DI void big_entry_store(uint4* dst, const TriSetup& s, int px0, int px1, int py0, int py1, uint32_t data) {
+  dst[0] = make_uint4((uint32_t)s.ax, (uint32_t)s.ay, (uint32_t)s.bx, (uint32_t)s.by);
+  dst[1] = make_uint4((uint32_t)s.cx, (uint32_t)s.cy, __float_as_uint(s.za), __float_as_uint(s.dzb));
+  dst[2] = make_uint4(__float_as_uint(s.dzc), (uint32_t)px0, (uint32_t)px1, (uint32_t)py0);
+  dst[3] = make_uint4((uint32_t)py1, (uint32_t)s.bias, data, 0u);
+}
+
+OXC_DI void big_entry_load(const uint4* src, TriSetup& s, uint32_t& data) {
+  const uint4 a = src[0], b = src[1], c = src[2], d = src[3];
+  s.ax = (int)a.x; s.ay = (int)a.y; s.bx = (int)a.z; s.by = (int)a.w;
+  s.cx = (int)b.x; s.cy = (int)b.y; s.za = __uint_as_float(b.z); s.dzb = __uint_as_float(b.w);
+  s.dzc = __uint_as_float(c.x); s.px0 = (int)c.y; s.px1 = (int)c.z; s.py0 = (int)c.w;
+  s.py1 = (int)d.x; s.bias = (int)d.y; s.narrow = false;
+  data = d.z;
+}
+
+// Pushes the triangle as chunks; returns false when the queue cannot take all of them (the caller then rasterises the
+// triangle inline).  Reservations are never undone — with concurrent pushers an undo would shift other warps' slots —,
+// so a reservation that straddles the capacity fills its slots below the capacity with EMPTY entries (px1 < px0), and
+// the consumer processes min(counter, capacity) entries.
+OXC_DI bool big_push(const TriParams& p, const TriSetup& s, uint32_t data) {
+  if (*reinterpret_cast<volatile uint32_t*>(&p.big_counters[0]) >= p.big_capacity) return false; // also bounds the counter's growth
+  const uint32_t cw = (uint32_t)(s.px1 - s.px0) / BIG_CHUNK_W + 1u, ch = (uint32_t)(s.py1 - s.py0) / BIG_CHUNK_H + 1u;
+  const uint32_t n = cw * ch;
+  const uint32_t base = atomicAdd(&p.big_counters[0], n);
+  if (base >= p.big_capacity) return false;
+  if (base + n > p.big_capacity) {
+    for (uint32_t k = base; k < p.big_capacity; k++) big_entry_store(p.big_queue + (size_t)k * 4, s, 1, 0, 1, 0, data);
+    return false;
+  }
+  uint32_t k = base;
+  for (uint32_t cy = 0; cy < ch; cy++)
+    for (uint32_t cx = 0; cx < cw; cx++, k++) {
+      const int x0 = s.px0 + (int)(cx * BIG_CHUNK_W), y0 = s.py0 + (int)(cy * BIG_CHUNK_H);
+      big_entry_store(p.big_queue + (size_t)k * 4, s, x0, min(s.px1, x0 + BIG_CHUNK_W - 1), y0, min(s.py1, y0 + BIG_CHUNK_H - 1), data);
+    }
+  return true;
+}
+
+// One warp per queued chunk, chunks taken from a counter: the chunk is covered in 8x4-pixel tiles (raster spec steps 5-6).
+__global__ void __launch_bounds__(256) k_raster_big(const __grid_constant__ TriParams p) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t total = min(p.big_counters[0], p.big_capacity);
+  const int lx = lane & 7, ly = lane >> 3;
+  for (;;) {
+    uint32_t i = 0;
+    if (lane == 0) i = atomicAdd(&p.big_counters[1], 1u);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    if (i >= total) break;
+    TriSetup b;
+    uint32_t data;
+    big_entry_load(p.big_queue + (size_t)i * 4, b, data);
+    for (int ty = b.py0; ty <= b.py1; ty += 4)
+      for (int tx = b.px0; tx <= b.px1; tx += 8) {
+        const int px = tx + lx, py = ty + ly;
+        if (px <= b.px1 && py <= b.py1) raster_pixel(b, px, py, data, p.visbuf, p.width);
+      }
+  }
+}
+
 __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_visbuffer(const __grid_constant__ TriParams p) {
   __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   __shared__ ScreenVert scr_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
@@ -413,9 +484,10 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
         kept += pass ? 1u : 0u;
         const uint32_t data = (w.gid << OXC_VIS_PRIMITIVE_BITS) | (t & OXC_VIS_PRIMITIVE_MASK);
         const int bw = draw ? s.px1 - s.px0 + 1 : 0, bh = draw ? s.py1 - s.py0 + 1 : 0;
-        const bool big = draw && (bw * bh > RASTER_BIG_PIXELS);
+        bool big = draw && (bw * bh > RASTER_BIG_PIXELS);
         if (draw && !big) raster_small(s, data, p.visbuf, p.width);
-        // large triangles: broadcast the setup; the warp covers the bounding box in 8x4-pixel tiles
+        if (big && p.big_queue && big_push(p, s, data)) big = false; // deferred to k_raster_big
+        // large triangles the queue could not take: broadcast the setup; the warp covers the bounding box in 8x4-pixel tiles
         uint32_t big_mask = __ballot_sync(0xffffffffu, big);
         while (big_mask) {
           const int src = __ffs(big_mask) - 1;

@@ -6,6 +6,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -115,6 +116,9 @@ struct OxcContext {
   uint32_t* d_reordered = nullptr;
   unsigned long long* d_tri_counter = nullptr;
   uint32_t* d_raster_work = nullptr;
+  uint4* d_big_queue = nullptr;      // deferred large triangles of the raster (kernels_tri.cuh)
+  uint32_t* d_big_counters = nullptr;
+  uint32_t big_capacity = 0;
   // hiz
   float* d_hiz = nullptr;
   HizDesc hiz{};
@@ -232,6 +236,13 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   TRY(dalloc(&c->d_draw_cmd, 1));
   TRY(dalloc(&c->d_tri_counter, 1));
   TRY(dalloc(&c->d_raster_work, 1));
+  c->big_capacity = 1u << 18; // 262144 chunks x 64 B = 16 MB; overflow falls back to inline rasterisation
+  if (const char* e = getenv("OXC_BIG_CAPACITY")) { // test hook: force the overflow paths
+    const long v = atol(e);
+    if (v >= 1 && v <= (1l << 24)) c->big_capacity = (uint32_t)v;
+  }
+  TRY(dalloc(&c->d_big_queue, (size_t)c->big_capacity * 4));
+  TRY(dalloc(&c->d_big_counters, 2));
   TRY(dalloc(&c->d_id_base_auto, 1));
   if (info->alloc_reordered_indices) TRY(dalloc(&c->d_reordered, (size_t)N * OXC_MESHLET_MAX_PRIMITIVES * 3));
   if (info->max_views > 1) {
@@ -292,7 +303,7 @@ void oxc_destroy(OxcContext* c) {
   cudaFree(c->d_lod_aabb); cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
   cudaFree(c->d_meshlet_instances); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
-  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_id_base_auto); cudaFree(c->d_hiz);
+  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_big_queue); cudaFree(c->d_big_counters); cudaFree(c->d_id_base_auto); cudaFree(c->d_hiz);
   cudaFree(c->d_view_planes); cudaFree(c->d_views); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts); cudaFree(c->d_inst_views); cudaFree(c->d_view_pv);
   delete c;
 }
@@ -610,7 +621,11 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
   uint32_t grid = (uint32_t)(c->sm_count * (c->occ_raster > 0 ? c->occ_raster : 1));
   if (grid > tiles) grid = tiles;
   if (grid == 0) grid = 1;
+  p.big_queue = c->d_big_queue; p.big_counters = c->d_big_counters; p.big_capacity = c->big_capacity;
+  CK(cudaMemsetAsync(c->d_big_counters, 0, 8, s));
   k_raster_visbuffer<<<grid, TRI_THREADS, 0, s>>>(p);
+  LAUNCHED();
+  k_raster_big<<<c->sm_count * 8, 256, 0, s>>>(p); // the deferred large triangles, one warp per <= 64x32-pixel chunk
   LAUNCHED();
   return OXC_OK;
 }

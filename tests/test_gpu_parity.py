@@ -876,3 +876,40 @@ def test_clear_with_depth_equals_clear_then_merge(capi):
     for p in (d_dev, a_dev, b_dev):
         ctx.free(p)
     ctx.close()
+
+
+def test_raster_big_triangle_queue_and_overflow(capi, orc):
+    """large triangles are deferred to k_raster_big in <= 64x32-pixel chunks; when the queue is full (or a reservation
+    straddles its end) they are rasterised inline — the image is the oracle's either way"""
+    import os
+
+    from tests.helpers_scene import quad_scene
+
+    W = H = 256
+    sc, cam = quad_scene(W, H, depth_a=0.3, depth_b=0.7)
+    hs = orc.HostScene(sc)
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    visible = np.zeros(1, dtype=np.uint32)
+    ref = orc.clear_visbuffer(W, H)
+    ntri = orc.raster(hs, mi, visible, 0, 1, cam, ref)
+    assert ntri == 2 and (ref != 0xFFFFFFFF).sum() > 10000
+    for cap in (None, 5, 12, 1):
+        if cap is None:
+            os.environ.pop("OXC_BIG_CAPACITY", None)
+        else:
+            os.environ["OXC_BIG_CAPACITY"] = str(cap)
+        try:
+            ctx = make_ctx(capi, sc)
+        finally:
+            os.environ.pop("OXC_BIG_CAPACITY", None)
+        vis_dev = ctx.alloc(W * H * 8)
+        for _ in range(2):  # twice: the counters are reset per launch
+            ctx.clear_visbuffer(vis_dev, W, H)
+            ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+            ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
+            ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, W, H, vis_dev)
+            got = ctx.download(vis_dev, np.uint64, W * H).reshape(H, W)
+            np.testing.assert_array_equal(got, ref, err_msg=f"capacity {cap}")
+            assert ctx.raster_triangle_count() == 2
+        ctx.free(vis_dev)
+        ctx.close()
