@@ -467,16 +467,7 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
         bool draw = false;
         if (t < w.tri_count) {
           const uint32_t base = w.tri_offset + t * 3u;
-#ifdef OXC_RASTER_MICRO_FUNNEL
-          // the triangle's three index bytes span at most two words of the (4-byte padded) run: one or two loads + a funnel shift
-          const uint32_t sh = (base & 3u) * 8u;
-          const uint32_t lo = __ldg(&w.micro[base >> 2]);
-          const uint32_t hi = sh > 8u ? __ldg(&w.micro[(base >> 2) + 1u]) : 0u;
-          const uint32_t packed = __funnelshift_r(lo, hi, sh);
-          const uint32_t i0 = packed & 0xFFu, i1 = (packed >> 8) & 0xFFu, i2 = (packed >> 16) & 0xFFu;
-#else
           const uint32_t i0 = micro_index(w.micro, base + 0u), i1 = micro_index(w.micro, base + 1u), i2 = micro_index(w.micro, base + 2u);
-#endif
           const float4 c0 = clip_s[i0], c1 = clip_s[i1], c2 = clip_s[i2];
           pass = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f && !triangle_backface(c0, c1, c2); // cull_triangles.slang:68-69
           if (pass) draw = tri_setup(scr_s[i0], scr_s[i1], scr_s[i2], p.width, p.height, s);
