@@ -163,6 +163,29 @@ def cpu_frustum_loops(scene, cam, cores):
         orc.cpu_baseline_cull(hs, mi, n, cam, 1, 1)
         best = min(best, time.perf_counter() - t0)
     out["configs0_10k_bounds_scalar_1t"] = {"meshlets_per_s": n / best, "meshlets": n}
+    # configs[0], first half: "meshlet build of one mesh" — the host-side builder (oxb_build_mesh: fetch remap, quantisation,
+    # scan meshlets, AABBs + normal cones, blob) on a procedural 131k-triangle torus, one thread.  Host C++ of the
+    # product, no GPU involved; meshoptimizer (the reference's builder) is not available here, so this is not a comparison.
+    try:
+        from oxylus_b200 import capi as _capi
+        nu, nv = 512, 128
+        uu, vv = np.meshgrid(np.arange(nu) / nu * 2 * np.pi, np.arange(nv) / nv * 2 * np.pi, indexing="ij")
+        pos = np.stack([(2 + 0.7 * np.cos(vv)) * np.cos(uu), (2 + 0.7 * np.cos(vv)) * np.sin(uu), 0.7 * np.sin(vv)], axis=2).reshape(-1, 3)
+        nrm = np.stack([np.cos(vv) * np.cos(uu), np.cos(vv) * np.sin(uu), np.sin(vv)], axis=2).reshape(-1, 3)
+        i, j = np.meshgrid(np.arange(nu), np.arange(nv), indexing="ij")
+        a, b = i * nv + j, ((i + 1) % nu) * nv + j
+        c, d = i * nv + (j + 1) % nv, ((i + 1) % nu) * nv + (j + 1) % nv
+        idx = np.stack([a, b, d, a, d, c], axis=2).reshape(-1).astype(np.uint32)
+        best = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            bm = _capi.BuiltMesh(pos, [(idx, 0.0)], normals=nrm)
+            best = min(best, time.perf_counter() - t0)
+        out["configs0_meshlet_build_1t"] = {"triangles_per_s": len(idx) / 3 / best, "triangles": int(len(idx) // 3),
+                                            "meshlets": bm.lod0_meshlet_count, "ms": best * 1e3}
+        bm.close()
+    except Exception as e:  # the builder lives in liboxcull.so; never let a baseline extra break the bench line
+        out["configs0_meshlet_build_1t"] = {"error": str(e)[:200]}
     return out
 
 
