@@ -1028,7 +1028,10 @@ typedef struct FrameJob {
   uint32_t width, height;
   uint64_t* vis;
   uint64_t ntri;
+  uint32_t* next;       /* shared cursor: raster workers take chunks of FRAME_RASTER_CHUNK survivors (near meshlets cost 10x) */
+  uint32_t n_items;
 } FrameJob;
+#define FRAME_RASTER_CHUNK 32u
 
 static void* frame_cull_worker(void* arg) {
   FrameJob* j = (FrameJob*)arg;
@@ -1056,20 +1059,37 @@ static void raster_triangle_atomic(const float clip[3][4], uint32_t data, uint32
 static void* frame_raster_worker(void* arg) {
   FrameJob* j = (FrameJob*)arg;
   uint64_t ntri = 0;
-  for (uint32_t g = j->lo; g < j->hi; g++) {
-    uint32_t mii = j->visible[g];
-    TriMeshlet t;
-    fetch_tri_meshlet(j->scene, j->mis, mii, j->cam, &t);
-    for (uint32_t tri = 0; tri < t.meshlet.triangle_count && tri < 64; tri++) {
-      float clip[3][4];
-      tri_clip(j->scene, &t, tri, clip);
-      if (!tri_passes(clip)) continue;
-      ntri++;
-      raster_triangle_atomic(clip, (mii << OXC_VIS_PRIMITIVE_BITS) | (tri & OXC_VIS_PRIMITIVE_MASK), j->width, j->height,
-                             j->vis);
+  for (;;) {
+    const uint32_t lo = __atomic_fetch_add(j->next, FRAME_RASTER_CHUNK, __ATOMIC_RELAXED);
+    if (lo >= j->n_items) break;
+    const uint32_t hi = lo + FRAME_RASTER_CHUNK < j->n_items ? lo + FRAME_RASTER_CHUNK : j->n_items;
+    for (uint32_t g = lo; g < hi; g++) {
+      uint32_t mii = j->visible[g];
+      TriMeshlet t;
+      fetch_tri_meshlet(j->scene, j->mis, mii, j->cam, &t);
+      for (uint32_t tri = 0; tri < t.meshlet.triangle_count && tri < 64; tri++) {
+        float clip[3][4];
+        tri_clip(j->scene, &t, tri, clip);
+        if (!tri_passes(clip)) continue;
+        ntri++;
+        raster_triangle_atomic(clip, (mii << OXC_VIS_PRIMITIVE_BITS) | (tri & OXC_VIS_PRIMITIVE_MASK), j->width, j->height,
+                               j->vis);
+      }
     }
   }
   j->ntri = ntri;
+  return NULL;
+}
+
+/* mask rewrite (cull_meshlets_hiz.slang:81-87) for a range of meshlet instances; neighbouring ranges share words */
+static void* frame_mask_worker(void* arg) {
+  FrameJob* j = (FrameJob*)arg;
+  for (uint32_t i = j->lo; i < j->hi; i++) {
+    OxcMeshletInstance mi = j->mis[i];
+    uint32_t vi = j->scene->mesh_instances[mi.mesh_instance_index].meshlet_instance_visibility_offset + mi.meshlet_index;
+    if (j->new_visible[i]) __atomic_fetch_or(&j->mask[vi / 32], 1u << (vi & 31), __ATOMIC_RELAXED);
+    else __atomic_fetch_and(&j->mask[vi / 32], ~(1u << (vi & 31)), __ATOMIC_RELAXED);
+  }
   return NULL;
 }
 
@@ -1173,18 +1193,18 @@ uint64_t orc_cpu_frame(const OrcScene* scene, const OxcCullCamera* cam, uint32_t
     }
     free(scratch);
     if (pass) vc->late_visible_meshlet_instances = n; else vc->early_visible_meshlet_instances = n;
-    /* mask rewrite (cull_meshlets_hiz.slang:81-87) */
-    for (uint32_t i = 0; i < total; i++) {
-      OxcMeshletInstance mi = meshlet_instances[i];
-      uint32_t vi = scene->mesh_instances[mi.mesh_instance_index].meshlet_instance_visibility_offset + mi.meshlet_index;
-      if (newvis[i]) mask[vi / 32] |= 1u << (vi & 31); else mask[vi / 32] &= ~(1u << (vi & 31));
+    /* mask rewrite (cull_meshlets_hiz.slang:81-87): same [lo, hi) ranges of meshlet instances as the cull */
+    for (int t = 0; t < n_threads; t++) {
+      jobs[t].lo = (uint32_t)(((uint64_t)total * (uint64_t)t) / (uint64_t)n_threads);
+      jobs[t].hi = (uint32_t)(((uint64_t)total * (uint64_t)(t + 1)) / (uint64_t)n_threads);
     }
-    /* raster this pass's survivors */
+    run_jobs(jobs, n_threads, frame_mask_worker);
+    /* raster this pass's survivors: chunks of FRAME_RASTER_CHUNK from a shared cursor */
+    uint32_t cursor = 0;
     for (int t = 0; t < n_threads; t++) {
       FrameJob* j = &jobs[t];
       j->visible = visible_indices + base; j->width = width; j->height = height; j->vis = vis;
-      j->lo = (uint32_t)(((uint64_t)n * (uint64_t)t) / (uint64_t)n_threads);
-      j->hi = (uint32_t)(((uint64_t)n * (uint64_t)(t + 1)) / (uint64_t)n_threads);
+      j->next = &cursor; j->n_items = n;
     }
     run_jobs(jobs, n_threads, frame_raster_worker);
     for (int t = 0; t < n_threads; t++) ntri += jobs[t].ntri;
