@@ -91,3 +91,22 @@ def test_product_never_imports_oracle():
                     assert needle not in txt or "oracle/" in txt and needle not in re.sub(r"(#|//|/\*|\"\"\").*", "", txt), (f, needle)
     out = subprocess.run(["nm", "-D", "--undefined-only", capi.lib_path()], capture_output=True, text=True).stdout
     assert "orc_" not in out
+
+
+def _build_host_min(tmp_path):
+    exe = str(tmp_path / "host_min")
+    libdir = os.path.dirname(capi.lib_path())
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "host_min.c"), "-L", libdir, "-loxcull", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe])
+    return exe
+
+
+def test_plain_c_host_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """examples/host_min.c: a C11 host using nothing but include/oxcull.h.  Without a CUDA device it must stop at oxc_create
+    with the no-device error (exit code 3), never silently compute on the CPU."""
+    capi.load()
+    exe = _build_host_min(tmp_path)
+    if _has_gpu():
+        pytest.skip("GPU present: covered by the gpu-marked test")
+    res = subprocess.run([exe], capture_output=True, text=True)
+    assert res.returncode == 3 and "no CUDA device" in res.stderr

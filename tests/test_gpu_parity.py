@@ -913,3 +913,13 @@ def test_raster_big_triangle_queue_and_overflow(capi, orc):
             assert ctx.raster_triangle_count() == 2
         ctx.free(vis_dev)
         ctx.close()
+
+
+def test_plain_c_host_runs(capi, tmp_path):
+    """examples/host_min.c on the GPU: the quad covers exactly a quarter of the 64x48 image"""
+    from tests.test_abi_cpu import _build_host_min
+    import subprocess
+
+    res = subprocess.run([_build_host_min(tmp_path)], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "768 of 3072 pixels" in res.stdout
