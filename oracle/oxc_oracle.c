@@ -590,6 +590,96 @@ static void raster_triangle(const float clip[3][4], uint32_t data, uint32_t W, u
     }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Clipped raster (SPECIFICATION ONLY — the CUDA raster does not implement it yet).
+ * The plain spec drops a triangle when a vertex has w <= 0 or a snapped coordinate exceeds 2^22 (steps 2-3); a hardware
+ * rasteriser clips such triangles instead (DrawGeometry.cpp:104-190 relies on it: geometry around the camera).  Only those
+ * triangles take this path, so every triangle the plain spec draws is drawn identically:
+ *   Sutherland-Hodgman in clip space against, in this order, near (w - z >= 0), left (w + x >= 0), right (w - x >= 0),
+ *   bottom (w + y >= 0), top (w - y >= 0); a vertex with distance exactly 0 is inside.  An edge that crosses a plane is
+ *   cut at  P = I + t * (O - I),  t = dI / (dI - dO)  evaluated FROM THE INSIDE VERTEX I TO THE OUTSIDE VERTEX O (so the two
+ *   triangles sharing the edge compute the same point whatever their winding), per component, f32, this operation order.
+ *   The polygon (<= 8 vertices) is drawn as the fan (P0, Pi, Pi+1) with the plain rules (snapping, tie-break, depth).
+ * ---------------------------------------------------------------------------------------------- */
+static int tri_dropped_by_range(const float clip[3][4], uint32_t W, uint32_t H) {
+  for (int i = 0; i < 3; i++) {
+    if (!(clip[i][3] > 0.0f)) return 1;
+    float rw = 1.0f / clip[i][3];
+    float nx = clip[i][0] * rw, ny = clip[i][1] * rw;
+    float sx = (nx * 0.5f + 0.5f) * (float)W, sy = (ny * 0.5f + 0.5f) * (float)H;
+    float qx = floorf(sx * 256.0f + 0.5f), qy = floorf(sy * 256.0f + 0.5f);
+    if (!(fabsf(qx) <= 4194304.0f && fabsf(qy) <= 4194304.0f)) return 1;
+  }
+  return 0;
+}
+
+static inline float clip_plane_distance(const float v[4], int plane) {
+  switch (plane) {
+    case 0: return v[3] - v[2]; /* near (reverse-Z: z <= w) */
+    case 1: return v[3] + v[0];
+    case 2: return v[3] - v[0];
+    case 3: return v[3] + v[1];
+    default: return v[3] - v[1];
+  }
+}
+
+static void raster_triangle_clipped(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis) {
+  float poly[2][12][4];
+  int n = 3, cur = 0;
+  memcpy(poly[0], clip, sizeof(float) * 12);
+  for (int plane = 0; plane < 5 && n >= 3; plane++) {
+    float(*in)[4] = poly[cur];
+    float(*out)[4] = poly[cur ^ 1];
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+      const float* A = in[i];
+      const float* B = in[(i + 1) % n];
+      const float dA = clip_plane_distance(A, plane), dB = clip_plane_distance(B, plane);
+      const int inA = dA >= 0.0f, inB = dB >= 0.0f;
+      if (inA) { memcpy(out[m], A, 16); m++; }
+      if (inA != inB) {
+        const float* I = inA ? A : B;
+        const float* O = inA ? B : A;
+        const float dI = inA ? dA : dB, dO = inA ? dB : dA;
+        const float t = dI / (dI - dO);
+        for (int k = 0; k < 4; k++) out[m][k] = I[k] + t * (O[k] - I[k]);
+        m++;
+      }
+    }
+    n = m;
+    cur ^= 1;
+  }
+  if (n < 3) return;
+  for (int i = 1; i + 1 < n; i++) {
+    float tri[3][4];
+    memcpy(tri[0], poly[cur][0], 16); memcpy(tri[1], poly[cur][i], 16); memcpy(tri[2], poly[cur][i + 1], 16);
+    raster_triangle(tri, data, W, H, vis);
+  }
+}
+
+void orc_raster_visbuffer_clip(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                               const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
+                               const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,
+                               uint64_t* triangles_rasterised, uint64_t* triangles_clipped) {
+  uint64_t ntri = 0, nclip = 0;
+  for (uint32_t g = 0; g < pass_count; g++) {
+    uint32_t mii = visible_indices[pass_first + g];
+    TriMeshlet t;
+    fetch_tri_meshlet(scene, meshlet_instances, mii, cam, &t);
+    for (uint32_t tri = 0; tri < t.meshlet.triangle_count && tri < 64; tri++) {
+      float clip[3][4];
+      tri_clip(scene, &t, tri, clip);
+      if (!tri_passes(clip)) continue;
+      ntri++;
+      uint32_t data = ((mii + id_base) << OXC_VIS_PRIMITIVE_BITS) | (tri & OXC_VIS_PRIMITIVE_MASK);
+      if (tri_dropped_by_range(clip, width, height)) { nclip++; raster_triangle_clipped(clip, data, width, height, vis); }
+      else raster_triangle(clip, data, width, height, vis);
+    }
+  }
+  if (triangles_rasterised) *triangles_rasterised += ntri;
+  if (triangles_clipped) *triangles_clipped += nclip;
+}
+
 void orc_raster_visbuffer(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
                           const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
                           const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,

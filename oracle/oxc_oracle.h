@@ -114,6 +114,12 @@ void orc_raster_visbuffer(const OrcScene* scene, const OxcMeshletInstance* meshl
                           const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height,
                           uint64_t* vis, uint64_t* triangles_rasterised);
 void orc_resolve_visbuffer(const uint64_t* vis, uint32_t width, uint32_t height, uint32_t* vis32, float* depth);
+/* SPECIFICATION ONLY (not implemented by the CUDA raster yet): as orc_raster_visbuffer, but triangles the plain spec drops
+ * for w <= 0 / coordinate overflow are clipped in clip space against near + the four side planes and drawn as a fan. */
+void orc_raster_visbuffer_clip(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                               const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
+                               const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,
+                               uint64_t* triangles_rasterised, uint64_t* triangles_clipped);
 
 /* passes/cull_meshlets_hpb.slang:27-99 + cull.slang:137-166 test_vsm_page.  hpb: levels of (layers x s x s) bytes. */
 void orc_cull_meshlets_hpb(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, const OxcCullCamera* cam,

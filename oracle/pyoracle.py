@@ -162,6 +162,15 @@ def raster(hs, mi, visible, first, count, cam, vis, id_base=0):
     return int(ntri.value)
 
 
+def raster_clip(hs, mi, visible, first, count, cam, vis, id_base=0):
+    """specification-only variant with near / side-plane clipping; returns (triangles passing the cull, triangles clipped)"""
+    h, w = vis.shape
+    ntri, nclip = C.c_uint64(0), C.c_uint64(0)
+    lib().orc_raster_visbuffer_clip(hs.ref, _p(mi), _p(visible), C.c_uint32(first), C.c_uint32(count), _p(cam),
+                                    C.c_uint32(id_base), C.c_uint32(w), C.c_uint32(h), _p(vis), C.byref(ntri), C.byref(nclip))
+    return int(ntri.value), int(nclip.value)
+
+
 def resolve(vis):
     h, w = vis.shape
     v32 = np.zeros((h, w), dtype=np.uint32)
