@@ -1157,9 +1157,29 @@ static void* frame_raster_worker(void* arg) {
       uint32_t mii = j->visible[g];
       TriMeshlet t;
       fetch_tri_meshlet(j->scene, j->mis, mii, j->cam, &t);
+      /* transform the meshlet's vertices once (as visbuffer_encode_ms.slang:135-137 does per vertex); the values are the
+       * ones tri_clip computes per corner, so the image is unchanged */
+      const uint32_t* micro = (const uint32_t*)(j->scene->blob + t.lod->local_triangle_indices);
+      const uint32_t* vidx = (const uint32_t*)(j->scene->blob + t.lod->indirect_vertex_indices);
+      const uint16_t* pos = (const uint16_t*)(j->scene->blob + t.mesh->vertex_positions);
+      float vclip[OXC_MESHLET_MAX_VERTICES][4];
+      const uint32_t nv = t.meshlet.vertex_count < OXC_MESHLET_MAX_VERTICES ? t.meshlet.vertex_count : OXC_MESHLET_MAX_VERTICES;
+      for (uint32_t v = 0; v < nv; v++) {
+        const uint32_t vi = vidx[t.meshlet.indirect_vertex_index_offset + v];
+        Vec4_f32 pp = {orc_dequantize_half(pos[vi * 4 + 0]), orc_dequantize_half(pos[vi * 4 + 1]),
+                       orc_dequantize_half(pos[vi * 4 + 2]), 1.0f};
+        Vec4_f32 cp = mul_mv_f32(t.mvp, pp);
+        vclip[v][0] = cp.x; vclip[v][1] = cp.y; vclip[v][2] = cp.z; vclip[v][3] = cp.w;
+      }
       for (uint32_t tri = 0; tri < t.meshlet.triangle_count && tri < 64; tri++) {
         float clip[3][4];
-        tri_clip(j->scene, &t, tri, clip);
+        const uint32_t base = t.meshlet.local_triangle_index_offset + tri * 3;
+        const uint32_t l0 = micro_index(micro, base), l1 = micro_index(micro, base + 1), l2 = micro_index(micro, base + 2);
+        if (l0 < nv && l1 < nv && l2 < nv) {
+          memcpy(clip[0], vclip[l0], 16); memcpy(clip[1], vclip[l1], 16); memcpy(clip[2], vclip[l2], 16);
+        } else {
+          tri_clip(j->scene, &t, tri, clip);
+        }
         if (!tri_passes(clip)) continue;
         ntri++;
         raster_triangle_atomic(clip, (mii << OXC_VIS_PRIMITIVE_BITS) | (tri & OXC_VIS_PRIMITIVE_MASK), j->width, j->height,
