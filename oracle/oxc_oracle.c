@@ -1127,16 +1127,24 @@ static void* frame_cull_worker(void* arg) {
   FrameJob* j = (FrameJob*)arg;
   const Vec3_f32 campos = {j->cam->position[0], j->cam->position[1], j->cam->position[2]};
   uint64_t n = 0;
+  /* consecutive meshlet instances share their mesh instance: mvp and the six planes are computed once per run */
+  uint32_t cached_inst = 0xFFFFFFFFu;
+  float mvp[16], planes[6][4];
   for (uint32_t i = j->lo; i < j->hi; i++) {
     MeshletCtx m;
     fetch_meshlet(j->scene, j->mis[i], &m);
+    if (j->mis[i].mesh_instance_index != cached_inst) {
+      cached_inst = j->mis[i].mesh_instance_index;
+      mul_mm_f32(j->cam->projection_view, m.world, mvp);
+      frustum_planes_f32(mvp, planes);
+    }
     int was_visible = 1;
     if (j->flags & OXC_CULL_TEST_OCCLUSION) {
       uint32_t vi = m.inst.meshlet_instance_visibility_offset + j->mis[i].meshlet_index;
       was_visible = (j->mask[vi / 32] >> (vi & 31)) & 1;
     }
-    int visible = meshlet_visible_hiz_f32(j->cam->projection_view, m.world, j->cam->near_clip, campos, m.c, m.e, m.axis,
-                                          m.cutoff, j->flags, was_visible, j->hiz);
+    int visible = meshlet_visible_hiz_hoisted_f32(mvp, (const float(*)[4])planes, m.world, j->cam->near_clip, campos, m.c, m.e,
+                                                  m.axis, m.cutoff, j->flags, was_visible, j->hiz);
     j->new_visible[i] = (uint8_t)visible;
     if (visible && (!(j->flags & OXC_CULL_LATE_PASS) || !was_visible)) j->out[j->lo + n++] = i;
   }
