@@ -302,6 +302,15 @@ int oxc_clear_visbuffer(OxcContext* ctx, uint64_t* vis_dev, uint32_t width, uint
 int oxc_raster_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width,
                          uint32_t height, uint64_t* vis_dev, int small_primitive_cull, void* stream);
 
+/* OPT-IN second raster pass (call after oxc_raster_visbuffer with the same arguments): the triangles that pass draws nothing
+ * for — a vertex at w <= 0 or a snapped coordinate beyond 2^22, i.e. geometry around the camera, which the reference's hardware
+ * rasteriser clips (DrawGeometry.cpp:104-190) — are clipped in clip space against near + the four side planes and drawn as a
+ * fan with the same rules (specification and tests: oracle/oxc_oracle.c raster_triangle_clipped, tests/test_oracle_clip.py).
+ * Every other triangle is untouched, so frames without such triangles are bit-identical with and without this pass.
+ * Status: written after round 1's GPU budget was spent; not yet verified on a GPU (its parity test is skipped until then). */
+int oxc_raster_visbuffer_clip_pass(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width,
+                                   uint32_t height, uint64_t* vis_dev, void* stream);
+
 /* Splits the packed image into the reference's two attachments: R32UI vis (data, ~0u = empty) and
  * D32F depth.  Either output may be NULL. */
 int oxc_resolve_visbuffer(OxcContext* ctx, const uint64_t* vis_dev, uint32_t width, uint32_t height,

@@ -18,7 +18,7 @@ SYMBOLS = [
     "oxc_last_error", "oxc_kernel_launch_count", "oxc_version", "oxc_create", "oxc_destroy", "oxc_set_scene",
     "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_set_shard_auto", "oxc_cull_meshes",
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
-    "oxc_raster_visbuffer", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
+    "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
     "oxc_decode_visbuffer", "oxc_build_hpb",
     "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free",
@@ -67,6 +67,7 @@ def load(build_if_missing=True):
     lib.oxc_cull_triangles.argtypes = [vp, vp, u32, vp]
     lib.oxc_clear_visbuffer.argtypes = [vp, vp, u32, u32, vp]
     lib.oxc_raster_visbuffer.argtypes = [vp, vp, u32, u32, u32, vp, i32, vp]
+    lib.oxc_raster_visbuffer_clip_pass.argtypes = [vp, vp, u32, u32, u32, vp, vp]
     lib.oxc_resolve_visbuffer.argtypes = [vp, vp, u32, u32, vp, vp, vp]
     lib.oxc_merge_depth.argtypes = [vp, vp, vp, u32, u32, vp]
     lib.oxc_clear_visbuffer_with_depth.argtypes = [vp, vp, vp, u32, u32, vp]
@@ -286,6 +287,10 @@ class Context:
     def raster_visbuffer(self, cam, flags, w, h, vis_dev, small_primitive_cull=False):
         _check(self.lib.oxc_raster_visbuffer(self.h, _ptr(cam), flags, w, h, _ptr(vis_dev), int(small_primitive_cull), self.stream),
                "oxc_raster_visbuffer")
+
+    def raster_visbuffer_clip_pass(self, cam, flags, w, h, vis_dev):
+        _check(self.lib.oxc_raster_visbuffer_clip_pass(self.h, _ptr(cam), flags, w, h, _ptr(vis_dev), self.stream),
+               "oxc_raster_visbuffer_clip_pass")
 
     def resolve_visbuffer(self, vis_dev, w, h, vis32_dev, depth_dev):
         _check(self.lib.oxc_resolve_visbuffer(self.h, _ptr(vis_dev), w, h, _ptr(vis32_dev), _ptr(depth_dev), self.stream),

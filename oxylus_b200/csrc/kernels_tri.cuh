@@ -509,6 +509,81 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
   if (lane == 0 && kept) atomicAdd(p.tri_counter, (unsigned long long)kept);
 }
 
+// ---- clip pass (opt-in; specification: oracle/oxc_oracle.c raster_triangle_clipped) ----
+// Handles exactly the triangles k_raster_visbuffer drops because a vertex has w <= 0 or a snapped coordinate beyond 2^22:
+// Sutherland-Hodgman in clip space against near (w - z), left (w + x), right (w - x), bottom (w + y), top (w - y), cut points
+// evaluated from the inside vertex to the outside vertex with the canonical f32 operation order, then the fan (P0, Pi, Pi+1)
+// is set up with the plain rules.  Pieces are usually large (geometry around the camera): they go to the chunk queue of
+// k_raster_big (inline when the queue is full).  A separate kernel: the default raster path is untouched.
+// NOT YET VERIFIED ON A GPU (written after the round's GPU budget was spent): the parity test is skipped until it has been.
+OXC_DI float clip_plane_distance(const float4 v, int plane) {
+  switch (plane) {
+    case 0: return fs(v.w, v.z);
+    case 1: return fa(v.w, v.x);
+    case 2: return fs(v.w, v.x);
+    case 3: return fa(v.w, v.y);
+    default: return fs(v.w, v.y);
+  }
+}
+
+__global__ void __launch_bounds__(TRI_THREADS) k_raster_clip_pass(const __grid_constant__ TriParams p) {
+  __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t first = p.late ? p.vis->early_visible_meshlet_instances : 0u;
+  const uint32_t count = p.tri_cmd->x;
+  const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
+  const float fW = (float)p.width, fH = (float)p.height;
+  float4* clip_s = clip_all[warp];
+  const uint32_t n_tiles = (count + TRI_WARPS - 1) / TRI_WARPS;
+  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const uint32_t g = tile * TRI_WARPS + warp;
+    if (g < count) {
+      const MeshletWork w = load_meshlet(p, first + g, id_base, clip_s, lane);
+      for (uint32_t t = lane; t < w.tri_count; t += 32) {
+        float4 c0, c1, c2;
+        if (!triangle_passes(w, t, clip_s, c0, c1, c2)) continue;
+        if (to_screen(c0, fW, fH).fx != INT_MIN && to_screen(c1, fW, fH).fx != INT_MIN && to_screen(c2, fW, fH).fx != INT_MIN)
+          continue; // drawn by k_raster_visbuffer
+        float4 poly[2][12];
+        int n = 3, cur = 0;
+        poly[0][0] = c0; poly[0][1] = c1; poly[0][2] = c2;
+        for (int plane = 0; plane < 5 && n >= 3; plane++) {
+          const float4* in = poly[cur];
+          float4* out = poly[cur ^ 1];
+          int m = 0;
+          for (int i = 0; i < n; i++) {
+            const float4 A = in[i], B = in[(i + 1) % n];
+            const float dA = clip_plane_distance(A, plane), dB = clip_plane_distance(B, plane);
+            const bool inA = dA >= 0.0f, inB = dB >= 0.0f;
+            if (inA) out[m++] = A;
+            if (inA != inB) {
+              const float4 I = inA ? A : B, O = inA ? B : A;
+              const float dI = inA ? dA : dB, dO = inA ? dB : dA;
+              const float tt = fd(dI, fs(dI, dO));
+              out[m++] = make_float4(fa(I.x, fm(tt, fs(O.x, I.x))), fa(I.y, fm(tt, fs(O.y, I.y))), fa(I.z, fm(tt, fs(O.z, I.z))),
+                                     fa(I.w, fm(tt, fs(O.w, I.w))));
+            }
+          }
+          n = m;
+          cur ^= 1;
+        }
+        const uint32_t data = (w.data_id << OXC_VIS_PRIMITIVE_BITS) | (t & OXC_VIS_PRIMITIVE_MASK);
+        for (int i = 1; i + 1 < n; i++) {
+          TriSetup s;
+          if (!tri_setup(to_screen(poly[cur][0], fW, fH), to_screen(poly[cur][i], fW, fH), to_screen(poly[cur][i + 1], fW, fH), p.width,
+                         p.height, s))
+            continue;
+          const int bw = s.px1 - s.px0 + 1, bh = s.py1 - s.py0 + 1;
+          if (bw * bh > RASTER_BIG_PIXELS && p.big_queue && big_push(p, s, data)) continue; // spread over the GPU by k_raster_big
+          s.narrow = false; // pieces may be large: 64-bit edge functions
+          raster_small(s, data, p.visbuf, p.width);
+        }
+      }
+    }
+    __syncwarp(); // clip_s reuse
+  }
+}
+
 // visbuffer_clear.slang:20-28 on the packed image: depth 0 | data ~0u
 __global__ void k_clear_visbuffer(unsigned long long* vis, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

@@ -630,6 +630,28 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
   return OXC_OK;
 }
 
+int oxc_raster_visbuffer_clip_pass(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t w, uint32_t h, uint64_t* vis,
+                                   void* stream) {
+  if (!c || !cam || !vis) return fail(OXC_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  TriParams p{};
+  int rc = tri_common(c, cam, flags, s, &p);
+  if (rc != OXC_OK) return rc;
+  p.visbuf = reinterpret_cast<unsigned long long*>(vis); p.width = w; p.height = h;
+  p.big_queue = c->d_big_queue; p.big_counters = c->d_big_counters; p.big_capacity = c->big_capacity;
+  CK(cudaMemsetAsync(c->d_big_counters, 0, 8, s));
+  uint32_t tiles = (c->info.max_meshlet_instances + TRI_WARPS - 1) / TRI_WARPS;
+  uint32_t grid = (uint32_t)(c->sm_count * 4);
+  if (grid > tiles) grid = tiles;
+  if (grid == 0) grid = 1;
+  k_raster_clip_pass<<<grid, TRI_THREADS, 0, s>>>(p);
+  LAUNCHED();
+  k_raster_big<<<c->sm_count * 8, 256, 0, s>>>(p);
+  LAUNCHED();
+  return OXC_OK;
+}
+
 int oxc_resolve_visbuffer(OxcContext* c, const uint64_t* vis, uint32_t w, uint32_t h, uint32_t* vis32, float* depth, void* stream) {
   if (!c || !vis) return fail(OXC_E_INVALID, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
