@@ -412,16 +412,30 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
   // and RASTER_BATCH), so the kernel ends with single-meshlet grabs.  With a fixed batch of 8 a warp's last grab was 1/7 of
   // its whole share and the average SM sat idle for the last third of the launch (ncu: sm__cycles_active 67 % of elapsed).
   const uint32_t n_warps2 = gridDim.x * TRI_WARPS * 2u;
+#ifdef OXC_RASTER_STATIC_SCHEDULE
+  // experiment: no work counter at all — grab k of warp w is the k-th block of RASTER_BATCH survivors
+  // in a warp-strided order.  Tests whether the same-address atomics are what the late pass waits on.
+  uint32_t static_iter = 0;
+  const uint32_t warp_global = blockIdx.x * TRI_WARPS + warp, n_warps = gridDim.x * TRI_WARPS;
+#endif
   for (;;) {
     uint32_t g0 = 0, batch = 1;
+#ifdef OXC_RASTER_STATIC_SCHEDULE
+    batch = min((uint32_t)RASTER_BATCH, max(1u, count / n_warps2));
+    g0 = (static_iter++ * n_warps + warp_global) * batch;
+#else
     if (lane == 0) {
       const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(p.work_counter); // heuristic only: a stale value is harmless
       const uint32_t rem = count > seen ? count - seen : 0u;
       batch = min((uint32_t)RASTER_BATCH, max(1u, rem / n_warps2));
+#ifdef OXC_RASTER_LATE_FIXED_BATCH
+      if (p.late) batch = OXC_RASTER_LATE_FIXED_BATCH; // experiment: fewer same-address atomics in the late pass
+#endif
       g0 = atomicAdd(p.work_counter, batch);
     }
     g0 = __shfl_sync(0xffffffffu, g0, 0);
     batch = __shfl_sync(0xffffffffu, batch, 0);
+#endif
     if (g0 >= count) break;
     const uint32_t nb = min(batch, count - g0);
     MeshletHeader mine;
