@@ -242,10 +242,8 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     if multi:
-        if "OXC_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["OXC_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)  # the version banner goes to stdout: keep stdout to the one JSON line
+        # NCCL_DEBUG is left exactly as the launcher set it (the driver reads the communicator banner for its rank proof);
+        # the JSON line is the last line rank 0 prints
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     n_gpus = world
     capi.load(build_if_missing=False)

@@ -163,6 +163,8 @@ enum {
 #define OXC_VIS_PRIMITIVE_BITS 8u
 #define OXC_VIS_PRIMITIVE_MASK 0xFFu
 #define OXC_VIS_CLEAR 0xFFFFFFFFu
+/* OxcCreateInfo::wide_ids packing (no reference equivalent): 26-bit meshlet instance id, 6-bit triangle */
+#define OXC_VIS_WIDE_PRIMITIVE_BITS 6u
 /* oxc_cull_meshlets_multiview: upper bound on batched views */
 #define OXC_MAX_VIEWS 16
 
@@ -191,6 +193,13 @@ typedef struct OxcCreateInfo {
   uint32_t alloc_reordered_indices; /* 1: allocate the 768 B x max index buffer for oxc_cull_triangles
                                        (RendererInstance.cpp:1727-1731); 0: fused raster only */
   uint32_t max_views;             /* 0/1, or up to OXC_MAX_VIEWS for oxc_cull_meshlets_multiview */
+  uint32_t max_mask_bits;         /* 0: = max_meshlet_instances.  Multi-GPU shards: the persistent visibility mask is indexed by the
+                                     GLOBAL meshlet_instance_visibility_offset, so a shard context keeps max_meshlet_instances at
+                                     its own share (8 + 4 B each) and sets this to the whole scene's LOD0 meshlet count (1 bit each) */
+  uint32_t wide_ids;              /* 0: the reference's 24 + 8 bit vis-buffer word (visbuffer.slang:9-14; <= 2^24 meshlet instances,
+                                     the raster / decode entry points refuse larger scenes with OXC_E_CAPACITY);
+                                     1: 26 + 6 bit word (meshlets hold <= 64 triangles, so 6 bits suffice) for scenes of up to
+                                     2^26 meshlet instances (BASELINE configs[4], 50 M).  Same ordering of equal-depth winners. */
 } OxcCreateInfo;
 
 /* Host-side scene tables (what Scene::runtime_update hands to RendererInstance::update,
@@ -226,7 +235,23 @@ typedef struct OxcOutputs {
   uint32_t* view_visibility_bits;                  /* multiview: one u32 per meshlet instance, bit v = view v (NULL if max_views<=1) */
   uint32_t* view_visible_counts;                   /* multiview: u32[OXC_MAX_VIEWS] */
   uint64_t* raster_triangle_count;                 /* triangles that survived cull and were rasterised, cumulative per clear */
+  uint32_t* status_flags;                          /* sticky OXC_STATUS_* bits raised by kernels (see oxc_check_status) */
+  uint32_t vis_primitive_bits;                     /* 8 (reference packing) or 6 (OxcCreateInfo::wide_ids) */
 } OxcOutputs;
+
+/* Device-side error conditions.  Kernels never write out of bounds: they clamp, raise a sticky bit in
+ * OxcOutputs::status_flags and carry on; oxc_check_status reads the word (synchronises `stream`), returns
+ * OXC_E_CAPACITY / OXC_E_INVALID when a bit is set and clears it. */
+enum {
+  OXC_STATUS_MESHLET_OVERFLOW = 1 << 0, /* cull_meshes wanted to emit more than max_meshlet_instances (clamped) */
+  OXC_STATUS_BAD_GEOMETRY = 1 << 1,     /* a micro index >= vertex_count or a vertex index >= Mesh::vertex_count (triangle skipped) */
+  OXC_STATUS_SURVIVOR_OVERFLOW = 1 << 2,/* oxc_mgpu_exchange_frame: a rank's survivor list exceeded the gather capacity (truncated) */
+  OXC_STATUS_ID_OVERFLOW = 1 << 3       /* a vis-buffer id did not fit the id bits of the packing (pixel skipped) */
+};
+int oxc_check_status(OxcContext* ctx, void* stream, uint32_t* flags_out /* may be NULL */);
+/* The Hi-Z pyramid was written through OxcOutputs::hiz by something other than an oxc_* call (an external reduce,
+ * a terrain pass): the early pass may no longer assume the per-frame cleared image. */
+int oxc_mark_hiz_dirty(OxcContext* ctx);
 
 const char* oxc_last_error(void);
 /* number of CUDA kernels this library has launched in this process (bench.py "gpu_launches") */
@@ -298,7 +323,9 @@ int oxc_clear_visbuffer(OxcContext* ctx, uint64_t* vis_dev, uint32_t width, uint
  * visbuffer_encode_ms.slang:110-171; DrawGeometry.cpp:104-190): per surviving meshlet of this pass,
  * per-triangle near/backface cull then rasterisation with atomicMax on asuint(depth)<<32 | data
  * (reverse-Z GreaterOrEqual == max; visbuffer.slang:72-74 packing).  small_primitive_cull != 0
- * additionally drops triangles whose pixel bbox covers no sample centre (not in the reference). */
+ * additionally drops triangles whose pixel bbox covers no sample centre BEFORE they are counted (north_star's
+ * small-primitive cull; the reference has none, cull_triangles.slang:59-90): the image is unchanged — such a triangle
+ * produces no fragment — only OxcOutputs::raster_triangle_count drops by the number culled. */
 int oxc_raster_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width,
                          uint32_t height, uint64_t* vis_dev, int small_primitive_cull, void* stream);
 

@@ -114,7 +114,9 @@ CULL_TEST_ALL = CULL_TEST_FRUSTUM | CULL_SELECT_LOD | CULL_TEST_OCCLUSION
 HIZ_MAX_LEVELS = 13
 MAX_VIEWS = 16
 VIS_PRIMITIVE_BITS = 8
+VIS_WIDE_PRIMITIVE_BITS = 6
 VIS_CLEAR = 0xFFFFFFFF
+STATUS_MESHLET_OVERFLOW, STATUS_BAD_GEOMETRY, STATUS_SURVIVOR_OVERFLOW, STATUS_ID_OVERFLOW = 1, 2, 4, 8
 
 # VSMPageState — Shaders/rmvsm.slang:16-28 ([Flags] enum)
 VSM_PAGE_VISIBLE = 1
@@ -147,6 +149,8 @@ class CreateInfo(C.Structure):
         ("hiz_height", C.c_uint32),
         ("alloc_reordered_indices", C.c_uint32),
         ("max_views", C.c_uint32),
+        ("max_mask_bits", C.c_uint32),
+        ("wide_ids", C.c_uint32),
     ]
 
 
@@ -172,6 +176,8 @@ class Outputs(C.Structure):
         ("view_visibility_bits", C.c_void_p),
         ("view_visible_counts", C.c_void_p),
         ("raster_triangle_count", C.c_void_p),
+        ("status_flags", C.c_void_p),
+        ("vis_primitive_bits", C.c_uint32),
     ]
 
 

@@ -20,7 +20,7 @@ SYMBOLS = [
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
     "oxc_decode_visbuffer", "oxc_build_hpb",
-    "oxc_get_outputs", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
+    "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
 ]
@@ -77,6 +77,8 @@ def load(build_if_missing=True):
     lib.oxc_decode_visbuffer.argtypes = [vp, vp, vp, vp, u32, u32, C.POINTER(abi.DecodeTargets), vp]
     lib.oxc_build_hpb.argtypes = [vp, vp, u32, u32, vp, u32, vp]
     lib.oxc_get_outputs.argtypes = [vp, C.POINTER(abi.Outputs)]
+    lib.oxc_check_status.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
+    lib.oxc_mark_hiz_dirty.argtypes = [vp]
     lib.oxc_copy.argtypes = [vp, vp, vp, u64, i32, vp]
     lib.oxc_sync.argtypes = [vp, vp]
     lib.oxc_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
@@ -196,9 +198,10 @@ class Context:
     """OxcContext wrapper.  `stream` is a raw cudaStream_t handle (int; 0 = default stream)."""
 
     def __init__(self, device, max_mesh_instances, max_meshlet_instances, hiz_w, hiz_h, alloc_reordered_indices=False,
-                 max_views=0, stream=0):
+                 max_views=0, stream=0, max_mask_bits=0, wide_ids=False):
         self.lib = load()
-        info = abi.CreateInfo(max_mesh_instances, max_meshlet_instances, hiz_w, hiz_h, int(alloc_reordered_indices), max_views)
+        info = abi.CreateInfo(max_mesh_instances, max_meshlet_instances, hiz_w, hiz_h, int(alloc_reordered_indices), max_views,
+                              max_mask_bits, int(wide_ids))
         h = C.c_void_p()
         _check(self.lib.oxc_create(device, C.byref(info), C.byref(h)), "oxc_create")
         self.h = h
@@ -327,6 +330,19 @@ class Context:
 
     def build_hpb(self, page_table_dev, size, layers, hpb_dev, levels):
         _check(self.lib.oxc_build_hpb(self.h, _ptr(page_table_dev), size, layers, _ptr(hpb_dev), levels, self.stream), "oxc_build_hpb")
+
+    def check_status(self):
+        """Raises OxcError when a kernel raised a sticky OXC_STATUS_* bit (and clears it); returns the flags (0) otherwise."""
+        f = C.c_uint32(0)
+        _check(self.lib.oxc_check_status(self.h, self.stream, C.byref(f)), "oxc_check_status")
+        return f.value
+
+    def status_flags(self):
+        """The sticky status word without raising / clearing."""
+        return int(self.download(self.out.status_flags, np.uint32, 1)[0])
+
+    def mark_hiz_dirty(self):
+        _check(self.lib.oxc_mark_hiz_dirty(self.h), "oxc_mark_hiz_dirty")
 
     # ---- plumbing ----
     def sync(self):

@@ -263,7 +263,7 @@ __global__ void k_lod_union_aabb(const OxcMesh* __restrict__ meshes, uint32_t n_
 // atomics (cull_meshes.slang:66-72): visibility.total and cull_meshlets_cmd.x = ceil(total / 64).
 __global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t* block_sums, uint32_t n_blocks,
                                                           OxcMeshletInstanceVisibility* vis,
-                                                          OxcDispatchIndirectCommand* cmd) {
+                                                          OxcDispatchIndirectCommand* cmd, uint32_t capacity, uint32_t* status) {
   __shared__ uint32_t warp_tot[32];
   __shared__ uint32_t carry_s;
   if (threadIdx.x == 0) carry_s = 0;
@@ -297,7 +297,11 @@ __global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t* block_sums, 
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    const uint32_t total = carry_s;
+    uint32_t total = carry_s;
+    if (total > capacity) { // backstop (oxc_set_scene already refuses scenes that cannot fit): clamp, never write out of bounds
+      total = capacity;
+      atomicOr(status, (uint32_t)OXC_STATUS_MESHLET_OVERFLOW);
+    }
     vis->total_visible_meshlet_instances = total;
     vis->early_visible_meshlet_instances = 0;
     vis->late_visible_meshlet_instances = 0;
@@ -312,7 +316,7 @@ __global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t* block_sums, 
 __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_expand_meshlet_instances(const uint32_t* __restrict__ counts,
                                                                                  const uint32_t* __restrict__ block_offsets,
                                                                                  uint32_t first, uint32_t count,
-                                                                                 OxcMeshletInstance* out) {
+                                                                                 OxcMeshletInstance* out, uint32_t capacity) {
   __shared__ uint32_t offs[CULL_MESHES_THREADS];
   __shared__ uint32_t cnts[CULL_MESHES_THREADS];
   __shared__ uint32_t warp_tot[CULL_MESHES_THREADS / 32];
@@ -338,7 +342,7 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_expand_meshlet_instance
     if (n == 0) continue;
     const uint32_t base = offs[k];
     const uint32_t mi = first + blockIdx.x * CULL_MESHES_THREADS + k;
-    for (uint32_t j = lane; j < n; j += 32) o2[base + j] = make_uint2(mi, j);
+    for (uint32_t j = lane; j < n && base + j < capacity; j += 32) o2[base + j] = make_uint2(mi, j);
   }
 }
 
@@ -784,8 +788,14 @@ __global__ void __launch_bounds__(CULL_THREADS) k_cull_meshlets_hpb(const __grid
   }
 }
 
+// projection_view of every view, passed BY VALUE as a kernel parameter (1 KB): no host->device copy of a caller / stack
+// array is recorded, so the entry points are safe under stream capture
+struct ViewMatrices {
+  float m[OXC_MAX_VIEWS][16];
+};
+
 __global__ void k_prepare_inst_views(const OxcMeshInstance* __restrict__ mesh_instances, const OxcTransformWorld* __restrict__ transforms,
-                                     const float* __restrict__ view_pv /* [n_views][16] */, uint32_t n_views, uint32_t first,
+                                     const __grid_constant__ ViewMatrices view_pv, uint32_t n_views, uint32_t first,
                                      uint32_t count, uint32_t inst_stride, InstView* out) {
   const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
   if (local >= count) return;
@@ -797,7 +807,7 @@ __global__ void k_prepare_inst_views(const OxcMeshInstance* __restrict__ mesh_in
   for (uint32_t v = 0; v < n_views; v++) {
     float pv[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) pv[k] = view_pv[v * 16 + k];
+    for (int k = 0; k < 16; k++) pv[k] = view_pv.m[v][k];
     float4 rows[4], planes[6];
     mul_mm_rows(pv, w, rows);
     frustum_planes(rows, planes);
@@ -890,7 +900,7 @@ __global__ void k_reset_terrain_cmd(OxcDrawIndirectCommand* c) { c->vertex_count
 
 // per view planes for the multi-view cull: planes of mul(view.projection_view, world)
 __global__ void k_prepare_view_planes(const OxcMeshInstance* __restrict__ mesh_instances,
-                                      const OxcTransformWorld* __restrict__ transforms, const OxcCullCamera* __restrict__ views,
+                                      const OxcTransformWorld* __restrict__ transforms, const __grid_constant__ ViewMatrices views,
                                       uint32_t n_views, uint32_t first, uint32_t count, uint32_t inst_stride,
                                       InstPlanes* out) {
   const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
@@ -903,7 +913,7 @@ __global__ void k_prepare_view_planes(const OxcMeshInstance* __restrict__ mesh_i
   for (uint32_t v = 0; v < n_views; v++) {
     float pv[16];
 #pragma unroll
-    for (int k = 0; k < 16; k++) pv[k] = views[v].projection_view[k];
+    for (int k = 0; k < 16; k++) pv[k] = views.m[v][k];
     float4 rows[4], planes[6];
     mul_mm_rows(pv, w, rows);
     frustum_planes(rows, planes);

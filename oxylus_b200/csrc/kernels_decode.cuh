@@ -26,6 +26,7 @@ struct DecodeParams {
   float4 pv_row[4];
   float res_x, res_y;
   uint32_t width, height;
+  uint32_t prim_bits; // 8 (visbuffer.slang:9-14) or 6 (OxcCreateInfo::wide_ids)
 };
 
 // scene.slang:486-489 decode_normal
@@ -44,11 +45,11 @@ __global__ void __launch_bounds__(DECODE_TX* DECODE_TY) k_decode_visbuffer(const
   const size_t pix = (size_t)y * p.width + x;
   float4 L = make_float4(0.f, 0.f, 0.f, 0.f), DX = L, DY = L, UN = L, UG = L;
   const uint32_t texel = p.vis64 ? (uint32_t)(__ldg(&p.vis64[pix]) & 0xFFFFFFFFull) : __ldg(&p.vis32[pix]); // :96
-  const uint32_t gid = (texel >> OXC_VIS_PRIMITIVE_BITS) & 0xFFFFFFu;                                       // visbuffer.slang:34
-  const uint32_t tri = texel & OXC_VIS_PRIMITIVE_MASK;
+  const uint32_t gid = texel >> p.prim_bits;                                                                // visbuffer.slang:34
+  const uint32_t tri = texel & ((1u << p.prim_bits) - 1u);
   const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
   const uint32_t mii = gid - id_base;
-  const bool discard = texel == 0xFFFFFFFFu || gid == 0xFFFFFEu || gid < id_base ||
+  const bool discard = texel == 0xFFFFFFFFu || gid == (0xFFFFFFFEu >> p.prim_bits) /* terrain sentinel, visbuffer.slang:16-20 */ || gid < id_base ||
                        mii >= __ldg(&p.vis->total_visible_meshlet_instances); // :97-99 (+ range guard)
   if (!discard) {
     const uint2 mi = __ldg(reinterpret_cast<const uint2*>(p.meshlet_instances) + mii); // :103

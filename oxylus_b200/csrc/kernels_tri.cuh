@@ -37,12 +37,16 @@ struct TriParams {
   uint4* big_queue;          // BIG_WORDS/4 uint4 per entry
   uint32_t* big_counters;
   uint32_t big_capacity;
+  uint32_t prim_bits;        // triangle bits of the vis-buffer word: 8 (visbuffer.slang:9-14) or 6 (OxcCreateInfo::wide_ids)
+  uint32_t small_primitive_cull; // 1: triangles whose snapped bounding box holds no sample centre are culled before they are counted
+  uint32_t* status;          // sticky OXC_STATUS_* bits
 };
 
 struct MeshletWork {
   uint32_t data_id;    // global meshlet instance id (<< 8 | tri later)
   uint32_t tri_count;
   uint32_t tri_offset; // byte offset of the micro indices
+  uint32_t vertex_count;
   const uint32_t* micro;
 };
 
@@ -60,6 +64,7 @@ OXC_DI MeshletWork load_meshlet(const TriParams& p, uint32_t slot, uint32_t id_b
   const uint32_t vertex_offset = m.x, vertex_count = min(m.z, (uint32_t)OXC_MESHLET_MAX_VERTICES);
   w.tri_offset = m.y;
   w.tri_count = min(m.w, (uint32_t)OXC_MESHLET_MAX_PRIMITIVES);
+  w.vertex_count = vertex_count;
   w.micro = g->local_triangle_indices;
   w.data_id = gid;
   const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
@@ -83,9 +88,11 @@ OXC_DI uint32_t micro_index(const uint32_t* __restrict__ buf, uint32_t byte_offs
 // cull_triangles.slang:59-69
 OXC_DI bool triangle_passes(const MeshletWork& w, uint32_t t, const float4* clip_s, float4& c0, float4& c1, float4& c2) {
   const uint32_t base = w.tri_offset + t * 3u;
-  c0 = clip_s[micro_index(w.micro, base + 0u)];
-  c1 = clip_s[micro_index(w.micro, base + 1u)];
-  c2 = clip_s[micro_index(w.micro, base + 2u)];
+  const uint32_t i0 = micro_index(w.micro, base + 0u), i1 = micro_index(w.micro, base + 1u), i2 = micro_index(w.micro, base + 2u);
+  if (max(i0, max(i1, i2)) >= w.vertex_count) return false; // malformed meshlet: never index past the transformed vertices
+  c0 = clip_s[i0];
+  c1 = clip_s[i1];
+  c2 = clip_s[i2];
   const bool in_front = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f;
   return in_front && !triangle_backface(c0, c1, c2);
 }
@@ -179,23 +186,24 @@ OXC_DI int edge_bias_bit(int ax, int ay, int bx, int by) {
   return ((dy > 0) || (dy == 0 && dx < 0)) ? 0 : 1;
 }
 
-// steps 2-4 of the raster spec; false = nothing to draw.  Rejections commute, so the cheapest go first:
+// steps 2-4 of the raster spec; anything but TRI_DRAW = nothing to draw.  Rejections commute, so the cheapest go first:
 // the bounding box (most sub-pixel triangles cover no sample centre) before the signed area.
-OXC_DI bool tri_setup(const ScreenVert v0, const ScreenVert v1, const ScreenVert v2, uint32_t W, uint32_t H, TriSetup& s) {
-  if (v0.fx == INT_MIN || v1.fx == INT_MIN || v2.fx == INT_MIN) return false;
+enum : int { TRI_DRAW = 0, TRI_INVALID_VERTEX = 1, TRI_NO_SAMPLE = 2, TRI_BACK_OR_DEGENERATE = 3 };
+OXC_DI int tri_setup(const ScreenVert v0, const ScreenVert v1, const ScreenVert v2, uint32_t W, uint32_t H, TriSetup& s) {
+  if (v0.fx == INT_MIN || v1.fx == INT_MIN || v2.fx == INT_MIN) return TRI_INVALID_VERTEX;
   const int minx = min(v0.fx, min(v1.fx, v2.fx)), maxx = max(v0.fx, max(v1.fx, v2.fx));
   const int miny = min(v0.fy, min(v1.fy, v2.fy)), maxy = max(v0.fy, max(v1.fy, v2.fy));
   s.px0 = max(0, (minx - 128 + 255) >> 8);
   s.px1 = min((int)W - 1, (maxx - 128) >> 8);
   s.py0 = max(0, (miny - 128 + 255) >> 8);
   s.py1 = min((int)H - 1, (maxy - 128) >> 8);
-  if (s.px1 < s.px0 || s.py1 < s.py0) return false; // covers no sample centre (== small-primitive cull)
+  if (s.px1 < s.px0 || s.py1 < s.py0) return TRI_NO_SAMPLE; // the snapped bounding box holds no sample centre
   // extent < 2^14 sub-pixels per axis: every edge-function value inside the bbox fits 32 bits
   s.narrow = (maxx - minx) < 16384 && (maxy - miny) < 16384;
   long long area2;
   if (s.narrow) area2 = (long long)((v1.fx - v0.fx) * (v2.fy - v0.fy) - (v1.fy - v0.fy) * (v2.fx - v0.fx));
   else area2 = orient2d(v0.fx, v0.fy, v1.fx, v1.fy, v2.fx, v2.fy);
-  if (area2 >= 0) return false;
+  if (area2 >= 0) return TRI_BACK_OR_DEGENERATE;
   s.ax = v0.fx; s.ay = v0.fy; s.bx = v2.fx; s.by = v2.fy; s.cx = v1.fx; s.cy = v1.fy;
   const float fa_ = (float)(-area2);
   s.za = v0.z;
@@ -203,7 +211,7 @@ OXC_DI bool tri_setup(const ScreenVert v0, const ScreenVert v1, const ScreenVert
   s.dzc = fd(fs(v1.z, v0.z), fa_);
   s.bias = edge_bias_bit(s.bx, s.by, s.cx, s.cy) | (edge_bias_bit(s.cx, s.cy, s.ax, s.ay) << 1) |
            (edge_bias_bit(s.ax, s.ay, s.bx, s.by) << 2);
-  return true;
+  return TRI_DRAW;
 }
 
 // steps 5-6 given the three edge-function values at the pixel centre
@@ -284,6 +292,7 @@ OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* v
 #define OXC_RASTER_BATCH 8
 #endif
 constexpr int RASTER_BATCH = OXC_RASTER_BATCH;       // meshlets per work grab
+static_assert(RASTER_BATCH >= 1 && RASTER_BATCH <= 32, "one header per lane: a grab holds at most 32 meshlets");
 constexpr int RASTER_BIG_PIXELS = OXC_RASTER_BIG_PIXELS; // bbox area above which the whole warp rasterises the triangle together
 
 // Header of one surviving meshlet, fetched by ONE lane (32 headers in flight per warp): the 4-level pointer
@@ -412,30 +421,16 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
   // and RASTER_BATCH), so the kernel ends with single-meshlet grabs.  With a fixed batch of 8 a warp's last grab was 1/7 of
   // its whole share and the average SM sat idle for the last third of the launch (ncu: sm__cycles_active 67 % of elapsed).
   const uint32_t n_warps2 = gridDim.x * TRI_WARPS * 2u;
-#ifdef OXC_RASTER_STATIC_SCHEDULE
-  // experiment: no work counter at all — grab k of warp w is the k-th block of RASTER_BATCH survivors
-  // in a warp-strided order.  Tests whether the same-address atomics are what the late pass waits on.
-  uint32_t static_iter = 0;
-  const uint32_t warp_global = blockIdx.x * TRI_WARPS + warp, n_warps = gridDim.x * TRI_WARPS;
-#endif
   for (;;) {
     uint32_t g0 = 0, batch = 1;
-#ifdef OXC_RASTER_STATIC_SCHEDULE
-    batch = min((uint32_t)RASTER_BATCH, max(1u, count / n_warps2));
-    g0 = (static_iter++ * n_warps + warp_global) * batch;
-#else
     if (lane == 0) {
       const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(p.work_counter); // heuristic only: a stale value is harmless
       const uint32_t rem = count > seen ? count - seen : 0u;
       batch = min((uint32_t)RASTER_BATCH, max(1u, rem / n_warps2));
-#ifdef OXC_RASTER_LATE_FIXED_BATCH
-      if (p.late) batch = OXC_RASTER_LATE_FIXED_BATCH; // experiment: fewer same-address atomics in the late pass
-#endif
       g0 = atomicAdd(p.work_counter, batch);
     }
     g0 = __shfl_sync(0xffffffffu, g0, 0);
     batch = __shfl_sync(0xffffffffu, batch, 0);
-#endif
     if (g0 >= count) break;
     const uint32_t nb = min(batch, count - g0);
     MeshletHeader mine;
@@ -482,12 +477,18 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
         if (t < w.tri_count) {
           const uint32_t base = w.tri_offset + t * 3u;
           const uint32_t i0 = micro_index(w.micro, base + 0u), i1 = micro_index(w.micro, base + 1u), i2 = micro_index(w.micro, base + 2u);
-          const float4 c0 = clip_s[i0], c1 = clip_s[i1], c2 = clip_s[i2];
-          pass = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f && !triangle_backface(c0, c1, c2); // cull_triangles.slang:68-69
-          if (pass) draw = tri_setup(scr_s[i0], scr_s[i1], scr_s[i2], p.width, p.height, s);
+          if (max(i0, max(i1, i2)) < w.vertex_count) { // malformed meshlets never index past the transformed vertices
+            const float4 c0 = clip_s[i0], c1 = clip_s[i1], c2 = clip_s[i2];
+            pass = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f && !triangle_backface(c0, c1, c2); // cull_triangles.slang:68-69
+            if (pass) {
+              const int why = tri_setup(scr_s[i0], scr_s[i1], scr_s[i2], p.width, p.height, s);
+              draw = why == TRI_DRAW;
+              if (why == TRI_NO_SAMPLE && p.small_primitive_cull) pass = false; // north_star small-primitive cull (opt-in)
+            }
+          }
         }
         kept += pass ? 1u : 0u;
-        const uint32_t data = (w.gid << OXC_VIS_PRIMITIVE_BITS) | (t & OXC_VIS_PRIMITIVE_MASK);
+        const uint32_t data = (w.gid << p.prim_bits) | t;
         const int bw = draw ? s.px1 - s.px0 + 1 : 0, bh = draw ? s.py1 - s.py0 + 1 : 0;
         bool big = draw && (bw * bh > RASTER_BIG_PIXELS);
         if (draw && !big) raster_small(s, data, p.visbuf, p.width);
@@ -581,11 +582,11 @@ __global__ void __launch_bounds__(TRI_THREADS) k_raster_clip_pass(const __grid_c
           n = m;
           cur ^= 1;
         }
-        const uint32_t data = (w.data_id << OXC_VIS_PRIMITIVE_BITS) | (t & OXC_VIS_PRIMITIVE_MASK);
+        const uint32_t data = (w.data_id << p.prim_bits) | t;
         for (int i = 1; i + 1 < n; i++) {
           TriSetup s;
-          if (!tri_setup(to_screen(poly[cur][0], fW, fH), to_screen(poly[cur][i], fW, fH), to_screen(poly[cur][i + 1], fW, fH), p.width,
-                         p.height, s))
+          if (tri_setup(to_screen(poly[cur][0], fW, fH), to_screen(poly[cur][i], fW, fH), to_screen(poly[cur][i + 1], fW, fH), p.width,
+                        p.height, s) != TRI_DRAW)
             continue;
           const int bw = s.px1 - s.px0 + 1, bh = s.py1 - s.py0 + 1;
           if (bw * bh > RASTER_BIG_PIXELS && p.big_queue && big_push(p, s, data)) continue; // spread over the GPU by k_raster_big

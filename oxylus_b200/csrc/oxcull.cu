@@ -133,16 +133,18 @@ struct OxcContext {
   bool id_base_auto = false;
   // multiview
   InstPlanes* d_view_planes = nullptr;
-  OxcCullCamera* d_views = nullptr;
   uint32_t* d_view_bits = nullptr;
   uint32_t* d_view_counts = nullptr;
   InstView* d_inst_views = nullptr; // shadow-clipmap cull: [max_views][max_mesh_instances]
-  float* d_view_pv = nullptr;       // [OXC_MAX_VIEWS][16]
   // launch shapes
   int occ_cull[2][2][2] = {};
   bool hiz_zero = true; // the pyramid holds the cleared (all-zero) image: lets the early pass skip the Hi-Z fetches
   int occ_tri = 1, occ_raster = 1, occ_mv = 1;
   bool hpb_smem_opt_in = false;
+  uint32_t* d_status = nullptr;   // sticky OXC_STATUS_* bits raised by kernels
+  std::vector<uint64_t> id_prefix; // [I + 1] prefix sums of the largest-LOD meshlet count per mesh instance (host side)
+  uint64_t scene_id_bound = 0;    // upper bound of the GLOBAL meshlet-instance id range (sum over all mesh instances of the largest LOD)
+  uint32_t prim_bits = OXC_VIS_PRIMITIVE_BITS; // triangle bits of the vis-buffer word (8 = reference, 6 = wide_ids)
 };
 
 namespace {
@@ -163,6 +165,17 @@ void shard_range(const OxcContext* c, uint32_t cam_count, uint32_t* first, uint3
   if (hi < lo) hi = lo;
   *first = lo;
   *count = hi - lo;
+}
+
+// meshlet instances the mesh instances [first, first + count) can emit at most (count 0xFFFFFFFF = to the end)
+uint64_t shard_need(const std::vector<uint64_t>& prefix, uint32_t first, uint32_t count) {
+  if (prefix.empty()) return 0;
+  const uint64_t n = prefix.size() - 1;
+  const uint64_t lo = first < n ? first : n;
+  uint64_t hi = n;
+  if (count != 0xFFFFFFFFu && (uint64_t)first + count < hi) hi = (uint64_t)first + count;
+  if (hi < lo) hi = lo;
+  return prefix[hi] - prefix[lo];
 }
 
 bool same_camera(const OxcCullCamera& a, const OxcCullCamera& b) {
@@ -228,7 +241,7 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   TRY(dalloc(&c->d_block_sums, (size_t)(I + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS + 1));
   TRY(dalloc(&c->d_meshlet_instances, (size_t)N + CULL_TILE)); // + one tile: full-size bulk copies of the last tile stay in bounds
   TRY(dalloc(&c->d_visible, (size_t)N));
-  c->mask_words = (N + 31) / 32; // RendererInstance.cpp:1651
+  c->mask_words = ((info->max_mask_bits > N ? info->max_mask_bits : N) + 31) / 32; // RendererInstance.cpp:1651
   TRY(dalloc(&c->d_mask, (size_t)c->mask_words));
   TRY(dalloc(&c->d_vis, 1));
   TRY(dalloc(&c->d_cull_meshlets_cmd, 1));
@@ -244,14 +257,14 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   TRY(dalloc(&c->d_big_queue, (size_t)c->big_capacity * 4));
   TRY(dalloc(&c->d_big_counters, 2));
   TRY(dalloc(&c->d_id_base_auto, 1));
+  TRY(dalloc(&c->d_status, 1));
+  c->prim_bits = info->wide_ids ? OXC_VIS_WIDE_PRIMITIVE_BITS : OXC_VIS_PRIMITIVE_BITS;
   if (info->alloc_reordered_indices) TRY(dalloc(&c->d_reordered, (size_t)N * OXC_MESHLET_MAX_PRIMITIVES * 3));
   if (info->max_views > 1) {
     TRY(dalloc(&c->d_view_planes, (size_t)I * info->max_views));
-    TRY(dalloc(&c->d_views, (size_t)OXC_MAX_VIEWS));
     TRY(dalloc(&c->d_view_bits, (size_t)N));
     TRY(dalloc(&c->d_view_counts, (size_t)OXC_MAX_VIEWS));
     TRY(dalloc(&c->d_inst_views, (size_t)I * info->max_views));
-    TRY(dalloc(&c->d_view_pv, (size_t)OXC_MAX_VIEWS * 16));
   }
   // Hi-Z pyramid: levels = min(floor(log2(max(w,h))) + 1, 13)  (Texture.hpp:144-146, RendererInstance.cpp:583-586)
   {
@@ -276,6 +289,7 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   CK(cudaMemset(c->d_hiz, 0, (size_t)c->hiz_total * 4));
   CK(cudaMemset(c->d_vis, 0, sizeof(OxcMeshletInstanceVisibility)));
   CK(cudaMemset(c->d_tri_counter, 0, 8));
+  CK(cudaMemset(c->d_status, 0, 4));
   OxcDispatchIndirectCommand one{0, 1, 1};
   CK(cudaMemcpy(c->d_cull_meshlets_cmd, &one, sizeof one, cudaMemcpyHostToDevice));
   CK(cudaMemcpy(c->d_cull_triangles_cmd, &one, sizeof one, cudaMemcpyHostToDevice));
@@ -303,8 +317,8 @@ void oxc_destroy(OxcContext* c) {
   cudaFree(c->d_lod_aabb); cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
   cudaFree(c->d_meshlet_instances); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
-  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_big_queue); cudaFree(c->d_big_counters); cudaFree(c->d_id_base_auto); cudaFree(c->d_hiz);
-  cudaFree(c->d_view_planes); cudaFree(c->d_views); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts); cudaFree(c->d_inst_views); cudaFree(c->d_view_pv);
+  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_big_queue); cudaFree(c->d_big_counters); cudaFree(c->d_id_base_auto); cudaFree(c->d_status); cudaFree(c->d_hiz);
+  cudaFree(c->d_view_planes); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts); cudaFree(c->d_inst_views);
   delete c;
 }
 
@@ -346,6 +360,43 @@ int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
       if (d.meshlets & 15u) { relocs.push_back({rec, d.meshlets, (uint64_t)d.meshlet_count * sizeof(OxcMeshlet), 0}); reloc_bytes += (relocs.back().size + 15u) & ~15ull; }
       if (d.meshlet_bounds & 15u) { relocs.push_back({rec, d.meshlet_bounds, (uint64_t)d.meshlet_count * sizeof(OxcMeshletBounds), 1}); reloc_bytes += (relocs.back().size + 15u) & ~15ull; }
     }
+  }
+  // Instance table: every index in range, and the meshlet instances / mask bits the scene can ever need fit the
+  // create-time capacities — whatever LOD the mesh-level cull selects.  The reference sizes these buffers from the scene itself
+  // (RendererInstance.cpp:1651-1665,1717-1732); here they are create-time capacities, so an oversized scene is an error, not a
+  // device fault.  (The kernels additionally clamp and raise OXC_STATUS_MESHLET_OVERFLOW, see k_scan_block_sums.)
+  uint64_t id_bound = 0;
+  std::vector<uint64_t> id_prefix((size_t)sc->mesh_instance_count + 1, 0);
+  {
+    std::vector<uint32_t> max_lod_count(sc->mesh_count, 0);
+    for (uint32_t m = 0; m < sc->mesh_count; m++) {
+      const OxcMeshLOD* lods = reinterpret_cast<const OxcMeshLOD*>(sc->blob + sc->meshes[m].lods);
+      for (uint32_t l = 0; l < sc->meshes[m].lod_count; l++) {
+        OxcMeshLOD d;
+        memcpy(&d, &lods[l], sizeof d);
+        if (d.meshlet_count > max_lod_count[m]) max_lod_count[m] = d.meshlet_count;
+      }
+    }
+    const uint64_t mask_bits = (uint64_t)c->mask_words * 32u;
+    for (uint32_t i = 0; i < sc->mesh_instance_count; i++) {
+      const OxcMeshInstance& mi = sc->mesh_instances[i];
+      if (mi.mesh_index >= sc->mesh_count) return fail(OXC_E_INVALID, "mesh instance %u: mesh_index %u >= mesh_count %u", i, mi.mesh_index, sc->mesh_count);
+      if (mi.transform_index >= sc->transform_count)
+        return fail(OXC_E_INVALID, "mesh instance %u: transform_index %u >= transform_count %u", i, mi.transform_index, sc->transform_count);
+      if (mi.lod_index >= sc->meshes[mi.mesh_index].lod_count)
+        return fail(OXC_E_INVALID, "mesh instance %u: lod_index %u >= lod_count %u", i, mi.lod_index, sc->meshes[mi.mesh_index].lod_count);
+      const uint32_t n = max_lod_count[mi.mesh_index];
+      if ((uint64_t)mi.meshlet_instance_visibility_offset + n > mask_bits)
+        return fail(OXC_E_CAPACITY, "mesh instance %u: visibility offset %u + %u meshlets exceeds the %llu mask bits of max_meshlet_instances %u", i,
+                    mi.meshlet_instance_visibility_offset, n, (unsigned long long)mask_bits, c->info.max_meshlet_instances);
+      id_bound += n;
+      id_prefix[i + 1] = id_bound;
+    }
+    // the whole scene need not fit one context — a shard only expands its own range —, but the context's range must
+    const uint64_t need = shard_need(id_prefix, c->shard_first, c->shard_count);
+    if (need > c->info.max_meshlet_instances)
+      return fail(OXC_E_CAPACITY, "mesh instances [%u, +%u) can emit %llu meshlet instances > max_meshlet_instances %u", c->shard_first,
+                  c->shard_count, (unsigned long long)need, c->info.max_meshlet_instances);
   }
   // device copy of the blob: the caller's bytes, or (8-byte aligned tables present) a patched copy with those tables
   // appended at 16-byte aligned offsets and the MeshLOD records pointing at the copies
@@ -398,6 +449,8 @@ int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
     LAUNCHED();
   }
   c->mesh_count = sc->mesh_count; c->mesh_instance_count = sc->mesh_instance_count; c->transform_count = sc->transform_count;
+  c->scene_id_bound = id_bound;
+  c->id_prefix.swap(id_prefix);
   c->scene_set = true;
   c->cache_valid = false;
   // instance table changed => zero_fill_pass on the mask (RendererInstance.cpp:1651-1665)
@@ -433,6 +486,9 @@ int oxc_clear_hiz(OxcContext* c, void* stream) {
 
 int oxc_set_shard(OxcContext* c, uint32_t first, uint32_t count, const uint32_t* id_base_dev) {
   if (!c) return fail(OXC_E_INVALID, "null context");
+  if (c->scene_set && shard_need(c->id_prefix, first, count) > c->info.max_meshlet_instances)
+    return fail(OXC_E_CAPACITY, "mesh instances [%u, +%u) can emit %llu meshlet instances > max_meshlet_instances %u", first, count,
+                (unsigned long long)shard_need(c->id_prefix, first, count), c->info.max_meshlet_instances);
   c->shard_first = first; c->shard_count = count; c->id_base = id_base_dev; c->id_base_auto = false;
   c->cache_valid = false;
   return OXC_OK;
@@ -440,6 +496,9 @@ int oxc_set_shard(OxcContext* c, uint32_t first, uint32_t count, const uint32_t*
 
 int oxc_set_shard_auto(OxcContext* c, uint32_t first, uint32_t count) {
   if (!c) return fail(OXC_E_INVALID, "null context");
+  if (c->scene_set && shard_need(c->id_prefix, first, count) > c->info.max_meshlet_instances)
+    return fail(OXC_E_CAPACITY, "mesh instances [%u, +%u) can emit %llu meshlet instances > max_meshlet_instances %u", first, count,
+                (unsigned long long)shard_need(c->id_prefix, first, count), c->info.max_meshlet_instances);
   c->shard_first = first; c->shard_count = count; c->id_base = c->d_id_base_auto; c->id_base_auto = true;
   c->cache_valid = false;
   return OXC_OK;
@@ -469,10 +528,10 @@ int oxc_cull_meshes(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, voi
   } else {
     k_cull_meshes<<<n_blocks, CULL_MESHES_THREADS, 0, s>>>(p);
     LAUNCHED();
-    k_scan_block_sums<<<1, 1024, 0, s>>>(c->d_block_sums, n_blocks, c->d_vis, c->d_cull_meshlets_cmd);
+    k_scan_block_sums<<<1, 1024, 0, s>>>(c->d_block_sums, n_blocks, c->d_vis, c->d_cull_meshlets_cmd, c->info.max_meshlet_instances, c->d_status);
     LAUNCHED();
     k_expand_meshlet_instances<<<n_blocks, CULL_MESHES_THREADS, 0, s>>>(c->d_counts, c->d_block_sums, p.first, p.count,
-                                                                      c->d_meshlet_instances);
+                                                                      c->d_meshlet_instances, c->info.max_meshlet_instances);
     LAUNCHED();
   }
   c->cached_cam = *cam;
@@ -570,14 +629,16 @@ static int tri_common(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, c
   p->meshlet_instances = c->d_meshlet_instances; p->inst = c->d_inst; p->geom = c->d_geom; p->vis = c->d_vis;
   p->visible_indices = c->d_visible; p->tri_cmd = c->d_cull_triangles_cmd; p->id_base = c->id_base; p->late = (flags & OXC_CULL_LATE_PASS) ? 1u : 0u;
   p->reordered_indices = c->d_reordered; p->draw_cmd = c->d_draw_cmd; p->tri_counter = c->d_tri_counter;
+  p->prim_bits = c->prim_bits; p->status = c->d_status; p->small_primitive_cull = 0;
   return OXC_OK;
 }
 
 int oxc_cull_triangles(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, void* stream) {
   if (!c || !cam) return fail(OXC_E_INVALID, "null argument");
   if (!c->d_reordered) return fail(OXC_E_STATE, "context created without alloc_reordered_indices");
-  if (c->info.max_meshlet_instances > (1u << 24))
-    return fail(OXC_E_CAPACITY, "24-bit meshlet instance ids (visbuffer.slang:9-10) overflow above 2^24 instances");
+  if (c->scene_id_bound > (1ull << (32u - OXC_VIS_PRIMITIVE_BITS)))
+    return fail(OXC_E_CAPACITY, "the scene can emit %llu meshlet instances: ids overflow the %u id bits of the vis-buffer word (visbuffer.slang:9-10)%s",
+                (unsigned long long)c->scene_id_bound, 24u, " (the reordered index buffer always uses the reference packing)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(c->device));
   TriParams p{};
@@ -607,14 +668,17 @@ int oxc_clear_visbuffer(OxcContext* c, uint64_t* vis, uint32_t w, uint32_t h, vo
 
 int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t w, uint32_t h, uint64_t* vis,
                          int small_primitive_cull, void* stream) {
-  (void)small_primitive_cull; // triangles that cover no sample centre never reach the pixel loop either way
   if (!c || !cam || !vis) return fail(OXC_E_INVALID, "null argument");
+  if (c->scene_id_bound > (1ull << (32u - c->prim_bits)))
+    return fail(OXC_E_CAPACITY, "the scene can emit %llu meshlet instances: ids overflow the %u id bits of the vis-buffer word (visbuffer.slang:9-10)%s",
+                (unsigned long long)c->scene_id_bound, 32u - c->prim_bits, c->info.wide_ids ? "" : "; create the context with wide_ids = 1 (26 + 6 bit packing)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(c->device));
   TriParams p{};
   int rc = tri_common(c, cam, flags, s, &p);
   if (rc != OXC_OK) return rc;
   p.visbuf = reinterpret_cast<unsigned long long*>(vis); p.width = w; p.height = h;
+  p.small_primitive_cull = small_primitive_cull ? 1u : 0u;
   p.work_counter = c->d_raster_work;
   CK(cudaMemsetAsync(c->d_raster_work, 0, 4, s));
   uint32_t tiles = (c->info.max_meshlet_instances + TRI_WARPS - 1) / TRI_WARPS;
@@ -633,6 +697,9 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
 int oxc_raster_visbuffer_clip_pass(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t w, uint32_t h, uint64_t* vis,
                                    void* stream) {
   if (!c || !cam || !vis) return fail(OXC_E_INVALID, "null argument");
+  if (c->scene_id_bound > (1ull << (32u - c->prim_bits)))
+    return fail(OXC_E_CAPACITY, "the scene can emit %llu meshlet instances: ids overflow the %u id bits of the vis-buffer word (visbuffer.slang:9-10)%s",
+                (unsigned long long)c->scene_id_bound, 32u - c->prim_bits, c->info.wide_ids ? "" : "; create the context with wide_ids = 1 (26 + 6 bit packing)");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(c->device));
   TriParams p{};
@@ -687,13 +754,14 @@ int oxc_cull_meshlets_multiview(OxcContext* c, const OxcCullCamera* views, uint3
   if (!c->scene_set || !c->cache_valid) return fail(OXC_E_STATE, "oxc_cull_meshes must run first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(c->device));
-  CK(cudaMemcpyAsync(c->d_views, views, (size_t)n_views * sizeof(OxcCullCamera), cudaMemcpyHostToDevice, s));
+  ViewMatrices vm{};
+  for (uint32_t v = 0; v < n_views; v++) memcpy(vm.m[v], views[v].projection_view, sizeof vm.m[v]);
   CK(cudaMemsetAsync(c->d_view_counts, 0, OXC_MAX_VIEWS * 4, s));
   uint32_t first, count;
   shard_range(c, c->cached_cam.mesh_instance_count, &first, &count);
   const uint32_t stride = c->info.max_mesh_instances;
   if (count) {
-    k_prepare_view_planes<<<(count + 127) / 128, 128, 0, s>>>(c->d_mesh_instances, c->d_transforms, c->d_views, n_views, first,
+    k_prepare_view_planes<<<(count + 127) / 128, 128, 0, s>>>(c->d_mesh_instances, c->d_transforms, vm, n_views, first,
                                                              count, stride, c->d_view_planes);
     LAUNCHED();
   }
@@ -758,20 +826,19 @@ int oxc_cull_meshlets_hpb(OxcContext* c, const OxcCullCamera* cam, const OxcVirt
   CK(cudaSetDevice(c->device));
   int rc = refresh_inst_cache(c, cam, s); // InstCull for the coarse view
   if (rc != OXC_OK) return rc;
-  float pv[OXC_MAX_VIEWS][16];
+  ViewMatrices vm{};
   HpbParams p{};
   for (uint32_t v = 0; v < n; v++) {
-    memcpy(pv[v], clipmaps[v].projection_view_mat, sizeof pv[v]);
+    memcpy(vm.m[v], clipmaps[v].projection_view_mat, sizeof vm.m[v]);
     p.z_near[v] = clipmaps[v].z_near;
     p.page_offset[v][0] = clipmaps[v].page_offset[0]; p.page_offset[v][1] = clipmaps[v].page_offset[1];
     if (dirty[v]) p.dirty_mask |= 1u << v;
   }
-  CK(cudaMemcpyAsync(c->d_view_pv, pv, (size_t)n * 16 * sizeof(float), cudaMemcpyHostToDevice, s));
   uint32_t first, count;
   shard_range(c, c->cached_cam.mesh_instance_count, &first, &count);
   const uint32_t stride = c->info.max_mesh_instances;
   if (count) {
-    k_prepare_inst_views<<<(count + 127) / 128, 128, 0, s>>>(c->d_mesh_instances, c->d_transforms, c->d_view_pv, n, first, count, stride, c->d_inst_views);
+    k_prepare_inst_views<<<(count + 127) / 128, 128, 0, s>>>(c->d_mesh_instances, c->d_transforms, vm, n, first, count, stride, c->d_inst_views);
     LAUNCHED();
   }
   k_set_cmd3<<<1, 1, 0, s>>>(c->d_cull_triangles_cmd, 0, 1, 1); // CullGeometry.cpp:125-127
@@ -809,6 +876,9 @@ int oxc_decode_visbuffer(OxcContext* c, const OxcCullCamera* cam, const uint64_t
   if (!c || !cam || !t) return fail(OXC_E_INVALID, "null argument");
   if ((vis64_dev == nullptr) == (vis32_dev == nullptr)) return fail(OXC_E_INVALID, "exactly one of vis64_dev / vis32_dev");
   if (!c->scene_set) return fail(OXC_E_STATE, "oxc_set_scene first");
+  if (c->scene_id_bound > (1ull << (32u - c->prim_bits)))
+    return fail(OXC_E_CAPACITY, "the scene can emit %llu meshlet instances: ids overflow the %u id bits of the vis-buffer word (visbuffer.slang:9-10)%s",
+                (unsigned long long)c->scene_id_bound, 32u - c->prim_bits, c->info.wide_ids ? "" : "; create the context with wide_ids = 1 (26 + 6 bit packing)");
   if (w == 0 || h == 0) return OXC_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(c->device));
@@ -822,7 +892,7 @@ int oxc_decode_visbuffer(OxcContext* c, const OxcCullCamera* cam, const uint64_t
   const float* m = cam->projection_view; // column-major: row i = (m[i], m[4+i], m[8+i], m[12+i])
   for (int i = 0; i < 4; i++) p.pv_row[i] = make_float4(m[i], m[4 + i], m[8 + i], m[12 + i]);
   p.res_x = cam->resolution[0]; p.res_y = cam->resolution[1];
-  p.width = w; p.height = h;
+  p.width = w; p.height = h; p.prim_bits = c->prim_bits;
   const dim3 grid((w + DECODE_TX - 1) / DECODE_TX, (h + DECODE_TY - 1) / DECODE_TY);
   k_decode_visbuffer<<<grid, dim3(DECODE_TX, DECODE_TY), 0, s>>>(p);
   LAUNCHED();
@@ -859,6 +929,29 @@ int oxc_build_hpb(OxcContext* c, const uint32_t* page_table_dev, uint32_t size, 
   return OXC_OK;
 }
 
+int oxc_check_status(OxcContext* c, void* stream, uint32_t* flags_out) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  uint32_t f = 0;
+  CK(cudaMemcpyAsync(&f, c->d_status, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (flags_out) *flags_out = f;
+  if (!f) return OXC_OK;
+  CK(cudaMemsetAsync(c->d_status, 0, 4, s));
+  if (f & (OXC_STATUS_MESHLET_OVERFLOW | OXC_STATUS_SURVIVOR_OVERFLOW | OXC_STATUS_ID_OVERFLOW))
+    return fail(OXC_E_CAPACITY, "device status 0x%x:%s%s%s", f, (f & OXC_STATUS_MESHLET_OVERFLOW) ? " cull_meshes exceeded max_meshlet_instances (clamped)" : "",
+                (f & OXC_STATUS_SURVIVOR_OVERFLOW) ? " a survivor list exceeded the gather capacity (truncated)" : "",
+                (f & OXC_STATUS_ID_OVERFLOW) ? " a meshlet-instance id overflowed the vis-buffer id bits" : "");
+  return fail(OXC_E_INVALID, "device status 0x%x: malformed geometry (micro index >= vertex_count or vertex index >= Mesh::vertex_count); such triangles are skipped", f);
+}
+
+int oxc_mark_hiz_dirty(OxcContext* c) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  c->hiz_zero = false;
+  return OXC_OK;
+}
+
 int oxc_get_outputs(OxcContext* c, OxcOutputs* o) {
   if (!c || !o) return fail(OXC_E_INVALID, "null argument");
   memset(o, 0, sizeof *o);
@@ -871,6 +964,8 @@ int oxc_get_outputs(OxcContext* c, OxcOutputs* o) {
   o->visibility_mask_words = c->mask_words;
   o->view_visibility_bits = c->d_view_bits; o->view_visible_counts = c->d_view_counts;
   o->raster_triangle_count = reinterpret_cast<uint64_t*>(c->d_tri_counter);
+  o->status_flags = c->d_status;
+  o->vis_primitive_bits = c->prim_bits;
   return OXC_OK;
 }
 

@@ -48,7 +48,7 @@ def test_struct_sizes_match_reference_layouts():
     # SceneGPU.hpp scalar-layout sizes
     assert abi.MESHLET_BOUNDS_DT.itemsize == 16 and abi.MESH_DT.itemsize == 64 and abi.MESH_LOD_DT.itemsize == 64
     assert abi.CULL_CAMERA_DT.itemsize == 96 and abi.MESH_INSTANCE_DT.itemsize == 20 and abi.VISIBILITY_DT.itemsize == 12
-    assert C.sizeof(abi.CreateInfo) == 24 and C.sizeof(abi.SceneDesc) == 64
+    assert C.sizeof(abi.CreateInfo) == 32 and C.sizeof(abi.SceneDesc) == 64
     assert abi.MESH_DT.fields["bounds"][1] == 40 and abi.MESH_LOD_DT.fields["error"][1] == 60
     assert abi.MESHLET_BOUNDS_DT.fields["aabb_extent"][1] == 8 and abi.MESHLET_BOUNDS_DT.fields["cone_cutoff"][1] == 15
 

@@ -915,9 +915,6 @@ def test_raster_big_triangle_queue_and_overflow(capi, orc):
         ctx.close()
 
 
-@pytest.mark.skipif(not __import__("os").environ.get("OXC_RUN_UNVERIFIED"),
-                    reason="oxc_raster_visbuffer_clip_pass was written after round 1's GPU budget was spent; "
-                           "OXC_RUN_UNVERIFIED=1 runs it — remove this mark once it has passed on a B200")
 def test_clip_pass_parity(capi, orc):
     """opt-in clip pass vs the oracle's clipped raster: a ground plane through the camera (coarse: 2 huge triangles; medium:
     24x24 quads, some of them crossing the near / side planes), drawn by oxc_raster_visbuffer + oxc_raster_visbuffer_clip_pass"""

@@ -23,7 +23,6 @@ from oxylus_b200 import abi, capi, dist as oxdist, pipeline, synth  # noqa: E402
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    os.environ.pop("NCCL_DEBUG", None)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
     sc = synth.make_scene(300_000, config_index=5, width=1280, height=720, n_unique_meshes=64)
