@@ -426,6 +426,8 @@ int oxc_build_hpb(OxcContext* ctx, const uint32_t* page_table_dev, uint32_t page
                   uint8_t* hpb_dev, uint32_t hpb_levels, void* stream);
 
 int oxc_get_outputs(OxcContext* ctx, OxcOutputs* out);
+/* Instrumentation hook: 128 u64 counters that builds with -DOXC_RASTER_STATS fill (tools/raster_stats.py); zero otherwise. */
+void* oxc_debug_stats_ptr(OxcContext* ctx);
 
 /* Plumbing for hosts without their own CUDA bindings (the ctypes tests / bench): async copy on `stream`
  * (kind 0 = host->device, 1 = device->host, 2 = device->device), stream sync, raw device allocations. */

@@ -20,7 +20,7 @@ SYMBOLS = [
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
     "oxc_decode_visbuffer", "oxc_build_hpb",
-    "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
+    "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_debug_stats_ptr", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
 ]
@@ -79,6 +79,8 @@ def load(build_if_missing=True):
     lib.oxc_get_outputs.argtypes = [vp, C.POINTER(abi.Outputs)]
     lib.oxc_check_status.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
     lib.oxc_mark_hiz_dirty.argtypes = [vp]
+    lib.oxc_debug_stats_ptr.argtypes = [vp]
+    lib.oxc_debug_stats_ptr.restype = vp
     lib.oxc_copy.argtypes = [vp, vp, vp, u64, i32, vp]
     lib.oxc_sync.argtypes = [vp, vp]
     lib.oxc_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
@@ -340,6 +342,9 @@ class Context:
     def status_flags(self):
         """The sticky status word without raising / clearing."""
         return int(self.download(self.out.status_flags, np.uint32, 1)[0])
+
+    def debug_stats_ptr(self):
+        return self.lib.oxc_debug_stats_ptr(self.h)
 
     def mark_hiz_dirty(self):
         _check(self.lib.oxc_mark_hiz_dirty(self.h), "oxc_mark_hiz_dirty")

@@ -11,7 +11,7 @@ constexpr int CULL_THREADS = 256;
 #define OXC_CULL_ITEMS 2
 #endif
 #ifndef OXC_CULL_MIN_BLOCKS
-#define OXC_CULL_MIN_BLOCKS 5
+#define OXC_CULL_MIN_BLOCKS 4
 #endif
 constexpr int CULL_ITEMS = OXC_CULL_ITEMS;               // meshlet instances per thread per tile
 constexpr int CULL_TILE = CULL_THREADS * CULL_ITEMS;   // 512 per CTA iteration -> one atomic per 512
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(1024) k_scan_block_sums(uint32_t* block_sums, 
 __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_expand_meshlet_instances(const uint32_t* __restrict__ counts,
                                                                                  const uint32_t* __restrict__ block_offsets,
                                                                                  uint32_t first, uint32_t count,
-                                                                                 OxcMeshletInstance* out, uint32_t capacity) {
+                                                                                 OxcMeshletInstance* out, uint32_t capacity, uint2* slabs) {
   __shared__ uint32_t offs[CULL_MESHES_THREADS];
   __shared__ uint32_t cnts[CULL_MESHES_THREADS];
   __shared__ uint32_t warp_tot[CULL_MESHES_THREADS / 32];
@@ -342,7 +342,10 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_expand_meshlet_instance
     if (n == 0) continue;
     const uint32_t base = offs[k];
     const uint32_t mi = first + blockIdx.x * CULL_MESHES_THREADS + k;
-    for (uint32_t j = lane; j < n && base + j < capacity; j += 32) o2[base + j] = make_uint2(mi, j);
+    for (uint32_t j = lane; j < n && base + j < capacity; j += 32) {
+      o2[base + j] = make_uint2(mi, j);
+      if (((base + j) & 31u) == 0u) slabs[(base + j) >> 5] = make_uint2(mi, j); // slab table: 8 B per 32 meshlet instances
+    }
   }
 }
 
@@ -353,23 +356,31 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_expand_meshlet_instance
 //   HIZ  = use_hiz: project_aabb + test_occlusion run when OCC || LATE (:61, any-bit HAS_FLAG)
 //   ZERO = the pyramid is known to be the per-frame cleared image (early pass)
 //
-// Persistent CTAs walk tiles of 1024 meshlet instances (256 threads x 4 items):
-//   phase A  staged loads (instance -> InstCull tail -> mask word -> bounds, each level issued for all four
-//            items before use); canonical frustum test; filtered cone test; items that still need the
-//            Hi-Z test are appended to a shared-memory queue
-//   phase B  the queue is consumed DENSELY (no lanes idling on culled items): filtered projection + occlusion;
-//            margin-ambiguous items go to a second queue
-//   phase C  canonical evaluation of the ambiguous items (a fraction of a percent)
-//   phase D  owners collect the verdicts: mask update = one XOR of the changed own bits per touched word per
-//            warp (reference: one atomic or/and per lane, :81-87); survivors compacted with warp ballots and
-//            ONE global atomic per tile (reference: three per surviving lane, :70-78)
-// Outputs are bit-identical to the canonical path for every input (oxc_filtered.cuh).
+// Round-2 design: a three-stage pipeline with WARP-PRIVATE shared-memory queues, so every expensive stage runs on 32 live
+// lanes whatever fraction of the input reaches it (round 1 ran each stage on the lanes of a fixed tile: ncu showed the
+// occlusion stage executing 362 warp instructions per 32 input meshlets for ~16 live entries).
+//
+//   stage 0  one lane per meshlet-instance INDEX, 32 consecutive indices ("slab") per warp.  The (mesh instance, meshlet)
+//            pair is recovered from the slab table (8 B per 32 meshlets, written by the expansion) plus the per-instance
+//            meshlet counts — the 8 B/meshlet id stream of round 1 is no longer read.  Mask bit -> was_visible.
+//            Early pass: only was_visible items need any work (:57) -> queue 0.   Late pass: every item -> stage A.
+//   stage A  one 128-bit bounds load, half decode, frustum (instance-inside flag, else centre-inside filter, else
+//            canonical), filtered cone.  Items that still need the Hi-Z test -> queue 1; the others are final.
+//   stage B  filtered projection + occlusion on 32 queue entries; margin-ambiguous entries -> queue 2.
+//   stage C  canonical project_aabb + test_occlusion on 32 ambiguous entries (a fraction of a percent of the input).
+//   finish   mask update = one XOR of the changed bits per touched word per warp (reference: an atomic or/and per lane,
+//            :81-87); survivors go to a warp-private staging buffer flushed with ONE pair of global atomics per ~100
+//            survivors (reference: three atomics per surviving lane, :70-78).
+// A queue holds < 32 entries between slabs; a stage runs as soon as its queue reaches 32, and once more (partially filled)
+// when the warp runs out of slabs.  Outputs are bit-identical to the canonical path for every input (oxc_filtered.cuh);
+// survivor ORDER is unspecified, as in the reference (atomics order).
 // ------------------------------------------------------------------------------------------------
-constexpr int CULL_WARP_ITEMS = 32 * CULL_ITEMS; // items owned by one warp per tile
+constexpr int CULL_WARPS = CULL_THREADS / 32;
+constexpr int CULL_Q = 64;        // queue capacity per warp (< 32 carried over + <= 32 appended)
+constexpr int CULL_EMIT = 128;    // survivor staging per warp (flushed above 96)
 constexpr uint32_t CULL_TILE_BYTES = CULL_TILE * sizeof(OxcMeshletInstance);
 
-// ---- TMA (bulk async copy engine) staging of the meshlet-instance stream: 1-D cp.async.bulk global -> shared,
-//      completion on an mbarrier; the next tile's 4 KB are in flight while the current tile is culled ----
+// ---- TMA (bulk async copy engine): 1-D cp.async.bulk global -> shared, completion on an mbarrier ----
 OXC_DI uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 OXC_DI void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
@@ -383,6 +394,7 @@ OXC_DI void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes, ui
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
+OXC_DI void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
 OXC_DI void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
@@ -397,222 +409,334 @@ OXC_DI void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
-// one queued Hi-Z test: decoded bounds + instance + the owner's slot (item k of lane l: k*32 + l)
-struct __align__(16) OccEntry {
-  float cx, cy, cz, ex;
-  float ey, ez;
-  uint32_t inst, slot;
+// queue 0 entry (early pass): where the bounds are + what to update.  16 + 4 B.
+// queue 1 / 2 entry: decoded bounds + the same bookkeeping.  32 + 4 B.
+template <bool Q0>
+struct __align__(16) CullShared {
+  uint32_t hiz_off[OXC_HIZ_MAX_LEVELS];
+  float s8_lut[256]; // scene.slang:408-418: i8 / 127.0 for every i8 (IEEE divide, once per CTA)
+  uint4 q0a[CULL_WARPS][Q0 ? CULL_Q : 1];     // bounds ptr lo, hi | mesh instance | meshlet-instance index
+  uint32_t q0b[CULL_WARPS][Q0 ? CULL_Q : 1];  // mask bit index (was_visible is implied)
+  uint4 q1a[CULL_WARPS][CULL_Q];     // cx cy cz ex
+  uint4 q1b[CULL_WARPS][CULL_Q];     // ey ez | mesh instance | meshlet-instance index
+  uint32_t q1c[CULL_WARPS][CULL_Q];  // mask bit index | was_visible << 31
+  uint4 q2a[CULL_WARPS][CULL_Q];
+  uint4 q2b[CULL_WARPS][CULL_Q];
+  uint32_t q2c[CULL_WARPS][CULL_Q];
+  uint32_t emit[CULL_WARPS][CULL_EMIT];
+};
+
+// Centre-inside frustum filter.  The canonical test (test_frustum_planes) rejects on plane i iff
+// fl(dot(c (+) s*h, n_i)) <= -w_i with s = sign(n_i) and h >= 0, i.e. it evaluates Σ n_k c_k + Σ |n_k| h_k (each
+// term rounded).  With M = Σ|c_k| + Σ h_k and |n_k| <= 1 + 4u the canonical value differs from the real one by
+// <= 4.3u M, and the real one is >= Σ n_k c_k.  D = fma-chain(Σ n_k c_k + w_i) carries <= 3u (M + |w_i|).  Hence
+//     D > 2^-19 (M + |w_i|)   (= 32u: > 4x slack)   ==>  the canonical test does NOT reject on plane i.
+// True for all six planes => visible, exactly as the canonical test decides.  NaN / Inf anywhere makes a comparison
+// false => "unknown" => the canonical path runs.
+OXC_DI bool frustum_centre_inside(const float4* __restrict__ planes, float cx, float cy, float cz, float ex, float ey, float ez) {
+  const float M = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + 0.5f * (fabsf(ex) + fabsf(ey) + fabsf(ez)));
+  const float Mk = M * 1.9073486328125e-06f; // 2^-19
+  bool inside = true;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const float4 pl = __ldg(&planes[i]);
+    const float D = fmaf(cx, pl.x, fmaf(cy, pl.y, fmaf(cz, pl.z, pl.w)));
+    inside = inside && (D > fmaf(fabsf(pl.w), 1.9073486328125e-06f, Mk));
+  }
+  return inside;
+}
+
+template <bool HIZ, bool OCC, bool LATE, bool ZERO>
+struct CullWarp {
+  using Shared = CullShared<OCC && !LATE>;
+  const CullParams& p;
+  Shared& sh;
+  const uint32_t lane, warp, lane_lt;
+  const uint32_t early_count, id_base;
+  uint32_t n0 = 0, n1 = 0, n2 = 0, ne = 0; // warp-uniform fill levels
+
+  OXC_DI CullWarp(const CullParams& p_, Shared& sh_, uint32_t early, uint32_t idb)
+      : p(p_), sh(sh_), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), lane_lt((1u << (threadIdx.x & 31)) - 1u), early_count(early), id_base(idb) {}
+
+  // ---- survivor staging: one pair of global atomics per flush ----
+  OXC_DI void flush() {
+    __syncwarp();
+    uint32_t base = 0;
+    if (lane == 0 && ne) {
+      if (!HIZ) base = atomicAdd(&p.tri_cmd->x, ne);                                            // cull_meshlets.slang:64
+      else {
+        if (!LATE) base = atomicAdd(&p.vis->early_visible_meshlet_instances, ne);              // :70
+        else base = atomicAdd(&p.vis->late_visible_meshlet_instances, ne) + early_count;        // :72-73
+        atomicAdd(&p.tri_cmd->x, ne);                                                           // :78
+      }
+    }
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t j = lane; j < ne; j += 32) p.visible_indices[base + j] = sh.emit[warp][j];    // :76
+    __syncwarp();
+    ne = 0;
+  }
+
+  // ---- verdict -> mask + survivor list.  vi = mask bit index, idx = local meshlet-instance index ----
+  OXC_DI void finish(bool active, bool visible, bool was_visible, uint32_t vi, uint32_t idx) {
+    if (OCC) { // :81-87 mask rewrite: XOR of the changed bits, aggregated per word within the warp
+      const bool changed = active && (visible != was_visible);
+      if (__any_sync(0xffffffffu, changed)) {
+        const uint32_t word = vi >> 5, bit = 1u << (vi & 31);
+        const uint32_t peers = __match_any_sync(0xffffffffu, changed ? word : 0xFFFFFFFFu);
+        const uint32_t delta = __reduce_or_sync(peers, changed ? bit : 0u);
+        if (changed && lane == (uint32_t)(__ffs(peers) - 1)) atomicXor(&p.mask[word], delta);
+      }
+    }
+    const bool emit = active && visible && (!LATE || !was_visible); // :67
+    const uint32_t bal = __ballot_sync(0xffffffffu, emit);
+    if (bal) {
+      if (emit) sh.emit[warp][ne + __popc(bal & lane_lt)] = idx + id_base;
+      ne += __popc(bal);
+      if (ne > CULL_EMIT - 32) flush();
+    }
+  }
+
+  // ---- stage C: canonical evaluation of `cnt` margin-ambiguous entries from the top of queue 2 ----
+  OXC_DI void stage_c(uint32_t cnt) {
+    __syncwarp();
+    const bool active = lane < cnt;
+    bool visible = true, was = false;
+    uint32_t vi = 0, idx = 0;
+    if (active) {
+      const uint32_t j = n2 - cnt + lane;
+      const uint4 a = sh.q2a[warp][j], b = sh.q2b[warp][j];
+      const uint32_t c = sh.q2c[warp][j];
+      vi = c & 0x7FFFFFFFu; was = (c >> 31) != 0; idx = b.w;
+      const InstCull* ic = p.inst + b.z;
+      const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
+      ScreenAabb sa;
+      if (project_aabb(r0, r1, r2, r3, p.near_clip, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
+                       __uint_as_float(b.x), __uint_as_float(b.y), sa))
+        visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, sh.hiz_off);
+    }
+    n2 -= cnt;
+    __syncwarp();
+    finish(active, visible, was, vi, idx);
+  }
+
+  // ---- stage B: filtered projection + occlusion on `cnt` entries from the top of queue 1 ----
+  OXC_DI void stage_b(uint32_t cnt) {
+    __syncwarp();
+    const bool active = lane < cnt;
+    Tri t = TRI_TRUE;
+    bool was = false;
+    uint32_t vi = 0, idx = 0, c = 0;
+    uint4 a = make_uint4(0, 0, 0, 0), b = a;
+    if (active) {
+      const uint32_t j = n1 - cnt + lane;
+      a = sh.q1a[warp][j]; b = sh.q1b[warp][j]; c = sh.q1c[warp][j];
+      vi = c & 0x7FFFFFFFu; was = (c >> 31) != 0; idx = b.w;
+      const InstCull* ic = p.inst + b.z;
+      const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
+      t = occlusion_visible_fast(r0, r1, r2, r3, p.near_clip, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z),
+                                 __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y), p.hiz.data, p.hiz.width, p.hiz.height,
+                                 p.hiz.levels, sh.hiz_off, __ldg(&ic->nrm[1].w) != 0.0f);
+    }
+    n1 -= cnt;
+    __syncwarp();
+    const bool amb = active && t == TRI_AMBIGUOUS;
+    const uint32_t bal = __ballot_sync(0xffffffffu, amb);
+    if (bal) {
+      if (amb) {
+        const uint32_t j = n2 + __popc(bal & lane_lt);
+        sh.q2a[warp][j] = a; sh.q2b[warp][j] = b; sh.q2c[warp][j] = c;
+      }
+      n2 += __popc(bal);
+    }
+    finish(active && !amb, t == TRI_TRUE, was, vi, idx);
+    if (n2 >= 32) stage_c(32);
+  }
+
+  // ---- stage A: bounds -> frustum -> cone; `active` lanes hold (bounds pointer, mesh instance, index, mask bit, was) ----
+  OXC_DI void stage_a(bool active, const uint4 b, uint32_t inst, uint32_t idx, uint32_t vi, bool was) {
+    bool visible = active;
+    bool queue = false;
+    float cx = 0.f, cy = 0.f, cz = 0.f, ex = 0.f, ey = 0.f, ez = 0.f;
+    if (active) {
+      const InstCull* ic = p.inst + inst;
+      // scene.slang:401-435 unpack: u16x3 center | i8x2 cone xy | u16x3 extent | i8 cone z | i8 cutoff
+      cx = dequantize_half_hw(b.x & 0xFFFFu); cy = dequantize_half_hw(b.x >> 16); cz = dequantize_half_hw(b.y & 0xFFFFu);
+      ex = dequantize_half_hw(b.z & 0xFFFFu); ey = dequantize_half_hw(b.z >> 16); ez = dequantize_half_hw(b.w & 0xFFFFu);
+      // :59 frustum (the three tests commute).  Skipped when the whole instance is provably inside every plane for the
+      // canonical test (InstCull::nrm[2].w, see k_cull_meshes); else decided by the centre-inside filter when it can.
+#ifndef OXC_EXP_NO_FRUSTUM
+      if (__ldg(&ic->nrm[2].w) == 0.0f && !frustum_centre_inside(ic->plane, cx, cy, cz, ex, ey, ez))
+        visible = test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
+#endif
+      // :58 cone
+      const float cutoff = sh.s8_lut[((b.w >> 24) + 128u) & 0xFFu];
+#ifdef OXC_EXP_NO_CONE
+      if (false) {
+#else
+      if (visible && cutoff < 1.0f) {
+#endif
+        const ConeInputs ci = cone_inputs(ic, cx, cy, cz, ex, ey, ez, sh.s8_lut[(((b.y >> 16) & 0xFFu) + 128u) & 0xFFu],
+                                          sh.s8_lut[((b.y >> 24) + 128u) & 0xFFu], sh.s8_lut[(((b.w >> 16) & 0xFFu) + 128u) & 0xFFu],
+                                          p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]);
+        const Tri t = cone_visible_fast(ci, cutoff);
+        visible = t == TRI_AMBIGUOUS ? cone_visible_exact(ci, cutoff) : (t == TRI_TRUE);
+      }
+      // :61-65 occlusion
+#ifdef OXC_EXP_NO_OCC // timing experiment only (results are wrong)
+      if (false) {
+#else
+      if (HIZ && (OCC || LATE) && visible) {
+#endif
+        queue = true;
+        if (ZERO) queue = !cleared_hiz_surely_visible(__ldg(&ic->mvp_row[2]), __ldg(&ic->mvp_row[3]), cx, cy, cz, ex, ey, ez);
+      }
+    }
+    if (HIZ) {
+      const uint32_t bal = __ballot_sync(0xffffffffu, queue);
+      if (bal) {
+        if (queue) {
+          const uint32_t j = n1 + __popc(bal & lane_lt);
+          sh.q1a[warp][j] = make_uint4(__float_as_uint(cx), __float_as_uint(cy), __float_as_uint(cz), __float_as_uint(ex));
+          sh.q1b[warp][j] = make_uint4(__float_as_uint(ey), __float_as_uint(ez), inst, idx);
+          sh.q1c[warp][j] = vi | (was ? 0x80000000u : 0u);
+        }
+        n1 += __popc(bal);
+      }
+    }
+    finish(active && !queue, visible, was, vi, idx);
+    if (HIZ && n1 >= 32) stage_b(32);
+  }
+
+  // ---- stage A fed from queue 0 (early pass) ----
+  OXC_DI void stage_a_from_q0(uint32_t cnt) {
+    __syncwarp();
+    const bool active = lane < cnt;
+    uint4 a = make_uint4(0, 0, 0, 0);
+    uint32_t vi = 0;
+    if (active) { a = sh.q0a[warp][n0 - cnt + lane]; vi = sh.q0b[warp][n0 - cnt + lane]; }
+    n0 -= cnt;
+    __syncwarp();
+    uint4 b = make_uint4(0, 0, 0, 0);
+    if (active) b = __ldg(reinterpret_cast<const uint4*>(((uint64_t)a.y << 32) | a.x)); // MeshletBounds of a was_visible item
+    stage_a(active, b, a.z, a.w, vi, true);
+  }
+
+  // ---- stage 0, software-pipelined over the warp's slabs ----
+  // The index -> (mesh instance, meshlet) -> {mask word, bounds} resolution is a chain of three dependent loads; a warp
+  // owns only a handful of slabs, so the chain of slab k+1.. is issued while slab k is being tested:
+  //     iteration k:   issue  slab-table entry of k+3,  InstCull tail of k+2,  mask word + bounds of k+1;   test k
+  // (round 1 staged the 8 B/meshlet id stream with the bulk-copy engine and still paid the dependent InstCull -> mask ->
+  // bounds chain per tile; the first cut of this kernel without the pipeline was latency-bound at 40 us per 1 M.)
+  struct Resolved { // slab whose mask word / bounds are in flight
+    uint4 bounds;
+    uint32_t maskw, inst, idx, vi;
+    bool valid;
+  };
+
+  OXC_DI uint2 load_slab_entry(uint32_t s, uint32_t n_slabs) const { return s < n_slabs ? __ldg(&p.slabs[s]) : make_uint2(0u, 0u); }
+  OXC_DI uint4 load_tail(uint32_t s, uint32_t n_slabs, uint2 sl) const {
+    return s < n_slabs ? __ldg(reinterpret_cast<const uint4*>(&p.inst[sl.x].bounds_lo)) : make_uint4(0, 0, 0, 0xFFFFFFFFu);
+  }
+  // finish the resolution of slab s (entry sl, first instance's tail already here) and put the mask word and — when the
+  // pass needs every item (late / no mask) — the bounds in flight
+  OXC_DI Resolved resolve(uint32_t s, uint32_t total, uint2 sl, uint4 tail) const {
+    Resolved r;
+    r.idx = s * 32u + lane;
+    r.valid = r.idx < total; // also false for s >= n_slabs
+    uint32_t cur = sl.x, m = sl.y + lane;
+    if (r.valid) {
+      while (m >= tail.w) { // the slab runs past this mesh instance (instances with no meshlets are stepped over)
+        m -= tail.w;
+        cur++;
+        tail = __ldg(reinterpret_cast<const uint4*>(&p.inst[cur].bounds_lo));
+      }
+    }
+    const uint4* bptr = reinterpret_cast<const uint4*>(((uint64_t)tail.y << 32) | tail.x) + m;
+    r.inst = cur;
+    r.vi = tail.z + m; // :45-49
+    r.maskw = 0xFFFFFFFFu; // :44 (no occlusion flag: treated as previously visible)
+    if (OCC && r.valid) r.maskw = __ldg(&p.mask[r.vi >> 5]); // plain load: only this launch's owner lane changes the bit
+    r.bounds = make_uint4(0, 0, 0, 0);
+    if (r.valid) { // the 272-byte InstCull record of the lane's mesh instance -> L1, one slab ahead of its first use: without this
+                   // stage A paid 4-5 serialised L2 round trips (flag, planes, normal matrix, rows — each behind a branch)
+      const char* rec = reinterpret_cast<const char*>(p.inst + cur);
+      prefetch_l1(rec); prefetch_l1(rec + 128); prefetch_l1(rec + 256);
+    }
+    if (OCC && !LATE) { // early pass: the bounds are fetched by stage A for the was_visible items only; keep the address
+      r.bounds.x = (uint32_t)(uint64_t)bptr; r.bounds.y = (uint32_t)((uint64_t)bptr >> 32);
+      if (r.valid) prefetch_l1(bptr);
+    } else if (r.valid) {
+      r.bounds = __ldg(bptr); // MeshletBounds, one 128-bit load (consecutive lanes: consecutive 16 B records of one LOD)
+    }
+    return r;
+  }
+
+  OXC_DI void consume(const Resolved& r) {
+    const bool was = ((r.maskw >> (r.vi & 31)) & 1u) != 0;
+    const bool need = r.valid && (LATE || was); // :57
+    if (OCC && !LATE) {
+      // early pass: items that were not visible need no test at all (visible = was_visible && ..., mask unchanged, nothing
+      // emitted) — the rest is compacted so stage A runs on full warps
+      const uint32_t bal = __ballot_sync(0xffffffffu, need);
+      if (bal) {
+        if (need) {
+          const uint32_t j = n0 + __popc(bal & lane_lt);
+          sh.q0a[warp][j] = make_uint4(r.bounds.x, r.bounds.y, r.inst, r.idx);
+          sh.q0b[warp][j] = r.vi;
+        }
+        n0 += __popc(bal);
+        if (n0 >= 32) stage_a_from_q0(32);
+      }
+    } else {
+      stage_a(need, r.bounds, r.inst, r.idx, r.vi, was);
+    }
+  }
+
+  OXC_DI void run(uint32_t first_slab, uint32_t stride, uint32_t total) {
+    const uint32_t n_slabs = (total + 31u) >> 5;
+    if (first_slab >= n_slabs) return;
+    // prologue: fill the pipeline
+    uint2 sl1 = load_slab_entry(first_slab, n_slabs);
+    uint2 sl2 = load_slab_entry(first_slab + stride, n_slabs);
+    uint2 sl3 = load_slab_entry(first_slab + 2 * stride, n_slabs);
+    uint4 tail1 = load_tail(first_slab, n_slabs, sl1);
+    uint4 tail2 = load_tail(first_slab + stride, n_slabs, sl2);
+    Resolved r0 = resolve(first_slab, total, sl1, tail1);
+    for (uint32_t s = first_slab; s < n_slabs; s += stride) {
+      // issue the loads of the slabs ahead ...
+      const uint2 sl4 = load_slab_entry(s + 3 * stride, n_slabs);
+      const uint4 tail3 = load_tail(s + 2 * stride, n_slabs, sl3);
+      const Resolved r1 = resolve(s + stride, total, sl2, tail2);
+      // ... and test this one while they are in flight
+      consume(r0);
+      r0 = r1; sl2 = sl3; sl3 = sl4; tail2 = tail3;
+    }
+  }
+
+  OXC_DI void drain() {
+    if (OCC && !LATE) { if (n0) stage_a_from_q0(n0); }
+    if (HIZ) {
+      if (n1) stage_b(n1);
+      if (n2) stage_c(n2);
+    }
+    if (ne) flush();
+  }
 };
 
 template <bool HIZ, bool OCC, bool LATE, bool ZERO>
 __global__ void __launch_bounds__(CULL_THREADS, OXC_CULL_MIN_BLOCKS) k_cull_meshlets(const __grid_constant__ CullParams p) {
-  __shared__ uint32_t hiz_off[OXC_HIZ_MAX_LEVELS];
-  __shared__ uint32_t warp_cnt[CULL_THREADS / 32];
-  __shared__ uint32_t tile_base_s;
-  __shared__ float s8_lut[256]; // scene.slang:408-418: i8 / 127.0 for every i8 (IEEE divide, once per CTA)
-  __shared__ __align__(128) uint2 mi_s[2][CULL_TILE]; // double-buffered tiles of the instance stream (TMA destination)
-  __shared__ __align__(8) uint64_t mi_bar[2];
-  // warp-private queues: no CTA barrier between the phases
-  __shared__ OccEntry q_ent[HIZ ? CULL_THREADS / 32 : 1][HIZ ? CULL_WARP_ITEMS : 1];
-  __shared__ uint8_t q_amb[HIZ ? CULL_THREADS / 32 : 1][HIZ ? CULL_WARP_ITEMS : 1]; // entry indices needing the canonical path
-  __shared__ uint8_t q_res[HIZ ? CULL_THREADS / 32 : 1][HIZ ? CULL_WARP_ITEMS : 1]; // verdict per owner slot
-  if (threadIdx.x < OXC_HIZ_MAX_LEVELS) hiz_off[threadIdx.x] = p.hiz.level_offset[threadIdx.x];
-  s8_lut[threadIdx.x] = s8_over_127((int)threadIdx.x - 128);
-  if (threadIdx.x == 0) { mbar_init(&mi_bar[0], 1); mbar_init(&mi_bar[1], 1); mbar_fence_init(); }
+  extern __shared__ __align__(16) unsigned char cull_smem_raw[];
+  using Shared = CullShared<OCC && !LATE>;
+  Shared& sh = *reinterpret_cast<Shared*>(cull_smem_raw);
+  if (threadIdx.x < OXC_HIZ_MAX_LEVELS) sh.hiz_off[threadIdx.x] = p.hiz.level_offset[threadIdx.x];
+  sh.s8_lut[threadIdx.x] = s8_over_127((int)threadIdx.x - 128);
   __syncthreads();
   const uint32_t total = p.vis->total_visible_meshlet_instances; // :26
-  const uint32_t early_count = LATE ? p.vis->early_visible_meshlet_instances : 0u; // :73 (final: early kernel completed)
+  const uint32_t early_count = LATE ? p.vis->early_visible_meshlet_instances : 0u; // :73 (final: the early kernel has completed)
   const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t lane_lt = (1u << lane) - 1u;
-  const uint32_t n_tiles = (total + CULL_TILE - 1) / CULL_TILE;
-  const uint2* mi2 = reinterpret_cast<const uint2*>(p.meshlet_instances);
-
-  // prologue: this CTA's first tile (the buffer is padded by one tile, so a full-size copy never leaves the allocation)
-  if (threadIdx.x == 0 && blockIdx.x < n_tiles) {
-    mbar_expect_tx(&mi_bar[0], CULL_TILE_BYTES);
-    tma_load_1d(mi_s[0], mi2 + (size_t)blockIdx.x * CULL_TILE, CULL_TILE_BYTES, &mi_bar[0]);
-  }
-  uint32_t it = 0;
-  for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-    const uint32_t tile_first = tile * CULL_TILE;
-    const uint32_t buf = it & 1u;
-    // next tile -> other buffer (its previous readers finished before the trailing barrier of the last iteration)
-    if (threadIdx.x == 0 && tile + gridDim.x < n_tiles) {
-      mbar_expect_tx(&mi_bar[buf ^ 1u], CULL_TILE_BYTES);
-      tma_load_1d(mi_s[buf ^ 1u], mi2 + (size_t)(tile + gridDim.x) * CULL_TILE, CULL_TILE_BYTES, &mi_bar[buf ^ 1u]);
-    }
-    mbar_wait(&mi_bar[buf], (it >> 1) & 1u);
-    // ---- phase A: staged loads ----
-    uint2 mi[CULL_ITEMS];
-#pragma unroll
-    for (int k = 0; k < CULL_ITEMS; k++) {
-      const uint32_t i = tile_first + k * CULL_THREADS + threadIdx.x;
-      mi[k] = i < total ? mi_s[buf][k * CULL_THREADS + threadIdx.x] : make_uint2(0xFFFFFFFFu, 0u);
-    }
-    const uint4* bptr[CULL_ITEMS];
-    uint32_t word[CULL_ITEMS], bit[CULL_ITEMS];
-#pragma unroll
-    for (int k = 0; k < CULL_ITEMS; k++) {
-      bptr[k] = nullptr; word[k] = 0xFFFFFFFFu; bit[k] = 0;
-      if (mi[k].x != 0xFFFFFFFFu) {
-        const uint4 tail = __ldg(reinterpret_cast<const uint4*>(&p.inst[mi[k].x].bounds_lo));
-        bptr[k] = reinterpret_cast<const uint4*>(((uint64_t)tail.y << 32) | tail.x) + mi[k].y;
-        if (OCC) { // :45-49
-          const uint32_t vi = tail.z + mi[k].y;
-          word[k] = vi >> 5;
-          bit[k] = 1u << (vi & 31);
-        }
-      }
-    }
-    uint32_t was_bits = 0; // bit k: was_visible of item k (:50; true when !OCC, :44)
-#pragma unroll
-    for (int k = 0; k < CULL_ITEMS; k++) {
-      bool wv = true;
-      if (OCC && mi[k].x != 0xFFFFFFFFu) wv = (p.mask[word[k]] & bit[k]) != 0; // plain load: only this thread ever changes this bit
-      was_bits |= (wv ? 1u : 0u) << k;
-    }
-    uint4 bnd[CULL_ITEMS];
-#pragma unroll
-    for (int k = 0; k < CULL_ITEMS; k++) {
-      const bool need = mi[k].x != 0xFFFFFFFFu && (LATE || ((was_bits >> k) & 1u)); // :57
-      bnd[k] = need ? __ldg(bptr[k]) : make_uint4(0, 0, 0, 0); // MeshletBounds, one 128-bit load
-    }
-    uint32_t vis_bits = 0;     // bit k: verdict so far
-    uint32_t pending_bits = 0; // bit k: verdict comes from the queue (q_res)
-    uint32_t n_occ = 0;        // warp-uniform queue length
-#pragma unroll
-    for (int k = 0; k < CULL_ITEMS; k++) {
-      const bool valid = mi[k].x != 0xFFFFFFFFu;
-      bool visible = valid && (LATE ? true : ((was_bits >> k) & 1u)); // :57
-      bool queue = false;
-      float cx = 0.f, cy = 0.f, cz = 0.f, ex = 0.f, ey = 0.f, ez = 0.f;
-      if (visible) {
-        const InstCull* ic = p.inst + mi[k].x;
-        const uint4 b = bnd[k];
-        // scene.slang:401-435 unpack: u16x3 center | i8x2 cone xy | u16x3 extent | i8 cone z | i8 cutoff
-        cx = dequantize_half_hw(b.x & 0xFFFFu); cy = dequantize_half_hw(b.x >> 16); cz = dequantize_half_hw(b.y & 0xFFFFu);
-        ex = dequantize_half_hw(b.z & 0xFFFFu); ey = dequantize_half_hw(b.z >> 16); ez = dequantize_half_hw(b.w & 0xFFFFu);
-        // :59 frustum (canonical; evaluated first: the three tests commute).  Skipped when the whole instance is
-        // provably inside every plane for the canonical test (InstCull::nrm[2].w, see k_cull_meshes).
-        if (__ldg(&ic->nrm[2].w) == 0.0f) visible = test_frustum_planes(ic->plane, cx, cy, cz, ex, ey, ez);
-        // :58 cone
-        const float cutoff = s8_lut[((b.w >> 24) + 128u) & 0xFFu];
-        if (visible && cutoff < 1.0f) {
-          const ConeInputs ci = cone_inputs(ic, cx, cy, cz, ex, ey, ez, s8_lut[(((b.y >> 16) & 0xFFu) + 128u) & 0xFFu],
-                                            s8_lut[((b.y >> 24) + 128u) & 0xFFu], s8_lut[(((b.w >> 16) & 0xFFu) + 128u) & 0xFFu],
-                                            p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]);
-          const Tri t = cone_visible_fast(ci, cutoff);
-          visible = t == TRI_AMBIGUOUS ? cone_visible_exact(ci, cutoff) : (t == TRI_TRUE);
-        }
-        // :61-65 occlusion
-        if (HIZ && (OCC || LATE) && visible) {
-          queue = true;
-          if (ZERO) queue = !cleared_hiz_surely_visible(__ldg(&ic->mvp_row[2]), __ldg(&ic->mvp_row[3]), cx, cy, cz, ex, ey, ez);
-        }
-      }
-      if (HIZ) { // append to the warp's dense queue (ballot prefix: no atomics)
-        const uint32_t bal = __ballot_sync(0xffffffffu, queue);
-        if (queue) {
-          OccEntry e;
-          e.cx = cx; e.cy = cy; e.cz = cz; e.ex = ex; e.ey = ey; e.ez = ez; e.inst = mi[k].x; e.slot = k * 32 + lane;
-          q_ent[warp][n_occ + __popc(bal & lane_lt)] = e;
-          pending_bits |= 1u << k;
-        }
-        n_occ += __popc(bal);
-      }
-      vis_bits |= (visible ? 1u : 0u) << k;
-    }
-    if (HIZ) {
-      // ---- phase B: the warp consumes its queue densely ----
-      __syncwarp();
-      uint32_t n_amb = 0;
-      for (uint32_t j0 = 0; j0 < n_occ; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        Tri t = TRI_TRUE;
-        if (j < n_occ) {
-          const OccEntry e = q_ent[warp][j];
-          const InstCull* ic = p.inst + e.inst;
-          const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
-          t = occlusion_visible_fast(r0, r1, r2, r3, p.near_clip, e.cx, e.cy, e.cz, e.ex, e.ey, e.ez, p.hiz.data, p.hiz.width,
-                                     p.hiz.height, p.hiz.levels, hiz_off, __ldg(&ic->nrm[1].w) != 0.0f);
-          if (t != TRI_AMBIGUOUS) q_res[warp][e.slot] = (uint8_t)t;
-        }
-        const uint32_t bal = __ballot_sync(0xffffffffu, t == TRI_AMBIGUOUS);
-        if (t == TRI_AMBIGUOUS) q_amb[warp][n_amb + __popc(bal & lane_lt)] = (uint8_t)j;
-        n_amb += __popc(bal);
-      }
-      // ---- phase C: canonical evaluation of the margin-ambiguous entries (a fraction of a percent) ----
-      __syncwarp();
-      for (uint32_t a0 = 0; a0 < n_amb; a0 += 32) {
-        const uint32_t a = a0 + lane;
-        if (a < n_amb) {
-          const OccEntry e = q_ent[warp][q_amb[warp][a]];
-          const InstCull* ic = p.inst + e.inst;
-          const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
-          ScreenAabb sa;
-          bool visible = true;
-          if (project_aabb(r0, r1, r2, r3, p.near_clip, e.cx, e.cy, e.cz, e.ex, e.ey, e.ez, sa))
-            visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, hiz_off);
-          q_res[warp][e.slot] = visible ? 1 : 0;
-        }
-      }
-      __syncwarp();
-    }
-    // ---- phase D: verdicts -> mask + survivor list ----
-    uint32_t emit_bits = 0;
-#pragma unroll
-    for (int k = 0; k < CULL_ITEMS; k++) {
-      const bool valid = mi[k].x != 0xFFFFFFFFu;
-      const bool was_visible = (was_bits >> k) & 1u;
-      bool visible = (vis_bits >> k) & 1u;
-      if (HIZ && ((pending_bits >> k) & 1u)) visible = q_res[warp][k * 32 + lane] != 0;
-      // :81-87 mask rewrite: XOR of the changed own bits, aggregated per word within the warp
-      if (OCC) {
-        const bool changed = valid && (visible != was_visible);
-        const uint32_t key = changed ? word[k] : 0xFFFFFFFFu;
-        if (__any_sync(0xffffffffu, changed)) {
-          const uint32_t peers = __match_any_sync(0xffffffffu, key);
-          const uint32_t delta = __reduce_or_sync(peers, changed ? bit[k] : 0u);
-          if (changed && lane == (uint32_t)(__ffs(peers) - 1)) atomicXor(&p.mask[word[k]], delta);
-        }
-      }
-      if (visible && (!LATE || !was_visible)) emit_bits |= 1u << k; // :67
-    }
-    // ---- compaction: warp ballots -> CTA scan -> one atomic per tile ----
-    uint32_t warp_total = 0;
-    uint32_t offs[CULL_ITEMS];
-#pragma unroll
-    for (int k = 0; k < CULL_ITEMS; k++) {
-      const uint32_t bal = __ballot_sync(0xffffffffu, (emit_bits >> k) & 1u);
-      offs[k] = warp_total + __popc(bal & ((1u << lane) - 1u));
-      warp_total += __popc(bal);
-    }
-    if (lane == 0) warp_cnt[warp] = warp_total;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t s = 0;
-#pragma unroll
-      for (int w = 0; w < CULL_THREADS / 32; w++) { const uint32_t c = warp_cnt[w]; warp_cnt[w] = s; s += c; }
-      uint32_t base = 0;
-      if (s) {
-        if (!HIZ) base = atomicAdd(&p.tri_cmd->x, s);                                           // cull_meshlets.slang:64
-        else {
-          if (!LATE) base = atomicAdd(&p.vis->early_visible_meshlet_instances, s);             // :70
-          else base = atomicAdd(&p.vis->late_visible_meshlet_instances, s) + early_count;       // :72-73
-          atomicAdd(&p.tri_cmd->x, s);                                                          // :78
-        }
-      }
-      tile_base_s = base;
-    }
-    __syncthreads();
-    const uint32_t wbase = tile_base_s + warp_cnt[warp];
-#pragma unroll
-    for (int k = 0; k < CULL_ITEMS; k++)
-      if ((emit_bits >> k) & 1u)
-        p.visible_indices[wbase + offs[k]] = tile_first + k * CULL_THREADS + threadIdx.x + id_base; // :76
-    __syncthreads(); // warp_cnt / tile_base_s / queues reuse
-  }
+  CullWarp<HIZ, OCC, LATE, ZERO> w(p, sh, early_count, id_base);
+  w.run(blockIdx.x * CULL_WARPS + (threadIdx.x >> 5), gridDim.x * CULL_WARPS, total);
+  w.drain();
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -31,6 +31,7 @@ struct TriParams {
   // raster output
   unsigned long long* visbuf;
   uint32_t width, height;
+  float f_width, f_height;   // (float)width / height: kernel-parameter operands cost no registers
   unsigned long long* tri_counter;
   uint32_t* work_counter;    // zeroed before every raster launch
   // deferred large triangles (k_raster_big): [0] = entries pushed, [1] = entries taken; zeroed before every raster launch
@@ -382,6 +383,31 @@ OXC_DI bool big_push(const TriParams& p, const TriSetup& s, uint32_t data) {
   return true;
 }
 
+constexpr uint32_t BIG_PUSH_ALONE = 4; // chunks a single lane may push by itself
+OXC_DI uint32_t big_chunk_count(const TriSetup& s) {
+  return ((uint32_t)(s.px1 - s.px0) / BIG_CHUNK_W + 1u) * ((uint32_t)(s.py1 - s.py0) / BIG_CHUNK_H + 1u);
+}
+
+// The same push done by a whole warp for ONE triangle (setup already broadcast to every lane): lane l writes chunks l, l + 32, ...
+OXC_DI bool big_push_warp(const TriParams& p, const TriSetup& s, uint32_t data, uint32_t lane) {
+  const uint32_t cw = (uint32_t)(s.px1 - s.px0) / BIG_CHUNK_W + 1u, ch = (uint32_t)(s.py1 - s.py0) / BIG_CHUNK_H + 1u;
+  const uint32_t n = cw * ch;
+  uint32_t base = 0xFFFFFFFFu;
+  if (lane == 0 && *reinterpret_cast<volatile uint32_t*>(&p.big_counters[0]) < p.big_capacity) base = atomicAdd(&p.big_counters[0], n);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (base >= p.big_capacity) return false;
+  if (base + n > p.big_capacity) { // straddles the capacity: fill the reserved slots below it with EMPTY entries (see big_push)
+    for (uint32_t k = base + lane; k < p.big_capacity; k += 32) big_entry_store(p.big_queue + (size_t)k * 4, s, 1, 0, 1, 0, data);
+    return false;
+  }
+  for (uint32_t k = lane; k < n; k += 32) {
+    const uint32_t cy = k / cw, cx = k - cy * cw;
+    const int x0 = s.px0 + (int)(cx * BIG_CHUNK_W), y0 = s.py0 + (int)(cy * BIG_CHUNK_H);
+    big_entry_store(p.big_queue + (size_t)(base + k) * 4, s, x0, min(s.px1, x0 + BIG_CHUNK_W - 1), y0, min(s.py1, y0 + BIG_CHUNK_H - 1), data);
+  }
+  return true;
+}
+
 // One warp per queued chunk, chunks taken from a counter: the chunk is covered in 8x4-pixel tiles (raster spec steps 5-6).
 __global__ void __launch_bounds__(256) k_raster_big(const __grid_constant__ TriParams p) {
   const uint32_t lane = threadIdx.x & 31;
@@ -410,16 +436,21 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
   const uint32_t first = p.late ? p.vis->early_visible_meshlet_instances : 0u; // cull_triangles.slang:34-37
   const uint32_t count = p.tri_cmd->x;                                         // dispatch_indirect(cull_triangles_cmd), CullGeometry.cpp:365
   const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
-  const float fW = (float)p.width, fH = (float)p.height;
   float4* clip_s = clip_all[warp];
   ScreenVert* scr_s = scr_all[warp];
   uint32_t kept = 0;
-  // warps pull batches of RASTER_BATCH consecutive survivors from a global work counter (dynamic balance);
-  // lanes 0..RASTER_BATCH-1 each chase one meshlet header, so RASTER_BATCH pointer chases are in flight together
-  // batch size adapts to the survivor count so short lists (late pass) still spread over every warp
+#ifdef OXC_RASTER_STATS
+  unsigned long long t_entry, t_chase = 0, t_proc = 0, n_done = 0, n_grabs = 0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_entry));
+#endif
+  // warps pull batches of up to RASTER_BATCH consecutive survivors from a global work counter (dynamic balance); lanes
+  // 0..nb-1 each chase one meshlet header, so nb pointer chases are in flight together.
   // Guided self-scheduling: the grab size shrinks with the work that is left (remaining / (2 x warps in the grid), between 1
-  // and RASTER_BATCH), so the kernel ends with single-meshlet grabs.  With a fixed batch of 8 a warp's last grab was 1/7 of
-  // its whole share and the average SM sat idle for the last third of the launch (ncu: sm__cycles_active 67 % of elapsed).
+  // and RASTER_BATCH), so the kernel ends with single-meshlet grabs.
+  // Measured in round 2 (per-warp %globaltimer stamps, tools/raster_stats.py): a grab costs ~3.8 us in the early and ~7 us in
+  // the late pass (thousands of warps on one L2 atomic address).  Dealing the list onto 32 interleaved sequences with one
+  // counter each cut the late pass (119 -> 97 us) but cost the early pass more (365 -> 388..421 us: the extra scheduler
+  // state spills at the 64-register cap), so the single counter stays.
   const uint32_t n_warps2 = gridDim.x * TRI_WARPS * 2u;
   for (;;) {
     uint32_t g0 = 0, batch = 1;
@@ -433,14 +464,23 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
     batch = __shfl_sync(0xffffffffu, batch, 0);
     if (g0 >= count) break;
     const uint32_t nb = min(batch, count - g0);
+    const uint32_t my_survivor = g0 + lane;
+#ifdef OXC_RASTER_STATS
+    unsigned long long t_a, t_b, t_c;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_a));
+#endif
     MeshletHeader mine;
     mine.gid = 0; mine.inst = 0; mine.vertex_offset = 0; mine.vertex_count = 0; mine.tri_offset = 0; mine.tri_count = 0;
     mine.micro = nullptr; mine.vidx = nullptr; mine.pos = nullptr;
-    if (lane < nb) mine = fetch_header(p, first + g0 + lane, id_base);
+    if (lane < nb) mine = fetch_header(p, first + my_survivor, id_base);
     // vertex indices of the first meshlet, prefetched one meshlet ahead from here on
     MeshletHeader cur = bcast_header(mine, 0);
     uint32_t vi0 = lane < cur.vertex_count ? __ldg(&cur.vidx[lane]) : 0u;
     uint32_t vi1 = lane + 32u < cur.vertex_count ? __ldg(&cur.vidx[lane + 32u]) : 0u;
+#ifdef OXC_RASTER_STATS
+    if (vi0 + vi1 == 0xFFFFFFFFu) kept++; // keep the loads ahead of the timer read
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_b));
+#endif
     for (uint32_t j = 0; j < nb; j++) {
       const MeshletHeader w = cur;
       // positions of this meshlet (indices already here) ...
@@ -459,13 +499,13 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
         const float x = dequantize_half_hw(q0.x & 0xFFFFu), y = dequantize_half_hw(q0.x >> 16), z = dequantize_half_hw(q0.y & 0xFFFFu);
         const float4 c = make_float4(row_dot_p1(r0, x, y, z), row_dot_p1(r1, x, y, z), row_dot_p1(r2, x, y, z), row_dot_p1(r3, x, y, z));
         clip_s[lane] = c;
-        scr_s[lane] = to_screen(c, fW, fH);
+        scr_s[lane] = to_screen(c, p.f_width, p.f_height);
       }
       if (w.vertex_count > 32u) {
         const float x = dequantize_half_hw(q1.x & 0xFFFFu), y = dequantize_half_hw(q1.x >> 16), z = dequantize_half_hw(q1.y & 0xFFFFu);
         const float4 c = make_float4(row_dot_p1(r0, x, y, z), row_dot_p1(r1, x, y, z), row_dot_p1(r2, x, y, z), row_dot_p1(r3, x, y, z));
         clip_s[lane + 32] = c;
-        scr_s[lane + 32] = to_screen(c, fW, fH);
+        scr_s[lane + 32] = to_screen(c, p.f_width, p.f_height);
       }
       __syncwarp();
       const uint32_t rounds = (w.tri_count + 31u) >> 5;
@@ -490,10 +530,30 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
         kept += pass ? 1u : 0u;
         const uint32_t data = (w.gid << p.prim_bits) | t;
         const int bw = draw ? s.px1 - s.px0 + 1 : 0, bh = draw ? s.py1 - s.py0 + 1 : 0;
+#if defined(OXC_RASTER_STATS) && OXC_RASTER_STATS == 1
+        {  // instrumentation build only: per round (32 triangles) histogram of the LARGEST per-lane pixel loop and the round's sums
+          const int area = (draw && bw * bh <= RASTER_BIG_PIXELS) ? bw * bh : 0;
+          const int mx = __reduce_max_sync(0xffffffffu, area), sm = __reduce_add_sync(0xffffffffu, area);
+          const int nd = __popc(__ballot_sync(0xffffffffu, area > 0));
+          const int nbig = __popc(__ballot_sync(0xffffffffu, draw && bw * bh > RASTER_BIG_PIXELS));
+          if (lane == 0) {
+            unsigned long long* st = reinterpret_cast<unsigned long long*>(p.big_queue) + (size_t)p.big_capacity * 8 + (p.late ? 64 : 0);
+            atomicAdd(&st[min(mx, 33)], 1ull);          // [0..33] histogram of max area
+            atomicAdd(&st[40], (unsigned long long)sm); // total candidate pixels (small path)
+            atomicAdd(&st[41], (unsigned long long)mx); // sum of per-round maxima
+            atomicAdd(&st[42], (unsigned long long)nd); // drawing lanes
+            atomicAdd(&st[43], 1ull);                   // rounds
+            atomicAdd(&st[44], (unsigned long long)nbig);
+          }
+        }
+#endif
         bool big = draw && (bw * bh > RASTER_BIG_PIXELS);
         if (draw && !big) raster_small(s, data, p.visbuf, p.width);
-        if (big && p.big_queue && big_push(p, s, data)) big = false; // deferred to k_raster_big
-        // large triangles the queue could not take: broadcast the setup; the warp covers the bounding box in 8x4-pixel tiles
+        // a triangle of a few chunks is pushed by its own lane; one of many chunks (a screen-filling triangle is ~1000) is
+        // pushed by the whole warp below — per-warp timestamps showed single lanes spending 30-80 us writing chunk entries,
+        // the tail of both raster launches
+        const bool few = big && big_chunk_count(s) <= BIG_PUSH_ALONE;
+        if (few && p.big_queue && big_push(p, s, data)) big = false; // deferred to k_raster_big
         uint32_t big_mask = __ballot_sync(0xffffffffu, big);
         while (big_mask) {
           const int src = __ffs(big_mask) - 1;
@@ -508,6 +568,8 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
           b.py0 = __shfl_sync(0xffffffffu, s.py0, src); b.py1 = __shfl_sync(0xffffffffu, s.py1, src);
           b.bias = __shfl_sync(0xffffffffu, s.bias, src);
           const uint32_t bdata = __shfl_sync(0xffffffffu, data, src);
+          if (p.big_queue && big_push_warp(p, b, bdata, lane)) continue; // chunks written by all 32 lanes
+          // the queue could not take it: the warp covers the bounding box in 8x4-pixel tiles right here
           const int lx = lane & 7, ly = lane >> 3;
           for (int ty = b.py0; ty <= b.py1; ty += 4)
             for (int tx = b.px0; tx <= b.px1; tx += 8) {
@@ -518,7 +580,20 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
       }
       __syncwarp(); // clip_s / scr_s reuse
     }
+#ifdef OXC_RASTER_STATS
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_c));
+    t_chase += t_b - t_a; t_proc += t_c - t_b; n_done += nb; n_grabs++;
+#endif
   }
+#ifdef OXC_RASTER_STATS
+  if (lane == 0) { // per-warp record: entry, exit, time in the header chase, time processing, meshlets, grabs
+    unsigned long long t_exit;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_exit));
+    unsigned long long* rec = reinterpret_cast<unsigned long long*>(p.big_queue) + (size_t)p.big_capacity * 8 + 128 +
+                              ((size_t)(p.late ? gridDim.x * TRI_WARPS : 0) + blockIdx.x * TRI_WARPS + warp) * 6;
+    rec[0] = t_entry; rec[1] = t_exit; rec[2] = t_chase; rec[3] = t_proc; rec[4] = n_done; rec[5] = n_grabs;
+  }
+#endif
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
   if (lane == 0 && kept) atomicAdd(p.tri_counter, (unsigned long long)kept);

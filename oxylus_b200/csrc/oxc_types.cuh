@@ -63,6 +63,7 @@ struct HizDesc {
 };
 
 struct CullParams {
+  const uint2* slabs; // (mesh instance, meshlet) of meshlet-instance index 32 k, written by the expansion
   const OxcMeshletInstance* meshlet_instances;
   const InstCull* inst;
   OxcMeshletInstanceVisibility* vis;

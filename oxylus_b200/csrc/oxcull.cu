@@ -106,6 +106,7 @@ struct OxcContext {
   float* d_lod_aabb = nullptr; // [mesh_cap][OXC_MESH_MAX_LODS][6]
   // frame buffers
   OxcMeshletInstance* d_meshlet_instances = nullptr;
+  uint2* d_slabs = nullptr; // (mesh instance, meshlet) of every 32nd meshlet instance
   uint32_t* d_visible = nullptr;
   uint32_t* d_mask = nullptr;
   uint32_t mask_words = 0;
@@ -240,6 +241,7 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   TRY(dalloc(&c->d_counts, (size_t)I));
   TRY(dalloc(&c->d_block_sums, (size_t)(I + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS + 1));
   TRY(dalloc(&c->d_meshlet_instances, (size_t)N + CULL_TILE)); // + one tile: full-size bulk copies of the last tile stay in bounds
+  TRY(dalloc(&c->d_slabs, (size_t)N / 32 + 2));
   TRY(dalloc(&c->d_visible, (size_t)N));
   c->mask_words = ((info->max_mask_bits > N ? info->max_mask_bits : N) + 31) / 32; // RendererInstance.cpp:1651
   TRY(dalloc(&c->d_mask, (size_t)c->mask_words));
@@ -254,7 +256,12 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
     const long v = atol(e);
     if (v >= 1 && v <= (1l << 24)) c->big_capacity = (uint32_t)v;
   }
-  TRY(dalloc(&c->d_big_queue, (size_t)c->big_capacity * 4));
+#ifdef OXC_RASTER_STATS
+  TRY(dalloc(&c->d_big_queue, (size_t)c->big_capacity * 4 + 64 + (1u << 16))); // + statistics slots + per-warp timeline records
+#else
+  TRY(dalloc(&c->d_big_queue, (size_t)c->big_capacity * 4 + 64 /* 128 u64 statistics slots of the OXC_RASTER_STATS build */));
+#endif
+  CK(cudaMemset(c->d_big_queue + (size_t)c->big_capacity * 4, 0, 1024));
   TRY(dalloc(&c->d_big_counters, 2));
   TRY(dalloc(&c->d_id_base_auto, 1));
   TRY(dalloc(&c->d_status, 1));
@@ -296,11 +303,16 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   OxcDrawIndexedIndirectCommand dc{0, 1, 0, 0, 0};
   CK(cudaMemcpy(c->d_draw_cmd, &dc, sizeof dc, cudaMemcpyHostToDevice));
 #define OCC(dst, kern, threads) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(dst), kern, threads, 0))
-  OCC(c->occ_cull[0][0][0], (k_cull_meshlets<false, false, false, false>), CULL_THREADS);
-  OCC(c->occ_cull[1][0][0], (k_cull_meshlets<true, false, false, false>), CULL_THREADS);
-  OCC(c->occ_cull[1][0][1], (k_cull_meshlets<true, false, true, false>), CULL_THREADS);
-  OCC(c->occ_cull[1][1][0], (k_cull_meshlets<true, true, false, false>), CULL_THREADS);
-  OCC(c->occ_cull[1][1][1], (k_cull_meshlets<true, true, true, false>), CULL_THREADS);
+#define OCCC(dst, H, O, L)                                                                                                        \
+  CK(cudaFuncSetAttribute(k_cull_meshlets<H, O, L, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<O && !L>)));  \
+  CK(cudaFuncSetAttribute(k_cull_meshlets<H, O, L, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<O && !L>)));   \
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&(dst), (k_cull_meshlets<H, O, L, false>), CULL_THREADS, sizeof(CullShared<O && !L>)))
+  OCCC(c->occ_cull[0][0][0], false, false, false);
+  OCCC(c->occ_cull[1][0][0], true, false, false);
+  OCCC(c->occ_cull[1][0][1], true, false, true);
+  OCCC(c->occ_cull[1][1][0], true, true, false);
+  OCCC(c->occ_cull[1][1][1], true, true, true);
+#undef OCCC
   c->occ_cull[0][0][1] = c->occ_cull[0][1][0] = c->occ_cull[0][1][1] = c->occ_cull[0][0][0];
   OCC(c->occ_tri, k_cull_triangles, TRI_THREADS);
   OCC(c->occ_raster, k_raster_visbuffer, TRI_THREADS);
@@ -315,7 +327,7 @@ void oxc_destroy(OxcContext* c) {
   cudaSetDevice(c->device);
   cudaFree(c->d_meshes); cudaFree(c->d_mesh_instances); cudaFree(c->d_transforms); cudaFree(c->d_blob);
   cudaFree(c->d_lod_aabb); cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
-  cudaFree(c->d_meshlet_instances); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
+  cudaFree(c->d_meshlet_instances); cudaFree(c->d_slabs); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
   cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_big_queue); cudaFree(c->d_big_counters); cudaFree(c->d_id_base_auto); cudaFree(c->d_status); cudaFree(c->d_hiz);
   cudaFree(c->d_view_planes); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts); cudaFree(c->d_inst_views);
@@ -531,7 +543,7 @@ int oxc_cull_meshes(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, voi
     k_scan_block_sums<<<1, 1024, 0, s>>>(c->d_block_sums, n_blocks, c->d_vis, c->d_cull_meshlets_cmd, c->info.max_meshlet_instances, c->d_status);
     LAUNCHED();
     k_expand_meshlet_instances<<<n_blocks, CULL_MESHES_THREADS, 0, s>>>(c->d_counts, c->d_block_sums, p.first, p.count,
-                                                                      c->d_meshlet_instances, c->info.max_meshlet_instances);
+                                                                      c->d_meshlet_instances, c->info.max_meshlet_instances, c->d_slabs);
     LAUNCHED();
   }
   c->cached_cam = *cam;
@@ -549,6 +561,7 @@ int oxc_cull_meshlets(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, i
   k_set_cmd3<<<1, 1, 0, s>>>(c->d_cull_triangles_cmd, 0, 1, 1); // CullGeometry.cpp:125-127
   LAUNCHED();
   CullParams p{};
+  p.slabs = c->d_slabs;
   p.meshlet_instances = c->d_meshlet_instances; p.inst = c->d_inst; p.vis = c->d_vis; p.visible_indices = c->d_visible;
   p.mask = c->d_mask; p.tri_cmd = c->d_cull_triangles_cmd; p.id_base = c->id_base; p.hiz = c->hiz;
   p.cam_pos[0] = cam->position[0]; p.cam_pos[1] = cam->position[1]; p.cam_pos[2] = cam->position[2];
@@ -557,12 +570,12 @@ int oxc_cull_meshlets(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, i
   const bool hizp = use_hiz != 0;
   const bool occ = hizp && (flags & OXC_CULL_TEST_OCCLUSION) != 0;
   const bool late = hizp && (flags & OXC_CULL_LATE_PASS) != 0;
-  const uint32_t tiles = (c->info.max_meshlet_instances + CULL_TILE - 1) / CULL_TILE;
+  const uint32_t tiles = (c->info.max_meshlet_instances + CULL_THREADS - 1) / CULL_THREADS;
   int occn = c->occ_cull[hizp][occ][late];
   uint32_t grid = (uint32_t)(c->sm_count * (occn > 0 ? occn : 1));
   if (grid > tiles) grid = tiles;
   if (grid == 0) grid = 1;
-#define GO(H, O, L, Z) k_cull_meshlets<H, O, L, Z><<<grid, CULL_THREADS, 0, s>>>(p)
+#define GO(H, O, L, Z) k_cull_meshlets<H, O, L, Z><<<grid, CULL_THREADS, sizeof(CullShared<O && !L>), s>>>(p)
   const bool zero = hizp && c->hiz_zero;
   if (hizp) {
     if (occ) {
@@ -677,7 +690,7 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
   TriParams p{};
   int rc = tri_common(c, cam, flags, s, &p);
   if (rc != OXC_OK) return rc;
-  p.visbuf = reinterpret_cast<unsigned long long*>(vis); p.width = w; p.height = h;
+  p.visbuf = reinterpret_cast<unsigned long long*>(vis); p.width = w; p.height = h; p.f_width = (float)w; p.f_height = (float)h;
   p.small_primitive_cull = small_primitive_cull ? 1u : 0u;
   p.work_counter = c->d_raster_work;
   CK(cudaMemsetAsync(c->d_raster_work, 0, 4, s));
@@ -705,7 +718,7 @@ int oxc_raster_visbuffer_clip_pass(OxcContext* c, const OxcCullCamera* cam, uint
   TriParams p{};
   int rc = tri_common(c, cam, flags, s, &p);
   if (rc != OXC_OK) return rc;
-  p.visbuf = reinterpret_cast<unsigned long long*>(vis); p.width = w; p.height = h;
+  p.visbuf = reinterpret_cast<unsigned long long*>(vis); p.width = w; p.height = h; p.f_width = (float)w; p.f_height = (float)h;
   p.big_queue = c->d_big_queue; p.big_counters = c->d_big_counters; p.big_capacity = c->big_capacity;
   CK(cudaMemsetAsync(c->d_big_counters, 0, 8, s));
   uint32_t tiles = (c->info.max_meshlet_instances + TRI_WARPS - 1) / TRI_WARPS;
@@ -945,6 +958,9 @@ int oxc_check_status(OxcContext* c, void* stream, uint32_t* flags_out) {
                 (f & OXC_STATUS_ID_OVERFLOW) ? " a meshlet-instance id overflowed the vis-buffer id bits" : "");
   return fail(OXC_E_INVALID, "device status 0x%x: malformed geometry (micro index >= vertex_count or vertex index >= Mesh::vertex_count); such triangles are skipped", f);
 }
+
+// instrumentation builds (-DOXC_RASTER_STATS): device pointer of the 128 u64 statistics slots behind the chunk queue
+void* oxc_debug_stats_ptr(OxcContext* c) { return c ? static_cast<void*>(c->d_big_queue + (size_t)c->big_capacity * 4) : nullptr; }
 
 int oxc_mark_hiz_dirty(OxcContext* c) {
   if (!c) return fail(OXC_E_INVALID, "null context");
