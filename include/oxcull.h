@@ -246,7 +246,8 @@ enum {
   OXC_STATUS_MESHLET_OVERFLOW = 1 << 0, /* cull_meshes wanted to emit more than max_meshlet_instances (clamped) */
   OXC_STATUS_BAD_GEOMETRY = 1 << 1,     /* a micro index >= vertex_count or a vertex index >= Mesh::vertex_count (triangle skipped) */
   OXC_STATUS_SURVIVOR_OVERFLOW = 1 << 2,/* oxc_mgpu_exchange_frame: a rank's survivor list exceeded the gather capacity (truncated) */
-  OXC_STATUS_ID_OVERFLOW = 1 << 3       /* a vis-buffer id did not fit the id bits of the packing (pixel skipped) */
+  OXC_STATUS_ID_OVERFLOW = 1 << 3,      /* a vis-buffer id did not fit the id bits of the packing (pixel skipped) */
+  OXC_STATUS_PEER_TIMEOUT = 1 << 4      /* oxc_mgpu_exchange_hiz: a peer did not raise its flag within 30 s (OXC_MGPU_TIMEOUT_MS); that frame's pyramid is incomplete */
 };
 int oxc_check_status(OxcContext* ctx, void* stream, uint32_t* flags_out /* may be NULL */);
 /* The Hi-Z pyramid was written through OxcOutputs::hiz by something other than an oxc_* call (an external reduce,
@@ -424,6 +425,44 @@ int oxc_decode_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, const uin
  * level k-1.  Output layout == the hpb_dev input of oxc_cull_meshlets_hpb. */
 int oxc_build_hpb(OxcContext* ctx, const uint32_t* page_table_dev, uint32_t page_table_size, uint32_t layers,
                   uint8_t* hpb_dev, uint32_t hpb_levels, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange (SURVEY §8e, §8b oxc_mgpu_*; the reference is single-GPU).  One context per GPU / process, mesh instances
+ * sharded with oxc_set_shard_auto.  Per frame a sharded host runs
+ *     clear, cull_meshes, cull_meshlets(early), raster      (local)
+ *     oxc_mgpu_exchange_hiz                                 instead of oxc_build_hiz_packed
+ *     cull_meshlets(late), raster                           (local)
+ *     oxc_mgpu_exchange_frame                               merged image + everybody's survivor lists
+ * and gets bit for bit what one GPU computes for the whole scene (max / set union are associative and commutative).
+ *
+ * oxc_mgpu_init is COLLECTIVE (every rank calls it): it creates the NCCL communicator from the 128-byte id rank 0 obtained with
+ * oxc_mgpu_get_unique_id and handed to the other ranks by any means (the tests broadcast it with torch.distributed; an MPI
+ * or socket broadcast does as well), and maps every peer's Hi-Z exchange buffer with CUDA IPC.  oxc_mgpu_init_with_comm adopts
+ * a communicator the host already owns (ncclComm_t passed as void*).  NCCL itself is dlopen'ed on first use.
+ *
+ * exchange_hiz: the rank's point-sampled mip-0 texels are max-reduced directly into every peer's exchange buffer over NVLink
+ * peer memory by the sampling kernel itself (only the texels the rank drew a fragment into travel), a per-rank flag is the
+ * barrier, then every rank builds the identical pyramid.  Without peer access it falls back to ncclAllReduce(max) of mip 0.
+ * exchange_frame: ncclAllReduce(ncclUint64, ncclMax) of the packed vis buffer in place (NULL skips it) + ncclAllGather of
+ * {total, early, late, gathered} counters and of fixed-capacity survivor-id segments into the buffers OxcMgpuInfo names; a rank
+ * whose survivors exceed survivor_capacity raises OXC_STATUS_SURVIVOR_OVERFLOW (oxc_check_status) — never a silent truncation.
+ * ---------------------------------------------------------------------------------------------- */
+#define OXC_MGPU_ID_BYTES 128
+typedef struct OxcMgpuInfo {
+  uint32_t active, rank, world;
+  uint32_t survivor_capacity;       /* ids per rank segment */
+  uint32_t hiz_over_peer_memory;    /* 1: NVLink peer-memory reduction; 0: NCCL fallback */
+  uint32_t* gathered_counts[2];     /* device, per slot: world x {total, early, late, ids gathered} */
+  uint32_t* gathered_ids[2];        /* device, per slot: world segments of survivor_capacity global meshlet-instance ids */
+} OxcMgpuInfo;
+int oxc_mgpu_get_unique_id(uint8_t id[OXC_MGPU_ID_BYTES]);
+int oxc_mgpu_init(OxcContext* ctx, uint32_t rank, uint32_t world, const uint8_t id[OXC_MGPU_ID_BYTES],
+                  uint32_t survivor_capacity /* 0 = max_meshlet_instances; the ranks agree on the largest value requested */);
+int oxc_mgpu_init_with_comm(OxcContext* ctx, void* nccl_comm, uint32_t survivor_capacity);
+int oxc_mgpu_shutdown(OxcContext* ctx);
+int oxc_mgpu_info(OxcContext* ctx, OxcMgpuInfo* out);
+int oxc_mgpu_exchange_hiz(OxcContext* ctx, const uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream);
+int oxc_mgpu_exchange_frame(OxcContext* ctx, uint64_t* vis_dev /* may be NULL */, uint32_t width, uint32_t height, int slot, void* stream);
 
 int oxc_get_outputs(OxcContext* ctx, OxcOutputs* out);
 /* Instrumentation hook: 128 u64 counters that builds with -DOXC_RASTER_STATS fill (tools/raster_stats.py); zero otherwise. */

@@ -116,7 +116,7 @@ MAX_VIEWS = 16
 VIS_PRIMITIVE_BITS = 8
 VIS_WIDE_PRIMITIVE_BITS = 6
 VIS_CLEAR = 0xFFFFFFFF
-STATUS_MESHLET_OVERFLOW, STATUS_BAD_GEOMETRY, STATUS_SURVIVOR_OVERFLOW, STATUS_ID_OVERFLOW = 1, 2, 4, 8
+STATUS_MESHLET_OVERFLOW, STATUS_BAD_GEOMETRY, STATUS_SURVIVOR_OVERFLOW, STATUS_ID_OVERFLOW, STATUS_PEER_TIMEOUT = 1, 2, 4, 8, 16
 
 # VSMPageState — Shaders/rmvsm.slang:16-28 ([Flags] enum)
 VSM_PAGE_VISIBLE = 1
@@ -179,6 +179,20 @@ class Outputs(C.Structure):
         ("status_flags", C.c_void_p),
         ("vis_primitive_bits", C.c_uint32),
     ]
+
+
+class MgpuInfo(C.Structure):
+    """OxcMgpuInfo"""
+
+    _fields_ = [
+        ("active", C.c_uint32), ("rank", C.c_uint32), ("world", C.c_uint32), ("survivor_capacity", C.c_uint32),
+        ("hiz_over_peer_memory", C.c_uint32),
+        ("gathered_counts", C.c_void_p * 2),
+        ("gathered_ids", C.c_void_p * 2),
+    ]
+
+
+MGPU_ID_BYTES = 128
 
 
 class DecodeTargets(C.Structure):

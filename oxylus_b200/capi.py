@@ -20,7 +20,9 @@ SYMBOLS = [
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
     "oxc_decode_visbuffer", "oxc_build_hpb",
-    "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_debug_stats_ptr", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
+    "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_debug_stats_ptr",
+    "oxc_mgpu_get_unique_id", "oxc_mgpu_init", "oxc_mgpu_init_with_comm", "oxc_mgpu_shutdown", "oxc_mgpu_info", "oxc_mgpu_exchange_hiz",
+    "oxc_mgpu_exchange_frame", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
 ]
@@ -79,6 +81,13 @@ def load(build_if_missing=True):
     lib.oxc_get_outputs.argtypes = [vp, C.POINTER(abi.Outputs)]
     lib.oxc_check_status.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
     lib.oxc_mark_hiz_dirty.argtypes = [vp]
+    lib.oxc_mgpu_get_unique_id.argtypes = [vp]
+    lib.oxc_mgpu_init.argtypes = [vp, u32, u32, vp, u32]
+    lib.oxc_mgpu_init_with_comm.argtypes = [vp, vp, u32]
+    lib.oxc_mgpu_shutdown.argtypes = [vp]
+    lib.oxc_mgpu_info.argtypes = [vp, C.POINTER(abi.MgpuInfo)]
+    lib.oxc_mgpu_exchange_hiz.argtypes = [vp, vp, u32, u32, vp]
+    lib.oxc_mgpu_exchange_frame.argtypes = [vp, vp, u32, u32, i32, vp]
     lib.oxc_debug_stats_ptr.argtypes = [vp]
     lib.oxc_debug_stats_ptr.restype = vp
     lib.oxc_copy.argtypes = [vp, vp, vp, u64, i32, vp]
@@ -342,6 +351,41 @@ class Context:
     def status_flags(self):
         """The sticky status word without raising / clearing."""
         return int(self.download(self.out.status_flags, np.uint32, 1)[0])
+
+    # ---- multi-GPU exchange (oxc_mgpu_*) ----
+    @staticmethod
+    def mgpu_unique_id():
+        """128-byte communicator id (rank 0 creates it; the host hands it to the other ranks)."""
+        buf = (C.c_uint8 * abi.MGPU_ID_BYTES)()
+        _check(load().oxc_mgpu_get_unique_id(buf), "oxc_mgpu_get_unique_id")
+        return bytes(buf)
+
+    def mgpu_init(self, rank, world, unique_id, survivor_capacity=0):
+        buf = (C.c_uint8 * abi.MGPU_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        _check(self.lib.oxc_mgpu_init(self.h, rank, world, buf, survivor_capacity), "oxc_mgpu_init")
+        return self.mgpu_info()
+
+    def mgpu_info(self):
+        info = abi.MgpuInfo()
+        _check(self.lib.oxc_mgpu_info(self.h, C.byref(info)), "oxc_mgpu_info")
+        return info
+
+    def mgpu_exchange_hiz(self, vis_dev, w, h):
+        _check(self.lib.oxc_mgpu_exchange_hiz(self.h, _ptr(vis_dev), w, h, self.stream), "oxc_mgpu_exchange_hiz")
+
+    def mgpu_exchange_frame(self, vis_dev, w, h, slot=0, stream=None):
+        _check(self.lib.oxc_mgpu_exchange_frame(self.h, _ptr(vis_dev), w, h, slot, self.stream if stream is None else stream),
+               "oxc_mgpu_exchange_frame")
+
+    def mgpu_shutdown(self):
+        _check(self.lib.oxc_mgpu_shutdown(self.h), "oxc_mgpu_shutdown")
+
+    def mgpu_gathered(self, slot=0):
+        """(counts[world, 4] = total, early, late, gathered ; list of per-rank id arrays) of the last exchange_frame into `slot`."""
+        info = self.mgpu_info()
+        cnt = self.download(info.gathered_counts[slot], np.uint32, info.world * 4).reshape(info.world, 4)
+        ids = self.download(info.gathered_ids[slot], np.uint32, info.world * info.survivor_capacity).reshape(info.world, info.survivor_capacity)
+        return cnt, [ids[r, : cnt[r, 3]] for r in range(info.world)]
 
     def debug_stats_ptr(self):
         return self.lib.oxc_debug_stats_ptr(self.h)

@@ -11,9 +11,13 @@
 #include <new>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h> // types only: the library is dlopen'ed by oxc_mgpu_init (single-GPU hosts never need it)
+
 #include "kernels_cull.cuh"
 #include "kernels_decode.cuh"
 #include "kernels_hiz.cuh"
+#include "kernels_mgpu.cuh"
 #include "kernels_tri.cuh"
 
 using namespace oxc;
@@ -142,6 +146,22 @@ struct OxcContext {
   bool hiz_zero = true; // the pyramid holds the cleared (all-zero) image: lets the early pass skip the Hi-Z fetches
   int occ_tri = 1, occ_raster = 1, occ_mv = 1;
   bool hpb_smem_opt_in = false;
+  // multi-GPU (oxc_mgpu_*)
+  struct Mgpu {
+    bool active = false, own_comm = false, peer_hiz = false;
+    uint32_t rank = 0, world = 1, capacity = 0;
+    ncclComm_t comm = nullptr;
+    uint32_t* xbuf = nullptr;         // [2][hw*hh] exchange texels + [2][MGPU_MAX_RANKS] flags (one cudaMalloc: one IPC handle)
+    size_t xbuf_words = 0;
+    void* peer_base[MGPU_MAX_RANKS] = {};
+    MgpuPeers peers{};
+    uint32_t* d_seq = nullptr;
+    unsigned long long timeout_ns = 30000000000ull; // how long a rank waits for its peers' Hi-Z flags (OXC_MGPU_TIMEOUT_MS)
+    uint32_t* cnt_stage[2] = {nullptr, nullptr};
+    uint32_t* ids_stage[2] = {nullptr, nullptr};
+    uint32_t* cnt_all[2] = {nullptr, nullptr};
+    uint32_t* ids_all[2] = {nullptr, nullptr};
+  } mg;
   uint32_t* d_status = nullptr;   // sticky OXC_STATUS_* bits raised by kernels
   std::vector<uint64_t> id_prefix; // [I + 1] prefix sums of the largest-LOD meshlet count per mesh instance (host side)
   uint64_t scene_id_bound = 0;    // upper bound of the GLOBAL meshlet-instance id range (sum over all mesh instances of the largest LOD)
@@ -149,6 +169,8 @@ struct OxcContext {
 };
 
 namespace {
+
+void mgpu_release(OxcContext* c); // defined with the oxc_mgpu_* entry points
 
 template <typename T>
 int dalloc(T** p, size_t n) {
@@ -325,6 +347,7 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
 void oxc_destroy(OxcContext* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  if (c->mg.active) { cudaDeviceSynchronize(); mgpu_release(c); }
   cudaFree(c->d_meshes); cudaFree(c->d_mesh_instances); cudaFree(c->d_transforms); cudaFree(c->d_blob);
   cudaFree(c->d_lod_aabb); cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
   cudaFree(c->d_meshlet_instances); cudaFree(c->d_slabs); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
@@ -965,6 +988,257 @@ void* oxc_debug_stats_ptr(OxcContext* c) { return c ? static_cast<void*>(c->d_bi
 int oxc_mark_hiz_dirty(OxcContext* c) {
   if (!c) return fail(OXC_E_INVALID, "null context");
   c->hiz_zero = false;
+  return OXC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU exchange.  NCCL is loaded with dlopen: a host that never calls oxc_mgpu_* needs no NCCL at all, and a
+ * process that already carries one (PyTorch) shares it.
+ * ---------------------------------------------------------------------------------------------- */
+} // extern "C"
+
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*CommCount)(const ncclComm_t, int*) = nullptr;
+  ncclResult_t (*CommUserRank)(const ncclComm_t, int*) = nullptr;
+} g_nccl;
+
+int nccl_load() {
+  if (g_nccl.lib) return OXC_OK;
+  void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return fail(OXC_E_INVALID, "libnccl.so.2 not found (%s): oxc_mgpu_* needs NCCL", dlerror());
+#define SYM(field, name)                                                                    \
+  g_nccl.field = reinterpret_cast<decltype(g_nccl.field)>(dlsym(lib, name));                \
+  if (!g_nccl.field) return fail(OXC_E_INVALID, "libnccl.so.2 lacks %s", name)
+  SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllReduce, "ncclAllReduce"); SYM(AllGather, "ncclAllGather"); SYM(GetErrorString, "ncclGetErrorString");
+  SYM(CommCount, "ncclCommCount"); SYM(CommUserRank, "ncclCommUserRank");
+#undef SYM
+  g_nccl.lib = lib;
+  return OXC_OK;
+}
+#define NCK(expr)                                                                                                   \
+  do {                                                                                                              \
+    ncclResult_t r_ = (expr);                                                                                       \
+    if (r_ != ncclSuccess) return fail(OXC_E_CUDA, "%s: %s (%s:%d)", #expr, g_nccl.GetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+
+void mgpu_release(OxcContext* c) {
+  OxcContext::Mgpu& m = c->mg;
+  for (uint32_t r = 0; r < m.world && r < (uint32_t)MGPU_MAX_RANKS; r++)
+    if (r != m.rank && m.peer_base[r]) cudaIpcCloseMemHandle(m.peer_base[r]);
+  cudaFree(m.xbuf); cudaFree(m.d_seq);
+  for (int k = 0; k < 2; k++) { cudaFree(m.cnt_stage[k]); cudaFree(m.ids_stage[k]); cudaFree(m.cnt_all[k]); cudaFree(m.ids_all[k]); }
+  if (m.comm && m.own_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(m.comm);
+  m = OxcContext::Mgpu();
+}
+
+#define MGDBG(...) do { if (getenv("OXC_MGPU_DEBUG")) { fprintf(stderr, "[oxc_mgpu r%u] ", rank); fprintf(stderr, __VA_ARGS__); fprintf(stderr, "\n"); fflush(stderr); } } while (0)
+int mgpu_setup(OxcContext* c, ncclComm_t comm, bool own, uint32_t rank, uint32_t world, uint32_t survivor_capacity) {
+  OxcContext::Mgpu& m = c->mg;
+  MGDBG("setup: world %u, communicator ready", world);
+  m.comm = comm; m.own_comm = own; m.rank = rank; m.world = world;
+  m.capacity = survivor_capacity ? survivor_capacity : c->info.max_meshlet_instances;
+  if (const char* e = getenv("OXC_MGPU_TIMEOUT_MS")) {
+    const long long v = atoll(e);
+    if (v > 0) m.timeout_ns = (unsigned long long)v * 1000000ull;
+  }
+  if (world > 1) { // ncclAllGather needs the same segment size on every rank: agree on the largest request
+    uint32_t* d_cap = nullptr;
+    CK(cudaMalloc(&d_cap, 4));
+    CK(cudaMemcpy(d_cap, &m.capacity, 4, cudaMemcpyHostToDevice));
+    NCK(g_nccl.AllReduce(d_cap, d_cap, 1, ncclUint32, ncclMax, comm, nullptr));
+    CK(cudaStreamSynchronize(nullptr));
+    CK(cudaMemcpy(&m.capacity, d_cap, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_cap);
+    MGDBG("survivor segment capacity %u", m.capacity);
+  }
+  const size_t texels = (size_t)c->hiz.width * c->hiz.height;
+  m.xbuf_words = 2 * texels + 2 * MGPU_MAX_RANKS;
+  CK(cudaMalloc(&m.xbuf, m.xbuf_words * 4));
+  CK(cudaMemset(m.xbuf, 0, m.xbuf_words * 4));
+  CK(cudaMalloc(&m.d_seq, 4));
+  CK(cudaMemset(m.d_seq, 0, 4));
+  for (int k = 0; k < 2; k++) {
+    CK(cudaMalloc(&m.cnt_stage[k], 16));
+    CK(cudaMalloc(&m.ids_stage[k], (size_t)m.capacity * 4));
+    CK(cudaMalloc(&m.cnt_all[k], (size_t)world * 16));
+    CK(cudaMalloc(&m.ids_all[k], (size_t)world * m.capacity * 4));
+    CK(cudaMemset(m.cnt_all[k], 0, (size_t)world * 16));
+  }
+  // Exchange the CUDA-IPC handles of the Hi-Z exchange buffers through the communicator itself (64 bytes per rank), then map
+  // every peer's buffer.  Any failure (no peer access between the devices, IPC disabled in the container) leaves peer_hiz false:
+  // oxc_mgpu_exchange_hiz then falls back to an NCCL all-reduce of the mip-0 texels — slower, same result.
+  m.peer_hiz = false;
+  m.peers = MgpuPeers{};
+  m.peers.rank = rank; m.peers.world = world;
+  m.peers.xbuf[rank] = m.xbuf; m.peers.flags[rank] = m.xbuf + 2 * texels;
+  m.peer_base[rank] = m.xbuf;
+  if (world > 1) {
+    cudaIpcMemHandle_t mine{};
+    const bool have = cudaIpcGetMemHandle(&mine, m.xbuf) == cudaSuccess;
+    if (!have) cudaGetLastError();
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    unsigned char *d_one = nullptr, *d_all = nullptr;
+    CK(cudaMalloc(&d_one, 128));
+    CK(cudaMalloc(&d_all, (size_t)128 * world));
+    unsigned char rec[128] = {};
+    memcpy(rec, &mine, 64);
+    rec[64] = have ? 1 : 0;
+    CK(cudaMemcpy(d_one, rec, 128, cudaMemcpyHostToDevice));
+    MGDBG("ipc handle %s; allgather of the handles", have ? "ok" : "UNAVAILABLE");
+    NCK(g_nccl.AllGather(d_one, d_all, 128, ncclUint8, comm, nullptr));
+    CK(cudaStreamSynchronize(nullptr));
+    MGDBG("handles gathered");
+    std::vector<unsigned char> all((size_t)128 * world);
+    CK(cudaMemcpy(all.data(), d_all, all.size(), cudaMemcpyDeviceToHost));
+    cudaFree(d_one); cudaFree(d_all);
+    bool ok = true;
+    for (uint32_t r = 0; r < world && ok; r++) ok = all[(size_t)r * 128 + 64] == 1;
+    for (uint32_t r = 0; r < world && ok; r++) {
+      if (r == rank) continue;
+      cudaIpcMemHandle_t h;
+      memcpy(&h, &all[(size_t)r * 128], 64);
+      void* base = nullptr;
+      if (cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      m.peer_base[r] = base;
+      m.peers.xbuf[r] = static_cast<uint32_t*>(base);
+      m.peers.flags[r] = static_cast<uint32_t*>(base) + 2 * texels;
+    }
+    MGDBG("peer buffers mapped: %s", ok ? "yes" : "NO");
+    // every rank must take the same path: agree through one more tiny collective (min over ranks of "ok")
+    uint32_t* d_ok = nullptr;
+    CK(cudaMalloc(&d_ok, 4));
+    const uint32_t okv = ok ? 1u : 0u;
+    CK(cudaMemcpy(d_ok, &okv, 4, cudaMemcpyHostToDevice));
+    NCK(g_nccl.AllReduce(d_ok, d_ok, 1, ncclUint32, ncclMin, comm, nullptr));
+    CK(cudaStreamSynchronize(nullptr));
+    uint32_t all_ok = 0;
+    CK(cudaMemcpy(&all_ok, d_ok, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_ok);
+    m.peer_hiz = all_ok != 0;
+    MGDBG("hiz exchange over %s", m.peer_hiz ? "NVLink peer memory" : "NCCL all-reduce (fallback)");
+  }
+  m.active = true;
+  return OXC_OK;
+}
+} // namespace
+
+extern "C" {
+
+int oxc_mgpu_get_unique_id(uint8_t id[OXC_MGPU_ID_BYTES]) {
+  if (!id) return fail(OXC_E_INVALID, "null argument");
+  int rc = nccl_load();
+  if (rc != OXC_OK) return rc;
+  static_assert(sizeof(ncclUniqueId) == OXC_MGPU_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId u;
+  NCK(g_nccl.GetUniqueId(&u));
+  memcpy(id, &u, sizeof u);
+  return OXC_OK;
+}
+
+int oxc_mgpu_init(OxcContext* c, uint32_t rank, uint32_t world, const uint8_t id[OXC_MGPU_ID_BYTES], uint32_t survivor_capacity) {
+  if (!c || !id) return fail(OXC_E_INVALID, "null argument");
+  if (world == 0 || world > (uint32_t)MGPU_MAX_RANKS || rank >= world) return fail(OXC_E_INVALID, "rank %u / world %u (max %d ranks)", rank, world, MGPU_MAX_RANKS);
+  if (c->mg.active) return fail(OXC_E_STATE, "oxc_mgpu_init called twice");
+  CK(cudaSetDevice(c->device));
+  int rc = nccl_load();
+  if (rc != OXC_OK) return rc;
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof u);
+  ncclComm_t comm = nullptr;
+  NCK(g_nccl.CommInitRank(&comm, (int)world, u, (int)rank));
+  rc = mgpu_setup(c, comm, true, rank, world, survivor_capacity);
+  if (rc != OXC_OK) mgpu_release(c);
+  return rc;
+}
+
+int oxc_mgpu_init_with_comm(OxcContext* c, void* nccl_comm, uint32_t survivor_capacity) {
+  if (!c || !nccl_comm) return fail(OXC_E_INVALID, "null argument");
+  if (c->mg.active) return fail(OXC_E_STATE, "oxc_mgpu_init called twice");
+  CK(cudaSetDevice(c->device));
+  int rc = nccl_load();
+  if (rc != OXC_OK) return rc;
+  int world = 0, rank = 0;
+  NCK(g_nccl.CommCount(static_cast<ncclComm_t>(nccl_comm), &world));
+  NCK(g_nccl.CommUserRank(static_cast<ncclComm_t>(nccl_comm), &rank));
+  if (world <= 0 || world > MGPU_MAX_RANKS) return fail(OXC_E_INVALID, "communicator of %d ranks (max %d)", world, MGPU_MAX_RANKS);
+  rc = mgpu_setup(c, static_cast<ncclComm_t>(nccl_comm), false, (uint32_t)rank, (uint32_t)world, survivor_capacity);
+  if (rc != OXC_OK) mgpu_release(c);
+  return rc;
+}
+
+int oxc_mgpu_shutdown(OxcContext* c) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  mgpu_release(c);
+  return OXC_OK;
+}
+
+int oxc_mgpu_info(OxcContext* c, OxcMgpuInfo* out) {
+  if (!c || !out) return fail(OXC_E_INVALID, "null argument");
+  memset(out, 0, sizeof *out);
+  out->active = c->mg.active; out->rank = c->mg.rank; out->world = c->mg.world; out->survivor_capacity = c->mg.capacity;
+  out->hiz_over_peer_memory = c->mg.peer_hiz;
+  for (int k = 0; k < 2; k++) { out->gathered_counts[k] = c->mg.cnt_all[k]; out->gathered_ids[k] = c->mg.ids_all[k]; }
+  return OXC_OK;
+}
+
+// generate_hiz with the other ranks' depth: replaces oxc_build_hiz_packed between the two passes of a sharded frame
+int oxc_mgpu_exchange_hiz(OxcContext* c, const uint64_t* vis, uint32_t w, uint32_t h, void* stream) {
+  if (!c || !vis || !w || !h) return fail(OXC_E_INVALID, "bad argument");
+  if (!c->mg.active) return fail(OXC_E_STATE, "oxc_mgpu_init first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  OxcContext::Mgpu& m = c->mg;
+  if (m.world == 1) return oxc_build_hiz_packed(c, vis, w, h, stream);
+  const size_t n = (size_t)c->hiz.width * c->hiz.height;
+  if (m.peer_hiz) {
+    const uint32_t grid = (uint32_t)((n + 255) / 256 < (size_t)c->sm_count * 8 ? (n + 255) / 256 : (size_t)c->sm_count * 8);
+    k_mgpu_hiz_push<<<grid, 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(vis), w, h, c->hiz.width, c->hiz.height, ilog2(c->hiz.width),
+                                         ilog2(c->hiz.height), m.peers, m.d_seq);
+    LAUNCHED();
+    k_mgpu_signal<<<1, 32, 0, s>>>(m.peers, m.d_seq);
+    LAUNCHED();
+    k_mgpu_hiz_collect<<<c->sm_count * 4, 256, 0, s>>>(m.peers, m.d_seq, c->d_hiz, n, c->d_status, m.timeout_ns);
+    LAUNCHED();
+  } else {
+    int rc = oxc_build_hiz_mip0_packed(c, vis, w, h, stream);
+    if (rc != OXC_OK) return rc;
+    // depths are >= +0: the unsigned order of the bits is the order of the floats
+    NCK(g_nccl.AllReduce(c->d_hiz, c->d_hiz, n, ncclUint32, ncclMax, m.comm, s));
+  }
+  return oxc_build_hiz_from_mip0(c, stream);
+}
+
+// End of a sharded frame: per-pixel max of the packed vis buffer over the ranks (in place), and every rank's survivor list +
+// counters gathered into the context's buffers of `slot` (0/1: a host that overlaps this exchange with the next frame on a
+// side stream alternates the slots).
+int oxc_mgpu_exchange_frame(OxcContext* c, uint64_t* vis, uint32_t w, uint32_t h, int slot, void* stream) {
+  if (!c || (slot != 0 && slot != 1)) return fail(OXC_E_INVALID, "bad argument");
+  if (!c->mg.active) return fail(OXC_E_STATE, "oxc_mgpu_init first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  OxcContext::Mgpu& m = c->mg;
+  k_mgpu_stage_survivors<<<c->sm_count, 256, 0, s>>>(c->d_vis, c->d_visible, m.capacity, m.cnt_stage[slot], m.ids_stage[slot], c->d_status);
+  LAUNCHED();
+  if (m.world == 1) {
+    CK(cudaMemcpyAsync(m.cnt_all[slot], m.cnt_stage[slot], 16, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(m.ids_all[slot], m.ids_stage[slot], (size_t)m.capacity * 4, cudaMemcpyDeviceToDevice, s));
+    return OXC_OK;
+  }
+  if (vis) NCK(g_nccl.AllReduce(vis, vis, (size_t)w * h, ncclUint64, ncclMax, m.comm, s)); // reverse-Z GreaterOrEqual == max of depth|id
+  NCK(g_nccl.AllGather(m.cnt_stage[slot], m.cnt_all[slot], 4, ncclUint32, m.comm, s));
+  NCK(g_nccl.AllGather(m.ids_stage[slot], m.ids_all[slot], m.capacity, ncclUint32, m.comm, s));
   return OXC_OK;
 }
 

@@ -26,14 +26,29 @@ def wrap_device(ptr, n, dtype, device):
 
 
 class VisibilityPipeline:
-    def __init__(self, scene, device=0, shard=None, alloc_reordered_indices=False, auto_id_base=False):
+    """shard = (first mesh instance, count) restricts the context to a contiguous range of mesh instances (multi-GPU).
+    mgpu = dict(rank=, world=, unique_id=, survivor_capacity=0): the product's multi-GPU exchange (oxc_mgpu_*) is set up and
+    frame() uses oxc_mgpu_exchange_hiz between the passes; exchange_frame() merges the outputs.
+    shard_capacity: meshlet instances this context can hold (default: the whole scene; a shard host passes its own share so
+    the 8 B + 4 B per-meshlet buffers are shard-sized while the 1-bit mask still spans the scene)."""
+
+    def __init__(self, scene, device=0, shard=None, alloc_reordered_indices=False, auto_id_base=False, mgpu=None,
+                 shard_capacity=None, wide_ids=False):
         self.scene = scene
         self.device = torch.device("cuda", device)
         torch.cuda.set_device(self.device)
         hw, hh = scene.hiz_extent()
-        self.ctx = capi.Context(device, max(1, scene.mesh_instance_count), max(1, scene.max_meshlet_instance_count), hw, hh,
-                                alloc_reordered_indices=alloc_reordered_indices, stream=0)
+        cap = max(1, scene.max_meshlet_instance_count if shard_capacity is None else shard_capacity)
+        self.ctx = capi.Context(device, max(1, scene.mesh_instance_count), cap, hw, hh,
+                                alloc_reordered_indices=alloc_reordered_indices, stream=0,
+                                max_mask_bits=max(1, scene.max_meshlet_instance_count), wide_ids=wide_ids)
+        if shard is not None:  # before set_scene: the capacity check is made against the shard's range
+            if auto_id_base:
+                self.ctx.set_shard_auto(shard[0], shard[1])  # id base from a local count-only replay: no exchange
         self.ctx.set_scene(scene)
+        self.mgpu = None
+        if mgpu is not None:
+            self.mgpu = self.ctx.mgpu_init(mgpu["rank"], mgpu["world"], mgpu["unique_id"], mgpu.get("survivor_capacity", 0))
         self.w, self.h = scene.width, scene.height
         # two packed vis buffers: multi-GPU runs alternate them so the trailing exchange of frame i (side stream) can
         # overlap frame i+1; single-GPU code only ever uses buffer 0
@@ -43,11 +58,8 @@ class VisibilityPipeline:
         if scene.occluder_depth is not None:
             self.occluder = torch.from_numpy(np.ascontiguousarray(scene.occluder_depth)).to(self.device)
         self.id_base = torch.zeros(1, dtype=torch.int32, device=self.device)
-        if shard is not None:
-            if auto_id_base:
-                self.ctx.set_shard_auto(shard[0], shard[1])  # id base from a local count-only replay: no exchange
-            else:
-                self.ctx.set_shard(shard[0], shard[1], self.id_base.data_ptr())
+        if shard is not None and not auto_id_base:
+            self.ctx.set_shard(shard[0], shard[1], self.id_base.data_ptr())
         self.use_torch_stream()
 
     def select_buffer(self, b):
@@ -81,8 +93,10 @@ class VisibilityPipeline:
         c.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, v)
         if mark:
             mark("raster_early")
-        if between_passes:
-            # multi-GPU: only the point-sampled mip 0 is exchanged (max over ranks commutes with sampling)
+        if self.mgpu is not None:
+            c.mgpu_exchange_hiz(v, w, h)  # mip-0 texels max-reduced into every peer over NVLink, then the identical pyramid
+        elif between_passes:
+            # legacy host-driven exchange: only the point-sampled mip 0 travels (max over ranks commutes with sampling)
             c.build_hiz_mip0_packed(v, w, h)
             between_passes()
             c.build_hiz_from_mip0()
@@ -120,6 +134,11 @@ class VisibilityPipeline:
         c.build_hiz_from_mip0()
         c.cull_meshlets(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, True)
         c.raster_visbuffer(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, v)
+
+    def exchange_frame(self, slot=0, stream=None, with_image=True):
+        """oxc_mgpu_exchange_frame: vis-buffer max-reduce (in place) + survivor allgather into the context's slot buffers."""
+        self.ctx.mgpu_exchange_frame(self.vis64.data_ptr() if with_image else None, self.w, self.h, slot,
+                                     None if stream is None else stream.cuda_stream)
 
     def counters(self):
         vis = self.ctx.visibility()

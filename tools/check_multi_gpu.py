@@ -1,13 +1,10 @@
 #!/usr/bin/env python
-"""Multi-GPU parity check on real GPUs (run under torchrun, N >= 2):
-
-    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/check_multi_gpu.py
-
-Every rank culls + rasterises its mesh-instance shard (CUDA kernels through the C ABI), with the real exchange
-steps (id-base allgather, Hi-Z mip-0 max-reduce, vis-buffer max-reduce, survivor allgather).  Rank 0 then runs
-the SAME scene on one GPU and asserts bit-identical results: packed vis buffer, sorted survivor ids, per-rank
-mask slices, Hi-Z pyramid.  Correctness rule of SURVEY.md §8e: G GPUs == 1 GPU, bit for bit.
-"""
+"""G GPUs == 1 GPU, bit for bit, through the product's multi-GPU API (oxc_mgpu_*):
+    torchrun --standalone --nproc-per-node G tools/check_multi_gpu.py
+Every rank runs the sharded pipeline (oxc_set_shard_auto + oxc_mgpu_exchange_hiz / _frame); rank 0 also runs the whole scene
+on one GPU and compares: merged vis buffer, gathered survivor ids (as a set), the Hi-Z pyramid of every rank, the visibility
+mask (each rank's slice).  torch.distributed only broadcasts the 128-byte communicator id and gathers the verdicts."""
+import json
 import os
 import sys
 
@@ -23,80 +20,70 @@ from oxylus_b200 import abi, capi, dist as oxdist, pipeline, synth  # noqa: E402
 def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    dev = torch.device("cuda", local)
-    sc = synth.make_scene(300_000, config_index=5, width=1280, height=720, n_unique_meshes=64)
+    dist.init_process_group("gloo")  # plumbing only: the data path is the product's own NCCL communicator + peer memory
+    n = int(os.environ.get("OXC_CHECK_MESHLETS", 300_000))
+    sc = synth.make_scene(n, config_index=5, width=1280, height=720, n_unique_meshes=64)
     lod0 = oxdist.lod0_counts_of(sc)
     parts = oxdist.partition_mesh_instances(lod0, world)
-    cap = max(int(lod0[f:f + c].sum()) for f, c in parts)
-    auto = os.environ.get("OXC_AUTO_ID_BASE", "1") == "1"
-    pipe = pipeline.VisibilityPipeline(sc, device=local, shard=parts[rank], auto_id_base=auto)
-    out = pipe.ctx.out
-    vis_view = pipeline.wrap_device(out.visibility, 3, torch.int32, dev)
-    ids_view = pipeline.wrap_device(out.visible_meshlet_instances_indices, cap, torch.int32, dev)
-    hw, hh = sc.hiz_extent()
-    mip0_view = pipeline.wrap_device(out.hiz, hw * hh, torch.int32, dev)
-    vis_all = torch.zeros(world * 3, dtype=torch.int32, device=dev)
-    ids_all = torch.zeros(world * cap, dtype=torch.int32, device=dev)
-
-    def after_cull_meshes():
-        dist.all_gather_into_tensor(vis_all, vis_view)
-        pipe.id_base.copy_(vis_all.view(world, 3)[:rank, 0].sum())
-
-    def between_passes():
-        dist.all_reduce(mip0_view, op=dist.ReduceOp.MAX)
-
-    def after_frame():
-        oxdist.reduce_visbuffer(pipe.vis64)
-        dist.all_gather_into_tensor(vis_all, vis_view)
-        dist.all_gather_into_tensor(ids_all, ids_view)
-
-    single = pipeline.VisibilityPipeline(sc, device=local) if rank == 0 else None
-    ok = True
+    cap = int(lod0[parts[rank][0]: parts[rank][0] + parts[rank][1]].sum())
+    uid = [capi.Context.mgpu_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    pipe = pipeline.VisibilityPipeline(sc, device=local, shard=parts[rank], auto_id_base=True, shard_capacity=max(cap, 1),
+                                       mgpu=dict(rank=rank, world=world, unique_id=uid[0], survivor_capacity=max(1024, cap)))
+    ref = pipeline.VisibilityPipeline(sc, device=local) if rank == 0 else None
+    ok, detail = True, {}
+    torch.cuda.synchronize()
+    dist.barrier()
+    dbg = (lambda *a: print(f"[check r{rank}]", *a, file=sys.stderr, flush=True)) if os.environ.get("OXC_MGPU_DEBUG") else (lambda *a: None)
     for f in range(4):
-        cam = sc.camera(2.0 * f)
-        pipe.frame(cam, after_cull_meshes=None if auto else after_cull_meshes, between_passes=between_passes, after_frame=after_frame)
+        cam = sc.camera(2.0 * (f % 2))
+        dbg("frame", f, "start")
+        pipe.frame(cam)
         torch.cuda.synchronize()
-        counts = vis_all.view(world, 3).cpu().numpy()
-        ids = ids_all.view(world, cap).cpu().numpy()
-        merged = np.concatenate([ids[r, : counts[r, 1] + counts[r, 2]] for r in range(world)]).astype(np.uint32)
-        img = pipe.vis64.cpu().numpy().view(np.uint64)
-        masks = [None] * world
-        dist.all_gather_object(masks, pipe.ctx.mask())
-        hiz = np.concatenate([l.reshape(-1) for l in pipe.ctx.hiz_levels()])
+        dbg("frame", f, "kernels + hiz exchange done; status", pipe.ctx.status_flags())
+        pipe.exchange_frame(slot=f & 1)
+        torch.cuda.synchronize()
+        dbg("frame", f, "exchange_frame done")
+        pipe.ctx.check_status()
+        cnt, ids = pipe.ctx.mgpu_gathered(f & 1)
+        hiz = np.concatenate([l.ravel() for l in pipe.ctx.hiz_levels()]).view(np.uint32)
         if rank == 0:
-            single.frame(cam)
+            ref.frame(cam)
             torch.cuda.synchronize()
-            c1 = single.counters()
-            ref_ids = single.ctx.visible_indices(c1["early"] + c1["late"])
-            ref_img = single.vis64.cpu().numpy().view(np.uint64)
-            ref_hiz = np.concatenate([l.reshape(-1) for l in single.ctx.hiz_levels()])
-            ref_mask = single.ctx.mask()
-            # union of the ranks' owned mask bit ranges
-            off = sc.mesh_instances["meshlet_instance_visibility_offset"].astype(np.int64)
-            total_bits = sc.max_meshlet_instance_count
-            merged_bits = np.zeros(len(ref_mask) * 32, dtype=np.uint8)
-            for r, (first, count) in enumerate(parts):
-                lo = int(off[first]) if count else total_bits
-                hi = int(off[first + count]) if first + count < len(off) else total_bits
-                bits = np.unpackbits(masks[r].view(np.uint8), bitorder="little")
-                merged_bits[lo:hi] = bits[lo:hi]
-            merged_mask = np.packbits(merged_bits, bitorder="little").view(np.uint32)
-            checks = dict(
-                totals=int(counts[:, 0].sum()) == c1["total"],
-                early=int(counts[:, 1].sum()) == c1["early"], late=int(counts[:, 2].sum()) == c1["late"],
-                survivors=np.array_equal(np.sort(merged), np.sort(ref_ids)),
-                visbuffer=np.array_equal(img, ref_img), hiz=np.array_equal(hiz.view(np.uint32), ref_hiz.view(np.uint32)),
-                mask=np.array_equal(merged_mask, ref_mask))
-            print(f"frame {f}: world={world} survivors={len(ref_ids)} " + " ".join(f"{k}={'OK' if v else 'MISMATCH'}" for k, v in checks.items()),
-                  flush=True)
-            ok = ok and all(checks.values())
-    flag = torch.tensor([1 if ok else 0], device=dev)
-    dist.broadcast(flag, 0)
-    dist.destroy_process_group()
+            rc = ref.counters()
+            r_ids = ref.ctx.visible_indices(rc["early"] + rc["late"])
+            same_img = bool(torch.equal(pipe.vis64, ref.vis64))
+            same_ids = bool(np.array_equal(np.sort(np.concatenate(ids)), np.sort(r_ids)))
+            same_cnt = int(cnt[:, 0].sum()) == rc["total"] and int(cnt[:, 1].sum()) == rc["early"] and int(cnt[:, 2].sum()) == rc["late"]
+            ref_hiz = np.concatenate([l.ravel() for l in ref.ctx.hiz_levels()]).view(np.uint32)
+            ref_mask = ref.ctx.mask()
+            detail[f] = dict(image=same_img, ids=same_ids, counts=same_cnt)
+            ok = ok and same_img and same_ids and same_cnt
+        else:
+            ref_hiz, ref_mask = None, None
+        box = [ref_hiz, ref_mask]
+        dist.broadcast_object_list(box, src=0)
+        same_hiz = bool(np.array_equal(hiz, box[0]))
+        # this rank's slice of the persistent mask (bits are laid out in mesh-instance order)
+        off = sc.mesh_instances["meshlet_instance_visibility_offset"].astype(np.int64)
+        lo = int(off[parts[rank][0]]) if parts[rank][1] else 0
+        hi = lo + cap
+        mine = np.unpackbits(pipe.ctx.mask().view(np.uint8), bitorder="little")[lo:hi]
+        want = np.unpackbits(box[1].view(np.uint8), bitorder="little")[lo:hi]
+        verdict = [same_hiz and bool(np.array_equal(mine, want))]
+        gathered = [None] * world
+        dist.all_gather_object(gathered, verdict[0])
+        if rank == 0:
+            detail[f]["hiz_and_mask_per_rank"] = gathered
+            ok = ok and all(gathered)
+    info = pipe.mgpu
     if rank == 0:
-        print("MULTI-GPU PARITY: " + ("PASS" if ok else "FAIL"), flush=True)
-    sys.exit(0 if int(flag.item()) else 1)
+        print(json.dumps({"check": "multi_gpu_equals_single_gpu", "world": world, "meshlets": n, "pass": bool(ok),
+                          "hiz_over_peer_memory": bool(info.hiz_over_peer_memory), "frames": detail}), flush=True)
+        ref.close()
+    pipe.close()
+    dist.destroy_process_group()
+    sys.exit(0 if ok or rank != 0 else 1)
 
 
 if __name__ == "__main__":
