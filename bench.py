@@ -50,6 +50,11 @@ def parse_args():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: run the trailing exchange on the main stream (no overlap with the next frame)")
     ap.add_argument("--cpu-frames", type=int, default=2)
+    ap.add_argument("--total-meshlets", type=int, default=0,
+                    help="strong scaling: a fixed scene of this many meshlet instances split over the GPUs (BASELINE configs[4]: 50000000)")
+    ap.add_argument("--unique-meshes", type=int, default=256,
+                    help="256 = the contract scene (bounds L2-resident); 65536 makes bounds / vertex data stream from HBM")
+    ap.add_argument("--parity-frames", type=int, default=3, help="N>1: frames of the pre-timing check N GPUs == 1 GPU (0 = skip)")
     return ap.parse_args()
 
 
@@ -197,7 +202,7 @@ def run_reference(args):
     from oxylus_b200 import synth
 
     cores = os.cpu_count() or 1
-    scene = synth.make_scene(args.meshlets * max(1, args.gpus), config_index=2, width=args.width, height=args.height)
+    scene = make_bench_scene(args, max(1, args.gpus))
     # bounded sample: every step is one full frame of the same scene on all host threads
     for _ in range(max(0, min(args.warmup, 1))):
         cpu_frames(scene, 1, cores)
@@ -206,7 +211,8 @@ def run_reference(args):
     value = scene.max_meshlet_instance_count / sec
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": n, "warmup": min(args.warmup, 1),
-        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "steps_requested": args.steps, "steps_note": "the CPU arm is capped at 4 timed frames / 1 warm-up frame (~0.1 s per frame)",
+        "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong" if args.total_meshlets else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, scene),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": f"{n} full frames of the {scene.max_meshlet_instance_count}-meshlet scene, oracle port, pthreads"},
@@ -216,12 +222,30 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def make_bench_scene(args, world):
+    """The scene both arms run: configs[1] per GPU (weak scaling; instances shrunk by world^-1/2 so the screen coverage and
+    with it the per-GPU share of visible work stays what one GPU sees), or a fixed scene (--total-meshlets, strong scaling)."""
+    from oxylus_b200 import synth
+
+    if args.total_meshlets:
+        return synth.make_scene(args.total_meshlets, config_index=2, width=args.width, height=args.height, n_unique_meshes=args.unique_meshes)
+    return synth.make_scene(args.meshlets * world, config_index=2, width=args.width, height=args.height, n_unique_meshes=args.unique_meshes,
+                            instance_scale=float(world) ** -0.5)
+
+
 def workload_config(args, scene):
-    return {"workload": "BASELINE.json configs[1]: 1M meshlet instances per GPU, 1 camera, two-pass Hi-Z occlusion cull + vis-buffer raster",
-            "meshlet_instances_per_gpu": args.meshlets, "resolution": [args.width, args.height],
+    world = max(1, args.gpus)
+    if args.total_meshlets:
+        wl = (f"BASELINE.json configs[4] shape: {args.total_meshlets} meshlet instances, instance-sharded over {world} GPU(s), "
+              "two-pass Hi-Z occlusion cull + vis-buffer raster, NCCL survivor allgather + vis-buffer max-reduce")
+    else:
+        wl = "BASELINE.json configs[1]: 1M meshlet instances per GPU, 1 camera, two-pass Hi-Z occlusion cull + vis-buffer raster"
+    return {"workload": wl,
+            "meshlet_instances_per_gpu": scene.max_meshlet_instance_count // world, "resolution": [args.width, args.height],
             "hiz": list(scene.hiz_extent()), "mesh_instances": scene.mesh_instance_count, "unique_meshes": len(scene.meshes),
+            "instance_scale": (1.0 if args.total_meshlets else float(world) ** -0.5),
             "l2": "flushed between timed steps (256 MiB write, untimed)", "cameras": "yaw 0 / 2 deg alternating, steady-state mask",
-            "parallelism": f"mesh-instance shards x{args.gpus}" if args.gpus > 1 else "single GPU"}
+            "parallelism": f"mesh-instance shards x{world}" if world > 1 else "single GPU"}
 
 
 def main():
@@ -243,184 +267,178 @@ def main():
     torch.cuda.set_device(local_rank)
     if multi:
         # NCCL_DEBUG is left exactly as the launcher set it (the driver reads the communicator banner for its rank proof);
-        # the JSON line is the last line rank 0 prints
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        # the JSON line is the last line rank 0 prints.  torch.distributed is plumbing here (id broadcast, timing reductions):
+        # the data path is the product's own communicator + NVLink peer memory (oxc_mgpu_*).
+        # gloo, not nccl: a second NCCL communicator in the process (torch's) interleaving with the product's own on other
+        # streams is a documented deadlock hazard; barriers / timing reductions are host-side anyway
+        dist.init_process_group("gloo")
     n_gpus = world
+    args.gpus = world
     capi.load(build_if_missing=False)
 
     # ---------------- scene ----------------
-    total_meshlets = args.meshlets * n_gpus
-    scene = synth.make_scene(total_meshlets, config_index=2, width=args.width, height=args.height)
-    shard = None
+    scene = make_bench_scene(args, world)
+    wide_ids = scene.max_meshlet_instance_count > (1 << 24)
+    shard, mg, cap = None, None, None
     if multi:
-        parts = oxdist.partition_mesh_instances(oxdist.lod0_counts_of(scene), world)
+        lod0 = oxdist.lod0_counts_of(scene)
+        parts = oxdist.partition_mesh_instances(lod0, world)
         shard = parts[rank]
-    pipe = pipeline.VisibilityPipeline(scene, device=local_rank, shard=shard, auto_id_base=True)
+        cap = max(1, max(int(lod0[f:f + c].sum()) for f, c in parts))
+        uid = [capi.Context.mgpu_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        # survivor gather segments: half a shard is ample for this scene (~1/3 visible); exceeding it is a hard error
+        # (OXC_STATUS_SURVIVOR_OVERFLOW, checked below), never a silent truncation
+        mg = dict(rank=rank, world=world, unique_id=uid[0], survivor_capacity=max(1024, cap // 2))
+    pipe = pipeline.VisibilityPipeline(scene, device=local_rank, shard=shard, auto_id_base=True, shard_capacity=cap, mgpu=mg, wide_ids=wide_ids)
     cams = [scene.camera(0.0), scene.camera(2.0)]
     dev = pipe.device
     w, h = scene.width, scene.height
 
-    # multi-GPU exchange state
-    hooks, gathered = {}, {}
-    if multi:
-        lod0 = oxdist.lod0_counts_of(scene)
-        cap = max(int(lod0[f:f + c].sum()) for f, c in parts)
-        out = pipe.ctx.out
-        # zero-copy torch views of the context's device buffers (no staging copies in the exchange)
-        vis_view = pipeline.wrap_device(out.visibility, 3, torch.int32, dev)            # total / early / late
-        # survivor allgather: fixed-capacity segments (NCCL has no allgatherv).  Half a shard is ample for this scene
-        # (~30 % visible); an overflow is detected from the gathered counts after the run and reported.
-        gcap = max(1024, cap // 2)
-        ids_view = pipeline.wrap_device(out.visible_meshlet_instances_indices, gcap, torch.int32, dev)
-        vis_all = torch.zeros(world * 3, dtype=torch.int32, device=dev)
-        ids_all = torch.zeros(world * gcap, dtype=torch.int32, device=dev)
-
-        after_cull_meshes = None  # global id base: computed locally by oxc_cull_meshes (oxc_set_shard_auto), no exchange
-
-        hw_, hh_ = scene.hiz_extent()
-        mip0_view = pipeline.wrap_device(out.hiz, hw_ * hh_, torch.int32, dev)  # level 0 starts at offset 0
-
-        def between_passes():
-            dist.all_reduce(mip0_view, op=dist.ReduceOp.MAX)  # depths are >= +0: int32 order == float order
-
-        def after_frame():
-            oxdist.reduce_visbuffer(pipe.vis64)               # per-pixel max of the packed depth|id image (NVLS all-reduce)
-            dist.all_gather_into_tensor(vis_all, vis_view)   # early / late counts of every rank
-            dist.all_gather_into_tensor(ids_all, ids_view)   # survivor ids (global), fixed-capacity segments
-            gathered["last"] = (ids_all, vis_all)
-
-        hooks = dict(after_cull_meshes=after_cull_meshes, between_passes=between_passes, after_frame=after_frame)
-
     def barrier():
+        torch.cuda.synchronize()
         if multi:
             dist.barrier()
         torch.cuda.synchronize()
 
+    _dbg_on = bool(os.environ.get("OXC_BENCH_DEBUG"))
+
+    def dbg(*a):
+        if _dbg_on:
+            print(f"[bench r{rank} {time.perf_counter():.2f}]", *a, file=sys.stderr, flush=True)
+
+    dbg("pipeline ready", "peer hiz" if (multi and pipe.mgpu.hiz_over_peer_memory) else "")
+    # ---------------- N > 1: N GPUs == 1 GPU, bit for bit, before anything is timed ----------------
+    parity = None
+    if multi and args.parity_frames > 0:
+        barrier()
+        for f in range(args.parity_frames):
+            pipe.select_buffer(0)
+            pipe.frame(cams[f % 2])
+            pipe.exchange_frame(slot=0)
+        torch.cuda.synchronize()
+        pipe.ctx.check_status()
+        if rank == 0:
+            cnt_g, ids_g = pipe.ctx.mgpu_gathered(0)
+            ref = pipeline.VisibilityPipeline(scene, device=local_rank, wide_ids=wide_ids)
+            for f in range(args.parity_frames):
+                ref.frame(cams[f % 2])
+            torch.cuda.synchronize()
+            rc = ref.counters()
+            r_ids = ref.ctx.visible_indices(rc["early"] + rc["late"])
+            parity = {"image": bool(torch.equal(pipe.vis64, ref.vis64)),
+                      "survivor_ids": bool(np.array_equal(np.sort(np.concatenate(ids_g)), np.sort(r_ids))),
+                      "counts": bool(int(cnt_g[:, 0].sum()) == rc["total"] and int(cnt_g[:, 1].sum()) == rc["early"] and int(cnt_g[:, 2].sum()) == rc["late"]),
+                      "hiz": bool(np.array_equal(np.concatenate([l.ravel() for l in pipe.ctx.hiz_levels()]).view(np.uint32),
+                                                 np.concatenate([l.ravel() for l in ref.ctx.hiz_levels()]).view(np.uint32))),
+                      "frames": args.parity_frames}
+            parity["pass"] = all(parity[k] for k in ("image", "survivor_ids", "counts", "hiz"))
+            ref.close()
+            del ref
+            torch.cuda.empty_cache()
+        barrier()
+
+    dbg("parity check done", parity)
     # ---------------- warm-up (also brings the visibility mask to steady state) ----------------
     W = max(4, args.warmup)  # >= 4 so the persistent visibility mask reaches its steady state
     K = max(1, args.steps)
     sampler = ClockSampler(local_rank)  # samples span warm-up + timed region + per-kernel loop (all GPU-busy)
     sampler.start()
     for i in range(W):
-        pipe.frame(cams[i % 2], **hooks)
+        pipe.select_buffer(i & 1)
+        pipe.frame(cams[i % 2])
+        if multi:
+            pipe.exchange_frame(slot=i & 1)
     torch.cuda.synchronize()
 
-    # ---------------- CUDA graphs of one frame per camera ----------------
+    dbg("warm-up done")
+    # ---------------- CUDA graphs: one whole frame per camera / buffer ----------------
+    # N > 1: the Hi-Z exchange is the product's own kernels over peer memory, so the WHOLE frame (both passes, the exchange in
+    # between and the staging of the survivor list) is one graph; only the trailing NCCL calls stay outside (side stream).
     graphs = None
-    if not args.no_graph and not multi:  # N > 1 launches eagerly: capturing the NCCL exchange steps hung in testing
+    if not args.no_graph:
         try:
             graphs = []
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                pipe.use_torch_stream()
-                for cam in cams:
+                for b, cam in enumerate(cams):
+                    pipe.select_buffer(b)  # camera index == buffer index: both alternate every step
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g, stream=side):
                         pipe.use_torch_stream()
-                        pipe.frame(cam, **hooks)  # N > 1: the NCCL exchange steps are captured with the kernels
+                        pipe.frame(cam)
+                        if multi:
+                            pipe.ctx.mgpu_stage_survivors(b)
                     graphs.append(g)
             torch.cuda.current_stream().wait_stream(side)
             pipe.use_torch_stream()
-            for i in range(2):
-                graphs[i % 2].replay()
+            pipe.select_buffer(0)
             torch.cuda.synchronize()
-        except Exception as e:  # capture of the collectives unsupported: launch eagerly (still correct, more launch gaps)
+            if multi:
+                barrier()
+            if not multi:
+                for i in range(2):
+                    graphs[i % 2].replay()
+                torch.cuda.synchronize()
+        except Exception as e:
             sys.stderr.write(f"[bench] CUDA graph capture failed ({e!r}); timing eager launches\n")
             graphs = None
             pipe.use_torch_stream()
-            torch.cuda.synchronize()
-
-    # N > 1: the two halves of the frame around the Hi-Z exchange are captured as CUDA graphs; the NCCL collectives are
-    # launched between / after them (capturing the collectives themselves hung in testing)
-    half_graphs = None
-    if multi and not args.no_graph:
-        try:
-            half_graphs = []
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for b, cam in enumerate(cams):
-                    pipe.select_buffer(b)  # camera index == buffer index: both alternate every step
-                    pair = []
-                    for part in (pipe.frame_before_exchange, pipe.frame_after_exchange):
-                        g = torch.cuda.CUDAGraph()
-                        with torch.cuda.graph(g, stream=side):
-                            pipe.use_torch_stream()
-                            part(cam)
-                        pair.append(g)
-                    half_graphs.append(pair)
-            torch.cuda.current_stream().wait_stream(side)
-            pipe.use_torch_stream()
-            pipe.select_buffer(0)
-            torch.cuda.synchronize()
-        except Exception as e:
-            sys.stderr.write(f"[bench] half-frame graph capture failed ({e!r}); timing eager launches\n")
-            half_graphs = None
-            pipe.use_torch_stream()
             pipe.select_buffer(0)
             torch.cuda.synchronize()
 
-    # N > 1: trailing exchange (vis-buffer max-reduce, survivor allgather) on a side stream with its own communicator and
-    # double-buffered vis / survivor staging, so it overlaps the next frame; buffer b is reused two frames later, after
-    # its exchange has completed (event wait on the main stream)
+    # N > 1: trailing exchange (vis-buffer max-reduce, survivor allgather) on a side stream, double-buffered (vis buffer b and
+    # gather slot b), so it overlaps the next frame; buffer b is reused two frames later, after its exchange has completed
     overlap = None
     if multi and not args.no_overlap:
-        overlap = dict(pg=dist.new_group(), cs=torch.cuda.Stream(),
-                       ids_stage=[torch.zeros(gcap, dtype=torch.int32, device=dev) for _ in range(2)],
-                       cnt_stage=[torch.zeros(3, dtype=torch.int32, device=dev) for _ in range(2)],
-                       ids_all=[torch.zeros(world * gcap, dtype=torch.int32, device=dev) for _ in range(2)],
-                       cnt_all=[torch.zeros(world * 3, dtype=torch.int32, device=dev) for _ in range(2)],
-                       frame_done=[torch.cuda.Event() for _ in range(2)], tail_done=[torch.cuda.Event() for _ in range(2)],
-                       pending=[False, False])
+        overlap = dict(cs=torch.cuda.Stream(), frame_done=[torch.cuda.Event() for _ in range(2)],
+                       tail_done=[torch.cuda.Event() for _ in range(2)], pending=[False, False])
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
-    def step_overlapped(i):
-        b = i & 1
-        o = overlap
-        main = torch.cuda.current_stream()
-        if o["pending"][b]:
-            main.wait_event(o["tail_done"][b])  # the exchange that last used buffer b (two frames ago) has finished
+    def run_frame(b, mark=None):
         pipe.select_buffer(b)
-        if half_graphs is not None:
-            half_graphs[b][0].replay()
-            hooks["between_passes"]()
-            half_graphs[b][1].replay()
+        if graphs is not None and mark is None:
+            graphs[b].replay()
         else:
-            pipe.frame(cams[b], between_passes=hooks["between_passes"])
-        o["ids_stage"][b].copy_(ids_view)   # the context's survivor list / counters are overwritten by the next frame
-        o["cnt_stage"][b].copy_(vis_view)
-        o["frame_done"][b].record(main)
-        o["cs"].wait_event(o["frame_done"][b])
-        with torch.cuda.stream(o["cs"]):
-            dist.all_reduce(pipe.vis64_bufs[b], op=dist.ReduceOp.MAX, group=o["pg"])
-            dist.all_gather_into_tensor(o["cnt_all"][b], o["cnt_stage"][b], group=o["pg"])
-            dist.all_gather_into_tensor(o["ids_all"][b], o["ids_stage"][b], group=o["pg"])
-            o["tail_done"][b].record(o["cs"])
-        o["pending"][b] = True
+            pipe.frame(cams[b], mark=mark)
+            if multi:
+                pipe.ctx.mgpu_stage_survivors(b)
 
     def step(i, mark=None):
-        if graphs is not None and mark is None:
-            graphs[i % 2].replay()
-        elif overlap is not None and mark is None:
-            step_overlapped(i)
-        elif half_graphs is not None and mark is None:
-            pipe.select_buffer(i & 1)
-            half_graphs[i % 2][0].replay()
-            hooks["between_passes"]()
-            half_graphs[i % 2][1].replay()
-            hooks["after_frame"]()
+        b = i & 1
+        if not multi:
+            return run_frame(b, mark)
+        main = torch.cuda.current_stream()
+        if overlap is not None and mark is None:
+            o = overlap
+            if o["pending"][b]:
+                main.wait_event(o["tail_done"][b])  # the exchange that last used buffer / slot b (two frames ago) has finished
+            run_frame(b)
+            o["frame_done"][b].record(main)
+            o["cs"].wait_event(o["frame_done"][b])
+            pipe.exchange_frame(slot=b, stream=o["cs"], already_staged=True, vis=pipe.vis64_bufs[b])
+            o["tail_done"][b].record(o["cs"])
+            o["pending"][b] = True
         else:
-            pipe.select_buffer(0)
-            pipe.frame(cams[i % 2], mark=mark, **hooks)
+            run_frame(b, mark)
+            pipe.exchange_frame(slot=b, already_staged=True, vis=pipe.vis64_bufs[b])
+            if mark:
+                mark("exchange")
 
-    if overlap is not None:  # warm the second communicator / side stream outside the timed region
+    def drain():
+        if overlap is not None:
+            torch.cuda.current_stream().wait_stream(overlap["cs"])
+
+    dbg("graphs", graphs is not None)
+    if overlap is not None:  # warm the side stream outside the timed region
         for i in range(4):
-            step_overlapped(i)
-        torch.cuda.current_stream().wait_stream(overlap["cs"])
+            step(i)
+        drain()
         torch.cuda.synchronize()
 
+    dbg("overlap warm-up done")
     # ---------------- timed region: exactly K steps ----------------
     launches0 = capi.kernel_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -430,21 +448,22 @@ def main():
         flush.fill_(i & 0xFF)  # L2 flush, outside the per-step event pair
         ev[i][0].record()
         step(i)
-        if overlap is not None and i == K - 1:
-            torch.cuda.current_stream().wait_stream(overlap["cs"])  # the last steps' exchanges are inside the timed region
+        if i == K - 1:
+            drain()  # the last steps' exchanges are inside the timed region
         ev[i][1].record()
     barrier()
     t_wall = time.perf_counter() - t_wall0
     step_ms = [a.elapsed_time(b) for a, b in ev]
     ms_per_step = float(np.mean(step_ms))
-    if graphs is not None:
-        launches_per_step = None  # replayed nodes are counted below from an eager frame
-    launches_timed = capi.kernel_launch_count() - launches0
     cnt = pipe.counters()
+    if multi:
+        pipe.ctx.check_status()  # survivor-gather overflow / peer time-out are errors, not footnotes
 
+    dbg("timed region done", ms_per_step)
     # ---------------- per-kernel durations (same steps, eager launches, one CUDA event after every stage) ----------------
-    stage_names = ["begin"] + pipeline.STAGES
-    stage_acc = {n: [] for n in pipeline.STAGES}
+    stage_list = pipeline.STAGES + (["exchange"] if multi else [])
+    stage_names = ["begin"] + stage_list
+    stage_acc = {n: [] for n in stage_list}
     stage_acc["clear"] = []
     l0 = capi.kernel_launch_count()
     for i in range(K):
@@ -464,31 +483,40 @@ def main():
         for a, b in zip(stage_names[:-1], stage_names[1:]):
             stage_acc[b].append(marks[a].elapsed_time(marks[b]))
     launches_per_frame = (capi.kernel_launch_count() - l0) // K
+    cnt_stage = pipe.counters()  # counters of the last frame of the per-stage loop (the frame the kernel times belong to)
     # keep the GPU busy with the same steps until the sampler has a few readings, then stop it
-    t_busy = time.perf_counter()
-    while len(sampler.samples) < 5 and time.perf_counter() - t_busy < 2.0:
-        step(0)
+    if multi:  # every rank must run the same number of (collective) steps: a fixed count, not a clock-driven loop
+        for i in range(64):
+            step(i)
+        drain()
         torch.cuda.synchronize()
+    else:
+        t_busy = time.perf_counter()
+        while len(sampler.samples) < 5 and time.perf_counter() - t_busy < 2.0:
+            step(0)
+            torch.cuda.synchronize()
     clocks = sampler.stop()
     stages_ms = {k: float(np.mean(v)) for k, v in stage_acc.items()}
-    cnt_late = pipe.counters()
 
-    stages_all = None
+    dbg("stage loop done")
+    per_rank = None
     if multi:
         keys = sorted(stages_ms)
-        t_st = torch.tensor([stages_ms[k] for k in keys] + [cnt_late["early"] + cnt_late["late"], cnt_late["triangles"]], dtype=torch.float64, device=dev)
-        g_st = torch.empty(world * len(t_st), dtype=torch.float64, device=dev)
-        dist.all_gather_into_tensor(g_st, t_st)
-        g_st = g_st.view(world, -1).cpu().numpy()
-        stages_all = {k: [round(float(g_st[r, i]), 4) for r in range(world)] for i, k in enumerate(keys)}
-        stages_all["survivors"] = [int(g_st[r, len(keys)]) for r in range(world)]
-        stages_all["triangles"] = [int(g_st[r, len(keys) + 1]) for r in range(world)]
+        t_st = torch.tensor([stages_ms[k] for k in keys] + [cnt_stage["total"], cnt_stage["early"] + cnt_stage["late"], cnt_stage["triangles"]],
+                            dtype=torch.float64, device=dev)
+        parts_st = [torch.empty(len(t_st), dtype=torch.float64) for _ in range(world)]
+        dist.all_gather(parts_st, t_st.cpu())
+        g_st = torch.stack(parts_st).numpy()
+        per_rank = {"stages_ms": {k: [round(float(g_st[r, i]), 4) for r in range(world)] for i, k in enumerate(keys)},
+                    "meshlet_instances": [int(g_st[r, len(keys)]) for r in range(world)],
+                    "survivors": [int(g_st[r, len(keys) + 1]) for r in range(world)],
+                    "triangles": [int(g_st[r, len(keys) + 2]) for r in range(world)]}
     # max over ranks
     if multi:
-        t = torch.tensor([ms_per_step], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms_per_step], dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_per_step = float(t.item())
-        tot = torch.tensor([cnt["total"], cnt["triangles"]], dtype=torch.float64, device=dev)
+        tot = torch.tensor([cnt["total"], cnt["triangles"]], dtype=torch.float64)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
         job_meshlets, job_tris = float(tot[0].item()), float(tot[1].item())
     else:
@@ -497,39 +525,49 @@ def main():
 
     # ---------------- roofline of the dominant cull kernel (late pass: every meshlet instance fully tested) ----------------
     peak, peak_src = measured_peak_hbm()
-    N_local = cnt_late["total"]
+    N_local = cnt_stage["total"]
     I_local = shard[1] if shard else scene.mesh_instance_count
-    M_bits = scene.max_meshlet_instance_count
-    S_late = cnt_late["late"]
-    algo_bytes = N_local * 24 + 2 * 4 * ((M_bits + 31) // 32) + 4 * S_late + I_local * 84 + len(scene.meshes) * 128
+    M_bits = scene.max_meshlet_instance_count // world  # mask words this rank's meshlets touch
+    S_late = cnt_stage["late"]
+    U = len(scene.meshes)
+    # SURVEY 8d (the contract's formula: the reference's 8 B/meshlet id stream + 16 B bounds, reference tables)
+    algo_survey = N_local * 24 + 2 * 4 * ((M_bits + 31) // 32) + 4 * S_late + I_local * 84 + U * 128
+    # what THIS kernel has to move: no id stream any more (8 B per 32 meshlets of slab table instead), 16 B bounds, mask
+    # read + write, survivors, one 272 B InstCull record per mesh instance
+    algo_kernel = N_local * 16 + ((N_local + 31) // 32) * 8 + 2 * 4 * ((M_bits + 31) // 32) + 4 * S_late + I_local * 272
     t_late = stages_ms["cull_late"] * 1e-3
-    achieved = algo_bytes / t_late / 1e9 if t_late > 0 else 0.0
-    traffic = None
+    achieved = algo_kernel / t_late / 1e9 if t_late > 0 else 0.0
+    traffic, traffic_src = None, None
     prof = os.path.join(ROOT, "profiles", "ncu_cull_late_summary.json")
     if os.path.exists(prof):
         try:
-            traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+            pj = json.load(open(prof))
+            traffic, traffic_src = pj.get("dram_bytes_per_launch"), pj.get("source", "profiles/ncu_cull_late_summary.json")
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "kernel": "k_cull_meshlets<HIZ,OCC,LATE> (late pass)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": algo_bytes, "kernel_ms": stages_ms["cull_late"],
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": f"constant from a committed ncu --set full capture ({traffic_src}), not measured in this run" if traffic else None,
+                "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo_kernel, "kernel_ms": stages_ms["cull_late"],
+                "frac_survey_8d_formula": (algo_survey / t_late / 1e9 / peak) if t_late > 0 else None,
+                "algorithmic_bytes_survey_8d_formula": algo_survey,
                 "meshlets_per_s_kernel": N_local / t_late if t_late > 0 else None,
-                "note": "algorithmic bytes = N*24 + 8*ceil(M/32) + 4*S + I*84 + U*128 (SURVEY 8d, Hi-Z bytes excluded); "
-                        "256 unique meshes => bounds are L2-resident and the kernel is issue-bound (DESIGN.md)"}
+                "late_survivors_in_timed_frame": S_late,
+                "note": "algorithmic bytes = N*16 + 8*ceil(N/32) + 8*ceil(M/32) + 4*S + I*272 (this kernel: slab table instead of the 8 B/meshlet "
+                        "id stream, one InstCull record per mesh instance); frac_survey_8d_formula uses SURVEY 8d's N*24 + ... for comparison with "
+                        f"round 1.  {U} unique meshes" + (" => bounds are L2-resident and the kernel is latency/issue-bound (DESIGN.md)" if U <= 1024 else " => bounds stream from HBM")}
 
-    # the other kernels of the step against the same HBM roofline (SURVEY 8d byte formulas; 64 triangles / 49 vertices
-    # per meshlet in the synthetic meshes): the step is dominated by the raster, which is instruction-bound like the cull
     def _k(name, algo, ms):
         return {"kernel": name, "algorithmic_bytes": int(algo), "ms": ms, "achieved_gbs": algo / (ms * 1e-3) / 1e9 if ms > 0 else None,
                 "frac": algo / (ms * 1e-3) / 1e9 / peak if ms > 0 else None}
     per_meshlet = 16 + 3 * 64 + 4 * 49 + 8 * 49          # Meshlet + micro indices + vertex indices + positions
     hw_, hh_ = scene.hiz_extent()
     roofline["other_kernels"] = [] if any(k not in stages_ms for k in ("cull_early", "raster_early", "hiz", "raster_late")) else [
-        _k("k_cull_meshlets<HIZ,OCC,EARLY,ZERO>", N_local * 24 + 2 * 4 * ((M_bits + 31) // 32) + 4 * cnt_late["early"] + I_local * 84, stages_ms["cull_early"]),
-        _k("k_raster_visbuffer (early)", cnt_late["early"] * per_meshlet + 8 * w * h, stages_ms["raster_early"]),
-        _k("k_hiz_tiles + k_hiz_tail", 4 * hw_ * hh_ + 4 * (4 * hw_ * hh_) // 3, stages_ms["hiz"]),
-        _k("k_raster_visbuffer (late)", cnt_late["late"] * per_meshlet, stages_ms["raster_late"]),
+        _k("k_cull_meshlets<HIZ,OCC,EARLY,ZERO>", ((N_local + 31) // 32) * 8 + 2 * 4 * ((M_bits + 31) // 32) + cnt_stage["early"] * 20 + I_local * 272, stages_ms["cull_early"]),
+        _k("k_raster_visbuffer (early)", cnt_stage["early"] * per_meshlet + 8 * w * h, stages_ms["raster_early"]),
+        _k("k_hiz_tiles + k_hiz_tail" + (" + peer exchange" if multi else ""), 4 * hw_ * hh_ + 4 * (4 * hw_ * hh_) // 3, stages_ms["hiz"]),
+        _k("k_raster_visbuffer (late)", cnt_stage["late"] * per_meshlet, stages_ms["raster_late"]),
     ]
 
     # ---------------- e2e through the reference-facing host API with HOST buffers ----------------
@@ -543,11 +581,14 @@ def main():
         xf_pinned = pin((len(scene.transforms), 16), torch.float32)
         xf_pinned[...] = scene.transforms["world"]
         # per-frame HOST outputs = the integer results of the path: the R32UI vis image, the survivor ids and the counters.
-        # The D32F depth attachment only feeds GPU passes (Hi-Z, shading) and stays device-resident, as in the engine.
-        outbufs = [dict(vis32=pin((h, w), torch.int32).view(np.uint32),
-                        idx=pin((max(1, scene.max_meshlet_instance_count),), torch.int32).view(np.uint32)) for _ in range(2)]
+        # The D32F depth attachment only feeds GPU passes (Hi-Z, shading) and stays device-resident, as in the engine;
+        # e2e_with_depth reads it back as well.
+        def outbufs_for(with_depth):
+            return [dict(vis32=pin((h, w), torch.int32).view(np.uint32),
+                         idx=pin((max(1, scene.max_meshlet_instance_count),), torch.int32).view(np.uint32),
+                         **({"depth": pin((h, w), torch.float32)} if with_depth else {})) for _ in range(2)]
 
-        def e2e_steps(n):
+        def e2e_steps(n, outbufs):
             """n pipelined frames: frame i's device->host copies overlap frame i+1's kernels (oxr_submit / oxr_wait);
             every frame still pays its own H2D (camera, transforms) and D2H (vis32, survivor ids, counters)."""
             prev, res_ = None, None
@@ -559,20 +600,26 @@ def main():
                 prev = t
             return r.wait(prev)
 
-        e2e_steps(W)
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        res = e2e_steps(K)
-        torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / K
+        def e2e_measure(with_depth):
+            ob = outbufs_for(with_depth)
+            e2e_steps(W, ob)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            res = e2e_steps(K, ob)
+            torch.cuda.synchronize()
+            sec = (time.perf_counter() - t0) / K
+            d2h = ob[0]["vis32"].nbytes + ob[0]["idx"].nbytes + 12 + 8 + 8 + (ob[0]["depth"].nbytes if with_depth else 0)
+            return res, sec, d2h
+
+        res, e2e_s, d2h = e2e_measure(False)
         h2d = 96 + xf_pinned.nbytes
-        d2h = outbufs[0]["vis32"].nbytes + outbufs[0]["idx"].nbytes + 12 + 8 + 8
         e2e = {"value": res["total"] / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": e2e_s * 1e3, "api": "oxr_update_transforms + oxr_submit / oxr_wait (C++ ox::RendererInstance mirror over the C ABI), pinned host buffers, "
                       "2 frames in flight; H2D camera + all transforms, D2H vis32 image + survivor ids + counters (depth stays on the device)"}
+        res_d, e2e_d_s, d2h_d = e2e_measure(True)
+        e2e["e2e_with_depth"] = {"value": res_d["total"] / e2e_d_s, "ms_per_step": e2e_d_s * 1e3, "d2h_bytes_per_step": int(d2h_d),
+                                 "note": "same, plus the D32F depth attachment read back every frame"}
         r.close()
-    elif multi:
-        e2e = None
 
     # ---------------- CPU baseline (rank 0, N = 1 only) ----------------
     cpu_baseline = None
@@ -585,37 +632,13 @@ def main():
                         "triangles_per_s": last["triangles"] / sec,
                         "frustum_cull_draw_list_loops": cpu_frustum_loops(scene, cams[0], cores)}
 
-    overlap_check = None
-    if overlap is not None:
-        # the overlapped steps must deliver what the serial exchange delivers: replay the same 4-frame sequence from a
-        # zeroed visibility mask through both paths and compare counts, survivor sets and the reduced image
-        torch.cuda.current_stream().wait_stream(overlap["cs"])
-        torch.cuda.synchronize()
-        pipe.ctx.reset_visibility_mask()
-        for i in range(4):
-            step_overlapped(i)
-        torch.cuda.current_stream().wait_stream(overlap["cs"])
-        torch.cuda.synchronize()
-        img_o = pipe.vis64_bufs[1].clone()
-        cnt_o = overlap["cnt_all"][1].view(world, 3).cpu().numpy()
-        ids_o = overlap["ids_all"][1].view(world, gcap).cpu().numpy()
-        pipe.ctx.reset_visibility_mask()
-        pipe.select_buffer(0)
-        for i in range(4):
-            pipe.frame(cams[i % 2], **hooks)
-        torch.cuda.synchronize()
-        cnt_s = vis_all.view(world, 3).cpu().numpy()
-        ids_s = ids_all.view(world, gcap).cpu().numpy()
-        same_ids = all(np.array_equal(np.sort(ids_o[r, : cnt_o[r, 1] + cnt_o[r, 2]]), np.sort(ids_s[r, : cnt_s[r, 1] + cnt_s[r, 2]])) for r in range(world))
-        overlap_check = bool(np.array_equal(cnt_o, cnt_s) and same_ids and torch.equal(img_o, pipe.vis64))
-
+    dbg("reductions done")
     exchange = None
     if multi:
         def time_op(fn, n=10):
             for _ in range(2):
                 fn()
-            torch.cuda.synchronize()
-            dist.barrier()
+            barrier()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             for _ in range(n):
@@ -624,25 +647,31 @@ def main():
             torch.cuda.synchronize()
             return a.elapsed_time(b) / n * 1e3  # us
 
-        op_us = {"all_reduce_max_visbuffer_%dMB" % (pipe.vis64.numel() * 8 >> 20): time_op(lambda: oxdist.reduce_visbuffer(pipe.vis64)),
-                 "all_reduce_max_hiz_mip0_%dMB" % (mip0_view.numel() * 4 >> 20): time_op(lambda: dist.all_reduce(mip0_view, op=dist.ReduceOp.MAX)),
-                 "all_gather_survivor_ids_%dMB_per_rank" % (gcap * 4 >> 20): time_op(lambda: dist.all_gather_into_tensor(ids_all, ids_view)),
-                 "all_gather_counts": time_op(lambda: dist.all_gather_into_tensor(vis_all, vis_view))}
-        cnts = vis_all.view(world, 3).cpu().numpy()
-        exchange = {"survivor_gather_capacity": int(gcap), "max_survivors_per_rank": int((cnts[:, 1] + cnts[:, 2]).max()),
-                    "overflow": bool((cnts[:, 1] + cnts[:, 2]).max() > gcap), "op_us_back_to_back": op_us,
-                    "steps": "id base from a local count-only replay (no exchange); all_reduce(MAX) Hi-Z mip 0; all_reduce(MAX) vis buffer; allgather(counts); allgather(survivor ids)"}
+        info = pipe.ctx.mgpu_info()
+        pipe.select_buffer(0)
+        op_us = {"oxc_mgpu_exchange_frame (vis-buffer %d MB max-reduce + count / id allgathers, %d MB ids per rank)" % (pipe.vis64.numel() * 8 >> 20, info.survivor_capacity * 4 >> 20):
+                 time_op(lambda: pipe.exchange_frame(slot=0)),
+                 "oxc_mgpu_exchange_hiz (mip-0 push over peer memory + flag barrier + pyramid)": time_op(lambda: pipe.ctx.mgpu_exchange_hiz(pipe.vis64.data_ptr(), w, h))}
+        cnt_g, _ = pipe.ctx.mgpu_gathered(0)
+        exchange = {"survivor_gather_capacity": int(info.survivor_capacity), "max_survivors_per_rank": int((cnt_g[:, 1] + cnt_g[:, 2]).max()),
+                    "hiz_over_peer_memory": bool(info.hiz_over_peer_memory), "op_us_back_to_back": op_us,
+                    "steps": "global ids from a local count-only replay (no exchange); Hi-Z: mip-0 texels max-reduced into every peer's buffer by the "
+                             "sampling kernel over NVLink peer memory + flag barrier (inside the frame's CUDA graph); after the frame, on a side stream: "
+                             "ncclAllReduce(u64 max) of the packed vis buffer, ncclAllGather of counters and survivor ids"}
+        pipe.ctx.check_status()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if args.total_meshlets else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, scene),
             "triangles_rasterised_per_s": job_tris / (ms_per_step * 1e-3),
             "per_frame": {"meshlet_instances": job_meshlets, "early_survivors": cnt["early"], "late_survivors": cnt["late"],
                           "triangles_rasterised": job_tris},
             "stages_ms": stages_ms, "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "clocks": clocks,
             "gpu_launches": int(launches_per_frame * K), "gpu_launches_per_step": int(launches_per_frame),
-            "cuda_graph": (graphs is not None) or (half_graphs is not None), "exchange_overlapped": overlap is not None, "overlap_check": overlap_check, "wall_s_timed_region": t_wall, "exchange": exchange, "stages_ms_per_rank": stages_all,
+            "cuda_graph": graphs is not None, "exchange_overlapped": overlap is not None,
+            "parity_vs_1gpu": (parity["pass"] if parity else None), "parity_detail": parity,
+            "wall_s_timed_region": t_wall, "exchange": exchange, "per_rank": per_rank,
         }
         print(json.dumps(line), flush=True)
     pipe.close()

@@ -462,7 +462,13 @@ int oxc_mgpu_init_with_comm(OxcContext* ctx, void* nccl_comm, uint32_t survivor_
 int oxc_mgpu_shutdown(OxcContext* ctx);
 int oxc_mgpu_info(OxcContext* ctx, OxcMgpuInfo* out);
 int oxc_mgpu_exchange_hiz(OxcContext* ctx, const uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream);
-int oxc_mgpu_exchange_frame(OxcContext* ctx, uint64_t* vis_dev /* may be NULL */, uint32_t width, uint32_t height, int slot, void* stream);
+/* A host that overlaps the exchange of frame i (side stream) with frame i + 1 (main stream) copies the frame's survivor list and
+ * counters into the slot's staging buffers ON THE MAIN STREAM first (oxc_mgpu_stage_survivors: the context's own list is
+ * rewritten by the next frame's cull), then calls oxc_mgpu_exchange_frame with OXC_MGPU_ALREADY_STAGED on the side stream. */
+#define OXC_MGPU_ALREADY_STAGED 1u
+int oxc_mgpu_stage_survivors(OxcContext* ctx, int slot, void* stream);
+int oxc_mgpu_exchange_frame(OxcContext* ctx, uint64_t* vis_dev /* may be NULL */, uint32_t width, uint32_t height, int slot,
+                            uint32_t flags, void* stream);
 
 int oxc_get_outputs(OxcContext* ctx, OxcOutputs* out);
 /* Instrumentation hook: 128 u64 counters that builds with -DOXC_RASTER_STATS fill (tools/raster_stats.py); zero otherwise. */

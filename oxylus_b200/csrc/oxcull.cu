@@ -1223,7 +1223,7 @@ int oxc_mgpu_exchange_hiz(OxcContext* c, const uint64_t* vis, uint32_t w, uint32
 // End of a sharded frame: per-pixel max of the packed vis buffer over the ranks (in place), and every rank's survivor list +
 // counters gathered into the context's buffers of `slot` (0/1: a host that overlaps this exchange with the next frame on a
 // side stream alternates the slots).
-int oxc_mgpu_exchange_frame(OxcContext* c, uint64_t* vis, uint32_t w, uint32_t h, int slot, void* stream) {
+int oxc_mgpu_stage_survivors(OxcContext* c, int slot, void* stream) {
   if (!c || (slot != 0 && slot != 1)) return fail(OXC_E_INVALID, "bad argument");
   if (!c->mg.active) return fail(OXC_E_STATE, "oxc_mgpu_init first");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -1231,6 +1231,19 @@ int oxc_mgpu_exchange_frame(OxcContext* c, uint64_t* vis, uint32_t w, uint32_t h
   OxcContext::Mgpu& m = c->mg;
   k_mgpu_stage_survivors<<<c->sm_count, 256, 0, s>>>(c->d_vis, c->d_visible, m.capacity, m.cnt_stage[slot], m.ids_stage[slot], c->d_status);
   LAUNCHED();
+  return OXC_OK;
+}
+
+int oxc_mgpu_exchange_frame(OxcContext* c, uint64_t* vis, uint32_t w, uint32_t h, int slot, uint32_t flags, void* stream) {
+  if (!c || (slot != 0 && slot != 1)) return fail(OXC_E_INVALID, "bad argument");
+  if (!c->mg.active) return fail(OXC_E_STATE, "oxc_mgpu_init first");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  OxcContext::Mgpu& m = c->mg;
+  if (!(flags & OXC_MGPU_ALREADY_STAGED)) {
+    int rc = oxc_mgpu_stage_survivors(c, slot, stream);
+    if (rc != OXC_OK) return rc;
+  }
   if (m.world == 1) {
     CK(cudaMemcpyAsync(m.cnt_all[slot], m.cnt_stage[slot], 16, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(m.ids_all[slot], m.ids_stage[slot], (size_t)m.capacity * 4, cudaMemcpyDeviceToDevice, s));

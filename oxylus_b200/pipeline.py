@@ -135,10 +135,11 @@ class VisibilityPipeline:
         c.cull_meshlets(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, True)
         c.raster_visbuffer(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, v)
 
-    def exchange_frame(self, slot=0, stream=None, with_image=True):
+    def exchange_frame(self, slot=0, stream=None, with_image=True, already_staged=False, vis=None):
         """oxc_mgpu_exchange_frame: vis-buffer max-reduce (in place) + survivor allgather into the context's slot buffers."""
-        self.ctx.mgpu_exchange_frame(self.vis64.data_ptr() if with_image else None, self.w, self.h, slot,
-                                     None if stream is None else stream.cuda_stream)
+        v = self.vis64 if vis is None else vis
+        self.ctx.mgpu_exchange_frame(v.data_ptr() if with_image else None, self.w, self.h, slot,
+                                     None if stream is None else stream.cuda_stream, already_staged=already_staged)
 
     def counters(self):
         vis = self.ctx.visibility()

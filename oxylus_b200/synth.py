@@ -346,12 +346,15 @@ def make_scene(
     n_occluders: int = 32,
     placement: str = "frustum",
     seed: int = None,
+    instance_scale: float = 1.0,
 ) -> Scene:
     """Scene with exactly n_meshlets LOD0 meshlet instances (Σ over mesh instances).
 
     placement="frustum": instance centres inside the view frustum of the yaw-0 camera (every mesh
     instance intersects the frustum, so cull_meshes emits all n_meshlets with single-LOD meshes);
     placement="box": the SURVEY §8d 400x100x400 box 200 units ahead (≈45 % of instances outside).
+    instance_scale multiplies every mesh instance's uniform scale: weak-scaling runs shrink instances by world^-1/2 so
+    the screen coverage — hence the share of meshlets that survive occlusion, per GPU — stays what it is on one GPU.
     """
     seed = SEED_BASE + config_index if seed is None else seed
     lo, hi = meshlets_per_mesh
@@ -386,7 +389,7 @@ def make_scene(
     q = np.stack([uniform(seed, 30 + a, n_inst, -1.0, 1.0) for a in range(4)], axis=1)
     q /= np.maximum(np.linalg.norm(q, axis=1, keepdims=True), 1e-9)
     w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
-    s = uniform(seed, 34, n_inst, 0.5, 2.0)
+    s = uniform(seed, 34, n_inst, 0.5, 2.0) * float(instance_scale)
     rot = np.empty((n_inst, 3, 3))
     rot[:, 0, 0] = 1 - 2 * (y * y + z * z); rot[:, 0, 1] = 2 * (x * y - z * w); rot[:, 0, 2] = 2 * (x * z + y * w)
     rot[:, 1, 0] = 2 * (x * y + z * w); rot[:, 1, 1] = 1 - 2 * (x * x + z * z); rot[:, 1, 2] = 2 * (y * z - x * w)
