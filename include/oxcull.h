@@ -315,6 +315,13 @@ int oxc_build_hiz_from_mip0(OxcContext* ctx, void* stream);
  * block per surviving meshlet of this pass (early: [0,E); late: [E,E+L)).  Requires
  * alloc_reordered_indices. */
 int oxc_cull_triangles(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, void* stream);
+/* Same, with north_star's small-primitive cull switched on (the reference has none, cull_triangles.slang:59-90, so this is a
+ * separate opt-in entry point): a triangle that passed the near / backface test is additionally dropped when all three
+ * vertices project in front of the camera and its bounding box, snapped to the 24.8 raster grid of a width x height target,
+ * holds no sample centre — it cannot produce a fragment (specification: oracle/oxc_oracle.c orc_triangle_covers_no_sample).
+ * The vis buffer rendered from the shorter index buffer is identical. */
+int oxc_cull_triangles_small_primitive(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width,
+                                       uint32_t height, void* stream);
 
 /* visbuffer_clear.slang:20-28 on the packed 64-bit image (visbuffer.slang:49-79):
  * every pixel = depth 0.0 | data ~0u. */

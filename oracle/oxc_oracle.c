@@ -591,6 +591,70 @@ static void raster_triangle(const float clip[3][4], uint32_t data, uint32_t W, u
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * Small-primitive cull — north_star item; the reference has none (cull_triangles.slang:59-90), so it is OPT-IN and
+ * specified here: a triangle that passed cull_triangles' test is additionally culled iff all three vertices snap
+ * (raster spec steps 2-3: w > 0, |fx|, |fy| <= 2^22) and the snapped bounding box holds no sample centre
+ * (px1 < px0 or py1 < py0 after clamping to the image, exactly the bounds raster_triangle loops over).  Such a triangle
+ * produces no fragment, so the vis buffer is unchanged; only the index buffer / the triangle count shrink.
+ * ---------------------------------------------------------------------------------------------- */
+int orc_triangle_covers_no_sample(const float clip[3][4], uint32_t W, uint32_t H) {
+  int64_t fx[3], fy[3];
+  for (int i = 0; i < 3; i++) {
+    if (!(clip[i][3] > 0.0f)) return 0;
+    float rw = 1.0f / clip[i][3];
+    float nx = clip[i][0] * rw, ny = clip[i][1] * rw;
+    float sx = (nx * 0.5f + 0.5f) * (float)W, sy = (ny * 0.5f + 0.5f) * (float)H;
+    float qx = floorf(sx * 256.0f + 0.5f), qy = floorf(sy * 256.0f + 0.5f);
+    if (!(fabsf(qx) <= 4194304.0f && fabsf(qy) <= 4194304.0f)) return 0;
+    fx[i] = (int64_t)qx;
+    fy[i] = (int64_t)qy;
+  }
+  int64_t minx = fx[0] < fx[1] ? (fx[0] < fx[2] ? fx[0] : fx[2]) : (fx[1] < fx[2] ? fx[1] : fx[2]);
+  int64_t maxx = fx[0] > fx[1] ? (fx[0] > fx[2] ? fx[0] : fx[2]) : (fx[1] > fx[2] ? fx[1] : fx[2]);
+  int64_t miny = fy[0] < fy[1] ? (fy[0] < fy[2] ? fy[0] : fy[2]) : (fy[1] < fy[2] ? fy[1] : fy[2]);
+  int64_t maxy = fy[0] > fy[1] ? (fy[0] > fy[2] ? fy[0] : fy[2]) : (fy[1] > fy[2] ? fy[1] : fy[2]);
+  int64_t px0 = (minx - 128 + 255) >> 8, px1 = (maxx - 128) >> 8;
+  int64_t py0 = (miny - 128 + 255) >> 8, py1 = (maxy - 128) >> 8;
+  if (px0 < 0) px0 = 0;
+  if (py0 < 0) py0 = 0;
+  if (px1 > (int64_t)W - 1) px1 = (int64_t)W - 1;
+  if (py1 > (int64_t)H - 1) py1 = (int64_t)H - 1;
+  return px1 < px0 || py1 < py0;
+}
+
+/* cull_triangles with the opt-in small-primitive cull: same outputs as orc_cull_triangles minus the culled triangles;
+ * returns how many were culled */
+uint64_t orc_cull_triangles_small_primitive(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                                            const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
+                                            const OxcCullCamera* cam, uint32_t id_base, uint32_t W, uint32_t H,
+                                            uint32_t* reordered_indices, OxcDrawIndexedIndirectCommand* draw_cmd) {
+  uint64_t culled = 0;
+  draw_cmd->index_count = 0; draw_cmd->instance_count = 1; draw_cmd->first_index = 0;
+  draw_cmd->vertex_offset = 0; draw_cmd->first_instance = 0;
+  for (uint32_t g = 0; g < pass_count; g++) {
+    uint32_t mii = visible_indices[pass_first + g];
+    TriMeshlet t;
+    fetch_tri_meshlet(scene, meshlet_instances, mii, cam, &t);
+    for (uint32_t tri = 0; tri < t.meshlet.triangle_count && tri < 64; tri++) {
+      float clip[3][4];
+      tri_clip(scene, &t, tri, clip);
+      if (!tri_passes(clip)) continue;
+      if (orc_triangle_covers_no_sample(clip, W, H)) { culled++; continue; }
+      if (reordered_indices) {
+        uint32_t off = draw_cmd->index_count;
+        uint32_t masked = (mii + id_base) << OXC_VIS_PRIMITIVE_BITS;
+        uint32_t ti = tri * 3;
+        reordered_indices[off + 0] = masked | ((ti + 0) & OXC_VIS_PRIMITIVE_MASK);
+        reordered_indices[off + 1] = masked | ((ti + 1) & OXC_VIS_PRIMITIVE_MASK);
+        reordered_indices[off + 2] = masked | ((ti + 2) & OXC_VIS_PRIMITIVE_MASK);
+      }
+      draw_cmd->index_count += 3;
+    }
+  }
+  return culled;
+}
+
+/* ------------------------------------------------------------------------------------------------
  * Clipped raster (SPECIFICATION ONLY — the CUDA raster does not implement it yet).
  * The plain spec drops a triangle when a vertex has w <= 0 or a snapped coordinate exceeds 2^22 (steps 2-3); a hardware
  * rasteriser clips such triangles instead (DrawGeometry.cpp:104-190 relies on it: geometry around the camera).  Only those

@@ -109,6 +109,14 @@ void orc_cull_triangles(const OrcScene* scene, const OxcMeshletInstance* meshlet
 /* SW raster (spec in DESIGN.md §raster): same triangle cull, then rasterise with
  * max on asuint(depth)<<32 | (id<<8 | tri).  vis must be pre-cleared (orc_clear_visbuffer). */
 void orc_clear_visbuffer(uint64_t* vis, uint32_t width, uint32_t height);
+/* north_star's small-primitive cull (opt-in; no reference equivalent): specification in oxc_oracle.c */
+int orc_triangle_covers_no_sample(const float clip[3][4], uint32_t width, uint32_t height);
+uint64_t orc_cull_triangles_small_primitive(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                                            const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
+                                            const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height,
+                                            uint32_t* reordered_indices /* may be NULL: count only */,
+                                            OxcDrawIndexedIndirectCommand* draw_cmd);
+
 void orc_raster_visbuffer(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
                           const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
                           const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height,

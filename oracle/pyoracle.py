@@ -148,6 +148,17 @@ def cull_triangles(hs, mi, visible, first, count, cam, id_base=0):
     return out[: int(cmd["index_count"][0])], cmd
 
 
+def cull_triangles_small_primitive(hs, mi, visible, first, count, cam, w, h, id_base=0):
+    """(index buffer, draw cmd, number of triangles the opt-in small-primitive cull removed)"""
+    out = np.zeros(max(1, count) * 64 * 3, dtype=np.uint32)
+    cmd = np.zeros(1, dtype=abi.DRAW_CMD_DT)
+    fn = lib().orc_cull_triangles_small_primitive
+    fn.restype = C.c_uint64
+    culled = fn(hs.ref, _p(mi), _p(visible), C.c_uint32(first), C.c_uint32(count), _p(cam), C.c_uint32(id_base), C.c_uint32(w), C.c_uint32(h),
+                _p(out), _p(cmd))
+    return out[: int(cmd["index_count"][0])], cmd, int(culled)
+
+
 def clear_visbuffer(w, h):
     vis = np.zeros((h, w), dtype=np.uint64)
     lib().orc_clear_visbuffer(_p(vis), C.c_uint32(w), C.c_uint32(h))

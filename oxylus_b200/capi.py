@@ -17,7 +17,7 @@ E_NO_DEVICE = -3
 SYMBOLS = [
     "oxc_last_error", "oxc_kernel_launch_count", "oxc_version", "oxc_create", "oxc_destroy", "oxc_set_scene",
     "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_set_shard_auto", "oxc_cull_meshes",
-    "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_clear_visbuffer",
+    "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_cull_triangles_small_primitive", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
     "oxc_decode_visbuffer", "oxc_build_hpb",
     "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_debug_stats_ptr",
@@ -67,6 +67,7 @@ def load(build_if_missing=True):
     lib.oxc_build_hiz_mip0_packed.argtypes = [vp, vp, u32, u32, vp]
     lib.oxc_build_hiz_from_mip0.argtypes = [vp, vp]
     lib.oxc_cull_triangles.argtypes = [vp, vp, u32, vp]
+    lib.oxc_cull_triangles_small_primitive.argtypes = [vp, vp, u32, u32, u32, vp]
     lib.oxc_clear_visbuffer.argtypes = [vp, vp, u32, u32, vp]
     lib.oxc_raster_visbuffer.argtypes = [vp, vp, u32, u32, u32, vp, i32, vp]
     lib.oxc_raster_visbuffer_clip_pass.argtypes = [vp, vp, u32, u32, u32, vp, vp]
@@ -295,6 +296,9 @@ class Context:
 
     def cull_triangles(self, cam, flags):
         _check(self.lib.oxc_cull_triangles(self.h, _ptr(cam), flags, self.stream), "oxc_cull_triangles")
+
+    def cull_triangles_small_primitive(self, cam, flags, w, h):
+        _check(self.lib.oxc_cull_triangles_small_primitive(self.h, _ptr(cam), flags, w, h, self.stream), "oxc_cull_triangles_small_primitive")
 
     def clear_visbuffer(self, vis_dev, w, h):
         _check(self.lib.oxc_clear_visbuffer(self.h, _ptr(vis_dev), w, h, self.stream), "oxc_clear_visbuffer")

@@ -98,6 +98,9 @@ OXC_DI bool triangle_passes(const MeshletWork& w, uint32_t t, const float4* clip
   return in_front && !triangle_backface(c0, c1, c2);
 }
 
+struct ScreenVert;
+OXC_DI bool tri_covers_no_sample(float4 c0, float4 c1, float4 c2, float fW, float fH, uint32_t W, uint32_t H);
+
 // ---- cull_triangles: materialise the reference's reordered index buffer ----
 __global__ void __launch_bounds__(TRI_THREADS) k_cull_triangles(const __grid_constant__ TriParams p) {
   __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
@@ -121,6 +124,8 @@ __global__ void __launch_bounds__(TRI_THREADS) k_cull_triangles(const __grid_con
         const uint32_t t = lane + 32u * k;
         float4 c0, c1, c2;
         pass[k] = t < w.tri_count && triangle_passes(w, t, clip_s, c0, c1, c2);
+        // opt-in small-primitive cull (north_star; the reference has none): snapped bounding box without a sample centre
+        if (pass[k] && p.small_primitive_cull && tri_covers_no_sample(c0, c1, c2, p.f_width, p.f_height, p.width, p.height)) pass[k] = false;
         const uint32_t bal = __ballot_sync(0xffffffffu, pass[k]);
         rank[k] = wtotal + __popc(bal & ((1u << lane) - 1u));
         wtotal += __popc(bal);
@@ -169,6 +174,17 @@ OXC_DI ScreenVert to_screen(float4 c, float fW, float fH) {
   if (!(fabsf(qx) <= 4194304.0f && fabsf(qy) <= 4194304.0f)) return v;
   v.fx = (int)qx; v.fy = (int)qy; v.z = fm(c.z, rw);
   return v;
+}
+
+// oracle: orc_triangle_covers_no_sample
+OXC_DI bool tri_covers_no_sample(float4 c0, float4 c1, float4 c2, float fW, float fH, uint32_t W, uint32_t H) {
+  const ScreenVert v0 = to_screen(c0, fW, fH), v1 = to_screen(c1, fW, fH), v2 = to_screen(c2, fW, fH);
+  if (v0.fx == INT_MIN || v1.fx == INT_MIN || v2.fx == INT_MIN) return false;
+  const int minx = min(v0.fx, min(v1.fx, v2.fx)), maxx = max(v0.fx, max(v1.fx, v2.fx));
+  const int miny = min(v0.fy, min(v1.fy, v2.fy)), maxy = max(v0.fy, max(v1.fy, v2.fy));
+  const int px0 = max(0, (minx - 128 + 255) >> 8), px1 = min((int)W - 1, (maxx - 128) >> 8);
+  const int py0 = max(0, (miny - 128 + 255) >> 8), py1 = min((int)H - 1, (maxy - 128) >> 8);
+  return px1 < px0 || py1 < py0;
 }
 
 struct TriSetup {

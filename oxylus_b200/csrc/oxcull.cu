@@ -669,7 +669,18 @@ static int tri_common(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, c
   return OXC_OK;
 }
 
+static int cull_triangles_impl(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t spc, uint32_t w, uint32_t h, void* stream);
+
 int oxc_cull_triangles(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, void* stream) {
+  return cull_triangles_impl(c, cam, flags, 0, 0, 0, stream);
+}
+
+int oxc_cull_triangles_small_primitive(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t width, uint32_t height, void* stream) {
+  if (!width || !height) return fail(OXC_E_INVALID, "the small-primitive cull needs the raster extent");
+  return cull_triangles_impl(c, cam, flags, 1, width, height, stream);
+}
+
+static int cull_triangles_impl(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t spc, uint32_t w, uint32_t h, void* stream) {
   if (!c || !cam) return fail(OXC_E_INVALID, "null argument");
   if (!c->d_reordered) return fail(OXC_E_STATE, "context created without alloc_reordered_indices");
   if (c->scene_id_bound > (1ull << (32u - OXC_VIS_PRIMITIVE_BITS)))
@@ -680,6 +691,7 @@ int oxc_cull_triangles(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, 
   TriParams p{};
   int rc = tri_common(c, cam, flags, s, &p);
   if (rc != OXC_OK) return rc;
+  p.small_primitive_cull = spc; p.width = w; p.height = h; p.f_width = (float)w; p.f_height = (float)h;
   k_reset_draw_cmd<<<1, 1, 0, s>>>(c->d_draw_cmd); // CullGeometry.cpp:380-382
   LAUNCHED();
   uint32_t tiles = (c->info.max_meshlet_instances + TRI_WARPS - 1) / TRI_WARPS;

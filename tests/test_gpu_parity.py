@@ -168,6 +168,137 @@ def test_cull_triangles_parity(capi, orc):
     ctx.close()
 
 
+def test_small_primitive_cull_parity(capi, orc):
+    """north_star's small-primitive cull, opt-in on both triangle paths: (a) oxc_raster_visbuffer(small_primitive_cull=1)
+    draws the identical image and counts exactly the oracle's number of culled triangles fewer; (b)
+    oxc_cull_triangles_small_primitive emits the oracle's shorter index buffer."""
+    sc = synth.make_scene(config_index=3, **SCENES["medium"])
+    hs = orc.HostScene(sc)
+    ctx = make_ctx(capi, sc, reordered=True)
+    cam = sc.camera(1.0)
+    w, h = sc.width, sc.height
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    ref_vis, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+    n = int(cmd["x"][0])
+    ref_idx, ref_draw, culled = orc.cull_triangles_small_primitive(hs, mi, ref_vis, 0, n, cam, w, h)
+    full_idx, _ = orc.cull_triangles(hs, mi, ref_vis, 0, n, cam)
+    assert culled > 0 and len(full_idx) - len(ref_idx) == 3 * culled
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, use_hiz=False)
+    # (b) index buffer
+    ctx.cull_triangles_small_primitive(cam, abi.CULL_TEST_FRUSTUM, w, h)
+    dc = ctx.draw_cmd()
+    assert int(dc["index_count"][0]) == int(ref_draw["index_count"][0])
+    got = ctx.reordered_indices(int(dc["index_count"][0])).reshape(-1, 3)
+    np.testing.assert_array_equal(got[np.argsort(got[:, 0], kind="stable")],
+                                  ref_idx.reshape(-1, 3)[np.argsort(ref_idx.reshape(-1, 3)[:, 0], kind="stable")])
+    # (a) raster: same image, fewer counted triangles
+    vis_dev = ctx.alloc(w * h * 8)
+    images, counts = [], []
+    for spc in (False, True):
+        ctx.clear_visbuffer(vis_dev, w, h)
+        ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev, small_primitive_cull=spc)
+        images.append(ctx.download(vis_dev, np.uint64, w * h))
+        counts.append(ctx.raster_triangle_count())
+    np.testing.assert_array_equal(images[0], images[1])
+    assert counts[0] == len(full_idx) // 3 and counts[1] == counts[0] - culled
+    ref_img = orc.clear_visbuffer(w, h)
+    orc.raster(hs, mi, ref_vis, 0, n, cam, ref_img)
+    np.testing.assert_array_equal(images[1].reshape(h, w), ref_img)
+    ctx.free(vis_dev)
+    ctx.close()
+
+
+def test_wide_id_packing_and_24_bit_refusal(capi, orc):
+    """Scenes that can emit more than 2^24 meshlet instances overflow the reference's 24 + 8 bit vis-buffer word: the raster
+    refuses them (OXC_E_CAPACITY) unless the context was created with wide_ids (26 + 6 bits).  The wide packing is the
+    oracle's image with every id word repacked — same winners (the tie-break order (id, triangle) is preserved)."""
+    # (a) wide packing on a small scene with a large id base: ids beyond 2^24
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    hs = orc.HostScene(sc)
+    w, h = sc.width, sc.height
+    hw, hh = sc.hiz_extent()
+    ctx = capi.Context(0, sc.mesh_instance_count, sc.max_meshlet_instance_count, hw, hh, wide_ids=True)
+    ctx.set_scene(sc)
+    base = (1 << 25) + 12345
+    base_dev = ctx.alloc(4)
+    ctx.upload(base_dev, np.array([base], dtype=np.uint32))
+    ctx.set_shard(0, sc.mesh_instance_count, base_dev)
+    cam = sc.camera(0.0)
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    ref_vis, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+    n = int(cmd["x"][0])
+    ref_img = orc.clear_visbuffer(w, h)
+    orc.raster(hs, mi, ref_vis, 0, n, cam, ref_img)
+    data = (ref_img & 0xFFFFFFFF).astype(np.uint64)
+    drawn = data != 0xFFFFFFFF
+    repacked = np.where(drawn, (((data >> 8) + base) << 6) | (data & 0xFF), data)
+    want = (ref_img & np.uint64(0xFFFFFFFF00000000)) | repacked
+    vis_dev = ctx.alloc(w * h * 8)
+    ctx.clear_visbuffer(vis_dev, w, h)
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, use_hiz=False)
+    np.testing.assert_array_equal(np.sort(ctx.visible_indices(n)), np.sort(ref_vis[:n]) + base)
+    ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+    got = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
+    np.testing.assert_array_equal(got, want)
+    assert ctx.out.vis_primitive_bits == 6
+    ctx.free(vis_dev); ctx.free(base_dev)
+    ctx.close()
+    # (b) a 17 M scene: refused with the reference packing, accepted with the wide one
+    big = synth.make_scene(17_000_000, config_index=2, width=640, height=360)
+    bhw, bhh = big.hiz_extent()
+    for wide in (False, True):
+        ctx = capi.Context(0, big.mesh_instance_count, big.max_meshlet_instance_count, bhw, bhh, wide_ids=wide)
+        ctx.set_scene(big)
+        cam = big.camera(0.0)
+        vis_dev = ctx.alloc(640 * 360 * 8)
+        ctx.clear_visbuffer(vis_dev, 640, 360)
+        ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+        ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, use_hiz=False)
+        if wide:
+            ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, 640, 360, vis_dev)
+            ctx.sync()
+            assert ctx.check_status() == 0 and ctx.raster_triangle_count() > 0
+        else:
+            with pytest.raises(capi.OxcError, match="wide_ids"):
+                ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, 640, 360, vis_dev)
+        ctx.free(vis_dev)
+        ctx.close()
+
+
+def test_scene_validation_and_capacity_errors(capi):
+    """a scene larger than the create-time capacities, or with an index out of range, is an error from oxc_set_scene
+    (OXC_E_CAPACITY / OXC_E_INVALID), not silent device-memory corruption."""
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    hw, hh = sc.hiz_extent()
+    ctx = capi.Context(0, sc.mesh_instance_count, sc.max_meshlet_instance_count - 1, hw, hh)
+    with pytest.raises(capi.OxcError, match="max_meshlet_instances"):
+        ctx.set_scene(sc)
+    ctx.close()
+    for field, bad in (("mesh_index", len(sc.meshes)), ("transform_index", len(sc.transforms)), ("lod_index", 9)):
+        ctx = capi.Context(0, sc.mesh_instance_count, sc.max_meshlet_instance_count, hw, hh)
+        keep = sc.mesh_instances[field][3]
+        sc.mesh_instances[field][3] = bad
+        try:
+            with pytest.raises(capi.OxcError, match=field):
+                ctx.set_scene(sc)
+        finally:
+            sc.mesh_instances[field][3] = keep
+        ctx.close()
+    # a shard context sized for its own share accepts the scene once the shard is set, and refuses a range that does not fit
+    from oxylus_b200 import dist as oxdist
+
+    half = sc.mesh_instance_count // 2
+    need = int(oxdist.lod0_counts_of(sc)[:half].sum())
+    ctx = capi.Context(0, sc.mesh_instance_count, need, hw, hh, max_mask_bits=sc.max_meshlet_instance_count)
+    ctx.set_shard_auto(0, half)
+    ctx.set_scene(sc)
+    with pytest.raises(capi.OxcError, match="max_meshlet_instances"):
+        ctx.set_shard_auto(0, sc.mesh_instance_count)
+    ctx.close()
+
+
 def test_hiz_build_shapes(capi, orc):
     """depth sizes whose Hi-Z extent differs from size/2 (point-sample mapping), incl. a sub-tile pyramid."""
     rng = np.random.default_rng(7)
@@ -553,7 +684,7 @@ def test_full_size_config2_properties(capi):
     r.set_external_depth(sc.occluder_depth)
     cam = sc.camera(0.0)
     prev = None
-    for f in range(4):
+    for f in range(4):  # 4 frames: the steady state (frames 2 -> 3) is part of what is checked
         got = r.render(cam, None)
         n = got["early"] + got["late"]
         ids = got["visible"]
@@ -573,6 +704,72 @@ def test_full_size_config2_properties(capi):
             assert got["late"] == prev["late"]
         prev = got
     r.close()
+
+
+def test_full_size_config2_parity(capi, orc):
+    """BASELINE.json configs[2] at FULL size (10 M meshlet instances, 3840x2160 vis buffer, per-triangle cull + SW raster):
+    two two-pass frames through the C++ host mirror, bit-exact against the threaded oracle frame — survivor set, visibility
+    mask, packed image (ids + depth), triangle count."""
+    import os
+
+    sc = synth.make_scene(10_000_000, config_index=3, width=3840, height=2160)
+    hs = orc.HostScene(sc)
+    r = capi.Renderer(0, sc)
+    r.set_external_depth(sc.occluder_depth)
+    mask_ref = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    threads = min(64, os.cpu_count() or 1)
+    for f in range(2):
+        cam = sc.camera(2.0 * (f % 2))
+        ref = orc.cpu_frame(hs, cam, sc.width, sc.height, mask_ref, sc.occluder_depth, threads)
+        got = r.render(cam, None)
+        e, l = int(ref["visibility"]["early"][0]), int(ref["visibility"]["late"][0])
+        assert (got["total"], got["early"], got["late"]) == (int(ref["visibility"]["total"][0]), e, l)
+        v32, d = orc.resolve(ref["vis64"])
+        np.testing.assert_array_equal(got["vis32"], v32)
+        np.testing.assert_array_equal(got["depth"].view(np.uint32), d.view(np.uint32))
+        np.testing.assert_array_equal(np.sort(got["visible"]), np.sort(ref["visible"][: e + l]))
+        np.testing.assert_array_equal(r.ctx.mask(), mask_ref)
+        assert got["raster_triangles"] == ref["triangles"]
+    # the pyramid the late pass used was built from the early image; its 2048^2 build is covered bit for bit by
+    # test_hiz_build_shapes (3840x2160 included) and, here, by the late survivor set being identical
+    assert r.ctx.check_status() == 0
+    r.close()
+
+
+def test_full_size_config3_multiview_parity(capi, orc):
+    """BASELINE.json configs[3] at FULL size: 16 shadow-cascade views x 5 M meshlet instances in ONE batched launch; view
+    bits and per-view counts bit-exact against the oracle (evaluated in parallel chunks: the C oracle releases the GIL)."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    n_views = 16
+    sc = synth.make_scene(5_000_000, config_index=4, width=1920, height=1080, placement="box")
+    hs = orc.HostScene(sc)
+    ctx = make_ctx(capi, sc, views=n_views)
+    cam = sc.camera()
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    total = int(vis["total"][0])
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    assert int(ctx.visibility()["total"][0]) == total and total > 2_000_000
+    dirs = synth.uniform(sc.seed, 90, 3 * n_views, -1.0, 1.0).reshape(n_views, 3)
+    dirs[:, 1] = -np.abs(dirs[:, 1]) - 0.2
+    views = np.concatenate([synth.make_ortho_view(dirs[v], (0.0, 0.0, -200.0), 60.0 * (1 + v % 4), 800.0, sc.mesh_instance_count)
+                            for v in range(n_views)])
+    workers = min(32, os.cpu_count() or 1)
+    edges = np.linspace(0, total, workers * 4 + 1).astype(np.int64)
+
+    def chunk(k):
+        a, b = int(edges[k]), int(edges[k + 1])
+        return orc.cull_meshlets_multiview(hs, np.ascontiguousarray(mi[a:b]), b - a, views, 1)
+
+    with ThreadPoolExecutor(workers) as ex:
+        parts = list(ex.map(chunk, range(len(edges) - 1)))
+    ref_bits = np.concatenate([p[0] for p in parts])
+    ref_counts = np.sum([p[1] for p in parts], axis=0).astype(np.uint32)
+    ctx.cull_meshlets_multiview(views, 1)
+    np.testing.assert_array_equal(ctx.view_bits(total), ref_bits)
+    np.testing.assert_array_equal(ctx.view_counts(), ref_counts)
+    ctx.close()
 
 
 def test_cull_meshlets_hpb_parity(capi, orc):

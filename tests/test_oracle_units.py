@@ -219,6 +219,36 @@ def test_raster_watertight_and_depth(orc):
     assert np.all(d[~covered] == 0.0)
 
 
+def test_small_primitive_cull_hand_cases(orc):
+    """north_star's small-primitive cull (opt-in; oracle/oxc_oracle.c orc_triangle_covers_no_sample): a 64x48 target, pixel
+    centres at k + 0.5.  clip = (ndc.x, ndc.y, z, 1)."""
+    import ctypes as C
+
+    W, H = 64, 48
+    fn = orc.lib().orc_triangle_covers_no_sample
+    fn.restype = C.c_int
+
+    def tri(px):  # pixel-space corners -> clip space with w = 1
+        a = np.zeros((3, 4), dtype=np.float32)
+        for i, (x, y) in enumerate(px):
+            a[i] = (x / W * 2.0 - 1.0, y / H * 2.0 - 1.0, 0.5, 1.0)
+        return a
+
+    def covers_none(px, w=None):
+        a = tri(px)
+        if w is not None:
+            a[:, 3] = w
+        return fn(a.ctypes.data_as(C.c_void_p), C.c_uint32(W), C.c_uint32(H))
+
+    assert covers_none([(10.6, 10.6), (10.9, 10.6), (10.6, 10.9)]) == 1       # strictly between the centres 10.5 and 11.5
+    assert covers_none([(10.4, 10.4), (10.7, 10.4), (10.4, 10.7)]) == 0       # bounding box contains the centre (10.5, 10.5)
+    assert covers_none([(10.6, 3.0), (10.9, 30.0), (10.7, 17.0)]) == 1        # tall sliver between two columns of centres
+    assert covers_none([(3.0, 10.6), (30.0, 10.9), (17.0, 10.7)]) == 1        # long sliver between two rows
+    assert covers_none([(10.6, 10.6), (12.9, 10.6), (10.6, 10.9)]) == 1       # spans a column of centres but no row
+    assert covers_none([(10.6, 10.6), (10.9, 10.6), (10.6, 10.9)], w=[1.0, -1.0, 1.0]) == 0  # a vertex behind the camera: never "small"
+    assert covers_none([(-5.8, 10.2), (-5.1, 10.9), (-5.4, 10.3)]) == 1       # left of the image: clamped bounds are empty
+
+
 def test_terrain_cull_hand_case(orc):
     """terrain_cull.slang:19-83 with projection_view = I: 2x1 patches over x in [-2,2], z in [0,1]; the left patch is
     outside the x in [-1,1] frustum slab only if it does not touch it (it spans [-2,0] -> straddles -> visible)."""
