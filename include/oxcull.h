@@ -247,6 +247,7 @@ enum {
   OXC_STATUS_BAD_GEOMETRY = 1 << 1,     /* a micro index >= vertex_count or a vertex index >= Mesh::vertex_count (triangle skipped) */
   OXC_STATUS_SURVIVOR_OVERFLOW = 1 << 2,/* oxc_mgpu_exchange_frame: a rank's survivor list exceeded the gather capacity (truncated) */
   OXC_STATUS_ID_OVERFLOW = 1 << 3,      /* a vis-buffer id did not fit the id bits of the packing (pixel skipped) */
+  OXC_STATUS_CLIP_OVERFLOW = 1 << 5,    /* more triangles crossed the near / guard-band planes than the clip queue holds (2^20): the rest was dropped */
   OXC_STATUS_PEER_TIMEOUT = 1 << 4      /* oxc_mgpu_exchange_hiz: a peer did not raise its flag within 30 s (OXC_MGPU_TIMEOUT_MS); that frame's pyramid is incomplete */
 };
 int oxc_check_status(OxcContext* ctx, void* stream, uint32_t* flags_out /* may be NULL */);
@@ -330,19 +331,20 @@ int oxc_clear_visbuffer(OxcContext* ctx, uint64_t* vis_dev, uint32_t width, uint
 /* Software replacement of cull_triangles + visbuffer_encode (visbuffer_encode.slang:24-74,
  * visbuffer_encode_ms.slang:110-171; DrawGeometry.cpp:104-190): per surviving meshlet of this pass,
  * per-triangle near/backface cull then rasterisation with atomicMax on asuint(depth)<<32 | data
- * (reverse-Z GreaterOrEqual == max; visbuffer.slang:72-74 packing).  small_primitive_cull != 0
+ * (reverse-Z GreaterOrEqual == max; visbuffer.slang:72-74 packing).  Triangles with a vertex at w <= 0 or outside the
+ * 2^22 snap range — geometry around the camera, which the reference's hardware rasteriser clips — are queued by the raster
+ * kernel and clipped against near + the four side planes by a follow-up kernel (Sutherland-Hodgman, fan of <= 6 pieces drawn
+ * with the same rules; specification + tests: oracle/oxc_oracle.c raster_triangle_clipped).  small_primitive_cull != 0
  * additionally drops triangles whose pixel bbox covers no sample centre BEFORE they are counted (north_star's
  * small-primitive cull; the reference has none, cull_triangles.slang:59-90): the image is unchanged — such a triangle
  * produces no fragment — only OxcOutputs::raster_triangle_count drops by the number culled. */
 int oxc_raster_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width,
                          uint32_t height, uint64_t* vis_dev, int small_primitive_cull, void* stream);
 
-/* OPT-IN second raster pass (call after oxc_raster_visbuffer with the same arguments): the triangles that pass draws nothing
- * for — a vertex at w <= 0 or a snapped coordinate beyond 2^22, i.e. geometry around the camera, which the reference's hardware
- * rasteriser clips (DrawGeometry.cpp:104-190) — are clipped in clip space against near + the four side planes and drawn as a
- * fan with the same rules (specification and tests: oracle/oxc_oracle.c raster_triangle_clipped, tests/test_oracle_clip.py).
- * Every other triangle is untouched, so frames without such triangles are bit-identical with and without this pass.
- * Status: written after round 1's GPU budget was spent; not yet verified on a GPU (its parity test is skipped until then). */
+/* Stand-alone clip pass: walks the pass's survivors again and clips / draws exactly the triangles described above.
+ * oxc_raster_visbuffer does this by itself since round 2 (it queues those triangles while it rasterises), so a host only needs
+ * this entry point after a raster that ran with the queue exhausted (OXC_STATUS_CLIP_OVERFLOW); drawing a triangle twice is
+ * harmless (same depth, same id). */
 int oxc_raster_visbuffer_clip_pass(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width,
                                    uint32_t height, uint64_t* vis_dev, void* stream);
 

@@ -655,7 +655,8 @@ uint64_t orc_cull_triangles_small_primitive(const OrcScene* scene, const OxcMesh
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Clipped raster (SPECIFICATION ONLY — the CUDA raster does not implement it yet).
+ * Clipped raster (round 2: implemented by the CUDA raster — oxc_raster_visbuffer queues exactly these triangles for
+ * k_raster_clip_queue — and used by the frame functions below).
  * The plain spec drops a triangle when a vertex has w <= 0 or a snapped coordinate exceeds 2^22 (steps 2-3); a hardware
  * rasteriser clips such triangles instead (DrawGeometry.cpp:104-190 relies on it: geometry around the camera).  Only those
  * triangles take this path, so every triangle the plain spec draws is drawn identically:
@@ -687,7 +688,8 @@ static inline float clip_plane_distance(const float v[4], int plane) {
   }
 }
 
-static void raster_triangle_clipped(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis) {
+typedef void (*RasterFn)(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis);
+static void raster_triangle_clipped_with(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis, RasterFn draw) {
   float poly[2][12][4];
   int n = 3, cur = 0;
   memcpy(poly[0], clip, sizeof(float) * 12);
@@ -717,8 +719,11 @@ static void raster_triangle_clipped(const float clip[3][4], uint32_t data, uint3
   for (int i = 1; i + 1 < n; i++) {
     float tri[3][4];
     memcpy(tri[0], poly[cur][0], 16); memcpy(tri[1], poly[cur][i], 16); memcpy(tri[2], poly[cur][i + 1], 16);
-    raster_triangle(tri, data, W, H, vis);
+    draw(tri, data, W, H, vis);
   }
+}
+static void raster_triangle_clipped(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis) {
+  raster_triangle_clipped_with(clip, data, W, H, vis, raster_triangle);
 }
 
 void orc_raster_visbuffer_clip(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
@@ -1254,8 +1259,10 @@ static void* frame_raster_worker(void* arg) {
         }
         if (!tri_passes(clip)) continue;
         ntri++;
-        raster_triangle_atomic(clip, (mii << OXC_VIS_PRIMITIVE_BITS) | (tri & OXC_VIS_PRIMITIVE_MASK), j->width, j->height,
-                               j->vis);
+        const uint32_t data = (mii << OXC_VIS_PRIMITIVE_BITS) | (tri & OXC_VIS_PRIMITIVE_MASK);
+        /* the product's raster clips what the plain spec drops (round 2): the frame follows */
+        if (tri_dropped_by_range(clip, j->width, j->height)) raster_triangle_clipped_with(clip, data, j->width, j->height, j->vis, raster_triangle_atomic);
+        else raster_triangle_atomic(clip, data, j->width, j->height, j->vis);
       }
     }
   }

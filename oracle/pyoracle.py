@@ -216,14 +216,14 @@ def frame(hs, cam, width, height, mask, occluder_depth=None, first=0, count=0xFF
     visible, tcmd_e = cull_meshlets_hiz(hs, mi, vis, cam, abi.CULL_TEST_ALL, hiz, mask)
     e = int(vis["early"][0])
     mask_after_early = mask.copy()
-    ntri_e = raster(hs, mi, visible, 0, e, cam, img, id_base)
+    ntri_e = raster_clip(hs, mi, visible, 0, e, cam, img, id_base)[0]  # the product's raster clips what the plain spec drops
     if between_passes:
         between_passes(img)
     _, depth = resolve(img)
     build_hiz(depth, hiz)
     visible, tcmd_l = cull_meshlets_hiz(hs, mi, vis, cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, hiz, mask, visible)
     l = int(vis["late"][0])
-    ntri_l = raster(hs, mi, visible, e, l, cam, img, id_base)
+    ntri_l = raster_clip(hs, mi, visible, e, l, cam, img, id_base)[0]
     if after_frame:
         after_frame(img)
     return dict(meshlet_instances=mi, visibility=vis, visible=visible, early=e, late=l, hiz=hiz, vis64=img,

@@ -117,6 +117,7 @@ VIS_PRIMITIVE_BITS = 8
 VIS_WIDE_PRIMITIVE_BITS = 6
 VIS_CLEAR = 0xFFFFFFFF
 STATUS_MESHLET_OVERFLOW, STATUS_BAD_GEOMETRY, STATUS_SURVIVOR_OVERFLOW, STATUS_ID_OVERFLOW, STATUS_PEER_TIMEOUT = 1, 2, 4, 8, 16
+STATUS_CLIP_OVERFLOW = 32
 
 # VSMPageState — Shaders/rmvsm.slang:16-28 ([Flags] enum)
 VSM_PAGE_VISIBLE = 1

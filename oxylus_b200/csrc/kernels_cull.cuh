@@ -723,8 +723,13 @@ struct CullWarp {
   }
 };
 
+#ifndef OXC_CULL_MIN_BLOCKS_EARLY
+#define OXC_CULL_MIN_BLOCKS_EARLY 3
+#endif
+// launch bounds per variant (measured on B200, round 2): the early pass (queue 0 -> stage A on compacted items) runs 21.6 us at
+// 3 CTAs / SM (85 registers) vs 26.6 us at 4; the late pass is indifferent (42 us) and keeps 4 CTAs / SM for the latency it hides
 template <bool HIZ, bool OCC, bool LATE, bool ZERO>
-__global__ void __launch_bounds__(CULL_THREADS, OXC_CULL_MIN_BLOCKS) k_cull_meshlets(const __grid_constant__ CullParams p) {
+__global__ void __launch_bounds__(CULL_THREADS, (OCC && !LATE) ? OXC_CULL_MIN_BLOCKS_EARLY : OXC_CULL_MIN_BLOCKS) k_cull_meshlets(const __grid_constant__ CullParams p) {
   extern __shared__ __align__(16) unsigned char cull_smem_raw[];
   using Shared = CullShared<OCC && !LATE>;
   Shared& sh = *reinterpret_cast<Shared*>(cull_smem_raw);

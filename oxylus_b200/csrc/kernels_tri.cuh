@@ -38,6 +38,9 @@ struct TriParams {
   uint4* big_queue;          // BIG_WORDS/4 uint4 per entry
   uint32_t* big_counters;
   uint32_t big_capacity;
+  uint32_t* clip_queue;      // data words (id << prim_bits | triangle) of the triangles the plain rules drop: clipped by k_raster_clip_queue
+  uint32_t* clip_counter;    // entries pushed; zeroed before every raster launch
+  uint32_t clip_capacity;
   uint32_t prim_bits;        // triangle bits of the vis-buffer word: 8 (visbuffer.slang:9-14) or 6 (OxcCreateInfo::wide_ids)
   uint32_t small_primitive_cull; // 1: triangles whose snapped bounding box holds no sample centre are culled before they are counted
   uint32_t* status;          // sticky OXC_STATUS_* bits
@@ -540,6 +543,11 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
               const int why = tri_setup(scr_s[i0], scr_s[i1], scr_s[i2], p.width, p.height, s);
               draw = why == TRI_DRAW;
               if (why == TRI_NO_SAMPLE && p.small_primitive_cull) pass = false; // north_star small-primitive cull (opt-in)
+              if (why == TRI_INVALID_VERTEX && p.clip_queue) { // a vertex at w <= 0 / beyond the snap range: clipped later, like a
+                const uint32_t slot = atomicAdd(p.clip_counter, 1u); // hardware rasteriser would (DrawGeometry.cpp:104-190)
+                if (slot < p.clip_capacity) p.clip_queue[slot] = (w.gid << p.prim_bits) | t;
+                else atomicOr(p.status, (uint32_t)OXC_STATUS_CLIP_OVERFLOW);
+              }
             }
           }
         }
@@ -615,13 +623,11 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
   if (lane == 0 && kept) atomicAdd(p.tri_counter, (unsigned long long)kept);
 }
 
-// ---- clip pass (opt-in; specification: oracle/oxc_oracle.c raster_triangle_clipped) ----
-// Handles exactly the triangles k_raster_visbuffer drops because a vertex has w <= 0 or a snapped coordinate beyond 2^22:
-// Sutherland-Hodgman in clip space against near (w - z), left (w + x), right (w - x), bottom (w + y), top (w - y), cut points
-// evaluated from the inside vertex to the outside vertex with the canonical f32 operation order, then the fan (P0, Pi, Pi+1)
-// is set up with the plain rules.  Pieces are usually large (geometry around the camera): they go to the chunk queue of
-// k_raster_big (inline when the queue is full).  A separate kernel: the default raster path is untouched.
-// NOT YET VERIFIED ON A GPU (written after the round's GPU budget was spent): the parity test is skipped until it has been.
+// ---- clipping of the triangles the plain rules drop (specification: oracle/oxc_oracle.c raster_triangle_clipped) ----
+// Sutherland-Hodgman in clip space against near (w - z), left (w + x), right (w - x), bottom (w + y), top (w - y); cut points
+// evaluated from the inside vertex to the outside vertex with the canonical f32 operation order; the fan (P0, Pi, Pi+1) is
+// set up with the plain rules.  Pieces are usually large (geometry around the camera): they go to the chunk queue of
+// k_raster_big (inline when the queue is full).
 OXC_DI float clip_plane_distance(const float4 v, int plane) {
   switch (plane) {
     case 0: return fs(v.w, v.z);
@@ -632,6 +638,70 @@ OXC_DI float clip_plane_distance(const float4 v, int plane) {
   }
 }
 
+OXC_DI void clip_and_draw(const TriParams& p, float4 c0, float4 c1, float4 c2, uint32_t data, float fW, float fH) {
+  float4 poly[2][12];
+  int n = 3, cur = 0;
+  poly[0][0] = c0; poly[0][1] = c1; poly[0][2] = c2;
+  for (int plane = 0; plane < 5 && n >= 3; plane++) {
+    const float4* in = poly[cur];
+    float4* out = poly[cur ^ 1];
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+      const float4 A = in[i], B = in[(i + 1) % n];
+      const float dA = clip_plane_distance(A, plane), dB = clip_plane_distance(B, plane);
+      const bool inA = dA >= 0.0f, inB = dB >= 0.0f;
+      if (inA) out[m++] = A;
+      if (inA != inB) {
+        const float4 I = inA ? A : B, O = inA ? B : A;
+        const float dI = inA ? dA : dB, dO = inA ? dB : dA;
+        const float tt = fd(dI, fs(dI, dO));
+        out[m++] = make_float4(fa(I.x, fm(tt, fs(O.x, I.x))), fa(I.y, fm(tt, fs(O.y, I.y))), fa(I.z, fm(tt, fs(O.z, I.z))),
+                               fa(I.w, fm(tt, fs(O.w, I.w))));
+      }
+    }
+    n = m;
+    cur ^= 1;
+  }
+  for (int i = 1; i + 1 < n; i++) {
+    TriSetup s;
+    if (tri_setup(to_screen(poly[cur][0], fW, fH), to_screen(poly[cur][i], fW, fH), to_screen(poly[cur][i + 1], fW, fH), p.width, p.height, s) != TRI_DRAW)
+      continue;
+    const int bw = s.px1 - s.px0 + 1, bh = s.py1 - s.py0 + 1;
+    if (bw * bh > RASTER_BIG_PIXELS && p.big_queue && big_push(p, s, data)) continue; // spread over the GPU by k_raster_big
+    s.narrow = false; // pieces may be large: 64-bit edge functions
+    raster_small(s, data, p.visbuf, p.width);
+  }
+}
+
+// One thread per queued triangle (k_raster_visbuffer queued its data word): the three clip-space corners are recomputed with
+// the canonical operation order (bit-identical to the ones the raster saw), then clipped and drawn.  Runs after every
+// k_raster_visbuffer and before k_raster_big; the queue is empty unless geometry crosses the near / guard-band planes.
+__global__ void __launch_bounds__(128) k_raster_clip_queue(const __grid_constant__ TriParams p) {
+  const uint32_t n = min(*p.clip_counter, p.clip_capacity);
+  const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
+  for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x) {
+    const uint32_t data = p.clip_queue[e];
+    const uint32_t gid = data >> p.prim_bits, t = data & ((1u << p.prim_bits) - 1u);
+    const uint2 mi = __ldg(reinterpret_cast<const uint2*>(p.meshlet_instances) + (gid - id_base));
+    const InstGeom* g = p.geom + mi.x;
+    const InstCull* ic = p.inst + mi.x;
+    const uint4 m = __ldg(reinterpret_cast<const uint4*>(g->meshlets + mi.y));
+    const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
+    float4 c[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const uint32_t li = micro_index(g->local_triangle_indices, m.y + t * 3u + k);
+      const uint32_t vi = __ldg(&g->indirect_vertex_indices[m.x + li]);
+      const uint2 q = __ldg(&g->vertex_positions[vi]);
+      const float x = dequantize_half_hw(q.x & 0xFFFFu), y = dequantize_half_hw(q.x >> 16), z = dequantize_half_hw(q.y & 0xFFFFu);
+      c[k] = make_float4(row_dot_p1(r0, x, y, z), row_dot_p1(r1, x, y, z), row_dot_p1(r2, x, y, z), row_dot_p1(r3, x, y, z));
+    }
+    clip_and_draw(p, c[0], c[1], c[2], data, p.f_width, p.f_height);
+  }
+}
+
+// ---- stand-alone clip pass (kept for hosts that drive the plain raster themselves): walks every survivor again and clips
+//      the triangles the plain rules drop.  oxc_raster_visbuffer no longer needs it — it queues those triangles itself. ----
 __global__ void __launch_bounds__(TRI_THREADS) k_raster_clip_pass(const __grid_constant__ TriParams p) {
   __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -650,40 +720,7 @@ __global__ void __launch_bounds__(TRI_THREADS) k_raster_clip_pass(const __grid_c
         if (!triangle_passes(w, t, clip_s, c0, c1, c2)) continue;
         if (to_screen(c0, fW, fH).fx != INT_MIN && to_screen(c1, fW, fH).fx != INT_MIN && to_screen(c2, fW, fH).fx != INT_MIN)
           continue; // drawn by k_raster_visbuffer
-        float4 poly[2][12];
-        int n = 3, cur = 0;
-        poly[0][0] = c0; poly[0][1] = c1; poly[0][2] = c2;
-        for (int plane = 0; plane < 5 && n >= 3; plane++) {
-          const float4* in = poly[cur];
-          float4* out = poly[cur ^ 1];
-          int m = 0;
-          for (int i = 0; i < n; i++) {
-            const float4 A = in[i], B = in[(i + 1) % n];
-            const float dA = clip_plane_distance(A, plane), dB = clip_plane_distance(B, plane);
-            const bool inA = dA >= 0.0f, inB = dB >= 0.0f;
-            if (inA) out[m++] = A;
-            if (inA != inB) {
-              const float4 I = inA ? A : B, O = inA ? B : A;
-              const float dI = inA ? dA : dB, dO = inA ? dB : dA;
-              const float tt = fd(dI, fs(dI, dO));
-              out[m++] = make_float4(fa(I.x, fm(tt, fs(O.x, I.x))), fa(I.y, fm(tt, fs(O.y, I.y))), fa(I.z, fm(tt, fs(O.z, I.z))),
-                                     fa(I.w, fm(tt, fs(O.w, I.w))));
-            }
-          }
-          n = m;
-          cur ^= 1;
-        }
-        const uint32_t data = (w.data_id << p.prim_bits) | t;
-        for (int i = 1; i + 1 < n; i++) {
-          TriSetup s;
-          if (tri_setup(to_screen(poly[cur][0], fW, fH), to_screen(poly[cur][i], fW, fH), to_screen(poly[cur][i + 1], fW, fH), p.width,
-                        p.height, s) != TRI_DRAW)
-            continue;
-          const int bw = s.px1 - s.px0 + 1, bh = s.py1 - s.py0 + 1;
-          if (bw * bh > RASTER_BIG_PIXELS && p.big_queue && big_push(p, s, data)) continue; // spread over the GPU by k_raster_big
-          s.narrow = false; // pieces may be large: 64-bit edge functions
-          raster_small(s, data, p.visbuf, p.width);
-        }
+        clip_and_draw(p, c0, c1, c2, (w.data_id << p.prim_bits) | t, fW, fH);
       }
     }
     __syncwarp(); // clip_s reuse

@@ -124,6 +124,9 @@ struct OxcContext {
   uint4* d_big_queue = nullptr;      // deferred large triangles of the raster (kernels_tri.cuh)
   uint32_t* d_big_counters = nullptr;
   uint32_t big_capacity = 0;
+  uint32_t* d_clip_queue = nullptr;  // triangles the plain raster rules drop (clipped by k_raster_clip_queue)
+  uint32_t* d_clip_counter = nullptr;
+  uint32_t clip_capacity = 1u << 20;
   // hiz
   float* d_hiz = nullptr;
   HizDesc hiz{};
@@ -285,6 +288,12 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
 #endif
   CK(cudaMemset(c->d_big_queue + (size_t)c->big_capacity * 4, 0, 1024));
   TRY(dalloc(&c->d_big_counters, 2));
+  if (const char* e = getenv("OXC_CLIP_CAPACITY")) { // test hook: force the overflow path
+    const long v = atol(e);
+    if (v >= 1 && v <= (1l << 24)) c->clip_capacity = (uint32_t)v;
+  }
+  TRY(dalloc(&c->d_clip_queue, (size_t)c->clip_capacity));
+  TRY(dalloc(&c->d_clip_counter, 1));
   TRY(dalloc(&c->d_id_base_auto, 1));
   TRY(dalloc(&c->d_status, 1));
   c->prim_bits = info->wide_ids ? OXC_VIS_WIDE_PRIMITIVE_BITS : OXC_VIS_PRIMITIVE_BITS;
@@ -352,7 +361,7 @@ void oxc_destroy(OxcContext* c) {
   cudaFree(c->d_lod_aabb); cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
   cudaFree(c->d_meshlet_instances); cudaFree(c->d_slabs); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
-  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_big_queue); cudaFree(c->d_big_counters); cudaFree(c->d_id_base_auto); cudaFree(c->d_status); cudaFree(c->d_hiz);
+  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_big_queue); cudaFree(c->d_big_counters); cudaFree(c->d_clip_queue); cudaFree(c->d_clip_counter); cudaFree(c->d_id_base_auto); cudaFree(c->d_status); cudaFree(c->d_hiz);
   cudaFree(c->d_view_planes); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts); cudaFree(c->d_inst_views);
   delete c;
 }
@@ -734,8 +743,12 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
   if (grid > tiles) grid = tiles;
   if (grid == 0) grid = 1;
   p.big_queue = c->d_big_queue; p.big_counters = c->d_big_counters; p.big_capacity = c->big_capacity;
+  p.clip_queue = c->d_clip_queue; p.clip_counter = c->d_clip_counter; p.clip_capacity = c->clip_capacity;
   CK(cudaMemsetAsync(c->d_big_counters, 0, 8, s));
+  CK(cudaMemsetAsync(c->d_clip_counter, 0, 4, s));
   k_raster_visbuffer<<<grid, TRI_THREADS, 0, s>>>(p);
+  LAUNCHED();
+  k_raster_clip_queue<<<c->sm_count, 128, 0, s>>>(p); // the triangles the plain rules drop (usually none: exits at once)
   LAUNCHED();
   k_raster_big<<<c->sm_count * 8, 256, 0, s>>>(p); // the deferred large triangles, one warp per <= 64x32-pixel chunk
   LAUNCHED();
@@ -987,10 +1000,12 @@ int oxc_check_status(OxcContext* c, void* stream, uint32_t* flags_out) {
   if (flags_out) *flags_out = f;
   if (!f) return OXC_OK;
   CK(cudaMemsetAsync(c->d_status, 0, 4, s));
-  if (f & (OXC_STATUS_MESHLET_OVERFLOW | OXC_STATUS_SURVIVOR_OVERFLOW | OXC_STATUS_ID_OVERFLOW))
-    return fail(OXC_E_CAPACITY, "device status 0x%x:%s%s%s", f, (f & OXC_STATUS_MESHLET_OVERFLOW) ? " cull_meshes exceeded max_meshlet_instances (clamped)" : "",
+  if (f & (OXC_STATUS_MESHLET_OVERFLOW | OXC_STATUS_SURVIVOR_OVERFLOW | OXC_STATUS_ID_OVERFLOW | OXC_STATUS_CLIP_OVERFLOW | OXC_STATUS_PEER_TIMEOUT))
+    return fail(OXC_E_CAPACITY, "device status 0x%x:%s%s%s%s%s", f, (f & OXC_STATUS_MESHLET_OVERFLOW) ? " cull_meshes exceeded max_meshlet_instances (clamped)" : "",
                 (f & OXC_STATUS_SURVIVOR_OVERFLOW) ? " a survivor list exceeded the gather capacity (truncated)" : "",
-                (f & OXC_STATUS_ID_OVERFLOW) ? " a meshlet-instance id overflowed the vis-buffer id bits" : "");
+                (f & OXC_STATUS_ID_OVERFLOW) ? " a meshlet-instance id overflowed the vis-buffer id bits" : "",
+                (f & OXC_STATUS_CLIP_OVERFLOW) ? " the clip queue overflowed (run oxc_raster_visbuffer_clip_pass)" : "",
+                (f & OXC_STATUS_PEER_TIMEOUT) ? " a peer GPU did not signal its Hi-Z exchange in time" : "");
   return fail(OXC_E_INVALID, "device status 0x%x: malformed geometry (micro index >= vertex_count or vertex index >= Mesh::vertex_count); such triangles are skipped", f);
 }
 

@@ -203,7 +203,7 @@ def test_small_primitive_cull_parity(capi, orc):
     np.testing.assert_array_equal(images[0], images[1])
     assert counts[0] == len(full_idx) // 3 and counts[1] == counts[0] - culled
     ref_img = orc.clear_visbuffer(w, h)
-    orc.raster(hs, mi, ref_vis, 0, n, cam, ref_img)
+    orc.raster_clip(hs, mi, ref_vis, 0, n, cam, ref_img)  # the product's raster clips what the plain spec drops
     np.testing.assert_array_equal(images[1].reshape(h, w), ref_img)
     ctx.free(vis_dev)
     ctx.close()
@@ -229,7 +229,7 @@ def test_wide_id_packing_and_24_bit_refusal(capi, orc):
     ref_vis, cmd = orc.cull_meshlets(hs, mi, vis, cam)
     n = int(cmd["x"][0])
     ref_img = orc.clear_visbuffer(w, h)
-    orc.raster(hs, mi, ref_vis, 0, n, cam, ref_img)
+    orc.raster_clip(hs, mi, ref_vis, 0, n, cam, ref_img)  # the product's raster clips what the plain spec drops
     data = (ref_img & 0xFFFFFFFF).astype(np.uint64)
     drawn = data != 0xFFFFFFFF
     repacked = np.where(drawn, (((data >> 8) + base) << 6) | (data & 0xFF), data)
@@ -1088,7 +1088,7 @@ def test_raster_big_triangle_queue_and_overflow(capi, orc):
     mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
     visible = np.zeros(1, dtype=np.uint32)
     ref = orc.clear_visbuffer(W, H)
-    ntri = orc.raster(hs, mi, visible, 0, 1, cam, ref)
+    ntri, _ = orc.raster_clip(hs, mi, visible, 0, 1, cam, ref)
     assert ntri == 2 and (ref != 0xFFFFFFFF).sum() > 10000
     for cap in (None, 5, 12, 1):
         if cap is None:
@@ -1113,15 +1113,17 @@ def test_raster_big_triangle_queue_and_overflow(capi, orc):
 
 
 def test_clip_pass_parity(capi, orc):
-    """opt-in clip pass vs the oracle's clipped raster: a ground plane through the camera (coarse: 2 huge triangles; medium:
-    24x24 quads, some of them crossing the near / side planes), drawn by oxc_raster_visbuffer + oxc_raster_visbuffer_clip_pass"""
+    """Near / side-plane clipping vs the oracle's clipped raster: a ground plane through the camera (coarse: 2 huge triangles;
+    medium: 24x24 quads, some of them crossing the near / side planes).  oxc_raster_visbuffer queues the triangles the plain
+    rules drop and clips them itself; the stand-alone oxc_raster_visbuffer_clip_pass on top changes nothing; with the queue
+    exhausted (1 entry) the status word says so and the stand-alone pass completes the image."""
+    import os
     from tests.test_oracle_clip import ground_scene
 
     for cells in (1, 24):
         sc = ground_scene(cells, width=640, height=360)
         hs = orc.HostScene(sc)
         cam = sc.camera()
-        ctx = make_ctx(capi, sc)
         w, h = sc.width, sc.height
         mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
         visible, cmd = orc.cull_meshlets(hs, mi, vis, cam)
@@ -1129,21 +1131,35 @@ def test_clip_pass_parity(capi, orc):
         ref = orc.clear_visbuffer(w, h)
         ntri, nclip = orc.raster_clip(hs, mi, visible, 0, len(visible), cam, ref)
         assert nclip > 0
-        vis_dev = ctx.alloc(w * h * 8)
-        ctx.clear_visbuffer(vis_dev, w, h)
-        ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
-        ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
-        ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
-        plain = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
-        ctx.raster_visbuffer_clip_pass(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
-        got = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
         ref_plain = orc.clear_visbuffer(w, h)
         orc.raster(hs, mi, visible, 0, len(visible), cam, ref_plain)
-        np.testing.assert_array_equal(plain, ref_plain)
-        np.testing.assert_array_equal(got, ref)
-        assert ctx.raster_triangle_count() == ntri
-        ctx.free(vis_dev)
-        ctx.close()
+        assert not np.array_equal(ref, ref_plain)  # the clipped triangles do cover pixels
+        for capacity in (None, "1"):
+            if capacity:
+                os.environ["OXC_CLIP_CAPACITY"] = capacity
+            try:
+                ctx = make_ctx(capi, sc)
+            finally:
+                os.environ.pop("OXC_CLIP_CAPACITY", None)
+            vis_dev = ctx.alloc(w * h * 8)
+            ctx.clear_visbuffer(vis_dev, w, h)
+            ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+            ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
+            ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+            got = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
+            if capacity is None:
+                np.testing.assert_array_equal(got, ref)
+                assert ctx.check_status() == 0
+            elif nclip > 1:
+                assert ctx.status_flags() & abi.STATUS_CLIP_OVERFLOW
+                with pytest.raises(capi.OxcError):
+                    ctx.check_status()
+            ctx.raster_visbuffer_clip_pass(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+            got = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
+            np.testing.assert_array_equal(got, ref)
+            assert ctx.raster_triangle_count() == ntri
+            ctx.free(vis_dev)
+            ctx.close()
 
 
 def test_plain_c_host_runs(capi, tmp_path):
