@@ -479,6 +479,37 @@ int oxc_mgpu_stage_survivors(OxcContext* ctx, int slot, void* stream);
 int oxc_mgpu_exchange_frame(OxcContext* ctx, uint64_t* vis_dev /* may be NULL */, uint32_t width, uint32_t height, int slot,
                             uint32_t flags, void* stream);
 
+/* VSM page marking: passes/rmvsm_mark_visible_pages.slang:19-84 dispatched by Shadowmaps.cpp after the depth
+ * pre-pass.  One thread per depth pixel (depth == 0 = sky, skipped): unproject (scene.slang:189-193), clipmap level from the
+ * world-space footprint of the pixel diagonal (rmvsm.slang:156-186: log2(d / first_clipmap_texel_length), bias, clamp),
+ * project into that clipmap (rmvsm.slang:214-221), page coordinates (:200-206) wrapped by the clipmap's page offset (:129-138),
+ * then  prev = atomicOr(page_table[layer][y][x], Visible);  a page that was not visible before is either recorded in
+ * page_occupancy[physical address] (already backed) or pushed as an allocation request {x, y, layer}.
+ * Canonical arithmetic as everywhere (IEEE f32, no contraction); log2 is the library's own polynomial evaluated with those
+ * operations (oxc_exact.cuh canonical_log2 == oracle orc_log2_canonical), so CPU oracle and GPU agree bit for bit — the
+ * reference's driver log2 under SLANG fast-math is not bit-defined either.  Deviation: pixels whose page coordinates are
+ * invalid are skipped; the reference's wave-scalarisation loop lets the first lane of a wave through with them (:64-74), an
+ * out-of-bounds image atomic whose effect depends on the wave composition.
+ * Request ORDER is unspecified (atomics), as in the reference. */
+typedef struct OxcVsmContext { /* rmvsm.slang:116-127 VSMContext, scalar layout */
+  int32_t page_size;
+  int32_t page_table_size;
+  int32_t physical_page_table_size;
+  int32_t curr_clipmap_index;
+  int32_t clipmap_count;          /* <= 10 (shared_clipmaps[10], :17) */
+  int32_t depth_extent[2];
+  float first_clipmap_width;
+  float clipmap_selection_bias;
+  float virtual_extent;
+  float z_length;
+  float directional_light_dir[3];
+} OxcVsmContext;
+int oxc_mark_visible_pages(OxcContext* ctx, const float inv_projection_view[16] /* Camera::inv_projection_view, column-major */,
+                           const float resolution[2], const OxcVirtualClipmap* clipmaps /* host, clipmap_count entries */,
+                           const OxcVsmContext* vsm, const float* depth_dev, uint32_t* page_tables_dev /* [clipmap][size][size] */,
+                           uint32_t* page_occupancy_dev, uint32_t* request_count_dev, int32_t* requests_dev /* int3 per request */,
+                           uint32_t request_capacity, void* stream);
+
 int oxc_get_outputs(OxcContext* ctx, OxcOutputs* out);
 /* Instrumentation hook: 128 u64 counters that builds with -DOXC_RASTER_STATS fill (tools/raster_stats.py); zero otherwise. */
 void* oxc_debug_stats_ptr(OxcContext* ctx);

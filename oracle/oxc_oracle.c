@@ -888,6 +888,85 @@ void orc_build_hpb(const uint32_t* page_table, uint32_t size, uint32_t layers, u
 }
 
 /* ------------------------------------------------------------------------------------------------
+ * VSM page marking — passes/rmvsm_mark_visible_pages.slang:19-84 with rmvsm.slang:116-221.
+ * log2 is the canonical polynomial below (strict f32 operations: the CUDA side evaluates the very same sequence).
+ * ---------------------------------------------------------------------------------------------- */
+float orc_log2_canonical(float x) {
+  if (!(x > 0.0f)) return -3.0e38f;              /* zero, negative, NaN */
+  if (!(x <= 3.0e38f)) return 3.0e38f;           /* +inf */
+  int32_t e = 0;
+  if (x < 1.17549435e-38f) { x = x * 16777216.0f; e = -24; } /* denormal: scale into the normal range (exact) */
+  uint32_t bits = f2bits(x);
+  e += (int32_t)(bits >> 23) - 127;
+  float m = bits2f((bits & 0x007FFFFFu) | 0x3F800000u); /* [1, 2) */
+  if (m > 1.41421354f) { m = m * 0.5f; e += 1; }        /* [0.7071, 1.4142] */
+  const float t = (m - 1.0f) / (m + 1.0f);
+  const float t2 = t * t;
+  /* log2(m) = 2/ln2 * (t + t^3/3 + t^5/5 + t^7/7 + ...) */
+  float p = 0.412198562f;                        /* 2/(7 ln 2) */
+  p = 0.577078044f + t2 * p;                     /* 2/(5 ln 2) */
+  p = 0.961796701f + t2 * p;                     /* 2/(3 ln 2) */
+  p = 2.88539004f + t2 * p;                      /* 2/ln 2 */
+  return (float)e + t * p;
+}
+
+static Vec4_f32 unproject_uv_h(const float inv_pv[16], float u, float v, float depth) { /* scene.slang:189-193 */
+  Vec4_f32 ndc = {u * 2.0f - 1.0f, v * 2.0f - 1.0f, depth, 1.0f};
+  Vec4_f32 h = mul_mv_f32(inv_pv, ndc);
+  Vec4_f32 w = {h.x / h.w, h.y / h.w, h.z / h.w, 1.0f};
+  return w;
+}
+
+void orc_mark_visible_pages(const float inv_pv[16], const float resolution[2], const OxcVirtualClipmap* clipmaps,
+                            const OxcVsmContext* vsm, const float* depth, uint32_t* page_tables, uint32_t* page_occupancy,
+                            uint32_t* request_count, int32_t* requests, uint32_t request_capacity) {
+  const int32_t W = vsm->depth_extent[0], H = vsm->depth_extent[1], size = vsm->page_table_size;
+  /* rmvsm.slang:147-154 get_first_clipmap_texel_length */
+  const float scale_ratio = (float)(size - 1) / (float)size;
+  const float effective_width = vsm->first_clipmap_width * scale_ratio;
+  const float texel_length = (effective_width * 2.0f) / vsm->virtual_extent;
+  for (int32_t y = 0; y < H; y++)
+    for (int32_t x = 0; x < W; x++) {
+      const float d = depth[(size_t)y * W + x];
+      if (d == 0.0f) continue;                                                        /* :43-45 */
+      const float u = ((float)x + 0.5f) / (float)W, v = ((float)y + 0.5f) / (float)H;  /* :47 */
+      const Vec4_f32 wp = unproject_uv_h(inv_pv, u, v, d);
+      /* :156-186 (VMS_USE_DIAG_PIXEL_FOOTPRINT): distance between the unprojected left / right ends of the pixel */
+      const float ox = (1.0f / resolution[0]) * 0.5f, oy = (1.0f / resolution[1]) * 0.5f;
+      const Vec4_f32 a = unproject_uv_h(inv_pv, u - ox, v + oy, d), b = unproject_uv_h(inv_pv, u + ox, v + oy, d);
+      const float dx = a.x - b.x, dy = a.y - b.y, dz = a.z - b.z;
+      const float dist = sqrtf((dx * dx + dy * dy) + dz * dz);
+      float level_f = orc_log2_canonical(dist / texel_length);
+      level_f = level_f > 0.0f ? level_f : 0.0f;                                      /* max(level_f, 0) */
+      const float lf = ceilf(vsm->clipmap_selection_bias + level_f);
+      uint32_t ci = lf >= 4294967296.0f ? 0xFFFFFFFFu : (lf > 0.0f ? (uint32_t)lf : 0u); /* u32() saturates */
+      if (ci > (uint32_t)(vsm->clipmap_count - 1)) ci = (uint32_t)(vsm->clipmap_count - 1);
+      const OxcVirtualClipmap* cm = &clipmaps[ci];
+      Vec4_f32 wp1 = {wp.x, wp.y, wp.z, 1.0f};
+      const Vec4_f32 lh = mul_mv_f32(cm->projection_view_mat, wp1);                   /* :214-221 */
+      const float cu = (lh.x / lh.w + 1.0f) * 0.5f, cv = (lh.y / lh.w + 1.0f) * 0.5f;
+      if (cu < 0.0f || cv < 0.0f || cu > 1.0f || cv > 1.0f) continue;                  /* :200-203 (NaN passes, as in the shader) */
+      const float fxv = floorf(cu * (float)size), fyv = floorf(cv * (float)size);
+      const int32_t vx = to_i32_f32(fxv), vy = to_i32_f32(fyv);
+      if (vx < 0 || vy < 0 || vx > size - 1 || vy > size - 1) continue;               /* :129-133 */
+      /* com::mod(offset, size) on floats: x - y * floor(x / y)  (common/math.slang:99-101) */
+      const float fox = (float)(vx + cm->page_offset[0]), foy = (float)(vy + cm->page_offset[1]), fs = (float)size;
+      const int32_t wx = to_i32_f32(fox - fs * floorf(fox / fs)), wy = to_i32_f32(foy - fs * floorf(foy / fs));
+      if (wx < 0 || wy < 0 || wx > size - 1 || wy > size - 1) continue;
+      uint32_t* page = &page_tables[((size_t)ci * size + (size_t)wy) * size + (size_t)wx];
+      const uint32_t prev = *page;
+      *page = prev | 1u;                                                              /* VSMPageState.Visible */
+      if (!(prev & 1u)) {
+        if (prev & 4u) page_occupancy[prev >> 16] = 1u;                               /* backed: :76-80 */
+        else {
+          const uint32_t k = (*request_count)++;                                      /* :81-82 */
+          if (k < request_capacity) { requests[k * 3 + 0] = wx; requests[k * 3 + 1] = wy; requests[k * 3 + 2] = (int32_t)ci; }
+        }
+      }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
  * passes/visbuffer_decode.slang:42-183, geometry part: vis texel -> triangle re-fetch ->
  * analytic barycentrics + screen-space derivatives (compute_partial_derivatives :42-92), interpolated
  * texture coordinate with its gradients (:33-40,118-125 without the material's uv transform), geometric

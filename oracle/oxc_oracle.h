@@ -109,6 +109,12 @@ void orc_cull_triangles(const OrcScene* scene, const OxcMeshletInstance* meshlet
 /* SW raster (spec in DESIGN.md §raster): same triangle cull, then rasterise with
  * max on asuint(depth)<<32 | (id<<8 | tri).  vis must be pre-cleared (orc_clear_visbuffer). */
 void orc_clear_visbuffer(uint64_t* vis, uint32_t width, uint32_t height);
+/* VSM page marking (rmvsm_mark_visible_pages.slang) and the canonical log2 it uses */
+float orc_log2_canonical(float x);
+void orc_mark_visible_pages(const float inv_projection_view[16], const float resolution[2], const OxcVirtualClipmap* clipmaps,
+                            const OxcVsmContext* vsm, const float* depth, uint32_t* page_tables, uint32_t* page_occupancy,
+                            uint32_t* request_count, int32_t* requests, uint32_t request_capacity);
+
 /* north_star's small-primitive cull (opt-in; no reference equivalent): specification in oxc_oracle.c */
 int orc_triangle_covers_no_sample(const float clip[3][4], uint32_t width, uint32_t height);
 uint64_t orc_cull_triangles_small_primitive(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,

@@ -270,6 +270,22 @@ def build_hpb(page_table, levels):
     return out
 
 
+def log2_canonical(x):
+    fn = lib().orc_log2_canonical
+    fn.restype = C.c_float
+    return float(fn(C.c_float(x)))
+
+
+def mark_visible_pages(inv_pv, resolution, clipmaps, vsm, depth, page_tables, occupancy, request_capacity):
+    """rmvsm_mark_visible_pages.slang: updates page_tables / occupancy in place; returns the allocation requests [n, 3]."""
+    count = np.zeros(1, dtype=np.uint32)
+    req = np.zeros((max(1, request_capacity), 3), dtype=np.int32)
+    lib().orc_mark_visible_pages(_p(np.ascontiguousarray(inv_pv, dtype=np.float32)), _p(np.ascontiguousarray(resolution, dtype=np.float32)),
+                                 _p(np.ascontiguousarray(clipmaps)), _p(np.ascontiguousarray(vsm)), _p(np.ascontiguousarray(depth, dtype=np.float32)),
+                                 _p(page_tables), _p(occupancy), _p(count), _p(req), C.c_uint32(request_capacity))
+    return req[: min(int(count[0]), request_capacity)], int(count[0])
+
+
 def decode_visbuffer(hs, mi, total, cam, vis32):
     """Five (H, W, 4) f32 planes: lambda(+status), ddx, ddy, uv_normal, uv_grad."""
     v = np.ascontiguousarray(vis32, dtype=np.uint32)

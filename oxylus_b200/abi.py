@@ -182,6 +182,13 @@ class Outputs(C.Structure):
     ]
 
 
+VSM_CONTEXT_DT = np.dtype([("page_size", "<i4"), ("page_table_size", "<i4"), ("physical_page_table_size", "<i4"), ("curr_clipmap_index", "<i4"),
+                           ("clipmap_count", "<i4"), ("depth_extent", "<i4", (2,)), ("first_clipmap_width", "<f4"),
+                           ("clipmap_selection_bias", "<f4"), ("virtual_extent", "<f4"), ("z_length", "<f4"),
+                           ("directional_light_dir", "<f4", (3,))])
+assert VSM_CONTEXT_DT.itemsize == 56
+
+
 class MgpuInfo(C.Structure):
     """OxcMgpuInfo"""
 

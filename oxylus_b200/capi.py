@@ -19,7 +19,7 @@ SYMBOLS = [
     "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_set_shard_auto", "oxc_cull_meshes",
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_cull_triangles_small_primitive", "oxc_clear_visbuffer",
     "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
-    "oxc_decode_visbuffer", "oxc_build_hpb",
+    "oxc_decode_visbuffer", "oxc_build_hpb", "oxc_mark_visible_pages",
     "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_debug_stats_ptr",
     "oxc_mgpu_get_unique_id", "oxc_mgpu_init", "oxc_mgpu_init_with_comm", "oxc_mgpu_shutdown", "oxc_mgpu_info", "oxc_mgpu_exchange_hiz",
     "oxc_mgpu_exchange_frame", "oxc_mgpu_stage_survivors", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
@@ -79,6 +79,7 @@ def load(build_if_missing=True):
     lib.oxc_cull_terrain.argtypes = [vp, vp, vp, vp, u32, vp, vp, vp, vp]
     lib.oxc_decode_visbuffer.argtypes = [vp, vp, vp, vp, u32, u32, C.POINTER(abi.DecodeTargets), vp]
     lib.oxc_build_hpb.argtypes = [vp, vp, u32, u32, vp, u32, vp]
+    lib.oxc_mark_visible_pages.argtypes = [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, u32, vp]
     lib.oxc_get_outputs.argtypes = [vp, C.POINTER(abi.Outputs)]
     lib.oxc_check_status.argtypes = [vp, vp, C.POINTER(C.c_uint32)]
     lib.oxc_mark_hiz_dirty.argtypes = [vp]
@@ -343,6 +344,16 @@ class Context:
         t = abi.DecodeTargets(*[targets.get(k) for k in ("lambda_", "ddx", "ddy", "uv_normal", "uv_grad")])
         _check(self.lib.oxc_decode_visbuffer(self.h, _ptr(cam), _ptr(vis64_dev), _ptr(vis32_dev), w, h, C.byref(t), self.stream),
                "oxc_decode_visbuffer")
+
+    def mark_visible_pages(self, inv_pv, resolution, clipmaps, vsm, depth_dev, page_tables_dev, occupancy_dev, request_count_dev, requests_dev,
+                           request_capacity):
+        ipv = np.ascontiguousarray(inv_pv, dtype=np.float32)
+        res = np.ascontiguousarray(resolution, dtype=np.float32)
+        cm = np.ascontiguousarray(clipmaps)
+        vc = np.ascontiguousarray(vsm)
+        _check(self.lib.oxc_mark_visible_pages(self.h, _ptr(ipv), _ptr(res), _ptr(cm), _ptr(vc), _ptr(depth_dev), _ptr(page_tables_dev),
+                                               _ptr(occupancy_dev), _ptr(request_count_dev), _ptr(requests_dev), request_capacity, self.stream),
+               "oxc_mark_visible_pages")
 
     def build_hpb(self, page_table_dev, size, layers, hpb_dev, levels):
         _check(self.lib.oxc_build_hpb(self.h, _ptr(page_table_dev), size, layers, _ptr(hpb_dev), levels, self.stream), "oxc_build_hpb")

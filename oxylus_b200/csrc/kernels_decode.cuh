@@ -234,4 +234,87 @@ __global__ void k_hpb_level(const uint32_t* page_table, const uint8_t* src, uint
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// VSM page marking — passes/rmvsm_mark_visible_pages.slang:19-84 (+ rmvsm.slang:116-221).  One thread per depth pixel.
+// Lanes of a warp that hit the same page table entry elect one of them for the atomic (the reference's scalarisation loop,
+// :64-74, done with match.any): pixels are coherent, so a warp usually touches one or two pages.
+// ------------------------------------------------------------------------------------------------
+struct VsmMarkParams {
+  float4 inv_pv_row[4];       // rows of Camera::inv_projection_view
+  float inv_res_half[2];      // (1 / resolution) * 0.5
+  float clipmap_row[10][4][4];// rows of every clipmap's projection_view_mat
+  int page_offset[10][2];
+  const float* depth;
+  uint32_t* page_tables;
+  uint32_t* page_occupancy;
+  uint32_t* request_count;
+  int* requests;
+  uint32_t request_capacity;
+  int width, height, size, clipmap_count;
+  float texel_length, bias;
+};
+
+OXC_DI void vsm_unproject(const VsmMarkParams& p, float u, float v, float depth, float& x, float& y, float& z) {
+  const float nx = fs(fm(u, 2.0f), 1.0f), ny = fs(fm(v, 2.0f), 1.0f);
+  const float hx = row_dot4(p.inv_pv_row[0], nx, ny, depth, 1.0f), hy = row_dot4(p.inv_pv_row[1], nx, ny, depth, 1.0f);
+  const float hz = row_dot4(p.inv_pv_row[2], nx, ny, depth, 1.0f), hw = row_dot4(p.inv_pv_row[3], nx, ny, depth, 1.0f);
+  x = fd(hx, hw); y = fd(hy, hw); z = fd(hz, hw);
+}
+
+__global__ void __launch_bounds__(256) k_vsm_mark_visible_pages(const __grid_constant__ VsmMarkParams p) {
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  uint32_t address = 0xFFFFFFFFu; // page table entry this pixel marks (none)
+  int wx = 0, wy = 0, ci_out = 0;
+  if (x < p.width && y < p.height) {
+    const float d = __ldg(&p.depth[(size_t)y * p.width + x]);
+    if (d != 0.0f) {                                                                             // :43-45
+      const float u = fd(fa((float)x, 0.5f), (float)p.width), v = fd(fa((float)y, 0.5f), (float)p.height); // :47
+      float wxp, wyp, wzp;
+      vsm_unproject(p, u, v, d, wxp, wyp, wzp);
+      float ax, ay, az, bx, by, bz;                                                              // :156-186
+      vsm_unproject(p, fs(u, p.inv_res_half[0]), fa(v, p.inv_res_half[1]), d, ax, ay, az);
+      vsm_unproject(p, fa(u, p.inv_res_half[0]), fa(v, p.inv_res_half[1]), d, bx, by, bz);
+      const float dx = fs(ax, bx), dy = fs(ay, by), dz = fs(az, bz);
+      const float dist = fsq(fa(fa(fm(dx, dx), fm(dy, dy)), fm(dz, dz)));
+      float level_f = canonical_log2(fd(dist, p.texel_length));
+      level_f = level_f > 0.0f ? level_f : 0.0f;
+      const float lf = ceilf(fa(p.bias, level_f));
+      uint32_t ci = lf >= 4294967296.0f ? 0xFFFFFFFFu : (lf > 0.0f ? __float2uint_rz(lf) : 0u);
+      ci = ci > (uint32_t)(p.clipmap_count - 1) ? (uint32_t)(p.clipmap_count - 1) : ci;
+      const float(*cr)[4] = p.clipmap_row[ci];
+      const float lx = fa(fa(fa(fm(cr[0][0], wxp), fm(cr[0][1], wyp)), fm(cr[0][2], wzp)), fm(cr[0][3], 1.0f));
+      const float ly = fa(fa(fa(fm(cr[1][0], wxp), fm(cr[1][1], wyp)), fm(cr[1][2], wzp)), fm(cr[1][3], 1.0f));
+      const float lw = fa(fa(fa(fm(cr[3][0], wxp), fm(cr[3][1], wyp)), fm(cr[3][2], wzp)), fm(cr[3][3], 1.0f));
+      const float cu = fm(fa(fd(lx, lw), 1.0f), 0.5f), cv = fm(fa(fd(ly, lw), 1.0f), 0.5f);     // :214-221
+      if (!(cu < 0.0f || cv < 0.0f || cu > 1.0f || cv > 1.0f)) {                                  // :200-203
+        const float fsz = (float)p.size;
+        const float fxv = floorf(fm(cu, fsz)), fyv = floorf(fm(cv, fsz));
+        const int vx = !(fxv == fxv) ? 0 : (fxv >= 2147483648.0f ? INT_MAX : (fxv <= -2147483648.0f ? INT_MIN : (int)fxv));
+        const int vy = !(fyv == fyv) ? 0 : (fyv >= 2147483648.0f ? INT_MAX : (fyv <= -2147483648.0f ? INT_MIN : (int)fyv));
+        if (!(vx < 0 || vy < 0 || vx > p.size - 1 || vy > p.size - 1)) {                          // :129-133
+          const float fox = (float)(vx + p.page_offset[ci][0]), foy = (float)(vy + p.page_offset[ci][1]);
+          wx = (int)fs(fox, fm(fsz, floorf(fd(fox, fsz))));                                       // com::mod, common/math.slang:99-101
+          wy = (int)fs(foy, fm(fsz, floorf(fd(foy, fsz))));
+          if (!(wx < 0 || wy < 0 || wx > p.size - 1 || wy > p.size - 1)) {
+            address = ((uint32_t)ci * p.size + (uint32_t)wy) * p.size + (uint32_t)wx;
+            ci_out = (int)ci;
+          }
+        }
+      }
+    }
+  }
+  // one atomic per distinct page table entry per warp (:64-74)
+  const uint32_t peers = __match_any_sync(0xffffffffu, address);
+  if (address != 0xFFFFFFFFu && (threadIdx.x & 31) == (uint32_t)(__ffs(peers) - 1)) {
+    const uint32_t prev = atomicOr(&p.page_tables[address], 1u); // VSMPageState.Visible
+    if (!(prev & 1u)) {                                          // the page became visible this frame (:76-83)
+      if (prev & 4u) p.page_occupancy[prev >> 16] = 1u;          // already backed: keep the allocator off it
+      else {
+        const uint32_t k = atomicAdd(p.request_count, 1u);
+        if (k < p.request_capacity) { p.requests[k * 3 + 0] = wx; p.requests[k * 3 + 1] = wy; p.requests[k * 3 + 2] = ci_out; }
+      }
+    }
+  }
+}
+
 } // namespace oxc

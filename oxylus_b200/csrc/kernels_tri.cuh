@@ -448,6 +448,7 @@ __global__ void __launch_bounds__(256) k_raster_big(const __grid_constant__ TriP
   }
 }
 
+template <bool PREFETCH_GRAB>
 __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_visbuffer(const __grid_constant__ TriParams p) {
   __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   __shared__ ScreenVert scr_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
@@ -471,17 +472,38 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
   // counter each cut the late pass (119 -> 97 us) but cost the early pass more (365 -> 388..421 us: the extra scheduler
   // state spills at the 64-register cap), so the single counter stays.
   const uint32_t n_warps2 = gridDim.x * TRI_WARPS * 2u;
+  // PREFETCH_GRAB (late pass): the grab for the NEXT batch is issued before the current batch is processed, so the atomic's
+  // round trip (measured ~7 us in the late pass: every warp of the GPU on one address, few meshlets per warp) overlaps a batch
+  // of rasterisation.  A/B on B200: late pass 114 -> 98 us; the early pass (55 meshlets per warp, 12 grabs) loses more balance
+  // from the batch each warp holds in reserve than it gains (375 -> 400 us), so it keeps the plain grab.
+  uint32_t g_next = 0, batch_next = 1;
+  if (PREFETCH_GRAB && lane == 0) {
+    batch_next = min((uint32_t)RASTER_BATCH, max(1u, count / n_warps2));
+    g_next = atomicAdd(p.work_counter, batch_next);
+  }
   for (;;) {
     uint32_t g0 = 0, batch = 1;
-    if (lane == 0) {
-      const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(p.work_counter); // heuristic only: a stale value is harmless
-      const uint32_t rem = count > seen ? count - seen : 0u;
-      batch = min((uint32_t)RASTER_BATCH, max(1u, rem / n_warps2));
-      g0 = atomicAdd(p.work_counter, batch);
+    if (PREFETCH_GRAB) {
+      g0 = __shfl_sync(0xffffffffu, g_next, 0);
+      batch = __shfl_sync(0xffffffffu, batch_next, 0);
+      if (g0 >= count) break;
+      if (lane == 0) { // reserve the following batch now; its index is not needed before the next iteration
+        const uint32_t seen = g0 + batch; // what had been handed out when this batch was reserved (a lower bound now)
+        const uint32_t rem = count > seen ? count - seen : 0u;
+        batch_next = min((uint32_t)RASTER_BATCH, max(1u, rem / n_warps2));
+        g_next = atomicAdd(p.work_counter, batch_next);
+      }
+    } else {
+      if (lane == 0) {
+        const uint32_t seen = *reinterpret_cast<volatile uint32_t*>(p.work_counter); // heuristic only: a stale value is harmless
+        const uint32_t rem = count > seen ? count - seen : 0u;
+        batch = min((uint32_t)RASTER_BATCH, max(1u, rem / n_warps2));
+        g0 = atomicAdd(p.work_counter, batch);
+      }
+      g0 = __shfl_sync(0xffffffffu, g0, 0);
+      batch = __shfl_sync(0xffffffffu, batch, 0);
+      if (g0 >= count) break;
     }
-    g0 = __shfl_sync(0xffffffffu, g0, 0);
-    batch = __shfl_sync(0xffffffffu, batch, 0);
-    if (g0 >= count) break;
     const uint32_t nb = min(batch, count - g0);
     const uint32_t my_survivor = g0 + lane;
 #ifdef OXC_RASTER_STATS

@@ -224,6 +224,26 @@ OXC_DI bool test_frustum_rows(const float4 planes[6], float cx, float cy, float 
   return true;
 }
 
+// log2 for decision paths (VSM clipmap selection): the same operation sequence as oracle/oxc_oracle.c orc_log2_canonical, so the
+// result is bit-identical on both sides.  |error| < 1e-7 absolute on [2^-126, 2^127].
+OXC_DI float canonical_log2(float x) {
+  if (!(x > 0.0f)) return -3.0e38f;
+  if (!(x <= 3.0e38f)) return 3.0e38f;
+  int e = 0;
+  if (x < 1.17549435e-38f) { x = fm(x, 16777216.0f); e = -24; }
+  const uint32_t bits = __float_as_uint(x);
+  e += (int)(bits >> 23) - 127;
+  float m = __uint_as_float((bits & 0x007FFFFFu) | 0x3F800000u);
+  if (m > 1.41421354f) { m = fm(m, 0.5f); e += 1; }
+  const float t = fd(fs(m, 1.0f), fa(m, 1.0f));
+  const float t2 = fm(t, t);
+  float p = 0.412198562f;
+  p = fa(0.577078044f, fm(t2, p));
+  p = fa(0.961796701f, fm(t2, p));
+  p = fa(2.88539004f, fm(t2, p));
+  return fa((float)e, fm(t, p));
+}
+
 // cull.slang:169-171: determinant(f32x3x3(c0.xyw, c1.xyw, c2.xyw)) >= 0.0001
 OXC_DI bool triangle_backface(float4 c0, float4 c1, float4 c2) {
   const float m00 = c0.x, m01 = c0.y, m02 = c0.w;

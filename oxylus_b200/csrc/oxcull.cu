@@ -346,7 +346,7 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
 #undef OCCC
   c->occ_cull[0][0][1] = c->occ_cull[0][1][0] = c->occ_cull[0][1][1] = c->occ_cull[0][0][0];
   OCC(c->occ_tri, k_cull_triangles, TRI_THREADS);
-  OCC(c->occ_raster, k_raster_visbuffer, TRI_THREADS);
+  OCC(c->occ_raster, k_raster_visbuffer<false>, TRI_THREADS);
   OCC(c->occ_mv, k_cull_meshlets_multiview, CULL_THREADS);
 #undef OCC
   *out_ctx = c;
@@ -746,7 +746,8 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
   p.clip_queue = c->d_clip_queue; p.clip_counter = c->d_clip_counter; p.clip_capacity = c->clip_capacity;
   CK(cudaMemsetAsync(c->d_big_counters, 0, 8, s));
   CK(cudaMemsetAsync(c->d_clip_counter, 0, 4, s));
-  k_raster_visbuffer<<<grid, TRI_THREADS, 0, s>>>(p);
+  if (p.late) k_raster_visbuffer<true><<<grid, TRI_THREADS, 0, s>>>(p);
+  else k_raster_visbuffer<false><<<grid, TRI_THREADS, 0, s>>>(p);
   LAUNCHED();
   k_raster_clip_queue<<<c->sm_count, 128, 0, s>>>(p); // the triangles the plain rules drop (usually none: exits at once)
   LAUNCHED();
@@ -956,6 +957,40 @@ int oxc_decode_visbuffer(OxcContext* c, const OxcCullCamera* cam, const uint64_t
   p.width = w; p.height = h; p.prim_bits = c->prim_bits;
   const dim3 grid((w + DECODE_TX - 1) / DECODE_TX, (h + DECODE_TY - 1) / DECODE_TY);
   k_decode_visbuffer<<<grid, dim3(DECODE_TX, DECODE_TY), 0, s>>>(p);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+int oxc_mark_visible_pages(OxcContext* c, const float inv_pv[16], const float resolution[2], const OxcVirtualClipmap* clipmaps,
+                           const OxcVsmContext* vsm, const float* depth_dev, uint32_t* page_tables_dev, uint32_t* page_occupancy_dev,
+                           uint32_t* request_count_dev, int32_t* requests_dev, uint32_t request_capacity, void* stream) {
+  if (!c || !inv_pv || !resolution || !clipmaps || !vsm || !depth_dev || !page_tables_dev || !page_occupancy_dev || !request_count_dev || !requests_dev)
+    return fail(OXC_E_INVALID, "null argument");
+  if (vsm->clipmap_count < 1 || vsm->clipmap_count > 10 || vsm->page_table_size < 1 || vsm->depth_extent[0] < 1 || vsm->depth_extent[1] < 1)
+    return fail(OXC_E_INVALID, "bad VSMContext (clipmap_count 1..10, page_table_size >= 1)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  VsmMarkParams p{};
+  for (int i = 0; i < 4; i++) p.inv_pv_row[i] = make_float4(inv_pv[i], inv_pv[4 + i], inv_pv[8 + i], inv_pv[12 + i]);
+  // (1.0 / resolution) * 0.5 and the texel length with the oracle's operation order (host floats: IEEE, no contraction)
+  p.inv_res_half[0] = (1.0f / resolution[0]) * 0.5f; p.inv_res_half[1] = (1.0f / resolution[1]) * 0.5f;
+  for (int k = 0; k < vsm->clipmap_count; k++) {
+    for (int i = 0; i < 4; i++)
+      for (int j = 0; j < 4; j++) p.clipmap_row[k][i][j] = clipmaps[k].projection_view_mat[j * 4 + i];
+    p.page_offset[k][0] = clipmaps[k].page_offset[0]; p.page_offset[k][1] = clipmaps[k].page_offset[1];
+  }
+  p.depth = depth_dev; p.page_tables = page_tables_dev; p.page_occupancy = page_occupancy_dev; p.request_count = request_count_dev;
+  p.requests = requests_dev; p.request_capacity = request_capacity;
+  p.width = vsm->depth_extent[0]; p.height = vsm->depth_extent[1]; p.size = vsm->page_table_size; p.clipmap_count = vsm->clipmap_count;
+  {  // rmvsm.slang:147-154
+    volatile float scale_ratio = (float)(vsm->page_table_size - 1) / (float)vsm->page_table_size;
+    volatile float effective_width = vsm->first_clipmap_width * scale_ratio;
+    volatile float twice = effective_width * 2.0f;
+    p.texel_length = twice / vsm->virtual_extent;
+  }
+  p.bias = vsm->clipmap_selection_bias;
+  const dim3 grid((p.width + 31) / 32, (p.height + 7) / 8);
+  k_vsm_mark_visible_pages<<<grid, 256, 0, s>>>(p);
   LAUNCHED();
   return OXC_OK;
 }

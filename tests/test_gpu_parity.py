@@ -944,6 +944,39 @@ def test_build_hpb_parity(capi, orc):
     ctx.close()
 
 
+def test_mark_visible_pages_parity(capi, orc):
+    """rmvsm_mark_visible_pages.slang equivalent vs the oracle on a 1920x1080 depth image of a ground plane: page tables and
+    occupancy bit for bit, allocation requests as a set (push order is atomics order in the reference too)."""
+    from tests.test_oracle_units import make_vsm_case
+
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    ctx = make_ctx(capi, sc)
+    for (w, h, size) in ((1920, 1080, 64), (333, 177, 48)):
+        inv_pv, res, cm, vsm, depth, pt0 = make_vsm_case(w, h, size=size)
+        pt_ref = pt0.copy()
+        occ_ref = np.zeros(32 * 32, dtype=np.uint32)
+        cap = 1 << 16
+        req_ref, n_ref = orc.mark_visible_pages(inv_pv, res, cm, vsm, depth, pt_ref, occ_ref, cap)
+        assert n_ref > 100
+        d_depth, d_pt, d_occ = ctx.alloc(depth.nbytes), ctx.alloc(pt0.nbytes), ctx.alloc(occ_ref.nbytes)
+        d_cnt, d_req = ctx.alloc(4), ctx.alloc(cap * 12)
+        ctx.upload(d_depth, depth); ctx.upload(d_pt, pt0); ctx.upload(d_occ, np.zeros_like(occ_ref)); ctx.upload(d_cnt, np.zeros(1, np.uint32))
+        ctx.mark_visible_pages(inv_pv, res, cm, vsm, d_depth, d_pt, d_occ, d_cnt, d_req, cap)
+        np.testing.assert_array_equal(ctx.download(d_pt, np.uint32, pt0.size).reshape(pt0.shape), pt_ref)
+        np.testing.assert_array_equal(ctx.download(d_occ, np.uint32, occ_ref.size), occ_ref)
+        n = int(ctx.download(d_cnt, np.uint32, 1)[0])
+        assert n == n_ref
+        got = ctx.download(d_req, np.int32, n * 3).reshape(-1, 3)
+        assert sorted(map(tuple, got.tolist())) == sorted(map(tuple, req_ref.tolist()))
+        # second call on the updated tables: everything is visible already -> no new request
+        ctx.upload(d_cnt, np.zeros(1, np.uint32))
+        ctx.mark_visible_pages(inv_pv, res, cm, vsm, d_depth, d_pt, d_occ, d_cnt, d_req, cap)
+        assert int(ctx.download(d_cnt, np.uint32, 1)[0]) == 0
+        for d in (d_depth, d_pt, d_occ, d_cnt, d_req):
+            ctx.free(d)
+    ctx.close()
+
+
 def test_builder_scene_parity(capi, orc):
     """content produced by the mesh builder (oxb_build_mesh: scan meshlets, meshopt-style bounds / cones, 2 LODs) through
     the whole GPU path: cull_meshes (LOD selection), two-pass frames, raster, decode — bit-exact against the oracle; and

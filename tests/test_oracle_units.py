@@ -249,6 +249,84 @@ def test_small_primitive_cull_hand_cases(orc):
     assert covers_none([(-5.8, 10.2), (-5.1, 10.9), (-5.4, 10.3)]) == 1       # left of the image: clamped bounds are empty
 
 
+def test_log2_canonical_accuracy_and_specials(orc):
+    """The library's own log2 (decision path of the VSM clipmap selection): strict-f32 polynomial, |error| < 2e-7 absolute
+    against double-precision log2 across the range, exact at powers of two, defined for 0 / negative / inf / NaN / denormals."""
+    xs = np.concatenate([np.exp2(np.linspace(-120, 120, 4001)), np.linspace(0.5, 2.0, 2001), [1.0, 2.0, 4.0, 0.25, 1.41421354, 1.41421366]])
+    for x in xs.astype(np.float32):
+        got = orc.log2_canonical(float(x))
+        want = np.log2(np.float64(x))
+        assert abs(got - want) <= 2e-7 * max(1.0, abs(want)), (x, got, want)
+    for k in range(-126, 128):
+        assert orc.log2_canonical(float(np.float32(2.0) ** k)) == float(k)
+    assert orc.log2_canonical(0.0) < -1e38 and orc.log2_canonical(-1.0) < -1e38 and orc.log2_canonical(float("nan")) < -1e38
+    assert orc.log2_canonical(float("inf")) > 1e38
+    assert abs(orc.log2_canonical(float(np.float32(1e-41))) - np.log2(1e-41)) < 1e-3  # denormal input
+
+
+def make_vsm_case(w, h, size=64, clipmaps=6, seed=7):
+    """A camera looking down at a ground plane + seeded clipmaps: (inv_pv, resolution, clipmaps, vsm, depth, page_tables)"""
+    cam_pv = synth.mat_mul_cm(synth.perspective_reverse_z(60.0, w / h, 0.1, 1000.0), synth.look_at((0.0, 20.0, 0.0), (0.0, 0.0, -40.0), (0.0, 1.0, 0.0)))
+    inv_pv = np.linalg.inv(cam_pv.reshape(4, 4).T.astype(np.float64)).T.astype(np.float32).reshape(16)
+    # depth of the plane y = 0 seen from the camera (reverse-Z), sky (0) above the horizon
+    ys, xs = np.meshgrid(np.arange(h), np.arange(w), indexing="ij")
+    u, v = (xs + 0.5) / w, (ys + 0.5) / h
+    ipv = inv_pv.reshape(4, 4).T.astype(np.float64)
+    def unproj(z):
+        ndc = np.stack([u * 2 - 1, v * 2 - 1, np.full_like(u, z), np.ones_like(u)], axis=-1)
+        p = ndc @ ipv.T
+        return p[..., :3] / p[..., 3:4]
+    p0, p1 = unproj(1.0), unproj(1e-4)
+    t = p0[..., 1] / (p0[..., 1] - p1[..., 1])
+    hit = (t > 0) & (t < 1)
+    world = p0 + t[..., None] * (p1 - p0)
+    pv = cam_pv.reshape(4, 4).T.astype(np.float64)
+    clip = np.concatenate([world, np.ones_like(world[..., :1])], axis=-1) @ pv.T
+    depth = np.where(hit, clip[..., 2] / clip[..., 3], 0.0).astype(np.float32)
+    depth[(depth <= 0) | ~np.isfinite(depth)] = 0.0
+    cm = np.zeros(clipmaps, dtype=abi.CLIPMAP_DT)
+    for k in range(clipmaps):
+        view = synth.make_ortho_view((0.3, -1.0, 0.2), (0.0, 0.0, -40.0), 10.0 * (2 ** k), 400.0, 1)
+        cm["projection_view_mat"][k] = view["projection_view"][0]
+        cm["page_offset"][k] = (3 * k + 1, -2 * k)
+        cm["z_near"][k] = 0.0
+    vsm = np.zeros(1, dtype=abi.VSM_CONTEXT_DT)
+    vsm["page_size"], vsm["page_table_size"], vsm["physical_page_table_size"], vsm["clipmap_count"] = 128, size, 32, clipmaps
+    vsm["depth_extent"][0] = (w, h)
+    vsm["first_clipmap_width"], vsm["clipmap_selection_bias"], vsm["virtual_extent"], vsm["z_length"] = 10.0, 0.25, 200.0, 400.0
+    rng = np.random.default_rng(seed)
+    state = rng.integers(0, 8, size=(clipmaps, size, size), dtype=np.uint32)          # random Visible / Dirty / Backed bits
+    phys = rng.integers(0, 32 * 32, size=(clipmaps, size, size), dtype=np.uint32)
+    page_tables = (state | (phys << 16)).astype(np.uint32)
+    return inv_pv, np.array([w, h], dtype=np.float32), cm, vsm, depth, page_tables
+
+
+def test_mark_visible_pages_oracle_properties(orc):
+    """rmvsm_mark_visible_pages.slang on a ground plane: sky pixels mark nothing; every touched entry gains the Visible bit and
+    nothing else changes; a request is pushed exactly for the pages that were neither visible nor backed; occupancy is set
+    exactly for those that were backed but not visible; nearer pixels select finer clipmaps."""
+    inv_pv, res, cm, vsm, depth, pt0 = make_vsm_case(160, 90)
+    pt = pt0.copy()
+    occ = np.zeros(32 * 32, dtype=np.uint32)
+    req, n = orc.mark_visible_pages(inv_pv, res, cm, vsm, depth, pt, occ, 1 << 16)
+    changed = pt != pt0
+    assert n == len(req) and changed.any()
+    assert np.all((pt[changed] ^ pt0[changed]) == 1)                       # only the Visible bit, only 0 -> 1
+    newly = changed
+    backed = (pt0 & 4) != 0
+    want_req = {(int(x), int(y), int(c)) for c, y, x in zip(*np.nonzero(newly & ~backed))}
+    assert {tuple(r) for r in req.tolist()} == want_req and len(req) == len(want_req)
+    want_occ = np.zeros_like(occ)
+    want_occ[(pt0[newly & backed] >> 16)] = 1
+    np.testing.assert_array_equal(occ, want_occ)
+    layers = np.nonzero(changed)[0]
+    assert layers.min() == 0 or layers.min() < layers.max()               # several clipmap levels in use
+    # a sky-only image marks nothing
+    pt2 = pt0.copy()
+    req2, n2 = orc.mark_visible_pages(inv_pv, res, cm, vsm, np.zeros_like(depth), pt2, occ.copy(), 16)
+    assert n2 == 0 and np.array_equal(pt2, pt0)
+
+
 def test_terrain_cull_hand_case(orc):
     """terrain_cull.slang:19-83 with projection_view = I: 2x1 patches over x in [-2,2], z in [0,1]; the left patch is
     outside the x in [-1,1] frustum slab only if it does not touch it (it spans [-2,0] -> straddles -> visible)."""
