@@ -570,9 +570,10 @@ int oxr_wait(OxrRenderer* r, int ticket, OxrFrameResult* result);
  * oxb_* — mesh builder: host-side producer of the blob layout above, mirroring build_gltf_mesh
  * (Oxylus/src/Asset/AssetManager_GLTF.cpp:481-771) after the glTF accessors are read.  Pure host code (no CUDA).
  * The four meshoptimizer v1.2 calls of the reference (not vendored in /root/reference) are restated from their
- * published definitions — fetch remap, quantizeHalf, quantizeSnorm, computeMeshletBounds' normal cone —; the spatial
- * clusteriser (meshopt_buildMeshlets) and the simplifier are NOT: meshlets come from a linear scan of the index buffer
- * (<= 64 vertices, <= 64 triangles, Model.hpp:27-28) and coarser LODs are caller-supplied index buffers.
+ * published definitions — fetch remap, quantizeHalf, quantizeSnorm, computeMeshletBounds' normal cone — and the clusteriser
+ * (meshopt_buildMeshlets) by a greedy spatial clusteriser of the same scheme (cluster_mode 1; not bit-compatible with
+ * meshoptimizer's clusters); the simplifier is NOT reproduced: coarser LODs are caller-supplied index buffers.  Meshlets hold
+ * <= 64 vertices, <= 64 triangles (Model.hpp:27-28).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct OxbMeshInput {
   const float* positions;  /* vertex_count x 3 */
@@ -583,6 +584,9 @@ typedef struct OxbMeshInput {
   const uint32_t* lod_indices[OXC_MESH_MAX_LODS]; /* triangle lists in input vertex numbering; [0] = full detail */
   uint32_t lod_index_counts[OXC_MESH_MAX_LODS];
   float lod_errors[OXC_MESH_MAX_LODS];            /* MeshLOD::error (cull_meshes.slang:35-57 LOD selection) */
+  uint32_t cluster_mode;   /* 0: meshlets follow the caller's triangle order; 1: spatial clusteriser first (the role of
+                              meshopt_buildMeshlets, AssetManager_GLTF.cpp:630-676): adjacency-first greedy growth, nearest
+                              unused centroid when the meshlet has no unused neighbour */
 } OxbMeshInput;
 typedef struct OxbMesh OxbMesh;
 const char* oxb_last_error(void);

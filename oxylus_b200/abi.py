@@ -224,6 +224,7 @@ class MeshInput(C.Structure):
         ("lod_indices", C.c_void_p * MESH_MAX_LODS),
         ("lod_index_counts", C.c_uint32 * MESH_MAX_LODS),
         ("lod_errors", C.c_float * MESH_MAX_LODS),
+        ("cluster_mode", C.c_uint32),
     ]
 
 

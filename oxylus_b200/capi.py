@@ -142,7 +142,7 @@ class BuiltMesh:
     """OxbMesh wrapper: one mesh run through the host-side builder (oxb_build_mesh).  lods = [(indices, error), ...],
     LOD 0 first.  Host-only: works without a GPU."""
 
-    def __init__(self, positions, lods, normals=None, texcoords=None):
+    def __init__(self, positions, lods, normals=None, texcoords=None, spatial=False):
         self.lib = load()
         pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
         nrm = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
@@ -151,6 +151,7 @@ class BuiltMesh:
         mi = abi.MeshInput()
         mi.positions, mi.normals, mi.texcoords = _ptr(pos), _ptr(nrm), _ptr(tc)
         mi.vertex_count, mi.lod_count = len(pos), len(lods)
+        mi.cluster_mode = 1 if spatial else 0
         for l, (a, (_, err)) in enumerate(zip(idx, lods)):
             mi.lod_indices[l] = a.ctypes.data
             mi.lod_index_counts[l] = a.size

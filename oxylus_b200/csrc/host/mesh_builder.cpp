@@ -12,10 +12,11 @@
 //   meshopt_computeMeshletBounds      cone axis = centre of Ritter's bounding sphere of the unit triangle normals,
 //                                     cutoff = sqrt(1 - mindp^2) widened by the s8 quantisation error (+1 ulp of s8);
 //                                     mindp <= 0.1 -> cutoff 127 (cone test disabled, cull.slang:173 `cutoff >= 1.0`)
-// meshopt_buildMeshlets' kd-tree guided clustering and meshopt_simplifyWithAttributes are NOT reproduced: meshlets are
-// formed by a linear scan over the (caller-ordered) index buffer, closing a meshlet when the next triangle would exceed
-// 64 vertices or 64 triangles (Model::MAX_MESHLET_INDICES / MAX_MESHLET_PRIMITIVES, Model.hpp:27-28), and coarser LODs
-// are index buffers the caller supplies.  PARITY UNPINNED against meshoptimizer.
+// meshopt_buildMeshlets: cluster_mode 1 runs a greedy spatial clusteriser of the same published scheme (adjacency-first
+// growth, nearest-centroid reseeding — spatial_triangle_order below), cluster_mode 0 keeps the caller's triangle order; either
+// way meshlets are then formed by a linear scan that closes a meshlet when the next triangle would exceed 64 vertices or 64
+// triangles (Model::MAX_MESHLET_INDICES / MAX_MESHLET_PRIMITIVES, Model.hpp:27-28).  meshopt_simplifyWithAttributes is NOT
+// reproduced: coarser LODs are index buffers the caller supplies.  PARITY UNPINNED against meshoptimizer.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -99,6 +100,158 @@ struct ScanMeshlet {
   uint32_t vertex_offset, triangle_offset, vertex_count, triangle_count;
 };
 
+// Spatial clusteriser (cluster_mode 1) — the role meshopt_buildMeshlets' kd-tree guided growth plays in the reference
+// (AssetManager_GLTF.cpp:630-676).  It only REORDERS the triangles; the linear scan below then closes meshlets at the same
+// 64-vertex / 64-triangle limits, so "order + scan" is the whole definition.  Greedy growth, meshoptimizer's published scheme:
+//   * the next triangle is the unused one adjacent to the current meshlet that adds the fewest new vertices (one less when
+//     it is the last unused triangle of one of its vertices); ties: nearest centroid to the meshlet's centre, then lowest index;
+//   * when no unused triangle touches the meshlet, the unused triangle whose centroid is nearest to the meshlet's centre
+//     (uniform grid over the centroids instead of a kd-tree: same query, simpler structure);
+//   * a meshlet is closed when the chosen triangle does not fit.
+// Deterministic (no hashing, ties by index).  Not bit-compatible with meshoptimizer's clusters (parity unpinned).
+std::vector<uint32_t> spatial_triangle_order(const std::vector<uint32_t>& indices, const std::vector<float>& positions, uint32_t vertex_count) {
+  const uint32_t T = (uint32_t)(indices.size() / 3);
+  const uint32_t NONE = 0xFFFFFFFFu;
+  // vertex -> triangles (CSR)
+  std::vector<uint32_t> adj_off(vertex_count + 1, 0);
+  for (uint32_t i = 0; i < T * 3; i++) adj_off[indices[i] + 1]++;
+  for (uint32_t v = 0; v < vertex_count; v++) adj_off[v + 1] += adj_off[v];
+  std::vector<uint32_t> adj(T * 3), fill(adj_off.begin(), adj_off.end() - 1);
+  for (uint32_t t = 0; t < T; t++)
+    for (int k = 0; k < 3; k++) adj[fill[indices[t * 3 + k]]++] = t;
+  std::vector<uint32_t> live(vertex_count, 0);
+  for (uint32_t v = 0; v < vertex_count; v++) live[v] = adj_off[v + 1] - adj_off[v];
+  // centroids + uniform grid
+  std::vector<float> cen((size_t)T * 3);
+  float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+  for (uint32_t t = 0; t < T; t++)
+    for (int a = 0; a < 3; a++) {
+      const float c = (positions[(size_t)indices[t * 3] * 3 + a] + positions[(size_t)indices[t * 3 + 1] * 3 + a] + positions[(size_t)indices[t * 3 + 2] * 3 + a]) / 3.0f;
+      cen[(size_t)t * 3 + a] = c;
+      lo[a] = c < lo[a] ? c : lo[a]; hi[a] = c > hi[a] ? c : hi[a];
+    }
+  int G = 1;
+  while ((size_t)G * G * G * 8 < T && G < 128) G++;
+  float inv_cell[3];
+  for (int a = 0; a < 3; a++) inv_cell[a] = hi[a] > lo[a] ? (float)G / (hi[a] - lo[a]) : 0.0f;
+  auto cell_of = [&](const float* c, int out[3]) {
+    for (int a = 0; a < 3; a++) {
+      int g = (int)((c[a] - lo[a]) * inv_cell[a]);
+      out[a] = g < 0 ? 0 : (g >= G ? G - 1 : g);
+    }
+  };
+  std::vector<uint32_t> cell_off((size_t)G * G * G + 1, 0), cell_tri(T);
+  std::vector<uint32_t> tri_cell(T);
+  for (uint32_t t = 0; t < T; t++) {
+    int g[3];
+    cell_of(&cen[(size_t)t * 3], g);
+    tri_cell[t] = (uint32_t)((g[2] * G + g[1]) * G + g[0]);
+    cell_off[tri_cell[t] + 1]++;
+  }
+  for (size_t c = 0; c < cell_off.size() - 1; c++) cell_off[c + 1] += cell_off[c];
+  {
+    std::vector<uint32_t> f(cell_off.begin(), cell_off.end() - 1);
+    for (uint32_t t = 0; t < T; t++) cell_tri[f[tri_cell[t]]++] = t;
+  }
+  std::vector<uint32_t> cell_live(cell_off.size() - 1);
+  for (size_t c = 0; c + 1 < cell_off.size(); c++) cell_live[c] = cell_off[c + 1] - cell_off[c];
+  std::vector<uint8_t> used(T, 0);
+  auto nearest_unused = [&](const float* q) -> uint32_t {
+    int g[3];
+    cell_of(q, g);
+    uint32_t best = NONE;
+    float best_d = 3e38f;
+    for (int ring = 0; ring < G; ring++) {
+      // once a candidate exists, one more ring is enough when the ring's inner distance exceeds it; keep it simple: search until a
+      // ring beyond the first hit has been scanned
+      bool any_cell = false;
+      for (int z = g[2] - ring; z <= g[2] + ring; z++)
+        for (int y = g[1] - ring; y <= g[1] + ring; y++)
+          for (int x = g[0] - ring; x <= g[0] + ring; x++) {
+            if (x < 0 || y < 0 || z < 0 || x >= G || y >= G || z >= G) continue;
+            if (ring && x != g[0] - ring && x != g[0] + ring && y != g[1] - ring && y != g[1] + ring && z != g[2] - ring && z != g[2] + ring) continue; // shell only
+            const size_t c = (size_t)(z * G + y) * G + x;
+            if (!cell_live[c]) continue;
+            any_cell = true;
+            for (uint32_t k = cell_off[c]; k < cell_off[c + 1]; k++) {
+              const uint32_t t = cell_tri[k];
+              if (used[t]) continue;
+              const float dx = cen[(size_t)t * 3] - q[0], dy = cen[(size_t)t * 3 + 1] - q[1], dz = cen[(size_t)t * 3 + 2] - q[2];
+              const float d = dx * dx + dy * dy + dz * dz;
+              if (d < best_d || (d == best_d && t < best)) { best_d = d; best = t; }
+            }
+          }
+      (void)any_cell;
+      if (best != NONE) {
+        // cells of the next shells are at least `ring` cells away along some axis: stop once that bound exceeds the best distance
+        float min_cell = 3e38f;
+        for (int a = 0; a < 3; a++)
+          if (inv_cell[a] > 0.0f) { const float cs = 1.0f / inv_cell[a]; min_cell = cs < min_cell ? cs : min_cell; }
+        if (min_cell == 3e38f || (float)ring * min_cell * (float)ring * min_cell >= best_d) break;
+      }
+    }
+    return best;
+  };
+  std::vector<uint32_t> order;
+  order.reserve(T);
+  std::vector<uint32_t> slot(vertex_count, NONE); // meshlet-local slot of a vertex
+  std::vector<uint32_t> mverts;
+  uint32_t mtris = 0;
+  float centre[3] = {0, 0, 0};
+  float last[3] = {cen.empty() ? 0.0f : cen[0], cen.empty() ? 0.0f : cen[1], cen.empty() ? 0.0f : cen[2]};
+  auto close = [&]() {
+    for (uint32_t v : mverts) slot[v] = NONE;
+    mverts.clear();
+    mtris = 0;
+    centre[0] = centre[1] = centre[2] = 0.0f;
+  };
+  for (uint32_t done = 0; done < T; done++) {
+    uint32_t best = NONE, best_extra = 4;
+    float best_d = 3e38f;
+    float mc[3] = {0, 0, 0};
+    if (mtris) for (int a = 0; a < 3; a++) mc[a] = centre[a] / (float)mtris;
+    for (uint32_t v : mverts)
+      for (uint32_t k = adj_off[v]; k < adj_off[v + 1]; k++) {
+        const uint32_t t = adj[k];
+        if (used[t]) continue;
+        const uint32_t a = indices[t * 3], b = indices[t * 3 + 1], c = indices[t * 3 + 2];
+        uint32_t extra = (slot[a] == NONE) + (slot[b] == NONE && b != a) + (slot[c] == NONE && c != a && c != b);
+        // a vertex whose last unused triangle this is gets "finished" by taking it: meshoptimizer's live-triangle bonus
+        if (extra && (live[a] == 1 || live[b] == 1 || live[c] == 1)) extra--;
+        const float dx = cen[(size_t)t * 3] - mc[0], dy = cen[(size_t)t * 3 + 1] - mc[1], dz = cen[(size_t)t * 3 + 2] - mc[2];
+        const float d = dx * dx + dy * dy + dz * dz;
+        if (extra < best_extra || (extra == best_extra && (d < best_d || (d == best_d && t < best)))) { best = t; best_extra = extra; best_d = d; }
+      }
+    if (best != NONE) { // the real number of new vertices (the bonus above is a preference, not a count)
+      const uint32_t a = indices[best * 3], b = indices[best * 3 + 1], c = indices[best * 3 + 2];
+      best_extra = (slot[a] == NONE) + (slot[b] == NONE && b != a) + (slot[c] == NONE && c != a && c != b);
+    }
+    if (best == NONE) {
+      float q[3];
+      if (mtris) for (int a = 0; a < 3; a++) q[a] = centre[a] / (float)mtris;
+      else for (int a = 0; a < 3; a++) q[a] = last[a];
+      best = nearest_unused(q);
+      const uint32_t a = indices[best * 3], b = indices[best * 3 + 1], c = indices[best * 3 + 2];
+      best_extra = (slot[a] == NONE) + (slot[b] == NONE && b != a) + (slot[c] == NONE && c != a && c != b);
+    }
+    if (mverts.size() + best_extra > OXC_MESHLET_MAX_VERTICES || mtris >= OXC_MESHLET_MAX_PRIMITIVES) {
+      if (mtris) for (int a = 0; a < 3; a++) last[a] = centre[a] / (float)mtris;
+      close();
+    }
+    for (int k = 0; k < 3; k++) {
+      const uint32_t v = indices[best * 3 + k];
+      if (slot[v] == NONE) { slot[v] = (uint32_t)mverts.size(); mverts.push_back(v); }
+      live[v]--;
+    }
+    for (int a = 0; a < 3; a++) centre[a] += cen[(size_t)best * 3 + a];
+    mtris++;
+    used[best] = 1;
+    cell_live[tri_cell[best]]--;
+    order.push_back(best);
+  }
+  return order;
+}
+
 } // namespace
 
 struct OxbMesh {
@@ -120,6 +273,7 @@ int oxb_build_mesh(const OxbMeshInput* in, OxbMesh** out) {
     g_builder_error = "positions and at least one triangle of LOD 0 are required (build_gltf_mesh returns nullopt, :485-487,758-760)";
     return OXC_E_INVALID;
   }
+  if (in->cluster_mode > 1) { g_builder_error = "cluster_mode must be 0 (caller order) or 1 (spatial)"; return OXC_E_INVALID; }
   for (uint32_t l = 0; l < in->lod_count; l++) {
     if (!in->lod_indices[l] || in->lod_index_counts[l] % 3u) { g_builder_error = "LOD index buffers must be triangle lists"; return OXC_E_INVALID; }
     for (uint32_t i = 0; i < in->lod_index_counts[l]; i++)
@@ -187,6 +341,13 @@ int oxb_build_mesh(const OxbMeshInput* in, OxbMesh** out) {
     const uint32_t index_count = in->lod_index_counts[l];
     std::vector<uint32_t> indices(index_count);
     for (uint32_t i = 0; i < index_count; i++) indices[i] = m->vertex_remap[in->lod_indices[l][i]];
+    if (in->cluster_mode == 1) { // spatial clustering: reorder the triangles, then scan
+      const std::vector<uint32_t> order = spatial_triangle_order(indices, positions, vertex_count);
+      std::vector<uint32_t> sorted(index_count);
+      for (size_t k = 0; k < order.size(); k++)
+        for (int c = 0; c < 3; c++) sorted[k * 3 + c] = indices[(size_t)order[k] * 3 + c];
+      indices.swap(sorted);
+    }
 
     // linear-scan clustering: a meshlet closes when the next triangle does not fit
     std::vector<ScanMeshlet> raw;

@@ -193,3 +193,77 @@ def test_built_scene_runs_through_the_oracle_pipeline(orc):
     assert np.array_equal(d["lambda_"][:, :, 3] == 1.0, covered)
     uvs = d["uv_normal"][covered][:, :2]
     assert uvs.min() > -0.05 and uvs.max() < 1.05
+
+
+def _lod0_meshlet_triangles(got):
+    """per-meshlet triangle arrays (blob vertex numbering) of LOD 0 from parse()'s structure"""
+    lod = got["lods"][0]
+    ml, micro, vi = lod["meshlets"], lod["micro"], lod["vertex_indices"]
+    return [vi[vo + micro[to: to + 3 * tc].astype(np.int64)].reshape(-1, 3) for vo, to, vc, tc in ml]
+
+
+def test_spatial_clusteriser_properties():
+    """cluster_mode 1 (the role of meshopt_buildMeshlets): on a torus whose triangles arrive in a SHUFFLED order the spatial
+    clusteriser covers every triangle exactly once within the 64 / 64 limits, fills its meshlets and makes them compact — the
+    caller-order scan on the same input produces many more, scattered meshlets.  Deterministic."""
+    pos, nrm, uv, i0, _ = torus(64, 32)
+    rng = np.random.default_rng(3)
+    shuffled = i0.reshape(-1, 3)[rng.permutation(len(i0) // 3)].reshape(-1)
+    spatial = capi.BuiltMesh(pos, [(shuffled, 0.0)], normals=nrm, texcoords=uv, spatial=True)
+    linear = capi.BuiltMesh(pos, [(shuffled, 0.0)], normals=nrm, texcoords=uv, spatial=False)
+    again = capi.BuiltMesh(pos, [(shuffled, 0.0)], normals=nrm, texcoords=uv, spatial=True)
+    gs, gl, ga = parse(spatial), parse(linear), parse(again)
+    assert np.array_equal(gs["blob"], ga["blob"])  # deterministic
+    ts, tl = _lod0_meshlet_triangles(gs), _lod0_meshlet_triangles(gl)
+    n_tri = len(shuffled) // 3
+    ps = gs["positions_q"][:, :3].copy().view(np.float16).astype(np.float64)
+    pl = gl["positions_q"][:, :3].copy().view(np.float16).astype(np.float64)
+
+    def canon(tris, p):  # triangles as position triples: the vertex numbering is the same (fetch remap precedes clustering)
+        allt = np.concatenate(tris)
+        return {tuple(sorted(map(tuple, p[t]))) for t in allt}
+
+    assert sum(len(t) for t in ts) == n_tri and canon(ts, ps) == canon(tl, pl) and len(canon(ts, ps)) == n_tri
+    for t in ts:
+        assert 1 <= len(t) <= 64 and len(np.unique(t)) <= 64
+
+    def radius(tris, p):
+        return float(np.mean([np.linalg.norm(p[np.unique(t)] - p[np.unique(t)].mean(axis=0), axis=1).max() for t in tris]))
+
+    assert len(ts) <= 1.3 * np.ceil(n_tri / 64)              # nearly full meshlets
+    assert len(tl) >= 2 * len(ts)                            # the shuffled scan runs out of vertices long before 64 triangles
+    assert radius(ts, ps) < 0.35 * radius(tl, pl)            # ... and its meshlets span the whole mesh
+    for b in (spatial, linear, again):
+        b.close()
+
+
+def test_spatial_clusteriser_equals_scan_of_its_own_order(pyb):
+    """"order + scan" is the whole definition of cluster_mode 1: feeding the triangle order it produced back through the
+    caller-order path gives the same meshlets, and the independent Python builder reproduces that blob bit for bit."""
+    pos, nrm, uv, i0, _ = torus(24, 20)
+    rng = np.random.default_rng(5)
+    shuffled = i0.reshape(-1, 3)[rng.permutation(len(i0) // 3)].reshape(-1)
+    spatial = capi.BuiltMesh(pos, [(shuffled, 0.0)], normals=nrm, texcoords=uv, spatial=True)
+    gs = parse(spatial)
+    ts = _lod0_meshlet_triangles(gs)
+    # blob vertex numbering == order of first use in the shuffled buffer: map the clustered order back to input numbering
+    first_use = {}
+    for v in shuffled:
+        first_use.setdefault(int(v), len(first_use))
+    inverse = np.zeros(len(first_use), dtype=np.uint32)
+    for v, r in first_use.items():
+        inverse[r] = v
+    ordered = inverse[np.concatenate(ts).reshape(-1)]
+    again = capi.BuiltMesh(pos, [(ordered, 0.0)], normals=nrm, texcoords=uv, spatial=False)
+    ga = parse(again)
+    ta = _lod0_meshlet_triangles(ga)
+    assert len(ta) == len(ts)
+    ps = gs["positions_q"][:, :3]
+    pa = ga["positions_q"][:, :3]
+    for a, b in zip(ta, ts):
+        np.testing.assert_array_equal(pa[a], ps[b])          # same triangles, same corner order, meshlet by meshlet
+    want = pyb.build(pos, [(ordered, 0.0)], normals=nrm, texcoords=uv)
+    np.testing.assert_array_equal(ga["lods"][0]["meshlets"], want["lods"][0]["meshlets"])
+    np.testing.assert_array_equal(ga["lods"][0]["micro"], want["lods"][0]["micro"])
+    np.testing.assert_array_equal(ga["lods"][0]["vertex_indices"], want["lods"][0]["vertex_indices"])
+    spatial.close(); again.close()
