@@ -287,11 +287,22 @@ def main():
         cap = max(1, max(int(lod0[f:f + c].sum()) for f, c in parts))
         uid = [capi.Context.mgpu_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
-        # survivor gather segments: half a shard is ample for this scene (~1/3 visible); exceeding it is a hard error
-        # (OXC_STATUS_SURVIVOR_OVERFLOW, checked below), never a silent truncation
-        mg = dict(rank=rank, world=world, unique_id=uid[0], survivor_capacity=max(1024, cap // 2))
-    pipe = pipeline.VisibilityPipeline(scene, device=local_rank, shard=shard, auto_id_base=True, shard_capacity=cap, mgpu=mg, wide_ids=wide_ids)
+    pipe = pipeline.VisibilityPipeline(scene, device=local_rank, shard=shard, auto_id_base=True, shard_capacity=cap, wide_ids=wide_ids)
     cams = [scene.camera(0.0), scene.camera(2.0)]
+    if multi:
+        # survivor gather segments (ncclAllGather needs one size for all ranks): sized from four LOCAL frames — a rank that only
+        # sees its own occluders keeps MORE survivors than it will with everybody's Hi-Z — times two, max over ranks.
+        # Exceeding it later is a hard error (OXC_STATUS_SURVIVOR_OVERFLOW, checked below), never a silent truncation.
+        local_max = 0
+        for f in range(4):
+            pipe.frame(cams[f % 2])
+            c_ = pipe.counters()
+            local_max = max(local_max, c_["early"] + c_["late"])
+        t_cap = torch.tensor([local_max], dtype=torch.int64)
+        dist.all_reduce(t_cap, op=dist.ReduceOp.MAX)
+        pipe.ctx.reset_visibility_mask()
+        torch.cuda.synchronize()
+        pipe.mgpu = pipe.ctx.mgpu_init(rank, world, uid[0], min(cap, max(4096, 2 * int(t_cap.item()))))
     dev = pipe.device
     w, h = scene.width, scene.height
 
