@@ -275,7 +275,7 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   TRY(dalloc(&c->d_cull_triangles_cmd, 1));
   TRY(dalloc(&c->d_draw_cmd, 1));
   TRY(dalloc(&c->d_tri_counter, 1));
-  TRY(dalloc(&c->d_raster_work, 1));
+  TRY(dalloc(&c->d_raster_work, 4)); // work counter | chunk-queue counters (2) | clip-queue counter: one 16-byte memset per raster call
   c->big_capacity = 1u << 18; // 262144 chunks x 64 B = 16 MB; overflow falls back to inline rasterisation
   if (const char* e = getenv("OXC_BIG_CAPACITY")) { // test hook: force the overflow paths
     const long v = atol(e);
@@ -287,13 +287,13 @@ int oxc_create(int device, const OxcCreateInfo* info, OxcContext** out_ctx) {
   TRY(dalloc(&c->d_big_queue, (size_t)c->big_capacity * 4 + 64 /* 128 u64 statistics slots of the OXC_RASTER_STATS build */));
 #endif
   CK(cudaMemset(c->d_big_queue + (size_t)c->big_capacity * 4, 0, 1024));
-  TRY(dalloc(&c->d_big_counters, 2));
+  c->d_big_counters = c->d_raster_work + 1;
   if (const char* e = getenv("OXC_CLIP_CAPACITY")) { // test hook: force the overflow path
     const long v = atol(e);
     if (v >= 1 && v <= (1l << 24)) c->clip_capacity = (uint32_t)v;
   }
   TRY(dalloc(&c->d_clip_queue, (size_t)c->clip_capacity));
-  TRY(dalloc(&c->d_clip_counter, 1));
+  c->d_clip_counter = c->d_raster_work + 3;
   TRY(dalloc(&c->d_id_base_auto, 1));
   TRY(dalloc(&c->d_status, 1));
   c->prim_bits = info->wide_ids ? OXC_VIS_WIDE_PRIMITIVE_BITS : OXC_VIS_PRIMITIVE_BITS;
@@ -361,7 +361,7 @@ void oxc_destroy(OxcContext* c) {
   cudaFree(c->d_lod_aabb); cudaFree(c->d_inst); cudaFree(c->d_geom); cudaFree(c->d_counts); cudaFree(c->d_block_sums);
   cudaFree(c->d_meshlet_instances); cudaFree(c->d_slabs); cudaFree(c->d_visible); cudaFree(c->d_mask); cudaFree(c->d_vis);
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
-  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_big_queue); cudaFree(c->d_big_counters); cudaFree(c->d_clip_queue); cudaFree(c->d_clip_counter); cudaFree(c->d_id_base_auto); cudaFree(c->d_status); cudaFree(c->d_hiz);
+  cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_big_queue); cudaFree(c->d_clip_queue); cudaFree(c->d_id_base_auto); cudaFree(c->d_status); cudaFree(c->d_hiz);
   cudaFree(c->d_view_planes); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts); cudaFree(c->d_inst_views);
   delete c;
 }
@@ -574,7 +574,7 @@ int oxc_cull_meshes(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, voi
     LAUNCHED();
     k_scan_block_sums<<<1, 1024, 0, s>>>(c->d_block_sums, n_blocks, c->d_vis, c->d_cull_meshlets_cmd, c->info.max_meshlet_instances, c->d_status);
     LAUNCHED();
-    k_expand_meshlet_instances<<<n_blocks, CULL_MESHES_THREADS, 0, s>>>(c->d_counts, c->d_block_sums, p.first, p.count,
+    k_expand_meshlet_instances<<<n_blocks * EXPAND_SPLIT, CULL_MESHES_THREADS, 0, s>>>(c->d_counts, c->d_block_sums, p.first, p.count,
                                                                       c->d_meshlet_instances, c->info.max_meshlet_instances, c->d_slabs);
     LAUNCHED();
   }
@@ -590,8 +590,7 @@ int oxc_cull_meshlets(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, i
   CK(cudaSetDevice(c->device));
   int rc = refresh_inst_cache(c, cam, s);
   if (rc != OXC_OK) return rc;
-  k_set_cmd3<<<1, 1, 0, s>>>(c->d_cull_triangles_cmd, 0, 1, 1); // CullGeometry.cpp:125-127
-  LAUNCHED();
+  CK(cudaMemsetAsync(&c->d_cull_triangles_cmd->x, 0, 4, s)); // CullGeometry.cpp:125-127 ({0, 1, 1}: y and z are never modified)
   CullParams p{};
   p.slabs = c->d_slabs;
   p.meshlet_instances = c->d_meshlet_instances; p.inst = c->d_inst; p.vis = c->d_vis; p.visible_indices = c->d_visible;
@@ -737,15 +736,13 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
   p.visbuf = reinterpret_cast<unsigned long long*>(vis); p.width = w; p.height = h; p.f_width = (float)w; p.f_height = (float)h;
   p.small_primitive_cull = small_primitive_cull ? 1u : 0u;
   p.work_counter = c->d_raster_work;
-  CK(cudaMemsetAsync(c->d_raster_work, 0, 4, s));
+  CK(cudaMemsetAsync(c->d_raster_work, 0, 16, s)); // work counter, chunk-queue counters, clip-queue counter
   uint32_t tiles = (c->info.max_meshlet_instances + TRI_WARPS - 1) / TRI_WARPS;
   uint32_t grid = (uint32_t)(c->sm_count * (c->occ_raster > 0 ? c->occ_raster : 1));
   if (grid > tiles) grid = tiles;
   if (grid == 0) grid = 1;
   p.big_queue = c->d_big_queue; p.big_counters = c->d_big_counters; p.big_capacity = c->big_capacity;
   p.clip_queue = c->d_clip_queue; p.clip_counter = c->d_clip_counter; p.clip_capacity = c->clip_capacity;
-  CK(cudaMemsetAsync(c->d_big_counters, 0, 8, s));
-  CK(cudaMemsetAsync(c->d_clip_counter, 0, 4, s));
   if (p.late) k_raster_visbuffer<true><<<grid, TRI_THREADS, 0, s>>>(p);
   else k_raster_visbuffer<false><<<grid, TRI_THREADS, 0, s>>>(p);
   LAUNCHED();
