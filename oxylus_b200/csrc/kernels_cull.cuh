@@ -5,7 +5,10 @@
 
 namespace oxc {
 
-constexpr int CULL_MESHES_THREADS = 256;
+#ifndef OXC_CULL_MESHES_THREADS
+#define OXC_CULL_MESHES_THREADS 64
+#endif
+constexpr int CULL_MESHES_THREADS = OXC_CULL_MESHES_THREADS;
 constexpr int CULL_THREADS = 256;
 #ifndef OXC_CULL_ITEMS
 #define OXC_CULL_ITEMS 2
