@@ -7,6 +7,7 @@
 #include <climits>
 
 #include "oxc_exact.cuh"
+#include "oxc_tma.cuh"
 
 namespace oxc {
 
@@ -314,6 +315,7 @@ OXC_DI void raster_small(const TriSetup& s, uint32_t data, unsigned long long* v
 #ifndef OXC_RASTER_BATCH
 #define OXC_RASTER_BATCH 8
 #endif
+constexpr int MICRO_STAGE_BYTES = 224;               // 15 (alignment skew) + 192 (64 triangles x 3) rounded up to 16
 constexpr int RASTER_BATCH = OXC_RASTER_BATCH;       // meshlets per work grab
 static_assert(RASTER_BATCH >= 1 && RASTER_BATCH <= 32, "one header per lane: a grab holds at most 32 meshlets");
 constexpr int RASTER_BIG_PIXELS = OXC_RASTER_BIG_PIXELS; // bbox area above which the whole warp rasterises the triangle together
@@ -454,6 +456,18 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
   __shared__ float4 clip_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   __shared__ ScreenVert scr_all[TRI_WARPS][OXC_MESHLET_MAX_VERTICES];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef OXC_RASTER_TMA_MICRO
+  // OPT-IN (north_star: "micro-index data staged through TMA into shared memory"): the meshlet's micro-index run (<= 192 B,
+  // scene.slang:336-342) is staged by the bulk-copy engine (cp.async.bulk -> SASS UBLKCP) while the vertices are transformed, and
+  // the 3 byte fetches per triangle become shared-memory byte loads.  Bit-identical output (all 50 GPU tests), but measured
+  // SLOWER on B200 at the 64-register cap this kernel runs at: early raster 306 -> 330 us, late 61 -> 67 us (the three extra live
+  // values push 150 more bytes of spills into the hot loop; the L1-resident LDG it replaces was never the bottleneck).  Default off.
+  __shared__ __align__(16) uint8_t micro_all[TRI_WARPS][MICRO_STAGE_BYTES];
+  __shared__ __align__(8) uint64_t micro_bar[TRI_WARPS];
+  if (lane == 0) { mbar_init(&micro_bar[warp], 1); mbar_fence_init(); }
+  __syncwarp();
+  uint32_t micro_phase = 0; // parity of the warp's mbarrier: one bulk copy per meshlet
+#endif
   const uint32_t first = p.late ? p.vis->early_visible_meshlet_instances : 0u; // cull_triangles.slang:34-37
   const uint32_t count = p.tri_cmd->x;                                         // dispatch_indirect(cull_triangles_cmd), CullGeometry.cpp:365
   const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
@@ -527,6 +541,17 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
 #endif
     for (uint32_t j = 0; j < nb; j++) {
       const MeshletHeader w = cur;
+#ifdef OXC_RASTER_TMA_MICRO
+      // micro indices of this meshlet -> shared memory, asynchronously (16-byte aligned window around the run; the blob is
+      // padded so the window never leaves the allocation)
+      const uint64_t micro_addr = reinterpret_cast<uint64_t>(w.micro) + w.tri_offset;
+      const uint32_t micro_skew = (uint32_t)(micro_addr & 15u);
+      if (lane == 0) {
+        const uint32_t bytes = (micro_skew + w.tri_count * 3u + 15u) & ~15u;
+        mbar_expect_tx(&micro_bar[warp], bytes);
+        tma_load_1d(micro_all[warp], reinterpret_cast<const void*>(micro_addr - micro_skew), bytes, &micro_bar[warp]);
+      }
+#endif
       // positions of this meshlet (indices already here) ...
       const uint2 q0 = lane < w.vertex_count ? __ldg(&w.pos[vi0]) : make_uint2(0, 0);
       const uint2 q1 = lane + 32u < w.vertex_count ? __ldg(&w.pos[vi1]) : make_uint2(0, 0);
@@ -552,6 +577,11 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
         scr_s[lane + 32] = to_screen(c, p.f_width, p.f_height);
       }
       __syncwarp();
+#ifdef OXC_RASTER_TMA_MICRO
+      mbar_wait(&micro_bar[warp], micro_phase); // the micro indices have landed (usually long ago)
+      micro_phase ^= 1u;
+      const uint8_t* micro_s = micro_all[warp] + micro_skew;
+#endif
       const uint32_t rounds = (w.tri_count + 31u) >> 5;
       for (uint32_t k = 0; k < rounds; k++) {
         const uint32_t t = lane + 32u * k;
@@ -559,8 +589,12 @@ __global__ void __launch_bounds__(TRI_THREADS, OXC_RASTER_MIN_BLOCKS) k_raster_v
         TriSetup s;
         bool draw = false;
         if (t < w.tri_count) {
+#ifdef OXC_RASTER_TMA_MICRO
+          const uint32_t i0 = micro_s[t * 3u + 0u], i1 = micro_s[t * 3u + 1u], i2 = micro_s[t * 3u + 2u];
+#else
           const uint32_t base = w.tri_offset + t * 3u;
           const uint32_t i0 = micro_index(w.micro, base + 0u), i1 = micro_index(w.micro, base + 1u), i2 = micro_index(w.micro, base + 2u);
+#endif
           if (max(i0, max(i1, i2)) < w.vertex_count) { // malformed meshlets never index past the transformed vertices
             const float4 c0 = clip_s[i0], c1 = clip_s[i1], c2 = clip_s[i2];
             pass = c0.z >= 0.0f && c1.z >= 0.0f && c2.z >= 0.0f && !triangle_backface(c0, c1, c2); // cull_triangles.slang:68-69

@@ -476,8 +476,8 @@ int oxc_set_scene(OxcContext* c, const OxcSceneDesc* sc, void* stream) {
   }
   if (upload_size > c->blob_cap) {
     CK(cudaFree(c->d_blob)); c->d_blob = nullptr;
-    CK(cudaMalloc(&c->d_blob, (size_t)upload_size));
-    c->blob_cap = upload_size;
+    CK(cudaMalloc(&c->d_blob, (size_t)upload_size + 64)); // + slack: the raster's 16-byte aligned bulk copies of micro-index runs may
+    c->blob_cap = upload_size;                            //   read up to 15 bytes past the last run
   }
   CK(cudaMemcpyAsync(c->d_meshes, sc->meshes, (size_t)sc->mesh_count * sizeof(OxcMesh), cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(c->d_mesh_instances, sc->mesh_instances, (size_t)sc->mesh_instance_count * sizeof(OxcMeshInstance), cudaMemcpyHostToDevice, s));
