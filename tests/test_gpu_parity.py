@@ -944,6 +944,50 @@ def test_build_hpb_parity(capi, orc):
     ctx.close()
 
 
+def test_mgpu_api_single_rank(capi, orc):
+    """oxc_mgpu_* with a communicator of ONE rank (what a 1-GPU box can run; 2 and 8 ranks are checked against one GPU by
+    tools/check_multi_gpu.py and inside bench.py): exchange_hiz == generate_hiz, exchange_frame gathers this rank's
+    counters and survivors, an undersized gather segment raises the overflow status."""
+    import torch
+
+    from oxylus_b200 import pipeline
+
+    sc = synth.make_scene(config_index=2, **SCENES["box"])
+    hs = orc.HostScene(sc)
+    uid = capi.Context.mgpu_unique_id()
+    assert len(uid) == abi.MGPU_ID_BYTES
+    pipe = pipeline.VisibilityPipeline(sc, device=0, shard=(0, sc.mesh_instance_count), auto_id_base=True,
+                                       mgpu=dict(rank=0, world=1, unique_id=uid, survivor_capacity=sc.max_meshlet_instance_count))
+    info = pipe.ctx.mgpu_info()
+    assert (info.active, info.rank, info.world) == (1, 0, 1)
+    mask_ref = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    for f in range(3):
+        cam = sc.camera(2.0 * f)
+        ref = orc.frame(hs, cam, sc.width, sc.height, mask_ref, sc.occluder_depth)
+        pipe.frame(cam)
+        pipe.exchange_frame(slot=f & 1)
+        torch.cuda.synchronize()
+        assert pipe.ctx.check_status() == 0
+        cnt, ids = pipe.ctx.mgpu_gathered(f & 1)
+        e, l = ref["early"], ref["late"]
+        assert cnt.tolist() == [[int(ref["visibility"]["total"][0]), e, l, e + l]]
+        np.testing.assert_array_equal(np.sort(ids[0]), np.sort(ref["visible"][: e + l]))
+        np.testing.assert_array_equal(pipe.vis64.cpu().numpy().view(np.uint64), ref["vis64"])
+        for a, b in zip(pipe.ctx.hiz_levels(), [ref["hiz"].level(k) for k in range(len(pipe.ctx.hiz_levels()))]):
+            np.testing.assert_array_equal(a.view(np.uint32), np.asarray(b).view(np.uint32))
+    pipe.close()
+    # a gather segment smaller than the survivor list is a hard error, not a truncation
+    pipe = pipeline.VisibilityPipeline(sc, device=0, shard=(0, sc.mesh_instance_count), auto_id_base=True,
+                                       mgpu=dict(rank=0, world=1, unique_id=capi.Context.mgpu_unique_id(), survivor_capacity=16))
+    pipe.frame(sc.camera(0.0))
+    pipe.exchange_frame(slot=0)
+    torch.cuda.synchronize()
+    assert pipe.ctx.status_flags() & abi.STATUS_SURVIVOR_OVERFLOW
+    with pytest.raises(capi.OxcError, match="gather capacity"):
+        pipe.ctx.check_status()
+    pipe.close()
+
+
 def test_mark_visible_pages_parity(capi, orc):
     """rmvsm_mark_visible_pages.slang equivalent vs the oracle on a 1920x1080 depth image of a ground plane: page tables and
     occupancy bit for bit, allocation requests as a set (push order is atomics order in the reference too)."""
