@@ -251,6 +251,16 @@ enum {
   OXC_STATUS_PEER_TIMEOUT = 1 << 4      /* oxc_mgpu_exchange_hiz: a peer did not raise its flag within 30 s (OXC_MGPU_TIMEOUT_MS); that frame's pyramid is incomplete */
 };
 int oxc_check_status(OxcContext* ctx, void* stream, uint32_t* flags_out /* may be NULL */);
+/* CUDA-graph support: while a DEVICE camera buffer is bound, oxc_cull_meshes / oxc_cull_meshlets (and the InstCull refresh of
+ * the triangle passes) read projection_view / position / near_clip / resolution / acceptable_lod_error from it instead of from the
+ * by-value copy of their `camera` argument, so a captured frame replays with whatever camera the host copied into the buffer
+ * before the launch (the host mirror's oxr_submit does exactly that).  The `camera` argument is still required: host-side
+ * decisions (mesh_instance_count, "same camera as the InstCull cache") use it; pass the same camera for every pass of a frame.
+ * NULL unbinds. */
+int oxc_bind_camera_buffer(OxcContext* ctx, const OxcCullCamera* camera_dev);
+/* Fills a device camera buffer from PINNED host memory (cudaMallocHost / cudaHostRegister) with a kernel that reads the 96
+ * bytes over the bus: capturable, re-reads the host location at every replay, and does not occupy a copy engine. */
+int oxc_load_camera(OxcContext* ctx, OxcCullCamera* camera_dev, const OxcCullCamera* camera_pinned_host, void* stream);
 /* The Hi-Z pyramid was written through OxcOutputs::hiz by something other than an oxc_* call (an external reduce,
  * a terrain pass): the early pass may no longer assume the per-frame cleared image. */
 int oxc_mark_hiz_dirty(OxcContext* ctx);

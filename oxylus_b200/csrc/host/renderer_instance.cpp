@@ -83,6 +83,13 @@ RendererInstance::RendererInstance(int device, const OxcCreateInfo& info, uint32
     sl.ev_compute = e0;
     sl.ev_copy = e1;
   }
+  for (int k = 0; k < 2; k++) {
+    ok = ok && cudaMalloc(&d_cam_[k], sizeof(OxcCullCamera)) == cudaSuccess && cudaMallocHost(&h_cam_[k], sizeof(OxcCullCamera)) == cudaSuccess;
+  }
+  {
+    const char* e = std::getenv("OXR_NO_GRAPH");
+    use_graphs_ = !(e && e[0] == '1');
+  }
   if (!ok && error_.empty()) error_ = std::string("RendererInstance pipeline allocation failed: ") + cudaGetErrorString(cudaGetLastError());
 }
 
@@ -97,6 +104,8 @@ RendererInstance::~RendererInstance() {
     if (sl.ev_compute) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_compute));
     if (sl.ev_copy) cudaEventDestroy(static_cast<cudaEvent_t>(sl.ev_copy));
   }
+  drop_graphs();
+  for (int k = 0; k < 2; k++) { cudaFree(d_cam_[k]); if (h_cam_[k]) cudaFreeHost(h_cam_[k]); }
   if (ev_window_) cudaEventDestroy(static_cast<cudaEvent_t>(ev_window_));
   if (copy_stream_) cudaStreamDestroy(static_cast<cudaStream_t>(copy_stream_));
   if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
@@ -107,6 +116,8 @@ RendererInstance::~RendererInstance() {
 auto RendererInstance::update(const RendererInstanceUpdateInfo& info) -> int {
   if (!ctx_) return OXC_E_STATE;
   error_.clear();
+  drop_graphs(); // the scene tables may be reallocated: captured launches would keep the old addresses
+  oxc_bind_camera_buffer(ctx_, nullptr);
   return fail(oxc_set_scene(ctx_, &info.scene, stream_));
 }
 
@@ -154,15 +165,18 @@ auto RendererInstance::draw_for_visbuffer(MainGeometryContext& context) -> int {
                                    context.visbuffer_attachment, 0, stream_));
 }
 
-// The geometry section of RendererInstance::render (RendererInstance.cpp:768-884), enqueued on stream_.
-int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback, bool readback_on_device) {
+// The geometry section of RendererInstance::render (RendererInstance.cpp:768-884), enqueued on stream_, in two halves: the
+// pipelined path sends the previous frame's results to the host between them (flush_pending_copy), and replays each half
+// from a CUDA graph.
+//   head: attachments cleared, run_geometry_pass(false) up to and including its cull          (:562-588, :842-870)
+//   tail: its draw, generate_hiz, run_geometry_pass(true)                                      (:871-884)
+int RendererInstance::frame_head(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback, bool readback_on_device) {
   cudaStream_t s = static_cast<cudaStream_t>(stream_);
   const size_t px = (size_t)width_ * height_;
   int rc;
   OxcOutputs out;
   if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return rc;
   Readback* rb = static_cast<Readback*>(readback);
-
   // attachments: depth cleared to 0, vis buffer to ~0 (RendererInstance.cpp:562-571,629-680), Hi-Z cleared every frame (:579-588)
   if (occluder_depth_host) {
     if (cudaMemcpyAsync(d_occluder_, occluder_depth_host, px * 4, cudaMemcpyHostToDevice, s) != cudaSuccess) return OXC_E_CUDA;
@@ -173,48 +187,110 @@ int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occlud
   if (rc != OXC_OK) return rc;
   if ((rc = oxc_clear_hiz(ctx_, s)) != OXC_OK) return rc;
   g_trace.mark(s);
-  MainGeometryContext main_geometry_context;
-  main_geometry_context.visbuffer_attachment = d_vis64_;
-  main_geometry_context.width = width_;
-  main_geometry_context.height = height_;
+  if (readback_on_device) {
+    if (cudaMemsetAsync(rb->draw_index_count, 0, sizeof rb->draw_index_count, s) != cudaSuccess) return OXC_E_CUDA;
+  } else {
+    rb->draw_index_count[0] = rb->draw_index_count[1] = 0;
+  }
   // RendererInstance.cpp:796-800: hoisted so the early pass's visibility / dispatch buffers persist into the late pass
   CullGeometryContext cull_geometry_context;
   cull_geometry_context.use_hiz = true;
   cull_geometry_context.init_cull_meshes = true;
   cull_geometry_context.cull_camera = camera;
   cull_geometry_context.materialize_indices = out.reordered_indices != nullptr;
+  if ((rc = cull_geometry(cull_geometry_context)) != OXC_OK) return rc; // run_geometry_pass(false), cull half
+  g_trace.mark(s);
+  return OXC_OK;
+}
 
-  int pass_index = 0;
-  const auto run_geometry_pass = [&](bool late) -> int { // RendererInstance.cpp:842-881
-    if (late) {
-      cull_geometry_context.cull_flags |= OXC_CULL_LATE_PASS;
-      cull_geometry_context.init_cull_meshes = false;
-      cull_geometry_context.cull_camera = camera;
-    }
-    int r = cull_geometry(cull_geometry_context);
-    if (r != OXC_OK) return r;
-    g_trace.mark(s);
-    if (!late && pending_.active && (r = flush_pending_copy(true)) != OXC_OK) return r; // previous frame's results go out now
-    if (cull_geometry_context.materialize_indices)
-      if (cudaMemcpyAsync(&rb->draw_index_count[pass_index], &out.draw_cmd->index_count, 4, cudaMemcpyDefault, s) != cudaSuccess)
-        return OXC_E_CUDA;
-    pass_index++;
-    main_geometry_context.cull_flags = cull_geometry_context.cull_flags;
-    main_geometry_context.cull_camera = cull_geometry_context.cull_camera;
-    r = draw_for_visbuffer(main_geometry_context);
-    g_trace.mark(s);
-    return r;
-  };
-
-  if (readback_on_device) {
-    if (cudaMemsetAsync(rb->draw_index_count, 0, sizeof rb->draw_index_count, s) != cudaSuccess) return OXC_E_CUDA;
-  } else {
-    rb->draw_index_count[0] = rb->draw_index_count[1] = 0;
-  }
-  if ((rc = run_geometry_pass(false)) != OXC_OK) return rc; // :882
+int RendererInstance::frame_tail(const OxcCullCamera& camera, void* readback) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  int rc;
+  OxcOutputs out;
+  if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return rc;
+  Readback* rb = static_cast<Readback*>(readback);
+  const bool materialize = out.reordered_indices != nullptr;
+  MainGeometryContext main_geometry_context;
+  main_geometry_context.visbuffer_attachment = d_vis64_;
+  main_geometry_context.width = width_;
+  main_geometry_context.height = height_;
+  main_geometry_context.cull_camera = camera;
+  // run_geometry_pass(false), draw half (:871-881)
+  if (materialize && cudaMemcpyAsync(&rb->draw_index_count[0], &out.draw_cmd->index_count, 4, cudaMemcpyDefault, s) != cudaSuccess) return OXC_E_CUDA;
+  main_geometry_context.cull_flags = OXC_CULL_TEST_ALL;
+  if ((rc = draw_for_visbuffer(main_geometry_context)) != OXC_OK) return rc;
+  g_trace.mark(s);
   if ((rc = generate_hiz(main_geometry_context)) != OXC_OK) return rc; // :883
   g_trace.mark(s);
-  if ((rc = run_geometry_pass(true)) != OXC_OK) return rc;  // :884
+  // run_geometry_pass(true) (:884): cull_flags |= LatePass, init_cull_meshes = false
+  CullGeometryContext cull_geometry_context;
+  cull_geometry_context.use_hiz = true;
+  cull_geometry_context.init_cull_meshes = false;
+  cull_geometry_context.cull_flags = OXC_CULL_TEST_ALL | OXC_CULL_LATE_PASS;
+  cull_geometry_context.cull_camera = camera;
+  cull_geometry_context.materialize_indices = materialize;
+  if ((rc = cull_geometry(cull_geometry_context)) != OXC_OK) return rc;
+  g_trace.mark(s);
+  if (materialize && cudaMemcpyAsync(&rb->draw_index_count[1], &out.draw_cmd->index_count, 4, cudaMemcpyDefault, s) != cudaSuccess) return OXC_E_CUDA;
+  main_geometry_context.cull_flags = cull_geometry_context.cull_flags;
+  if ((rc = draw_for_visbuffer(main_geometry_context)) != OXC_OK) return rc;
+  g_trace.mark(s);
+  return OXC_OK;
+}
+
+int RendererInstance::run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback, bool readback_on_device) {
+  int rc;
+  if ((rc = frame_head(camera, occluder_depth_host, readback, readback_on_device)) != OXC_OK) return rc;
+  if (pending_.active && (rc = flush_pending_copy(true)) != OXC_OK) return rc; // previous frame's results go out now
+  return frame_tail(camera, readback);
+}
+
+// results of the frame -> the slot's device staging (drained by wait() of the slot's previous ticket)
+int RendererInstance::stage_results(int slot, bool want_vis32, bool want_depth, uint32_t n_ids) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  Slot& sl = slots_[slot];
+  int rc;
+  OxcOutputs out;
+  if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return rc;
+  Readback* dc = static_cast<Readback*>(sl.d_counters);
+  if (want_vis32 || want_depth)
+    if ((rc = oxc_resolve_visbuffer(ctx_, d_vis64_, width_, height_, want_vis32 ? sl.d_vis32 : nullptr, want_depth ? sl.d_depth : nullptr, s)) != OXC_OK)
+      return rc;
+  if (n_ids && cudaMemcpyAsync(sl.d_ids, out.visible_meshlet_instances_indices, (size_t)n_ids * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+    return OXC_E_CUDA;
+  if (cudaMemcpyAsync(&dc->visibility, out.visibility, sizeof dc->visibility, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return OXC_E_CUDA;
+  if (cudaMemcpyAsync(&dc->raster_triangles, out.raster_triangle_count, 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return OXC_E_CUDA;
+  return OXC_OK;
+}
+
+void RendererInstance::drop_graphs() {
+  for (auto& g : graphs_) {
+    if (g.head) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(g.head));
+    if (g.tail) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(g.tail));
+    g = FrameGraph();
+  }
+}
+
+// Captures one half of the frame into an executable graph.  `body` enqueues on stream_.  On any failure the capture is ended,
+// graphs are switched off for this renderer and the caller falls back to eager launches.
+template <typename Body>
+int RendererInstance::capture(void** exec_out, Body body) {
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  *exec_out = nullptr;
+  if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); return OXC_E_CUDA; }
+  const int rc = body();
+  cudaGraph_t graph = nullptr;
+  const cudaError_t e = cudaStreamEndCapture(s, &graph);
+  if (rc != OXC_OK || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    return rc != OXC_OK ? rc : OXC_E_CUDA;
+  }
+  cudaGraphExec_t exec = nullptr;
+  const cudaError_t ei = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ei != cudaSuccess) { cudaGetLastError(); return OXC_E_CUDA; }
+  *exec_out = exec;
   return OXC_OK;
 }
 
@@ -228,6 +304,7 @@ auto RendererInstance::render(const OxcCullCamera& camera, const float* occluder
   OxcOutputs out;
   if ((rc = oxc_get_outputs(ctx_, &out)) != OXC_OK) return fail(rc);
   Readback* rb = static_cast<Readback*>(h_pinned_);
+  if ((rc = oxc_bind_camera_buffer(ctx_, nullptr)) != OXC_OK) return fail(rc); // the graph path may have left a device camera bound
   if ((rc = run_frame(camera, occluder_depth_host, rb, false)) != OXC_OK) return fail(rc);
 
   // results back to the host (the engine would hand the attachments to decode_visbuffer, :923-925)
@@ -282,16 +359,48 @@ auto RendererInstance::submit(const OxcCullCamera& camera, uint32_t* vis32_host,
     g_trace.cur_slot = slot;
     g_trace.n_stage = 0;
   }
-  if ((rc = run_frame(camera, nullptr, dc, true)) != OXC_OK) return fail(rc);
-  // stage the results of this frame (the staging of this slot was drained by wait() of its previous ticket)
-  if (vis32_host || depth_host)
-    if ((rc = oxc_resolve_visbuffer(ctx_, d_vis64_, width_, height_, vis32_host ? sl.d_vis32 : nullptr, depth_host ? sl.d_depth : nullptr, s)) != OXC_OK)
-      return fail(rc);
-  uint32_t n_ids = visible_indices_host ? (visible_indices_capacity < ids_capacity_ ? visible_indices_capacity : ids_capacity_) : 0;
-  if (n_ids && cudaMemcpyAsync(sl.d_ids, out.visible_meshlet_instances_indices, (size_t)n_ids * 4, cudaMemcpyDeviceToDevice, s) != cudaSuccess)
-    return fail(OXC_E_CUDA);
-  if (cudaMemcpyAsync(&dc->visibility, out.visibility, sizeof dc->visibility, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(OXC_E_CUDA);
-  if (cudaMemcpyAsync(&dc->raster_triangles, out.raster_triangle_count, 8, cudaMemcpyDeviceToDevice, s) != cudaSuccess) return fail(OXC_E_CUDA);
+  const bool want_vis32 = vis32_host != nullptr, want_depth = depth_host != nullptr;
+  const uint32_t n_ids = visible_indices_host ? (visible_indices_capacity < ids_capacity_ ? visible_indices_capacity : ids_capacity_) : 0;
+  // Steady state: both halves of the frame replay from CUDA graphs (one pair per slot).  The camera reaches the kernels through
+  // a device buffer (oxc_bind_camera_buffer) that the head graph fills from this slot's pinned copy, so a replay only needs the
+  // new camera written there.  Everything else a graph bakes in is part of its key; a mismatch re-captures.
+  bool done = false;
+  if (use_graphs_ && !g_trace.on && out.reordered_indices == nullptr && d_cam_[slot] && h_cam_[slot]) {
+    FrameGraph& g = graphs_[slot];
+    const uint32_t key = (has_external_depth_ ? 1u : 0u) | (want_vis32 ? 2u : 0u) | (want_depth ? 4u : 0u);
+    *static_cast<OxcCullCamera*>(h_cam_[slot]) = camera;
+    if ((rc = oxc_bind_camera_buffer(ctx_, static_cast<const OxcCullCamera*>(d_cam_[slot]))) != OXC_OK) return fail(rc);
+    if (!g.head || !g.tail || g.key != key || g.n_ids != n_ids || g.mesh_instance_count != camera.mesh_instance_count) {
+      if (g.head) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(g.head));
+      if (g.tail) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(g.tail));
+      g = FrameGraph();
+      int rc_a = capture(&g.head, [&]() -> int {
+        const int r = oxc_load_camera(ctx_, static_cast<OxcCullCamera*>(d_cam_[slot]), static_cast<const OxcCullCamera*>(h_cam_[slot]), s);
+        return r != OXC_OK ? r : frame_head(camera, nullptr, dc, true);
+      });
+      int rc_b = rc_a == OXC_OK ? capture(&g.tail, [&]() -> int {
+        const int r = frame_tail(camera, dc);
+        return r != OXC_OK ? r : stage_results(slot, want_vis32, want_depth, n_ids);
+      }) : rc_a;
+      if (rc_a != OXC_OK || rc_b != OXC_OK) { // capture is not available here: eager launches from now on
+        drop_graphs();
+        use_graphs_ = false;
+      } else {
+        g.key = key; g.n_ids = n_ids; g.mesh_instance_count = camera.mesh_instance_count;
+      }
+    }
+    if (use_graphs_) {
+      if (cudaGraphLaunch(static_cast<cudaGraphExec_t>(g.head), s) != cudaSuccess) return fail(OXC_E_CUDA);
+      if (pending_.active && (rc = flush_pending_copy(true)) != OXC_OK) return fail(rc);
+      if (cudaGraphLaunch(static_cast<cudaGraphExec_t>(g.tail), s) != cudaSuccess) return fail(OXC_E_CUDA);
+      done = true;
+    }
+  }
+  if (!done) {
+    if ((rc = oxc_bind_camera_buffer(ctx_, nullptr)) != OXC_OK) return fail(rc);
+    if ((rc = run_frame(camera, nullptr, dc, true)) != OXC_OK) return fail(rc);
+    if ((rc = stage_results(slot, want_vis32, want_depth, n_ids)) != OXC_OK) return fail(rc);
+  }
   if (cudaEventRecord(static_cast<cudaEvent_t>(sl.ev_compute), s) != cudaSuccess) return fail(OXC_E_CUDA);
   // the device -> host copies are issued later, from inside the next frame (or by wait()): see PendingCopy
   if (g_trace.on) cudaEventRecord(g_trace.ev[slot][1], s);

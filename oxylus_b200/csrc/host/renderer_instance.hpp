@@ -79,7 +79,21 @@ public:
 private:
   int fail(int rc);
   int run_frame(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback_draw_counts, bool readback_on_device);
+  int frame_head(const OxcCullCamera& camera, const float* occluder_depth_host, void* readback_draw_counts, bool readback_on_device);
+  int frame_tail(const OxcCullCamera& camera, void* readback_draw_counts);
+  int stage_results(int slot, bool want_vis32, bool want_depth, uint32_t n_ids);
+  template <typename Body> int capture(void** exec_out, Body body);
+  void drop_graphs();
   int flush_pending_copy(bool behind_window);
+  // submit(): the two halves of a frame as executable CUDA graphs, one pair per slot (OXR_NO_GRAPH=1 disables)
+  struct FrameGraph {
+    void* head = nullptr;
+    void* tail = nullptr;
+    uint32_t key = 0, n_ids = 0, mesh_instance_count = 0;
+  } graphs_[2];
+  void* d_cam_[2] = {nullptr, nullptr}; // device camera the graph's kernels read (oxc_bind_camera_buffer)
+  void* h_cam_[2] = {nullptr, nullptr}; // pinned source of the head graph's camera upload
+  bool use_graphs_ = true;
   struct Slot {
     uint32_t* d_vis32 = nullptr;
     float* d_depth = nullptr;

@@ -33,11 +33,14 @@ struct MeshesParams {
   uint32_t flags;
   int select;            // 1: full cull_meshes (frustum + LOD select + counts); 0: refresh InstCull for a new camera only
   OxcCullCamera cam;
+  const OxcCullCamera* cam_dev; // oxc_bind_camera_buffer: read the camera from device memory (CUDA-graph replays with a new camera)
 };
 
 // cull_meshes.slang:17-61 — one thread per mesh instance of the shard.  Besides the reference's outputs
 // (lod_index write-back, meshlet count) it materialises InstCull / InstGeom for the later passes.
-__global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __grid_constant__ MeshesParams p) {
+__global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __grid_constant__ MeshesParams pp) {
+  const MeshesParams& p = pp;
+  const OxcCullCamera& cam = pp.cam_dev ? *pp.cam_dev : pp.cam;
   const uint32_t local = blockIdx.x * CULL_MESHES_THREADS + threadIdx.x;
   uint32_t meshlet_count = 0;
   if (local < p.count) {
@@ -52,7 +55,7 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __gri
       w[k * 4 + 0] = c.x; w[k * 4 + 1] = c.y; w[k * 4 + 2] = c.z; w[k * 4 + 3] = c.w;
     }
     float4 rows[4], planes[6];
-    mul_mm_rows(p.cam.projection_view, w, rows); // :32
+    mul_mm_rows(cam.projection_view, w, rows); // :32
     frustum_planes(rows, planes);
     const OxcMeshLOD* lods = reinterpret_cast<const OxcMeshLOD*>(mesh->lods);
     uint32_t lod_index = inst.lod_index;
@@ -69,14 +72,14 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __gri
           const float ex = fabsf(row_dot4(w0, bex, bey, bez, 0.0f)), ey = fabsf(row_dot4(w1, bex, bey, bez, 0.0f)),
                       ez = fabsf(row_dot4(w2, bex, bey, bez, 0.0f));
           const float rough_extent = omax(ex, omax(ey, ez));
-          const float dist = omax(fs(length3(fs(cx, p.cam.position[0]), fs(cy, p.cam.position[1]), fs(cz, p.cam.position[2])),
+          const float dist = omax(fs(length3(fs(cx, cam.position[0]), fs(cy, cam.position[1]), fs(cz, cam.position[2])),
                                      fm(0.5f, rough_extent)), 0.0f);
-          const float pixel_size_at_1m = fd(2.0f, omax(p.cam.resolution[0], p.cam.resolution[1]));
+          const float pixel_size_at_1m = fd(2.0f, omax(cam.resolution[0], cam.resolution[1]));
           const float aabb_size_at_1m = fd(rough_extent, dist);
           const float rough_pixel_size = fd(aabb_size_at_1m, pixel_size_at_1m);
           for (uint32_t i = 1; i < mesh->lod_count; i++) {
             const float err = fm(rough_pixel_size, lods[i].error);
-            if (err < p.cam.acceptable_lod_error) lod_index = i;
+            if (err < cam.acceptable_lod_error) lod_index = i;
             else break;
           }
         }
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __gri
 // under this camera (same frustum test + LOD selection as k_cull_meshes, count only).  Every rank can evaluate it
 // locally because the small tables are replicated; integer sum => order independent.
 __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_count_prefix_meshlets(const __grid_constant__ MeshesParams p, uint32_t* id_base) {
+  const OxcCullCamera& cam = p.cam_dev ? *p.cam_dev : p.cam;
   const uint32_t mi = blockIdx.x * CULL_MESHES_THREADS + threadIdx.x;
   uint32_t meshlet_count = 0;
   if (mi < p.first) {
@@ -192,7 +196,7 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_count_prefix_meshlets(c
 #pragma unroll
     for (int k = 0; k < 16; k++) w[k] = world[k];
     float4 rows[4], planes[6];
-    mul_mm_rows(p.cam.projection_view, w, rows);
+    mul_mm_rows(cam.projection_view, w, rows);
     frustum_planes(rows, planes);
     const OxcMeshLOD* lods = reinterpret_cast<const OxcMeshLOD*>(mesh->lods);
     const float bcx = mesh->bounds.aabb_center[0], bcy = mesh->bounds.aabb_center[1], bcz = mesh->bounds.aabb_center[2];
@@ -206,12 +210,12 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_count_prefix_meshlets(c
         const float ex = fabsf(row_dot4(w0, bex, bey, bez, 0.0f)), ey = fabsf(row_dot4(w1, bex, bey, bez, 0.0f)),
                     ez = fabsf(row_dot4(w2, bex, bey, bez, 0.0f));
         const float rough_extent = omax(ex, omax(ey, ez));
-        const float dist = omax(fs(length3(fs(cx, p.cam.position[0]), fs(cy, p.cam.position[1]), fs(cz, p.cam.position[2])),
+        const float dist = omax(fs(length3(fs(cx, cam.position[0]), fs(cy, cam.position[1]), fs(cz, cam.position[2])),
                                    fm(0.5f, rough_extent)), 0.0f);
-        const float pixel_size_at_1m = fd(2.0f, omax(p.cam.resolution[0], p.cam.resolution[1]));
+        const float pixel_size_at_1m = fd(2.0f, omax(cam.resolution[0], cam.resolution[1]));
         const float rough_pixel_size = fd(fd(rough_extent, dist), pixel_size_at_1m);
         for (uint32_t i = 1; i < mesh->lod_count; i++) {
-          if (fm(rough_pixel_size, lods[i].error) < p.cam.acceptable_lod_error) lod_index = i;
+          if (fm(rough_pixel_size, lods[i].error) < cam.acceptable_lod_error) lod_index = i;
           else break;
         }
       }
@@ -439,10 +443,19 @@ struct CullWarp {
   Shared& sh;
   const uint32_t lane, warp, lane_lt;
   const uint32_t early_count, id_base;
+  float cam_pos[3], near_clip; // from the kernel parameters, or from the bound device camera
   uint32_t n0 = 0, n1 = 0, n2 = 0, ne = 0; // warp-uniform fill levels
 
   OXC_DI CullWarp(const CullParams& p_, Shared& sh_, uint32_t early, uint32_t idb)
-      : p(p_), sh(sh_), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), lane_lt((1u << (threadIdx.x & 31)) - 1u), early_count(early), id_base(idb) {}
+      : p(p_), sh(sh_), lane(threadIdx.x & 31), warp(threadIdx.x >> 5), lane_lt((1u << (threadIdx.x & 31)) - 1u), early_count(early), id_base(idb) {
+    if (p_.cam_dev) {
+      cam_pos[0] = p_.cam_dev->position[0]; cam_pos[1] = p_.cam_dev->position[1]; cam_pos[2] = p_.cam_dev->position[2];
+      near_clip = p_.cam_dev->near_clip;
+    } else {
+      cam_pos[0] = p_.cam_pos[0]; cam_pos[1] = p_.cam_pos[1]; cam_pos[2] = p_.cam_pos[2];
+      near_clip = p_.near_clip;
+    }
+  }
 
   // ---- survivor staging: one pair of global atomics per flush ----
   OXC_DI void flush() {
@@ -496,7 +509,7 @@ struct CullWarp {
       const InstCull* ic = p.inst + b.z;
       const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
       ScreenAabb sa;
-      if (project_aabb(r0, r1, r2, r3, p.near_clip, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
+      if (project_aabb(r0, r1, r2, r3, near_clip, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w),
                        __uint_as_float(b.x), __uint_as_float(b.y), sa))
         visible = !test_occlusion(sa, p.hiz.data, p.hiz.width, p.hiz.height, p.hiz.levels, sh.hiz_off);
     }
@@ -519,7 +532,7 @@ struct CullWarp {
       vi = c & 0x7FFFFFFFu; was = (c >> 31) != 0; idx = b.w;
       const InstCull* ic = p.inst + b.z;
       const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
-      t = occlusion_visible_fast(r0, r1, r2, r3, p.near_clip, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z),
+      t = occlusion_visible_fast(r0, r1, r2, r3, near_clip, __uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z),
                                  __uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y), p.hiz.data, p.hiz.width, p.hiz.height,
                                  p.hiz.levels, sh.hiz_off, __ldg(&ic->nrm[1].w) != 0.0f);
     }
@@ -563,7 +576,7 @@ struct CullWarp {
 #endif
         const ConeInputs ci = cone_inputs(ic, cx, cy, cz, ex, ey, ez, sh.s8_lut[(((b.y >> 16) & 0xFFu) + 128u) & 0xFFu],
                                           sh.s8_lut[((b.y >> 24) + 128u) & 0xFFu], sh.s8_lut[(((b.w >> 16) & 0xFFu) + 128u) & 0xFFu],
-                                          p.cam_pos[0], p.cam_pos[1], p.cam_pos[2]);
+                                          cam_pos[0], cam_pos[1], cam_pos[2]);
         const Tri t = cone_visible_fast(ci, cutoff);
         visible = t == TRI_AMBIGUOUS ? cone_visible_exact(ci, cutoff) : (t == TRI_TRUE);
       }

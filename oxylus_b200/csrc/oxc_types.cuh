@@ -74,6 +74,7 @@ struct CullParams {
   HizDesc hiz;
   float cam_pos[3];
   float near_clip;
+  const OxcCullCamera* cam_dev; // non-null: position / near_clip are read from this device camera instead
 };
 
 } // namespace oxc

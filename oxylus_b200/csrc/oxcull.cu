@@ -165,6 +165,7 @@ struct OxcContext {
     uint32_t* cnt_all[2] = {nullptr, nullptr};
     uint32_t* ids_all[2] = {nullptr, nullptr};
   } mg;
+  const OxcCullCamera* cam_dev = nullptr; // oxc_bind_camera_buffer
   uint32_t* d_status = nullptr;   // sticky OXC_STATUS_* bits raised by kernels
   std::vector<uint64_t> id_prefix; // [I + 1] prefix sums of the largest-LOD meshlet count per mesh instance (host side)
   uint64_t scene_id_bound = 0;    // upper bound of the GLOBAL meshlet-instance id range (sum over all mesh instances of the largest LOD)
@@ -217,7 +218,7 @@ int refresh_inst_cache(OxcContext* c, const OxcCullCamera* cam, cudaStream_t s) 
   p.meshes = c->d_meshes; p.mesh_instances = c->d_mesh_instances; p.transforms = c->d_transforms;
   p.inst = c->d_inst; p.geom = c->d_geom; p.counts = c->d_counts; p.block_sums = c->d_block_sums; p.lod_aabb = c->d_lod_aabb;
   shard_range(c, c->cached_cam.mesh_instance_count, &p.first, &p.count);
-  p.flags = 0; p.select = 0; p.cam = *cam;
+  p.flags = 0; p.select = 0; p.cam = *cam; p.cam_dev = c->cam_dev;
   if (p.count) {
     k_cull_meshes<<<(p.count + CULL_MESHES_THREADS - 1) / CULL_MESHES_THREADS, CULL_MESHES_THREADS, 0, s>>>(p);
     LAUNCHED();
@@ -557,7 +558,7 @@ int oxc_cull_meshes(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, voi
   p.meshes = c->d_meshes; p.mesh_instances = c->d_mesh_instances; p.transforms = c->d_transforms;
   p.inst = c->d_inst; p.geom = c->d_geom; p.counts = c->d_counts; p.block_sums = c->d_block_sums; p.lod_aabb = c->d_lod_aabb;
   shard_range(c, cam->mesh_instance_count, &p.first, &p.count);
-  p.flags = flags; p.select = 1; p.cam = *cam;
+  p.flags = flags; p.select = 1; p.cam = *cam; p.cam_dev = c->cam_dev;
   if (c->id_base_auto) { // global id base of this shard = meshlets emitted by the mesh instances below it (no communication)
     CK(cudaMemsetAsync(c->d_id_base_auto, 0, 4, s));
     if (p.first) {
@@ -597,6 +598,7 @@ int oxc_cull_meshlets(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, i
   p.mask = c->d_mask; p.tri_cmd = c->d_cull_triangles_cmd; p.id_base = c->id_base; p.hiz = c->hiz;
   p.cam_pos[0] = cam->position[0]; p.cam_pos[1] = cam->position[1]; p.cam_pos[2] = cam->position[2];
   p.near_clip = cam->near_clip;
+  p.cam_dev = c->cam_dev;
   // the plain variant is dispatched with TestFrustum only (CullGeometry.cpp:275,298) and has no mask / late logic
   const bool hizp = use_hiz != 0;
   const bool occ = hizp && (flags & OXC_CULL_TEST_OCCLUSION) != 0;
@@ -1043,6 +1045,28 @@ int oxc_check_status(OxcContext* c, void* stream, uint32_t* flags_out) {
 
 // instrumentation builds (-DOXC_RASTER_STATS): device pointer of the 128 u64 statistics slots behind the chunk queue
 void* oxc_debug_stats_ptr(OxcContext* c) { return c ? static_cast<void*>(c->d_big_queue + (size_t)c->big_capacity * 4) : nullptr; }
+
+// 96 bytes from pinned (mapped) host memory into the device camera buffer by a kernel: inside a captured frame this keeps the
+// copy engines out of the frame's critical path (they are busy with the previous frame's read-back)
+__global__ void k_load_camera(OxcCullCamera* dst, const OxcCullCamera* src_pinned) {
+  if (threadIdx.x < sizeof(OxcCullCamera) / 4)
+    reinterpret_cast<uint32_t*>(dst)[threadIdx.x] = reinterpret_cast<const volatile uint32_t*>(src_pinned)[threadIdx.x];
+}
+
+int oxc_load_camera(OxcContext* c, OxcCullCamera* camera_dev, const OxcCullCamera* camera_pinned_host, void* stream) {
+  if (!c || !camera_dev || !camera_pinned_host) return fail(OXC_E_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  k_load_camera<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(camera_dev, camera_pinned_host);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+int oxc_bind_camera_buffer(OxcContext* c, const OxcCullCamera* camera_dev) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  c->cam_dev = camera_dev;
+  c->cache_valid = c->cache_valid && camera_dev == nullptr; // whatever InstCull holds was built for some other camera
+  return OXC_OK;
+}
 
 int oxc_mark_hiz_dirty(OxcContext* c) {
   if (!c) return fail(OXC_E_INVALID, "null context");
