@@ -290,19 +290,21 @@ def main():
     pipe = pipeline.VisibilityPipeline(scene, device=local_rank, shard=shard, auto_id_base=True, shard_capacity=cap, wide_ids=wide_ids)
     cams = [scene.camera(0.0), scene.camera(2.0)]
     if multi:
-        # survivor gather segments (ncclAllGather needs one size for all ranks): sized from four LOCAL frames — a rank that only
-        # sees its own occluders keeps MORE survivors than it will with everybody's Hi-Z — times two, max over ranks.
-        # Exceeding it later is a hard error (OXC_STATUS_SURVIVOR_OVERFLOW, checked below), never a silent truncation.
-        local_max = 0
+        # survivor gather segments (ncclAllGather moves whole segments, one size for all ranks): start with half a shard, run four
+        # real (exchanged) frames, then shrink to twice the largest survivor count any rank saw.  Exceeding the capacity later is
+        # a hard error (OXC_STATUS_SURVIVOR_OVERFLOW, checked below), never a silent truncation.
+        pipe.mgpu = pipe.ctx.mgpu_init(rank, world, uid[0], max(4096, cap // 2))
+        seen = 0
         for f in range(4):
             pipe.frame(cams[f % 2])
-            c_ = pipe.counters()
-            local_max = max(local_max, c_["early"] + c_["late"])
-        t_cap = torch.tensor([local_max], dtype=torch.int64)
-        dist.all_reduce(t_cap, op=dist.ReduceOp.MAX)
+            pipe.exchange_frame(slot=f & 1)
+            torch.cuda.synchronize()
+            cnt_w, _ = pipe.ctx.mgpu_gathered(f & 1)
+            seen = max(seen, int((cnt_w[:, 1] + cnt_w[:, 2]).max()))
+        pipe.ctx.check_status()
+        pipe.mgpu = pipe.ctx.mgpu_set_survivor_capacity(min(cap, max(4096, 2 * seen)))
         pipe.ctx.reset_visibility_mask()
         torch.cuda.synchronize()
-        pipe.mgpu = pipe.ctx.mgpu_init(rank, world, uid[0], min(cap, max(4096, 2 * int(t_cap.item()))))
     dev = pipe.device
     w, h = scene.width, scene.height
 

@@ -478,6 +478,10 @@ int oxc_mgpu_get_unique_id(uint8_t id[OXC_MGPU_ID_BYTES]);
 int oxc_mgpu_init(OxcContext* ctx, uint32_t rank, uint32_t world, const uint8_t id[OXC_MGPU_ID_BYTES],
                   uint32_t survivor_capacity /* 0 = max_meshlet_instances; the ranks agree on the largest value requested */);
 int oxc_mgpu_init_with_comm(OxcContext* ctx, void* nccl_comm, uint32_t survivor_capacity);
+/* Collective: changes the survivor segment capacity (the ranks agree on the largest value requested; gather buffers are
+ * reallocated, OxcMgpuInfo pointers change).  Typical use: init generously, run a few exchanged frames, shrink to a multiple of
+ * the survivor counts actually seen — the allgather moves whole segments. */
+int oxc_mgpu_set_survivor_capacity(OxcContext* ctx, uint32_t survivor_capacity);
 int oxc_mgpu_shutdown(OxcContext* ctx);
 int oxc_mgpu_info(OxcContext* ctx, OxcMgpuInfo* out);
 int oxc_mgpu_exchange_hiz(OxcContext* ctx, const uint64_t* vis_dev, uint32_t width, uint32_t height, void* stream);

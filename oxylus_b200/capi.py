@@ -22,7 +22,7 @@ SYMBOLS = [
     "oxc_decode_visbuffer", "oxc_build_hpb", "oxc_mark_visible_pages",
     "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_bind_camera_buffer", "oxc_load_camera", "oxc_debug_stats_ptr",
     "oxc_mgpu_get_unique_id", "oxc_mgpu_init", "oxc_mgpu_init_with_comm", "oxc_mgpu_shutdown", "oxc_mgpu_info", "oxc_mgpu_exchange_hiz",
-    "oxc_mgpu_exchange_frame", "oxc_mgpu_stage_survivors", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
+    "oxc_mgpu_exchange_frame", "oxc_mgpu_stage_survivors", "oxc_mgpu_set_survivor_capacity", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
 ]
@@ -93,6 +93,7 @@ def load(build_if_missing=True):
     lib.oxc_mgpu_exchange_hiz.argtypes = [vp, vp, u32, u32, vp]
     lib.oxc_mgpu_exchange_frame.argtypes = [vp, vp, u32, u32, i32, u32, vp]
     lib.oxc_mgpu_stage_survivors.argtypes = [vp, i32, vp]
+    lib.oxc_mgpu_set_survivor_capacity.argtypes = [vp, u32]
     lib.oxc_debug_stats_ptr.argtypes = [vp]
     lib.oxc_debug_stats_ptr.restype = vp
     lib.oxc_copy.argtypes = [vp, vp, vp, u64, i32, vp]
@@ -398,6 +399,10 @@ class Context:
     def mgpu_exchange_frame(self, vis_dev, w, h, slot=0, stream=None, already_staged=False):
         _check(self.lib.oxc_mgpu_exchange_frame(self.h, _ptr(vis_dev), w, h, slot, 1 if already_staged else 0,
                                                 self.stream if stream is None else stream), "oxc_mgpu_exchange_frame")
+
+    def mgpu_set_survivor_capacity(self, capacity):
+        _check(self.lib.oxc_mgpu_set_survivor_capacity(self.h, capacity), "oxc_mgpu_set_survivor_capacity")
+        return self.mgpu_info()
 
     def mgpu_shutdown(self):
         _check(self.lib.oxc_mgpu_shutdown(self.h), "oxc_mgpu_shutdown")

@@ -1259,6 +1259,33 @@ int oxc_mgpu_init_with_comm(OxcContext* c, void* nccl_comm, uint32_t survivor_ca
   return rc;
 }
 
+// Collective: the ranks agree on max(capacity) and reallocate the gather buffers.  For hosts that only learn how many
+// survivors a frame leaves once real (exchanged) frames have run: init generously, measure, shrink.
+int oxc_mgpu_set_survivor_capacity(OxcContext* c, uint32_t capacity) {
+  if (!c || capacity == 0) return fail(OXC_E_INVALID, "bad argument");
+  if (!c->mg.active) return fail(OXC_E_STATE, "oxc_mgpu_init first");
+  CK(cudaSetDevice(c->device));
+  CK(cudaDeviceSynchronize());
+  OxcContext::Mgpu& m = c->mg;
+  if (m.world > 1) {
+    uint32_t* d_cap = nullptr;
+    CK(cudaMalloc(&d_cap, 4));
+    CK(cudaMemcpy(d_cap, &capacity, 4, cudaMemcpyHostToDevice));
+    NCK(g_nccl.AllReduce(d_cap, d_cap, 1, ncclUint32, ncclMax, m.comm, nullptr));
+    CK(cudaStreamSynchronize(nullptr));
+    CK(cudaMemcpy(&capacity, d_cap, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_cap);
+  }
+  for (int k = 0; k < 2; k++) {
+    cudaFree(m.ids_stage[k]); cudaFree(m.ids_all[k]);
+    m.ids_stage[k] = m.ids_all[k] = nullptr;
+    CK(cudaMalloc(&m.ids_stage[k], (size_t)capacity * 4));
+    CK(cudaMalloc(&m.ids_all[k], (size_t)m.world * capacity * 4));
+  }
+  m.capacity = capacity;
+  return OXC_OK;
+}
+
 int oxc_mgpu_shutdown(OxcContext* c) {
   if (!c) return fail(OXC_E_INVALID, "null context");
   CK(cudaSetDevice(c->device));
