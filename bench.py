@@ -290,21 +290,9 @@ def main():
     pipe = pipeline.VisibilityPipeline(scene, device=local_rank, shard=shard, auto_id_base=True, shard_capacity=cap, wide_ids=wide_ids)
     cams = [scene.camera(0.0), scene.camera(2.0)]
     if multi:
-        # survivor gather segments (ncclAllGather moves whole segments, one size for all ranks): start with half a shard, run four
-        # real (exchanged) frames, then shrink to twice the largest survivor count any rank saw.  Exceeding the capacity later is
-        # a hard error (OXC_STATUS_SURVIVOR_OVERFLOW, checked below), never a silent truncation.
+        # survivor gather segments (ncclAllGather moves whole segments, one size for all ranks): half a shard to begin with — the
+        # cold frames (zeroed mask: everything that passes is a late survivor) need it; shrunk to steady state after the parity check
         pipe.mgpu = pipe.ctx.mgpu_init(rank, world, uid[0], max(4096, cap // 2))
-        seen = 0
-        for f in range(4):
-            pipe.frame(cams[f % 2])
-            pipe.exchange_frame(slot=f & 1)
-            torch.cuda.synchronize()
-            cnt_w, _ = pipe.ctx.mgpu_gathered(f & 1)
-            seen = max(seen, int((cnt_w[:, 1] + cnt_w[:, 2]).max()))
-        pipe.ctx.check_status()
-        pipe.mgpu = pipe.ctx.mgpu_set_survivor_capacity(min(cap, max(4096, 2 * seen)))
-        pipe.ctx.reset_visibility_mask()
-        torch.cuda.synchronize()
     dev = pipe.device
     w, h = scene.width, scene.height
 
@@ -351,6 +339,21 @@ def main():
             torch.cuda.empty_cache()
         barrier()
 
+    if multi:
+        # steady-state survivor counts from real (exchanged) frames -> gather capacity = twice the largest any rank saw.  The mask is
+        # NOT reset afterwards, so no cold frame follows; exceeding the capacity later is a hard error (OXC_STATUS_SURVIVOR_OVERFLOW,
+        # checked after the timed region), never a silent truncation.
+        seen = 0
+        for f in range(6):
+            pipe.select_buffer(0)
+            pipe.frame(cams[f % 2])
+            pipe.exchange_frame(slot=0)
+            torch.cuda.synchronize()
+            if f >= 4:
+                cnt_w, _ = pipe.ctx.mgpu_gathered(0)
+                seen = max(seen, int((cnt_w[:, 1] + cnt_w[:, 2]).max()))
+        pipe.ctx.check_status()
+        pipe.mgpu = pipe.ctx.mgpu_set_survivor_capacity(min(cap, max(4096, 2 * seen)))
     dbg("parity check done", parity)
     # ---------------- warm-up (also brings the visibility mask to steady state) ----------------
     W = max(4, args.warmup)  # >= 4 so the persistent visibility mask reaches its steady state
