@@ -586,8 +586,9 @@ int oxr_wait(OxrRenderer* r, int ticket, OxrFrameResult* result);
  * The four meshoptimizer v1.2 calls of the reference (not vendored in /root/reference) are restated from their
  * published definitions — fetch remap, quantizeHalf, quantizeSnorm, computeMeshletBounds' normal cone — and the clusteriser
  * (meshopt_buildMeshlets) by a greedy spatial clusteriser of the same scheme (cluster_mode 1; not bit-compatible with
- * meshoptimizer's clusters); the simplifier is NOT reproduced: coarser LODs are caller-supplied index buffers.  Meshlets hold
- * <= 64 vertices, <= 64 triangles (Model.hpp:27-28).
+ * meshoptimizer's clusters); coarser LODs are caller-supplied index buffers or (auto_lods) generated by an edge-collapse
+ * simplifier of meshopt_simplifyWithAttributes' scheme (oxb_simplify below).  Meshlets hold <= 64 vertices, <= 64 triangles
+ * (Model.hpp:27-28).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct OxbMeshInput {
   const float* positions;  /* vertex_count x 3 */
@@ -601,6 +602,10 @@ typedef struct OxbMeshInput {
   uint32_t cluster_mode;   /* 0: meshlets follow the caller's triangle order; 1: spatial clusteriser first (the role of
                               meshopt_buildMeshlets, AssetManager_GLTF.cpp:630-676): adjacency-first greedy growth, nearest
                               unused centroid when the meshlet has no unused neighbour */
+  uint32_t auto_lods;      /* 1: lod_count must be 1; LOD 1.. are generated like AssetManager_GLTF.cpp:596-641 — each simplified
+                              from the previous one to half its index count (normals as attributes, borders locked), MeshLOD::error
+                              = previous error + the step's relative error; the chain ends when the simplifier stalls more than
+                              50 % above its target, a step's error exceeds 0.5 or fewer than two triangles remain */
 } OxbMeshInput;
 typedef struct OxbMesh OxbMesh;
 const char* oxb_last_error(void);
@@ -611,6 +616,14 @@ uint32_t oxb_mesh_lod0_meshlet_count(const OxbMesh* m);   /* for MeshInstance::m
  * offset (also inside the copied MeshLOD table) rebased by base_offset: the tables OxcSceneDesc expects. */
 int oxb_mesh_emit(const OxbMesh* m, uint64_t base_offset, uint8_t* dst, OxcMesh* mesh_out);
 void oxb_mesh_free(OxbMesh* m);
+/* The role of meshopt_simplifyWithAttributes as build_gltf_mesh calls it (AssetManager_GLTF.cpp:604-628: attributes = normals
+ * with weight 1, meshopt_SimplifyLockBorder, relative error): edge collapses onto existing vertices, quadric error metric over
+ * positions + normal attribute quadrics per wedge, mesh borders locked, attribute seams kept closed, 2-manifolds stay
+ * 2-manifold.  dst holds index_count entries; returns the new index count (it may stay above target_index_count) or a negative
+ * OXC_E_* code.  normals may be NULL.  *result_error (may be NULL): largest position error of a performed collapse relative to
+ * the extent of the vertex buffer.  Same scheme as meshoptimizer, not its bits (csrc/host/mesh_simplifier.cpp). */
+int64_t oxb_simplify(uint32_t* dst, const uint32_t* indices, uint64_t index_count, const float* positions, const float* normals, uint32_t vertex_count,
+                     uint64_t target_index_count, float target_error, float* result_error);
 
 #ifdef __cplusplus
 }

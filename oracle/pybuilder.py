@@ -2,7 +2,8 @@
 build_gltf_mesh (Oxylus/src/Asset/AssetManager_GLTF.cpp:481-771) with the same substitutions the product makes for
 the meshoptimizer v1.2 calls (xmake/packages.lua:9; library absent from /root/reference and from this image):
 first-use fetch remap, meshopt_quantizeHalf / quantizeSnorm as published, Ritter-sphere normal cone as in
-meshopt_computeMeshletBounds, linear-scan meshlets instead of meshopt_buildMeshlets.
+meshopt_computeMeshletBounds, linear-scan meshlets instead of meshopt_buildMeshlets, the LOD chain of :596-641 over the
+edge-collapse simplifier restated in oracle/pysimplify.py.
 
 PARITY UNPINNED: nothing in the reference's tests pins meshlet build output, and meshoptimizer's own clustering is
 not reproduced.  Every float op below is an explicit np.float32 operation in the product's order (small inputs only:
@@ -67,7 +68,7 @@ def bounding_sphere(pts):
     return c, r
 
 
-def build(positions, lods, normals=None, texcoords=None, max_vertices=64, max_triangles=64):
+def build(positions, lods, normals=None, texcoords=None, max_vertices=64, max_triangles=64, auto_lods=False):
     """Returns dict(vertex_count, positions_q (V,4) u16, normals_q (V,) u32 | None, texcoords_q (V,2) u16 | None,
     remap, bounds_center/extent (f32 mesh bounds), lods=[dict(indices, meshlets (M,4) u32, bounds (M,) records as tuples,
     micro u8, vertex_indices u32, error)])."""
@@ -102,8 +103,17 @@ def build(positions, lods, normals=None, texcoords=None, max_vertices=64, max_tr
     fmax, flow = np.finfo(np.float32).max, np.finfo(np.float32).min
     mesh_min, mesh_max = np.full(3, fmax, dtype=np.float32), np.full(3, flow, dtype=np.float32)
     out["lods"] = []
-    for l, (idx_in, err) in enumerate(lods):
-        indices = remap[np.asarray(idx_in, dtype=np.uint32).reshape(-1)]
+    lods = [(remap[np.asarray(idx_in, dtype=np.uint32).reshape(-1)], err) for (idx_in, err) in lods]
+    if auto_lods:  # AssetManager_GLTF.cpp:596-641 in blob vertex numbering
+        import pysimplify
+
+        assert len(lods) == 1
+        nrm_blob = None
+        if normals is not None:
+            nrm_blob = np.zeros((vc, 3), dtype=np.float32)
+            nrm_blob[remap[used]] = np.asarray(normals, dtype=np.float32).reshape(-1, 3)[used]
+        lods = [(np.array(i, dtype=np.uint32), e) for (i, e) in pysimplify.lod_chain(lods[0][0], pos, nrm_blob, error0=lods[0][1])]
+    for l, (indices, err) in enumerate(lods):
         meshlets, vertex_indices, micro = [], [], []
         slot = {}
         cur = [0, 0, 0, 0]  # vertex_offset, triangle_offset, vertex_count, triangle_count

@@ -225,6 +225,7 @@ class MeshInput(C.Structure):
         ("lod_index_counts", C.c_uint32 * MESH_MAX_LODS),
         ("lod_errors", C.c_float * MESH_MAX_LODS),
         ("cluster_mode", C.c_uint32),
+        ("auto_lods", C.c_uint32),
     ]
 
 

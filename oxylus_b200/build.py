@@ -13,11 +13,11 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("OXC_LIB_PATH") or os.path.join(HERE, "liboxcull.so")
 
 SOURCES = [os.path.join(CSRC, "oxcull.cu"), os.path.join(CSRC, "host", "renderer_instance.cpp"),
-           os.path.join(CSRC, "host", "mesh_builder.cpp")]
+           os.path.join(CSRC, "host", "mesh_builder.cpp"), os.path.join(CSRC, "host", "mesh_simplifier.cpp")]
 DEPS = SOURCES + [
     os.path.join(CSRC, f)
     for f in ("oxc_types.cuh", "oxc_exact.cuh", "oxc_filtered.cuh", "oxc_tma.cuh", "kernels_cull.cuh", "kernels_decode.cuh", "kernels_hiz.cuh", "kernels_mgpu.cuh", "kernels_tri.cuh")
-] + [os.path.join(CSRC, "host", "renderer_instance.hpp"), os.path.join(os.path.dirname(HERE), "include", "oxcull.h")]
+] + [os.path.join(CSRC, "host", "renderer_instance.hpp"), os.path.join(CSRC, "host", "mesh_simplifier.hpp"), os.path.join(os.path.dirname(HERE), "include", "oxcull.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

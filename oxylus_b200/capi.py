@@ -23,7 +23,7 @@ SYMBOLS = [
     "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_bind_camera_buffer", "oxc_load_camera", "oxc_debug_stats_ptr",
     "oxc_mgpu_get_unique_id", "oxc_mgpu_init", "oxc_mgpu_init_with_comm", "oxc_mgpu_shutdown", "oxc_mgpu_info", "oxc_mgpu_exchange_hiz",
     "oxc_mgpu_exchange_frame", "oxc_mgpu_stage_survivors", "oxc_mgpu_set_survivor_capacity", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
-    "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free",
+    "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free", "oxb_simplify",
     "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
 ]
 
@@ -110,6 +110,8 @@ def load(build_if_missing=True):
     lib.oxb_mesh_emit.argtypes = [vp, u64, vp, vp]
     lib.oxb_mesh_free.argtypes = [vp]
     lib.oxb_mesh_free.restype = None
+    lib.oxb_simplify.argtypes = [vp, vp, u64, vp, vp, u32, u64, C.c_float, vp]
+    lib.oxb_simplify.restype = C.c_int64
     lib.oxr_create.argtypes = [i32, C.POINTER(abi.CreateInfo), u32, u32, C.POINTER(vp)]
     lib.oxr_destroy.argtypes = [vp]
     lib.oxr_destroy.restype = None
@@ -141,11 +143,25 @@ def _ptr(a):
     return C.c_void_p(int(a))
 
 
+def simplify(indices, positions, normals, target_index_count, target_error=3.4028234663852886e38):
+    """oxb_simplify: -> (new indices u32 array, result_error np.float32).  Host-only: works without a GPU."""
+    lib = load()
+    idx = np.ascontiguousarray(indices, dtype=np.uint32).reshape(-1)
+    pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
+    nrm = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    dst = np.zeros(max(idx.size, 1), dtype=np.uint32)
+    err = np.zeros(1, dtype=np.float32)
+    n = lib.oxb_simplify(_ptr(dst), _ptr(idx), idx.size, _ptr(pos), _ptr(nrm), len(pos), int(target_index_count), float(target_error), _ptr(err))
+    if n < 0:
+        raise OxcError(f"oxb_simplify failed ({n}): {lib.oxb_last_error().decode()}")
+    return dst[:n].copy(), err[0]
+
+
 class BuiltMesh:
     """OxbMesh wrapper: one mesh run through the host-side builder (oxb_build_mesh).  lods = [(indices, error), ...],
     LOD 0 first.  Host-only: works without a GPU."""
 
-    def __init__(self, positions, lods, normals=None, texcoords=None, spatial=False):
+    def __init__(self, positions, lods, normals=None, texcoords=None, spatial=False, auto_lods=False):
         self.lib = load()
         pos = np.ascontiguousarray(positions, dtype=np.float32).reshape(-1, 3)
         nrm = None if normals is None else np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
@@ -155,6 +171,7 @@ class BuiltMesh:
         mi.positions, mi.normals, mi.texcoords = _ptr(pos), _ptr(nrm), _ptr(tc)
         mi.vertex_count, mi.lod_count = len(pos), len(lods)
         mi.cluster_mode = 1 if spatial else 0
+        mi.auto_lods = 1 if auto_lods else 0
         for l, (a, (_, err)) in enumerate(zip(idx, lods)):
             mi.lod_indices[l] = a.ctypes.data
             mi.lod_index_counts[l] = a.size

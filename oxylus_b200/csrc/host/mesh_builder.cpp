@@ -15,8 +15,9 @@
 // meshopt_buildMeshlets: cluster_mode 1 runs a greedy spatial clusteriser of the same published scheme (adjacency-first
 // growth, nearest-centroid reseeding — spatial_triangle_order below), cluster_mode 0 keeps the caller's triangle order; either
 // way meshlets are then formed by a linear scan that closes a meshlet when the next triangle would exceed 64 vertices or 64
-// triangles (Model::MAX_MESHLET_INDICES / MAX_MESHLET_PRIMITIVES, Model.hpp:27-28).  meshopt_simplifyWithAttributes is NOT
-// reproduced: coarser LODs are index buffers the caller supplies.  PARITY UNPINNED against meshoptimizer.
+// triangles (Model::MAX_MESHLET_INDICES / MAX_MESHLET_PRIMITIVES, Model.hpp:27-28).  meshopt_simplifyWithAttributes: coarser
+// LODs are either index buffers the caller supplies or, with auto_lods, the chain of :596-641 produced by the edge-collapse
+// simplifier in mesh_simplifier.cpp.  PARITY UNPINNED against meshoptimizer.
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -26,6 +27,7 @@
 #include <vector>
 
 #include "../../../include/oxcull.h"
+#include "mesh_simplifier.hpp"
 
 namespace {
 
@@ -274,6 +276,8 @@ int oxb_build_mesh(const OxbMeshInput* in, OxbMesh** out) {
     return OXC_E_INVALID;
   }
   if (in->cluster_mode > 1) { g_builder_error = "cluster_mode must be 0 (caller order) or 1 (spatial)"; return OXC_E_INVALID; }
+  if (in->auto_lods > 1) { g_builder_error = "auto_lods must be 0 or 1"; return OXC_E_INVALID; }
+  if (in->auto_lods && in->lod_count != 1) { g_builder_error = "auto_lods generates LOD 1.. itself: pass LOD 0 only"; return OXC_E_INVALID; }
   for (uint32_t l = 0; l < in->lod_count; l++) {
     if (!in->lod_indices[l] || in->lod_index_counts[l] % 3u) { g_builder_error = "LOD index buffers must be triangle lists"; return OXC_E_INVALID; }
     for (uint32_t i = 0; i < in->lod_index_counts[l]; i++)
@@ -337,10 +341,39 @@ int oxb_build_mesh(const OxbMeshInput* in, OxbMesh** out) {
   std::memset(lods, 0, sizeof lods);
   const float FMAX = std::numeric_limits<float>::max(), FLOW = std::numeric_limits<float>::lowest();
   float mesh_min[3] = {FMAX, FMAX, FMAX}, mesh_max[3] = {FLOW, FLOW, FLOW};
+  // LOD index buffers in blob vertex numbering: the caller's, or the simplification chain of :596-641 (each LOD simplified
+  // from the previous one to half its index count, error accumulated; the chain ends when the simplifier stalls more than
+  // 50 % above the target, the step's relative error exceeds 0.5 or fewer than two triangles are left)
+  std::vector<std::vector<uint32_t>> lod_indices(in->lod_count);
+  std::vector<float> lod_errors(in->lod_count);
   for (uint32_t l = 0; l < in->lod_count; l++) {
-    const uint32_t index_count = in->lod_index_counts[l];
-    std::vector<uint32_t> indices(index_count);
-    for (uint32_t i = 0; i < index_count; i++) indices[i] = m->vertex_remap[in->lod_indices[l][i]];
+    lod_indices[l].resize(in->lod_index_counts[l]);
+    for (uint32_t i = 0; i < in->lod_index_counts[l]; i++) lod_indices[l][i] = m->vertex_remap[in->lod_indices[l][i]];
+    lod_errors[l] = in->lod_errors[l];
+  }
+  if (in->auto_lods) {
+    std::vector<float> normals;
+    if (in->normals) {
+      normals.resize((size_t)vertex_count * 3);
+      for (uint32_t v = 0; v < in->vertex_count; v++)
+        if (m->vertex_remap[v] != NONE) std::memcpy(&normals[(size_t)m->vertex_remap[v] * 3], &in->normals[(size_t)v * 3], 12);
+    }
+    for (uint32_t l = 1; l < OXC_MESH_MAX_LODS; l++) {
+      const std::vector<uint32_t>& last = lod_indices.back();
+      const size_t target = (last.size() + 5) / 6 * 3;
+      float step_error = 0.0f;
+      std::vector<uint32_t> simplified = oxb::simplify(last.data(), last.size(), positions.data(), in->normals ? normals.data() : nullptr, vertex_count,
+                                                       target, std::numeric_limits<float>::max(), &step_error);
+      const float error = lod_errors.back() + step_error;
+      if (simplified.size() > target + target / 2 || step_error > 0.5f || simplified.size() < 6) break;
+      lod_indices.push_back(std::move(simplified));
+      lod_errors.push_back(error);
+    }
+  }
+  const uint32_t lod_total = (uint32_t)lod_indices.size();
+  for (uint32_t l = 0; l < lod_total; l++) {
+    std::vector<uint32_t>& indices = lod_indices[l];
+    const uint32_t index_count = (uint32_t)indices.size();
     if (in->cluster_mode == 1) { // spatial clustering: reorder the triangles, then scan
       const std::vector<uint32_t> order = spatial_triangle_order(indices, positions, vertex_count);
       std::vector<uint32_t> sorted(index_count);
@@ -454,7 +487,7 @@ int oxb_build_mesh(const OxbMeshInput* in, OxbMesh** out) {
     d.meshlet_bounds_count = (uint32_t)bounds.size();
     d.local_triangle_indices_count = (uint32_t)micro.size();
     d.indirect_vertex_indices_count = (uint32_t)vertex_indices.size();
-    d.error = in->lod_errors[l];
+    d.error = lod_errors[l];
     m->meshlet_counts[l] = d.meshlet_count;
     m->mesh.lod_count++;
   }
@@ -499,5 +532,18 @@ int oxb_mesh_emit(const OxbMesh* m, uint64_t base_offset, uint8_t* dst, OxcMesh*
 }
 
 void oxb_mesh_free(OxbMesh* m) { delete m; }
+
+int64_t oxb_simplify(uint32_t* dst, const uint32_t* indices, uint64_t index_count, const float* positions, const float* normals, uint32_t vertex_count,
+                     uint64_t target_index_count, float target_error, float* result_error) {
+  if (!dst || !indices || !positions || index_count % 3u || target_index_count % 3u) {
+    g_builder_error = "oxb_simplify: null argument or index counts that are not multiples of 3";
+    return OXC_E_INVALID;
+  }
+  for (uint64_t i = 0; i < index_count; i++)
+    if (indices[i] >= vertex_count) { g_builder_error = "index out of range"; return OXC_E_INVALID; }
+  const std::vector<uint32_t> r = oxb::simplify(indices, (size_t)index_count, positions, normals, vertex_count, (size_t)target_index_count, target_error, result_error);
+  if (!r.empty()) std::memcpy(dst, r.data(), r.size() * 4);
+  return (int64_t)r.size();
+}
 
 } // extern "C"
