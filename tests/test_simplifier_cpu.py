@@ -296,3 +296,38 @@ def test_auto_lods_feed_the_cull(orc):
     lods = list(hs.mesh_instances["lod_index"])
     assert lods[0] == 0 and lods[0] <= lods[1] <= lods[2] and lods[2] >= 2
     assert r["late"] > 10
+
+
+def test_golden_builder_fixture():
+    """tests/golden/builder_small.json (written by make_golden_builder.py from the Python oracles) still describes what the
+    oracles AND the product build today: regression pin for the whole builder (remap, quantisation, simplification chain,
+    meshlets, bounds)."""
+    import hashlib
+    import importlib.util
+    import json
+    import os
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden_builder", os.path.join(here, "golden", "make_golden_builder.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(here, "golden", "builder_small.json")))
+    assert mod.generate() == want                                               # the oracles
+    sha = lambda a: hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()  # noqa: E731
+    pos, nrm, uv, i0, _ = torus(want["mesh"]["nu"], want["mesh"]["nv"])
+    built = capi.BuiltMesh(pos, [(i0, 0.0)], normals=nrm, texcoords=uv, auto_lods=True)
+    got = parse(built)                                                          # the product
+    assert got["vertex_count"] == want["vertex_count"] and sha(got["positions_q"]) == want["positions_sha"] and sha(got["normals_q"]) == want["normals_sha"]
+    assert len(got["lods"]) == len(want["lods"])
+    for g, w in zip(got["lods"], want["lods"]):
+        assert len(g["indices"]) == w["index_count"] and np.float32(g["error"]) == np.float32(w["error"]) and len(g["meshlets"]) == w["meshlets"]
+        assert sha(g["indices"]) == w["indices_sha"] and sha(g["meshlets"]) == w["meshlets_sha"] and sha(g["micro"]) == w["micro_sha"]
+        assert sha(g["vertex_indices"]) == w["vertex_indices_sha"]
+        b = g["bounds"]
+        rows = np.array([list(map(int, r["aabb_center"])) + list(map(int, r["cone_axis_xy"])) + list(map(int, r["aabb_extent"])) +
+                         [int(r["cone_axis_z"]), int(r["cone_cutoff"])] for r in b], dtype=np.int64)
+        assert sha(rows) == w["bounds_sha"]
+    half, err = capi.simplify(i0, pos, None, len(i0) // 2 // 3 * 3)
+    assert len(half) == want["positions_only_half"]["index_count"] and float(err) == want["positions_only_half"]["error"]
+    assert sha(half) == want["positions_only_half"]["indices_sha"]
+    built.close()
