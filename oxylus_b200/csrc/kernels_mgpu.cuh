@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) k_mgpu_hiz_push(const unsigned long long*
     sy = sy > height - 1 ? height - 1 : sy;
     const unsigned long long v = __ldg(&vis[(size_t)sy * width + sx]);
     const uint32_t d = (uint32_t)(v >> 32);
-    atomicMax(peers.xbuf[peers.rank] + parity * n + i, d); // own contribution (a peer's may already be there)
+    red_max_sys(peers.xbuf[peers.rank] + parity * n + i, d); // own contribution (a peer's may already be there: same scope as theirs)
     if ((uint32_t)v != OXC_VIS_CLEAR) {                     // this rank drew the sample pixel: tell everybody
       for (uint32_t r = 0; r < peers.world; r++)
         if (r != peers.rank) red_max_sys(peers.xbuf[r] + parity * n + i, d);
