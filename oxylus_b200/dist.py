@@ -1,16 +1,16 @@
-"""Multi-GPU sharding of the visibility pipeline (the reference is single-GPU).
+"""Host-side sharding logic of the multi-GPU path (the reference is single-GPU).
 
-One process per GPU.  Mesh instances are partitioned into contiguous ranges balanced by LOD0 meshlet count;
-rank r culls + rasterises only its range (oxc_set_shard), so its slice of the persistent visibility mask is
-never touched by another rank (mask bits are laid out by mesh-instance order, Scene.cpp:1255-1260).
-Exchange steps per frame (torch.distributed; NCCL on GPUs, gloo in the CPU tests):
+The exchange itself is product code behind the C ABI (oxc_mgpu_*: Hi-Z over NVLink peer memory, vis-buffer max-reduce and
+survivor allgather over NCCL — csrc/kernels_mgpu.cuh, oxcull.cu).  What lives here is what a host decides before it creates
+its contexts — the contiguous mesh-instance ranges, balanced by LOD0 meshlet count, rank r owns (mask bits are laid out by
+mesh-instance order, Scene.cpp:1255-1260, so a rank's slice of the persistent mask is private) — plus torch.distributed
+restatements of the three exchange steps that run on CPU tensors under gloo, so tests/test_dist_cpu.py can check the
+sharding algebra (global id bases, max-merge of the packed image, survivor segments) against the single-process oracle
+frame without a GPU:
   1. all_gather of each rank's emitted meshlet-instance count -> exclusive prefix = this rank's id base
-     (global meshlet-instance ids in survivor lists and vis-buffer payloads)
-  2. vis-buffer all_reduce(MAX) on the packed depth|id image after the early raster (every rank then builds
-     the identical Hi-Z) and after the late raster.  Depth bits of z in [0,1] are <= 0x3F800000, so the
-     signed int64 order NCCL applies equals the unsigned order of the packing.
+  2. all_reduce(MAX) of the packed depth|id image (depth bits of z in [0,1] are <= 0x3F800000, so the signed int64 order
+     equals the unsigned order of the packing)
   3. all_gather of the survivor lists (count-prefixed, fixed-capacity segments)
-The functions below are device-agnostic (they run on CPU tensors under gloo in tests/test_dist_cpu.py).
 """
 import numpy as np
 import torch
