@@ -101,6 +101,19 @@ def _build_host_min(tmp_path):
     return exe
 
 
+def test_plain_c_mesh_import_example(tmp_path):
+    """examples/mesh_import.c: the builder side of the ABI (oxb_*: clusteriser + generated LOD chain) from plain C11 — pure host
+    code, so it runs to completion without a GPU."""
+    capi.load()
+    exe = str(tmp_path / "mesh_import")
+    libdir = os.path.dirname(capi.lib_path())
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "mesh_import.c"), "-L", libdir, "-loxcull", f"-Wl,-rpath,{libdir}", "-lm", "-o", exe])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout + res.stderr
+    assert "lods 8" in res.stdout
+
+
 def test_plain_c_host_compiles_links_and_fails_loudly_without_gpu(tmp_path):
     """examples/host_min.c: a C11 host using nothing but include/oxcull.h.  Without a CUDA device it must stop at oxc_create
     with the no-device error (exit code 3), never silently compute on the CPU."""
