@@ -117,32 +117,10 @@ __global__ void __launch_bounds__(CULL_MESHES_THREADS) k_cull_meshes(const __gri
              fabsf(rows[k].z) <= 1.152921504606847e18f && fabsf(rows[k].w) <= 1.152921504606847e18f;
       ic.nrm[1].w = ok ? 1.0f : 0.0f;
     }
-    {  // nrm[2].w: 1.0 when every meshlet box of the selected LOD is provably inside all six planes for the
-       // canonical test, so the per-meshlet frustum test can be skipped.  U = union AABB of the decoded meshlet
-       // boxes (inflated for the rounding of c +- h).  The canonical test rejects only if fl(dot(p,n)) <= -w; its
-       // rounding error is <= 3.1u * sum|p_i| <= 3.1u * B with B = sum_i max(|Umin_i|, |Umax_i|), and the real
-       // p-vertex value is >= the n-vertex value of U.  Require n-vertex(U) + w > 2^-18 (B + |w|)  (64u: > 8x slack
-       // incl. the rounding of this very evaluation).
+    {  // nrm[2].w: 1.0 when every meshlet box of the selected LOD is provably inside all six planes for the canonical test, so
+       // the per-meshlet frustum test can be skipped (bound: union_box_inside_frustum, oxc_filtered.cuh)
       const float* ua = p.lod_aabb + ((size_t)inst.mesh_index * OXC_MESH_MAX_LODS + lod_index) * 6;
-      bool inside = p.lod_aabb != nullptr;
-      float B = 0.0f;
-      float lo[3], hi[3];
-#pragma unroll
-      for (int a = 0; a < 3; a++) {
-        const float mn = ua[a], mx = ua[3 + a];
-        const float pad = fmaxf(fabsf(mn), fabsf(mx)) * 4.76837158203125e-07f; // 2^-21 relative inflation
-        lo[a] = mn - pad; hi[a] = mx + pad;
-        B += fmaxf(fabsf(lo[a]), fabsf(hi[a]));
-        inside = inside && (mn <= mx); // NaN / empty => false
-      }
-#pragma unroll
-      for (int k = 0; k < 6; k++) {
-        const float4 pl = planes[k];
-        const float vx = pl.x >= 0.0f ? lo[0] : hi[0], vy = pl.y >= 0.0f ? lo[1] : hi[1], vz = pl.z >= 0.0f ? lo[2] : hi[2];
-        const float sv = fmaf(vx, pl.x, fmaf(vy, pl.y, fmaf(vz, pl.z, pl.w)));
-        inside = inside && (sv > (B + fabsf(pl.w)) * 3.814697265625e-06f);
-      }
-      ic.nrm[2].w = inside ? 1.0f : 0.0f;
+      ic.nrm[2].w = union_box_inside_frustum(planes, ua, p.lod_aabb != nullptr) ? 1.0f : 0.0f;
     }
     const uint64_t baddr = lod->meshlet_bounds;
     ic.bounds_lo = (uint32_t)baddr;
@@ -415,26 +393,6 @@ struct __align__(16) CullShared {
   uint64_t bnd_bar[CULL_WARPS][2];
 #endif
 };
-
-// Centre-inside frustum filter.  The canonical test (test_frustum_planes) rejects on plane i iff
-// fl(dot(c (+) s*h, n_i)) <= -w_i with s = sign(n_i) and h >= 0, i.e. it evaluates Σ n_k c_k + Σ |n_k| h_k (each
-// term rounded).  With M = Σ|c_k| + Σ h_k and |n_k| <= 1 + 4u the canonical value differs from the real one by
-// <= 4.3u M, and the real one is >= Σ n_k c_k.  D = fma-chain(Σ n_k c_k + w_i) carries <= 3u (M + |w_i|).  Hence
-//     D > 2^-19 (M + |w_i|)   (= 32u: > 4x slack)   ==>  the canonical test does NOT reject on plane i.
-// True for all six planes => visible, exactly as the canonical test decides.  NaN / Inf anywhere makes a comparison
-// false => "unknown" => the canonical path runs.
-OXC_DI bool frustum_centre_inside(const float4* __restrict__ planes, float cx, float cy, float cz, float ex, float ey, float ez) {
-  const float M = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + 0.5f * (fabsf(ex) + fabsf(ey) + fabsf(ez)));
-  const float Mk = M * 1.9073486328125e-06f; // 2^-19
-  bool inside = true;
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    const float4 pl = __ldg(&planes[i]);
-    const float D = fmaf(cx, pl.x, fmaf(cy, pl.y, fmaf(cz, pl.z, pl.w)));
-    inside = inside && (D > fmaf(fabsf(pl.w), 1.9073486328125e-06f, Mk));
-  }
-  return inside;
-}
 
 template <bool HIZ, bool OCC, bool LATE, bool ZERO>
 struct CullWarp {

@@ -12,6 +12,13 @@ namespace oxc {
 
 enum Tri : int { TRI_FALSE = 0, TRI_TRUE = 1, TRI_AMBIGUOUS = 2 };
 
+#ifdef OXC_HOST_SOUNDNESS_HARNESS
+// tests/filter_soundness.cpp compiles this header for the HOST and supplies the two approximate units itself: the exact
+// value perturbed adversarially within the error the PTX ISA allows, so the bounds below are tested against the worst case
+// the hardware may produce, not only against what one GPU happens to return.
+float rcp_approx(float x);
+float rsqrt_approx(float x);
+#else
 OXC_DI float rcp_approx(float x) {
   float r;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); // max relative error 2^-23 (PTX ISA)
@@ -21,6 +28,54 @@ OXC_DI float rsqrt_approx(float x) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); // max relative error 2^-22.4 (PTX ISA)
   return r;
+}
+#endif
+
+// Whole-instance frustum shortcut (k_cull_meshes).  U = union AABB of the decoded meshlet boxes of a LOD (ua = min xyz, max
+// xyz), inflated for the rounding of c +- h.  The canonical test rejects a box inside U only if fl(dot(p,n)) <= -w; its rounding
+// error is <= 3.1u * sum|p_i| <= 3.1u * B with B = sum_i max(|Umin_i|, |Umax_i|), and the real p-vertex value of any such box
+// is >= the n-vertex value of U.  Require n-vertex(U) + w > 2^-18 (B + |w|)  (64u: > 8x slack incl. the rounding of this very
+// evaluation) on all six planes: then no meshlet of the instance can fail the canonical frustum test.
+OXC_DI bool union_box_inside_frustum(const float4* planes, const float* __restrict__ ua, bool have_aabb) {
+  bool inside = have_aabb;
+  float B = 0.0f;
+  float lo[3], hi[3];
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    const float mn = ua[a], mx = ua[3 + a];
+    const float pad = fmaxf(fabsf(mn), fabsf(mx)) * 4.76837158203125e-07f; // 2^-21 relative inflation
+    lo[a] = mn - pad; hi[a] = mx + pad;
+    B += fmaxf(fabsf(lo[a]), fabsf(hi[a]));
+    inside = inside && (mn <= mx); // NaN / empty => false
+  }
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    const float4 pl = planes[k];
+    const float vx = pl.x >= 0.0f ? lo[0] : hi[0], vy = pl.y >= 0.0f ? lo[1] : hi[1], vz = pl.z >= 0.0f ? lo[2] : hi[2];
+    const float sv = fmaf(vx, pl.x, fmaf(vy, pl.y, fmaf(vz, pl.z, pl.w)));
+    inside = inside && (sv > (B + fabsf(pl.w)) * 3.814697265625e-06f);
+  }
+  return inside;
+}
+
+// Centre-inside frustum filter.  The canonical test (test_frustum_planes) rejects on plane i iff
+// fl(dot(c (+) s*h, n_i)) <= -w_i with s = sign(n_i) and h >= 0, i.e. it evaluates Σ n_k c_k + Σ |n_k| h_k (each
+// term rounded).  With M = Σ|c_k| + Σ h_k and |n_k| <= 1 + 4u the canonical value differs from the real one by
+// <= 4.3u M, and the real one is >= Σ n_k c_k.  D = fma-chain(Σ n_k c_k + w_i) carries <= 3u (M + |w_i|).  Hence
+//     D > 2^-19 (M + |w_i|)   (= 32u: > 4x slack)   ==>  the canonical test does NOT reject on plane i.
+// True for all six planes => visible, exactly as the canonical test decides.  NaN / Inf anywhere makes a comparison
+// false => "unknown" => the canonical path runs.
+OXC_DI bool frustum_centre_inside(const float4* __restrict__ planes, float cx, float cy, float cz, float ex, float ey, float ez) {
+  const float M = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + 0.5f * (fabsf(ex) + fabsf(ey) + fabsf(ez)));
+  const float Mk = M * 1.9073486328125e-06f; // 2^-19
+  bool inside = true;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const float4 pl = __ldg(&planes[i]);
+    const float D = fmaf(cx, pl.x, fmaf(cy, pl.y, fmaf(cz, pl.z, pl.w)));
+    inside = inside && (D > fmaf(fabsf(pl.w), 1.9073486328125e-06f, Mk));
+  }
+  return inside;
 }
 
 // ------------------------------------------------------------------------------------------------
