@@ -726,6 +726,14 @@ static void raster_triangle_clipped(const float clip[3][4], uint32_t data, uint3
   raster_triangle_clipped_with(clip, data, W, H, vis, raster_triangle);
 }
 
+/* one clip-space triangle through the rules above (plain raster, or the clipped one when the plain rules drop it): the unit the
+ * host cross-check of the CUDA raster core compares against (tests/raster_core_vs_oracle.cpp).  Returns 1 if it took the clip path. */
+int orc_raster_triangle(const float clip[3][4], uint32_t data, uint32_t width, uint32_t height, uint64_t* vis) {
+  if (tri_dropped_by_range(clip, width, height)) { raster_triangle_clipped(clip, data, width, height, vis); return 1; }
+  raster_triangle(clip, data, width, height, vis);
+  return 0;
+}
+
 void orc_raster_visbuffer_clip(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
                                const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
                                const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,

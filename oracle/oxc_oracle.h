@@ -109,6 +109,9 @@ void orc_cull_triangles(const OrcScene* scene, const OxcMeshletInstance* meshlet
 /* SW raster (spec in DESIGN.md §raster): same triangle cull, then rasterise with
  * max on asuint(depth)<<32 | (id<<8 | tri).  vis must be pre-cleared (orc_clear_visbuffer). */
 void orc_clear_visbuffer(uint64_t* vis, uint32_t width, uint32_t height);
+/* one clip-space triangle (after the near / backface test) through the raster specification, clipped when the plain rules drop
+ * it; returns 1 if the clip path was taken */
+int orc_raster_triangle(const float clip[3][4], uint32_t data, uint32_t width, uint32_t height, uint64_t* vis);
 /* VSM page marking (rmvsm_mark_visible_pages.slang) and the canonical log2 it uses */
 float orc_log2_canonical(float x);
 void orc_mark_visible_pages(const float inv_projection_view[16], const float resolution[2], const OxcVirtualClipmap* clipmaps,
