@@ -25,6 +25,15 @@ struct MgpuPeers {
   uint32_t rank, world;
 };
 
+#ifdef OXC_HOST_SOUNDNESS_HARNESS
+// host builds of the headers (tests/): the exchange needs peer GPUs and is never launched there; keep the file compilable
+OXC_DI void red_max_sys(uint32_t* addr, uint32_t v) { atomicMax(addr, v); }
+OXC_DI void st_release_sys(uint32_t* addr, uint32_t v) { *addr = v; }
+OXC_DI uint32_t ld_acquire_sys(const uint32_t* addr) { return *addr; }
+OXC_DI unsigned long long global_timer_ns() { return 0ull; }
+OXC_DI uint4 ld_cg_v4(const uint4* p) { return *p; }
+OXC_DI uint32_t ld_cg_u32(const uint32_t* p) { return *p; }
+#else
 OXC_DI void red_max_sys(uint32_t* addr, uint32_t v) { asm volatile("red.relaxed.sys.global.max.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
 OXC_DI void st_release_sys(uint32_t* addr, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(addr), "r"(v) : "memory"); }
 OXC_DI uint32_t ld_acquire_sys(const uint32_t* addr) {
@@ -32,6 +41,24 @@ OXC_DI uint32_t ld_acquire_sys(const uint32_t* addr) {
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
   return v;
 }
+OXC_DI unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// peers wrote with system-scope reductions that completed before their flags: a weak load after the acquire is enough, but the
+// lines may sit stale in this SM's L1 from two frames ago -> bypass it
+OXC_DI uint4 ld_cg_v4(const uint4* p) {
+  uint4 v;
+  asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+OXC_DI uint32_t ld_cg_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+#endif
 
 // One thread per Hi-Z mip-0 texel.  seq = *d_seq + 1 is the exchange this launch belongs to (device-side counter: the same
 // launch sequence replays correctly from a CUDA graph).
@@ -76,11 +103,9 @@ __global__ void __launch_bounds__(256) k_mgpu_hiz_collect(const __grid_constant_
   __syncthreads();
   if (threadIdx.x < peers.world) {
     const uint32_t* f = peers.flags[peers.rank] + (seq & 1u) * MGPU_MAX_RANKS + threadIdx.x;
-    unsigned long long t0, t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    const unsigned long long t0 = global_timer_ns();
     while ((int32_t)(ld_acquire_sys(f) - seq) < 0) {
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t1 - t0 > timeout_ns) { ok_s = 0; break; }
+      if (global_timer_ns() - t0 > timeout_ns) { ok_s = 0; break; }
       __nanosleep(200);
     }
   }
@@ -90,17 +115,13 @@ __global__ void __launch_bounds__(256) k_mgpu_hiz_collect(const __grid_constant_
   uint4* dst = reinterpret_cast<uint4*>(mip0);
   const size_t n4 = n / 4;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    // peers wrote with system-scope reductions that completed before their flags: a weak load after the acquire is enough,
-    // but the lines may sit stale in this SM's L1 from two frames ago -> bypass it
-    uint4 v;
-    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(src + i) : "memory");
+    const uint4 v = ld_cg_v4(src + i);
     dst[i] = v;
     src[i] = make_uint4(0, 0, 0, 0);
   }
   for (size_t i = n4 * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     uint32_t* s1 = peers.xbuf[peers.rank] + (seq & 1u) * n + i;
-    uint32_t v;
-    asm volatile("ld.global.cg.u32 %0, [%1];" : "=r"(v) : "l"(s1) : "memory");
+    const uint32_t v = ld_cg_u32(s1);
     reinterpret_cast<uint32_t*>(mip0)[i] = v;
     *s1 = 0;
   }

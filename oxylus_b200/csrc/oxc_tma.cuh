@@ -34,6 +34,10 @@ OXC_DI void mbar_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
 }
 
+#ifdef OXC_HOST_SOUNDNESS_HARNESS
+OXC_DI void prefetch_l1(const void*) {} // host builds of the headers (tests/): a hint has no result
+#else
 OXC_DI void prefetch_l1(const void* ptr) { asm volatile("prefetch.global.L1 [%0];" ::"l"(ptr)); }
+#endif
 
 } // namespace oxc

@@ -21,6 +21,7 @@ struct __align__(16) uint4 { unsigned int x, y, z, w; };
 static inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 static inline uint2 make_uint2(unsigned x, unsigned y) { return uint2{x, y}; }
+static inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
 template <typename T>
 static inline T __ldg(const T* p) { return *p; }
