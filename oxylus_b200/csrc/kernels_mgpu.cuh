@@ -26,10 +26,11 @@ struct MgpuPeers {
 };
 
 #ifdef OXC_HOST_SOUNDNESS_HARNESS
-// host builds of the headers (tests/): the exchange needs peer GPUs and is never launched there; keep the file compilable
+// host builds of the headers (tests/): the emulated multi-rank test runs the ranks as threads of one process, "peer memory" is
+// plain shared memory
 OXC_DI void red_max_sys(uint32_t* addr, uint32_t v) { atomicMax(addr, v); }
-OXC_DI void st_release_sys(uint32_t* addr, uint32_t v) { *addr = v; }
-OXC_DI uint32_t ld_acquire_sys(const uint32_t* addr) { return *addr; }
+OXC_DI void st_release_sys(uint32_t* addr, uint32_t v) { __atomic_store_n(addr, v, __ATOMIC_RELEASE); }
+OXC_DI uint32_t ld_acquire_sys(const uint32_t* addr) { return __atomic_load_n(addr, __ATOMIC_ACQUIRE); }
 OXC_DI unsigned long long global_timer_ns() { return 0ull; }
 OXC_DI uint4 ld_cg_v4(const uint4* p) { return *p; }
 OXC_DI uint32_t ld_cg_u32(const uint32_t* p) { return *p; }

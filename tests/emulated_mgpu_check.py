@@ -1,0 +1,131 @@
+#!/usr/bin/env python
+"""G emulated ranks == 1 context, bit for bit, through the product's multi-GPU API (oxc_mgpu_*) — the CPU-tier counterpart of
+tools/check_multi_gpu.py.  Run by tests/test_emulated_library_cpu.py with OXC_LIB_PATH = the SIMT-emulated library and an
+in-process NCCL stand-in on LD_LIBRARY_PATH: every rank is a THREAD with its own OxcContext (oxc_set_shard_auto), the Hi-Z
+exchange writes into the other ranks' buffers ("peer memory" = shared memory here) and waits on their flags, the trailing
+exchange goes through the communicator.  Compared with a single context over the whole scene: merged vis buffer, gathered
+survivor ids (as a set), counters, every Hi-Z level on every rank, each rank's slice of the persistent mask.
+
+    python tests/emulated_mgpu_check.py WORLD [MESHLETS]"""
+import json
+import os
+import sys
+import threading
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oxylus_b200 import abi, capi, synth  # noqa: E402  (not oxylus_b200.dist: it imports torch, which brings the real NCCL into the process)
+
+
+def lod0_counts_of(scene):  # == oxylus_b200.dist.lod0_counts_of
+    off = scene.mesh_instances["meshlet_instance_visibility_offset"].astype(np.int64)
+    return np.diff(np.concatenate([off, [scene.max_meshlet_instance_count]]))
+
+
+def partition_mesh_instances(counts, world):  # == oxylus_b200.dist.partition_mesh_instances
+    counts = np.asarray(counts, dtype=np.int64)
+    csum = np.concatenate([[0], np.cumsum(counts)])
+    bounds = [0]
+    for r in range(1, world):
+        b = int(np.searchsorted(csum, int(csum[-1]) * r / world, side="left"))
+        bounds.append(min(max(b, bounds[-1]), len(counts)))
+    bounds.append(len(counts))
+    return [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(world)]
+
+
+class Rank:
+    def __init__(self, sc, shard=None, cap=None):
+        hw, hh = sc.hiz_extent()
+        self.sc, self.w, self.h = sc, sc.width, sc.height
+        self.ctx = capi.Context(0, max(1, sc.mesh_instance_count), max(1, sc.max_meshlet_instance_count if cap is None else cap), hw, hh,
+                                max_mask_bits=max(1, sc.max_meshlet_instance_count))
+        if shard is not None:
+            self.ctx.set_shard_auto(shard[0], shard[1])
+        self.ctx.set_scene(sc)
+        self.vis = self.ctx.alloc(self.w * self.h * 8)
+        self.occ = self.ctx.alloc(self.w * self.h * 4)
+        self.ctx.upload(self.occ, sc.occluder_depth)
+        self.mgpu = False
+
+    def frame(self, cam):
+        c, w, h, v = self.ctx, self.w, self.h, self.vis
+        c.clear_visbuffer_with_depth(v, self.occ, w, h)
+        c.clear_hiz()
+        c.cull_meshes(cam, abi.CULL_TEST_ALL)
+        c.cull_meshlets(cam, abi.CULL_TEST_ALL, True)
+        c.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, v)
+        if self.mgpu:
+            c.mgpu_exchange_hiz(v, w, h)
+        else:
+            c.build_hiz_packed(v, w, h)
+        c.cull_meshlets(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, True)
+        c.raster_visbuffer(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, v)
+
+    def image(self):
+        return self.ctx.download(self.vis, np.uint64, self.w * self.h)
+
+    def hiz(self):
+        return np.concatenate([l.ravel() for l in self.ctx.hiz_levels()]).view(np.uint32)
+
+
+def main():
+    world = int(sys.argv[1])
+    n = int(sys.argv[2]) if len(sys.argv) > 2 else 12000
+    frames = 3
+    sc = synth.make_scene(n, config_index=5, width=320, height=180, n_unique_meshes=24)
+    lod0 = lod0_counts_of(sc)
+    parts = partition_mesh_instances(lod0, world)
+    caps = [int(lod0[p[0]: p[0] + p[1]].sum()) for p in parts]
+    uid = capi.Context.mgpu_unique_id()
+    ref = Rank(sc)
+    want = []
+    for f in range(frames):
+        ref.frame(sc.camera(2.0 * (f % 2)))
+        vis = ref.ctx.visibility()
+        e, l = int(vis["early"][0]), int(vis["late"][0])
+        want.append(dict(image=ref.image(), ids=np.sort(ref.ctx.visible_indices(e + l)), total=int(vis["total"][0]), early=e, late=l, hiz=ref.hiz(),
+                         mask=np.unpackbits(ref.ctx.mask().view(np.uint8), bitorder="little")))
+    results, errors = [None] * world, []
+    barrier = threading.Barrier(world)
+
+    def run(rank):
+        try:
+            r = Rank(sc, shard=parts[rank], cap=max(caps[rank], 1))
+            info = r.ctx.mgpu_init(rank, world, uid, max(1024, caps[rank]))
+            r.mgpu = True
+            out = []
+            for f in range(frames):
+                r.frame(sc.camera(2.0 * (f % 2)))
+                r.ctx.mgpu_exchange_frame(r.vis, r.w, r.h, slot=f & 1)
+                r.ctx.check_status()
+                cnt, ids = r.ctx.mgpu_gathered(f & 1)
+                off = sc.mesh_instances["meshlet_instance_visibility_offset"].astype(np.int64)
+                lo = int(off[parts[rank][0]]) if parts[rank][1] else 0
+                mine = np.unpackbits(r.ctx.mask().view(np.uint8), bitorder="little")[lo: lo + caps[rank]]
+                w_ = want[f]
+                out.append(dict(image=bool(np.array_equal(r.image(), w_["image"])), ids=bool(np.array_equal(np.sort(np.concatenate(ids)), w_["ids"])),
+                                counts=(int(cnt[:, 0].sum()), int(cnt[:, 1].sum()), int(cnt[:, 2].sum())) == (w_["total"], w_["early"], w_["late"]),
+                                hiz=bool(np.array_equal(r.hiz(), w_["hiz"])), mask=bool(np.array_equal(mine, w_["mask"][lo: lo + caps[rank]]))))
+                barrier.wait()  # nobody starts the next frame's Hi-Z exchange before everybody has read this frame's results
+            results[rank] = dict(frames=out, peer_memory=bool(info.hiz_over_peer_memory), local_total=int(r.ctx.visibility()["total"][0]))
+            barrier.wait()
+            r.ctx.mgpu_shutdown()
+        except Exception as ex:  # noqa: BLE001
+            errors.append(f"rank {rank}: {ex!r}")
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(k,)) for k in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    ok = not errors and all(r and all(all(f.values()) for f in r["frames"]) for r in results)
+    ok = ok and all(r["peer_memory"] for r in results) and sum(r["local_total"] > 0 for r in results) >= min(world, 2)
+    print(json.dumps({"check": "emulated_ranks_equal_single_context", "world": world, "meshlets": n, "pass": bool(ok), "errors": errors, "ranks": results}))
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()

@@ -232,7 +232,8 @@ OXC_SIMT_REDUCE(__reduce_min_sync, 0xffffffffu, (r < x ? r : x))
 static inline unsigned __activemask() { return simt::g_block->warps[simt::g_block->cur->warp].live; }
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 static inline int __ffs(int v) { return __builtin_ffs(v); }
-static inline void __nanosleep(unsigned) { simt::yield(); }
+// a polling loop waits for ANOTHER block / rank (a different OS thread): let that thread run, and do not count the round as a deadlock
+static inline void __nanosleep(unsigned) { simt::g_block->progress = true; std::this_thread::yield(); simt::yield(); }
 static inline void __threadfence() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline void __threadfence_system() { std::atomic_thread_fence(std::memory_order_seq_cst); }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
@@ -327,6 +328,7 @@ static inline cudaError_t cudaGraphInstantiate(cudaGraphExec_t* e, cudaGraph_t, 
 static inline cudaError_t cudaGraphDestroy(cudaGraph_t) { return cudaSuccess; }
 static inline cudaError_t cudaGraphExecDestroy(cudaGraphExec_t) { return cudaSuccess; }
 static inline cudaError_t cudaGraphLaunch(cudaGraphExec_t, cudaStream_t) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t*, void*) { return cudaErrorNotSupported; }
-static inline cudaError_t cudaIpcOpenMemHandle(void**, cudaIpcMemHandle_t, unsigned) { return cudaErrorNotSupported; }
+// "peer memory": ranks of an emulated multi-GPU run are threads of one process, so a handle is just the address
+static inline cudaError_t cudaIpcGetMemHandle(cudaIpcMemHandle_t* h, void* p) { memset(h, 0, sizeof *h); memcpy(h->reserved, &p, sizeof p); return cudaSuccess; }
+static inline cudaError_t cudaIpcOpenMemHandle(void** p, cudaIpcMemHandle_t h, unsigned) { memcpy(p, h.reserved, sizeof *p); return cudaSuccess; }
 static inline cudaError_t cudaIpcCloseMemHandle(void*) { return cudaSuccess; }

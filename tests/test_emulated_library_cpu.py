@@ -8,10 +8,13 @@ What this shows: the kernels' logic and arithmetic as written — queues, compac
 chunk queues, the host mirror's frame loop — reproduce the oracle under an independent execution model, without a GPU.  What it
 does not show: anything about GPU scheduling, memory ordering or speed.  TEST INFRASTRUCTURE: the emulated library is built into
 a temporary directory and nothing in oxylus_b200/ knows about it; the product has no CPU path (test_abi_cpu.py checks that)."""
+import json
 import os
 import re
 import subprocess
 import sys
+
+import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # bounded for the CPU tier: no 1 M / 10 M / 17 M scenes, no 150 k-meshlet 1080p scene, no NCCL; host_min links -loxcull by name
@@ -19,15 +22,35 @@ SELECT = ("not full_size and not config and not medium and not wide_id and not m
           "and not small_primitive_cull_parity")
 
 
-def test_gpu_parity_suite_on_the_simt_emulator(tmp_path):
+@pytest.fixture(scope="module")
+def emulated(tmp_path_factory):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import build_emulated
 
-    lib = build_emulated.build(str(tmp_path / "emu"))
-    env = dict(os.environ, OXC_LIB_PATH=lib, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    lib = build_emulated.build(str(tmp_path_factory.mktemp("emu")))
+    # LD_LIBRARY_PATH: the library dlopens "libnccl.so.2" — the in-process stand-in built next to it (multi-rank test)
+    return dict(os.environ, OXC_LIB_PATH=lib, PYTHONPATH=ROOT + os.pathsep + os.environ.get("PYTHONPATH", ""),
+                LD_LIBRARY_PATH=os.path.dirname(lib) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+
+
+def test_gpu_parity_suite_on_the_simt_emulator(emulated):
+    env = emulated
     res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
                           "-k", SELECT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
     tail = res.stdout[-3000:] + res.stderr[-2000:]
     assert res.returncode == 0, tail
     m = re.search(r"(\d+) passed", res.stdout)
     assert m and int(m.group(1)) >= 35 and "failed" not in res.stdout and "skipped" not in res.stdout, tail
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_multi_gpu_path_on_the_simt_emulator(emulated, world):
+    """oxc_mgpu_* with `world` emulated ranks (threads of one process, each with its own context; tests/emulated_mgpu_check.py):
+    sharding with the communication-free id base, the Hi-Z exchange through the peers' buffers and flags, the vis-buffer max-reduce
+    and the survivor allgather reproduce a single context over the whole scene bit for bit — image, survivor set, counters, every
+    Hi-Z level on every rank, each rank's mask slice, three frames.  (4 ranks never ran on hardware this round: 2 and 8 did.)"""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emulated_mgpu_check.py"), str(world)], cwd=ROOT, env=emulated, capture_output=True,
+                         text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    verdict = json.loads(res.stdout.strip().splitlines()[-1])
+    assert verdict["pass"] and verdict["world"] == world and all(r["peer_memory"] for r in verdict["ranks"])
