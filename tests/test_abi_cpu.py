@@ -3,6 +3,7 @@ declares, the header is valid C, and — with no GPU — the product path FAILS 
 import ctypes as C
 import os
 import re
+import shutil
 import subprocess
 
 import numpy as np
@@ -91,6 +92,26 @@ def test_product_never_imports_oracle():
                     assert needle not in txt or "oracle/" in txt and needle not in re.sub(r"(#|//|/\*|\"\"\").*", "", txt), (f, needle)
     out = subprocess.run(["nm", "-D", "--undefined-only", capi.lib_path()], capture_output=True, text=True).stdout
     assert "orc_" not in out
+
+
+def test_product_never_uses_the_test_emulator():
+    """tests/host_shim/ (host stand-ins for the CUDA headers, the SIMT emulator) is test infrastructure: nothing under oxylus_b200/
+    includes it, builds it or loads an emulated library, and the shipped liboxcull.so is the nvcc build (it holds sm_100a device
+    code and none of the emulator's symbols).  The only trace in the product sources is the OXC_HOST_SOUNDNESS_HARNESS guard around
+    inline PTX, which no product build defines."""
+    pkg = os.path.join(ROOT, "oxylus_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                for needle in ("host_shim", "liboxcull_emu", "build_emulated", "simt::", "fake_nccl"):
+                    assert needle not in txt, (f, needle)
+    assert "OXC_HOST_SOUNDNESS_HARNESS" not in open(os.path.join(pkg, "build.py")).read()
+    syms = subprocess.run(["nm", "-DC", capi.lib_path()], capture_output=True, text=True).stdout
+    assert "simt::" not in syms
+    if shutil.which("cuobjdump"):
+        elf = subprocess.run(["cuobjdump", "-lelf", capi.lib_path()], capture_output=True, text=True).stdout
+        assert "sm_100a" in elf, elf[:300]
 
 
 def _build_host_min(tmp_path):
