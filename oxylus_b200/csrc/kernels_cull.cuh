@@ -225,7 +225,7 @@ __global__ void k_lod_union_aabb(const OxcMesh* __restrict__ meshes, uint32_t n_
       for (int a = 0; a < 3; a++) {
         const float h = fabsf(e[a]) * 0.5f;
         const float a0 = c[a] - h, a1 = c[a] + h;
-        bad = bad || !(fabsf(a0) <= 3.0e38f) || !(fabsf(a1) <= 3.0e38f);
+        bad = bad || !(fabsf(a0) <= 3.0e38f) || !(fabsf(a1) <= 3.0e38f) || !(e[a] >= 0.0f); // the shortcut's bound assumes h >= 0
         mn[a] = fminf(mn[a], a0); mx[a] = fmaxf(mx[a], a1);
       }
     }

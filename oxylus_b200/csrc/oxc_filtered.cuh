@@ -66,6 +66,9 @@ OXC_DI bool union_box_inside_frustum(const float4* planes, const float* __restri
 // True for all six planes => visible, exactly as the canonical test decides.  NaN / Inf anywhere makes a comparison
 // false => "unknown" => the canonical path runs.
 OXC_DI bool frustum_centre_inside(const float4* __restrict__ planes, float cx, float cy, float cz, float ex, float ey, float ez) {
+  // h >= 0 is a precondition of the bound: a negative (or NaN) extent is not something a mesh builder produces, but the canonical
+  // test is defined for it (its p-vertex then lies on the other side of the centre) => leave such boxes to the canonical path
+  if (!(ex >= 0.0f && ey >= 0.0f && ez >= 0.0f)) return false;
   const float M = (fabsf(cx) + fabsf(cy)) + (fabsf(cz) + 0.5f * (fabsf(ex) + fabsf(ey) + fabsf(ez)));
   const float Mk = M * 1.9073486328125e-06f; // 2^-19
   bool inside = true;
@@ -125,7 +128,7 @@ OXC_DI Tri cone_visible_fast(const ConeInputs& c, float cutoff) {
   const float hh = fmaf(c.hz, c.hz, fmaf(c.hy, c.hy, c.hx * c.hx));
   const float L = fmaf(c.dz, c.nz, fmaf(c.dy, c.ny, c.dx * c.nx));
   const float len_n = nn * rsqrt_approx(nn), len_d = dd * rsqrt_approx(dd);
-  const float wr = (hh > 0.0f ? hh * rsqrt_approx(hh) : 0.0f) * c.maxscale; // |h| = 0 is legitimate (degenerate box)
+  const float wr = (hh > 0.0f ? hh * rsqrt_approx(hh) : hh) * c.maxscale; // |h| = 0 is legitimate (degenerate box); a NaN stays a NaN (=> ambiguous)
   const float rhs = fmaf(cutoff, len_d, wr) * len_n;
   const float T = (len_d + wr) * len_n * 7.62939453125e-06f; // 2^-17
   const float diff = L - rhs;

@@ -208,6 +208,13 @@ void random_bounds(Rng& r, float* b, double centre_range, double emin, double em
     const double e = emin * pow(emax / emin, r.uniform());
     b[3 + a] = random_half_value(r, e, e * 1.0001 + 1e-9);
   }
+  // one box in 16 carries a value no mesh builder produces but a MeshletBounds record can hold: the canonical evaluation is
+  // defined for it, so the fast paths must either agree or step aside (negative / NaN / infinite / denormal-flushed fields)
+  if (r.below(16) == 0) {
+    static const uint32_t specials[] = {0x0000, 0x8000, 0x7BFF, 0xFBFF, 0x7C00, 0xFC00, 0x7E00, 0xBC00, 0xB800, 0x0400, 0x8400};
+    const int n = 1 + (int)r.below(2);
+    for (int k = 0; k < n; k++) b[r.below(6)] = dequantize_half(specials[r.below(11)]);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ occlusion

@@ -65,7 +65,7 @@ void* hk_scene_create(const OxcSceneDesc* sc) {
         const float e[3] = {dequantize_half(v.z & 0xFFFFu), dequantize_half(v.z >> 16), dequantize_half(v.w & 0xFFFFu)};
         for (int a = 0; a < 3; a++) {
           const float hh = fabsf(e[a]) * 0.5f, a0 = c[a] - hh, a1 = c[a] + hh;
-          bad = bad || !(fabsf(a0) <= 3.0e38f) || !(fabsf(a1) <= 3.0e38f);
+          bad = bad || !(fabsf(a0) <= 3.0e38f) || !(fabsf(a1) <= 3.0e38f) || !(e[a] >= 0.0f);
           mn[a] = fminf(mn[a], a0); mx[a] = fmaxf(mx[a], a1);
         }
       }

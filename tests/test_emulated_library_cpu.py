@@ -54,3 +54,11 @@ def test_multi_gpu_path_on_the_simt_emulator(emulated, world):
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     verdict = json.loads(res.stdout.strip().splitlines()[-1])
     assert verdict["pass"] and verdict["world"] == world and all(r["peer_memory"] for r in verdict["ranks"])
+
+
+def test_hostile_inputs_on_the_simt_emulator(emulated):
+    """tests/emulated_torture_check.py: NaN / Inf / negative / denormal MeshletBounds fields, garbage cones, degenerate and extreme
+    transforms — two-pass frames still equal the oracle bit for bit (survivors, mask, packed image)."""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emulated_torture_check.py"), "2"], cwd=ROOT, env=emulated, capture_output=True,
+                         text=True, timeout=1200)
+    assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout[-2000:] + res.stderr[-2000:]
