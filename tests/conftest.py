@@ -27,3 +27,20 @@ def small_scene():
     from oxylus_b200 import synth
 
     return synth.make_scene(6000, config_index=2, width=640, height=360, n_unique_meshes=16)
+
+
+# OXC_TEST_HOSTILE_SCENES=<seed>: every synthetic scene the tests build gets hostile MeshletBounds fields / cones / transforms
+# (tests/emulated_torture_check.py: mutate).  Used by tests/test_emulated_library_cpu.py for a second pass of the GPU parity suite on the
+# SIMT-emulated library; unset (the driver's GPU tier, every ordinary run) = no effect.
+if os.environ.get("OXC_TEST_HOSTILE_SCENES"):
+    import numpy as _np
+
+    import emulated_torture_check as _etc
+    from oxylus_b200 import synth as _synth
+
+    _orig_make_scene = _synth.make_scene
+
+    def _hostile_make_scene(*a, **k):
+        return _etc.mutate(_orig_make_scene(*a, **k), _np.random.default_rng(int(os.environ["OXC_TEST_HOSTILE_SCENES"])), os.environ.get("OXC_TEST_HOSTILE_MODE", "all"))
+
+    _synth.make_scene = _hostile_make_scene

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Hostile-but-representable inputs through the whole two-pass frame: MeshletBounds fields set to NaN, +-Inf, negative extents,
-+-0, the largest half, denormal-flushed values, garbage cone bytes; transforms scaled by 1e-12 / 1e6, mirrored, with a zero
++-0, the largest half, denormal-flushed values, garbage cone bytes; vertex positions with the same special values; transforms scaled by 1e-12 / 1e6, mirrored, with a zero
 column, at the camera, far away.  No mesh builder produces such records, but the reference's shaders — and therefore the oracle —
 are defined for them, and "bit-identical to the canonical evaluation for every input" has to hold for them too (this is the
 scenario that found the cone filter turning a NaN radius into 0 and the frustum filter assuming h >= 0).
@@ -38,6 +38,13 @@ def mutate(base, rng, mode):
                 sel = rng.random(n) < 0.3
                 b[sel, 3] = rng.integers(0, 65536, int(sel.sum())).astype(np.uint16)
                 b[sel, 7] = rng.integers(0, 65536, int(sel.sum())).astype(np.uint16)
+    if mode in ("vertices", "all"):  # vertex positions: u16 x 4 per vertex (scene.slang:478-484)
+        for m in sc.meshes:
+            n = int(m["vertex_count"])
+            v = np.ndarray((n, 4), dtype=np.uint16, buffer=sc.blob.data, offset=int(m["vertex_positions"]))
+            for c in range(3):
+                sel = rng.random(n) < 0.02
+                v[sel, c] = SPECIALS[rng.integers(0, len(SPECIALS), int(sel.sum()))]
     if mode in ("transforms", "all"):
         t = sc.transforms["world"]
         for i in np.nonzero(rng.random(len(t)) < 0.2)[0]:
@@ -93,10 +100,10 @@ def main():
     base = synth.make_scene(8000, config_index=2, width=320, height=180, n_unique_meshes=24, max_lods=2, ragged=True)
     bad = []
     for seed in range(seeds):
-        for mode in ("bounds", "cones", "transforms", "all"):
+        for mode in ("bounds", "cones", "vertices", "transforms", "all"):
             if not frames_equal(mutate(base, np.random.default_rng(seed * 10 + 1), mode)):
                 bad.append((seed, mode))
-    print(f"{seeds * 4} hostile scenes x 2 frames: {'ok' if not bad else 'MISMATCH ' + repr(bad)}")
+    print(f"{seeds * 5} hostile scenes x 2 frames: {'ok' if not bad else 'MISMATCH ' + repr(bad)}")
     sys.exit(1 if bad else 0)
 
 

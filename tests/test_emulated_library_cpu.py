@@ -59,6 +59,17 @@ def test_multi_gpu_path_on_the_simt_emulator(emulated, world):
 def test_hostile_inputs_on_the_simt_emulator(emulated):
     """tests/emulated_torture_check.py: NaN / Inf / negative / denormal MeshletBounds fields, garbage cones, degenerate and extreme
     transforms — two-pass frames still equal the oracle bit for bit (survivors, mask, packed image)."""
-    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emulated_torture_check.py"), "2"], cwd=ROOT, env=emulated, capture_output=True,
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emulated_torture_check.py"), "1"], cwd=ROOT, env=emulated, capture_output=True,
                          text=True, timeout=1200)
     assert res.returncode == 0 and res.stdout.strip().endswith("ok"), res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_gpu_parity_suite_with_hostile_scenes_on_the_simt_emulator(emulated):
+    """the same suite once more with OXC_TEST_HOSTILE_SCENES set (tests/conftest.py): every synthetic scene the tests build gets
+    the hostile record contents above, vertex positions included — hpb / multiview / plain culls, triangle cull, clip and chunk
+    queues, decode, the host mirror: every parity assertion still holds"""
+    env = dict(emulated, OXC_TEST_HOSTILE_SCENES="7", OXC_TEST_HOSTILE_MODE="all")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                          "-k", SELECT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=1500)
+    m = re.search(r"(\d+) passed", res.stdout)
+    assert res.returncode == 0 and m and int(m.group(1)) >= 35, res.stdout[-3000:] + res.stderr[-2000:]
