@@ -64,19 +64,38 @@ def mutate(base, rng, mode):
     return sc
 
 
-def frames_equal(sc, frames=2):
+def hostile_cameras(sc):
+    """cameras a host could hand over by mistake: degenerate near planes, a far-away eye, badly scaled or NaN matrix entries,
+    LOD thresholds of 0 / Inf"""
+    out = []
+    for k in range(10):
+        cam = sc.camera(5.0 * k).copy()
+        if k == 1: cam["near_clip"] = 1e-30
+        if k == 2: cam["near_clip"] = 50.0
+        if k == 3: cam["position"][0] = [1e6, 0, 0]
+        if k == 4: cam["projection_view"][0] *= np.float32(1e-6)
+        if k == 5: cam["projection_view"][0] *= np.float32(1e6)
+        if k == 6: cam["acceptable_lod_error"] = 0.0
+        if k == 7: cam["acceptable_lod_error"] = np.inf
+        if k == 8: cam["projection_view"][0][5] = np.nan
+        if k == 9: cam["near_clip"] = np.nan
+        out.append(cam)
+    return out
+
+
+def frames_equal(sc, frames=2, cams=None, occluder_depth=None):
     hs = orc.HostScene(sc)
     w, h = sc.width, sc.height
     hw, hh = sc.hiz_extent()
     ctx = capi.Context(0, sc.mesh_instance_count, sc.max_meshlet_instance_count, hw, hh)
     ctx.set_scene(sc)
     vis, occ = ctx.alloc(w * h * 8), ctx.alloc(w * h * 4)
-    ctx.upload(occ, sc.occluder_depth)
+    depth = sc.occluder_depth if occluder_depth is None else occluder_depth
+    ctx.upload(occ, depth)
     mask = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
     ok = True
-    for f in range(frames):
-        cam = sc.camera(3.0 * f)
-        ref = orc.frame(hs, cam, w, h, mask, sc.occluder_depth)
+    for cam in (cams if cams is not None else [sc.camera(3.0 * f) for f in range(frames)]):
+        ref = orc.frame(hs, cam, w, h, mask, depth)
         ctx.clear_visbuffer_with_depth(vis, occ, w, h)
         ctx.clear_hiz()
         ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
@@ -90,6 +109,7 @@ def frames_equal(sc, frames=2):
         same = (e, l) == (ref["early"], ref["late"])
         same = same and np.array_equal(np.sort(ctx.visible_indices(e + l)), np.sort(ref["visible"][: ref["early"] + ref["late"]]))
         same = same and np.array_equal(ctx.download(vis, np.uint64, w * h).reshape(h, w), ref["vis64"]) and np.array_equal(ctx.mask(), mask)
+        same = same and np.array_equal(np.concatenate([x.ravel() for x in ctx.hiz_levels()]).view(np.uint32), ref["hiz"].data.view(np.uint32))
         ok = ok and bool(same)
     ctx.close()
     return ok
@@ -103,7 +123,15 @@ def main():
         for mode in ("bounds", "cones", "vertices", "transforms", "all"):
             if not frames_equal(mutate(base, np.random.default_rng(seed * 10 + 1), mode)):
                 bad.append((seed, mode))
-    print(f"{seeds * 5} hostile scenes x 2 frames: {'ok' if not bad else 'MISMATCH ' + repr(bad)}")
+    if not frames_equal(base, cams=hostile_cameras(base)):
+        bad.append("cameras")
+    depth = base.occluder_depth.copy()
+    rng = np.random.default_rng(3)
+    sel = rng.random(depth.shape) < 0.01
+    depth[sel] = rng.choice(np.array([np.nan, np.inf, -np.inf, -1.0, 2.0, 1e-45, -0.0], dtype=np.float32), int(sel.sum()))
+    if not frames_equal(base, occluder_depth=depth):
+        bad.append("external depth")
+    print(f"{seeds * 5} hostile scenes x 2 frames, 10 hostile cameras, hostile external depth: {'ok' if not bad else 'MISMATCH ' + repr(bad)}")
     sys.exit(1 if bad else 0)
 
 
