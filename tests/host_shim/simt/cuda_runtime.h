@@ -95,10 +95,18 @@ inline void run_block(BlockState& b, unsigned n_threads) {
     f.ctx.uc_stack.ss_sp = f.stack; f.ctx.uc_stack.ss_size = FIBER_STACK; f.ctx.uc_link = nullptr;
     makecontext(&f.ctx, reinterpret_cast<void (*)()>(fiber_entry), 0);
   }
-  unsigned idle_rounds = 0;
+  // OXC_SIMT_ORDER=reverse|shuffle: resume the fibers in another order.  Each fiber runs until it has to wait, so lanes of a warp
+  // are as far from lockstep as they can be; changing the order changes who gets ahead of whom.  A kernel that leans on implicit
+  // warp-synchronous execution (a shared-memory hand-off without __syncwarp) gives different results under different orders.
+  static const int order_mode = [] { const char* e = std::getenv("OXC_SIMT_ORDER"); return !e ? 0 : (e[0] == 'r' ? 1 : 2); }();
+  unsigned idle_rounds = 0, round = 0;
   while (b.live_threads) {
     b.progress = false;
-    for (unsigned t = 0; t < n_threads; t++) {
+    round++;
+    for (unsigned i = 0; i < n_threads; i++) {
+      unsigned t = i;
+      if (order_mode == 1) t = n_threads - 1 - i;
+      else if (order_mode == 2) t = (unsigned)(((unsigned long long)i * 2654435761ull + round * 40503ull) % n_threads); // not a permutation every round: fine, it only picks who runs next
       Fiber& f = b.fibers[t];
       if (f.done) continue;
       b.cur = &f;
