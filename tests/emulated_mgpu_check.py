@@ -109,6 +109,10 @@ def main():
                                 counts=(int(cnt[:, 0].sum()), int(cnt[:, 1].sum()), int(cnt[:, 2].sum())) == (w_["total"], w_["early"], w_["late"]),
                                 hiz=bool(np.array_equal(r.hiz(), w_["hiz"])), mask=bool(np.array_equal(mine, w_["mask"][lo: lo + caps[rank]]))))
                 barrier.wait()  # nobody starts the next frame's Hi-Z exchange before everybody has read this frame's results
+                if f == 0:  # collective resize of the survivor segments to what the frame needed (bench.py does this after warm-up)
+                    seen = int(cnt[:, 3].max())
+                    info2 = r.ctx.mgpu_set_survivor_capacity(max(64, 2 * seen + rank))  # different requests: the ranks agree on the largest
+                    assert info2.survivor_capacity == max(64, 2 * seen + world - 1), (info2.survivor_capacity, seen)
             results[rank] = dict(frames=out, peer_memory=bool(info.hiz_over_peer_memory), local_total=int(r.ctx.visibility()["total"][0]))
             barrier.wait()
             r.ctx.mgpu_shutdown()
