@@ -248,6 +248,7 @@ enum {
   OXC_STATUS_SURVIVOR_OVERFLOW = 1 << 2,/* oxc_mgpu_exchange_frame: a rank's survivor list exceeded the gather capacity (truncated) */
   OXC_STATUS_ID_OVERFLOW = 1 << 3,      /* a vis-buffer id did not fit the id bits of the packing (pixel skipped) */
   OXC_STATUS_CLIP_OVERFLOW = 1 << 5,    /* more triangles crossed the near / guard-band planes than the clip queue holds (2^20): the rest was dropped */
+  OXC_STATUS_BAD_MATERIAL = 1 << 6,     /* a MeshInstance::material_index outside the table of oxc_set_materials (rasterised as opaque) */
   OXC_STATUS_PEER_TIMEOUT = 1 << 4      /* oxc_mgpu_exchange_hiz: a peer did not raise its flag within 30 s (OXC_MGPU_TIMEOUT_MS); that frame's pyramid is incomplete */
 };
 int oxc_check_status(OxcContext* ctx, void* stream, uint32_t* flags_out /* may be NULL */);
@@ -350,6 +351,64 @@ int oxc_clear_visbuffer(OxcContext* ctx, uint64_t* vis_dev, uint32_t width, uint
  * produces no fragment — only OxcOutputs::raster_triangle_count drops by the number culled. */
 int oxc_raster_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width,
                          uint32_t height, uint64_t* vis_dev, int small_primitive_cull, void* stream);
+
+/* ---- alpha-tested discard of the vis-buffer encode (visbuffer_encode.slang:54-66) -------------------------------------------
+ * The reference's fragment shader discards a fragment of a material that has an albedo image when
+ *   material.albedo_color.a * albedo_image.SampleGrad(sampler, uv).a  <  clamp(material.alpha_cutoff, 0.001, 1.0)
+ * (scene.slang:51-66,92-94,115-124).  Once a material table is set, oxc_raster_visbuffer does the same: the pass's survivors
+ * are split by material (one extra kernel), meshlets of materials WITHOUT an albedo image go through the unchanged raster
+ * kernel, the others through k_raster_alpha, which evaluates the test per covered sample before the packed atomic max.
+ * The hardware sampler's arithmetic is not specified bit for bit, so the test is SPECIFIED here (oracle: orc_alpha_keep,
+ * oracle/oxc_oracle.c; canonical binary32 order, IEEE divide):
+ *   - uv at the pixel centre: perspective-correct barycentrics of the ORIGINAL triangle from its homogeneous edge functions
+ *     (rows of adj[x y w]; no per-vertex divide, so clipped triangles — vertices at w <= 0 — interpolate like any other);
+ *     vertices of a mesh without texture coordinates have uv = (0, 0) (scene.slang:355-361)
+ *   - mip level 0 only (images are single level), filter / address modes from the material's sampler (default: linear,
+ *     repeat — Texture.hpp:38-45): texel centre convention x = u * width - 0.5, weights = the f32 fractions (no 8-bit weight
+ *     quantisation), alpha = texel / 255
+ *   - NaN alpha or cutoff keeps the fragment (the comparison is false)
+ * The raster_triangle_count still counts every triangle that passed the near / backface test (discard is per fragment). */
+typedef struct OxcMaterial { /* SceneGPU.hpp:67-82 / scene.slang:51-66, 56 B */
+  uint16_t albedo_color[4];   /* halves */
+  uint16_t emissive_color[3];
+  uint16_t roughness_factor;
+  uint16_t metallic_factor;
+  uint16_t alpha_cutoff;      /* half */
+  uint32_t flags;             /* MaterialFlag, scene.slang:34-49 */
+  uint32_t sampler_index;
+  uint32_t albedo_image_index;
+  uint32_t normal_image_index;
+  uint32_t emissive_image_index;
+  uint32_t metallic_roughness_image_index;
+  uint32_t occlusion_image_index;
+  uint16_t uv_size[2];
+  uint16_t uv_offset[2];
+} OxcMaterial;
+#define OXC_MATERIAL_HAS_ALBEDO_IMAGE (1u << 0) /* MaterialFlag::HasAlbedoImage */
+#define OXC_MATERIAL_ALPHA_MASK (1u << 8)       /* MaterialFlag::AlphaMask (informational: the encode pass tests HasAlbedoImage only) */
+
+enum OxcImageFormat { OXC_IMAGE_RGBA8_UNORM = 0 /* alpha = byte 3 (sRGB variants: alpha is linear) */, OXC_IMAGE_R8_UNORM = 1 /* alpha only */ };
+typedef struct OxcAlphaImage {  /* one entry of the engine's bindless image table, the part this pass reads */
+  const void* texels_dev;       /* device pointer, tightly packed rows, level 0 */
+  uint32_t width, height;       /* >= 1 */
+  uint32_t format;              /* OxcImageFormat */
+  uint32_t reserved;
+} OxcAlphaImage;
+enum OxcSamplerFilter { OXC_FILTER_LINEAR = 0, OXC_FILTER_NEAREST = 1 };
+enum OxcSamplerAddress { OXC_ADDRESS_REPEAT = 0, OXC_ADDRESS_CLAMP_TO_EDGE = 1, OXC_ADDRESS_MIRRORED_REPEAT = 2 };
+typedef struct OxcSamplerDesc { uint32_t filter, address_u, address_v; } OxcSamplerDesc; /* vuk::SamplerCreateInfo subset, AssetManager_GLTF.cpp:75-120 */
+typedef struct OxcMaterialTable {
+  const OxcMaterial* materials;    /* host */
+  uint32_t material_count;
+  const OxcAlphaImage* images;     /* host array of device images */
+  uint32_t image_count;
+  const OxcSamplerDesc* samplers;  /* host; may be NULL: every sampler_index then means linear + repeat */
+  uint32_t sampler_count;
+} OxcMaterialTable;
+/* Copies the tables (the image texels stay where they are).  table == NULL or material_count == 0 switches the test off again.
+ * OXC_E_INVALID when a material with HasAlbedoImage names an image outside the table or an image is malformed.  A mesh instance
+ * whose material_index lies outside the table is rasterised as opaque and raises OXC_STATUS_BAD_MATERIAL. */
+int oxc_set_materials(OxcContext* ctx, const OxcMaterialTable* table, void* stream);
 
 /* Stand-alone clip pass: walks the pass's survivors again and clips / draws exactly the triangles described above.
  * oxc_raster_visbuffer does this by itself since round 2 (it queues those triangles while it rasterises), so a host only needs

@@ -540,12 +540,116 @@ static inline int edge_bias(int64_t ax, int64_t ay, int64_t bx, int64_t by) {
   return ((dy > 0) || (dy == 0 && dx < 0)) ? 0 : -1;
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Alpha-tested discard of the vis-buffer encode — visbuffer_encode.slang:54-66:
+ *     if (material.flags & HasAlbedoImage) {
+ *       alpha = material.sample_albedo_color(grad).a        // scene.slang:115-124: albedo_color * image.SampleGrad(sampler, uv)
+ *       if (alpha < clamp(material.get_alpha_cutoff(), 0.001, 1.0)) discard;
+ *     }
+ * uv is the rasteriser's perspective-correct interpolation of the vertex shader's tex_coord (:36,:44; (0,0) for a mesh
+ * without texture coordinates, scene.slang:355-361).  Interpolation and sampling happen in fixed-function hardware whose
+ * arithmetic is not specified bit for bit, so THIS is the specification the CUDA raster follows (include/oxcull.h repeats it):
+ *   1. per vertex of the drawn triangle: rw = 1 / w (the value of raster step 3) and (u, v).
+ *   2. at a covered sample the raster's own integer edge functions E_a, E_b, E_c (step 5; exact, >= 0, sum = 2*area > 0) are
+ *      the screen-space barycentric weights; perspective correction the way a hardware rasteriser does it:
+ *        p_i = (float)E_i * rw_i,  l_i = p_i * (1 / ((p_a + p_b) + p_c)),  u = (l_a*u_a + l_b*u_b) + l_c*u_c, v likewise
+ *      — every term is non-negative: no cancellation, however small or thin the triangle.
+ *   3. triangles that take the clip path: Sutherland-Hodgman carries (u, v) with the position (clip space is linear in the
+ *      attributes): a cut vertex gets uv = uv_I + t * (uv_O - uv_I) with the same t, same operation order; every piece of the
+ *      fan is then an ordinary triangle for steps 1-2.
+ *   4. level 0 of the image (single-level images; no gradient / LOD), filter and address modes of the material's sampler
+ *      (default linear + repeat, Texture.hpp:38-45).  Linear: x = u*width - 0.5, x0 = floor(x), wx = x - x0, texels x0 and
+ *      x0 + 1 (wrapped), top = a00 + wx*(a10 - a00), bot likewise, a = top + wy*(bot - top); alpha of a texel = byte / 255.
+ *      Nearest: texel floor(u*width).  float -> int saturates, NaN -> 0.
+ *   5. keep iff !(albedo_color.a * a < cutoff), cutoff = clamp(dequantize_half(alpha_cutoff), 0.001, 1.0) (NaN stays NaN).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct OrcAlphaMaterial {
+  const uint8_t* texels;
+  uint32_t width, height, format, filter, address_u, address_v;
+  float albedo_a, cutoff;
+} OrcAlphaMaterial;
+
+static inline int alpha_f2i(float f) {
+  return !(f == f) ? 0 : (f >= 2147483648.0f ? 2147483647 : (f <= -2147483648.0f ? (-2147483647 - 1) : (int)f));
+}
+static inline uint32_t alpha_wrap(int64_t i, uint32_t n, uint32_t mode) {
+  const int64_t N = (int64_t)n;
+  if (mode == OXC_ADDRESS_CLAMP_TO_EDGE) return (uint32_t)(i < 0 ? 0 : (i > N - 1 ? N - 1 : i));
+  if (mode == OXC_ADDRESS_MIRRORED_REPEAT) {
+    int64_t r = i % (2 * N);
+    if (r < 0) r += 2 * N;
+    return (uint32_t)(r < N ? r : 2 * N - 1 - r);
+  }
+  int64_t r = i % N;
+  if (r < 0) r += N;
+  return (uint32_t)r;
+}
+static inline float alpha_texel(const OrcAlphaMaterial* a, uint32_t x, uint32_t y) {
+  const size_t i = (size_t)y * a->width + x;
+  const uint32_t t = a->format == OXC_IMAGE_R8_UNORM ? a->texels[i] : a->texels[i * 4 + 3];
+  return (float)t / 255.0f;
+}
+static float alpha_sample(const OrcAlphaMaterial* a, float u, float v) {
+  const float fw = (float)a->width, fh = (float)a->height;
+  if (a->filter == OXC_FILTER_NEAREST) {
+    const int ix = alpha_f2i(floorf(u * fw)), iy = alpha_f2i(floorf(v * fh));
+    return alpha_texel(a, alpha_wrap(ix, a->width, a->address_u), alpha_wrap(iy, a->height, a->address_v));
+  }
+  const float x = u * fw - 0.5f, y = v * fh - 0.5f;
+  const float x0 = floorf(x), y0 = floorf(y);
+  const float wx = x - x0, wy = y - y0;
+  const int ix = alpha_f2i(x0), iy = alpha_f2i(y0);
+  const uint32_t xa = alpha_wrap(ix, a->width, a->address_u), xb = alpha_wrap((int64_t)ix + 1, a->width, a->address_u);
+  const uint32_t ya = alpha_wrap(iy, a->height, a->address_v), yb = alpha_wrap((int64_t)iy + 1, a->height, a->address_v);
+  const float a00 = alpha_texel(a, xa, ya), a10 = alpha_texel(a, xb, ya), a01 = alpha_texel(a, xa, yb), a11 = alpha_texel(a, xb, yb);
+  const float top = a00 + wx * (a10 - a00), bot = a01 + wx * (a11 - a01);
+  return top + wy * (bot - top);
+}
+/* steps 2, 4, 5: e = the three edge-function values of the sample, rw / uv in the same (a, b, c) order */
+static int alpha_keep_fragment(const OrcAlphaMaterial* a, const int64_t e[3], const float rw[3], const float uv[3][2]) {
+  const float p0 = (float)e[0] * rw[0], p1 = (float)e[1] * rw[1], p2 = (float)e[2] * rw[2];
+  const float inv = 1.0f / ((p0 + p1) + p2);
+  const float l0 = p0 * inv, l1 = p1 * inv, l2 = p2 * inv;
+  const float u = (l0 * uv[0][0] + l1 * uv[1][0]) + l2 * uv[2][0];
+  const float v = (l0 * uv[0][1] + l1 * uv[1][1]) + l2 * uv[2][1];
+  const float alpha = a->albedo_a * alpha_sample(a, u, v);
+  return !(alpha < a->cutoff);
+}
+/* returns 0 when the material is not alpha tested (no albedo image) */
+static int alpha_material_setup(const OxcMaterialTable* tab, uint32_t material_index, OrcAlphaMaterial* a) {
+  if (!tab || material_index >= tab->material_count) return 0;
+  const OxcMaterial* m = &tab->materials[material_index];
+  if (!(m->flags & OXC_MATERIAL_HAS_ALBEDO_IMAGE) || m->albedo_image_index >= tab->image_count) return 0;
+  const OxcAlphaImage* im = &tab->images[m->albedo_image_index];
+  a->texels = (const uint8_t*)im->texels_dev; /* the oracle's images live in host memory */
+  a->width = im->width; a->height = im->height; a->format = im->format;
+  a->filter = OXC_FILTER_LINEAR; a->address_u = OXC_ADDRESS_REPEAT; a->address_v = OXC_ADDRESS_REPEAT;
+  if (tab->samplers && m->sampler_index < tab->sampler_count) {
+    a->filter = tab->samplers[m->sampler_index].filter;
+    a->address_u = tab->samplers[m->sampler_index].address_u;
+    a->address_v = tab->samplers[m->sampler_index].address_v;
+  }
+  a->albedo_a = orc_dequantize_half(m->albedo_color[3]);
+  const float c = orc_dequantize_half(m->alpha_cutoff);
+  a->cutoff = !(c == c) ? c : (c < 0.001f ? 0.001f : (c > 1.0f ? 1.0f : c));
+  return 1;
+}
+
+static void raster_triangle_uv(const float clip[3][4], const float (*uv)[2], const OrcAlphaMaterial* am, uint32_t data, uint32_t W,
+                               uint32_t H, uint64_t* vis);
 static void raster_triangle(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis) {
+  raster_triangle_uv(clip, NULL, NULL, data, W, H, vis);
+}
+
+/* the raster specification above; am != NULL adds the alpha test (uv = the three vertices' texture coordinates) */
+static void raster_triangle_uv(const float clip[3][4], const float (*uv)[2], const OrcAlphaMaterial* am, uint32_t data, uint32_t W,
+                               uint32_t H, uint64_t* vis) {
   if (!(clip[0][3] > 0.0f && clip[1][3] > 0.0f && clip[2][3] > 0.0f)) return; /* step 2 */
   int64_t fx[3], fy[3];
-  float z[3];
+  float z[3], rws[3];
   for (int i = 0; i < 3; i++) {
     float rw = 1.0f / clip[i][3];
+    rws[i] = rw;
     float nx = clip[i][0] * rw, ny = clip[i][1] * rw;
     z[i] = clip[i][2] * rw;
     float sx = (nx * 0.5f + 0.5f) * (float)W, sy = (ny * 0.5f + 0.5f) * (float)H;
@@ -582,6 +686,12 @@ static void raster_triangle(const float clip[3][4], uint32_t data, uint32_t W, u
       if ((e0 + b0) < 0 || (e1 + b1) < 0 || (e2 + b2) < 0) continue;
       float zz = (za + (float)e1 * dzb) + (float)e2 * dzc;
       if (!(zz >= 0.0f && zz <= 1.0f)) continue;
+      if (am) { /* discard, visbuffer_encode.slang:62-64; (a, b, c) = vertices (0, 2, 1) */
+        const int64_t e[3] = {e0, e1, e2};
+        const float rwo[3] = {rws[0], rws[2], rws[1]};
+        const float uvo[3][2] = {{uv[0][0], uv[0][1]}, {uv[2][0], uv[2][1]}, {uv[1][0], uv[1][1]}};
+        if (!alpha_keep_fragment(am, e, rwo, uvo)) continue;
+      }
       uint32_t zbits = f2bits(zz);
       if (zbits == 0x80000000u) zbits = 0u; /* -0.0 -> +0.0 so unsigned order == depth order */
       uint64_t v = ((uint64_t)zbits << 32) | (uint64_t)data;
@@ -776,6 +886,113 @@ void orc_raster_visbuffer(const OrcScene* scene, const OxcMeshletInstance* meshl
     }
   }
   if (triangles_rasterised) *triangles_rasterised += ntri;
+}
+
+/* uv of the three corners of triangle `tri` (visbuffer_encode.slang:36; scene.slang:355-361, 491-497) */
+static void tri_uv(const OrcScene* s, const TriMeshlet* t, uint32_t tri, float uv[3][2]) {
+  const uint32_t* micro = (const uint32_t*)(s->blob + t->lod->local_triangle_indices);
+  const uint32_t* vidx = (const uint32_t*)(s->blob + t->lod->indirect_vertex_indices);
+  const uint16_t* tc = t->mesh->texture_coords ? (const uint16_t*)(s->blob + t->mesh->texture_coords) : NULL;
+  uint32_t base = t->meshlet.local_triangle_index_offset + tri * 3;
+  for (int c = 0; c < 3; c++) {
+    uint32_t local = micro_index(micro, base + (uint32_t)c);
+    uint32_t v = vidx[t->meshlet.indirect_vertex_index_offset + local];
+    uv[c][0] = tc ? orc_dequantize_half(tc[v * 2 + 0]) : 0.0f;
+    uv[c][1] = tc ? orc_dequantize_half(tc[v * 2 + 1]) : 0.0f;
+  }
+}
+
+/* Sutherland-Hodgman of raster_triangle_clipped_with carrying (u, v) (alpha spec step 3): vertex = x y z w u v */
+static void raster_triangle_clipped_uv(const float clip[3][4], const float uv[3][2], const OrcAlphaMaterial* am, uint32_t data,
+                                       uint32_t W, uint32_t H, uint64_t* vis) {
+  float poly[2][12][6];
+  int n = 3, cur = 0;
+  for (int i = 0; i < 3; i++) { memcpy(poly[0][i], clip[i], 16); poly[0][i][4] = uv[i][0]; poly[0][i][5] = uv[i][1]; }
+  for (int plane = 0; plane < 5 && n >= 3; plane++) {
+    float(*in)[6] = poly[cur];
+    float(*out)[6] = poly[cur ^ 1];
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+      const float* A = in[i];
+      const float* B = in[(i + 1) % n];
+      const float dA = clip_plane_distance(A, plane), dB = clip_plane_distance(B, plane);
+      const int inA = dA >= 0.0f, inB = dB >= 0.0f;
+      if (inA) { memcpy(out[m], A, 24); m++; }
+      if (inA != inB) {
+        const float* I = inA ? A : B;
+        const float* O = inA ? B : A;
+        const float dI = inA ? dA : dB, dO = inA ? dB : dA;
+        const float t = dI / (dI - dO);
+        for (int k = 0; k < 6; k++) out[m][k] = I[k] + t * (O[k] - I[k]);
+        m++;
+      }
+    }
+    n = m;
+    cur ^= 1;
+  }
+  if (n < 3) return;
+  for (int i = 1; i + 1 < n; i++) {
+    float tri[3][4], tuv[3][2];
+    const int idx[3] = {0, i, i + 1};
+    for (int k = 0; k < 3; k++) { memcpy(tri[k], poly[cur][idx[k]], 16); tuv[k][0] = poly[cur][idx[k]][4]; tuv[k][1] = poly[cur][idx[k]][5]; }
+    raster_triangle_uv(tri, tuv, am, data, W, H, vis);
+  }
+}
+
+/* one clip-space triangle of an alpha-tested material through the whole specification (plain or clip path) */
+int orc_raster_triangle_alpha(const OxcMaterialTable* table, uint32_t material_index, const float clip[3][4], const float uv[3][2],
+                              uint32_t data, uint32_t width, uint32_t height, uint64_t* vis) {
+  OrcAlphaMaterial am;
+  const OrcAlphaMaterial* a = alpha_material_setup(table, material_index, &am) ? &am : NULL;
+  if (tri_dropped_by_range(clip, width, height)) {
+    if (a) raster_triangle_clipped_uv(clip, uv, a, data, width, height, vis);
+    else raster_triangle_clipped(clip, data, width, height, vis);
+    return 1;
+  }
+  raster_triangle_uv(clip, uv, a, data, width, height, vis);
+  return 0;
+}
+float orc_alpha_sample(const OxcAlphaImage* image, const OxcSamplerDesc* sampler /* NULL: linear + repeat */, float u, float v) {
+  OrcAlphaMaterial a;
+  memset(&a, 0, sizeof a);
+  a.texels = (const uint8_t*)image->texels_dev; a.width = image->width; a.height = image->height; a.format = image->format;
+  if (sampler) { a.filter = sampler->filter; a.address_u = sampler->address_u; a.address_v = sampler->address_v; }
+  return alpha_sample(&a, u, v);
+}
+
+/* orc_raster_visbuffer_clip with the alpha-tested discard of visbuffer_encode.slang:54-66 (specification above raster_triangle).
+ * table->images[].texels_dev are HOST pointers here.  triangles_rasterised counts the triangles that pass the cull, as before. */
+void orc_raster_visbuffer_alpha(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                                const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
+                                const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,
+                                const OxcMaterialTable* table, uint64_t* triangles_rasterised, uint64_t* alpha_tested_triangles) {
+  uint64_t ntri = 0, nalpha = 0;
+  for (uint32_t g = 0; g < pass_count; g++) {
+    uint32_t mii = visible_indices[pass_first + g];
+    TriMeshlet t;
+    fetch_tri_meshlet(scene, meshlet_instances, mii, cam, &t);
+    const uint32_t material_index = scene->mesh_instances[meshlet_instances[mii].mesh_instance_index].material_index; /* :46 */
+    OrcAlphaMaterial am;
+    const OrcAlphaMaterial* a = alpha_material_setup(table, material_index, &am) ? &am : NULL;
+    for (uint32_t tri = 0; tri < t.meshlet.triangle_count && tri < 64; tri++) {
+      float clip[3][4], uv[3][2];
+      tri_clip(scene, &t, tri, clip);
+      if (!tri_passes(clip)) continue;
+      ntri++;
+      uint32_t data = ((mii + id_base) << OXC_VIS_PRIMITIVE_BITS) | (tri & OXC_VIS_PRIMITIVE_MASK);
+      if (!a) {
+        if (tri_dropped_by_range(clip, width, height)) raster_triangle_clipped(clip, data, width, height, vis);
+        else raster_triangle(clip, data, width, height, vis);
+        continue;
+      }
+      nalpha++;
+      tri_uv(scene, &t, tri, uv);
+      if (tri_dropped_by_range(clip, width, height)) raster_triangle_clipped_uv(clip, uv, a, data, width, height, vis);
+      else raster_triangle_uv(clip, uv, a, data, width, height, vis);
+    }
+  }
+  if (triangles_rasterised) *triangles_rasterised += ntri;
+  if (alpha_tested_triangles) *alpha_tested_triangles += nalpha;
 }
 
 void orc_resolve_visbuffer(const uint64_t* vis, uint32_t width, uint32_t height, uint32_t* vis32, float* depth) {

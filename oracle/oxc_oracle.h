@@ -138,6 +138,18 @@ void orc_raster_visbuffer_clip(const OrcScene* scene, const OxcMeshletInstance* 
                                const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,
                                uint64_t* triangles_rasterised, uint64_t* triangles_clipped);
 
+/* Alpha-tested discard of the vis-buffer encode (visbuffer_encode.slang:54-66; specification in oxc_oracle.c above
+ * raster_triangle, repeated in include/oxcull.h).  Image texels are HOST pointers for the oracle. */
+/* one clip-space triangle of material `material_index` (uv = its three texture coordinates) through the raster + alpha
+ * specification, plain or clip path; returns 1 if it took the clip path */
+int orc_raster_triangle_alpha(const OxcMaterialTable* table, uint32_t material_index, const float clip[3][4], const float uv[3][2],
+                              uint32_t data, uint32_t width, uint32_t height, uint64_t* vis);
+float orc_alpha_sample(const OxcAlphaImage* image, const OxcSamplerDesc* sampler, float u, float v);
+void orc_raster_visbuffer_alpha(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
+                                const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
+                                const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,
+                                const OxcMaterialTable* table, uint64_t* triangles_rasterised, uint64_t* alpha_tested_triangles);
+
 /* passes/cull_meshlets_hpb.slang:27-99 + cull.slang:137-166 test_vsm_page.  hpb: levels of (layers x s x s) bytes. */
 void orc_cull_meshlets_hpb(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, const OxcCullCamera* cam,
                            const OxcVirtualClipmap* clipmaps, const uint32_t* dirty_flags, uint32_t clipmap_count,

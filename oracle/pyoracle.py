@@ -182,6 +182,51 @@ def raster_clip(hs, mi, visible, first, count, cam, vis, id_base=0):
     return int(ntri.value), int(nclip.value)
 
 
+class MaterialTable:
+    """host-side OxcMaterialTable for the oracle: images = list of (uint8 array [h, w, 4] or [h, w], format)"""
+
+    def __init__(self, materials, images=(), samplers=None):
+        self.materials = np.ascontiguousarray(materials, dtype=abi.MATERIAL_DT)
+        self.texels = [np.ascontiguousarray(t, dtype=np.uint8) for t, _ in images]
+        self.images = np.zeros(len(images), dtype=abi.ALPHA_IMAGE_DT)
+        for i, (t, fmt) in enumerate(images):
+            self.images[i] = (self.texels[i].ctypes.data, t.shape[1], t.shape[0], fmt, 0)
+        self.samplers = None if samplers is None else np.ascontiguousarray(samplers, dtype=abi.SAMPLER_DT)
+        self.ref = abi.MaterialTable()
+        self.ref.materials, self.ref.material_count = self.materials.ctypes.data, len(self.materials)
+        self.ref.images, self.ref.image_count = (self.images.ctypes.data if len(self.images) else None), len(self.images)
+        if self.samplers is not None:
+            self.ref.samplers, self.ref.sampler_count = self.samplers.ctypes.data, len(self.samplers)
+
+
+def raster_alpha(hs, mi, visible, first, count, cam, vis, table: MaterialTable, id_base=0):
+    """clipped raster with the alpha-tested discard of visbuffer_encode.slang:54-66; returns (triangles passing the cull,
+    triangles of alpha-tested materials among them)"""
+    h, w = vis.shape
+    ntri, nalpha = C.c_uint64(0), C.c_uint64(0)
+    lib().orc_raster_visbuffer_alpha(hs.ref, _p(mi), _p(visible), C.c_uint32(first), C.c_uint32(count), _p(cam), C.c_uint32(id_base),
+                                     C.c_uint32(w), C.c_uint32(h), _p(vis), C.byref(table.ref), C.byref(ntri), C.byref(nalpha))
+    return int(ntri.value), int(nalpha.value)
+
+
+def alpha_sample(texels, fmt, u, v, sampler=None):
+    t = np.ascontiguousarray(texels, dtype=np.uint8)
+    img = np.zeros(1, dtype=abi.ALPHA_IMAGE_DT)
+    img[0] = (t.ctypes.data, t.shape[1], t.shape[0], fmt, 0)
+    smp = None if sampler is None else np.array([sampler], dtype=abi.SAMPLER_DT)
+    lib().orc_alpha_sample.restype = C.c_float
+    return float(lib().orc_alpha_sample(_p(img), _p(smp), C.c_float(u), C.c_float(v)))
+
+
+def raster_triangle_alpha(table: MaterialTable, material_index, clip, uv, data, vis):
+    """one clip-space triangle of `material_index` through the raster + alpha specification; returns 1 if it was clipped"""
+    c = np.ascontiguousarray(clip, dtype=np.float32).reshape(3, 4)
+    t = np.ascontiguousarray(uv, dtype=np.float32).reshape(3, 2)
+    h, w = vis.shape
+    return int(lib().orc_raster_triangle_alpha(C.byref(table.ref), C.c_uint32(material_index), _p(c), _p(t), C.c_uint32(data), C.c_uint32(w),
+                                               C.c_uint32(h), _p(vis)))
+
+
 def resolve(vis):
     h, w = vis.shape
     v32 = np.zeros((h, w), dtype=np.uint32)
@@ -200,7 +245,7 @@ def merge_occluder_depth(vis, occluder_depth):
 
 
 def frame(hs, cam, width, height, mask, occluder_depth=None, first=0, count=0xFFFFFFFF, id_base_fn=None,
-          between_passes=None, after_frame=None):
+          between_passes=None, after_frame=None, materials=None):
     """Serial two-pass frame exactly as RendererInstance::render sequences it (RendererInstance.cpp:842-884).
     Returns dict with every intermediate the GPU parity tests compare.
 
@@ -216,14 +261,19 @@ def frame(hs, cam, width, height, mask, occluder_depth=None, first=0, count=0xFF
     visible, tcmd_e = cull_meshlets_hiz(hs, mi, vis, cam, abi.CULL_TEST_ALL, hiz, mask)
     e = int(vis["early"][0])
     mask_after_early = mask.copy()
-    ntri_e = raster_clip(hs, mi, visible, 0, e, cam, img, id_base)[0]  # the product's raster clips what the plain spec drops
+    def _raster(first_, count_):
+        if materials is not None:  # visbuffer_encode.slang:54-66
+            return raster_alpha(hs, mi, visible, first_, count_, cam, img, materials, id_base)[0]
+        return raster_clip(hs, mi, visible, first_, count_, cam, img, id_base)[0]  # the product's raster clips what the plain spec drops
+
+    ntri_e = _raster(0, e)
     if between_passes:
         between_passes(img)
     _, depth = resolve(img)
     build_hiz(depth, hiz)
     visible, tcmd_l = cull_meshlets_hiz(hs, mi, vis, cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, hiz, mask, visible)
     l = int(vis["late"][0])
-    ntri_l = raster_clip(hs, mi, visible, e, l, cam, img, id_base)[0]
+    ntri_l = _raster(e, l)
     if after_frame:
         after_frame(img)
     return dict(meshlet_instances=mi, visibility=vis, visible=visible, early=e, late=l, hiz=hiz, vis64=img,

@@ -118,6 +118,48 @@ VIS_WIDE_PRIMITIVE_BITS = 6
 VIS_CLEAR = 0xFFFFFFFF
 STATUS_MESHLET_OVERFLOW, STATUS_BAD_GEOMETRY, STATUS_SURVIVOR_OVERFLOW, STATUS_ID_OVERFLOW, STATUS_PEER_TIMEOUT = 1, 2, 4, 8, 16
 STATUS_CLIP_OVERFLOW = 32
+STATUS_BAD_MATERIAL = 64
+
+# Material — SceneGPU.hpp:67-82 / scene.slang:51-66 (56 B); MaterialFlag scene.slang:34-49
+MATERIAL_DT = np.dtype(
+    [
+        ("albedo_color", "<u2", (4,)),
+        ("emissive_color", "<u2", (3,)),
+        ("roughness_factor", "<u2"),
+        ("metallic_factor", "<u2"),
+        ("alpha_cutoff", "<u2"),
+        ("flags", "<u4"),
+        ("sampler_index", "<u4"),
+        ("albedo_image_index", "<u4"),
+        ("normal_image_index", "<u4"),
+        ("emissive_image_index", "<u4"),
+        ("metallic_roughness_image_index", "<u4"),
+        ("occlusion_image_index", "<u4"),
+        ("uv_size", "<u2", (2,)),
+        ("uv_offset", "<u2", (2,)),
+    ]
+)
+assert MATERIAL_DT.itemsize == 56
+MATERIAL_HAS_ALBEDO_IMAGE, MATERIAL_ALPHA_MASK = 1, 1 << 8
+IMAGE_RGBA8_UNORM, IMAGE_R8_UNORM = 0, 1
+FILTER_LINEAR, FILTER_NEAREST = 0, 1
+ADDRESS_REPEAT, ADDRESS_CLAMP_TO_EDGE, ADDRESS_MIRRORED_REPEAT = 0, 1, 2
+ALPHA_IMAGE_DT = np.dtype([("texels", "<u8"), ("width", "<u4"), ("height", "<u4"), ("format", "<u4"), ("reserved", "<u4")])
+SAMPLER_DT = np.dtype([("filter", "<u4"), ("address_u", "<u4"), ("address_v", "<u4")])
+
+
+class MaterialTable(C.Structure):
+    """OxcMaterialTable"""
+
+    _fields_ = [
+        ("materials", C.c_void_p),
+        ("material_count", C.c_uint32),
+        ("images", C.c_void_p),
+        ("image_count", C.c_uint32),
+        ("samplers", C.c_void_p),
+        ("sampler_count", C.c_uint32),
+    ]
+
 
 # VSMPageState — Shaders/rmvsm.slang:16-28 ([Flags] enum)
 VSM_PAGE_VISIBLE = 1

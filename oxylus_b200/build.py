@@ -16,7 +16,7 @@ SOURCES = [os.path.join(CSRC, "oxcull.cu"), os.path.join(CSRC, "host", "renderer
            os.path.join(CSRC, "host", "mesh_builder.cpp"), os.path.join(CSRC, "host", "mesh_simplifier.cpp")]
 DEPS = SOURCES + [
     os.path.join(CSRC, f)
-    for f in ("oxc_types.cuh", "oxc_exact.cuh", "oxc_filtered.cuh", "oxc_raster_core.cuh", "oxc_tma.cuh", "kernels_cull.cuh", "kernels_decode.cuh", "kernels_hiz.cuh", "kernels_mgpu.cuh", "kernels_tri.cuh")
+    for f in ("oxc_types.cuh", "oxc_exact.cuh", "oxc_filtered.cuh", "oxc_raster_core.cuh", "oxc_tma.cuh", "kernels_cull.cuh", "kernels_decode.cuh", "kernels_hiz.cuh", "kernels_mgpu.cuh", "kernels_tri.cuh", "kernels_alpha.cuh", "oxc_alpha.cuh")
 ] + [os.path.join(CSRC, "host", "renderer_instance.hpp"), os.path.join(CSRC, "host", "mesh_simplifier.hpp"), os.path.join(os.path.dirname(HERE), "include", "oxcull.h")]
 
 NVCC_FLAGS = [

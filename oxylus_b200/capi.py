@@ -71,6 +71,7 @@ def load(build_if_missing=True):
     lib.oxc_clear_visbuffer.argtypes = [vp, vp, u32, u32, vp]
     lib.oxc_raster_visbuffer.argtypes = [vp, vp, u32, u32, u32, vp, i32, vp]
     lib.oxc_raster_visbuffer_clip_pass.argtypes = [vp, vp, u32, u32, u32, vp, vp]
+    lib.oxc_set_materials.argtypes = [vp, C.POINTER(abi.MaterialTable), vp]
     lib.oxc_resolve_visbuffer.argtypes = [vp, vp, u32, u32, vp, vp, vp]
     lib.oxc_merge_depth.argtypes = [vp, vp, vp, u32, u32, vp]
     lib.oxc_clear_visbuffer_with_depth.argtypes = [vp, vp, vp, u32, u32, vp]
@@ -328,6 +329,23 @@ class Context:
     def raster_visbuffer(self, cam, flags, w, h, vis_dev, small_primitive_cull=False):
         _check(self.lib.oxc_raster_visbuffer(self.h, _ptr(cam), flags, w, h, _ptr(vis_dev), int(small_primitive_cull), self.stream),
                "oxc_raster_visbuffer")
+
+    def set_materials(self, materials, images=None, samplers=None):
+        """oxc_set_materials: `materials` abi.MATERIAL_DT array (None switches the alpha test off); `images` a list of
+        (device pointer, width, height, format); `samplers` an abi.SAMPLER_DT array or None (linear + repeat)"""
+        if materials is None or len(materials) == 0:
+            _check(self.lib.oxc_set_materials(self.h, None, self.stream), "oxc_set_materials")
+            return
+        mats = np.ascontiguousarray(materials, dtype=abi.MATERIAL_DT)
+        imgs = np.zeros(len(images or []), dtype=abi.ALPHA_IMAGE_DT)
+        for i, (ptr, w, h, fmt) in enumerate(images or []):
+            imgs[i] = (int(ptr), w, h, fmt, 0)
+        smp = None if samplers is None else np.ascontiguousarray(samplers, dtype=abi.SAMPLER_DT)
+        t = abi.MaterialTable()
+        t.materials, t.material_count = mats.ctypes.data, len(mats)
+        t.images, t.image_count = (imgs.ctypes.data if len(imgs) else None), len(imgs)
+        t.samplers, t.sampler_count = (None if smp is None else smp.ctypes.data), (0 if smp is None else len(smp))
+        _check(self.lib.oxc_set_materials(self.h, C.byref(t), self.stream), "oxc_set_materials")
 
     def raster_visbuffer_clip_pass(self, cam, flags, w, h, vis_dev):
         _check(self.lib.oxc_raster_visbuffer_clip_pass(self.h, _ptr(cam), flags, w, h, _ptr(vis_dev), self.stream),

@@ -1,0 +1,140 @@
+// oxc_alpha.cuh — the alpha test of the vis-buffer encode (visbuffer_encode.slang:54-66) as pure per-thread functions:
+// perspective-correct uv at a covered sample from the raster's own integer edge functions, one filtered alpha fetch, the
+// comparison against the clamped cutoff; the uv-carrying clipper for triangles that take the clip path.
+// No warp intrinsics, no shared memory: tests compile this source for the host.
+// Specification: include/oxcull.h (comment above OxcMaterial) == oracle/oxc_oracle.c (comment above raster_triangle),
+// operation for operation.
+#pragma once
+#include <climits>
+
+#include "oxc_exact.cuh"
+
+namespace oxc {
+
+// Device copy of one material, reduced to what the encode pass reads (scene.slang:51-66).
+struct __align__(16) AlphaMaterial {
+  const uint8_t* texels; // null: no albedo image (opaque for this pass)
+  uint32_t width, height;
+  uint32_t format;       // OxcImageFormat
+  uint32_t filter, address_u, address_v;
+  float albedo_a;        // dequantize_half(albedo_color.w)
+  float cutoff;          // the clamped cutoff: min(max(dequantize_half(alpha_cutoff), 0.001), 1.0); NaN stays NaN
+};
+static_assert(sizeof(AlphaMaterial) == 48, "AlphaMaterial");
+
+// Per drawn triangle, in the raster's (a, b, c) order (TriSetup: a = vertex 0, b = vertex 2, c = vertex 1): 1 / w and uv.
+struct AlphaTri {
+  float rw[3];
+  float u[3], v[3];
+};
+
+// clip-space vertices + uv of the triangle as submitted (vertex order 0, 1, 2) -> the raster's order
+OXC_DI void alpha_tri_setup(const float4 c0, const float4 c1, const float4 c2, float u0, float v0, float u1, float v1, float u2, float v2,
+                            AlphaTri& t) {
+  t.rw[0] = fd(1.0f, c0.w); t.rw[1] = fd(1.0f, c2.w); t.rw[2] = fd(1.0f, c1.w); // the rw of to_screen (raster spec step 3)
+  t.u[0] = u0; t.u[1] = u2; t.u[2] = u1;
+  t.v[0] = v0; t.v[1] = v2; t.v[2] = v1;
+}
+
+// float -> int, NaN -> 0, saturating (the host build and the device agree for every input)
+OXC_DI int alpha_f2i(float f) {
+  return !(f == f) ? 0 : (f >= 2147483648.0f ? INT_MAX : (f <= -2147483648.0f ? INT_MIN : (int)f));
+}
+
+OXC_DI uint32_t alpha_wrap(long long i, uint32_t n, uint32_t mode) {
+  const long long N = (long long)n;
+  if (mode == OXC_ADDRESS_CLAMP_TO_EDGE) return (uint32_t)(i < 0 ? 0 : (i > N - 1 ? N - 1 : i));
+  if (mode == OXC_ADDRESS_MIRRORED_REPEAT) {
+    long long r = i % (2 * N);
+    if (r < 0) r += 2 * N;
+    return (uint32_t)(r < N ? r : 2 * N - 1 - r);
+  }
+  long long r = i % N;
+  if (r < 0) r += N;
+  return (uint32_t)r;
+}
+
+OXC_DI float alpha_texel(const AlphaMaterial& m, uint32_t x, uint32_t y) {
+  const size_t i = (size_t)y * m.width + x;
+  const uint32_t t = m.format == OXC_IMAGE_R8_UNORM ? m.texels[i] : m.texels[i * 4 + 3];
+  return fd((float)t, 255.0f);
+}
+
+// level 0 of the albedo image's alpha channel at (u, v)
+OXC_DI float alpha_sample(const AlphaMaterial& m, float u, float v) {
+  const float fw = (float)m.width, fh = (float)m.height;
+  if (m.filter == OXC_FILTER_NEAREST) {
+    const int ix = alpha_f2i(floorf(fm(u, fw))), iy = alpha_f2i(floorf(fm(v, fh)));
+    return alpha_texel(m, alpha_wrap(ix, m.width, m.address_u), alpha_wrap(iy, m.height, m.address_v));
+  }
+  const float x = fs(fm(u, fw), 0.5f), y = fs(fm(v, fh), 0.5f);
+  const float x0 = floorf(x), y0 = floorf(y);
+  const float wx = fs(x, x0), wy = fs(y, y0);
+  const int ix = alpha_f2i(x0), iy = alpha_f2i(y0);
+  const uint32_t xa = alpha_wrap(ix, m.width, m.address_u), xb = alpha_wrap((long long)ix + 1, m.width, m.address_u);
+  const uint32_t ya = alpha_wrap(iy, m.height, m.address_v), yb = alpha_wrap((long long)iy + 1, m.height, m.address_v);
+  const float a00 = alpha_texel(m, xa, ya), a10 = alpha_texel(m, xb, ya), a01 = alpha_texel(m, xa, yb), a11 = alpha_texel(m, xb, yb);
+  const float top = fa(a00, fm(wx, fs(a10, a00))), bot = fa(a01, fm(wx, fs(a11, a01)));
+  return fa(top, fm(wy, fs(bot, top)));
+}
+
+// true = the fragment survives the alpha test (visbuffer_encode.slang:62-64 with the comparison negated).  e0..e2 = the raster's
+// edge-function values at the sample (weights of a, b, c; exact integers, >= 0 inside, sum = 2 * area > 0): perspective
+// correction of non-negative terms only, so tiny and thin triangles interpolate without cancellation.
+OXC_DI bool alpha_keep(const AlphaMaterial& m, const AlphaTri& t, long long e0, long long e1, long long e2) {
+  const float p0 = fm((float)e0, t.rw[0]), p1 = fm((float)e1, t.rw[1]), p2 = fm((float)e2, t.rw[2]);
+  const float inv = fd(1.0f, fa(fa(p0, p1), p2));
+  const float l0 = fm(p0, inv), l1 = fm(p1, inv), l2 = fm(p2, inv);
+  const float u = fa(fa(fm(l0, t.u[0]), fm(l1, t.u[1])), fm(l2, t.u[2]));
+  const float v = fa(fa(fm(l0, t.v[0]), fm(l1, t.v[1])), fm(l2, t.v[2]));
+  const float a = fm(m.albedo_a, alpha_sample(m, u, v));
+  return !(a < m.cutoff);
+}
+
+// Sutherland-Hodgman of clip_polygon (oxc_raster_core.cuh) carrying uv: clip space is linear in the attributes, so a cut vertex
+// gets uv_I + t * (uv_O - uv_I) with the position's t and operation order.  Same planes, same order, same inside rule.
+struct ClipVertUV {
+  float4 c;
+  float u, v;
+};
+OXC_DI float clip_plane_distance_uv(const float4 v, int plane) {
+  switch (plane) {
+    case 0: return fs(v.w, v.z);
+    case 1: return fa(v.w, v.x);
+    case 2: return fs(v.w, v.x);
+    case 3: return fa(v.w, v.y);
+    default: return fs(v.w, v.y);
+  }
+}
+OXC_DI int clip_polygon_uv(const ClipVertUV v0, const ClipVertUV v1, const ClipVertUV v2, ClipVertUV (*poly)[12], int& cur) {
+  int n = 3;
+  cur = 0;
+  poly[0][0] = v0; poly[0][1] = v1; poly[0][2] = v2;
+  for (int plane = 0; plane < 5 && n >= 3; plane++) {
+    const ClipVertUV* in = poly[cur];
+    ClipVertUV* out = poly[cur ^ 1];
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+      const ClipVertUV A = in[i], B = in[(i + 1) % n];
+      const float dA = clip_plane_distance_uv(A.c, plane), dB = clip_plane_distance_uv(B.c, plane);
+      const bool inA = dA >= 0.0f, inB = dB >= 0.0f;
+      if (inA) out[m++] = A;
+      if (inA != inB) {
+        const ClipVertUV I = inA ? A : B, O = inA ? B : A;
+        const float dI = inA ? dA : dB, dO = inA ? dB : dA;
+        const float tt = fd(dI, fs(dI, dO));
+        ClipVertUV r;
+        r.c = make_float4(fa(I.c.x, fm(tt, fs(O.c.x, I.c.x))), fa(I.c.y, fm(tt, fs(O.c.y, I.c.y))), fa(I.c.z, fm(tt, fs(O.c.z, I.c.z))),
+                          fa(I.c.w, fm(tt, fs(O.c.w, I.c.w))));
+        r.u = fa(I.u, fm(tt, fs(O.u, I.u)));
+        r.v = fa(I.v, fm(tt, fs(O.v, I.v)));
+        out[m++] = r;
+      }
+    }
+    n = m;
+    cur ^= 1;
+  }
+  return n;
+}
+
+} // namespace oxc

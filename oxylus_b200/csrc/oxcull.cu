@@ -19,6 +19,7 @@
 #include "kernels_hiz.cuh"
 #include "kernels_mgpu.cuh"
 #include "kernels_tri.cuh"
+#include "kernels_alpha.cuh"
 
 using namespace oxc;
 
@@ -170,6 +171,12 @@ struct OxcContext {
   std::vector<uint64_t> id_prefix; // [I + 1] prefix sums of the largest-LOD meshlet count per mesh instance (host side)
   uint64_t scene_id_bound = 0;    // upper bound of the GLOBAL meshlet-instance id range (sum over all mesh instances of the largest LOD)
   uint32_t prim_bits = OXC_VIS_PRIMITIVE_BITS; // triangle bits of the vis-buffer word (8 = reference, 6 = wide_ids)
+  // alpha-tested discard (oxc_set_materials): device material table, the two survivor lists of a raster pass and their counters
+  AlphaMaterial* d_alpha_materials = nullptr;
+  uint32_t alpha_material_count = 0;
+  bool alpha_active = false;           // at least one material has an albedo image
+  uint32_t* d_alpha_lists = nullptr;   // [2][max_meshlet_instances]: opaque, alpha-tested
+  uint8_t* d_alpha_cmd = nullptr;      // 64 B: opaque cmd @0, alpha-tested cmd @16, an all-zero visibility record @32
 };
 
 namespace {
@@ -364,6 +371,7 @@ void oxc_destroy(OxcContext* c) {
   cudaFree(c->d_cull_meshlets_cmd); cudaFree(c->d_cull_triangles_cmd); cudaFree(c->d_draw_cmd);
   cudaFree(c->d_reordered); cudaFree(c->d_tri_counter); cudaFree(c->d_raster_work); cudaFree(c->d_big_queue); cudaFree(c->d_clip_queue); cudaFree(c->d_id_base_auto); cudaFree(c->d_status); cudaFree(c->d_hiz);
   cudaFree(c->d_view_planes); cudaFree(c->d_view_bits); cudaFree(c->d_view_counts); cudaFree(c->d_inst_views);
+  cudaFree(c->d_alpha_materials); cudaFree(c->d_alpha_lists); cudaFree(c->d_alpha_cmd);
   delete c;
 }
 
@@ -745,13 +753,96 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
   if (grid == 0) grid = 1;
   p.big_queue = c->d_big_queue; p.big_counters = c->d_big_counters; p.big_capacity = c->big_capacity;
   p.clip_queue = c->d_clip_queue; p.clip_counter = c->d_clip_counter; p.clip_capacity = c->clip_capacity;
-  if (p.late) k_raster_visbuffer<true><<<grid, TRI_THREADS, 0, s>>>(p);
-  else k_raster_visbuffer<false><<<grid, TRI_THREADS, 0, s>>>(p);
+  TriParams pm = p; // what the plain raster kernel walks: the pass's survivors, or their opaque part
+  AlphaParams ap{};
+  if (c->alpha_active) { // visbuffer_encode.slang:54-66: split the survivors by material (kernels_alpha.cuh)
+    ap.mesh_instances = c->d_mesh_instances; ap.materials = c->d_alpha_materials; ap.material_count = c->alpha_material_count;
+    ap.opaque_list = c->d_alpha_lists; ap.masked_list = c->d_alpha_lists + c->info.max_meshlet_instances;
+    ap.opaque_cmd = reinterpret_cast<OxcDispatchIndirectCommand*>(c->d_alpha_cmd);
+    ap.masked_cmd = reinterpret_cast<OxcDispatchIndirectCommand*>(c->d_alpha_cmd + 16);
+    CK(cudaMemsetAsync(c->d_alpha_cmd, 0, 64, s));
+    k_partition_alpha<<<c->sm_count * 4, 256, 0, s>>>(p, ap);
+    LAUNCHED();
+    pm.visible_indices = ap.opaque_list; pm.tri_cmd = ap.opaque_cmd;
+    pm.vis = reinterpret_cast<const OxcMeshletInstanceVisibility*>(c->d_alpha_cmd + 32); // the list starts at 0 in either pass
+  }
+  if (p.late) k_raster_visbuffer<true><<<grid, TRI_THREADS, 0, s>>>(pm);
+  else k_raster_visbuffer<false><<<grid, TRI_THREADS, 0, s>>>(pm);
   LAUNCHED();
   k_raster_clip_queue<<<c->sm_count, 128, 0, s>>>(p); // the triangles the plain rules drop (usually none: exits at once)
   LAUNCHED();
+  if (c->alpha_active) {
+    k_raster_alpha<<<c->sm_count * 8, ALPHA_THREADS, 0, s>>>(p, ap); // the alpha-tested meshlets, one warp each
+    LAUNCHED();
+  }
   k_raster_big<<<c->sm_count * 8, 256, 0, s>>>(p); // the deferred large triangles, one warp per <= 64x32-pixel chunk
   LAUNCHED();
+  return OXC_OK;
+}
+
+// scene.slang:92-94 on the host (integer bit manipulation: identical to the device's dequantize_half)
+static float host_dequantize_half(uint16_t h) {
+  const uint32_t sgn = ((uint32_t)h & 0x8000u) << 16, em = (uint32_t)h & 0x7fffu;
+  uint32_t r = (em + (112u << 10)) << 13;
+  r = (em < (1u << 10)) ? 0u : r;
+  r += (em >= (31u << 10)) ? (112u << 23) : 0u;
+  const uint32_t bits = sgn | r;
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+
+int oxc_set_materials(OxcContext* c, const OxcMaterialTable* t, void* stream) {
+  if (!c) return fail(OXC_E_INVALID, "null context");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  if (!t || t->material_count == 0) { // back to the plain encode
+    c->alpha_active = false;
+    c->alpha_material_count = 0;
+    return OXC_OK;
+  }
+  if (!t->materials || (t->image_count && !t->images) || (t->sampler_count && !t->samplers)) return fail(OXC_E_INVALID, "material table: null array");
+  std::vector<AlphaMaterial> ms(t->material_count);
+  bool any = false;
+  for (uint32_t i = 0; i < t->material_count; i++) {
+    const OxcMaterial& m = t->materials[i];
+    AlphaMaterial& d = ms[i];
+    memset(&d, 0, sizeof d);
+    if (!(m.flags & OXC_MATERIAL_HAS_ALBEDO_IMAGE)) continue; // visbuffer_encode.slang:55: no image, no test
+    if (m.albedo_image_index >= t->image_count)
+      return fail(OXC_E_INVALID, "material %u: albedo_image_index %u outside the image table (%u)", i, m.albedo_image_index, t->image_count);
+    const OxcAlphaImage& im = t->images[m.albedo_image_index];
+    if (!im.texels_dev || im.width == 0 || im.height == 0 || im.width > (1u << 16) || im.height > (1u << 16) ||
+        (im.format != OXC_IMAGE_RGBA8_UNORM && im.format != OXC_IMAGE_R8_UNORM))
+      return fail(OXC_E_INVALID, "image %u: null texels, extent outside 1..65536 or unknown format", m.albedo_image_index);
+    d.texels = static_cast<const uint8_t*>(im.texels_dev); d.width = im.width; d.height = im.height; d.format = im.format;
+    d.filter = OXC_FILTER_LINEAR; d.address_u = OXC_ADDRESS_REPEAT; d.address_v = OXC_ADDRESS_REPEAT; // Texture.hpp:38-45 defaults
+    if (t->samplers && m.sampler_index < t->sampler_count) {
+      const OxcSamplerDesc& sd = t->samplers[m.sampler_index];
+      if (sd.filter > OXC_FILTER_NEAREST || sd.address_u > OXC_ADDRESS_MIRRORED_REPEAT || sd.address_v > OXC_ADDRESS_MIRRORED_REPEAT)
+        return fail(OXC_E_INVALID, "sampler %u: unknown filter / address mode", m.sampler_index);
+      d.filter = sd.filter; d.address_u = sd.address_u; d.address_v = sd.address_v;
+    }
+    d.albedo_a = host_dequantize_half(m.albedo_color[3]);
+    const float cut = host_dequantize_half(m.alpha_cutoff);
+    d.cutoff = !(cut == cut) ? cut : (cut < 0.001f ? 0.001f : (cut > 1.0f ? 1.0f : cut)); // clamp(.., 0.001, 1.0); NaN keeps everything
+    any = true;
+  }
+  if (t->material_count > c->alpha_material_count || !c->d_alpha_materials) {
+    c->alpha_active = false;
+    CK(cudaStreamSynchronize(s)); // a raster in flight may still read the old table
+    cudaFree(c->d_alpha_materials);
+    c->d_alpha_materials = nullptr;
+    if (dalloc(&c->d_alpha_materials, (size_t)t->material_count) != OXC_OK) return OXC_E_CUDA;
+  }
+  if (!c->d_alpha_lists) {
+    if (dalloc(&c->d_alpha_lists, (size_t)c->info.max_meshlet_instances * 2) != OXC_OK) return OXC_E_CUDA;
+    if (dalloc(&c->d_alpha_cmd, (size_t)64) != OXC_OK) return OXC_E_CUDA;
+  }
+  CK(cudaMemcpyAsync(c->d_alpha_materials, ms.data(), ms.size() * sizeof(AlphaMaterial), cudaMemcpyHostToDevice, s));
+  CK(cudaStreamSynchronize(s)); // ms is a stack-owned staging copy
+  c->alpha_material_count = t->material_count;
+  c->alpha_active = any;
   return OXC_OK;
 }
 
@@ -1040,6 +1131,8 @@ int oxc_check_status(OxcContext* c, void* stream, uint32_t* flags_out) {
                 (f & OXC_STATUS_ID_OVERFLOW) ? " a meshlet-instance id overflowed the vis-buffer id bits" : "",
                 (f & OXC_STATUS_CLIP_OVERFLOW) ? " the clip queue overflowed (run oxc_raster_visbuffer_clip_pass)" : "",
                 (f & OXC_STATUS_PEER_TIMEOUT) ? " a peer GPU did not signal its Hi-Z exchange in time" : "");
+  if (f & OXC_STATUS_BAD_MATERIAL)
+    return fail(OXC_E_INVALID, "device status 0x%x: a MeshInstance::material_index lies outside the table of oxc_set_materials (rasterised as opaque)", f);
   return fail(OXC_E_INVALID, "device status 0x%x: malformed geometry (micro index >= vertex_count or vertex index >= Mesh::vertex_count); such triangles are skipped", f);
 }
 

@@ -1239,6 +1239,132 @@ def test_clip_pass_parity(capi, orc):
             ctx.close()
 
 
+def _alpha_tables(capi, orc, ctx):
+    """four materials (opaque; RGBA8 checker, linear + repeat; R8 noise, nearest + clamp, albedo alpha 0.8; R8 gradient, linear +
+    mirrored / repeat) as an oracle table (host texels) and set on the context (device texels)"""
+    from tests.test_oracle_alpha import checker, material
+
+    rng = np.random.default_rng(5)
+    images = [(checker(16, 2), abi.IMAGE_RGBA8_UNORM), (rng.integers(0, 256, (8, 8), dtype=np.uint8), abi.IMAGE_R8_UNORM),
+              (np.ascontiguousarray(np.tile(np.linspace(0, 255, 16).astype(np.uint8), (16, 1))), abi.IMAGE_R8_UNORM)]
+    mats = np.array([material(), material(image=0, cutoff=0.5), material(image=1, cutoff=0.3, albedo_a=0.8, sampler=1),
+                     material(image=2, cutoff=0.5, sampler=2)], dtype=abi.MATERIAL_DT)
+    smp = np.array([(0, 0, 0), (abi.FILTER_NEAREST, abi.ADDRESS_CLAMP_TO_EDGE, abi.ADDRESS_CLAMP_TO_EDGE),
+                    (abi.FILTER_LINEAR, abi.ADDRESS_MIRRORED_REPEAT, abi.ADDRESS_REPEAT)], dtype=abi.SAMPLER_DT)
+    dev = []
+    for tex, fmt in images:
+        d = ctx.alloc(tex.size)
+        ctx.upload(d, tex)
+        dev.append((d, tex.shape[1], tex.shape[0], fmt))
+    ctx.set_materials(mats, dev, smp)
+    return orc.MaterialTable(mats, images, smp), [d for d, _, _, _ in dev]
+
+
+def test_alpha_discard_parity(capi, orc):
+    """visbuffer_encode.slang:54-66: with a material table set, the raster discards fragments whose albedo alpha is below the
+    cutoff.  Two-pass frames (so the holes reach the Hi-Z and the late cull) on a scene whose mesh instances cycle through four
+    materials: survivors, mask, packed image and triangle count equal the oracle's frame bit for bit; switching the table off
+    again gives the plain frame; a material index outside the table raises OXC_STATUS_BAD_MATERIAL."""
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    sc.mesh_instances["material_index"] = np.arange(sc.mesh_instance_count) % 4
+    hs = orc.HostScene(sc)
+    ctx = make_ctx(capi, sc)
+    tab, texels = _alpha_tables(capi, orc, ctx)
+    w, h = sc.width, sc.height
+    vis_dev = ctx.alloc(w * h * 8)
+    occ_dev = ctx.alloc(w * h * 4)
+    ctx.upload(occ_dev, sc.occluder_depth)
+    mask_ref = np.zeros(ctx.out.visibility_mask_words, dtype=np.uint32)
+    mask_plain = np.zeros_like(mask_ref)
+    differs = False
+    for f in range(3):
+        cam = sc.camera(2.0 * f)
+        ref = orc.frame(hs, cam, w, h, mask_ref, sc.occluder_depth, materials=tab)
+        plain = orc.frame(orc.HostScene(sc), cam, w, h, mask_plain, sc.occluder_depth)
+        differs = differs or not np.array_equal(ref["vis64"], plain["vis64"])
+        got = _frame_gpu(capi, ctx, sc, cam, occ_dev, vis_dev)
+        assert (got["early"], got["late"]) == (ref["early"], ref["late"]), f"frame {f}"
+        np.testing.assert_array_equal(got["mask"], mask_ref)
+        e, l = ref["early"], ref["late"]
+        np.testing.assert_array_equal(np.sort(got["visible"][:e]), np.sort(ref["visible"][:e]))
+        np.testing.assert_array_equal(np.sort(got["visible"][e : e + l]), np.sort(ref["visible"][e : e + l]))
+        np.testing.assert_array_equal(got["vis64"], ref["vis64"])
+        assert got["ntri"] == ref["ntri_early"] + ref["ntri_late"]
+        assert ctx.check_status() == 0
+    assert differs  # the table does discard fragments in this scene
+    # table off: the plain encode again (mask continues from the alpha frames on both sides)
+    ctx.set_materials(None)
+    cam = sc.camera(6.0)
+    ref = orc.frame(hs, cam, w, h, mask_ref, sc.occluder_depth)
+    got = _frame_gpu(capi, ctx, sc, cam, occ_dev, vis_dev)
+    np.testing.assert_array_equal(got["vis64"], ref["vis64"])
+    np.testing.assert_array_equal(got["mask"], mask_ref)
+    # a material index outside the table: rasterised as opaque, flagged
+    from tests.test_oracle_alpha import material
+
+    ctx.set_materials(np.array([material()], dtype=abi.MATERIAL_DT))  # 1 material, no image: the test stays off, nothing to flag
+    _frame_gpu(capi, ctx, sc, cam, occ_dev, vis_dev)
+    assert ctx.check_status() == 0
+    tab1, tex1 = _alpha_tables(capi, orc, ctx)
+    sc2 = synth.make_scene(config_index=2, **SCENES["small"])
+    sc2.mesh_instances["material_index"] = np.where(np.arange(sc2.mesh_instance_count) % 5 == 0, 9, 1)
+    ctx.set_scene(sc2)
+    ctx.reset_visibility_mask()
+    got = _frame_gpu(capi, ctx, sc2, cam, occ_dev, vis_dev)
+    assert ctx.status_flags() & abi.STATUS_BAD_MATERIAL
+    with pytest.raises(capi.OxcError):
+        ctx.check_status()
+    # ... and the image is the oracle's, which treats such instances as opaque too
+    ref = orc.frame(orc.HostScene(sc2), cam, w, h, np.zeros_like(mask_ref), sc2.occluder_depth, materials=tab1)
+    np.testing.assert_array_equal(got["vis64"], ref["vis64"])
+    for d in texels + tex1 + [vis_dev, occ_dev]:
+        ctx.free(d)
+    ctx.close()
+
+
+def test_alpha_discard_clip_path_parity(capi, orc):
+    """a textured ground plane through the camera, alpha tested: every triangle on screen takes the clip path (uv carried
+    through the cuts) and the coarse version's two triangles are far above the whole-warp threshold"""
+    from tests.test_oracle_alpha import checker, material, textured_ground
+
+    for cells in (1, 24):
+        sc = textured_ground(cells, width=640, height=360)
+        sc.mesh_instances["material_index"] = 0
+        hs = orc.HostScene(sc)
+        cam = sc.camera()
+        w, h = sc.width, sc.height
+        tex = checker(4, 1, rgba=False)
+        mats = np.array([material(image=0, cutoff=0.5)], dtype=abi.MATERIAL_DT)
+        tab = orc.MaterialTable(mats, [(tex, abi.IMAGE_R8_UNORM)])
+        mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+        visible, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+        visible = visible[: int(cmd["x"][0])]
+        ref = orc.clear_visbuffer(w, h)
+        ntri, nalpha = orc.raster_alpha(hs, mi, visible, 0, len(visible), cam, ref, tab)
+        assert nalpha == ntri > 0
+        plain = orc.clear_visbuffer(w, h)
+        orc.raster_clip(hs, mi, visible, 0, len(visible), cam, plain)
+        assert 0 < ((ref & 0xFFFFFFFF) != 0xFFFFFFFF).sum() < ((plain & 0xFFFFFFFF) != 0xFFFFFFFF).sum()
+        ctx = make_ctx(capi, sc)
+        tex_dev = ctx.alloc(tex.size)
+        ctx.upload(tex_dev, tex)
+        ctx.set_materials(mats, [(tex_dev, 4, 4, abi.IMAGE_R8_UNORM)])
+        vis_dev = ctx.alloc(w * h * 8)
+        ctx.clear_visbuffer(vis_dev, w, h)
+        ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+        ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
+        ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+        got = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
+        np.testing.assert_array_equal(got, ref)
+        assert ctx.raster_triangle_count() == ntri
+        assert ctx.check_status() == 0
+        with pytest.raises(capi.OxcError):  # a material that names an image outside the table is refused
+            ctx.set_materials(np.array([material(image=3)], dtype=abi.MATERIAL_DT), [(tex_dev, 4, 4, abi.IMAGE_R8_UNORM)])
+        ctx.free(vis_dev)
+        ctx.free(tex_dev)
+        ctx.close()
+
+
 def test_plain_c_host_runs(capi, tmp_path):
     """examples/host_min.c on the GPU: the quad covers exactly a quarter of the 64x48 image"""
     from tests.test_abi_cpu import _build_host_min

@@ -1,0 +1,251 @@
+"""Specification tests of the alpha-tested discard (visbuffer_encode.slang:54-66; spec: oracle/oxc_oracle.c above raster_triangle).
+Oracle only: hand-computed samples, an independent binary64 perspective-correct interpolation, and pass-level properties."""
+import numpy as np
+import pytest
+
+from oxylus_b200 import abi, capi, synth
+
+
+def half(x):
+    return int(np.float16(x).view(np.uint16))
+
+
+def material(image=None, cutoff=0.5, albedo_a=1.0, sampler=0, flags=None):
+    m = np.zeros(1, dtype=abi.MATERIAL_DT)
+    m["albedo_color"][0] = [half(1.0), half(1.0), half(1.0), half(albedo_a)]
+    m["alpha_cutoff"] = half(cutoff)
+    m["sampler_index"] = sampler
+    if image is not None:
+        m["flags"] = abi.MATERIAL_HAS_ALBEDO_IMAGE | abi.MATERIAL_ALPHA_MASK
+        m["albedo_image_index"] = image
+    if flags is not None:
+        m["flags"] = flags
+    return m[0]
+
+
+def checker(n, cell, lo=0, hi=255, rgba=True):
+    y, x = np.mgrid[0:n, 0:n]
+    a = np.where(((x // cell) + (y // cell)) % 2 == 0, hi, lo).astype(np.uint8)
+    if not rgba:
+        return a
+    t = np.full((n, n, 4), 200, dtype=np.uint8)
+    t[:, :, 3] = a
+    return t
+
+
+def textured_ground(cells, width=320, height=180):
+    """tests/test_oracle_clip.py's ground plane (crosses the near and both side planes) with uv = (x, z) / 10"""
+    xs = np.linspace(-50.0, 50.0, cells + 1)
+    zs = np.linspace(10.0, -100.0, cells + 1)
+    gx, gz = np.meshgrid(xs, zs, indexing="ij")
+    pos = np.stack([gx, np.full_like(gx, -1.0), gz], axis=2).reshape(-1, 3).astype(np.float32)
+    uv = np.stack([gx / 10.0, gz / 10.0], axis=2).reshape(-1, 2).astype(np.float32)
+    i, j = np.meshgrid(np.arange(cells), np.arange(cells), indexing="ij")
+    a, b = i * (cells + 1) + j, (i + 1) * (cells + 1) + j
+    c, d = i * (cells + 1) + j + 1, (i + 1) * (cells + 1) + j + 1
+    tris = np.stack([a, d, c, a, b, d], axis=2).reshape(-1, 3).astype(np.uint32)
+    built = [capi.BuiltMesh(pos, [(tris.reshape(-1), 0.0)], texcoords=uv)]
+    xf = np.eye(4, dtype=np.float32).reshape(1, 16)
+    return capi.assemble_scene(built, np.arange(1), xf, width, height)
+
+
+def test_alpha_sample_hand_cases(orc):
+    img = np.array([[0, 255], [255, 0]], dtype=np.uint8)  # R8, texel (x, y) = img[y, x]
+    s = orc.alpha_sample
+    # texel centres (linear filter returns the texel itself)
+    assert s(img, abi.IMAGE_R8_UNORM, 0.25, 0.25) == 0.0
+    assert s(img, abi.IMAGE_R8_UNORM, 0.75, 0.25) == 1.0
+    assert s(img, abi.IMAGE_R8_UNORM, 0.25, 0.75) == 1.0
+    # half way between two texel centres: 0.5; the centre of the image: mean of all four
+    assert s(img, abi.IMAGE_R8_UNORM, 0.5, 0.25) == 0.5
+    assert s(img, abi.IMAGE_R8_UNORM, 0.5, 0.5) == 0.5
+    # repeat: u = 0 lies half way between texel 1 (wrapped) and texel 0
+    assert s(img, abi.IMAGE_R8_UNORM, 0.0, 0.25) == 0.5
+    assert s(img, abi.IMAGE_R8_UNORM, 1.25, -0.75) == s(img, abi.IMAGE_R8_UNORM, 0.25, 0.25)
+    # clamp to edge: left of the first texel centre is the first texel
+    clamp = (abi.FILTER_LINEAR, abi.ADDRESS_CLAMP_TO_EDGE, abi.ADDRESS_CLAMP_TO_EDGE)
+    assert s(img, abi.IMAGE_R8_UNORM, 0.0, 0.25, clamp) == 0.0
+    assert s(img, abi.IMAGE_R8_UNORM, -3.0, 0.25, clamp) == 0.0
+    assert s(img, abi.IMAGE_R8_UNORM, 7.0, 0.25, clamp) == 1.0
+    # mirrored repeat: [0,1) forward, [1,2) backward
+    mirror = (abi.FILTER_NEAREST, abi.ADDRESS_MIRRORED_REPEAT, abi.ADDRESS_MIRRORED_REPEAT)
+    assert s(img, abi.IMAGE_R8_UNORM, 0.25, 0.25, mirror) == 0.0
+    assert s(img, abi.IMAGE_R8_UNORM, 1.25, 0.25, mirror) == 1.0   # texel 1 mirrored
+    assert s(img, abi.IMAGE_R8_UNORM, 1.75, 0.25, mirror) == 0.0
+    assert s(img, abi.IMAGE_R8_UNORM, -0.25, 0.25, mirror) == 0.0  # texel -1 -> 0
+    # nearest, repeat; RGBA8 reads byte 3
+    near = (abi.FILTER_NEAREST, abi.ADDRESS_REPEAT, abi.ADDRESS_REPEAT)
+    assert s(img, abi.IMAGE_R8_UNORM, 0.49, 0.0, near) == 0.0 and s(img, abi.IMAGE_R8_UNORM, 0.51, 0.0, near) == 1.0
+    rgba = np.zeros((1, 1, 4), dtype=np.uint8)
+    rgba[0, 0] = [9, 9, 9, 51]
+    assert s(rgba, abi.IMAGE_RGBA8_UNORM, 0.3, 0.9) == np.float32(51) / np.float32(255)
+    # special values: NaN / Inf coordinates are defined (texel 0 / saturated index), never a crash
+    for u in (np.nan, np.inf, -np.inf, 1e30, -1e30):
+        v = s(img, abi.IMAGE_R8_UNORM, u, 0.25)
+        assert np.isnan(v) or 0.0 <= v <= 1.0
+        assert 0.0 <= s(img, abi.IMAGE_R8_UNORM, u, 0.25, near) <= 1.0
+
+
+def _front_facing(clip):
+    """orient the triangle so that the raster keeps it (negative clip-space determinant, cull.slang:169-171)"""
+    m = np.stack([clip[:, 0], clip[:, 1], clip[:, 3]], axis=0).astype(np.float64)
+    return np.linalg.det(m) < 0
+
+
+def test_alpha_matches_binary64_perspective_interpolation(orc):
+    """the kept / discarded pattern of single triangles with very different w per vertex equals the textbook
+    perspective-correct interpolation (homogeneous barycentrics solved in binary64 from the UNSNAPPED clip coordinates) of a
+    per-texel checkerboard — away from texel boundaries, where f32 rounding and the 1/256-pixel snapping cannot matter"""
+    rng = np.random.default_rng(11)
+    W, H = 96, 64
+    tex = checker(8, 1, rgba=False)  # 8x8 texels, every texel its own cell; nearest filter => alpha = cell parity
+    near = np.array([(abi.FILTER_NEAREST, abi.ADDRESS_REPEAT, abi.ADDRESS_REPEAT)], dtype=abi.SAMPLER_DT)
+    tab = orc.MaterialTable([material(image=0, cutoff=0.5)], [(tex, abi.IMAGE_R8_UNORM)], near)
+    plain_tab = orc.MaterialTable([material()])
+    checked = kept = dropped = 0
+    for _ in range(200):
+        w = rng.uniform(0.5, 20.0, 3)
+        ndc = rng.uniform(-0.9, 0.9, (3, 2))
+        clip = np.zeros((3, 4), dtype=np.float32)
+        clip[:, 0:2] = (ndc * w[:, None]).astype(np.float32)
+        clip[:, 2] = (0.5 * w).astype(np.float32)
+        clip[:, 3] = w.astype(np.float32)
+        uv = rng.uniform(-1.0, 2.0, (3, 2)).astype(np.float32)
+        if not _front_facing(clip):
+            clip[[1, 2]] = clip[[2, 1]]
+            uv[[1, 2]] = uv[[2, 1]]
+        cover = orc.clear_visbuffer(W, H)
+        assert orc.raster_triangle_alpha(plain_tab, 0, clip, uv, 7, cover) == 0
+        img = orc.clear_visbuffer(W, H)
+        assert orc.raster_triangle_alpha(tab, 0, clip, uv, 7, img) == 0
+        covered = (cover & 0xFFFFFFFF) == 7
+        got = (img & 0xFFFFFFFF) == 7
+        assert not (got & ~covered).any()
+        c64, uv64 = clip.astype(np.float64), uv.astype(np.float64)
+        M = np.stack([c64[:, 0], c64[:, 1], c64[:, 3]], axis=0)
+        for py, px in zip(*np.nonzero(covered)):
+            X, Y = (px + 0.5) / W * 2 - 1, (py + 0.5) / H * 2 - 1
+            l = np.linalg.solve(M, np.array([X, Y, 1.0]))
+            l = l / l.sum()
+            if l.min() < 0.05:  # keep to the interior: the snapped triangle differs from the exact one by < 1/256 pixel
+                continue
+            u, v = l @ uv64[:, 0], l @ uv64[:, 1]
+            fu, fv = u * 8 - np.floor(u * 8), v * 8 - np.floor(v * 8)
+            if min(fu, 1 - fu, fv, 1 - fv) < 0.05:
+                continue
+            expect = ((int(np.floor(u * 8)) + int(np.floor(v * 8))) % 2) == 0  # alpha 1 on even cells
+            assert bool(got[py, px]) == expect, (clip, uv, px, py)
+            checked += 1
+            kept += expect
+            dropped += not expect
+    assert checked > 3000 and kept > 1000 and dropped > 1000
+
+
+def test_alpha_cutoff_and_flags(orc):
+    W, H = 16, 16
+    clip = np.array([[-1, -1, 0.5, 1], [-1, 3, 0.5, 1], [3, -1, 0.5, 1]], dtype=np.float32)  # covers the screen
+    if not _front_facing(clip):
+        clip[[1, 2]] = clip[[2, 1]]
+    uv = np.array([[0.5, 0.5], [0.5, 0.5], [0.5, 0.5]], dtype=np.float32)                    # constant uv
+    tex = np.full((4, 4), 128, dtype=np.uint8)                                              # alpha 128/255 = 0.50196
+    img = [(tex, abi.IMAGE_R8_UNORM)]
+
+    def keep(mat, images=img):
+        vis = orc.clear_visbuffer(W, H)
+        orc.raster_triangle_alpha(orc.MaterialTable([mat], images), 0, clip, uv, 3, vis)
+        n = int(((vis & 0xFFFFFFFF) == 3).sum())
+        assert n in (0, W * H)
+        return n == W * H
+
+    assert keep(material(image=0, cutoff=0.5))           # 0.50196 >= 0.5
+    assert not keep(material(image=0, cutoff=0.51))
+    assert not keep(material(image=0, cutoff=0.5, albedo_a=0.9))   # albedo_color.a scales the sample (scene.slang:116-121)
+    assert keep(material(image=0, cutoff=0.0))           # clamp(0, 0.001, 1): 0.50196 >= 0.001
+    assert not keep(material(image=0, cutoff=5.0))       # clamp(5, 0.001, 1) = 1 > 0.50196
+    zero = [(np.zeros((4, 4), dtype=np.uint8), abi.IMAGE_R8_UNORM)]
+    assert not keep(material(image=0, cutoff=0.0), zero)  # 0 < 0.001
+    # no HasAlbedoImage flag: never tested, whatever the cutoff (visbuffer_encode.slang:55)
+    assert keep(material(image=0, cutoff=5.0, flags=abi.MATERIAL_ALPHA_MASK))
+    # NaN cutoff keeps the fragment (the comparison is false)
+    m = material(image=0)
+    m["alpha_cutoff"] = 0x7E00
+    assert keep(m)
+
+
+@pytest.fixture(scope="module")
+def scene_and_tables(orc):
+    sc = synth.make_scene(4000, config_index=2, width=480, height=270, n_unique_meshes=12)
+    sc.mesh_instances["material_index"] = np.arange(sc.mesh_instance_count) % 4
+    return sc
+
+
+def _survivors(orc, sc):
+    hs = orc.HostScene(sc)
+    cam = sc.camera()
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    visible, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+    return hs, cam, mi, visible[: int(cmd["x"][0])]
+
+
+def test_alpha_pass_properties(orc, scene_and_tables):
+    sc = scene_and_tables
+    hs, cam, mi, visible = _survivors(orc, sc)
+    w, h = sc.width, sc.height
+    plain = orc.clear_visbuffer(w, h)
+    ntri_plain, _ = orc.raster_clip(hs, mi, visible, 0, len(visible), cam, plain)
+    mats = [material(), material(image=0, cutoff=0.5), material(image=1, cutoff=0.3, albedo_a=0.8, sampler=1), material(image=2, cutoff=0.5, sampler=2)]
+    smp = np.array([(0, 0, 0), (abi.FILTER_NEAREST, abi.ADDRESS_CLAMP_TO_EDGE, abi.ADDRESS_CLAMP_TO_EDGE),
+                    (abi.FILTER_LINEAR, abi.ADDRESS_MIRRORED_REPEAT, abi.ADDRESS_REPEAT)], dtype=abi.SAMPLER_DT)
+
+    def run(images):
+        img = orc.clear_visbuffer(w, h)
+        ntri, nalpha = orc.raster_alpha(hs, mi, visible, 0, len(visible), cam, img, orc.MaterialTable(mats, images, smp))
+        return img, ntri, nalpha
+
+    opaque = [(np.full((4, 4, 4), 255, np.uint8), abi.IMAGE_RGBA8_UNORM), (np.full((4, 4), 255, np.uint8), abi.IMAGE_R8_UNORM),
+              (np.full((2, 2), 255, np.uint8), abi.IMAGE_R8_UNORM)]
+    img, ntri, nalpha = run(opaque)
+    assert ntri == ntri_plain and 0 < nalpha < ntri
+    np.testing.assert_array_equal(img, plain)  # alpha 1 everywhere: nothing is discarded
+
+    clear = [(np.zeros((4, 4, 4), np.uint8), abi.IMAGE_RGBA8_UNORM), (np.zeros((4, 4), np.uint8), abi.IMAGE_R8_UNORM),
+             (np.zeros((2, 2), np.uint8), abi.IMAGE_R8_UNORM)]
+    img0, ntri0, _ = run(clear)
+    assert ntri0 == ntri_plain  # the triangle count is taken before the per-fragment test
+    ids = (img0 & 0xFFFFFFFF).astype(np.uint32)
+    drawn = ids != 0xFFFFFFFF
+    inst_of = mi["mesh_instance_index"][(ids[drawn] >> 8)]
+    assert (sc.mesh_instances["material_index"][inst_of] == 0).all()  # only the material without an image is left
+    # ... and what is left is exactly the image of the opaque meshlets alone
+    keep = sc.mesh_instances["material_index"][mi["mesh_instance_index"][visible]] == 0
+    only = orc.clear_visbuffer(w, h)
+    orc.raster_clip(hs, mi, np.ascontiguousarray(visible[keep]), 0, int(keep.sum()), cam, only)
+    np.testing.assert_array_equal(img0, only)
+
+    rng = np.random.default_rng(5)
+    mixed = [(checker(16, 2), abi.IMAGE_RGBA8_UNORM), (rng.integers(0, 256, (8, 8), dtype=np.uint8), abi.IMAGE_R8_UNORM),
+             (np.tile(np.linspace(0, 255, 16).astype(np.uint8), (16, 1)), abi.IMAGE_R8_UNORM)]
+    img1, _, _ = run(mixed)
+    assert (img1 <= plain).all() and (img1 >= img0).all()  # discarding fragments can only lower the packed max
+    assert (img1 != plain).any() and (img1 != img0).any()
+
+
+def test_alpha_through_the_clip_path(orc):
+    """a textured ground plane through the camera: every triangle that reaches the screen is clipped; the checker pattern must
+    be the same whether the plane is 1 quad (huge clipped triangles) or 40 x 40 quads (mostly unclipped) — the interpolation
+    runs over the original triangle, not over the clipped pieces"""
+    tab_img = [(checker(4, 1, rgba=False), abi.IMAGE_R8_UNORM)]
+    near = np.array([(abi.FILTER_NEAREST, abi.ADDRESS_REPEAT, abi.ADDRESS_REPEAT)], dtype=abi.SAMPLER_DT)
+    covers = []
+    for cells in (1, 40):
+        sc = textured_ground(cells)
+        sc.mesh_instances["material_index"] = 0
+        hs, cam, mi, visible = _survivors(orc, sc)
+        img = orc.clear_visbuffer(sc.width, sc.height)
+        tab = orc.MaterialTable([material(image=0, cutoff=0.5)], tab_img, near)
+        ntri, nalpha = orc.raster_alpha(hs, mi, visible, 0, len(visible), cam, img, tab)
+        assert nalpha == ntri > 0
+        covers.append((img & 0xFFFFFFFF) != 0xFFFFFFFF)
+    a, b = covers
+    assert 0.15 * a.size < a.sum() < 0.35 * a.size   # half of the lower half of the screen
+    assert (a ^ b).sum() < 0.01 * a.size            # the two tessellations disagree on cell-boundary pixels only
