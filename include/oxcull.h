@@ -623,6 +623,9 @@ int oxr_update_transforms(OxrRenderer* r, const OxcTransformWorld* transforms, u
 /* Depth laid down by passes outside this path (terrain, RendererInstance.cpp:862-873): a width x height D32F HOST
  * image copied to the device once and merged into every following frame; NULL removes it. */
 int oxr_set_external_depth(OxrRenderer* r, const float* depth_host);
+/* oxc_set_materials on the renderer's context (alpha-tested discard of the vis-buffer encode, visbuffer_encode.slang:54-66);
+ * NULL switches it off.  Re-captures the frame graphs: the raster's launch sequence changes with it. */
+int oxr_set_materials(OxrRenderer* r, const OxcMaterialTable* table);
 /* RendererInstance::render geometry section.  occluder_depth_host (may be NULL) is a width x height
  * D32F image uploaded THIS frame and merged into the frame depth before the early pass (replaces the image of
  * oxr_set_external_depth).  Outputs may be NULL.  Synchronous. */

@@ -18,13 +18,13 @@ SYMBOLS = [
     "oxc_last_error", "oxc_kernel_launch_count", "oxc_version", "oxc_create", "oxc_destroy", "oxc_set_scene",
     "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_set_shard_auto", "oxc_cull_meshes",
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_cull_triangles_small_primitive", "oxc_clear_visbuffer",
-    "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
+    "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_set_materials", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
     "oxc_decode_visbuffer", "oxc_build_hpb", "oxc_mark_visible_pages",
     "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_bind_camera_buffer", "oxc_load_camera", "oxc_debug_stats_ptr",
     "oxc_mgpu_get_unique_id", "oxc_mgpu_init", "oxc_mgpu_init_with_comm", "oxc_mgpu_shutdown", "oxc_mgpu_info", "oxc_mgpu_exchange_hiz",
     "oxc_mgpu_exchange_frame", "oxc_mgpu_stage_survivors", "oxc_mgpu_set_survivor_capacity", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free", "oxb_simplify",
-    "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_render", "oxr_submit", "oxr_wait",
+    "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_set_materials", "oxr_render", "oxr_submit", "oxr_wait",
 ]
 
 
@@ -120,6 +120,7 @@ def load(build_if_missing=True):
     lib.oxr_update.argtypes = [vp, C.POINTER(abi.SceneDesc)]
     lib.oxr_update_transforms.argtypes = [vp, vp, u32, u32]
     lib.oxr_set_external_depth.argtypes = [vp, vp]
+    lib.oxr_set_materials.argtypes = [vp, C.POINTER(abi.MaterialTable)]
     lib.oxr_submit.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(C.c_int)]
     lib.oxr_wait.argtypes = [vp, i32, C.POINTER(abi.FrameResult)]
     lib.oxr_render.argtypes = [vp, vp, vp, vp, vp, vp, u32, C.POINTER(abi.FrameResult)]
@@ -230,6 +231,23 @@ def assemble_scene(built, mesh_of_instance, transforms, width, height, transform
     return synth.Scene(meshes, inst, xf, blob, int(lod0.sum()), width, height, seed)
 
 
+def material_table(materials, images=None, samplers=None):
+    """(abi.MaterialTable or None, the arrays it points to) from an abi.MATERIAL_DT array, a list of (device pointer, width,
+    height, format) and an optional abi.SAMPLER_DT array"""
+    if materials is None or len(materials) == 0:
+        return None, ()
+    mats = np.ascontiguousarray(materials, dtype=abi.MATERIAL_DT)
+    imgs = np.zeros(len(images or []), dtype=abi.ALPHA_IMAGE_DT)
+    for i, (ptr, w, h, fmt) in enumerate(images or []):
+        imgs[i] = (int(ptr), w, h, fmt, 0)
+    smp = None if samplers is None else np.ascontiguousarray(samplers, dtype=abi.SAMPLER_DT)
+    t = abi.MaterialTable()
+    t.materials, t.material_count = mats.ctypes.data, len(mats)
+    t.images, t.image_count = (imgs.ctypes.data if len(imgs) else None), len(imgs)
+    t.samplers, t.sampler_count = (None if smp is None else smp.ctypes.data), (0 if smp is None else len(smp))
+    return t, (mats, imgs, smp)
+
+
 class Context:
     """OxcContext wrapper.  `stream` is a raw cudaStream_t handle (int; 0 = default stream)."""
 
@@ -333,19 +351,8 @@ class Context:
     def set_materials(self, materials, images=None, samplers=None):
         """oxc_set_materials: `materials` abi.MATERIAL_DT array (None switches the alpha test off); `images` a list of
         (device pointer, width, height, format); `samplers` an abi.SAMPLER_DT array or None (linear + repeat)"""
-        if materials is None or len(materials) == 0:
-            _check(self.lib.oxc_set_materials(self.h, None, self.stream), "oxc_set_materials")
-            return
-        mats = np.ascontiguousarray(materials, dtype=abi.MATERIAL_DT)
-        imgs = np.zeros(len(images or []), dtype=abi.ALPHA_IMAGE_DT)
-        for i, (ptr, w, h, fmt) in enumerate(images or []):
-            imgs[i] = (int(ptr), w, h, fmt, 0)
-        smp = None if samplers is None else np.ascontiguousarray(samplers, dtype=abi.SAMPLER_DT)
-        t = abi.MaterialTable()
-        t.materials, t.material_count = mats.ctypes.data, len(mats)
-        t.images, t.image_count = (imgs.ctypes.data if len(imgs) else None), len(imgs)
-        t.samplers, t.sampler_count = (None if smp is None else smp.ctypes.data), (0 if smp is None else len(smp))
-        _check(self.lib.oxc_set_materials(self.h, C.byref(t), self.stream), "oxc_set_materials")
+        t, keep = material_table(materials, images, samplers)
+        _check(self.lib.oxc_set_materials(self.h, None if t is None else C.byref(t), self.stream), "oxc_set_materials")
 
     def raster_visbuffer_clip_pass(self, cam, flags, w, h, vis_dev):
         _check(self.lib.oxc_raster_visbuffer_clip_pass(self.h, _ptr(cam), flags, w, h, _ptr(vis_dev), self.stream),
@@ -554,6 +561,11 @@ class Renderer:
     def update_transforms(self, transforms, first=0):
         t = transforms if isinstance(transforms, np.ndarray) and transforms.flags.c_contiguous else np.ascontiguousarray(transforms)
         _check(self.lib.oxr_update_transforms(self.h, _ptr(t), first, len(t)), "oxr_update_transforms")
+
+    def set_materials(self, materials, images=None, samplers=None):
+        """oxr_set_materials (see Context.set_materials)"""
+        t, keep = material_table(materials, images, samplers)
+        _check(self.lib.oxr_set_materials(self.h, None if t is None else C.byref(t)), "oxr_set_materials")
 
     def set_external_depth(self, depth):
         d = None if depth is None else np.ascontiguousarray(depth, dtype=np.float32)

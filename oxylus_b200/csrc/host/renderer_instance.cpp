@@ -126,6 +126,15 @@ auto RendererInstance::update_transforms(const OxcTransformWorld* transforms, ui
   return fail(oxc_update_transforms(ctx_, transforms, first, count, stream_));
 }
 
+// the reference uploads its material table with the scene (RendererInstance.cpp:1333-1788); the vis-buffer encode reads it for
+// the alpha-tested discard (visbuffer_encode.slang:54-66)
+auto RendererInstance::set_materials(const OxcMaterialTable* table) -> int {
+  if (!ctx_) return OXC_E_STATE;
+  error_.clear();
+  drop_graphs(); // the raster's launch sequence depends on whether a table is set
+  return fail(oxc_set_materials(ctx_, table, stream_));
+}
+
 auto RendererInstance::set_external_depth(const float* depth_host) -> int {
   if (!ctx_) return OXC_E_STATE;
   has_external_depth_ = depth_host != nullptr;
@@ -518,6 +527,11 @@ int oxr_update(OxrRenderer* r, const OxcSceneDesc* scene) {
 int oxr_update_transforms(OxrRenderer* r, const OxcTransformWorld* transforms, uint32_t first, uint32_t count) {
   if (!r || !transforms) return OXC_E_INVALID;
   return r->impl.update_transforms(transforms, first, count);
+}
+
+int oxr_set_materials(OxrRenderer* r, const OxcMaterialTable* table) {
+  if (!r) return OXC_E_INVALID;
+  return r->impl.set_materials(table);
 }
 
 int oxr_set_external_depth(OxrRenderer* r, const float* depth_host) {

@@ -58,6 +58,7 @@ public:
   // dirty-range transform upload (RendererInstance.cpp:16-109,1590-1599); async on the renderer's stream
   auto update_transforms(const OxcTransformWorld* transforms, uint32_t first, uint32_t count) -> int;
   // depth laid down by passes outside this path (terrain): kept on the device until replaced; nullptr clears it
+  auto set_materials(const OxcMaterialTable* table) -> int; // nullptr: plain encode
   auto set_external_depth(const float* depth_host) -> int;
   auto cull_geometry(CullGeometryContext& context) -> int;
   auto generate_hiz(MainGeometryContext& context) -> int;

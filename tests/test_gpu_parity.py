@@ -1322,6 +1322,55 @@ def test_alpha_discard_parity(capi, orc):
     ctx.close()
 
 
+def test_renderer_alpha_discard_pipelined(capi, orc):
+    """oxr_set_materials on the host mirror: the pipelined frames (oxr_submit / oxr_wait replay the frame from CUDA graphs) are
+    re-captured with the alpha kernels in them when the table is set and again when it is removed — every frame equals the
+    oracle's frame with / without the table"""
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    sc.mesh_instances["material_index"] = np.arange(sc.mesh_instance_count) % 4
+    hs = orc.HostScene(sc)
+    r = capi.Renderer(0, sc)
+    r.set_external_depth(sc.occluder_depth)
+    tab, texels = _alpha_tables(capi, orc, r.ctx)  # sets the table on the context; the renderer call below is what drops the graphs
+    r.set_materials(None)
+    mask_ref = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    bufs = [dict(vis32=np.zeros((sc.height, sc.width), np.uint32), depth=np.zeros((sc.height, sc.width), np.float32),
+                 idx=np.zeros(sc.max_meshlet_instance_count, np.uint32)) for _ in range(2)]
+    images = [(d, t.shape[1], t.shape[0], fmt) for d, (t, fmt) in zip(texels, zip(tab.texels, [int(f) for f in tab.images["format"]]))]
+    with_table = [False, False, True, True, True, False, False]
+    refs, prev = [], None
+
+    def check(frame_index, res):
+        ref = refs[frame_index]
+        b = bufs[frame_index % 2]
+        assert (res["total"], res["early"], res["late"]) == ref[0], frame_index
+        np.testing.assert_array_equal(b["vis32"], ref[1])
+        np.testing.assert_array_equal(b["depth"].view(np.uint32), ref[2].view(np.uint32))
+        np.testing.assert_array_equal(np.sort(b["idx"][: res["early"] + res["late"]]), ref[3])
+
+    for f, on in enumerate(with_table):
+        cam = sc.camera(2.0 * f)
+        if f and on != with_table[f - 1]:
+            if prev is not None:  # the table belongs to the frames in flight: drain before changing it
+                check(f - 1, r.wait(prev))
+                prev = None
+            r.set_materials(tab.materials if on else None, images, tab.samplers)
+        ref = orc.frame(hs, cam, sc.width, sc.height, mask_ref, sc.occluder_depth, materials=tab if on else None)
+        v32, d = orc.resolve(ref["vis64"])
+        n = ref["early"] + ref["late"]
+        refs.append(((int(ref["visibility"]["total"][0]), ref["early"], ref["late"]), v32, d, np.sort(ref["visible"][:n])))
+        t = r.submit(cam, bufs[f % 2])
+        if prev is not None:
+            check(f - 1, r.wait(prev))
+        prev = t
+    check(len(with_table) - 1, r.wait(prev))
+    np.testing.assert_array_equal(r.ctx.mask(), mask_ref)
+    assert not np.array_equal(refs[1][1], refs[2][1])
+    for d in texels:
+        r.ctx.free(d)
+    r.close()
+
+
 def test_alpha_discard_clip_path_parity(capi, orc):
     """a textured ground plane through the camera, alpha tested: every triangle on screen takes the clip path (uv carried
     through the cuts) and the coarse version's two triangles are far above the whole-warp threshold"""
