@@ -6,7 +6,10 @@ exchange writes into the other ranks' buffers ("peer memory" = shared memory her
 exchange goes through the communicator.  Compared with a single context over the whole scene: merged vis buffer, gathered
 survivor ids (as a set), counters, every Hi-Z level on every rank, each rank's slice of the persistent mask.
 
-    python tests/emulated_mgpu_check.py WORLD [MESHLETS]"""
+    python tests/emulated_mgpu_check.py WORLD [MESHLETS] [alpha]
+
+`alpha`: the mesh instances cycle through four materials and every context gets the material table (oxc_set_materials), so the
+shards' rasters discard fragments (visbuffer_encode.slang:54-66): the holes travel through the Hi-Z exchange and the merge."""
 import json
 import os
 import sys
@@ -35,8 +38,28 @@ def partition_mesh_instances(counts, world):  # == oxylus_b200.dist.partition_me
     return [(bounds[r], bounds[r + 1] - bounds[r]) for r in range(world)]
 
 
+def set_alpha_table(ctx):
+    """four materials: opaque, RGBA8 checker (linear, repeat), R8 noise (nearest, clamp, albedo alpha 0.8), R8 gradient (mirror)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_alpha import checker, material
+
+    rng = np.random.default_rng(5)
+    images = [(checker(16, 2), abi.IMAGE_RGBA8_UNORM), (rng.integers(0, 256, (8, 8), dtype=np.uint8), abi.IMAGE_R8_UNORM),
+              (np.ascontiguousarray(np.tile(np.linspace(0, 255, 16).astype(np.uint8), (16, 1))), abi.IMAGE_R8_UNORM)]
+    mats = np.array([material(), material(image=0, cutoff=0.5), material(image=1, cutoff=0.3, albedo_a=0.8, sampler=1),
+                     material(image=2, cutoff=0.5, sampler=2)], dtype=abi.MATERIAL_DT)
+    smp = np.array([(0, 0, 0), (abi.FILTER_NEAREST, abi.ADDRESS_CLAMP_TO_EDGE, abi.ADDRESS_CLAMP_TO_EDGE),
+                    (abi.FILTER_LINEAR, abi.ADDRESS_MIRRORED_REPEAT, abi.ADDRESS_REPEAT)], dtype=abi.SAMPLER_DT)
+    dev = []
+    for tex, fmt in images:
+        d = ctx.alloc(tex.size)
+        ctx.upload(d, tex)
+        dev.append((d, tex.shape[1], tex.shape[0], fmt))
+    ctx.set_materials(mats, dev, smp)
+
+
 class Rank:
-    def __init__(self, sc, shard=None, cap=None):
+    def __init__(self, sc, shard=None, cap=None, alpha=False):
         hw, hh = sc.hiz_extent()
         self.sc, self.w, self.h = sc, sc.width, sc.height
         self.ctx = capi.Context(0, max(1, sc.mesh_instance_count), max(1, sc.max_meshlet_instance_count if cap is None else cap), hw, hh,
@@ -44,6 +67,8 @@ class Rank:
         if shard is not None:
             self.ctx.set_shard_auto(shard[0], shard[1])
         self.ctx.set_scene(sc)
+        if alpha:
+            set_alpha_table(self.ctx)
         self.vis = self.ctx.alloc(self.w * self.h * 8)
         self.occ = self.ctx.alloc(self.w * self.h * 4)
         self.ctx.upload(self.occ, sc.occluder_depth)
@@ -73,13 +98,22 @@ class Rank:
 def main():
     world = int(sys.argv[1])
     n = int(sys.argv[2]) if len(sys.argv) > 2 else 12000
+    alpha = len(sys.argv) > 3 and sys.argv[3] == "alpha"
     frames = 3
     sc = synth.make_scene(n, config_index=5, width=320, height=180, n_unique_meshes=24)
+    if alpha:
+        sc.mesh_instances["material_index"] = np.arange(sc.mesh_instance_count) % 4
     lod0 = lod0_counts_of(sc)
     parts = partition_mesh_instances(lod0, world)
     caps = [int(lod0[p[0]: p[0] + p[1]].sum()) for p in parts]
     uid = capi.Context.mgpu_unique_id()
-    ref = Rank(sc)
+    ref = Rank(sc, alpha=alpha)
+    if alpha:  # the table must change the image, or the run would prove nothing about it
+        plain = Rank(sc)
+        plain.frame(sc.camera(0.0))
+        ref.frame(sc.camera(0.0))
+        assert not np.array_equal(plain.image(), ref.image())
+        ref.ctx.reset_visibility_mask()
     want = []
     for f in range(frames):
         ref.frame(sc.camera(2.0 * (f % 2)))
@@ -92,7 +126,7 @@ def main():
 
     def run(rank):
         try:
-            r = Rank(sc, shard=parts[rank], cap=max(caps[rank], 1))
+            r = Rank(sc, shard=parts[rank], cap=max(caps[rank], 1), alpha=alpha)
             info = r.ctx.mgpu_init(rank, world, uid, max(1024, caps[rank]))
             r.mgpu = True
             out = []
@@ -127,7 +161,7 @@ def main():
         t.join()
     ok = not errors and all(r and all(all(f.values()) for f in r["frames"]) for r in results)
     ok = ok and all(r["peer_memory"] for r in results) and sum(r["local_total"] > 0 for r in results) >= min(world, 2)
-    print(json.dumps({"check": "emulated_ranks_equal_single_context", "world": world, "meshlets": n, "pass": bool(ok), "errors": errors, "ranks": results}))
+    print(json.dumps({"check": "emulated_ranks_equal_single_context", "world": world, "meshlets": n, "alpha": alpha, "pass": bool(ok), "errors": errors, "ranks": results}))
     sys.exit(0 if ok else 1)
 
 

@@ -61,6 +61,15 @@ def mutate(base, rng, mode):
                 t[i, 12:15] = (0, 0, 0)
             else:
                 t[i, 12:15] *= np.float32(1e4)
+    if mode in ("texcoords", "all"):  # u16 x 2 halves per vertex (scene.slang:491-497): NaN / Inf / huge / denormal uv reach the alpha
+        for m in sc.meshes:           # test's interpolation, texel addressing and wrap modes (drawn last: earlier draws unchanged)
+            if int(m["texture_coords"]) == 0:
+                continue
+            n = int(m["vertex_count"])
+            v = np.ndarray((n, 2), dtype=np.uint16, buffer=sc.blob.data, offset=int(m["texture_coords"]))
+            for c in range(2):
+                sel = rng.random(n) < 0.03
+                v[sel, c] = SPECIALS[rng.integers(0, len(SPECIALS), int(sel.sum()))]
     return sc
 
 

@@ -56,6 +56,17 @@ def test_multi_gpu_path_on_the_simt_emulator(emulated, world):
     assert verdict["pass"] and verdict["world"] == world and all(r["peer_memory"] for r in verdict["ranks"])
 
 
+def test_multi_gpu_path_with_alpha_discard_on_the_simt_emulator(emulated):
+    """the same check with a material table on every rank (visbuffer_encode.slang:54-66): each shard splits its own survivors by
+    material (global ids minus the rank's id base), the discarded fragments' holes travel through the Hi-Z exchange and the
+    vis-buffer merge — 2 emulated ranks equal one context bit for bit, and the table does change the image"""
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "emulated_mgpu_check.py"), "2", "12000", "alpha"], cwd=ROOT, env=emulated,
+                         capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    verdict = json.loads(res.stdout.strip().splitlines()[-1])
+    assert verdict["pass"] and verdict["alpha"] and verdict["world"] == 2
+
+
 def test_hostile_inputs_on_the_simt_emulator(emulated):
     """tests/emulated_torture_check.py: NaN / Inf / negative / denormal MeshletBounds fields, garbage cones, degenerate and extreme
     transforms — two-pass frames still equal the oracle bit for bit (survivors, mask, packed image)."""
