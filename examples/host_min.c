@@ -1,5 +1,6 @@
 /* host_min.c — the smallest plain-C host of liboxcull.so: one hand-built meshlet (a quad), one frame of the visibility
- * path (cull_meshes -> cull_meshlets -> raster -> resolve), results back on the host.
+ * path (cull_meshes -> cull_meshlets -> raster -> resolve), results back on the host; then the same frame with a material
+ * table whose 2x2 checker image makes the encode pass discard two quadrants of the quad (visbuffer_encode.slang:54-66).
  *
  *   gcc -std=c11 -Iinclude examples/host_min.c -Loxylus_b200 -loxcull -Wl,-rpath,$PWD/oxylus_b200 -o host_min
  *
@@ -54,10 +55,12 @@ int main(void) {
   lod.meshlets = 32; lod.meshlet_bounds = 48; lod.local_triangle_indices = 64; lod.indirect_vertex_indices = 80;
   lod.meshlet_count = 1; lod.meshlet_bounds_count = 1; lod.local_triangle_indices_count = 8; lod.indirect_vertex_indices_count = 4;
   memcpy(blob + 96, &lod, sizeof lod);
+  uint16_t* tc = (uint16_t*)(blob + 160); /* texture coordinates: uv = pos.xy + 0.5, half2 per vertex (scene.slang:491-497) */
+  for (int v = 0; v < 4; v++) { tc[v * 2 + 0] = half_bits(pos[v][0] + 0.5f); tc[v * 2 + 1] = half_bits(pos[v][1] + 0.5f); }
 
   OxcMesh mesh;
   memset(&mesh, 0, sizeof mesh);
-  mesh.vertex_positions = 0; mesh.vertex_count = 4; mesh.lod_count = 1; mesh.lods = 96;
+  mesh.vertex_positions = 0; mesh.vertex_count = 4; mesh.lod_count = 1; mesh.lods = 96; mesh.texture_coords = 160;
   mesh.bounds.aabb_center[2] = 0.5f;
   mesh.bounds.aabb_extent[0] = 1.0f; mesh.bounds.aabb_extent[1] = 1.0f; mesh.bounds.aabb_extent[2] = 0.01f;
   OxcMeshInstance inst;
@@ -93,8 +96,39 @@ int main(void) {
   unsigned covered = 0;
   for (int i = 0; i < W * H; i++) covered += vis32[i] != OXC_VIS_CLEAR;
   printf("%s: %u of %d pixels covered by the quad (expected %d)\n", oxc_version(), covered, W * H, (W / 2) * (H / 2));
+  /* ---- the same frame with an alpha-tested material: 2x2 R8 checker, nearest + clamp, cutoff 0.5 ---- */
+  const uint8_t texels[4] = {255, 0, 0, 255};
+  void* tex_dev = NULL;
+  CHECK(oxc_device_alloc(ctx, sizeof texels, &tex_dev));
+  CHECK(oxc_copy(ctx, tex_dev, texels, sizeof texels, /*host->device*/ 0, NULL));
+  OxcMaterial mat;
+  memset(&mat, 0, sizeof mat);
+  mat.albedo_color[3] = half_bits(1.0f);
+  mat.alpha_cutoff = half_bits(0.5f);
+  mat.flags = OXC_MATERIAL_HAS_ALBEDO_IMAGE | OXC_MATERIAL_ALPHA_MASK;
+  OxcAlphaImage image = {tex_dev, 2, 2, OXC_IMAGE_R8_UNORM, 0};
+  OxcSamplerDesc sampler = {OXC_FILTER_NEAREST, OXC_ADDRESS_CLAMP_TO_EDGE, OXC_ADDRESS_CLAMP_TO_EDGE};
+  OxcMaterialTable table = {&mat, 1, &image, 1, &sampler, 1};
+  CHECK(oxc_set_materials(ctx, &table, NULL)); /* MeshInstance::material_index is 0 */
+  CHECK(oxc_clear_visbuffer(ctx, (uint64_t*)vis64, W, H, NULL));
+  CHECK(oxc_raster_visbuffer(ctx, &cam, OXC_CULL_TEST_ALL, W, H, (uint64_t*)vis64, 0, NULL));
+  CHECK(oxc_resolve_visbuffer(ctx, (const uint64_t*)vis64, W, H, (uint32_t*)vis32_dev, NULL, NULL));
+  CHECK(oxc_copy(ctx, vis32, vis32_dev, sizeof vis32, /*device->host*/ 1, NULL));
+  CHECK(oxc_check_status(ctx, NULL, NULL));
+  unsigned kept = 0, wrong = 0;
+  for (int y = 0; y < H; y++)
+    for (int x = 0; x < W; x++) {
+      const int in_quad = x >= W / 4 && x < 3 * W / 4 && y >= H / 4 && y < 3 * H / 4;
+      const int opaque_texel = (x < W / 2) == (y < H / 2); /* texels (0,0) and (1,1) are 255 */
+      const int drawn = vis32[y * W + x] != OXC_VIS_CLEAR;
+      kept += drawn;
+      wrong += drawn != (in_quad && opaque_texel);
+    }
+  printf("alpha-tested: %u of %u quad pixels kept, %u pixels differ from the checker (expected %d kept, 0 differ)\n", kept, covered, wrong,
+         (W / 2) * (H / 2) / 2);
+  oxc_device_free(ctx, tex_dev);
   oxc_device_free(ctx, vis64);
   oxc_device_free(ctx, vis32_dev);
   oxc_destroy(ctx);
-  return covered == (W / 2) * (H / 2) ? 0 : 2;
+  return covered == (W / 2) * (H / 2) && kept == (W / 2) * (H / 2) / 2 && wrong == 0 ? 0 : 2;
 }

@@ -67,6 +67,18 @@ def test_multi_gpu_path_with_alpha_discard_on_the_simt_emulator(emulated):
     assert verdict["pass"] and verdict["alpha"] and verdict["world"] == 2
 
 
+def test_plain_c_host_on_the_simt_emulator(emulated, tmp_path):
+    """examples/host_min.c (plain C11 against include/oxcull.h) linked with the emulated library: the quad frame and the
+    alpha-tested frame (oxc_set_materials from C) print what the GPU test expects from the real library"""
+    lib = emulated["OXC_LIB_PATH"]
+    exe = str(tmp_path / "host_min_emu")
+    subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "host_min.c"),
+                           "-L", os.path.dirname(lib), "-l:" + os.path.basename(lib), "-Wl,-rpath," + os.path.dirname(lib), "-lm", "-o", exe])
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=emulated)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "768 of 3072 pixels" in res.stdout and "alpha-tested: 384 of 768 quad pixels kept, 0 pixels differ" in res.stdout
+
+
 def test_hostile_inputs_on_the_simt_emulator(emulated):
     """tests/emulated_torture_check.py: NaN / Inf / negative / denormal MeshletBounds fields, garbage cones, degenerate and extreme
     transforms — two-pass frames still equal the oracle bit for bit (survivors, mask, packed image)."""

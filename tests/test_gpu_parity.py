@@ -1415,10 +1415,12 @@ def test_alpha_discard_clip_path_parity(capi, orc):
 
 
 def test_plain_c_host_runs(capi, tmp_path):
-    """examples/host_min.c on the GPU: the quad covers exactly a quarter of the 64x48 image"""
+    """examples/host_min.c on the GPU: the quad covers exactly a quarter of the 64x48 image; with its 2x2 checker material two
+    quadrants of the quad are discarded (the same binary run against the emulated library in the CPU tier prints the same)"""
     from tests.test_abi_cpu import _build_host_min
     import subprocess
 
     res = subprocess.run([_build_host_min(tmp_path)], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "768 of 3072 pixels" in res.stdout
+    assert "alpha-tested: 384 of 768 quad pixels kept, 0 pixels differ" in res.stdout  # oxc_set_materials from plain C
