@@ -107,7 +107,7 @@ int main(void) {
   mat.alpha_cutoff = half_bits(0.5f);
   mat.flags = OXC_MATERIAL_HAS_ALBEDO_IMAGE | OXC_MATERIAL_ALPHA_MASK;
   OxcAlphaImage image = {tex_dev, 2, 2, OXC_IMAGE_R8_UNORM, 0};
-  OxcSamplerDesc sampler = {OXC_FILTER_NEAREST, OXC_ADDRESS_CLAMP_TO_EDGE, OXC_ADDRESS_CLAMP_TO_EDGE};
+  OxcSamplerDesc sampler = {OXC_FILTER_NEAREST, OXC_FILTER_NEAREST, OXC_MIPMAP_NEAREST, OXC_ADDRESS_CLAMP_TO_EDGE, OXC_ADDRESS_CLAMP_TO_EDGE};
   OxcMaterialTable table = {&mat, 1, &image, 1, &sampler, 1};
   CHECK(oxc_set_materials(ctx, &table, NULL)); /* MeshInstance::material_index is 0 */
   CHECK(oxc_clear_visbuffer(ctx, (uint64_t*)vis64, W, H, NULL));

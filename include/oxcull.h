@@ -363,9 +363,13 @@ int oxc_raster_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, uint32_t 
  *   - uv at the pixel centre: perspective-correct barycentrics of the ORIGINAL triangle from its homogeneous edge functions
  *     (rows of adj[x y w]; no per-vertex divide, so clipped triangles — vertices at w <= 0 — interpolate like any other);
  *     vertices of a mesh without texture coordinates have uv = (0, 0) (scene.slang:355-361)
- *   - mip level 0 only (images are single level), filter / address modes from the material's sampler (default: linear,
- *     repeat — Texture.hpp:38-45): texel centre convention x = u * width - 0.5, weights = the f32 fractions (no 8-bit weight
- *     quantisation), alpha = texel / 255
+ *   - filter / address / mipmap modes from the material's sampler (default: linear, linear, repeat — Texture.hpp:38-45; no
+ *     anisotropy, LOD bias or clamp: the reference sets none): texel centre convention x = u * width - 0.5, weights = the f32
+ *     fractions (no 8-bit weight quantisation), alpha = texel / 255
+ *   - images with a mip chain (and samplers whose mag and min filters differ) select the level like SampleGrad with
+ *     ddx / ddy(tex_coord) does (visbuffer_encode.slang:57-60): "fine" quad differences of the interpolated uv, the isotropic
+ *     rule lambda = log2(max(|ddx(uv) * size|, |ddy(uv) * size|)) with the library's canonical log2, lambda > 0 -> min filter,
+ *     else mag filter; trilinear blend of floor(lambda) and the next level, or the nearest level
  *   - NaN alpha or cutoff keeps the fragment (the comparison is false)
  * The raster_triangle_count still counts every triangle that passed the near / backface test (discard is per fragment). */
 typedef struct OxcMaterial { /* SceneGPU.hpp:67-82 / scene.slang:51-66, 56 B */
@@ -389,20 +393,25 @@ typedef struct OxcMaterial { /* SceneGPU.hpp:67-82 / scene.slang:51-66, 56 B */
 
 enum OxcImageFormat { OXC_IMAGE_RGBA8_UNORM = 0 /* alpha = byte 3 (sRGB variants: alpha is linear) */, OXC_IMAGE_R8_UNORM = 1 /* alpha only */ };
 typedef struct OxcAlphaImage {  /* one entry of the engine's bindless image table, the part this pass reads */
-  const void* texels_dev;       /* device pointer, tightly packed rows, level 0 */
-  uint32_t width, height;       /* >= 1 */
+  const void* texels_dev;       /* device pointer to level 0, tightly packed rows; level l (max(1, width >> l) x max(1, height >> l)) */
+  uint32_t width, height;       /*   follows level l - 1 immediately (vkCmdCopyImageToBuffer with consecutive regions).  1..65536 */
   uint32_t format;              /* OxcImageFormat */
-  uint32_t reserved;
+  uint32_t level_count;         /* 0 or 1: level 0 only; at most floor(log2(max(width, height))) + 1 */
 } OxcAlphaImage;
 enum OxcSamplerFilter { OXC_FILTER_LINEAR = 0, OXC_FILTER_NEAREST = 1 };
+enum OxcSamplerMipmapMode { OXC_MIPMAP_LINEAR = 0, OXC_MIPMAP_NEAREST = 1 };
 enum OxcSamplerAddress { OXC_ADDRESS_REPEAT = 0, OXC_ADDRESS_CLAMP_TO_EDGE = 1, OXC_ADDRESS_MIRRORED_REPEAT = 2 };
-typedef struct OxcSamplerDesc { uint32_t filter, address_u, address_v; } OxcSamplerDesc; /* vuk::SamplerCreateInfo subset, AssetManager_GLTF.cpp:75-120 */
+typedef struct OxcSamplerDesc { /* vuk::SamplerCreateInfo subset, AssetManager_GLTF.cpp:75-120 */
+  uint32_t mag_filter, min_filter; /* OxcSamplerFilter */
+  uint32_t mipmap_mode;            /* OxcSamplerMipmapMode */
+  uint32_t address_u, address_v;   /* OxcSamplerAddress */
+} OxcSamplerDesc;
 typedef struct OxcMaterialTable {
   const OxcMaterial* materials;    /* host */
   uint32_t material_count;
   const OxcAlphaImage* images;     /* host array of device images */
   uint32_t image_count;
-  const OxcSamplerDesc* samplers;  /* host; may be NULL: every sampler_index then means linear + repeat */
+  const OxcSamplerDesc* samplers;  /* host; may be NULL: every sampler_index then means linear, linear, repeat */
   uint32_t sampler_count;
 } OxcMaterialTable;
 /* Copies the tables (the image texels stay where they are).  table == NULL or material_count == 0 switches the test off again.

@@ -557,15 +557,27 @@ static inline int edge_bias(int64_t ax, int64_t ay, int64_t bx, int64_t by) {
  *   3. triangles that take the clip path: Sutherland-Hodgman carries (u, v) with the position (clip space is linear in the
  *      attributes): a cut vertex gets uv = uv_I + t * (uv_O - uv_I) with the same t, same operation order; every piece of the
  *      fan is then an ordinary triangle for steps 1-2.
- *   4. level 0 of the image (single-level images; no gradient / LOD), filter and address modes of the material's sampler
- *      (default linear + repeat, Texture.hpp:38-45).  Linear: x = u*width - 0.5, x0 = floor(x), wx = x - x0, texels x0 and
- *      x0 + 1 (wrapped), top = a00 + wx*(a10 - a00), bot likewise, a = top + wy*(bot - top); alpha of a texel = byte / 255.
- *      Nearest: texel floor(u*width).  float -> int saturates, NaN -> 0.
+ *   4. the texel fetch: filter / address / mipmap modes of the material's sampler (default linear, linear, repeat — Texture.hpp:
+ *      38-45; no anisotropy, no LOD bias or clamp: the reference sets none).  One level — linear: x = u*width - 0.5, x0 = floor(x),
+ *      wx = x - x0, texels x0 and x0 + 1 (wrapped), top = a00 + wx*(a10 - a00), bot likewise, a = top + wy*(bot - top); nearest:
+ *      texel floor(u*width); alpha of a texel = byte / 255; float -> int saturates, NaN -> 0.
+ *      Level selection (images with a mip chain, or samplers whose mag and min filters differ) — SampleGrad with
+ *      ddx / ddy(tex_coord) (visbuffer_encode.slang:57-60) and the isotropic LOD rule of the Vulkan specification:
+ *        derivatives are the "fine" quad differences: with qx = px & ~1, qy = py & ~1,
+ *          ddx(uv) = uv(qx + 1, py) - uv(qx, py),  ddy(uv) = uv(px, qy + 1) - uv(px, qy),
+ *        uv(.) = steps 1-2 evaluated with the edge functions stepped to that pixel (exact integers; outside the triangle the same
+ *        formula extrapolates, as helper invocations do);
+ *        mx = ddx(u)*width0, my = ddx(v)*height0, rho_x^2 = mx*mx + my*my, rho_y^2 likewise, rho^2 = (rho_x^2 > rho_y^2 ? rho_x^2 :
+ *        rho_y^2), lambda = 0.5 * log2_canonical(rho^2)  (orc_log2_canonical; NaN / 0 -> very negative);
+ *        lambda > 0 selects the min filter, else the mag filter; lc = !(lambda > 0) ? 0 : min(lambda, levels - 1);
+ *        mipmap linear: d = floor(lc), e = min(d + 1, levels - 1), f = lc - d, a = (1 - f)*a_d + f*a_e;
+ *        mipmap nearest: level (lc <= 0.5 ? 0 : ceil(lc + 0.5) - 1).
+ *      Level l is max(1, width0 >> l) x max(1, height0 >> l) texels and follows level l - 1 in memory, tightly packed.
  *   5. keep iff !(albedo_color.a * a < cutoff), cutoff = clamp(dequantize_half(alpha_cutoff), 0.001, 1.0) (NaN stays NaN).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct OrcAlphaMaterial {
   const uint8_t* texels;
-  uint32_t width, height, format, filter, address_u, address_v;
+  uint32_t width, height, format, levels, mag_filter, min_filter, mipmap_mode, address_u, address_v;
   float albedo_a, cutoff;
 } OrcAlphaMaterial;
 
@@ -584,36 +596,82 @@ static inline uint32_t alpha_wrap(int64_t i, uint32_t n, uint32_t mode) {
   if (r < 0) r += N;
   return (uint32_t)r;
 }
-static inline float alpha_texel(const OrcAlphaMaterial* a, uint32_t x, uint32_t y) {
-  const size_t i = (size_t)y * a->width + x;
-  const uint32_t t = a->format == OXC_IMAGE_R8_UNORM ? a->texels[i] : a->texels[i * 4 + 3];
+static inline float alpha_texel(const OrcAlphaMaterial* a, const uint8_t* base, uint32_t w, uint32_t x, uint32_t y) {
+  const size_t i = (size_t)y * w + x;
+  const uint32_t t = a->format == OXC_IMAGE_R8_UNORM ? base[i] : base[i * 4 + 3];
   return (float)t / 255.0f;
 }
-static float alpha_sample(const OrcAlphaMaterial* a, float u, float v) {
-  const float fw = (float)a->width, fh = (float)a->height;
-  if (a->filter == OXC_FILTER_NEAREST) {
+/* one level of the image with one filter */
+static float alpha_sample_level(const OrcAlphaMaterial* a, uint32_t level, uint32_t filter, float u, float v) {
+  const uint8_t* base = a->texels;
+  uint32_t w = a->width, h = a->height;
+  for (uint32_t l = 0; l < level; l++) { /* levels are tightly packed one after the other */
+    base += (size_t)w * h * (a->format == OXC_IMAGE_R8_UNORM ? 1u : 4u);
+    w = w > 1 ? w >> 1 : 1;
+    h = h > 1 ? h >> 1 : 1;
+  }
+  const float fw = (float)w, fh = (float)h;
+  if (filter == OXC_FILTER_NEAREST) {
     const int ix = alpha_f2i(floorf(u * fw)), iy = alpha_f2i(floorf(v * fh));
-    return alpha_texel(a, alpha_wrap(ix, a->width, a->address_u), alpha_wrap(iy, a->height, a->address_v));
+    return alpha_texel(a, base, w, alpha_wrap(ix, w, a->address_u), alpha_wrap(iy, h, a->address_v));
   }
   const float x = u * fw - 0.5f, y = v * fh - 0.5f;
   const float x0 = floorf(x), y0 = floorf(y);
   const float wx = x - x0, wy = y - y0;
   const int ix = alpha_f2i(x0), iy = alpha_f2i(y0);
-  const uint32_t xa = alpha_wrap(ix, a->width, a->address_u), xb = alpha_wrap((int64_t)ix + 1, a->width, a->address_u);
-  const uint32_t ya = alpha_wrap(iy, a->height, a->address_v), yb = alpha_wrap((int64_t)iy + 1, a->height, a->address_v);
-  const float a00 = alpha_texel(a, xa, ya), a10 = alpha_texel(a, xb, ya), a01 = alpha_texel(a, xa, yb), a11 = alpha_texel(a, xb, yb);
+  const uint32_t xa = alpha_wrap(ix, w, a->address_u), xb = alpha_wrap((int64_t)ix + 1, w, a->address_u);
+  const uint32_t ya = alpha_wrap(iy, h, a->address_v), yb = alpha_wrap((int64_t)iy + 1, h, a->address_v);
+  const float a00 = alpha_texel(a, base, w, xa, ya), a10 = alpha_texel(a, base, w, xb, ya), a01 = alpha_texel(a, base, w, xa, yb),
+              a11 = alpha_texel(a, base, w, xb, yb);
   const float top = a00 + wx * (a10 - a00), bot = a01 + wx * (a11 - a01);
   return top + wy * (bot - top);
 }
-/* steps 2, 4, 5: e = the three edge-function values of the sample, rw / uv in the same (a, b, c) order */
-static int alpha_keep_fragment(const OrcAlphaMaterial* a, const int64_t e[3], const float rw[3], const float uv[3][2]) {
+/* steps 1-2: uv from three edge-function values; rw / uv in the raster's (a, b, c) order */
+static void alpha_interpolate(const int64_t e[3], const float rw[3], const float uv[3][2], float* u, float* v) {
   const float p0 = (float)e[0] * rw[0], p1 = (float)e[1] * rw[1], p2 = (float)e[2] * rw[2];
   const float inv = 1.0f / ((p0 + p1) + p2);
   const float l0 = p0 * inv, l1 = p1 * inv, l2 = p2 * inv;
-  const float u = (l0 * uv[0][0] + l1 * uv[1][0]) + l2 * uv[2][0];
-  const float v = (l0 * uv[0][1] + l1 * uv[1][1]) + l2 * uv[2][1];
-  const float alpha = a->albedo_a * alpha_sample(a, u, v);
-  return !(alpha < a->cutoff);
+  *u = (l0 * uv[0][0] + l1 * uv[1][0]) + l2 * uv[2][0];
+  *v = (l0 * uv[0][1] + l1 * uv[1][1]) + l2 * uv[2][1];
+}
+/* steps 2, 4, 5 at pixel (px, py): e = its three edge-function values, ex / ey = their increments per pixel in x / y */
+static int alpha_keep_fragment(const OrcAlphaMaterial* a, int64_t px, int64_t py, const int64_t e[3], const int64_t ex[3],
+                               const int64_t ey[3], const float rw[3], const float uv[3][2]) {
+  float u, v;
+  alpha_interpolate(e, rw, uv, &u, &v);
+  float alpha;
+  if (a->levels <= 1 && a->mag_filter == a->min_filter) {
+    alpha = alpha_sample_level(a, 0, a->min_filter, u, v); /* nothing to select */
+  } else {
+    const int64_t ox = -(px & 1), oy = -(py & 1); /* to the quad's first column / row */
+    int64_t eA[3], eB[3], eC[3], eD[3];
+    for (int i = 0; i < 3; i++) {
+      eA[i] = e[i] + ox * ex[i]; eB[i] = eA[i] + ex[i];
+      eC[i] = e[i] + oy * ey[i]; eD[i] = eC[i] + ey[i];
+    }
+    float uA, vA, uB, vB, uC, vC, uD, vD;
+    alpha_interpolate(eA, rw, uv, &uA, &vA); alpha_interpolate(eB, rw, uv, &uB, &vB);
+    alpha_interpolate(eC, rw, uv, &uC, &vC); alpha_interpolate(eD, rw, uv, &uD, &vD);
+    const float w0 = (float)a->width, h0 = (float)a->height;
+    const float mx = (uB - uA) * w0, my = (vB - vA) * h0, nx = (uD - uC) * w0, ny = (vD - vC) * h0;
+    const float rx2 = mx * mx + my * my, ry2 = nx * nx + ny * ny;
+    const float r2 = rx2 > ry2 ? rx2 : ry2;
+    const float lambda = 0.5f * orc_log2_canonical(r2);
+    const uint32_t filter = lambda > 0.0f ? a->min_filter : a->mag_filter;
+    const float q = (float)(a->levels > 1 ? a->levels - 1 : 0);
+    const float lc = !(lambda > 0.0f) ? 0.0f : (lambda > q ? q : lambda);
+    if (a->mipmap_mode == OXC_MIPMAP_NEAREST) {
+      uint32_t d = lc <= 0.5f ? 0u : (uint32_t)ceilf(lc + 0.5f) - 1u;
+      if (d > (uint32_t)q) d = (uint32_t)q;
+      alpha = alpha_sample_level(a, d, filter, u, v);
+    } else {
+      const uint32_t d = (uint32_t)floorf(lc), dn = d + 1u > (uint32_t)q ? (uint32_t)q : d + 1u;
+      const float f = lc - (float)d;
+      const float lo = alpha_sample_level(a, d, filter, u, v), hi = alpha_sample_level(a, dn, filter, u, v);
+      alpha = (1.0f - f) * lo + f * hi;
+    }
+  }
+  return !(a->albedo_a * alpha < a->cutoff);
 }
 /* returns 0 when the material is not alpha tested (no albedo image) */
 static int alpha_material_setup(const OxcMaterialTable* tab, uint32_t material_index, OrcAlphaMaterial* a) {
@@ -622,12 +680,13 @@ static int alpha_material_setup(const OxcMaterialTable* tab, uint32_t material_i
   if (!(m->flags & OXC_MATERIAL_HAS_ALBEDO_IMAGE) || m->albedo_image_index >= tab->image_count) return 0;
   const OxcAlphaImage* im = &tab->images[m->albedo_image_index];
   a->texels = (const uint8_t*)im->texels_dev; /* the oracle's images live in host memory */
-  a->width = im->width; a->height = im->height; a->format = im->format;
-  a->filter = OXC_FILTER_LINEAR; a->address_u = OXC_ADDRESS_REPEAT; a->address_v = OXC_ADDRESS_REPEAT;
+  a->width = im->width; a->height = im->height; a->format = im->format; a->levels = im->level_count ? im->level_count : 1;
+  a->mag_filter = OXC_FILTER_LINEAR; a->min_filter = OXC_FILTER_LINEAR; a->mipmap_mode = OXC_MIPMAP_LINEAR;
+  a->address_u = OXC_ADDRESS_REPEAT; a->address_v = OXC_ADDRESS_REPEAT;
   if (tab->samplers && m->sampler_index < tab->sampler_count) {
-    a->filter = tab->samplers[m->sampler_index].filter;
-    a->address_u = tab->samplers[m->sampler_index].address_u;
-    a->address_v = tab->samplers[m->sampler_index].address_v;
+    const OxcSamplerDesc* sd = &tab->samplers[m->sampler_index];
+    a->mag_filter = sd->mag_filter; a->min_filter = sd->min_filter; a->mipmap_mode = sd->mipmap_mode;
+    a->address_u = sd->address_u; a->address_v = sd->address_v;
   }
   a->albedo_a = orc_dequantize_half(m->albedo_color[3]);
   const float c = orc_dequantize_half(m->alpha_cutoff);
@@ -688,9 +747,12 @@ static void raster_triangle_uv(const float clip[3][4], const float (*uv)[2], con
       if (!(zz >= 0.0f && zz <= 1.0f)) continue;
       if (am) { /* discard, visbuffer_encode.slang:62-64; (a, b, c) = vertices (0, 2, 1) */
         const int64_t e[3] = {e0, e1, e2};
+        /* orient2d(a, b, p) = (bx-ax)*(py-ay) - (by-ay)*(px-ax): per pixel (256 sub-pixels) d/dpx = -(by-ay)*256, d/dpy = (bx-ax)*256 */
+        const int64_t ex[3] = {-(cy - by) * 256, -(ay - cy) * 256, -(by - ay) * 256};
+        const int64_t ey[3] = {(cx - bx) * 256, (ax - cx) * 256, (bx - ax) * 256};
         const float rwo[3] = {rws[0], rws[2], rws[1]};
         const float uvo[3][2] = {{uv[0][0], uv[0][1]}, {uv[2][0], uv[2][1]}, {uv[1][0], uv[1][1]}};
-        if (!alpha_keep_fragment(am, e, rwo, uvo)) continue;
+        if (!alpha_keep_fragment(am, px, py, e, ex, ey, rwo, uvo)) continue;
       }
       uint32_t zbits = f2bits(zz);
       if (zbits == 0x80000000u) zbits = 0u; /* -0.0 -> +0.0 so unsigned order == depth order */
@@ -952,12 +1014,13 @@ int orc_raster_triangle_alpha(const OxcMaterialTable* table, uint32_t material_i
   raster_triangle_uv(clip, uv, a, data, width, height, vis);
   return 0;
 }
-float orc_alpha_sample(const OxcAlphaImage* image, const OxcSamplerDesc* sampler /* NULL: linear + repeat */, float u, float v) {
+float orc_alpha_sample(const OxcAlphaImage* image, const OxcSamplerDesc* sampler /* NULL: linear + repeat */, uint32_t level, float u, float v) {
   OrcAlphaMaterial a;
   memset(&a, 0, sizeof a);
   a.texels = (const uint8_t*)image->texels_dev; a.width = image->width; a.height = image->height; a.format = image->format;
-  if (sampler) { a.filter = sampler->filter; a.address_u = sampler->address_u; a.address_v = sampler->address_v; }
-  return alpha_sample(&a, u, v);
+  uint32_t filter = OXC_FILTER_LINEAR;
+  if (sampler) { filter = sampler->min_filter; a.address_u = sampler->address_u; a.address_v = sampler->address_v; }
+  return alpha_sample_level(&a, level, filter, u, v);
 }
 
 /* orc_raster_visbuffer_clip with the alpha-tested discard of visbuffer_encode.slang:54-66 (specification above raster_triangle).

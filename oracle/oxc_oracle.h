@@ -144,7 +144,7 @@ void orc_raster_visbuffer_clip(const OrcScene* scene, const OxcMeshletInstance* 
  * specification, plain or clip path; returns 1 if it took the clip path */
 int orc_raster_triangle_alpha(const OxcMaterialTable* table, uint32_t material_index, const float clip[3][4], const float uv[3][2],
                               uint32_t data, uint32_t width, uint32_t height, uint64_t* vis);
-float orc_alpha_sample(const OxcAlphaImage* image, const OxcSamplerDesc* sampler, float u, float v);
+float orc_alpha_sample(const OxcAlphaImage* image, const OxcSamplerDesc* sampler, uint32_t level, float u, float v); /* one level, min_filter */
 void orc_raster_visbuffer_alpha(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances,
                                 const uint32_t* visible_indices, uint32_t pass_first, uint32_t pass_count,
                                 const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,

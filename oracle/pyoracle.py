@@ -182,21 +182,51 @@ def raster_clip(hs, mi, visible, first, count, cam, vis, id_base=0):
     return int(ntri.value), int(nclip.value)
 
 
+def mip_chain(level0):
+    """2x2 box-filtered mip chain (rounded to nearest) of a uint8 image [h, w] or [h, w, 4] down to 1x1: list of levels"""
+    levels = [np.ascontiguousarray(level0, dtype=np.uint8)]
+    while levels[-1].shape[0] > 1 or levels[-1].shape[1] > 1:
+        a = levels[-1].astype(np.uint32)
+        h, w = a.shape[0], a.shape[1]
+        ys = (np.arange(max(1, h // 2)) * 2)
+        xs = (np.arange(max(1, w // 2)) * 2)
+        y1, x1 = np.minimum(ys + 1, h - 1), np.minimum(xs + 1, w - 1)
+        s = a[ys][:, xs] + a[ys][:, x1] + a[y1][:, xs] + a[y1][:, x1]
+        levels.append(((s + 2) // 4).astype(np.uint8))
+    return levels
+
+
 class MaterialTable:
-    """host-side OxcMaterialTable for the oracle: images = list of (uint8 array [h, w, 4] or [h, w], format)"""
+    """host-side OxcMaterialTable for the oracle: images = list of (texels, format) with texels a uint8 array [h, w, 4] / [h, w]
+    (single level) or a LIST of such arrays (levels 0.., packed one after the other as the ABI wants them)"""
 
     def __init__(self, materials, images=(), samplers=None):
         self.materials = np.ascontiguousarray(materials, dtype=abi.MATERIAL_DT)
-        self.texels = [np.ascontiguousarray(t, dtype=np.uint8) for t, _ in images]
+        self.texels, self.level0, self.levels = [], [], []
+        for t, _ in images:
+            lv = t if isinstance(t, (list, tuple)) else [t]
+            self.level0.append(np.ascontiguousarray(lv[0], dtype=np.uint8))
+            self.levels.append(len(lv))
+            self.texels.append(np.ascontiguousarray(np.concatenate([np.ascontiguousarray(l, dtype=np.uint8).reshape(-1) for l in lv])))
         self.images = np.zeros(len(images), dtype=abi.ALPHA_IMAGE_DT)
-        for i, (t, fmt) in enumerate(images):
-            self.images[i] = (self.texels[i].ctypes.data, t.shape[1], t.shape[0], fmt, 0)
+        for i, (_, fmt) in enumerate(images):
+            self.images[i] = (self.texels[i].ctypes.data, self.level0[i].shape[1], self.level0[i].shape[0], fmt, self.levels[i] if self.levels[i] > 1 else 0)
         self.samplers = None if samplers is None else np.ascontiguousarray(samplers, dtype=abi.SAMPLER_DT)
         self.ref = abi.MaterialTable()
         self.ref.materials, self.ref.material_count = self.materials.ctypes.data, len(self.materials)
         self.ref.images, self.ref.image_count = (self.images.ctypes.data if len(self.images) else None), len(self.images)
         if self.samplers is not None:
             self.ref.samplers, self.ref.sampler_count = self.samplers.ctypes.data, len(self.samplers)
+
+    def device_images(self, ctx):
+        """uploads every image (all levels) through `ctx`; returns (the `images` argument of set_materials, the device pointers)"""
+        out, ptrs = [], []
+        for i, t in enumerate(self.texels):
+            d = ctx.alloc(t.size)
+            ctx.upload(d, t)
+            ptrs.append(d)
+            out.append((d, int(self.images["width"][i]), int(self.images["height"][i]), int(self.images["format"][i]), int(self.images["level_count"][i])))
+        return out, ptrs
 
 
 def raster_alpha(hs, mi, visible, first, count, cam, vis, table: MaterialTable, id_base=0):
@@ -209,13 +239,15 @@ def raster_alpha(hs, mi, visible, first, count, cam, vis, table: MaterialTable, 
     return int(ntri.value), int(nalpha.value)
 
 
-def alpha_sample(texels, fmt, u, v, sampler=None):
-    t = np.ascontiguousarray(texels, dtype=np.uint8)
+def alpha_sample(texels, fmt, u, v, sampler=None, level=0):
+    """one level of an image (texels: one array, or the list of its levels) through the sampler's min filter / address modes"""
+    lv = texels if isinstance(texels, (list, tuple)) else [texels]
+    t = np.ascontiguousarray(np.concatenate([np.ascontiguousarray(l, dtype=np.uint8).reshape(-1) for l in lv]))
     img = np.zeros(1, dtype=abi.ALPHA_IMAGE_DT)
-    img[0] = (t.ctypes.data, t.shape[1], t.shape[0], fmt, 0)
+    img[0] = (t.ctypes.data, lv[0].shape[1], lv[0].shape[0], fmt, len(lv))
     smp = None if sampler is None else np.array([sampler], dtype=abi.SAMPLER_DT)
     lib().orc_alpha_sample.restype = C.c_float
-    return float(lib().orc_alpha_sample(_p(img), _p(smp), C.c_float(u), C.c_float(v)))
+    return float(lib().orc_alpha_sample(_p(img), _p(smp), C.c_uint32(level), C.c_float(u), C.c_float(v)))
 
 
 def raster_triangle_alpha(table: MaterialTable, material_index, clip, uv, data, vis):

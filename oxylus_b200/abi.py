@@ -144,8 +144,14 @@ MATERIAL_HAS_ALBEDO_IMAGE, MATERIAL_ALPHA_MASK = 1, 1 << 8
 IMAGE_RGBA8_UNORM, IMAGE_R8_UNORM = 0, 1
 FILTER_LINEAR, FILTER_NEAREST = 0, 1
 ADDRESS_REPEAT, ADDRESS_CLAMP_TO_EDGE, ADDRESS_MIRRORED_REPEAT = 0, 1, 2
-ALPHA_IMAGE_DT = np.dtype([("texels", "<u8"), ("width", "<u4"), ("height", "<u4"), ("format", "<u4"), ("reserved", "<u4")])
-SAMPLER_DT = np.dtype([("filter", "<u4"), ("address_u", "<u4"), ("address_v", "<u4")])
+MIPMAP_LINEAR, MIPMAP_NEAREST = 0, 1
+ALPHA_IMAGE_DT = np.dtype([("texels", "<u8"), ("width", "<u4"), ("height", "<u4"), ("format", "<u4"), ("level_count", "<u4")])
+SAMPLER_DT = np.dtype([("mag_filter", "<u4"), ("min_filter", "<u4"), ("mipmap_mode", "<u4"), ("address_u", "<u4"), ("address_v", "<u4")])
+
+
+def sampler(mag=FILTER_LINEAR, min=FILTER_LINEAR, mip=MIPMAP_LINEAR, u=ADDRESS_REPEAT, v=ADDRESS_REPEAT):  # noqa: A002
+    """one SAMPLER_DT record (defaults = the reference's default sampler, Texture.hpp:38-45)"""
+    return (mag, min, mip, u, v)
 
 
 class MaterialTable(C.Structure):

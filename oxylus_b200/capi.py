@@ -233,13 +233,13 @@ def assemble_scene(built, mesh_of_instance, transforms, width, height, transform
 
 def material_table(materials, images=None, samplers=None):
     """(abi.MaterialTable or None, the arrays it points to) from an abi.MATERIAL_DT array, a list of (device pointer, width,
-    height, format) and an optional abi.SAMPLER_DT array"""
+    height, format[, level_count]) and an optional abi.SAMPLER_DT array"""
     if materials is None or len(materials) == 0:
         return None, ()
     mats = np.ascontiguousarray(materials, dtype=abi.MATERIAL_DT)
     imgs = np.zeros(len(images or []), dtype=abi.ALPHA_IMAGE_DT)
-    for i, (ptr, w, h, fmt) in enumerate(images or []):
-        imgs[i] = (int(ptr), w, h, fmt, 0)
+    for i, im in enumerate(images or []):  # (device pointer, width, height, format[, level_count])
+        imgs[i] = (int(im[0]), im[1], im[2], im[3], im[4] if len(im) > 4 else 0)
     smp = None if samplers is None else np.ascontiguousarray(samplers, dtype=abi.SAMPLER_DT)
     t = abi.MaterialTable()
     t.materials, t.material_count = mats.ctypes.data, len(mats)

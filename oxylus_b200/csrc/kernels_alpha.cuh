@@ -70,7 +70,11 @@ OXC_DI void shade_pixel_alpha(const TriSetup& s, const AlphaMaterial& m, const A
   if ((e0 - (s.bias & 1)) < 0 || (e1 - ((s.bias >> 1) & 1)) < 0 || (e2 - ((s.bias >> 2) & 1)) < 0) return;
   const float zz = fa(fa(s.za, fm((float)e1, s.dzb)), fm((float)e2, s.dzc));
   if (!(zz >= 0.0f && zz <= 1.0f)) return;
-  if (!alpha_keep(m, t, e0, e1, e2)) return; // discard (visbuffer_encode.slang:62-64)
+  {  // discard (visbuffer_encode.slang:62-64); edge-function increments per pixel as in raster_small (oxc_raster_core.cuh)
+    const long long ex[3] = {-(long long)(s.cy - s.by) * 256, -(long long)(s.ay - s.cy) * 256, -(long long)(s.by - s.ay) * 256};
+    const long long ey[3] = {(long long)(s.cx - s.bx) * 256, (long long)(s.ax - s.cx) * 256, (long long)(s.bx - s.ax) * 256};
+    if (!alpha_keep(m, t, px, py, e0, e1, e2, ex, ey)) return;
+  }
   uint32_t zb = __float_as_uint(zz);
   zb = zb == 0x80000000u ? 0u : zb;
   atomicMax(vis + (size_t)py * W + px, ((unsigned long long)zb << 32) | data);

@@ -815,13 +815,20 @@ int oxc_set_materials(OxcContext* c, const OxcMaterialTable* t, void* stream) {
     if (!im.texels_dev || im.width == 0 || im.height == 0 || im.width > (1u << 16) || im.height > (1u << 16) ||
         (im.format != OXC_IMAGE_RGBA8_UNORM && im.format != OXC_IMAGE_R8_UNORM))
       return fail(OXC_E_INVALID, "image %u: null texels, extent outside 1..65536 or unknown format", m.albedo_image_index);
+    uint32_t full_chain = 1;
+    for (uint32_t e = im.width > im.height ? im.width : im.height; e > 1; e >>= 1) full_chain++;
+    if (im.level_count > full_chain) return fail(OXC_E_INVALID, "image %u: level_count %u > %u levels of a %u x %u image", m.albedo_image_index, im.level_count, full_chain, im.width, im.height);
     d.texels = static_cast<const uint8_t*>(im.texels_dev); d.width = im.width; d.height = im.height; d.format = im.format;
-    d.filter = OXC_FILTER_LINEAR; d.address_u = OXC_ADDRESS_REPEAT; d.address_v = OXC_ADDRESS_REPEAT; // Texture.hpp:38-45 defaults
+    d.levels = im.level_count ? im.level_count : 1u;
+    d.mag_filter = OXC_FILTER_LINEAR; d.min_filter = OXC_FILTER_LINEAR; d.mipmap_mode = OXC_MIPMAP_LINEAR; // Texture.hpp:38-45 defaults
+    d.address_u = OXC_ADDRESS_REPEAT; d.address_v = OXC_ADDRESS_REPEAT;
     if (t->samplers && m.sampler_index < t->sampler_count) {
       const OxcSamplerDesc& sd = t->samplers[m.sampler_index];
-      if (sd.filter > OXC_FILTER_NEAREST || sd.address_u > OXC_ADDRESS_MIRRORED_REPEAT || sd.address_v > OXC_ADDRESS_MIRRORED_REPEAT)
-        return fail(OXC_E_INVALID, "sampler %u: unknown filter / address mode", m.sampler_index);
-      d.filter = sd.filter; d.address_u = sd.address_u; d.address_v = sd.address_v;
+      if (sd.mag_filter > OXC_FILTER_NEAREST || sd.min_filter > OXC_FILTER_NEAREST || sd.mipmap_mode > OXC_MIPMAP_NEAREST ||
+          sd.address_u > OXC_ADDRESS_MIRRORED_REPEAT || sd.address_v > OXC_ADDRESS_MIRRORED_REPEAT)
+        return fail(OXC_E_INVALID, "sampler %u: unknown filter / mipmap / address mode", m.sampler_index);
+      d.mag_filter = sd.mag_filter; d.min_filter = sd.min_filter; d.mipmap_mode = sd.mipmap_mode;
+      d.address_u = sd.address_u; d.address_v = sd.address_v;
     }
     d.albedo_a = host_dequantize_half(m.albedo_color[3]);
     const float cut = host_dequantize_half(m.alpha_cutoff);

@@ -63,18 +63,18 @@ def test_alpha_sample_hand_cases(orc):
     assert s(img, abi.IMAGE_R8_UNORM, 0.0, 0.25) == 0.5
     assert s(img, abi.IMAGE_R8_UNORM, 1.25, -0.75) == s(img, abi.IMAGE_R8_UNORM, 0.25, 0.25)
     # clamp to edge: left of the first texel centre is the first texel
-    clamp = (abi.FILTER_LINEAR, abi.ADDRESS_CLAMP_TO_EDGE, abi.ADDRESS_CLAMP_TO_EDGE)
+    clamp = abi.sampler(u=abi.ADDRESS_CLAMP_TO_EDGE, v=abi.ADDRESS_CLAMP_TO_EDGE)
     assert s(img, abi.IMAGE_R8_UNORM, 0.0, 0.25, clamp) == 0.0
     assert s(img, abi.IMAGE_R8_UNORM, -3.0, 0.25, clamp) == 0.0
     assert s(img, abi.IMAGE_R8_UNORM, 7.0, 0.25, clamp) == 1.0
     # mirrored repeat: [0,1) forward, [1,2) backward
-    mirror = (abi.FILTER_NEAREST, abi.ADDRESS_MIRRORED_REPEAT, abi.ADDRESS_MIRRORED_REPEAT)
+    mirror = abi.sampler(abi.FILTER_NEAREST, abi.FILTER_NEAREST, u=abi.ADDRESS_MIRRORED_REPEAT, v=abi.ADDRESS_MIRRORED_REPEAT)
     assert s(img, abi.IMAGE_R8_UNORM, 0.25, 0.25, mirror) == 0.0
     assert s(img, abi.IMAGE_R8_UNORM, 1.25, 0.25, mirror) == 1.0   # texel 1 mirrored
     assert s(img, abi.IMAGE_R8_UNORM, 1.75, 0.25, mirror) == 0.0
     assert s(img, abi.IMAGE_R8_UNORM, -0.25, 0.25, mirror) == 0.0  # texel -1 -> 0
     # nearest, repeat; RGBA8 reads byte 3
-    near = (abi.FILTER_NEAREST, abi.ADDRESS_REPEAT, abi.ADDRESS_REPEAT)
+    near = abi.sampler(abi.FILTER_NEAREST, abi.FILTER_NEAREST)
     assert s(img, abi.IMAGE_R8_UNORM, 0.49, 0.0, near) == 0.0 and s(img, abi.IMAGE_R8_UNORM, 0.51, 0.0, near) == 1.0
     rgba = np.zeros((1, 1, 4), dtype=np.uint8)
     rgba[0, 0] = [9, 9, 9, 51]
@@ -99,7 +99,7 @@ def test_alpha_matches_binary64_perspective_interpolation(orc):
     rng = np.random.default_rng(11)
     W, H = 96, 64
     tex = checker(8, 1, rgba=False)  # 8x8 texels, every texel its own cell; nearest filter => alpha = cell parity
-    near = np.array([(abi.FILTER_NEAREST, abi.ADDRESS_REPEAT, abi.ADDRESS_REPEAT)], dtype=abi.SAMPLER_DT)
+    near = np.array([abi.sampler(abi.FILTER_NEAREST, abi.FILTER_NEAREST)], dtype=abi.SAMPLER_DT)
     tab = orc.MaterialTable([material(image=0, cutoff=0.5)], [(tex, abi.IMAGE_R8_UNORM)], near)
     plain_tab = orc.MaterialTable([material()])
     checked = kept = dropped = 0
@@ -172,6 +172,104 @@ def test_alpha_cutoff_and_flags(orc):
     assert keep(m)
 
 
+def _screen_triangle(W, H, texels_per_pixel_x, texels_per_pixel_y, n_tex):
+    """one w = 1 triangle covering the whole W x H screen whose uv advances by the given number of level-0 texels per pixel"""
+    clip = np.array([[-1, -1, 0.5, 1], [3, -1, 0.5, 1], [-1, 3, 0.5, 1]], dtype=np.float32)
+    uv = np.array([[0, 0], [2 * W * texels_per_pixel_x / n_tex, 0], [0, 2 * H * texels_per_pixel_y / n_tex]], dtype=np.float32)
+    if not _front_facing(clip):
+        clip[[1, 2]] = clip[[2, 1]]
+        uv[[1, 2]] = uv[[2, 1]]
+    return clip, uv
+
+
+def _kept_fraction(orc, tab, clip, uv, W, H):
+    vis = orc.clear_visbuffer(W, H)
+    orc.raster_triangle_alpha(tab, 0, clip, uv, 3, vis)
+    return float(((vis & 0xFFFFFFFF) == 3).sum()) / (W * H)
+
+
+def test_mip_level_selection_hand_cases(orc):
+    """SampleGrad's level selection (visbuffer_encode.slang:57-60 + the isotropic LOD rule): an 8 x 8 image whose levels are constant
+    (alpha 1, 0, 1, 0 for levels 0..3) tells which level a fragment read"""
+    W = H = 32
+    levels = [np.full((8 >> l, 8 >> l), 255 if l % 2 == 0 else 0, dtype=np.uint8) for l in range(4)]
+    img = [(levels, abi.IMAGE_R8_UNORM)]
+
+    def kept(s_x, s_y, cutoff=0.5, smp=None):
+        tab = orc.MaterialTable([material(image=0, cutoff=cutoff)], img, None if smp is None else np.array([smp], dtype=abi.SAMPLER_DT))
+        clip, uv = _screen_triangle(W, H, s_x, s_y, 8)
+        return _kept_fraction(orc, tab, clip, uv, W, H)
+
+    assert kept(1, 1) == 1.0        # lambda = 0: level 0
+    assert kept(0.25, 0.25) == 1.0  # magnified: level 0
+    assert kept(2, 2) == 0.0        # lambda = 1: level 1
+    assert kept(4, 4) == 1.0        # lambda = 2: level 2
+    assert kept(8, 8) == 0.0        # lambda = 3: level 3
+    assert kept(64, 64) == 0.0      # clamped to the last level
+    assert kept(4, 1) == 1.0 and kept(1, 4) == 1.0  # the larger of the two footprints decides (isotropic rule)
+    r2 = float(np.sqrt(2.0))
+    assert kept(r2, r2, cutoff=0.4) == 1.0 and kept(r2, r2, cutoff=0.6) == 0.0  # lambda = 0.5: half of level 0, half of level 1
+    assert kept(2 ** 1.25, 1, cutoff=0.2) == 1.0 and kept(2 ** 1.25, 1, cutoff=0.3) == 0.0  # 0.75 * level 1 + 0.25 * level 2 = 0.25
+    nearest_mip = abi.sampler(mip=abi.MIPMAP_NEAREST)
+    assert kept(2 ** 0.4, 1, smp=nearest_mip) == 1.0  # lambda 0.4 -> level 0
+    assert kept(2 ** 0.6, 1, smp=nearest_mip) == 0.0  # lambda 0.6 -> level 1
+    assert kept(2 ** 1.6, 1, smp=nearest_mip) == 1.0  # lambda 1.6 -> level 2
+    # a single-level image never leaves level 0
+    one = orc.MaterialTable([material(image=0, cutoff=0.5)], [(levels[0], abi.IMAGE_R8_UNORM)])
+    clip, uv = _screen_triangle(W, H, 8, 8, 8)
+    assert _kept_fraction(orc, one, clip, uv, W, H) == 1.0
+
+
+def test_mag_and_min_filter_selection(orc):
+    """lambda > 0 uses the min filter, else the mag filter: a sampler with mag = nearest, min = linear equals the all-nearest
+    sampler when the image is magnified and the all-linear sampler when it is minified"""
+    W = H = 48
+    rng = np.random.default_rng(2)
+    tex = rng.integers(0, 256, (8, 8), dtype=np.uint8)
+    img = [(tex, abi.IMAGE_R8_UNORM)]
+
+    def image(smp, s):
+        tab = orc.MaterialTable([material(image=0, cutoff=0.5)], img, np.array([smp], dtype=abi.SAMPLER_DT))
+        clip, uv = _screen_triangle(W, H, s, s, 8)
+        vis = orc.clear_visbuffer(W, H)
+        orc.raster_triangle_alpha(tab, 0, clip, uv, 3, vis)
+        return (vis & 0xFFFFFFFF) == 3
+
+    mixed = abi.sampler(mag=abi.FILTER_NEAREST, min=abi.FILTER_LINEAR)
+    nearest, linear = abi.sampler(abi.FILTER_NEAREST, abi.FILTER_NEAREST), abi.sampler()
+    assert not np.array_equal(image(nearest, 0.13), image(linear, 0.13)) and not np.array_equal(image(nearest, 1.7), image(linear, 1.7))
+    np.testing.assert_array_equal(image(mixed, 0.13), image(nearest, 0.13))
+    np.testing.assert_array_equal(image(mixed, 1.7), image(linear, 1.7))
+
+
+def test_mip_levels_follow_the_perspective(orc):
+    """the textured ground plane with a full mip chain whose levels are constant (level l: alpha 1 for even l, 0 for odd l): bands
+    of kept / discarded rows, coarser levels towards the horizon — the derivative-based selection at work across huge clipped
+    triangles; rows closer to the horizon never use a finer level than rows below them"""
+    sc = textured_ground(1)
+    sc.mesh_instances["material_index"] = 0
+    hs = orc.HostScene(sc)
+    cam = sc.camera()
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    visible, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+    visible = visible[: int(cmd["x"][0])]
+    n = 256
+    levels = [np.full((max(1, n >> l), max(1, n >> l)), 255 if l % 2 == 0 else 0, dtype=np.uint8) for l in range(9)]
+    tab = orc.MaterialTable([material(image=0, cutoff=0.5)], [(levels, abi.IMAGE_R8_UNORM)], np.array([abi.sampler(mip=abi.MIPMAP_NEAREST)], dtype=abi.SAMPLER_DT))
+    img = orc.clear_visbuffer(sc.width, sc.height)
+    orc.raster_alpha(hs, mi, visible, 0, len(visible), cam, img, tab)
+    plain = orc.clear_visbuffer(sc.width, sc.height)
+    orc.raster_clip(hs, mi, visible, 0, len(visible), cam, plain)
+    ground = (plain & 0xFFFFFFFF) != 0xFFFFFFFF
+    kept = (img & 0xFFFFFFFF) != 0xFFFFFFFF
+    col = sc.width // 2
+    rows = np.nonzero(ground[:, col])[0]
+    state = kept[rows, col].astype(int)
+    flips = int(np.abs(np.diff(state)).sum())
+    assert 3 <= flips <= 9, flips        # several level bands between the camera and the horizon in the centre column
+    assert 0.2 < kept[ground].mean() < 0.8
+
+
 @pytest.fixture(scope="module")
 def scene_and_tables(orc):
     sc = synth.make_scene(4000, config_index=2, width=480, height=270, n_unique_meshes=12)
@@ -194,8 +292,8 @@ def test_alpha_pass_properties(orc, scene_and_tables):
     plain = orc.clear_visbuffer(w, h)
     ntri_plain, _ = orc.raster_clip(hs, mi, visible, 0, len(visible), cam, plain)
     mats = [material(), material(image=0, cutoff=0.5), material(image=1, cutoff=0.3, albedo_a=0.8, sampler=1), material(image=2, cutoff=0.5, sampler=2)]
-    smp = np.array([(0, 0, 0), (abi.FILTER_NEAREST, abi.ADDRESS_CLAMP_TO_EDGE, abi.ADDRESS_CLAMP_TO_EDGE),
-                    (abi.FILTER_LINEAR, abi.ADDRESS_MIRRORED_REPEAT, abi.ADDRESS_REPEAT)], dtype=abi.SAMPLER_DT)
+    smp = np.array([abi.sampler(), abi.sampler(abi.FILTER_NEAREST, abi.FILTER_NEAREST, u=abi.ADDRESS_CLAMP_TO_EDGE, v=abi.ADDRESS_CLAMP_TO_EDGE),
+                    abi.sampler(u=abi.ADDRESS_MIRRORED_REPEAT)], dtype=abi.SAMPLER_DT)
 
     def run(images):
         img = orc.clear_visbuffer(w, h)
@@ -235,7 +333,7 @@ def test_alpha_through_the_clip_path(orc):
     be the same whether the plane is 1 quad (huge clipped triangles) or 40 x 40 quads (mostly unclipped) — the interpolation
     runs over the original triangle, not over the clipped pieces"""
     tab_img = [(checker(4, 1, rgba=False), abi.IMAGE_R8_UNORM)]
-    near = np.array([(abi.FILTER_NEAREST, abi.ADDRESS_REPEAT, abi.ADDRESS_REPEAT)], dtype=abi.SAMPLER_DT)
+    near = np.array([abi.sampler(abi.FILTER_NEAREST, abi.FILTER_NEAREST)], dtype=abi.SAMPLER_DT)
     covers = []
     for cells in (1, 40):
         sc = textured_ground(cells)
