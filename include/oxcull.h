@@ -358,11 +358,13 @@ int oxc_raster_visbuffer(OxcContext* ctx, const OxcCullCamera* camera, uint32_t 
  * (scene.slang:51-66,92-94,115-124).  Once a material table is set, oxc_raster_visbuffer does the same: the pass's survivors
  * are split by material (one extra kernel), meshlets of materials WITHOUT an albedo image go through the unchanged raster
  * kernel, the others through k_raster_alpha, which evaluates the test per covered sample before the packed atomic max.
- * The hardware sampler's arithmetic is not specified bit for bit, so the test is SPECIFIED here (oracle: orc_alpha_keep,
- * oracle/oxc_oracle.c; canonical binary32 order, IEEE divide):
- *   - uv at the pixel centre: perspective-correct barycentrics of the ORIGINAL triangle from its homogeneous edge functions
- *     (rows of adj[x y w]; no per-vertex divide, so clipped triangles — vertices at w <= 0 — interpolate like any other);
- *     vertices of a mesh without texture coordinates have uv = (0, 0) (scene.slang:355-361)
+ * The hardware's interpolation and sampling arithmetic is not specified bit for bit, so the test is SPECIFIED here (full text:
+ * oracle/oxc_oracle.c above raster_triangle; canonical binary32 order, IEEE divide):
+ *   - uv at a covered sample: the raster's own integer edge functions E_a, E_b, E_c (exact, >= 0, sum = 2 * area) are the
+ *     screen-space weights; perspective correction p_i = (float)E_i * (1 / w_i), l_i = p_i / ((p_a + p_b) + p_c),
+ *     u = (l_a*u_a + l_b*u_b) + l_c*u_c — non-negative terms only, no cancellation for tiny or thin triangles.  Triangles that
+ *     take the clip path carry uv through the Sutherland-Hodgman cuts (same t as the position).  Vertices of a mesh without
+ *     texture coordinates have uv = (0, 0) (scene.slang:355-361)
  *   - filter / address / mipmap modes from the material's sampler (default: linear, linear, repeat — Texture.hpp:38-45; no
  *     anisotropy, LOD bias or clamp: the reference sets none): texel centre convention x = u * width - 0.5, weights = the f32
  *     fractions (no 8-bit weight quantisation), alpha = texel / 255

@@ -871,7 +871,20 @@ int oxc_raster_visbuffer_clip_pass(OxcContext* c, const OxcCullCamera* cam, uint
   uint32_t grid = (uint32_t)(c->sm_count * 4);
   if (grid > tiles) grid = tiles;
   if (grid == 0) grid = 1;
-  k_raster_clip_pass<<<grid, TRI_THREADS, 0, s>>>(p);
+  TriParams pm = p;
+  if (c->alpha_active) { // alpha-tested meshlets clip in place (k_raster_alpha) and never depend on the queue: walk the others only
+    AlphaParams ap{};
+    ap.mesh_instances = c->d_mesh_instances; ap.materials = c->d_alpha_materials; ap.material_count = c->alpha_material_count;
+    ap.opaque_list = c->d_alpha_lists; ap.masked_list = c->d_alpha_lists + c->info.max_meshlet_instances;
+    ap.opaque_cmd = reinterpret_cast<OxcDispatchIndirectCommand*>(c->d_alpha_cmd);
+    ap.masked_cmd = reinterpret_cast<OxcDispatchIndirectCommand*>(c->d_alpha_cmd + 16);
+    CK(cudaMemsetAsync(c->d_alpha_cmd, 0, 64, s));
+    k_partition_alpha<<<c->sm_count * 4, 256, 0, s>>>(p, ap);
+    LAUNCHED();
+    pm.visible_indices = ap.opaque_list; pm.tri_cmd = ap.opaque_cmd;
+    pm.vis = reinterpret_cast<const OxcMeshletInstanceVisibility*>(c->d_alpha_cmd + 32);
+  }
+  k_raster_clip_pass<<<grid, TRI_THREADS, 0, s>>>(pm);
   LAUNCHED();
   k_raster_big<<<c->sm_count * 8, 256, 0, s>>>(p);
   LAUNCHED();

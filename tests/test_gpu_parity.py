@@ -1487,6 +1487,9 @@ def test_alpha_discard_clip_path_parity(capi, orc):
         np.testing.assert_array_equal(got, ref)
         assert ctx.raster_triangle_count() == ntri
         assert ctx.check_status() == 0
+        # the stand-alone clip pass leaves alpha-tested meshlets alone (they were clipped, with the test, by the raster itself)
+        ctx.raster_visbuffer_clip_pass(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+        np.testing.assert_array_equal(ctx.download(vis_dev, np.uint64, w * h).reshape(h, w), ref)
         with pytest.raises(capi.OxcError):  # a material that names an image outside the table is refused
             ctx.set_materials(np.array([material(image=3)], dtype=abi.MATERIAL_DT), [(tex_dev, 4, 4, abi.IMAGE_R8_UNORM)])
         ctx.free(vis_dev)
