@@ -1,6 +1,7 @@
 /* host_min.c — the smallest plain-C host of liboxcull.so: one hand-built meshlet (a quad), one frame of the visibility
- * path (cull_meshes -> cull_meshlets -> raster -> resolve), results back on the host; then the same frame with a material
- * table whose 2x2 checker image makes the encode pass discard two quadrants of the quad (visbuffer_encode.slang:54-66).
+ * path (cull_meshes -> cull_meshlets -> raster -> resolve), results back on the host; `host_min alpha` then runs the same frame
+ * with a material table whose 2x2 checker image makes the encode pass discard two quadrants of the quad
+ * (visbuffer_encode.slang:54-66).
  *
  *   gcc -std=c11 -Iinclude examples/host_min.c -Loxylus_b200 -loxcull -Wl,-rpath,$PWD/oxylus_b200 -o host_min
  *
@@ -29,7 +30,8 @@ static uint16_t half_bits(float v) { /* round-to-nearest half for the few consta
     if (rc_ != OXC_OK) { fprintf(stderr, "%s failed (%d): %s\n", #call, rc_, oxc_last_error()); return rc_ == OXC_E_NO_DEVICE ? 3 : 1; } \
   } while (0)
 
-int main(void) {
+int main(int argc, char** argv) {
+  const int with_alpha = argc > 1 && strcmp(argv[1], "alpha") == 0; /* host_min alpha: second frame with a material table */
   enum { W = 64, H = 48 };
   /* ---- blob: positions | meshlet | bounds | micro indices | vertex indices | lod table (all 16-byte aligned) ---- */
   _Alignas(16) uint8_t blob[512];
@@ -96,6 +98,12 @@ int main(void) {
   unsigned covered = 0;
   for (int i = 0; i < W * H; i++) covered += vis32[i] != OXC_VIS_CLEAR;
   printf("%s: %u of %d pixels covered by the quad (expected %d)\n", oxc_version(), covered, W * H, (W / 2) * (H / 2));
+  if (!with_alpha) {
+    oxc_device_free(ctx, vis64);
+    oxc_device_free(ctx, vis32_dev);
+    oxc_destroy(ctx);
+    return covered == (W / 2) * (H / 2) ? 0 : 2;
+  }
   /* ---- the same frame with an alpha-tested material: 2x2 R8 checker, nearest + clamp, cutoff 0.5 ---- */
   const uint8_t texels[4] = {255, 0, 0, 255};
   void* tex_dev = NULL;

