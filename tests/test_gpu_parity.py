@@ -1508,6 +1508,37 @@ def test_alpha_discard_mipmapped_parity(capi, orc):
         ctx.close()
 
 
+def test_golden_alpha_frames(capi, orc):
+    """the CUDA path against the committed fixture tests/golden/alpha_small.json (two-pass frames with a single-level and a
+    mip-mapped material table; the fixture is what the oracle computes, test_oracle_alpha.py::test_golden_alpha_fixture)"""
+    from tests.test_oracle_alpha import load_golden_alpha
+
+    mg, want = load_golden_alpha()
+    state = {}
+
+    def frame_fn(name, parts, sc, cam, f):
+        mats, images, smp, tab = parts
+        if f == 0:
+            for st in state.values():
+                st["ctx"].close()
+            state.clear()
+            ctx = make_ctx(capi, sc)
+            dev, ptrs = tab.device_images(ctx)
+            ctx.set_materials(mats, dev, smp)
+            vis_dev, occ_dev = ctx.alloc(sc.width * sc.height * 8), ctx.alloc(sc.width * sc.height * 4)
+            ctx.upload(occ_dev, sc.occluder_depth)
+            state[name] = dict(ctx=ctx, vis=vis_dev, occ=occ_dev)
+        st = state[name]
+        got = _frame_gpu(capi, st["ctx"], sc, cam, st["occ"], st["vis"])
+        assert st["ctx"].check_status() == 0
+        return dict(vis64=got["vis64"], early=got["early"], late=got["late"], ntri=got["ntri"])
+
+    got = mg.generate(frame_fn)
+    for st in state.values():
+        st["ctx"].close()
+    assert got == want
+
+
 def test_alpha_clip_pass_leaves_alpha_meshlets_alone(capi, orc):
     """the stand-alone clip pass after a raster with a material table: alpha-tested meshlets were clipped (with the test) by the
     raster itself, so the pass must not draw their clipped triangles again without the test"""
