@@ -1539,6 +1539,68 @@ def test_golden_alpha_frames(capi, orc):
     assert got == want
 
 
+def test_alpha_discard_random_triangles(capi, orc):
+    """fuzz: meshes of random triangles around and through the camera (slivers, sub-pixel and screen-filling ones, vertices behind
+    the near plane, uv from tiny to huge), random images (with / without mip chains, RGBA8 / R8), random sampler modes and cutoffs:
+    the CUDA raster's image equals the oracle's bit for bit — small path, whole-warp path, clip path and level selection under
+    inputs no scene generator produces"""
+    from oxylus_b200 import capi as capi_mod
+    from tests.test_oracle_alpha import material
+
+    import os
+
+    n_seeds = int(os.environ.get("OXC_ALPHA_FUZZ_SEEDS", "6"))  # profiles/r2_emulated_alpha_fuzz.log: 400 seeds on the emulated library
+    discarding = 0
+    for seed in range(n_seeds):
+        rng = np.random.default_rng(100 + seed)
+        n_tri = 192
+        centre = np.stack([rng.uniform(-3, 3, n_tri), rng.uniform(-2, 2, n_tri), rng.uniform(-8, 0.5, n_tri)], axis=1)
+        size = 10.0 ** rng.uniform(-2.5, 0.8, n_tri)
+        pos = (centre[:, None, :] + rng.normal(0, 1, (n_tri, 3, 3)) * size[:, None, None]).astype(np.float32)
+        sliver = rng.random(n_tri) < 0.15
+        pos[sliver, 2] = pos[sliver, 1] + (pos[sliver, 2] - pos[sliver, 1]) * np.float32(1e-3)
+        uv = (rng.normal(0, 1, (n_tri, 3, 2)) * (10.0 ** rng.uniform(-2, 1.5, n_tri))[:, None, None]).astype(np.float32)
+        idx = np.arange(n_tri * 3, dtype=np.uint32)
+        built = [capi_mod.BuiltMesh(pos.reshape(-1, 3), [(idx, 0.0)], texcoords=uv.reshape(-1, 2))]
+        sc = capi_mod.assemble_scene(built, np.arange(1), np.eye(4, dtype=np.float32).reshape(1, 16), 320, 200)
+        sc.mesh_instances["material_index"] = 0
+        n = int(2 ** rng.integers(0, 6))
+        fmt = abi.IMAGE_R8_UNORM if rng.random() < 0.5 else abi.IMAGE_RGBA8_UNORM
+        tex = rng.integers(0, 256, (n, max(1, n // int(2 ** rng.integers(0, 2)))) + ((4,) if fmt == abi.IMAGE_RGBA8_UNORM else ()), dtype=np.uint8)
+        img = (orc.mip_chain(tex) if seed % 2 == 0 else tex, fmt)
+        smp = np.array([abi.sampler(int(rng.integers(2)), int(rng.integers(2)), int(rng.integers(2)), int(rng.integers(3)), int(rng.integers(3)))], dtype=abi.SAMPLER_DT)
+        mats = np.array([material(image=0, cutoff=float(rng.uniform(0.2, 0.8)), albedo_a=float(rng.uniform(0.7, 1.0)))], dtype=abi.MATERIAL_DT)
+        tab = orc.MaterialTable(mats, [img], smp)
+        hs = orc.HostScene(sc)
+        cam = sc.camera()
+        w, h = sc.width, sc.height
+        mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+        visible, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+        visible = visible[: int(cmd["x"][0])]
+        ref = orc.clear_visbuffer(w, h)
+        ntri, nalpha = orc.raster_alpha(hs, mi, visible, 0, len(visible), cam, ref, tab)
+        plain = orc.clear_visbuffer(w, h)
+        _, nclip = orc.raster_clip(hs, mi, visible, 0, len(visible), cam, plain)
+        assert ntri > 20 and nalpha == ntri and nclip > 0, (seed, ntri, nclip)
+        assert ((plain & 0xFFFFFFFF) != 0xFFFFFFFF).sum() > 200, seed
+        discarding += int(not np.array_equal(ref, plain))
+        ctx = make_ctx(capi, sc)
+        dev, ptrs = tab.device_images(ctx)
+        ctx.set_materials(mats, dev, smp)
+        vis_dev = ctx.alloc(w * h * 8)
+        ctx.clear_visbuffer(vis_dev, w, h)
+        ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+        ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
+        ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+        got = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
+        np.testing.assert_array_equal(got, ref, err_msg=f"seed {seed}")
+        assert ctx.raster_triangle_count() == ntri and ctx.check_status() == 0
+        for d in ptrs + [vis_dev]:
+            ctx.free(d)
+        ctx.close()
+    assert discarding >= n_seeds // 2  # (a random image can lie entirely above or below the cutoff)
+
+
 def test_alpha_clip_pass_leaves_alpha_meshlets_alone(capi, orc):
     """the stand-alone clip pass after a raster with a material table: alpha-tested meshlets were clipped (with the test) by the
     raster itself, so the pass must not draw their clipped triangles again without the test"""
