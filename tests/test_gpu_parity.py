@@ -1543,7 +1543,7 @@ def test_alpha_discard_random_triangles(capi, orc):
     """fuzz: meshes of random triangles around and through the camera (slivers, sub-pixel and screen-filling ones, vertices behind
     the near plane, uv from tiny to huge), random images (with / without mip chains, RGBA8 / R8), random sampler modes and cutoffs:
     the CUDA raster's image equals the oracle's bit for bit — small path, whole-warp path, clip path and level selection under
-    inputs no scene generator produces"""
+    inputs no scene generator produces.  The plain raster (no table) is checked on the same triangles first."""
     from oxylus_b200 import capi as capi_mod
     from tests.test_oracle_alpha import material
 
@@ -1585,12 +1585,15 @@ def test_alpha_discard_random_triangles(capi, orc):
         assert ((plain & 0xFFFFFFFF) != 0xFFFFFFFF).sum() > 200, seed
         discarding += int(not np.array_equal(ref, plain))
         ctx = make_ctx(capi, sc)
-        dev, ptrs = tab.device_images(ctx)
-        ctx.set_materials(mats, dev, smp)
         vis_dev = ctx.alloc(w * h * 8)
         ctx.clear_visbuffer(vis_dev, w, h)
         ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
         ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
+        ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)  # no table yet: the plain raster on the same triangles
+        np.testing.assert_array_equal(ctx.download(vis_dev, np.uint64, w * h).reshape(h, w), plain, err_msg=f"seed {seed} (plain)")
+        dev, ptrs = tab.device_images(ctx)
+        ctx.set_materials(mats, dev, smp)
+        ctx.clear_visbuffer(vis_dev, w, h)
         ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
         got = ctx.download(vis_dev, np.uint64, w * h).reshape(h, w)
         np.testing.assert_array_equal(got, ref, err_msg=f"seed {seed}")
