@@ -416,6 +416,10 @@ typedef struct OxcMaterialTable {
   const OxcSamplerDesc* samplers;  /* host; may be NULL: every sampler_index then means linear, linear, repeat */
   uint32_t sampler_count;
 } OxcMaterialTable;
+OXC_STATIC_ASSERT(sizeof(OxcMaterial) == 56, "Material");            /* SceneGPU.hpp:67-82 */
+OXC_STATIC_ASSERT(sizeof(OxcAlphaImage) == 24, "AlphaImage");
+OXC_STATIC_ASSERT(sizeof(OxcSamplerDesc) == 20, "SamplerDesc");
+OXC_STATIC_ASSERT(sizeof(OxcMaterialTable) == 48, "MaterialTable");
 /* Copies the tables (the image texels stay where they are).  table == NULL or material_count == 0 switches the test off again.
  * OXC_E_INVALID when a material with HasAlbedoImage names an image outside the table or an image is malformed.  A mesh instance
  * whose material_index lies outside the table is rasterised as opaque and raises OXC_STATUS_BAD_MATERIAL. */

@@ -52,6 +52,10 @@ def test_struct_sizes_match_reference_layouts():
     assert C.sizeof(abi.CreateInfo) == 32 and C.sizeof(abi.SceneDesc) == 64
     assert abi.MESH_DT.fields["bounds"][1] == 40 and abi.MESH_LOD_DT.fields["error"][1] == 60
     assert abi.MESHLET_BOUNDS_DT.fields["aabb_extent"][1] == 8 and abi.MESHLET_BOUNDS_DT.fields["cone_cutoff"][1] == 15
+    # Material (SceneGPU.hpp:67-82, 56 B: flags at 20, albedo_image_index at 28, uv_size at 48) and the tables of oxc_set_materials
+    assert abi.MATERIAL_DT.itemsize == 56 and abi.MATERIAL_DT.fields["flags"][1] == 20 and abi.MATERIAL_DT.fields["alpha_cutoff"][1] == 18
+    assert abi.MATERIAL_DT.fields["albedo_image_index"][1] == 28 and abi.MATERIAL_DT.fields["uv_size"][1] == 48
+    assert abi.ALPHA_IMAGE_DT.itemsize == 24 and abi.SAMPLER_DT.itemsize == 20 and C.sizeof(abi.MaterialTable) == 48
 
 
 def test_hiz_extent_and_layout():
