@@ -99,11 +99,20 @@ OXC_DI void alpha_interpolate(const AlphaTri& t, long long e0, long long e1, lon
   v = fa(fa(fm(l0, t.v[0]), fm(l1, t.v[1])), fm(l2, t.v[2]));
 }
 
+// alpha_keep is called from five places of k_raster_alpha (small / whole-warp / clipped paths); inlined everywhere the kernel was
+// 27 k instructions.  One out-of-line copy keeps it at a size the instruction cache can hold; the call costs nothing next to the
+// fetches.  (Host builds of this header — emulated library, tests — just inline it.)
+#ifdef __CUDACC__
+#define OXC_DNI __device__ __noinline__
+#else
+#define OXC_DNI inline
+#endif
+
 // true = the fragment at pixel (px, py) survives the alpha test (visbuffer_encode.slang:62-64 with the comparison negated).
 // e0..e2 = the raster's edge-function values at the sample, ex / ey = their increments per pixel in x / y (from the TriSetup).
 // Images with a mip chain (or different mag / min filters) select the level from the fine quad differences of uv (oracle spec 4).
-OXC_DI bool alpha_keep(const AlphaMaterial& m, const AlphaTri& t, int px, int py, long long e0, long long e1, long long e2, const long long ex[3],
-                       const long long ey[3]) {
+OXC_DNI bool alpha_keep(const AlphaMaterial& m, const AlphaTri& t, int px, int py, long long e0, long long e1, long long e2, const long long ex[3],
+                        const long long ey[3]) {
   float u, v, a;
   alpha_interpolate(t, e0, e1, e2, u, v);
   if (m.levels <= 1u && m.mag_filter == m.min_filter) {
