@@ -425,6 +425,16 @@ OXC_STATIC_ASSERT(sizeof(OxcMaterialTable) == 48, "MaterialTable");
  * whose material_index lies outside the table is rasterised as opaque and raises OXC_STATUS_BAD_MATERIAL. */
 int oxc_set_materials(OxcContext* ctx, const OxcMaterialTable* table, void* stream);
 
+/* RENDER_OVERDRAW of the encode pass (visbuffer_encode.slang:15,68-70, visbuffer_encode_ms.slang:189-191; MainGeometryContext::
+ * draw_overdraw / overdraw_attachment, RendererInstance.cpp:649-679,771-776): overdraw[pixel] += 1 for every fragment of this pass's
+ * survivors the fragment shader reaches its atomic with — covered sample, depth inside [0, 1], not discarded by the alpha test (table
+ * of oxc_set_materials, if any).  The depth comparison plays no part (the shader's side effect and discard put it after the shader).
+ * A separate launch next to oxc_raster_visbuffer (same arguments, R32UI counter image instead of the vis buffer); the image is
+ * accumulated into: clear it once per frame (oxc_clear_overdraw == the reference's vis_clear_pass, which clears both images). */
+int oxc_raster_overdraw(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width, uint32_t height,
+                        uint32_t* overdraw_dev, void* stream);
+int oxc_clear_overdraw(OxcContext* ctx, uint32_t* overdraw_dev, uint32_t width, uint32_t height, void* stream);
+
 /* Stand-alone clip pass: walks the pass's survivors again and clips / draws exactly the triangles described above.
  * oxc_raster_visbuffer does this by itself since round 2 (it queues those triangles while it rasterises), so a host only needs
  * this entry point after a raster that ran with the queue exhausted (OXC_STATUS_CLIP_OVERFLOW); drawing a triangle twice is

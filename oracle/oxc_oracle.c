@@ -694,6 +694,9 @@ static int alpha_material_setup(const OxcMaterialTable* tab, uint32_t material_i
   return 1;
 }
 
+/* non-NULL while orc_raster_overdraw runs: fragments are counted into this W x H image instead of being written to the vis buffer */
+static __thread uint32_t* tl_overdraw = NULL;
+
 static void raster_triangle_uv(const float clip[3][4], const float (*uv)[2], const OrcAlphaMaterial* am, uint32_t data, uint32_t W,
                                uint32_t H, uint64_t* vis);
 static void raster_triangle(const float clip[3][4], uint32_t data, uint32_t W, uint32_t H, uint64_t* vis) {
@@ -754,6 +757,7 @@ static void raster_triangle_uv(const float clip[3][4], const float (*uv)[2], con
         const float uvo[3][2] = {{uv[0][0], uv[0][1]}, {uv[2][0], uv[2][1]}, {uv[1][0], uv[1][1]}};
         if (!alpha_keep_fragment(am, px, py, e, ex, ey, rwo, uvo)) continue;
       }
+      if (tl_overdraw) { tl_overdraw[(size_t)py * W + (size_t)px] += 1u; continue; } /* RENDER_OVERDRAW, visbuffer_encode.slang:68-70 */
       uint32_t zbits = f2bits(zz);
       if (zbits == 0x80000000u) zbits = 0u; /* -0.0 -> +0.0 so unsigned order == depth order */
       uint64_t v = ((uint64_t)zbits << 32) | (uint64_t)data;
@@ -1056,6 +1060,21 @@ void orc_raster_visbuffer_alpha(const OrcScene* scene, const OxcMeshletInstance*
   }
   if (triangles_rasterised) *triangles_rasterised += ntri;
   if (alpha_tested_triangles) *alpha_tested_triangles += nalpha;
+}
+
+/* The encode pass's overdraw counter (visbuffer_encode.slang:15,68-70 / visbuffer_encode_ms.slang:189-191, RENDER_OVERDRAW;
+ * MainGeometryContext::draw_overdraw, RendererInstance.cpp:771-776): overdraw[pixel] += 1 for every fragment the fragment shader
+ * reaches its atomic with — covered sample (raster spec steps 1-5), depth inside [0, 1] (near / far clipping), not discarded by the
+ * alpha test.  The depth COMPARISON plays no part: the shader has a side effect and a discard and declares no early fragment
+ * tests, so the test runs after it; the counter is how many triangles were shaded at the pixel, not how many won.
+ * table may be NULL (no material is alpha tested).  overdraw is accumulated into (the reference clears it with the vis buffer,
+ * RendererInstance.cpp:649-679). */
+void orc_raster_overdraw(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, const uint32_t* visible_indices,
+                         uint32_t pass_first, uint32_t pass_count, const OxcCullCamera* cam, uint32_t width, uint32_t height,
+                         uint32_t* overdraw, const OxcMaterialTable* table) {
+  tl_overdraw = overdraw;
+  orc_raster_visbuffer_alpha(scene, meshlet_instances, visible_indices, pass_first, pass_count, cam, 0, width, height, NULL, table, NULL, NULL);
+  tl_overdraw = NULL;
 }
 
 void orc_resolve_visbuffer(const uint64_t* vis, uint32_t width, uint32_t height, uint32_t* vis32, float* depth) {

@@ -150,6 +150,11 @@ void orc_raster_visbuffer_alpha(const OrcScene* scene, const OxcMeshletInstance*
                                 const OxcCullCamera* cam, uint32_t id_base, uint32_t width, uint32_t height, uint64_t* vis,
                                 const OxcMaterialTable* table, uint64_t* triangles_rasterised, uint64_t* alpha_tested_triangles);
 
+/* RENDER_OVERDRAW of the encode pass (visbuffer_encode.slang:68-70): += 1 per shaded fragment (specification in oxc_oracle.c) */
+void orc_raster_overdraw(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, const uint32_t* visible_indices,
+                         uint32_t pass_first, uint32_t pass_count, const OxcCullCamera* cam, uint32_t width, uint32_t height,
+                         uint32_t* overdraw, const OxcMaterialTable* table /* may be NULL */);
+
 /* passes/cull_meshlets_hpb.slang:27-99 + cull.slang:137-166 test_vsm_page.  hpb: levels of (layers x s x s) bytes. */
 void orc_cull_meshlets_hpb(const OrcScene* scene, const OxcMeshletInstance* meshlet_instances, const OxcCullCamera* cam,
                            const OxcVirtualClipmap* clipmaps, const uint32_t* dirty_flags, uint32_t clipmap_count,

@@ -239,6 +239,13 @@ def raster_alpha(hs, mi, visible, first, count, cam, vis, table: MaterialTable, 
     return int(ntri.value), int(nalpha.value)
 
 
+def raster_overdraw(hs, mi, visible, first, count, cam, overdraw, table=None):
+    """RENDER_OVERDRAW of the encode pass: overdraw[h, w] (uint32) += 1 per shaded fragment of the pass's survivors"""
+    h, w = overdraw.shape
+    lib().orc_raster_overdraw(hs.ref, _p(mi), _p(visible), C.c_uint32(first), C.c_uint32(count), _p(cam), C.c_uint32(w), C.c_uint32(h),
+                              _p(overdraw), C.byref(table.ref) if table is not None else None)
+
+
 def alpha_sample(texels, fmt, u, v, sampler=None, level=0):
     """one level of an image (texels: one array, or the list of its levels) through the sampler's min filter / address modes"""
     lv = texels if isinstance(texels, (list, tuple)) else [texels]

@@ -18,7 +18,7 @@ SYMBOLS = [
     "oxc_last_error", "oxc_kernel_launch_count", "oxc_version", "oxc_create", "oxc_destroy", "oxc_set_scene",
     "oxc_update_transforms", "oxc_reset_visibility_mask", "oxc_clear_hiz", "oxc_set_shard", "oxc_set_shard_auto", "oxc_cull_meshes",
     "oxc_cull_meshlets", "oxc_build_hiz", "oxc_build_hiz_packed", "oxc_build_hiz_mip0_packed", "oxc_build_hiz_from_mip0", "oxc_cull_triangles", "oxc_cull_triangles_small_primitive", "oxc_clear_visbuffer",
-    "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_set_materials", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
+    "oxc_raster_visbuffer", "oxc_raster_visbuffer_clip_pass", "oxc_set_materials", "oxc_raster_overdraw", "oxc_clear_overdraw", "oxc_resolve_visbuffer", "oxc_merge_depth", "oxc_clear_visbuffer_with_depth", "oxc_cull_meshlets_multiview", "oxc_cull_meshlets_hpb", "oxc_cull_terrain",
     "oxc_decode_visbuffer", "oxc_build_hpb", "oxc_mark_visible_pages",
     "oxc_get_outputs", "oxc_check_status", "oxc_mark_hiz_dirty", "oxc_bind_camera_buffer", "oxc_load_camera", "oxc_debug_stats_ptr",
     "oxc_mgpu_get_unique_id", "oxc_mgpu_init", "oxc_mgpu_init_with_comm", "oxc_mgpu_shutdown", "oxc_mgpu_info", "oxc_mgpu_exchange_hiz",
@@ -72,6 +72,8 @@ def load(build_if_missing=True):
     lib.oxc_raster_visbuffer.argtypes = [vp, vp, u32, u32, u32, vp, i32, vp]
     lib.oxc_raster_visbuffer_clip_pass.argtypes = [vp, vp, u32, u32, u32, vp, vp]
     lib.oxc_set_materials.argtypes = [vp, C.POINTER(abi.MaterialTable), vp]
+    lib.oxc_raster_overdraw.argtypes = [vp, vp, u32, u32, u32, vp, vp]
+    lib.oxc_clear_overdraw.argtypes = [vp, vp, u32, u32, vp]
     lib.oxc_resolve_visbuffer.argtypes = [vp, vp, u32, u32, vp, vp, vp]
     lib.oxc_merge_depth.argtypes = [vp, vp, vp, u32, u32, vp]
     lib.oxc_clear_visbuffer_with_depth.argtypes = [vp, vp, vp, u32, u32, vp]
@@ -353,6 +355,12 @@ class Context:
         (device pointer, width, height, format); `samplers` an abi.SAMPLER_DT array or None (linear + repeat)"""
         t, keep = material_table(materials, images, samplers)
         _check(self.lib.oxc_set_materials(self.h, None if t is None else C.byref(t), self.stream), "oxc_set_materials")
+
+    def raster_overdraw(self, cam, flags, w, h, overdraw_dev):
+        _check(self.lib.oxc_raster_overdraw(self.h, _ptr(cam), flags, w, h, _ptr(overdraw_dev), self.stream), "oxc_raster_overdraw")
+
+    def clear_overdraw(self, overdraw_dev, w, h):
+        _check(self.lib.oxc_clear_overdraw(self.h, _ptr(overdraw_dev), w, h, self.stream), "oxc_clear_overdraw")
 
     def raster_visbuffer_clip_pass(self, cam, flags, w, h, vis_dev):
         _check(self.lib.oxc_raster_visbuffer_clip_pass(self.h, _ptr(cam), flags, w, h, _ptr(vis_dev), self.stream),

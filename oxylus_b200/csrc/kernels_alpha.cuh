@@ -21,6 +21,7 @@ struct AlphaParams {
   uint32_t* masked_list;
   OxcDispatchIndirectCommand* opaque_cmd; // .x = entries of opaque_list (zeroed before the launch)
   OxcDispatchIndirectCommand* masked_cmd;
+  uint32_t* overdraw;                     // k_raster_alpha<true>: the W x H fragment counter (RENDER_OVERDRAW)
 };
 
 OXC_DI bool alpha_material_of(const AlphaParams& a, const TriParams& p, uint32_t gid, uint32_t id_base, uint32_t& mat) {
@@ -61,29 +62,37 @@ __global__ void __launch_bounds__(256) k_partition_alpha(const __grid_constant__
   }
 }
 
-// shade one sample: coverage + depth exactly as shade_pixel (oxc_raster_core.cuh), then the alpha test, then the packed max
+// shade one sample: coverage + depth exactly as shade_pixel (oxc_raster_core.cuh), then the alpha test, then the packed max —
+// or, OVERDRAW, the fragment counter of the encode pass (visbuffer_encode.slang:68-70: the shader's atomic comes after the discard
+// and before any depth comparison)
+template <bool OVERDRAW>
 OXC_DI void shade_pixel_alpha(const TriSetup& s, const AlphaMaterial& m, const AlphaTri& t, int px, int py, uint32_t data,
-                              unsigned long long* vis, uint32_t W) {
+                              unsigned long long* vis, uint32_t* overdraw, uint32_t W) {
   const int sx = px * 256 + 128, sy = py * 256 + 128;
   const long long e0 = orient2d(s.bx, s.by, s.cx, s.cy, sx, sy), e1 = orient2d(s.cx, s.cy, s.ax, s.ay, sx, sy),
                   e2 = orient2d(s.ax, s.ay, s.bx, s.by, sx, sy);
   if ((e0 - (s.bias & 1)) < 0 || (e1 - ((s.bias >> 1) & 1)) < 0 || (e2 - ((s.bias >> 2) & 1)) < 0) return;
   const float zz = fa(fa(s.za, fm((float)e1, s.dzb)), fm((float)e2, s.dzc));
   if (!(zz >= 0.0f && zz <= 1.0f)) return;
-  {  // discard (visbuffer_encode.slang:62-64); edge-function increments per pixel as in raster_small (oxc_raster_core.cuh)
+  if (m.texels) {  // discard (visbuffer_encode.slang:62-64); edge-function increments per pixel as in raster_small (oxc_raster_core.cuh)
     const long long ex[3] = {-(long long)(s.cy - s.by) * 256, -(long long)(s.ay - s.cy) * 256, -(long long)(s.by - s.ay) * 256};
     const long long ey[3] = {(long long)(s.cx - s.bx) * 256, (long long)(s.ax - s.cx) * 256, (long long)(s.bx - s.ax) * 256};
     if (!alpha_keep(m, t, px, py, e0, e1, e2, ex, ey)) return;
+  }
+  if (OVERDRAW) {
+    atomicAdd(overdraw + (size_t)py * W + px, 1u);
+    return;
   }
   uint32_t zb = __float_as_uint(zz);
   zb = zb == 0x80000000u ? 0u : zb;
   atomicMax(vis + (size_t)py * W + px, ((unsigned long long)zb << 32) | data);
 }
 
+template <bool OVERDRAW>
 OXC_DI void raster_box_alpha(const TriSetup& s, const AlphaMaterial& m, const AlphaTri& t, uint32_t data, unsigned long long* vis,
-                             uint32_t W) {
+                             uint32_t* overdraw, uint32_t W) {
   for (int py = s.py0; py <= s.py1; py++)
-    for (int px = s.px0; px <= s.px1; px++) shade_pixel_alpha(s, m, t, px, py, data, vis, W);
+    for (int px = s.px0; px <= s.px1; px++) shade_pixel_alpha<OVERDRAW>(s, m, t, px, py, data, vis, overdraw, W);
 }
 
 constexpr int ALPHA_THREADS = 128, ALPHA_WARPS = ALPHA_THREADS / 32;
@@ -95,12 +104,16 @@ struct AlphaBigRecord {
   uint32_t data;
 };
 
+// OVERDRAW = false: the alpha-tested meshlets of the split (a.masked_list).  OVERDRAW = true: EVERY survivor of the pass (opaque
+// materials skip the test; a.materials may be null), fragments counted into a.overdraw instead of drawn.
+template <bool OVERDRAW>
 __global__ void __launch_bounds__(ALPHA_THREADS) k_raster_alpha(const __grid_constant__ TriParams p, const __grid_constant__ AlphaParams a) {
   __shared__ float4 clip_all[ALPHA_WARPS][OXC_MESHLET_MAX_VERTICES];
   __shared__ float2 uv_all[ALPHA_WARPS][OXC_MESHLET_MAX_VERTICES];
   __shared__ AlphaBigRecord big_all[ALPHA_WARPS];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const uint32_t count = a.masked_cmd->x;
+  const uint32_t first = OVERDRAW ? (p.late ? p.vis->early_visible_meshlet_instances : 0u) : 0u; // cull_triangles.slang:34-37
+  const uint32_t count = OVERDRAW ? p.tri_cmd->x : a.masked_cmd->x;
   const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
   float4* clip_s = clip_all[warp];
   float2* uv_s = uv_all[warp];
@@ -108,11 +121,18 @@ __global__ void __launch_bounds__(ALPHA_THREADS) k_raster_alpha(const __grid_con
   uint32_t kept = 0;
   for (uint32_t g = blockIdx.x * ALPHA_WARPS + warp; g < count; g += gridDim.x * ALPHA_WARPS) {
     // ---- the meshlet: pointer chase, vertices -> clip space (visbuffer_encode.slang:27-38), uv (scene.slang:355-361) ----
-    const uint32_t gid = a.masked_list[g];
+    const uint32_t gid = OVERDRAW ? __ldg(&p.visible_indices[first + g]) : a.masked_list[g];
     const uint2 mi = __ldg(reinterpret_cast<const uint2*>(p.meshlet_instances) + (gid - id_base));
     const InstGeom* gm = p.geom + mi.x;
     const InstCull* ic = p.inst + mi.x;
-    const AlphaMaterial m = a.materials[__ldg(&a.mesh_instances[mi.x].material_index)]; // in range: k_partition_alpha checked it
+    AlphaMaterial m;
+    if (OVERDRAW) { // any material: outside the table or without an image = opaque
+      const uint32_t mat = __ldg(&a.mesh_instances[mi.x].material_index);
+      m.texels = nullptr;
+      if (a.materials && mat < a.material_count) m = a.materials[mat];
+    } else {
+      m = a.materials[__ldg(&a.mesh_instances[mi.x].material_index)]; // in range and with an image: k_partition_alpha checked it
+    }
     const uint4 ml = __ldg(reinterpret_cast<const uint4*>(gm->meshlets + mi.y));
     const uint32_t vertex_count = min(ml.z, (uint32_t)OXC_MESHLET_MAX_VERTICES), tri_count = min(ml.w, (uint32_t)OXC_MESHLET_MAX_PRIMITIVES);
     const float4 r0 = __ldg(&ic->mvp_row[0]), r1 = __ldg(&ic->mvp_row[1]), r2 = __ldg(&ic->mvp_row[2]), r3 = __ldg(&ic->mvp_row[3]);
@@ -149,7 +169,7 @@ __global__ void __launch_bounds__(ALPHA_THREADS) k_raster_alpha(const __grid_con
                                       to_screen(c2, p.f_width, p.f_height), p.width, p.height, s);
             if (why == TRI_DRAW) {
               big = (s.px1 - s.px0 + 1) * (s.py1 - s.py0 + 1) > RASTER_BIG_PIXELS;
-              if (!big) raster_box_alpha(s, m, at, data, p.visbuf, p.width);
+              if (!big) raster_box_alpha<OVERDRAW>(s, m, at, data, p.visbuf, a.overdraw, p.width);
             } else if (why == TRI_INVALID_VERTEX) { // a vertex at w <= 0 / beyond the snap range: clipped like the plain raster does,
               ClipVertUV poly[2][12];                // with uv carried through the cuts (alpha spec step 3)
               int cur;
@@ -163,7 +183,7 @@ __global__ void __launch_bounds__(ALPHA_THREADS) k_raster_alpha(const __grid_con
                   continue;
                 AlphaTri pt;
                 alpha_tri_setup(q0.c, q1.c, q2.c, q0.u, q0.v, q1.u, q1.v, q2.u, q2.v, pt);
-                raster_box_alpha(ps, m, pt, data, p.visbuf, p.width);
+                raster_box_alpha<OVERDRAW>(ps, m, pt, data, p.visbuf, a.overdraw, p.width);
               }
             }
           }
@@ -182,7 +202,7 @@ __global__ void __launch_bounds__(ALPHA_THREADS) k_raster_alpha(const __grid_con
         for (int ty = b.s.py0; ty <= b.s.py1; ty += 4)
           for (int tx = b.s.px0; tx <= b.s.px1; tx += 8) {
             const int px = tx + lx, py = ty + ly;
-            if (px <= b.s.px1 && py <= b.s.py1) shade_pixel_alpha(b.s, m, b.t, px, py, b.data, p.visbuf, p.width);
+            if (px <= b.s.px1 && py <= b.s.py1) shade_pixel_alpha<OVERDRAW>(b.s, m, b.t, px, py, b.data, p.visbuf, a.overdraw, p.width);
           }
       }
     }
@@ -190,7 +210,7 @@ __global__ void __launch_bounds__(ALPHA_THREADS) k_raster_alpha(const __grid_con
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) kept += __shfl_xor_sync(0xffffffffu, kept, o);
-  if (lane == 0 && kept) atomicAdd(p.tri_counter, (unsigned long long)kept);
+  if (!OVERDRAW && lane == 0 && kept) atomicAdd(p.tri_counter, (unsigned long long)kept); // the counter pass draws nothing
 }
 
 } // namespace oxc

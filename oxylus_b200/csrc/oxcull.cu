@@ -772,11 +772,36 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
   k_raster_clip_queue<<<c->sm_count, 128, 0, s>>>(p); // the triangles the plain rules drop (usually none: exits at once)
   LAUNCHED();
   if (c->alpha_active) {
-    k_raster_alpha<<<c->sm_count * 8, ALPHA_THREADS, 0, s>>>(p, ap); // the alpha-tested meshlets, one warp each
+    k_raster_alpha<false><<<c->sm_count * 8, ALPHA_THREADS, 0, s>>>(p, ap); // the alpha-tested meshlets, one warp each
     LAUNCHED();
   }
   k_raster_big<<<c->sm_count * 8, 256, 0, s>>>(p); // the deferred large triangles, one warp per <= 64x32-pixel chunk
   LAUNCHED();
+  return OXC_OK;
+}
+
+// RENDER_OVERDRAW of the encode pass (visbuffer_encode.slang:15,68-70; MainGeometryContext::draw_overdraw): a separate launch of the
+// general per-meshlet raster with the fragment counter as its sink — the tuned raster kernels know nothing about it
+int oxc_raster_overdraw(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t w, uint32_t h, uint32_t* overdraw, void* stream) {
+  if (!c || !cam || !overdraw) return fail(OXC_E_INVALID, "null argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaSetDevice(c->device));
+  TriParams p{};
+  int rc = tri_common(c, cam, flags, s, &p);
+  if (rc != OXC_OK) return rc;
+  p.width = w; p.height = h; p.f_width = (float)w; p.f_height = (float)h;
+  AlphaParams ap{};
+  ap.mesh_instances = c->d_mesh_instances; ap.overdraw = overdraw;
+  if (c->alpha_active) { ap.materials = c->d_alpha_materials; ap.material_count = c->alpha_material_count; }
+  k_raster_alpha<true><<<c->sm_count * 8, ALPHA_THREADS, 0, s>>>(p, ap);
+  LAUNCHED();
+  return OXC_OK;
+}
+
+int oxc_clear_overdraw(OxcContext* c, uint32_t* overdraw, uint32_t w, uint32_t h, void* stream) {
+  if (!c || !overdraw) return fail(OXC_E_INVALID, "null argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemsetAsync(overdraw, 0, (size_t)w * h * 4, static_cast<cudaStream_t>(stream)));
   return OXC_OK;
 }
 

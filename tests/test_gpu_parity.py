@@ -1608,6 +1608,79 @@ def test_alpha_discard_random_triangles(capi, orc):
     assert discarding >= n_seeds // 2  # (a random image can lie entirely above or below the cutoff)
 
 
+def test_overdraw_counter_parity(capi, orc):
+    """oxc_raster_overdraw (RENDER_OVERDRAW of the encode pass, visbuffer_encode.slang:68-70): the fragment counter of both passes of
+    a two-pass frame, without and with a material table, equals the oracle's counter pixel for pixel; the frame's own outputs are
+    untouched by the extra launches; clipped screen-filling triangles count too"""
+    from tests.test_oracle_alpha import checker, material, textured_ground
+
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    sc.mesh_instances["material_index"] = np.arange(sc.mesh_instance_count) % 4
+    w, h = sc.width, sc.height
+    for with_table in (False, True):
+        hs = orc.HostScene(sc)
+        ctx = make_ctx(capi, sc)
+        tab, ptrs = _alpha_tables(capi, orc, ctx) if with_table else (None, [])
+        vis_dev, occ_dev, over_dev = ctx.alloc(w * h * 8), ctx.alloc(w * h * 4), ctx.alloc(w * h * 4)
+        ctx.upload(occ_dev, sc.occluder_depth)
+        mask_ref = np.zeros(ctx.out.visibility_mask_words, dtype=np.uint32)
+        for f in range(2):
+            cam = sc.camera(2.0 * f)
+            ref = orc.frame(hs, cam, w, h, mask_ref, sc.occluder_depth, materials=tab)
+            e, l = ref["early"], ref["late"]
+            want = np.zeros((h, w), dtype=np.uint32)
+            orc.raster_overdraw(hs, ref["meshlet_instances"], ref["visible"], 0, e, cam, want, tab)
+            orc.raster_overdraw(hs, ref["meshlet_instances"], ref["visible"], e, l, cam, want, tab)
+            # the frame, with the counter launched after each raster
+            ctx.clear_visbuffer(vis_dev, w, h)
+            ctx.clear_overdraw(over_dev, w, h)
+            ctx.clear_hiz()
+            ctx.merge_depth(vis_dev, occ_dev, w, h)
+            ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+            ctx.cull_meshlets(cam, abi.CULL_TEST_ALL, True)
+            ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL, w, h, vis_dev)
+            ctx.raster_overdraw(cam, abi.CULL_TEST_ALL, w, h, over_dev)
+            ctx.build_hiz_packed(vis_dev, w, h)
+            ctx.cull_meshlets(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, True)
+            ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, vis_dev)
+            ctx.raster_overdraw(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, over_dev)
+            np.testing.assert_array_equal(ctx.download(over_dev, np.uint32, w * h).reshape(h, w), want, err_msg=f"table {with_table} frame {f}")
+            np.testing.assert_array_equal(ctx.download(vis_dev, np.uint64, w * h).reshape(h, w), ref["vis64"])
+            np.testing.assert_array_equal(ctx.mask(), mask_ref)
+            assert ctx.raster_triangle_count() == ref["ntri_early"] + ref["ntri_late"] and ctx.check_status() == 0
+            assert want.max() >= 2 and (want > 0).sum() >= ((ref["vis64"] & 0xFFFFFFFF) != 0xFFFFFFFF).sum()
+        for d in ptrs + [vis_dev, occ_dev, over_dev]:
+            ctx.free(d)
+        ctx.close()
+    # clipped, screen-filling triangles (whole-warp path) with a checker material
+    sc = textured_ground(1, width=640, height=360)
+    sc.mesh_instances["material_index"] = 0
+    hs = orc.HostScene(sc)
+    cam = sc.camera()
+    w, h = sc.width, sc.height
+    tex = checker(4, 1, rgba=False)
+    mats = np.array([material(image=0, cutoff=0.5)], dtype=abi.MATERIAL_DT)
+    tab = orc.MaterialTable(mats, [(tex, abi.IMAGE_R8_UNORM)])
+    mi, vis, _ = orc.cull_meshes(hs, cam, abi.CULL_TEST_ALL)
+    visible, cmd = orc.cull_meshlets(hs, mi, vis, cam)
+    visible = visible[: int(cmd["x"][0])]
+    want = np.zeros((h, w), dtype=np.uint32)
+    orc.raster_overdraw(hs, mi, visible, 0, len(visible), cam, want, tab)
+    assert 0.05 * want.size < (want > 0).sum() < 0.45 * want.size
+    ctx = make_ctx(capi, sc)
+    dev, ptrs = tab.device_images(ctx)
+    ctx.set_materials(mats, dev)
+    over_dev = ctx.alloc(w * h * 4)
+    ctx.clear_overdraw(over_dev, w, h)
+    ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
+    ctx.cull_meshlets(cam, abi.CULL_TEST_FRUSTUM, False)
+    ctx.raster_overdraw(cam, abi.CULL_TEST_ALL, w, h, over_dev)
+    np.testing.assert_array_equal(ctx.download(over_dev, np.uint32, w * h).reshape(h, w), want)
+    for d in ptrs + [over_dev]:
+        ctx.free(d)
+    ctx.close()
+
+
 def test_alpha_clip_pass_leaves_alpha_meshlets_alone(capi, orc):
     """the stand-alone clip pass after a raster with a material table: alpha-tested meshlets were clipped (with the test) by the
     raster itself, so the pass must not draw their clipped triangles again without the test"""

@@ -349,6 +349,63 @@ def test_alpha_through_the_clip_path(orc):
     assert (a ^ b).sum() < 0.01 * a.size            # the two tessellations disagree on cell-boundary pixels only
 
 
+def test_overdraw_counter_hand_cases(orc):
+    """RENDER_OVERDRAW (visbuffer_encode.slang:68-70): every shaded fragment counts, whatever the depth test would say; discarded
+    fragments do not.  The ground plane drawn twice (two mesh instances of the same mesh, the second one lower) gives 2 where both
+    cover a pixel — although only one of them wins the vis buffer — and the checker material removes its share."""
+    sc1 = textured_ground(8)
+    xf = np.tile(np.eye(4, dtype=np.float32).reshape(1, 16), (2, 1))
+    xf[1, 13] = -0.5  # the second instance half a unit lower (column-major translation y)
+    from tests.test_oracle_alpha import textured_ground as _tg  # noqa: F401  (same module: keeps the helper's name searchable)
+    xs = np.linspace(-50.0, 50.0, 9)
+    zs = np.linspace(10.0, -100.0, 9)
+    gx, gz = np.meshgrid(xs, zs, indexing="ij")
+    pos = np.stack([gx, np.full_like(gx, -1.0), gz], axis=2).reshape(-1, 3).astype(np.float32)
+    uv = np.stack([gx / 10.0, gz / 10.0], axis=2).reshape(-1, 2).astype(np.float32)
+    i, j = np.meshgrid(np.arange(8), np.arange(8), indexing="ij")
+    a, b, c, d = i * 9 + j, (i + 1) * 9 + j, i * 9 + j + 1, (i + 1) * 9 + j + 1
+    tris = np.stack([a, d, c, a, b, d], axis=2).reshape(-1, 3).astype(np.uint32)
+    built = [capi.BuiltMesh(pos, [(tris.reshape(-1), 0.0)], texcoords=uv)]
+    sc = capi.assemble_scene(built, np.array([0, 0]), xf, sc1.width, sc1.height)
+    sc.mesh_instances["material_index"] = [0, 1]
+    hs, cam, mi, visible = _survivors(orc, sc)
+    w, h = sc.width, sc.height
+    plain = orc.clear_visbuffer(w, h)
+    orc.raster_clip(hs, mi, visible, 0, len(visible), cam, plain)
+    over = np.zeros((h, w), dtype=np.uint32)
+    orc.raster_overdraw(hs, mi, visible, 0, len(visible), cam, over)
+    covered = (plain & 0xFFFFFFFF) != 0xFFFFFFFF
+    assert set(np.unique(over)) == {0, 1, 2}
+    np.testing.assert_array_equal(over > 0, covered)       # a pixel is shaded at least once iff something was drawn there
+    assert (over == 2).sum() > 0.5 * covered.sum()         # both planes cover most of the lower half of the screen
+    # per instance: the counter is the sum of the two single-instance coverages
+    total = np.zeros((h, w), dtype=np.uint32)
+    for inst in (0, 1):
+        keep = mi["mesh_instance_index"][visible] == inst
+        img = orc.clear_visbuffer(w, h)
+        orc.raster_clip(hs, mi, np.ascontiguousarray(visible[keep]), 0, int(keep.sum()), cam, img)
+        total += ((img & 0xFFFFFFFF) != 0xFFFFFFFF).astype(np.uint32)
+    np.testing.assert_array_equal(over, total)
+    # accumulation: a second call adds the same again
+    orc.raster_overdraw(hs, mi, visible, 0, len(visible), cam, over)
+    np.testing.assert_array_equal(over, 2 * total)
+    # with the checker material on instance 1, its discarded fragments are not counted
+    tab = orc.MaterialTable([material(), material(image=0, cutoff=0.5)], [(checker(4, 1, rgba=False), abi.IMAGE_R8_UNORM)],
+                            np.array([abi.sampler(abi.FILTER_NEAREST, abi.FILTER_NEAREST)], dtype=abi.SAMPLER_DT))
+    over_a = np.zeros((h, w), dtype=np.uint32)
+    orc.raster_overdraw(hs, mi, visible, 0, len(visible), cam, over_a, tab)
+    assert (over_a <= total).all() and (over_a >= (total > 0) * 0).all()
+    keep1 = mi["mesh_instance_index"][visible] == 1
+    img1 = orc.clear_visbuffer(w, h)
+    orc.raster_alpha(hs, mi, np.ascontiguousarray(visible[keep1]), 0, int(keep1.sum()), cam, img1, tab)
+    keep0 = ~keep1
+    img0 = orc.clear_visbuffer(w, h)
+    orc.raster_clip(hs, mi, np.ascontiguousarray(visible[keep0]), 0, int(keep0.sum()), cam, img0)
+    expect = ((img0 & 0xFFFFFFFF) != 0xFFFFFFFF).astype(np.uint32) + ((img1 & 0xFFFFFFFF) != 0xFFFFFFFF).astype(np.uint32)
+    np.testing.assert_array_equal(over_a, expect)
+    assert (over_a != total).any()
+
+
 def load_golden_alpha():
     import importlib.util
     import json
