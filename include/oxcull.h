@@ -430,9 +430,13 @@ int oxc_set_materials(OxcContext* ctx, const OxcMaterialTable* table, void* stre
  * survivors the fragment shader reaches its atomic with — covered sample, depth inside [0, 1], not discarded by the alpha test (table
  * of oxc_set_materials, if any).  The depth comparison plays no part (the shader's side effect and discard put it after the shader).
  * A separate launch next to oxc_raster_visbuffer (same arguments, R32UI counter image instead of the vis buffer); the image is
- * accumulated into: clear it once per frame (oxc_clear_overdraw == the reference's vis_clear_pass, which clears both images). */
+ * accumulated into: clear it once per frame (oxc_clear_overdraw == the reference's vis_clear_pass, which clears both images).
+ * after_frame = 0: issued where the reference draws — right after the pass's oxc_raster_visbuffer, the pass's survivor count is the
+ * dispatch command's.  after_frame = 1: issued once the two-pass frame has completed (the command then holds the late count): the
+ * pass's range comes from the visibility record, early [0, E), late [E, E + L) (Hi-Z cull variants only: the plain
+ * oxc_cull_meshlets does not maintain that record). */
 int oxc_raster_overdraw(OxcContext* ctx, const OxcCullCamera* camera, uint32_t cull_flags, uint32_t width, uint32_t height,
-                        uint32_t* overdraw_dev, void* stream);
+                        uint32_t* overdraw_dev, int after_frame, void* stream);
 int oxc_clear_overdraw(OxcContext* ctx, uint32_t* overdraw_dev, uint32_t width, uint32_t height, void* stream);
 
 /* Stand-alone clip pass: walks the pass's survivors again and clips / draws exactly the triangles described above.
@@ -648,6 +652,10 @@ int oxr_update_transforms(OxrRenderer* r, const OxcTransformWorld* transforms, u
 /* Depth laid down by passes outside this path (terrain, RendererInstance.cpp:862-873): a width x height D32F HOST
  * image copied to the device once and merged into every following frame; NULL removes it. */
 int oxr_set_external_depth(OxrRenderer* r, const float* depth_host);
+/* MainGeometryContext::draw_overdraw (RendererInstance.cpp:771-776): the encode pass's fragment counter (oxc_raster_overdraw, both
+ * passes) of the frame that oxr_render / oxr_wait completed last, for the camera it was rendered with; width x height u32 to the
+ * host.  Synchronous; the frame's own outputs are not touched. */
+int oxr_overdraw(OxrRenderer* r, const OxcCullCamera* camera, uint32_t* overdraw_host);
 /* oxc_set_materials on the renderer's context (alpha-tested discard of the vis-buffer encode, visbuffer_encode.slang:54-66);
  * NULL switches it off.  Re-captures the frame graphs: the raster's launch sequence changes with it. */
 int oxr_set_materials(OxrRenderer* r, const OxcMaterialTable* table);

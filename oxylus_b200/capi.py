@@ -24,7 +24,7 @@ SYMBOLS = [
     "oxc_mgpu_get_unique_id", "oxc_mgpu_init", "oxc_mgpu_init_with_comm", "oxc_mgpu_shutdown", "oxc_mgpu_info", "oxc_mgpu_exchange_hiz",
     "oxc_mgpu_exchange_frame", "oxc_mgpu_stage_survivors", "oxc_mgpu_set_survivor_capacity", "oxc_copy", "oxc_sync", "oxc_device_alloc", "oxc_device_free", "oxc_debug_dequantize_half",
     "oxb_last_error", "oxb_build_mesh", "oxb_mesh_blob_size", "oxb_mesh_lod0_meshlet_count", "oxb_mesh_emit", "oxb_mesh_free", "oxb_simplify",
-    "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_set_materials", "oxr_render", "oxr_submit", "oxr_wait",
+    "oxr_create", "oxr_destroy", "oxr_context", "oxr_update", "oxr_update_transforms", "oxr_set_external_depth", "oxr_set_materials", "oxr_overdraw", "oxr_render", "oxr_submit", "oxr_wait",
 ]
 
 
@@ -72,7 +72,7 @@ def load(build_if_missing=True):
     lib.oxc_raster_visbuffer.argtypes = [vp, vp, u32, u32, u32, vp, i32, vp]
     lib.oxc_raster_visbuffer_clip_pass.argtypes = [vp, vp, u32, u32, u32, vp, vp]
     lib.oxc_set_materials.argtypes = [vp, C.POINTER(abi.MaterialTable), vp]
-    lib.oxc_raster_overdraw.argtypes = [vp, vp, u32, u32, u32, vp, vp]
+    lib.oxc_raster_overdraw.argtypes = [vp, vp, u32, u32, u32, vp, i32, vp]
     lib.oxc_clear_overdraw.argtypes = [vp, vp, u32, u32, vp]
     lib.oxc_resolve_visbuffer.argtypes = [vp, vp, u32, u32, vp, vp, vp]
     lib.oxc_merge_depth.argtypes = [vp, vp, vp, u32, u32, vp]
@@ -123,6 +123,7 @@ def load(build_if_missing=True):
     lib.oxr_update_transforms.argtypes = [vp, vp, u32, u32]
     lib.oxr_set_external_depth.argtypes = [vp, vp]
     lib.oxr_set_materials.argtypes = [vp, C.POINTER(abi.MaterialTable)]
+    lib.oxr_overdraw.argtypes = [vp, vp, vp]
     lib.oxr_submit.argtypes = [vp, vp, vp, vp, vp, u32, C.POINTER(C.c_int)]
     lib.oxr_wait.argtypes = [vp, i32, C.POINTER(abi.FrameResult)]
     lib.oxr_render.argtypes = [vp, vp, vp, vp, vp, vp, u32, C.POINTER(abi.FrameResult)]
@@ -356,8 +357,8 @@ class Context:
         t, keep = material_table(materials, images, samplers)
         _check(self.lib.oxc_set_materials(self.h, None if t is None else C.byref(t), self.stream), "oxc_set_materials")
 
-    def raster_overdraw(self, cam, flags, w, h, overdraw_dev):
-        _check(self.lib.oxc_raster_overdraw(self.h, _ptr(cam), flags, w, h, _ptr(overdraw_dev), self.stream), "oxc_raster_overdraw")
+    def raster_overdraw(self, cam, flags, w, h, overdraw_dev, after_frame=False):
+        _check(self.lib.oxc_raster_overdraw(self.h, _ptr(cam), flags, w, h, _ptr(overdraw_dev), int(after_frame), self.stream), "oxc_raster_overdraw")
 
     def clear_overdraw(self, overdraw_dev, w, h):
         _check(self.lib.oxc_clear_overdraw(self.h, _ptr(overdraw_dev), w, h, self.stream), "oxc_clear_overdraw")
@@ -574,6 +575,12 @@ class Renderer:
         """oxr_set_materials (see Context.set_materials)"""
         t, keep = material_table(materials, images, samplers)
         _check(self.lib.oxr_set_materials(self.h, None if t is None else C.byref(t)), "oxr_set_materials")
+
+    def overdraw(self, cam):
+        """oxr_overdraw: the encode pass's fragment counter of the frame rendered last (uint32 [height, width])"""
+        out = np.zeros((self.scene.height, self.scene.width), dtype=np.uint32)
+        _check(self.lib.oxr_overdraw(self.h, _ptr(cam), _ptr(out)), "oxr_overdraw")
+        return out
 
     def set_external_depth(self, depth):
         d = None if depth is None else np.ascontiguousarray(depth, dtype=np.float32)

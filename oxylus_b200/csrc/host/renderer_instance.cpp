@@ -95,7 +95,7 @@ RendererInstance::RendererInstance(int device, const OxcCreateInfo& info, uint32
 
 RendererInstance::~RendererInstance() {
   if (stream_) cudaStreamSynchronize(static_cast<cudaStream_t>(stream_));
-  cudaFree(d_vis64_); cudaFree(d_vis32_); cudaFree(d_depth_); cudaFree(d_occluder_);
+  cudaFree(d_vis64_); cudaFree(d_vis32_); cudaFree(d_depth_); cudaFree(d_occluder_); cudaFree(d_overdraw_);
   if (h_pinned_) cudaFreeHost(h_pinned_);
   if (copy_stream_) cudaStreamSynchronize(static_cast<cudaStream_t>(copy_stream_));
   for (auto& sl : slots_) {
@@ -124,6 +124,24 @@ auto RendererInstance::update(const RendererInstanceUpdateInfo& info) -> int {
 auto RendererInstance::update_transforms(const OxcTransformWorld* transforms, uint32_t first, uint32_t count) -> int {
   if (!ctx_) return OXC_E_STATE;
   return fail(oxc_update_transforms(ctx_, transforms, first, count, stream_));
+}
+
+// MainGeometryContext::draw_overdraw (RendererInstance.cpp:771-776; debug view "Overdraw"): the encode pass's fragment counter for
+// the frame that was rendered last — both passes' survivor lists are still in place, so this runs after the frame, not inside it
+auto RendererInstance::overdraw(const OxcCullCamera& camera, uint32_t* overdraw_host) -> int {
+  if (!ctx_ || !error_.empty()) return OXC_E_STATE;
+  if (!overdraw_host) return OXC_E_INVALID;
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  const size_t px = (size_t)width_ * height_;
+  if (!d_overdraw_ && cudaMalloc(reinterpret_cast<void**>(&d_overdraw_), px * 4) != cudaSuccess) return fail(OXC_E_CUDA);
+  int rc;
+  if ((rc = oxc_bind_camera_buffer(ctx_, nullptr)) != OXC_OK) return fail(rc); // as render(): the camera comes from the argument
+  if ((rc = oxc_clear_overdraw(ctx_, d_overdraw_, width_, height_, s)) != OXC_OK) return fail(rc);
+  if ((rc = oxc_raster_overdraw(ctx_, &camera, OXC_CULL_TEST_ALL, width_, height_, d_overdraw_, /*after_frame=*/1, s)) != OXC_OK) return fail(rc);
+  if ((rc = oxc_raster_overdraw(ctx_, &camera, OXC_CULL_TEST_ALL | OXC_CULL_LATE_PASS, width_, height_, d_overdraw_, /*after_frame=*/1, s)) != OXC_OK) return fail(rc);
+  if (cudaMemcpyAsync(overdraw_host, d_overdraw_, px * 4, cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess)
+    return fail(OXC_E_CUDA);
+  return OXC_OK;
 }
 
 // the reference uploads its material table with the scene (RendererInstance.cpp:1333-1788); the vis-buffer encode reads it for
@@ -527,6 +545,11 @@ int oxr_update(OxrRenderer* r, const OxcSceneDesc* scene) {
 int oxr_update_transforms(OxrRenderer* r, const OxcTransformWorld* transforms, uint32_t first, uint32_t count) {
   if (!r || !transforms) return OXC_E_INVALID;
   return r->impl.update_transforms(transforms, first, count);
+}
+
+int oxr_overdraw(OxrRenderer* r, const OxcCullCamera* camera, uint32_t* overdraw_host) {
+  if (!r || !camera) return OXC_E_INVALID;
+  return r->impl.overdraw(*camera, overdraw_host);
 }
 
 int oxr_set_materials(OxrRenderer* r, const OxcMaterialTable* table) {

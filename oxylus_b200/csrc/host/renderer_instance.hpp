@@ -59,6 +59,7 @@ public:
   auto update_transforms(const OxcTransformWorld* transforms, uint32_t first, uint32_t count) -> int;
   // depth laid down by passes outside this path (terrain): kept on the device until replaced; nullptr clears it
   auto set_materials(const OxcMaterialTable* table) -> int; // nullptr: plain encode
+  auto overdraw(const OxcCullCamera& camera, uint32_t* overdraw_host) -> int; // fragment counter of the last rendered frame
   auto set_external_depth(const float* depth_host) -> int;
   auto cull_geometry(CullGeometryContext& context) -> int;
   auto generate_hiz(MainGeometryContext& context) -> int;
@@ -128,6 +129,7 @@ private:
   uint32_t* d_vis32_ = nullptr;
   float* d_depth_ = nullptr;
   float* d_occluder_ = nullptr;
+  uint32_t* d_overdraw_ = nullptr; // allocated by the first overdraw()
   bool has_external_depth_ = false;
   void* h_pinned_ = nullptr; // staging for small readbacks
   std::string error_;

@@ -22,6 +22,7 @@ struct AlphaParams {
   OxcDispatchIndirectCommand* opaque_cmd; // .x = entries of opaque_list (zeroed before the launch)
   OxcDispatchIndirectCommand* masked_cmd;
   uint32_t* overdraw;                     // k_raster_alpha<true>: the W x H fragment counter (RENDER_OVERDRAW)
+  uint32_t count_from_visibility;         // k_raster_alpha<true> after the frame: the pass's count from the visibility record
 };
 
 OXC_DI bool alpha_material_of(const AlphaParams& a, const TriParams& p, uint32_t gid, uint32_t id_base, uint32_t& mat) {
@@ -113,7 +114,11 @@ __global__ void __launch_bounds__(ALPHA_THREADS) k_raster_alpha(const __grid_con
   __shared__ AlphaBigRecord big_all[ALPHA_WARPS];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t first = OVERDRAW ? (p.late ? p.vis->early_visible_meshlet_instances : 0u) : 0u; // cull_triangles.slang:34-37
-  const uint32_t count = OVERDRAW ? p.tri_cmd->x : a.masked_cmd->x;
+  // the dispatch command holds the count of the pass that ran LAST; a counter pass issued after the frame takes it from the
+  // visibility record instead (early [0, E), late [E, E + L): cull_meshlets_hiz.slang:70-76)
+  const uint32_t count = !OVERDRAW ? a.masked_cmd->x
+                         : !a.count_from_visibility ? p.tri_cmd->x
+                         : (p.late ? p.vis->late_visible_meshlet_instances : p.vis->early_visible_meshlet_instances);
   const uint32_t id_base = p.id_base ? __ldg(p.id_base) : 0u;
   float4* clip_s = clip_all[warp];
   float2* uv_s = uv_all[warp];

@@ -782,7 +782,8 @@ int oxc_raster_visbuffer(OxcContext* c, const OxcCullCamera* cam, uint32_t flags
 
 // RENDER_OVERDRAW of the encode pass (visbuffer_encode.slang:15,68-70; MainGeometryContext::draw_overdraw): a separate launch of the
 // general per-meshlet raster with the fragment counter as its sink — the tuned raster kernels know nothing about it
-int oxc_raster_overdraw(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t w, uint32_t h, uint32_t* overdraw, void* stream) {
+int oxc_raster_overdraw(OxcContext* c, const OxcCullCamera* cam, uint32_t flags, uint32_t w, uint32_t h, uint32_t* overdraw, int after_frame,
+                        void* stream) {
   if (!c || !cam || !overdraw) return fail(OXC_E_INVALID, "null argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaSetDevice(c->device));
@@ -791,7 +792,7 @@ int oxc_raster_overdraw(OxcContext* c, const OxcCullCamera* cam, uint32_t flags,
   if (rc != OXC_OK) return rc;
   p.width = w; p.height = h; p.f_width = (float)w; p.f_height = (float)h;
   AlphaParams ap{};
-  ap.mesh_instances = c->d_mesh_instances; ap.overdraw = overdraw;
+  ap.mesh_instances = c->d_mesh_instances; ap.overdraw = overdraw; ap.count_from_visibility = after_frame ? 1u : 0u;
   if (c->alpha_active) { ap.materials = c->d_alpha_materials; ap.material_count = c->alpha_material_count; }
   k_raster_alpha<true><<<c->sm_count * 8, ALPHA_THREADS, 0, s>>>(p, ap);
   LAUNCHED();

@@ -1645,6 +1645,11 @@ def test_overdraw_counter_parity(capi, orc):
             ctx.raster_visbuffer(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, vis_dev)
             ctx.raster_overdraw(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, over_dev)
             np.testing.assert_array_equal(ctx.download(over_dev, np.uint32, w * h).reshape(h, w), want, err_msg=f"table {with_table} frame {f}")
+            # the same counter issued after the frame (the dispatch command now holds the late count: ranges from the visibility record)
+            ctx.clear_overdraw(over_dev, w, h)
+            ctx.raster_overdraw(cam, abi.CULL_TEST_ALL, w, h, over_dev, after_frame=True)
+            ctx.raster_overdraw(cam, abi.CULL_TEST_ALL | abi.CULL_LATE_PASS, w, h, over_dev, after_frame=True)
+            np.testing.assert_array_equal(ctx.download(over_dev, np.uint32, w * h).reshape(h, w), want, err_msg=f"after frame, table {with_table} frame {f}")
             np.testing.assert_array_equal(ctx.download(vis_dev, np.uint64, w * h).reshape(h, w), ref["vis64"])
             np.testing.assert_array_equal(ctx.mask(), mask_ref)
             assert ctx.raster_triangle_count() == ref["ntri_early"] + ref["ntri_late"] and ctx.check_status() == 0
@@ -1652,6 +1657,21 @@ def test_overdraw_counter_parity(capi, orc):
         for d in ptrs + [vis_dev, occ_dev, over_dev]:
             ctx.free(d)
         ctx.close()
+    # the host mirror: oxr_overdraw after a rendered frame == the oracle's counter over that frame's two passes
+    sc = synth.make_scene(config_index=2, **SCENES["small"])
+    hs = orc.HostScene(sc)
+    r = capi.Renderer(0, sc)
+    mask_ref = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
+    for f in range(2):
+        cam = sc.camera(3.0 * f)
+        ref = orc.frame(hs, cam, sc.width, sc.height, mask_ref, sc.occluder_depth)
+        got = r.render(cam, sc.occluder_depth)
+        assert (got["early"], got["late"]) == (ref["early"], ref["late"])
+        want = np.zeros((sc.height, sc.width), dtype=np.uint32)
+        orc.raster_overdraw(hs, ref["meshlet_instances"], ref["visible"], 0, ref["early"], cam, want)
+        orc.raster_overdraw(hs, ref["meshlet_instances"], ref["visible"], ref["early"], ref["late"], cam, want)
+        np.testing.assert_array_equal(r.overdraw(cam), want)
+    r.close()
     # clipped, screen-filling triangles (whole-warp path) with a checker material
     sc = textured_ground(1, width=640, height=360)
     sc.mesh_instances["material_index"] = 0
