@@ -92,19 +92,42 @@ def hostile_cameras(sc):
     return out
 
 
-def frames_equal(sc, frames=2, cams=None, occluder_depth=None):
+def alpha_table():
+    """four materials over mip-mapped / single-level images with every filter, mipmap and address mode between them (oracle table)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from test_oracle_alpha import checker, material
+
+    rng = np.random.default_rng(77)
+    images = [(orc.mip_chain(checker(32, 4)), abi.IMAGE_RGBA8_UNORM), (orc.mip_chain(rng.integers(0, 256, (16, 8), dtype=np.uint8)), abi.IMAGE_R8_UNORM),
+              (rng.integers(0, 256, (4, 4), dtype=np.uint8), abi.IMAGE_R8_UNORM)]
+    mats = np.array([material(), material(image=0, cutoff=0.5), material(image=1, cutoff=0.4, albedo_a=0.9, sampler=1), material(image=2, cutoff=0.5, sampler=2)],
+                    dtype=abi.MATERIAL_DT)
+    smp = np.array([abi.sampler(), abi.sampler(mip=abi.MIPMAP_NEAREST, u=abi.ADDRESS_MIRRORED_REPEAT, v=abi.ADDRESS_CLAMP_TO_EDGE),
+                    abi.sampler(mag=abi.FILTER_NEAREST, min=abi.FILTER_LINEAR)], dtype=abi.SAMPLER_DT)
+    return orc.MaterialTable(mats, images, smp), mats, smp
+
+
+def frames_equal(sc, frames=2, cams=None, occluder_depth=None, alpha=False):
+    if alpha:  # every fourth mesh instance opaque, the others alpha tested (visbuffer_encode.slang:54-66)
+        sc = copy.deepcopy(sc)
+        sc.mesh_instances["material_index"] = np.arange(sc.mesh_instance_count) % 4
     hs = orc.HostScene(sc)
     w, h = sc.width, sc.height
     hw, hh = sc.hiz_extent()
     ctx = capi.Context(0, sc.mesh_instance_count, sc.max_meshlet_instance_count, hw, hh)
     ctx.set_scene(sc)
+    tab = None
+    if alpha:
+        tab, mats, smp = alpha_table()
+        dev, _ = tab.device_images(ctx)
+        ctx.set_materials(mats, dev, smp)
     vis, occ = ctx.alloc(w * h * 8), ctx.alloc(w * h * 4)
     depth = sc.occluder_depth if occluder_depth is None else occluder_depth
     ctx.upload(occ, depth)
     mask = np.zeros((sc.max_meshlet_instance_count + 31) // 32, dtype=np.uint32)
     ok = True
     for cam in (cams if cams is not None else [sc.camera(3.0 * f) for f in range(frames)]):
-        ref = orc.frame(hs, cam, w, h, mask, depth)
+        ref = orc.frame(hs, cam, w, h, mask, depth, materials=tab)
         ctx.clear_visbuffer_with_depth(vis, occ, w, h)
         ctx.clear_hiz()
         ctx.cull_meshes(cam, abi.CULL_TEST_ALL)
@@ -134,13 +157,21 @@ def main():
                 bad.append((seed, mode))
     if not frames_equal(base, cams=hostile_cameras(base)):
         bad.append("cameras")
+    # the same hostility with a material table set: NaN / Inf uv, positions and cameras reach the interpolation, the level selection
+    # and the texel addressing of the alpha test
+    for seed in range(seeds):
+        if not frames_equal(mutate(base, np.random.default_rng(seed * 10 + 1), "all"), alpha=True):
+            bad.append((seed, "all + alpha"))
+    if not frames_equal(base, cams=hostile_cameras(base), alpha=True):
+        bad.append("cameras + alpha")
     depth = base.occluder_depth.copy()
     rng = np.random.default_rng(3)
     sel = rng.random(depth.shape) < 0.01
     depth[sel] = rng.choice(np.array([np.nan, np.inf, -np.inf, -1.0, 2.0, 1e-45, -0.0], dtype=np.float32), int(sel.sum()))
     if not frames_equal(base, occluder_depth=depth):
         bad.append("external depth")
-    print(f"{seeds * 5} hostile scenes x 2 frames, 10 hostile cameras, hostile external depth: {'ok' if not bad else 'MISMATCH ' + repr(bad)}")
+    print(f"{seeds * 5} hostile scenes x 2 frames, 10 hostile cameras, {seeds} hostile scenes + 10 hostile cameras with a material table, hostile external depth: "
+          f"{'ok' if not bad else 'MISMATCH ' + repr(bad)}")
     sys.exit(1 if bad else 0)
 
 
